@@ -1,0 +1,222 @@
+/*
+ * stencils_b200.h — C ABI of libstencils_b200.so
+ *
+ * Drop-in boundary for the per-cell sweep of rafaqz/Stencils.jl (reference v0.3.6).
+ * Every entry point replaces one mutating Julia entry point of the reference; the
+ * allocating wrappers (`gatherstencil`/`mapstencil`) stay on the host side (Julia shim
+ * `julia/StencilsB200.jl`, Python mirror `stencils.jl_b200/`).
+ *
+ *   sb200_gather       <- gatherstencil!(f, dest, source, args...)      src/gatherstencil.jl:89-103
+ *                         + gatherstencil_kernel!                        src/gatherstencil.jl:105-109
+ *                         + stencil/neighbors/getneighbor/bounded_index  src/array.jl:22-30,68-188
+ *   sb200_update_halo  <- update_boundary!(A)                            src/array.jl:195-239
+ *   sb200_scatter      <- scatterstencil!(f, op, dest, source)           src/scatterstencil.jl:36-112
+ *   sb200_iterate      <- loop of gatherstencil!(f, A::SwitchingStencilArray) + switch(A)
+ *                                                                        src/gatherstencil.jl:77-83, src/array.jl:610-611
+ *   sb200_stencil_offsets <- offsets(::Type{<:Stencil})                  src/stencils/{*}.jl
+ *   sb200_out_eltype   <- _return_type                                   src/gatherstencil.jl:41-59
+ *
+ * Conventions
+ *   - Arrays are Julia column-major: axis 0 here is Julia dim 1 (contiguous). Offsets are
+ *     (o0,o1,o2) with o0 along the contiguous axis. Indices in this ABI are 0-based.
+ *   - All data pointers are DEVICE pointers unless the name ends in `_host`.
+ *   - Calls are stream-ordered and non-blocking; the caller keeps every buffer alive until
+ *     the stream has drained. `stream` is a cudaStream_t passed as void* (NULL = default stream).
+ *   - No exceptions cross the ABI. Every function returns an sb200_status; the thread-local
+ *     message is read with sb200_last_error().
+ *   - An unsupported reducer / eltype / combination returns SB200_EUNSUPPORTED. There is no
+ *     CPU fallback anywhere in this library.
+ */
+#ifndef STENCILS_B200_H
+#define STENCILS_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SB200_VERSION 100 /* 0.1.0 */
+#define SB200_MAX_DIMS 3
+#define SB200_MAX_OFFSETS 1024
+
+typedef enum sb200_status {
+    SB200_OK = 0,
+    SB200_EINVAL = 1,       /* malformed descriptor / NULL pointer */
+    SB200_EUNSUPPORTED = 2, /* reducer/eltype/shape not implemented: shim raises ArgumentError */
+    SB200_ESIZE = 3,        /* _checksizes (src/gatherstencil.jl:118-124), radius-vs-axis (src/array.jl:451-453) */
+    SB200_ECUDA = 4,        /* CUDA runtime/driver error, message holds cudaGetErrorString */
+    SB200_ENOMEM = 5
+} sb200_status;
+
+/* Element types (Julia names). Bool is one byte holding 0/1. */
+typedef enum sb200_eltype {
+    SB200_BOOL = 0,
+    SB200_U8 = 1,
+    SB200_I32 = 2,
+    SB200_I64 = 3,
+    SB200_F32 = 4,
+    SB200_F64 = 5
+} sb200_eltype;
+
+/* Boundary conditions, src/boundary.jl:17,27-32,42,52 */
+typedef enum sb200_boundary {
+    SB200_REMOVE = 0, /* out-of-bounds neighbours read `padval` */
+    SB200_WRAP = 1,   /* single wrap: i<0 -> i+s, i>=s -> i-s   (src/array.jl:167-179) */
+    SB200_REFLECT = 2,/* mirror without repeating the edge       (src/array.jl:154-166) */
+    SB200_USE = 3     /* read the existing halo ring as it is (needs src_off >= radius) */
+} sb200_boundary;
+
+/* Named stencil shapes, src/stencils/{window,moore,vonneumman,shapes}.jl */
+typedef enum sb200_shape {
+    SB200_WINDOW = 0,
+    SB200_MOORE = 1,
+    SB200_VONNEUMANN = 2,
+    SB200_CROSS = 3,
+    SB200_ANGLEDCROSS = 4,
+    SB200_FORWARDSLASH = 5,
+    SB200_BACKSLASH = 6,
+    SB200_CIRCLE = 7,
+    SB200_VERTICAL = 8,
+    SB200_HORIZONTAL = 9,
+    SB200_DIAMOND = 10,
+    SB200_ANNULUS = 11, /* uses inner_radius */
+    SB200_CARDINAL = 12,
+    SB200_ORDINAL = 13
+    /* Positional / NamedStencil / Rectangle pass their offset table directly. */
+} sb200_shape;
+
+/* The function `f` applied to the filled stencil (fixed menu; anything else is unsupported). */
+typedef enum sb200_reducer {
+    SB200_SUM = 0,       /* sum(hood): strict left fold in offset order, seeded by the first value */
+    SB200_MEAN = 1,      /* sum(hood) / L */
+    SB200_MIN = 2,       /* minimum(hood): Julia min (NaN-propagating, -0.0 < +0.0) */
+    SB200_MAX = 3,       /* maximum(hood) */
+    SB200_KERNELDOT = 4, /* kernelproduct, src/stencils/kernel.jl:34-43: acc=0; acc += v_k*w_k, unfused */
+    SB200_LIFE = 5,      /* s = sum of (neighbour != 0); out = ((centre!=0 ? survive : born) >> s) & 1 */
+    SB200_DIFFUSION = 6  /* centre + alpha*(sum(hood) - L*centre), every operation rounded separately */
+} sb200_reducer;
+
+/* `op` of scatterstencil!, src/scatterstencil.jl:76-112 */
+typedef enum sb200_scatter_op { SB200_OP_ADD = 0, SB200_OP_MAX = 1, SB200_OP_MIN = 2 } sb200_scatter_op;
+
+/* Fixed menu for the user function of scatterstencil! (value sent to offset k). */
+typedef enum sb200_scatter_rule {
+    SB200_SCATTER_WEIGHTS = 0,        /* val_k = w_k                 (test/array.jl:391-393) */
+    SB200_SCATTER_CENTER_WEIGHTS = 1  /* val_k = centre * w_k        (test/array.jl:412-415 with w=1) */
+} sb200_scatter_rule;
+
+/*
+ * Sweep descriptor. Plain data, filled by the host shim from a StencilArray
+ * (src/array.jl:441-468): parent array, stencil, boundary, padding.
+ *
+ * Per axis a (0 = contiguous):
+ *   size[a]     logical size of the StencilArray (`size(A)`, src/array.jl:379,470-473)
+ *   src_ext[a]  extent of the source parent array            (= size + 2R for Halo padding)
+ *   src_off[a]  parent index of logical index 0              (= R for Halo: add_halo, src/array.jl:367-377; else 0)
+ *   dst_ext/dst_off the same for the destination (plain dest array: ext=size, off=0;
+ *               Switching+Halo dest: the padded twin buffer, src/gatherstencil.jl:77-83)
+ *   boundary[a] boundary condition on this axis. The reference has one condition for all axes;
+ *               the per-axis form is what the slab decomposition needs (ghost planes = USE on the
+ *               split axis). An axis with src_off>0 is read straight through its ring (Halo
+ *               semantics, src/array.jl:91-99); an axis with src_off==0 resolves out-of-bounds
+ *               neighbours on the fly (Conditional semantics, src/array.jl:101-138).
+ */
+typedef struct sb200_desc {
+    int32_t struct_size; /* = sizeof(sb200_desc) */
+    int32_t ndim;        /* array dimensionality 1..3 */
+    int64_t size[SB200_MAX_DIMS];
+    int64_t src_ext[SB200_MAX_DIMS];
+    int64_t dst_ext[SB200_MAX_DIMS];
+    int32_t src_off[SB200_MAX_DIMS];
+    int32_t dst_off[SB200_MAX_DIMS];
+    int32_t boundary[SB200_MAX_DIMS];
+    int32_t eltype;      /* sb200_eltype of the source */
+    int32_t out_eltype;  /* sb200_eltype of the destination; must equal sb200_out_eltype() */
+    uint64_t padval_bits;/* Remove(padval): raw bits of one `eltype` value in the low bytes */
+    int32_t radius;      /* stencil radius R = max |offset| */
+    int32_t noffsets;    /* L */
+    const int32_t* offsets_host; /* [L][3] ordered offset table (host memory), unused axes = 0 */
+    int32_t reducer;     /* sb200_reducer */
+    int32_t scatter_op;  /* sb200_scatter_op   (sb200_scatter only) */
+    int32_t scatter_rule;/* sb200_scatter_rule (sb200_scatter only) */
+    uint32_t born_mask;  /* LIFE: bit s set -> dead cell with s live neighbours is born   (B3 = 1<<3) */
+    uint32_t survive_mask;/* LIFE: bit s set -> live cell with s live neighbours survives (S23 = 0b1100) */
+    int32_t reserved0;
+    const void* weights_host; /* KERNELDOT / scatter: L values of `eltype` (host memory) */
+    double alpha;        /* DIFFUSION coefficient, converted to `eltype` before use */
+    /* Output sub-range [region_lo, region_hi) in logical coordinates; all-zero = whole array.
+       Used for boundary-first / interior overlap in the slab iterator and for chunked host sweeps. */
+    int64_t region_lo[SB200_MAX_DIMS];
+    int64_t region_hi[SB200_MAX_DIMS];
+    int32_t flags;       /* SB200_FLAG_* */
+    int32_t reserved1;
+} sb200_desc;
+
+#define SB200_FLAG_FORCE_GENERIC 1 /* bypass specialised kernels (testing: generic vs fast parity) */
+#define SB200_FLAG_ZERO_DEST 2     /* scatter: treat dest as zero-filled (Switching forms, src/scatterstencil.jl:119,130) */
+#define SB200_FLAG_NO_TMA 4        /* testing: use the non-TMA variant of a specialised kernel */
+
+/* ---- library ---- */
+int32_t sb200_version(void);
+/* Thread-local message of the last failing call on this thread ("" if none). */
+const char* sb200_last_error(void);
+/* Name of the kernel variant the last successful sweep on this thread dispatched to (diagnostics). */
+const char* sb200_last_kernel(void);
+/* Number of kernel launches issued by this library on this thread since the last reset. */
+int64_t sb200_launch_count(int32_t reset);
+
+/* ---- stencil algebra (host only) ---- */
+/* Ordered offsets of a named shape: box (-R:R)^ndim iterated with axis 0 fastest, filtered by the shape
+   predicate (src/stencils/{*}.jl). Writes up to cap triples; *count receives L. */
+int32_t sb200_stencil_offsets(int32_t shape, int32_t radius, int32_t inner_radius, int32_t ndim,
+                              int32_t* out, int32_t cap, int32_t* count);
+/* Result element type of reducer applied to a stencil of `eltype` (src/gatherstencil.jl:41-59). */
+int32_t sb200_out_eltype(int32_t reducer, int32_t eltype, int32_t* out);
+size_t sb200_sizeof(int32_t eltype);
+
+/* ---- sweeps (device pointers) ---- */
+int32_t sb200_gather(const sb200_desc* d, const void* src_parent, void* dst_parent, void* stream);
+int32_t sb200_update_halo(const sb200_desc* d, void* src_parent, void* stream);
+int32_t sb200_scatter(const sb200_desc* d, const void* src_parent, void* dst_parent, void* stream);
+/* nsteps x { update_halo(src) if the source has a ring and boundary != USE; gather(src->dst); swap }.
+   buf_a holds the state on entry; the final state is in buf_a if nsteps is even, else buf_b. */
+int32_t sb200_iterate(const sb200_desc* d, void* buf_a, void* buf_b, int32_t nsteps, void* stream);
+
+/* ---- host-buffer entry points (what a StencilArray over a CPU Array lowers to) ---- */
+/* H2D(src) -> [update_halo] -> gather -> D2H(dst), pipelined over row chunks on internal streams; blocking. */
+int32_t sb200_gather_host(const sb200_desc* d, const void* src_parent_host, void* dst_parent_host);
+/* H2D once, nsteps sweeps resident in HBM, D2H once; blocking. state_host is the source parent on
+   entry and receives the final source parent (SwitchingStencilArray loop). */
+int32_t sb200_iterate_host(const sb200_desc* d, void* state_parent_host, int32_t nsteps);
+
+/* ---- device memory helpers so a shim needs no CUDA binding of its own ---- */
+int32_t sb200_device_count(int32_t* n);
+int32_t sb200_set_device(int32_t dev);
+int32_t sb200_malloc(void** p, size_t bytes);
+int32_t sb200_free(void* p);
+int32_t sb200_malloc_host(void** p, size_t bytes); /* pinned */
+int32_t sb200_free_host(void* p);
+int32_t sb200_memcpy_h2d(void* dst, const void* src_host, size_t bytes, void* stream);
+int32_t sb200_memcpy_d2h(void* dst_host, const void* src, size_t bytes, void* stream);
+int32_t sb200_memcpy_d2d(void* dst, const void* src, size_t bytes, void* stream);
+int32_t sb200_memset(void* p, int32_t byte, size_t bytes, void* stream);
+int32_t sb200_stream_sync(void* stream);
+
+/* ---- peer-memory ghost exchange for slab-partitioned iterated runs (one process per GPU) ---- */
+/* Export / import a CUDA IPC handle (64 bytes) for a buffer allocated with sb200_malloc. */
+int32_t sb200_ipc_export(void* p, void* handle64);
+int32_t sb200_ipc_import(const void* handle64, void** p);
+int32_t sb200_ipc_close(void* p);
+/* Copy `nplanes` trailing-axis planes of my buffer into a peer's buffer (P2P store over NVLink),
+   then publish `value` to a flag word in the peer's memory with system-scope release semantics. */
+int32_t sb200_push_planes(const void* src, void* peer_dst, size_t bytes, uint32_t* peer_flag, uint32_t value,
+                          void* stream);
+/* Stream-ordered wait until *flag >= value (acquire). */
+int32_t sb200_wait_flag(const uint32_t* flag, uint32_t value, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STENCILS_B200_H */

@@ -1,0 +1,124 @@
+"""ctypes view of include/stencils_b200.h: enums, the sweep descriptor and the library loader.
+
+The product path loads `lib/libstencils_b200.so` (hand-written sm_100a kernels behind a C ABI) and
+fails loudly when it is missing — there is no CPU or PyTorch fallback (BASELINE.json north_star).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "libstencils_b200.so")
+
+# ---- enums (include/stencils_b200.h) ----
+OK, EINVAL, EUNSUPPORTED, ESIZE, ECUDA, ENOMEM = range(6)
+BOOL, U8, I32, I64, F32, F64 = range(6)
+REMOVE, WRAP, REFLECT, USE = range(4)
+(WINDOW, MOORE, VONNEUMANN, CROSS, ANGLEDCROSS, FORWARDSLASH, BACKSLASH, CIRCLE, VERTICAL, HORIZONTAL,
+ DIAMOND, ANNULUS, CARDINAL, ORDINAL) = range(14)
+SUM, MEAN, MIN, MAX, KERNELDOT, LIFE, DIFFUSION = range(7)
+OP_ADD, OP_MAX, OP_MIN = range(3)
+SCATTER_WEIGHTS, SCATTER_CENTER_WEIGHTS = range(2)
+FLAG_FORCE_GENERIC, FLAG_ZERO_DEST, FLAG_NO_TMA = 1, 2, 4
+MAX_OFFSETS = 1024
+
+ELTYPE_OF_DTYPE = {
+    np.dtype(np.bool_): BOOL, np.dtype(np.uint8): U8, np.dtype(np.int32): I32,
+    np.dtype(np.int64): I64, np.dtype(np.float32): F32, np.dtype(np.float64): F64,
+}
+DTYPE_OF_ELTYPE = {v: k for k, v in ELTYPE_OF_DTYPE.items()}
+
+
+class Desc(C.Structure):
+    """struct sb200_desc"""
+    _fields_ = [
+        ("struct_size", C.c_int32), ("ndim", C.c_int32),
+        ("size", C.c_int64 * 3), ("src_ext", C.c_int64 * 3), ("dst_ext", C.c_int64 * 3),
+        ("src_off", C.c_int32 * 3), ("dst_off", C.c_int32 * 3), ("boundary", C.c_int32 * 3),
+        ("eltype", C.c_int32), ("out_eltype", C.c_int32),
+        ("padval_bits", C.c_uint64),
+        ("radius", C.c_int32), ("noffsets", C.c_int32),
+        ("offsets_host", C.c_void_p),
+        ("reducer", C.c_int32), ("scatter_op", C.c_int32), ("scatter_rule", C.c_int32),
+        ("born_mask", C.c_uint32), ("survive_mask", C.c_uint32), ("reserved0", C.c_int32),
+        ("weights_host", C.c_void_p),
+        ("alpha", C.c_double),
+        ("region_lo", C.c_int64 * 3), ("region_hi", C.c_int64 * 3),
+        ("flags", C.c_int32), ("reserved1", C.c_int32),
+    ]
+
+
+class SB200Error(RuntimeError):
+    def __init__(self, status: int, msg: str):
+        super().__init__(f"libstencils_b200 status {status}: {msg}")
+        self.status = status
+
+
+class ArgumentError(ValueError):
+    """Julia's ArgumentError: unsupported user function / eltype / shape, size mismatch."""
+
+
+_lib = None
+
+_SIGS = {
+    "sb200_version": (C.c_int32, []),
+    "sb200_last_error": (C.c_char_p, []),
+    "sb200_last_kernel": (C.c_char_p, []),
+    "sb200_launch_count": (C.c_int64, [C.c_int32]),
+    "sb200_stencil_offsets": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32,
+                                          C.POINTER(C.c_int32)]),
+    "sb200_out_eltype": (C.c_int32, [C.c_int32, C.c_int32, C.POINTER(C.c_int32)]),
+    "sb200_sizeof": (C.c_size_t, [C.c_int32]),
+    "sb200_gather": (C.c_int32, [C.POINTER(Desc), C.c_void_p, C.c_void_p, C.c_void_p]),
+    "sb200_update_halo": (C.c_int32, [C.POINTER(Desc), C.c_void_p, C.c_void_p]),
+    "sb200_scatter": (C.c_int32, [C.POINTER(Desc), C.c_void_p, C.c_void_p, C.c_void_p]),
+    "sb200_iterate": (C.c_int32, [C.POINTER(Desc), C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
+    "sb200_gather_host": (C.c_int32, [C.POINTER(Desc), C.c_void_p, C.c_void_p]),
+    "sb200_iterate_host": (C.c_int32, [C.POINTER(Desc), C.c_void_p, C.c_int32]),
+    "sb200_device_count": (C.c_int32, [C.POINTER(C.c_int32)]),
+    "sb200_set_device": (C.c_int32, [C.c_int32]),
+    "sb200_malloc": (C.c_int32, [C.POINTER(C.c_void_p), C.c_size_t]),
+    "sb200_free": (C.c_int32, [C.c_void_p]),
+    "sb200_malloc_host": (C.c_int32, [C.POINTER(C.c_void_p), C.c_size_t]),
+    "sb200_free_host": (C.c_int32, [C.c_void_p]),
+    "sb200_memcpy_h2d": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "sb200_memcpy_d2h": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "sb200_memcpy_d2d": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "sb200_memset": (C.c_int32, [C.c_void_p, C.c_int32, C.c_size_t, C.c_void_p]),
+    "sb200_stream_sync": (C.c_int32, [C.c_void_p]),
+    "sb200_ipc_export": (C.c_int32, [C.c_void_p, C.c_void_p]),
+    "sb200_ipc_import": (C.c_int32, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "sb200_ipc_close": (C.c_int32, [C.c_void_p]),
+    "sb200_push_planes": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_uint32, C.c_void_p]),
+    "sb200_wait_flag": (C.c_int32, [C.c_void_p, C.c_uint32, C.c_void_p]),
+}
+EXPORTED_SYMBOLS = tuple(_SIGS)
+
+
+def lib() -> C.CDLL:
+    """Load libstencils_b200.so (built in-tree by __graft_entry__.build() / csrc/build.py)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a). There is no CPU fallback for the stencil sweep.")
+        l = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(l, name)  # AttributeError here = header/library mismatch
+            fn.restype = res
+            fn.argtypes = args
+        _lib = l
+    return _lib
+
+
+def check(status: int) -> None:
+    if status == OK:
+        return
+    msg = lib().sb200_last_error().decode("utf-8", "replace")
+    if status in (EUNSUPPORTED, ESIZE, EINVAL):
+        raise ArgumentError(f"[sb200 status {status}] {msg}")
+    raise SB200Error(status, msg)
