@@ -1,0 +1,601 @@
+// api.cu — the extern "C" surface of libstencils_b200.so (include/stencils_b200.h): validation, the plan
+// cache (device copies of offset/weight tables + dispatch), host-buffer entry points and memory helpers.
+#include <algorithm>
+#include <array>
+#include <cstdarg>
+#include <cmath>
+#include <mutex>
+#include <unordered_map>
+#include <vector>
+#include "common.cuh"
+
+namespace sb {
+
+static thread_local char g_err[512] = "";
+static thread_local char g_kernel[96] = "";
+static thread_local long long g_launches = 0;
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+void set_kernel_name(const char* name) { snprintf(g_kernel, sizeof(g_kernel), "%s", name); }
+void count_launch(int n) { g_launches += n; }
+
+int num_sms() {
+    static thread_local int cached_dev = -1, cached = 0;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (dev != cached_dev) {
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return 148;
+        cached = prop.multiProcessorCount;
+        cached_dev = dev;
+    }
+    return cached;
+}
+
+// ------------------------------------------------------------------------------------------------ shapes
+// Shape predicates over the box (-R:R)^N iterated with axis 0 fastest (src/stencils/window.jl:4-8,
+// moore.jl:5-18, vonneumman.jl:5-15, shapes.jl:2-175).
+static int shape_keep(int shape, int R, int RI, int N, const int* t) {
+    int manh = 0, maxabs = 0, zeros = 0, sq = 0;
+    for (int a = 0; a < N; a++) {
+        const int v = std::abs(t[a]);
+        manh += v;
+        maxabs = std::max(maxabs, v);
+        zeros += t[a] == 0;
+        sq += t[a] * t[a];
+    }
+    auto count_tail = [&](auto pred) { int m = 0; for (int a = 1; a < N; a++) m += pred(t[a]) ? 1 : 0; return m; };
+    switch (shape) {
+    case SB200_WINDOW: return 1;
+    case SB200_MOORE: return manh != 0;
+    case SB200_VONNEUMANN: return manh >= 1 && manh <= R;
+    case SB200_CROSS: return zeros >= N - 1;
+    case SB200_ANGLEDCROSS: return count_tail([&](int x) { return std::abs(x) == std::abs(t[0]); }) == N - 1;
+    case SB200_FORWARDSLASH: return count_tail([&](int x) { return x == -t[0]; }) == N - 1;
+    case SB200_BACKSLASH: return count_tail([&](int x) { return x == t[0]; }) == N - 1;
+    case SB200_CIRCLE: return std::sqrt((double)sq) < R + 0.5;
+    case SB200_VERTICAL: return (N > 1 && t[1] == 0) || (N == 1 && t[0] == 0);
+    case SB200_HORIZONTAL: return N > 1 && t[0] == 0;
+    case SB200_DIAMOND: return manh <= R;
+    case SB200_ANNULUS: { const double dist = std::sqrt((double)sq); return dist < R + 0.5 && dist >= RI + 0.5; }
+    case SB200_CARDINAL: return manh == R && maxabs == R;
+    case SB200_ORDINAL: return manh == R * N && maxabs == R;
+    default: return -1;
+    }
+}
+
+static int gen_offsets(int shape, int R, int RI, int N, std::vector<int>& out) {
+    out.clear();
+    const int D = 2 * R + 1;
+    long long total = 1;
+    for (int a = 0; a < N; a++) total *= D;
+    for (long long lin = 0; lin < total; lin++) {
+        int t[3] = {0, 0, 0};
+        long long rem = lin;
+        for (int a = 0; a < N; a++) { t[a] = (int)(rem % D) - R; rem /= D; }
+        const int keep = shape_keep(shape, R, RI, N, t);
+        if (keep < 0) return SB200_EUNSUPPORTED;
+        if (keep) { out.push_back(t[0]); out.push_back(t[1]); out.push_back(t[2]); }
+    }
+    return SB200_OK;
+}
+
+static int out_eltype_of(int reducer, int eltype, int* out) {
+    if (eltype < SB200_BOOL || eltype > SB200_F64) { set_error("unknown eltype %d", eltype); return SB200_EUNSUPPORTED; }
+    const bool isf = eltype == SB200_F32 || eltype == SB200_F64;
+    switch (reducer) {
+    case SB200_SUM: *out = eltype == SB200_BOOL ? SB200_I64 : eltype; return SB200_OK;
+    case SB200_MEAN: *out = isf ? eltype : SB200_F64; return SB200_OK;
+    case SB200_MIN: case SB200_MAX: case SB200_LIFE: *out = eltype; return SB200_OK;
+    case SB200_KERNELDOT:
+        if (eltype == SB200_BOOL || eltype == SB200_U8) { set_error("kernelproduct needs Int32/Int64/Float32/Float64"); return SB200_EUNSUPPORTED; }
+        *out = eltype; return SB200_OK;
+    case SB200_DIFFUSION:
+        if (!isf) { set_error("diffusion needs Float32/Float64"); return SB200_EUNSUPPORTED; }
+        *out = eltype; return SB200_OK;
+    default:
+        set_error("unsupported user function (reducer %d): only sum, mean, minimum, maximum, kernelproduct, "
+                  "Life and Diffusion lower to CUDA kernels; there is no fallback", reducer);
+        return SB200_EUNSUPPORTED;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ plans
+enum PlanKind { PK_GATHER = 0, PK_HALO = 1, PK_SCATTER = 2 };
+
+static int validate(const sb200_desc* d, int kind) {
+    if (!d) { set_error("descriptor is NULL"); return SB200_EINVAL; }
+    if (d->struct_size != (int)sizeof(sb200_desc)) { set_error("sb200_desc.struct_size %d != %zu", d->struct_size, sizeof(sb200_desc)); return SB200_EINVAL; }
+    if (d->ndim < 1 || d->ndim > 3) { set_error("ndim must be 1..3, got %d", d->ndim); return SB200_EUNSUPPORTED; }
+    if (elsize(d->eltype) == 0) { set_error("unknown eltype %d", d->eltype); return SB200_EUNSUPPORTED; }
+    if (kind != PK_HALO) {
+        if (d->noffsets < 1 || d->noffsets > SB200_MAX_OFFSETS || !d->offsets_host) { set_error("offset table missing or larger than %d", SB200_MAX_OFFSETS); return SB200_EINVAL; }
+        int maxabs = 0;
+        for (int k = 0; k < d->noffsets; k++)
+            for (int a = 0; a < 3; a++) {
+                const int o = d->offsets_host[3 * k + a];
+                if (a >= d->ndim && o != 0) { set_error("stencil has more dimensions than the array"); return SB200_EINVAL; }
+                maxabs = std::max(maxabs, std::abs(o));
+            }
+        if (d->radius < maxabs) { set_error("radius %d smaller than the largest offset %d", d->radius, maxabs); return SB200_EINVAL; }
+    }
+    if (d->radius < 0) { set_error("negative radius"); return SB200_EINVAL; }
+    for (int a = 0; a < d->ndim; a++) {
+        if (d->size[a] < 1) { set_error("empty axis %d", a); return SB200_ESIZE; }
+        if (d->src_off[a] < 0 || d->dst_off[a] < 0) { set_error("negative offset"); return SB200_EINVAL; }
+        if (d->boundary[a] < SB200_REMOVE || d->boundary[a] > SB200_USE) { set_error("unknown boundary %d", d->boundary[a]); return SB200_EUNSUPPORTED; }
+        bool used = kind == PK_HALO;
+        if (kind != PK_HALO)
+            for (int k = 0; k < d->noffsets; k++) used |= d->offsets_host[3 * k + a] != 0;
+        if (d->src_off[a] > 0) {
+            if (d->src_off[a] < d->radius && used) { set_error("halo ring %d thinner than the radius %d on axis %d", d->src_off[a], d->radius, a); return SB200_ESIZE; }
+            if (d->src_ext[a] < d->size[a] + d->src_off[a] + (used ? d->radius : 0)) { set_error("source parent too small on axis %d", a); return SB200_ESIZE; }
+            // update_boundary! reads A[bounded_index(I)] which must land inside the inner region
+            if (kind == PK_HALO && (d->boundary[a] == SB200_WRAP || d->boundary[a] == SB200_REFLECT)) {
+                const long long hi = d->src_ext[a] - d->src_off[a] - d->size[a];
+                const long long need = std::max<long long>(d->src_off[a], hi) + (d->boundary[a] == SB200_REFLECT);
+                if (need > d->size[a]) { set_error("axis %d of size %lld is smaller than its halo ring", a, (long long)d->size[a]); return SB200_ESIZE; }
+            }
+        } else {
+            if (d->boundary[a] == SB200_USE) {
+                set_error("Use boundary needs Halo padding (no getneighbor method for Use + Conditional, src/array.jl:133-138)");
+                return SB200_EUNSUPPORTED;
+            }
+            if (d->src_ext[a] != d->size[a]) { set_error("Source array sizes must match on axis %d: %lld vs %lld", a, (long long)d->src_ext[a], (long long)d->size[a]); return SB200_ESIZE; }
+            if (used && d->radius >= d->size[a]) { set_error("stencil radius is larger than array axis %lld", (long long)d->size[a]); return SB200_ESIZE; }
+        }
+        if (kind != PK_HALO && d->dst_ext[a] < d->size[a] + d->dst_off[a]) { set_error("Source array sizes must match: dest too small on axis %d", a); return SB200_ESIZE; }
+    }
+    if (kind == PK_GATHER) {
+        int want = 0;
+        const int rc = out_eltype_of(d->reducer, d->eltype, &want);
+        if (rc) return rc;
+        if (want != d->out_eltype) { set_error("out_eltype %d does not match the reducer's result type %d", d->out_eltype, want); return SB200_EINVAL; }
+        if (d->reducer == SB200_KERNELDOT && !d->weights_host) { set_error("kernelproduct needs weights"); return SB200_EINVAL; }
+        if (d->reducer == SB200_LIFE && d->noffsets > 31) { set_error("Life rule needs at most 31 neighbours"); return SB200_EUNSUPPORTED; }
+        bool has_region = false;
+        for (int a = 0; a < d->ndim; a++) has_region |= d->region_lo[a] != 0 || d->region_hi[a] != 0;
+        if (has_region)
+            for (int a = 0; a < d->ndim; a++)
+                if (d->region_lo[a] < 0 || d->region_hi[a] > d->size[a] || d->region_lo[a] > d->region_hi[a]) { set_error("bad region on axis %d", a); return SB200_EINVAL; }
+    }
+    if (kind == PK_SCATTER) {
+        if (d->ndim != 2) { set_error("scatterstencil! is 2-D only (src/scatterstencil.jl:49-51)"); return SB200_EUNSUPPORTED; }
+        if (d->out_eltype != d->eltype) { set_error("scatterstencil! needs eltype(dest) == eltype(source)"); return SB200_EINVAL; }
+        if (!d->weights_host) { set_error("scatter needs weights"); return SB200_EINVAL; }
+        if (d->eltype < SB200_I32) { set_error("scatterstencil! supports Int32/Int64/Float32/Float64"); return SB200_EUNSUPPORTED; }
+        if (d->scatter_op < SB200_OP_ADD || d->scatter_op > SB200_OP_MIN) { set_error("unsupported scatter op %d", d->scatter_op); return SB200_EUNSUPPORTED; }
+        if (d->scatter_rule < 0 || d->scatter_rule > SB200_SCATTER_CENTER_WEIGHTS) { set_error("unsupported scatter rule %d", d->scatter_rule); return SB200_EUNSUPPORTED; }
+        if (d->radius > 63 || d->size[0] >= (1LL << 24) || d->size[1] >= (1LL << 23)) { set_error("scatter: radius/size out of range"); return SB200_EUNSUPPORTED; }
+    }
+    return SB200_OK;
+}
+
+static std::mutex g_plan_mu;
+static std::unordered_map<std::string, Plan*> g_plans;
+
+static std::string plan_key(const sb200_desc* d, int kind, int dev) {
+    std::string k;
+    sb200_desc c = *d;
+    c.offsets_host = nullptr;
+    c.weights_host = nullptr;
+    k.append((const char*)&kind, sizeof(kind));
+    k.append((const char*)&dev, sizeof(dev));
+    k.append((const char*)&c, sizeof(c));
+    if (kind != PK_HALO) {
+        k.append((const char*)d->offsets_host, sizeof(int32_t) * 3 * d->noffsets);
+        if (d->weights_host) k.append((const char*)d->weights_host, elsize(d->eltype) * d->noffsets);
+    }
+    return k;
+}
+
+static int get_plan(const sb200_desc* d, int kind, Plan** out) {
+    int rc = validate(d, kind);
+    if (rc) return rc;
+    int dev = 0;
+    SB_CUDA(cudaGetDevice(&dev));
+    std::string key = plan_key(d, kind, dev);
+    std::lock_guard<std::mutex> lock(g_plan_mu);
+    auto it = g_plans.find(key);
+    if (it != g_plans.end()) { *out = it->second; return SB200_OK; }
+    if (g_plans.size() > 4096) {  // unbounded descriptors (e.g. sliding regions): drop everything
+        for (auto& kv : g_plans) {
+            cudaFree(kv.second->offs_dev); cudaFree(kv.second->weights_dev); cudaFree(kv.second->scatter_order_dev);
+            delete kv.second;
+        }
+        g_plans.clear();
+    }
+    Plan* pl = new Plan();
+    pl->d = *d;
+    pl->key = key;
+    DevDesc& p = pl->dd;
+    memset(&p, 0, sizeof(p));
+    p.ndim = d->ndim; p.L = d->noffsets; p.R = d->radius; p.reducer = d->reducer;
+    long long ss = 1, ds = 1;
+    bool has_region = false;
+    for (int a = 0; a < d->ndim; a++) has_region |= d->region_lo[a] != 0 || d->region_hi[a] != 0;
+    for (int a = 0; a < 3; a++) {
+        const bool in = a < d->ndim;
+        p.size[a] = in ? d->size[a] : 1;
+        p.sext[a] = in ? d->src_ext[a] : 1;
+        p.sstr[a] = in ? ss : 0; p.dstr[a] = in ? ds : 0;
+        if (in) { ss *= d->src_ext[a]; ds *= d->dst_ext[a]; }
+        p.soff[a] = in ? d->src_off[a] : 0; p.doff[a] = in ? d->dst_off[a] : 0;
+        p.bc[a] = in ? d->boundary[a] : SB200_REMOVE;
+        p.lo[a] = (in && has_region) ? d->region_lo[a] : 0;
+        p.n[a] = in ? (has_region ? d->region_hi[a] - d->region_lo[a] : d->size[a]) : 1;
+        if (in && d->boundary[a] != d->boundary[0]) pl->uniform_bc = false;
+    }
+    p.padbits = d->padval_bits; p.born = d->born_mask; p.survive = d->survive_mask; p.alpha = d->alpha;
+    p.scatter_op = d->scatter_op; p.scatter_rule = d->scatter_rule; p.flags = d->flags;
+    if (kind != PK_HALO) {
+        const size_t ob = sizeof(int32_t) * 3 * d->noffsets;
+        SB_CUDA(cudaMalloc(&pl->offs_dev, ob));
+        SB_CUDA(cudaMemcpy(pl->offs_dev, d->offsets_host, ob, cudaMemcpyHostToDevice));
+        p.offs = pl->offs_dev;
+        if (d->weights_host) {
+            const size_t wb = elsize(d->eltype) * d->noffsets;
+            SB_CUDA(cudaMalloc(&pl->weights_dev, wb));
+            SB_CUDA(cudaMemcpy(pl->weights_dev, d->weights_host, wb, cudaMemcpyHostToDevice));
+            p.weights = pl->weights_dev;
+        }
+        // keep host copies alive inside the plan (callers may free theirs)
+        int32_t* oh = new int32_t[3 * d->noffsets];
+        memcpy(oh, d->offsets_host, ob);
+        pl->d.offsets_host = oh;
+        if (d->weights_host) {
+            char* wh = new char[elsize(d->eltype) * d->noffsets];
+            memcpy(wh, d->weights_host, elsize(d->eltype) * d->noffsets);
+            pl->d.weights_host = wh;
+        }
+        // recognise named shapes (specialised kernels key on them)
+        std::vector<int> gen;
+        int used_dims = 1;
+        for (int k = 0; k < d->noffsets; k++)
+            for (int a = 0; a < 3; a++) if (d->offsets_host[3 * k + a] != 0) used_dims = std::max(used_dims, a + 1);
+        for (int N = used_dims; N <= d->ndim && pl->shape_tag < 0; N++)
+            for (int shape = SB200_WINDOW; shape <= SB200_ORDINAL && pl->shape_tag < 0; shape++) {
+                if (shape == SB200_ANNULUS) continue;
+                if (gen_offsets(shape, d->radius, 0, N, gen) != SB200_OK) continue;
+                if ((int)gen.size() == 3 * d->noffsets && memcmp(gen.data(), d->offsets_host, ob) == 0) { pl->shape_tag = shape; pl->shape_ndim = N; }
+            }
+    }
+    if (kind == PK_SCATTER) {
+        // Static fold order per destination-column residue: sort k by (pass of its source column,
+        // source row ascending == o0 descending, k). See generic.cu scatter_generic.
+        const int S = 2 * d->radius + 1, L = d->noffsets;
+        std::vector<int> order(S * L);
+        for (int c = 0; c < S; c++) {
+            std::vector<std::array<long long, 3>> keys(L);
+            for (int k = 0; k < L; k++) {
+                const int o0 = d->offsets_host[3 * k], o1 = d->offsets_host[3 * k + 1];
+                const long long pass = (((c - o1) % S) + S) % S + 1;
+                keys[k] = {pass, -(long long)o0, (long long)k};
+            }
+            std::vector<int> idx(L);
+            for (int k = 0; k < L; k++) idx[k] = k;
+            std::sort(idx.begin(), idx.end(), [&](int a, int b) { return keys[a] < keys[b]; });
+            for (int q = 0; q < L; q++) order[c * L + q] = idx[q];
+        }
+        SB_CUDA(cudaMalloc(&pl->scatter_order_dev, sizeof(int) * S * L));
+        SB_CUDA(cudaMemcpy(pl->scatter_order_dev, order.data(), sizeof(int) * S * L, cudaMemcpyHostToDevice));
+    }
+    g_plans[key] = pl;
+    *out = pl;
+    return SB200_OK;
+}
+
+static int do_gather(const sb200_desc* d, const void* src, void* dst, cudaStream_t st) {
+    if (!src || !dst) { set_error("NULL data pointer"); return SB200_EINVAL; }
+    if (src == dst) { set_error("source and dest must not alias (the reference keeps distinct buffers)"); return SB200_EINVAL; }
+    Plan* pl = nullptr;
+    int rc = get_plan(d, PK_GATHER, &pl);
+    if (rc) return rc;
+    if (!(d->flags & SB200_FLAG_FORCE_GENERIC)) {
+        rc = try_life_swar(*pl, src, dst, st);
+        if (rc >= 0) return rc;
+        rc = try_diffusion3d(*pl, src, dst, st);
+        if (rc >= 0) return rc;
+        rc = try_tile2d(*pl, src, dst, st);
+        if (rc >= 0) return rc;
+    }
+    return launch_generic_gather(*pl, src, dst, st);
+}
+
+static int do_halo(const sb200_desc* d, void* parent, cudaStream_t st) {
+    if (!parent) { set_error("NULL data pointer"); return SB200_EINVAL; }
+    bool any = false;
+    for (int a = 0; a < d->ndim && a < 3; a++) any |= d->src_off[a] > 0 && d->boundary[a] != SB200_USE;
+    if (!any) return SB200_OK;
+    Plan* pl = nullptr;
+    sb200_desc c = *d;  // the halo plan does not depend on the stencil table / reducer / region
+    c.noffsets = 0; c.offsets_host = nullptr; c.weights_host = nullptr; c.reducer = 0; c.out_eltype = c.eltype;
+    c.flags = 0; c.alpha = 0; c.born_mask = c.survive_mask = 0; c.scatter_op = c.scatter_rule = 0;
+    memset(c.region_lo, 0, sizeof(c.region_lo)); memset(c.region_hi, 0, sizeof(c.region_hi));
+    memset(c.dst_ext, 0, sizeof(c.dst_ext)); memset(c.dst_off, 0, sizeof(c.dst_off));
+    int rc = get_plan(&c, PK_HALO, &pl);
+    if (rc) return rc;
+    return launch_update_halo(*pl, parent, st);
+}
+
+static bool needs_halo(const sb200_desc* d) {
+    for (int a = 0; a < d->ndim && a < 3; a++)
+        if (d->src_off[a] > 0 && d->boundary[a] != SB200_USE) return true;
+    return false;
+}
+
+// ---- peer-memory helpers ----
+__global__ void push_planes_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, size_t n16,
+                                   const unsigned char* __restrict__ srcb, unsigned char* __restrict__ dstb, size_t tail0,
+                                   size_t bytes, uint32_t* flag, uint32_t value, unsigned int* done_ctr) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x)
+        dst[i] = src[i];
+    for (size_t i = tail0 + blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < bytes; i += (size_t)gridDim.x * blockDim.x)
+        dstb[i] = srcb[i];
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned prev = atomicAdd(done_ctr, 1u);
+        if (prev == gridDim.x - 1) {  // last block: every block's stores are fenced -> publish
+            *done_ctr = 0;
+            __threadfence_system();
+            if (flag) {
+                asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(value) : "memory");
+            }
+        }
+    }
+}
+
+__global__ void wait_flag_kernel(const uint32_t* flag, uint32_t value) {
+    uint32_t v;
+    do {
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+        if ((int32_t)(v - value) >= 0) break;
+        __nanosleep(200);
+    } while (true);
+}
+
+static thread_local unsigned int* g_done_ctr = nullptr;  // 64 counters, one per in-flight push
+static thread_local unsigned g_push_seq = 0;
+
+}  // namespace sb
+
+using namespace sb;
+
+extern "C" {
+
+int32_t sb200_version(void) { return SB200_VERSION; }
+const char* sb200_last_error(void) { return g_err; }
+const char* sb200_last_kernel(void) { return g_kernel; }
+int64_t sb200_launch_count(int32_t reset) {
+    const long long v = g_launches;
+    if (reset) g_launches = 0;
+    return v;
+}
+
+int32_t sb200_stencil_offsets(int32_t shape, int32_t radius, int32_t inner_radius, int32_t ndim, int32_t* out,
+                              int32_t cap, int32_t* count) {
+    if (!count || ndim < 1 || ndim > 3 || radius < 0 || radius > 64) { set_error("bad arguments to sb200_stencil_offsets"); return SB200_EINVAL; }
+    std::vector<int> gen;
+    const int rc = gen_offsets(shape, radius, inner_radius, ndim, gen);
+    if (rc) { set_error("unknown stencil shape %d", shape); return rc; }
+    const int L = (int)gen.size() / 3;
+    if (out)
+        for (int k = 0; k < L && k < cap; k++) { out[3 * k] = gen[3 * k]; out[3 * k + 1] = gen[3 * k + 1]; out[3 * k + 2] = gen[3 * k + 2]; }
+    *count = L;
+    return SB200_OK;
+}
+
+int32_t sb200_out_eltype(int32_t reducer, int32_t eltype, int32_t* out) {
+    if (!out) { set_error("NULL out"); return SB200_EINVAL; }
+    return out_eltype_of(reducer, eltype, out);
+}
+size_t sb200_sizeof(int32_t eltype) { return elsize(eltype); }
+
+int32_t sb200_gather(const sb200_desc* d, const void* src, void* dst, void* stream) {
+    return do_gather(d, src, dst, (cudaStream_t)stream);
+}
+int32_t sb200_update_halo(const sb200_desc* d, void* parent, void* stream) {
+    const int rc = validate(d, PK_HALO);
+    if (rc) return rc;
+    return do_halo(d, parent, (cudaStream_t)stream);
+}
+int32_t sb200_scatter(const sb200_desc* d, const void* src, void* dst, void* stream) {
+    if (!src || !dst) { set_error("NULL data pointer"); return SB200_EINVAL; }
+    Plan* pl = nullptr;
+    int rc = get_plan(d, PK_SCATTER, &pl);
+    if (rc) return rc;
+    if (!(d->flags & SB200_FLAG_FORCE_GENERIC)) {
+        rc = try_scatter_fast(*pl, src, dst, (cudaStream_t)stream);
+        if (rc >= 0) return rc;
+    }
+    return launch_generic_scatter(*pl, src, dst, (cudaStream_t)stream);
+}
+
+int32_t sb200_iterate(const sb200_desc* d, void* buf_a, void* buf_b, int32_t nsteps, void* stream) {
+    if (nsteps < 0) { set_error("negative step count"); return SB200_EINVAL; }
+    if (!d) { set_error("descriptor is NULL"); return SB200_EINVAL; }
+    for (int a = 0; a < d->ndim && a < 3; a++)
+        if (d->src_ext[a] != d->dst_ext[a] || d->src_off[a] != d->dst_off[a]) {
+            set_error("source and dest arrays must be the same size (src/array.jl:574-575)");
+            return SB200_ESIZE;
+        }
+    if (d->eltype != d->out_eltype) { set_error("iterated sweeps need a reducer that preserves the element type"); return SB200_EUNSUPPORTED; }
+    void *s = buf_a, *t = buf_b;
+    const bool halo = needs_halo(d);
+    for (int i = 0; i < nsteps; i++) {
+        int rc;
+        if (halo && (rc = sb200_update_halo(d, s, stream))) return rc;
+        if ((rc = do_gather(d, s, t, (cudaStream_t)stream))) return rc;
+        void* tmp = s; s = t; t = tmp;
+    }
+    return SB200_OK;
+}
+
+// ---- host-buffer entry points ----
+static size_t parent_bytes(const sb200_desc* d, bool src) {
+    size_t n = 1;
+    for (int a = 0; a < d->ndim; a++) n *= (size_t)(src ? d->src_ext[a] : d->dst_ext[a]);
+    return n * elsize(src ? d->eltype : d->out_eltype);
+}
+
+struct HostScratch {
+    void* a = nullptr; size_t a_bytes = 0;
+    void* b = nullptr; size_t b_bytes = 0;
+    cudaStream_t st[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev[64];
+    bool init = false;
+};
+static thread_local HostScratch g_hs;
+
+static int ensure_scratch(size_t ab, size_t bb) {
+    if (!g_hs.init) {
+        for (int i = 0; i < 3; i++) SB_CUDA(cudaStreamCreateWithFlags(&g_hs.st[i], cudaStreamNonBlocking));
+        for (int i = 0; i < 64; i++) SB_CUDA(cudaEventCreateWithFlags(&g_hs.ev[i], cudaEventDisableTiming));
+        g_hs.init = true;
+    }
+    if (g_hs.a_bytes < ab) { if (g_hs.a) cudaFree(g_hs.a); g_hs.a = nullptr; g_hs.a_bytes = 0; SB_CUDA(cudaMalloc(&g_hs.a, ab)); g_hs.a_bytes = ab; }
+    if (g_hs.b_bytes < bb) { if (g_hs.b) cudaFree(g_hs.b); g_hs.b = nullptr; g_hs.b_bytes = 0; SB_CUDA(cudaMalloc(&g_hs.b, bb)); g_hs.b_bytes = bb; }
+    return SB200_OK;
+}
+
+int32_t sb200_gather_host(const sb200_desc* d, const void* src_host, void* dst_host) {
+    int rc = validate(d, PK_GATHER);
+    if (rc) return rc;
+    if (!src_host || !dst_host) { set_error("NULL data pointer"); return SB200_EINVAL; }
+    const size_t sb_ = parent_bytes(d, true), db = parent_bytes(d, false);
+    if ((rc = ensure_scratch(sb_, db))) return rc;
+    const int last = d->ndim - 1;
+    bool has_region = false;
+    for (int a = 0; a < d->ndim; a++) has_region |= d->region_lo[a] != 0 || d->region_hi[a] != 0;
+    // Chunk the slowest axis so H2D, the sweep and D2H of neighbouring chunks overlap (3 streams).
+    // Chunking needs each output chunk to depend only on a contiguous band of source planes, which holds
+    // when the slowest axis is not wrapped/reflected on the fly and there is no ring to refresh.
+    const long long nlast = d->size[last];
+    size_t plane_src = elsize(d->eltype), plane_dst = elsize(d->out_eltype);
+    for (int a = 0; a < last; a++) { plane_src *= (size_t)d->src_ext[a]; plane_dst *= (size_t)d->dst_ext[a]; }
+    const bool chunkable = !has_region && !needs_halo(d) && d->ndim >= 2 &&
+                           (d->src_off[last] > 0 || d->boundary[last] == SB200_REMOVE) && nlast >= 64 &&
+                           sb_ >= (size_t)(8u << 20) && d->dst_off[last] == 0 && d->dst_ext[last] == d->size[last];
+    if (!chunkable) {
+        cudaStream_t st = g_hs.st[0];
+        SB_CUDA(cudaMemcpyAsync(g_hs.a, src_host, sb_, cudaMemcpyHostToDevice, st));
+        if (needs_halo(d) && (rc = do_halo(d, g_hs.a, st))) return rc;
+        if (db != 0 && (d->dst_off[0] | d->dst_off[1] | d->dst_off[2]))  // keep the dest ring as the caller had it
+            SB_CUDA(cudaMemcpyAsync(g_hs.b, dst_host, db, cudaMemcpyHostToDevice, st));
+        if ((rc = do_gather(d, g_hs.a, g_hs.b, st))) return rc;
+        SB_CUDA(cudaMemcpyAsync(dst_host, g_hs.b, db, cudaMemcpyDeviceToHost, st));
+        if (needs_halo(d)) SB_CUDA(cudaMemcpyAsync(const_cast<void*>(src_host), g_hs.a, sb_, cudaMemcpyDeviceToHost, st));
+        SB_CUDA(cudaStreamSynchronize(st));
+        return SB200_OK;
+    }
+    int nchunks = 16;
+    if (nlast / nchunks < 2 * (long long)d->radius + 1) nchunks = 1;
+    const int R = d->radius, off = d->src_off[last];
+    long long sent_hi = 0;  // source planes [0, sent_hi) of the parent are on the device
+    const long long src_planes = d->src_ext[last];
+    for (int c = 0; c < nchunks; c++) {
+        const long long lo = nlast * c / nchunks, hi = nlast * (c + 1) / nchunks;
+        // source planes this chunk reads: parent planes [lo+off-R, hi+off+R) clipped
+        long long need_hi = std::min(src_planes, hi + off + R);
+        if (c == nchunks - 1) need_hi = src_planes;
+        cudaStream_t sh = g_hs.st[0], sk = g_hs.st[1], sd = g_hs.st[2];
+        if (need_hi > sent_hi) {
+            SB_CUDA(cudaMemcpyAsync((char*)g_hs.a + sent_hi * plane_src, (const char*)src_host + sent_hi * plane_src,
+                                    (size_t)(need_hi - sent_hi) * plane_src, cudaMemcpyHostToDevice, sh));
+            sent_hi = need_hi;
+        }
+        SB_CUDA(cudaEventRecord(g_hs.ev[2 * c], sh));
+        SB_CUDA(cudaStreamWaitEvent(sk, g_hs.ev[2 * c], 0));
+        sb200_desc cd = *d;
+        for (int a = 0; a < d->ndim; a++) { cd.region_lo[a] = 0; cd.region_hi[a] = d->size[a]; }
+        cd.region_lo[last] = lo; cd.region_hi[last] = hi;
+        if ((rc = do_gather(&cd, g_hs.a, g_hs.b, sk))) return rc;
+        SB_CUDA(cudaEventRecord(g_hs.ev[2 * c + 1], sk));
+        SB_CUDA(cudaStreamWaitEvent(sd, g_hs.ev[2 * c + 1], 0));
+        SB_CUDA(cudaMemcpyAsync((char*)dst_host + lo * plane_dst, (char*)g_hs.b + lo * plane_dst,
+                                (size_t)(hi - lo) * plane_dst, cudaMemcpyDeviceToHost, sd));
+    }
+    SB_CUDA(cudaStreamSynchronize(g_hs.st[2]));
+    SB_CUDA(cudaStreamSynchronize(g_hs.st[1]));
+    SB_CUDA(cudaStreamSynchronize(g_hs.st[0]));
+    return SB200_OK;
+}
+
+int32_t sb200_iterate_host(const sb200_desc* d, void* state_host, int32_t nsteps) {
+    int rc = validate(d, PK_GATHER);
+    if (rc) return rc;
+    if (!state_host) { set_error("NULL data pointer"); return SB200_EINVAL; }
+    const size_t sb_ = parent_bytes(d, true);
+    if ((rc = ensure_scratch(sb_, sb_))) return rc;
+    cudaStream_t st = g_hs.st[0];
+    SB_CUDA(cudaMemcpyAsync(g_hs.a, state_host, sb_, cudaMemcpyHostToDevice, st));
+    if (d->src_off[0] | d->src_off[1] | d->src_off[2]) SB_CUDA(cudaMemcpyAsync(g_hs.b, g_hs.a, sb_, cudaMemcpyDeviceToDevice, st));
+    if ((rc = sb200_iterate(d, g_hs.a, g_hs.b, nsteps, st))) return rc;
+    SB_CUDA(cudaMemcpyAsync(state_host, (nsteps % 2 == 0) ? g_hs.a : g_hs.b, sb_, cudaMemcpyDeviceToHost, st));
+    SB_CUDA(cudaStreamSynchronize(st));
+    return SB200_OK;
+}
+
+// ---- memory helpers ----
+int32_t sb200_device_count(int32_t* n) { if (!n) return SB200_EINVAL; int c = 0; SB_CUDA(cudaGetDeviceCount(&c)); *n = c; return SB200_OK; }
+int32_t sb200_set_device(int32_t dev) { SB_CUDA(cudaSetDevice(dev)); return SB200_OK; }
+int32_t sb200_malloc(void** p, size_t bytes) { if (!p) return SB200_EINVAL; SB_CUDA(cudaMalloc(p, bytes)); return SB200_OK; }
+int32_t sb200_free(void* p) { SB_CUDA(cudaFree(p)); return SB200_OK; }
+int32_t sb200_malloc_host(void** p, size_t bytes) { if (!p) return SB200_EINVAL; SB_CUDA(cudaMallocHost(p, bytes)); return SB200_OK; }
+int32_t sb200_free_host(void* p) { SB_CUDA(cudaFreeHost(p)); return SB200_OK; }
+int32_t sb200_memcpy_h2d(void* dst, const void* src, size_t bytes, void* stream) { SB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream)); return SB200_OK; }
+int32_t sb200_memcpy_d2h(void* dst, const void* src, size_t bytes, void* stream) { SB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream)); return SB200_OK; }
+int32_t sb200_memcpy_d2d(void* dst, const void* src, size_t bytes, void* stream) { SB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream)); return SB200_OK; }
+int32_t sb200_memset(void* p, int32_t byte, size_t bytes, void* stream) { SB_CUDA(cudaMemsetAsync(p, byte, bytes, (cudaStream_t)stream)); return SB200_OK; }
+int32_t sb200_stream_sync(void* stream) { SB_CUDA(cudaStreamSynchronize((cudaStream_t)stream)); return SB200_OK; }
+
+// ---- peer memory ----
+int32_t sb200_ipc_export(void* p, void* handle64) {
+    if (!p || !handle64) return SB200_EINVAL;
+    cudaIpcMemHandle_t h;
+    SB_CUDA(cudaIpcGetMemHandle(&h, p));
+    static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    memcpy(handle64, &h, 64);
+    return SB200_OK;
+}
+int32_t sb200_ipc_import(const void* handle64, void** p) {
+    if (!p || !handle64) return SB200_EINVAL;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    SB_CUDA(cudaIpcOpenMemHandle(p, h, cudaIpcMemLazyEnablePeerAccess));
+    return SB200_OK;
+}
+int32_t sb200_ipc_close(void* p) { SB_CUDA(cudaIpcCloseMemHandle(p)); return SB200_OK; }
+
+int32_t sb200_push_planes(const void* src, void* peer_dst, size_t bytes, uint32_t* peer_flag, uint32_t value, void* stream) {
+    if (!src || !peer_dst) { set_error("NULL data pointer"); return SB200_EINVAL; }
+    if (!g_done_ctr) {
+        SB_CUDA(cudaMalloc(&g_done_ctr, 64 * sizeof(unsigned int)));
+        SB_CUDA(cudaMemset(g_done_ctr, 0, 64 * sizeof(unsigned int)));
+    }
+    const bool aligned = (((uintptr_t)src | (uintptr_t)peer_dst) & 15) == 0;
+    const size_t n16 = aligned ? bytes / 16 : 0;
+    const size_t tail0 = n16 * 16;
+    size_t blocks = (std::max<size_t>(n16, 1) + 255) / 256;
+    blocks = std::min<size_t>(blocks, (size_t)num_sms() * 4);
+    push_planes_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+        (const uint4*)src, (uint4*)peer_dst, n16, (const unsigned char*)src, (unsigned char*)peer_dst, tail0, bytes,
+        peer_flag, value, g_done_ctr + (g_push_seq++ % 64));
+    SB_LAUNCH_CHECK();
+    return SB200_OK;
+}
+
+int32_t sb200_wait_flag(const uint32_t* flag, uint32_t value, void* stream) {
+    if (!flag) return SB200_EINVAL;
+    wait_flag_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(flag, value);
+    SB_LAUNCH_CHECK();
+    return SB200_OK;
+}
+
+}  // extern "C"

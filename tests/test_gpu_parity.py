@@ -1,0 +1,225 @@
+"""GPU parity: the C ABI (libstencils_b200.so, sm_100a kernels) against the CPU oracle on the same seeded
+inputs and the same sb200_desc. Bit-exact for every eltype and reducer (integer work, max/min and the float
+folds all follow the reference's operation order, so the tolerance is 0 ulp; BASELINE.json allows 2)."""
+import zlib
+
+import numpy as np
+import pytest
+
+from oracle import np_restatement as npr
+from stencils_b200 import _abi as A
+from stencils_b200._desc import build_desc
+from tests.util import bits_equal, dst_like, gpu_gather, gpu_scatter
+
+pytestmark = pytest.mark.gpu
+
+BC = {"remove": A.REMOVE, "wrap": A.WRAP, "reflect": A.REFLECT, "use": A.USE}
+RED = {"sum": A.SUM, "mean": A.MEAN, "min": A.MIN, "max": A.MAX, "kerneldot": A.KERNELDOT, "life": A.LIFE,
+       "diffusion": A.DIFFUSION}
+DTYPES = [np.bool_, np.uint8, np.int32, np.int64, np.float32, np.float64]
+
+
+def rand_array(rng, shape, dt):
+    dt = np.dtype(dt)
+    if dt == np.bool_:
+        return np.asfortranarray(rng.random(shape) < 0.4)
+    if dt.kind in "iu":
+        return np.asfortranarray(rng.integers(0, 200 if dt == np.uint8 else 100000, size=shape).astype(dt))
+    return np.asfortranarray((rng.random(shape) - 0.3).astype(dt))
+
+
+def both(orc, r, offs, R, bc, pad, red, flags=0, switching=False, **kw):
+    """Build parent + descriptor like StencilArray would, run oracle and GPU, compare dest and source ring."""
+    r = np.asfortranarray(r)
+    nd = r.ndim
+    et = A.ELTYPE_OF_DTYPE[r.dtype]
+    if pad == "cond":
+        parent, size, off = r.copy(order="F"), r.shape, (0,) * nd
+    elif pad == "out":
+        parent = np.full(tuple(s + 2 * R for s in r.shape), 77, dtype=r.dtype, order="F")
+        parent[tuple(slice(R, R + s) for s in r.shape)] = r
+        size, off = r.shape, (R,) * nd
+    else:
+        parent, size, off = r.copy(order="F"), tuple(s - 2 * R for s in r.shape), (R,) * nd
+    oet = orc.out_eltype(RED[red], et)
+    dst_off = off if switching else (0,) * nd
+    h = build_desc(size=size, eltype=et, out_eltype=oet, offsets=offs, radius=R, boundary=BC[bc], reducer=RED[red],
+                   src_off=off, dst_off=dst_off, src_ext=parent.shape, flags=flags, **kw)
+    halo = pad != "cond" and bc != "use"
+    p_cpu = parent.copy(order="F")
+    if halo:
+        orc.update_halo(h, p_cpu)
+    want = orc.gather(h, p_cpu, dst_like(h, 5))
+    got, p_gpu = gpu_gather(h, parent, dst_like(h, 5), halo=halo)
+    bits_equal(got, want)
+    bits_equal(p_gpu, p_cpu)  # the ring refresh is a visible side effect
+    return got
+
+
+@pytest.mark.parametrize("dt", DTYPES)
+@pytest.mark.parametrize("bc", ["remove", "wrap", "reflect"])
+@pytest.mark.parametrize("pad", ["cond", "out", "in"])
+def test_all_reducers_2d(orc, dt, bc, pad):
+    rng = np.random.default_rng(zlib.crc32(repr((str(dt), bc, pad)).encode()))
+    padval = {np.bool_: 1, np.uint8: 7}.get(dt, 3)
+    for shape_, (shape, R) in zip([(67, 45), (130, 96), (33, 70), (64, 64), (51, 38)],
+                                  [("Window", 1), ("Moore", 1), ("VonNeumann", 2), ("Circle", 3), ("Cross", 2)]):
+        r = rand_array(rng, shape_, dt)
+        offs = npr.offsets(shape, R, 2)
+        reds = ["sum", "mean", "min", "max"] + (["life"] if len(offs) <= 31 else [])
+        if np.dtype(dt).kind == "f":
+            reds += ["kerneldot", "diffusion"]
+        elif np.dtype(dt) in (np.int32, np.int64):
+            reds += ["kerneldot"]
+        for red in reds:
+            w = rng.integers(-3, 4, size=len(offs)) if np.dtype(dt).kind != "f" else rng.random(len(offs))
+            for flags in (0, A.FLAG_FORCE_GENERIC):
+                both(orc, r, offs, R, bc, pad, red, flags=flags, padval=padval, weights=w, alpha=0.1,
+                     born_mask=0b1001000, survive_mask=0b1100)
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64, np.int32, np.uint8])
+@pytest.mark.parametrize("nd", [1, 3])
+def test_1d_3d(orc, dt, nd):
+    rng = np.random.default_rng(nd)
+    r = rand_array(rng, (1000,) if nd == 1 else (37, 22, 19), dt)
+    for bc in ("remove", "wrap", "reflect"):
+        for pad in ("cond", "out", "in"):
+            for sh, R in [("Window", 1), ("VonNeumann", 1), ("Moore", 1), ("Window", 2)]:
+                offs = npr.offsets(sh, R, nd)
+                for red in ("sum", "mean", "max"):
+                    both(orc, r, offs, R, bc, pad, red, padval=2)
+                if np.dtype(dt).kind == "f":
+                    both(orc, r, offs, R, bc, pad, "diffusion", alpha=0.05)
+                    both(orc, r, offs, R, bc, pad, "diffusion", alpha=0.05, flags=A.FLAG_FORCE_GENERIC)
+
+
+def test_use_boundary_and_switching_dest(orc):
+    rng = np.random.default_rng(8)
+    r = rand_array(rng, (40, 30), np.float64)
+    offs = npr.offsets("Window", 2, 2)
+    both(orc, r, offs, 2, "use", "in", "sum")
+    both(orc, r, offs, 2, "use", "in", "mean", switching=True)
+    both(orc, r, offs, 2, "wrap", "out", "mean", switching=True)
+    both(orc, r, offs, 2, "reflect", "in", "max", switching=True)
+
+
+def test_stencil_dims_below_array_dims(orc):
+    rng = np.random.default_rng(9)
+    r3 = rand_array(rng, (20, 17, 9), np.float32)
+    for pad in ("cond", "out"):
+        for bc in ("remove", "wrap"):
+            both(orc, r3, npr.offsets("Window", 1, 2), 1, bc, pad, "sum")
+            both(orc, r3, npr.offsets("Window", 1, 1), 1, bc, pad, "mean")
+    r2 = rand_array(rng, (31, 29), np.int64)
+    both(orc, r2, npr.offsets("Window", 1, 1), 1, "reflect", "cond", "sum")
+
+
+def test_positional_named_rectangle_tables(orc):
+    rng = np.random.default_rng(10)
+    r = rand_array(rng, (45, 52), np.float32)
+    tables = [
+        ([(-1, 1), (-2, -1), (1, 0), (-2, 2)], 2),                       # README.md:102
+        ([(-1, 0), (0, -1), (1, 0), (0, 1)], 1),                         # NamedStencil n,e,w,s (test/stencils.jl:193)
+        ([(i, j) for j in range(-2, 2) for i in range(-1, 1)], 2),       # Rectangle((-1,0),(-2,1))
+        ([(3, -3)], 3),
+    ]
+    for offs, R in tables:
+        for bc in ("remove", "wrap", "reflect"):
+            for red in ("sum", "max", "min", "mean"):
+                both(orc, r, offs, R, bc, "cond", red, padval=-1.5)
+
+
+def test_float_specials(orc):
+    """NaN propagation and signed zeros of Julia's max/min (SURVEY §7 hard parts)."""
+    rng = np.random.default_rng(12)
+    for dt in (np.float32, np.float64):
+        r = rand_array(rng, (48, 40), dt)
+        r[rng.random(r.shape) < 0.05] = np.nan
+        r[rng.random(r.shape) < 0.2] = 0.0
+        r[rng.random(r.shape) < 0.2] = -0.0
+        r[rng.random(r.shape) < 0.02] = np.inf
+        r[rng.random(r.shape) < 0.02] = -np.inf
+        for sh, R in (("Window", 1), ("Circle", 2), ("Circle", 4)):
+            offs = npr.offsets(sh, R, 2)
+            for red in ("max", "min", "sum", "mean"):
+                for flags in (0, A.FLAG_FORCE_GENERIC):
+                    both(orc, r, offs, R, "wrap", "cond", red, flags=flags)
+                    both(orc, r, offs, R, "remove", "cond", red, flags=flags, padval=-0.0)
+
+
+def test_region(orc):
+    rng = np.random.default_rng(13)
+    r = rand_array(rng, (70, 60), np.float64)
+    offs = npr.offsets("Window", 1, 2)
+    h = build_desc(size=r.shape, eltype=A.F64, out_eltype=A.F64, offsets=offs, radius=1, boundary=A.WRAP, reducer=A.MEAN,
+                   region=((5, 10, 0), (64, 33, 0)))
+    want = orc.gather(h, r, dst_like(h, -5.0))
+    got, _ = gpu_gather(h, r, dst_like(h, -5.0))
+    bits_equal(got, want)
+
+
+@pytest.mark.parametrize("bc", ["remove", "wrap", "reflect"])
+@pytest.mark.parametrize("op", ["add", "max", "min"])
+@pytest.mark.parametrize("dt", [np.float32, np.float64, np.int32])
+def test_scatter(orc, bc, op, dt):
+    rng = np.random.default_rng(14)
+    cases = [([(-1, 1), (-2, -1), (1, 0), (-2, 2)], 2), (npr.offsets("Moore", 1, 2), 1), (npr.offsets("VonNeumann", 2, 2), 2)]
+    for offs, R in cases:
+        S = 2 * R + 1
+        for (ny, nx) in [(40, 7 * S), (33, 6 * S + 1), (2 * R + 1, 2 * R + 2)]:
+            if bc == "wrap" and nx % S:
+                continue  # reference race: two columns of one pass hit the same dest column
+            src = rand_array(rng, (ny, nx), dt)
+            w = (rng.random(len(offs)) if np.dtype(dt).kind == "f" else rng.integers(1, 5, len(offs))).astype(dt)
+            dest0 = rand_array(rng, (ny, nx), dt)
+            for rule in (A.SCATTER_WEIGHTS, A.SCATTER_CENTER_WEIGHTS):
+                for flags in (0, A.FLAG_ZERO_DEST, A.FLAG_FORCE_GENERIC):
+                    et = A.ELTYPE_OF_DTYPE[np.dtype(dt)]
+                    h = build_desc(size=(ny, nx), eltype=et, out_eltype=et, offsets=offs, radius=R, boundary=BC[bc],
+                                   weights=w, scatter_op={"add": A.OP_ADD, "max": A.OP_MAX, "min": A.OP_MIN}[op],
+                                   scatter_rule=rule, flags=flags)
+                    want = orc.scatter(h, src, dest0.copy(order="F"))
+                    bits_equal(gpu_scatter(h, src, dest0.copy(order="F")), want)
+
+
+def test_iterate_life_and_diffusion(orc):
+    from tests.util import stream, sync, to_dev, to_host
+    rng = np.random.default_rng(15)
+    l = A.lib()
+    a = np.asfortranarray((rng.random((256, 192)) < 0.35).astype(np.uint8))
+    h = build_desc(size=a.shape, eltype=A.U8, out_eltype=A.U8, offsets=npr.offsets("Moore", 1, 2), radius=1,
+                   boundary=A.WRAP, reducer=A.LIFE)
+    want = orc.iterate(h, a.copy(order="F"), np.zeros_like(a, order="F"), 25)
+    ta, tb = to_dev(a), to_dev(np.zeros_like(a, order="F"))
+    A.check(l.sb200_iterate(h.ptr(), ta.data_ptr(), tb.data_ptr(), 25, stream()))
+    sync()
+    bits_equal(to_host(tb, a.shape, a.dtype), want)
+    # diffusion 3-D with a Halo ring refreshed every step
+    g = rand_array(rng, (34, 30, 26), np.float32)
+    offs = npr.offsets("VonNeumann", 1, 3)
+    h = build_desc(size=(32, 28, 24), eltype=A.F32, out_eltype=A.F32, offsets=offs, radius=1, boundary=A.WRAP,
+                   reducer=A.DIFFUSION, alpha=0.1, src_off=(1, 1, 1), dst_off=(1, 1, 1))
+    b0 = g.copy(order="F")
+    want = orc.iterate(h, g.copy(order="F"), b0.copy(order="F"), 6)
+    ta, tb = to_dev(g), to_dev(b0)
+    A.check(l.sb200_iterate(h.ptr(), ta.data_ptr(), tb.data_ptr(), 6, stream()))
+    sync()
+    bits_equal(to_host(ta, g.shape, g.dtype), want)
+
+
+def test_errors_are_status_codes():
+    l = A.lib()
+    r = np.zeros((8, 8), order="F")
+    offs = npr.offsets("Window", 1, 2)
+    from tests.util import to_dev
+    t = to_dev(r)
+    h = build_desc(size=r.shape, eltype=A.F64, out_eltype=A.F64, offsets=offs, radius=1, boundary=A.USE, reducer=A.SUM)
+    assert l.sb200_gather(h.ptr(), t.data_ptr(), to_dev(r).data_ptr(), None) == A.EUNSUPPORTED
+    assert b"Use" in l.sb200_last_error()
+    h = build_desc(size=r.shape, eltype=A.F64, out_eltype=A.F64, offsets=offs, radius=1, boundary=A.REMOVE, reducer=99)
+    assert l.sb200_gather(h.ptr(), t.data_ptr(), to_dev(r).data_ptr(), None) == A.EUNSUPPORTED
+    h = build_desc(size=r.shape, eltype=A.F64, out_eltype=A.F64, offsets=npr.offsets("Window", 8, 2), radius=8,
+                   boundary=A.REMOVE, reducer=A.SUM)
+    assert l.sb200_gather(h.ptr(), t.data_ptr(), to_dev(r).data_ptr(), None) == A.ESIZE
+    assert l.sb200_gather(h.ptr(), t.data_ptr(), t.data_ptr(), None) != A.OK

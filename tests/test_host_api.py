@@ -1,0 +1,158 @@
+"""CPU tests of the host-side mirror (size bookkeeping, stencil algebra, error behaviour) and of the C-ABI
+library's link surface. No compute call is made here: the library loads and resolves on a machine without a GPU."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import stencils_b200 as sb
+from stencils_b200 import _abi as A
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "stencils_b200.h")).read()
+    declared = sorted(set(re.findall(r"^(?:int32_t|int64_t|size_t|const char\*)\s+(sb200_[a-z0-9_]+)\(", hdr, re.M)))
+    assert declared == sorted(A.EXPORTED_SYMBOLS)
+    lib = C.CDLL(A.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert A.lib().sb200_version() == 100
+
+
+def test_desc_layout_matches_header():
+    import subprocess
+    import tempfile
+    src = '#include <stdio.h>\n#include <stddef.h>\n#include "stencils_b200.h"\nint main(){printf("%zu %zu %zu %zu",sizeof(sb200_desc),' \
+          'offsetof(sb200_desc,offsets_host),offsetof(sb200_desc,alpha),offsetof(sb200_desc,flags));return 0;}'
+    with tempfile.TemporaryDirectory() as d:
+        open(os.path.join(d, "t.c"), "w").write(src)
+        subprocess.run(["/usr/bin/gcc", "-I", os.path.join(ROOT, "include"), os.path.join(d, "t.c"), "-o", os.path.join(d, "t")], check=True)
+        out = subprocess.run([os.path.join(d, "t")], capture_output=True, text=True, check=True).stdout.split()
+    assert [int(v) for v in out] == [C.sizeof(A.Desc), A.Desc.offsets_host.offset, A.Desc.alpha.offset, A.Desc.flags.offset]
+
+
+def test_offsets_match_goldens_through_the_abi(goldens):
+    name2cls = {"Moore": sb.Moore, "Window": sb.Window, "VonNeumann": sb.VonNeumann, "Ordinal": sb.Ordinal,
+                "Cardinal": sb.Cardinal}
+    for key, g in goldens["offsets"].items():
+        want = tuple(tuple(t) for t in g["v"])
+        if g["shape"] == "Annulus":
+            assert sb.Annulus(g["R"], g["RI"], g["N"]).offsets() == want, key
+        else:
+            assert name2cls[g["shape"]](g["R"], g["N"]).offsets() == want, key
+
+
+def test_abi_offsets_equal_oracle_for_all_shapes(orc):
+    classes = [sb.Window, sb.Moore, sb.VonNeumann, sb.Cross, sb.AngledCross, sb.ForwardSlash, sb.BackSlash, sb.Circle,
+               sb.Vertical, sb.Horizontal, sb.Diamond, None, sb.Cardinal, sb.Ordinal]
+    for enum, cls in enumerate(classes):
+        for N in (1, 2, 3):
+            for R in (1, 2, 3, 4):
+                if cls is None:
+                    got = sb.Annulus(R, R - 1, N).offsets()
+                else:
+                    got = cls(R, N).offsets()
+                assert list(got) == orc.offsets(enum, R, N, R - 1), (enum, N, R)
+
+
+def test_stencil_algebra():
+    m = sb.Moore(1)
+    assert sb.radius(m) == 1 and sb.diameter(m) == 3 and len(m) == 8                   # test/stencils.jl:18-23
+    sq2 = 2 ** 0.5
+    assert sb.distances(m) == (sq2, 1.0, sq2, 1.0, 1.0, sq2, 1.0, sq2)                 # test/stencils.jl:32
+    assert sb.indices(m, (1, 1)) == ((0, 0), (1, 0), (2, 0), (0, 1), (2, 1), (0, 2), (1, 2), (2, 2))
+    assert sb.indices(sb.Window(1, 2), (10, 10, 10)) == sb.indices(
+        sb.Positional((-1, -1, 0), (0, -1, 0), (1, -1, 0), (-1, 0, 0), (0, 0, 0), (1, 0, 0), (-1, 1, 0), (0, 1, 0), (1, 1, 0)),
+        (10, 10, 10))                                                                  # test/array.jl:113
+    h1 = sb.Positional(((-1, -1), (2, -2), (2, 2), (-1, 2), (0, 0)))
+    assert sb.radius(h1) == 2 and len(h1) == 5                                         # test/stencils.jl:143-144
+    r = sb.Rectangle((-1, 0), (-2, 1))
+    assert sb.radius(r) == 2 and len(r) == 8                                           # test/stencils.jl:167-168
+    assert len(sb.Rectangle(((-1, 0), (0, 1), (1, 1)))) == 4                           # test/stencils.jl:177-179
+    ns = sb.NamedStencil(n=(-1, 0), e=(0, -1), w=(1, 0), s=(0, 1))
+    # test/stencils.jl:215 compares two *unfilled* stencils (StaticVector equality on `nothing` neighbours),
+    # which only pins the length and the names:
+    ns2 = sb.NamedStencil(("n", "e", "w", "s"), sb.VonNeumann())
+    assert len(ns) == len(ns2) == 4 and ns.names == ns2.names and ns2.offsets() == sb.VonNeumann().offsets()
+    with pytest.raises(sb.ArgumentError):
+        sb.NamedStencil(("n", "s"), sb.VonNeumann())                                   # test/stencils.jl:216
+    p = sb.merge(sb.Horizontal(), sb.Vertical())
+    assert len(p) == 5 and list(p.offsets()) == sorted(p.offsets())                    # test/stencils.jl:319-321
+    with pytest.raises(sb.ArgumentError):
+        sb.merge(sb.Horizontal(1, 3), sb.Horizontal())                                 # test/stencils.jl:323
+    with pytest.raises(sb.ArgumentError):
+        sb.Kernel(sb.Window(2), np.arange(9))                                          # test/stencils.jl:272
+    assert sb.Kernel(np.arange(1, 10).reshape(3, 3)).stencil == sb.Window(1, 2)        # test/stencils.jl:273-275
+
+
+def test_filled_stencils_on_host(goldens):
+    F = goldens["fills"]
+    win = np.array(F["win_5x5"]["v"], dtype=np.int64)
+    res1 = sb.stencil(sb.StencilArray(win, sb.Positional(*[tuple(o) for o in F["positional_h1_at_3_3"]["offsets"]])), (3, 3))
+    assert list(sb.neighbors(res1)) == F["positional_h1_at_3_3"]["neighbors"] and sb.center(res1) == 0
+    ns = sb.NamedStencil(n=(-1, 0), e=(0, -1), w=(1, 0), s=(0, 1))
+    res = sb.stencil(sb.StencilArray(win, ns), (3, 3))
+    assert list(sb.neighbors(res)) == F["named_h1_at_3_3"]["neighbors"] and res.n == 1 and res.e == 0  # test/stencils.jl:199-203
+    A4 = sb.StencilArray(np.zeros((4, 4)), sb.Moore(1), boundary=sb.Wrap())
+    assert [list(t) for t in sb.indices(A4, (1, 1))] == goldens["indices"]["wrap_4x4_at_1_1"]["v"]
+    A4 = sb.StencilArray(np.zeros((4, 4)), sb.Moore(1), boundary=sb.Reflect())
+    assert [list(t) for t in sb.indices(A4, (1, 1))] == goldens["indices"]["reflect_4x4_at_1_1"]["v"]
+    S4 = sb.SwitchingStencilArray(np.zeros((4, 4)), sb.Moore(1), boundary=sb.Reflect())
+    assert [list(t) for t in sb.indices(S4, (1, 1))] == goldens["indices"]["reflect_4x4_at_1_1"]["v"]
+
+
+@pytest.mark.parametrize("nd", [1, 2, 3])
+def test_size_bookkeeping(nd):
+    """test/array.jl:16-107: Conditional keeps the size, Halo{:out} pads the parent, Halo{:in} shrinks the view."""
+    n = 100 if nd < 3 else 30
+    r = np.asfortranarray(np.random.default_rng(0).random((n,) * nd))
+    r0 = r.copy()
+    R = 10
+    a = sb.StencilArray(r, sb.VonNeumann(R, nd), padding=sb.Conditional(), boundary=sb.Remove(0.0))
+    b = sb.StencilArray(r, sb.Window(R, nd), padding=sb.Halo("out"), boundary=sb.Remove(0.0))
+    c = sb.StencilArray(r, sb.Moore(R, nd), padding=sb.Halo("in"), boundary=sb.Remove(0.0))
+    sa = sb.SwitchingStencilArray(r, sb.Window(R, nd), padding=sb.Conditional(), boundary=sb.Remove(0.0))
+    sb_ = sb.SwitchingStencilArray(r, sb.Window(R, nd), padding=sb.Halo("out"), boundary=sb.Remove(0.0))
+    sc = sb.SwitchingStencilArray(r, sb.Window(R, nd), padding=sb.Halo("in"), boundary=sb.Remove(0.0))
+    assert sa.source is not sa.dest
+    assert a.shape == a.parent.shape == sa.shape == sa.parent.shape == (n,) * nd
+    assert b.shape == sb_.shape == (n,) * nd and b.parent.shape == sb_.parent.shape == (n + 2 * R,) * nd
+    assert c.shape == sc.shape == (n - 2 * R,) * nd and c.parent.shape == sc.parent.shape == (n,) * nd
+    assert a.similar().shape == a.shape and b.similar().shape == b.shape and c.similar().shape == c.shape
+    c[...] = 0.0
+    assert (np.asarray(c) == 0).all()
+    assert np.array_equal(np.asarray(b), r0)
+    assert c.parent is r and not np.array_equal(r, r0)  # Halo{:in} wraps the user's own array (src/padding.jl:103)
+    with pytest.raises(sb.ArgumentError):
+        sb.StencilArray(np.zeros((5,) * nd), sb.Window(5, nd))  # src/array.jl:451-453
+
+
+def test_unsupported_user_function_raises_without_fallback():
+    a = sb.StencilArray(np.zeros((8, 8)), sb.Window(1))
+    with pytest.raises(sb.ArgumentError, match="no fallback"):
+        sb.mapstencil(lambda h: h.center, a)
+    with pytest.raises(sb.ArgumentError):
+        sb.mapstencil(sb.mean, a, np.zeros((8, 8)))  # extra array args: SURVEY §8f.1 (next)
+    with pytest.raises(sb.ArgumentError):
+        sb.mapstencil(sb.kernelproduct, a)           # needs a Kernel stencil
+    with pytest.raises(sb.ArgumentError):
+        sb.mapstencil(sb.Diffusion(0.1), sb.StencilArray(np.zeros((8, 8), dtype=np.int32), sb.VonNeumann(1)))
+    with pytest.raises(sb.ArgumentError):
+        sb.mapstencil(sb.mean, sb.StencilArray(np.zeros((8, 8)), sb.Window(1), boundary=sb.Remove()))
+    with pytest.raises(sb.ArgumentError):
+        sb.mapstencil(sb.mean, sb.StencilArray(np.zeros((8, 8), dtype=np.float16), sb.Window(1)))
+    with pytest.raises(sb.ArgumentError):
+        sb.mapstencil_(sb.mean, np.zeros((7, 8), order="F"), a)  # _checksizes
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "stencils.jl_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in txt.lower().replace("not a cpu fallback", ""), os.path.join(dirpath, f)
