@@ -263,8 +263,12 @@ __global__ void __launch_bounds__(256) scatter_generic(DevDesc p, const int* __r
         const long long ni = id % ny, nj = id / ny;
         T* cell = &dst[(ni + p.doff[0]) * p.dstr[0] + (nj + p.doff[1]) * p.dstr[1]];
         T acc = zero ? T(0) : *cell;
-        const bool edge0 = (p.bc[0] == SB200_WRAP || p.bc[0] == SB200_REFLECT) && (ni < p.R || ni >= ny - p.R);
-        const bool edge1 = (p.bc[1] == SB200_WRAP || p.bc[1] == SB200_REFLECT) && (nj < p.R || nj >= nx - p.R);
+        // cells that a wrapped (raw -j -> s-j, raw s-1+j -> j-1) or reflected (raw -j -> j, raw s-1+j -> s-1-j)
+        // target can land on, j = 1..R
+        const bool edge0 = (p.bc[0] == SB200_WRAP && (ni < p.R || ni >= ny - p.R)) ||
+                           (p.bc[0] == SB200_REFLECT && (ni <= p.R || ni >= ny - 1 - p.R));
+        const bool edge1 = (p.bc[1] == SB200_WRAP && (nj < p.R || nj >= nx - p.R)) ||
+                           (p.bc[1] == SB200_REFLECT && (nj <= p.R || nj >= nx - 1 - p.R));
         if (!edge0 && !edge1) {
             const int* ord = order + (int)(nj % S) * p.L;
             for (int q = 0; q < p.L; q++) {
