@@ -1,0 +1,418 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the stencil sweep (BASELINE.json metric: Gcell-updates/s and fraction of the
+HBM roofline per stencil config).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload life|mean|kernel|circle|scatter|diffusion]
+    python bench.py --impl reference ...        # the reference algorithm on the host cores (CPU oracle)
+
+One "step" is one sweep of the hot path over the whole grid. The default workload is BASELINE.json configs[1]:
+Game of Life, Moore(1), UInt8 16384x16384, Wrap, SwitchingStencilArray iterated. With N > 1 (torchrun, one rank
+per GPU) every rank owns a 16384x16384 slab of a 16384 x (16384*N) torus (weak scaling) and ghost rows travel
+over NVLink (stencils_b200.slab). Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic(workload):
+    """dram bytes per launch of the dominant kernel from the committed ncu --set full summary, if any."""
+    p = os.path.join(ROOT, "profiles", "ncu_summary.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get(workload, {}).get("dram_bytes_per_launch")
+        except Exception:
+            return None
+    return None
+
+
+# ------------------------------------------------------------------------------------------------ synthetic inputs
+def synth(shape, dtype, seed):
+    from stencils_b200.synth import synth_np
+    return synth_np(shape, dtype, seed)
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting", 0x10: "sync_boost"}
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.stop, self.thr, self.max_mhz = [], set(), threading.Event(), None, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        while not self.stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def __enter__(self):
+        if self.nv:
+            self.thr = threading.Thread(target=self._run, daemon=True)
+            self.thr.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        if self.thr:
+            self.thr.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------ workloads
+def workloads():
+    """name -> spec. bytes_per_cell is the algorithmic figure of SURVEY §8(d): each cell read once + written once."""
+    return {
+        "life": dict(desc="Game of Life: Moore(1), UInt8 16384x16384, Wrap, SwitchingStencilArray (BASELINE configs[1])",
+                     shape=(16384, 16384), dtype=np.uint8, bytes_per_cell=2, iterated=True, seed=0x5EED0002),
+        "mean": dict(desc="mapstencil(mean, Window(1)) Float64 16384x16384, Remove(0) (configs[0] at roofline size)",
+                     shape=(16384, 16384), dtype=np.float64, bytes_per_cell=16, iterated=False, seed=0x5EED0001),
+        "mean1000": dict(desc="mapstencil(mean, Window(1)) Float64 1000x1000, Remove(0) (configs[0], README size)",
+                         shape=(1000, 1000), dtype=np.float64, bytes_per_cell=16, iterated=False, seed=0x5EED0001),
+        "kernel": dict(desc="kernelproduct, Kernel(Window(3), 7x7 Float32) 16384x16384, Remove(0)/Conditional (configs[2])",
+                       shape=(16384, 16384), dtype=np.float32, bytes_per_cell=8, iterated=False, seed=0x5EED0003),
+        "circle": dict(desc="maximum over Circle(4), Float32 32768x32768, Remove(0) (configs[3]a)",
+                       shape=(32768, 32768), dtype=np.float32, bytes_per_cell=8, iterated=False, seed=0x5EED0004),
+        "scatter": dict(desc="scatterstencil!(+) Positional((-1,1),(-2,-1),(1,0),(-2,2)), val=centre*w, Float32 32768x32768 (configs[3]b)",
+                        shape=(32768, 32768), dtype=np.float32, bytes_per_cell=12, iterated=False, seed=0x5EED0004),
+        "diffusion": dict(desc="3-D diffusion: VonNeumann(1,3) Float32 1024^3, Wrap, iterated (configs[4])",
+                          shape=(1024, 1024, 1024), dtype=np.float32, bytes_per_cell=8, iterated=True, seed=0x5EED0005),
+    }
+
+
+def make_sweep(name, spec, torch, sb, shape=None):
+    """Returns (state dict, run(nsteps) -> None stream-ordered, cells_per_step)."""
+    shape = tuple(shape or spec["shape"])
+    dev = torch.device("cuda", torch.cuda.current_device())
+    from stencils_b200.synth import synth_torch
+    src = synth_torch(shape, spec["dtype"], spec["seed"], dev)  # bit-identical to synth_np (tests/test_gpu_api.py)
+    cells = int(np.prod(shape))
+    st = {"name": name}
+    if name == "life":
+        S = sb.SwitchingStencilArray(src, sb.Moore(1), boundary=sb.Wrap())
+        st["S"] = S
+
+        def run(n):
+            st["S"] = sb.iterate_(sb.Life(), st["S"], n)
+    elif name == "diffusion":
+        S = sb.SwitchingStencilArray(src, sb.VonNeumann(1, 3), boundary=sb.Wrap())
+        st["S"] = S
+
+        def run(n):
+            st["S"] = sb.iterate_(sb.Diffusion(0.1), st["S"], n)
+    elif name in ("mean", "mean1000"):
+        a = sb.StencilArray(src, sb.Window(1), boundary=sb.Remove(0.0))
+        dst = sb.colmajor_empty(shape, torch.float64, dev)
+
+        def run(n):
+            for _ in range(n):
+                sb.mapstencil_(sb.mean, dst, a)
+    elif name == "kernel":
+        w = synth((7, 7), np.float32, 0x5EED1003)
+        w = (w / w.sum(dtype=np.float32)).astype(np.float32)
+        a = sb.StencilArray(src, sb.Kernel(sb.Window(3), w), boundary=sb.Remove(np.float32(0)))
+        dst = sb.colmajor_empty(shape, torch.float32, dev)
+
+        def run(n):
+            for _ in range(n):
+                sb.mapstencil_(sb.kernelproduct, dst, a)
+    elif name == "circle":
+        a = sb.StencilArray(src, sb.Circle(4), boundary=sb.Remove(np.float32(0)))
+        dst = sb.colmajor_empty(shape, torch.float32, dev)
+
+        def run(n):
+            for _ in range(n):
+                sb.mapstencil_(sb.maximum, dst, a)
+    elif name == "scatter":
+        a = sb.StencilArray(src, sb.Positional((-1, 1), (-2, -1), (1, 0), (-2, 2)), boundary=sb.Remove(np.float32(0)))
+        dst = sb.colmajor_empty(shape, torch.float32, dev)
+        dst.zero_()
+        rule = sb.ScatterCenterWeights(np.array([0.4, 0.3, 0.2, 0.1], dtype=np.float32))
+        import operator
+
+        def run(n):
+            for _ in range(n):
+                sb.scatterstencil_(rule, operator.add, dst, a)
+    else:
+        raise SystemExit(f"unknown workload {name}")
+    return st, run, cells
+
+
+def time_steps(torch, run, steps, warmup, barrier=None, on_warm=None):
+    run(warmup)
+    torch.cuda.synchronize()
+    if on_warm:
+        on_warm()
+    if barrier:
+        barrier()
+    stream = torch.cuda.current_stream()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record(stream)
+    run(steps)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    if barrier:
+        barrier()
+    return e0.elapsed_time(e1)  # ms
+
+
+# ------------------------------------------------------------------------------------------------ CPU baseline / reference arm
+def cpu_life_step_factory(rows, spec):
+    """Reference algorithm (CPU oracle = restatement of Stencils.jl's CPU path) on a bounded sample: a
+    16384 x rows torus of the same synthetic field; per-cell work is identical to the full grid."""
+    from oracle import np_restatement as npr
+    from oracle import oracle as orc
+    from stencils_b200 import _abi as A
+    from stencils_b200._desc import build_desc
+    shape = (spec["shape"][0], rows)
+    a = np.asfortranarray(synth(shape, np.uint8, spec["seed"]))
+    b = np.zeros_like(a, order="F")
+    h = build_desc(size=shape, eltype=A.U8, out_eltype=A.U8, offsets=npr.offsets("Moore", 1, 2), radius=1,
+                   boundary=A.WRAP, reducer=A.LIFE)
+    bufs = [a, b]
+
+    def step():
+        orc.gather(h, bufs[0], bufs[1])
+        bufs.reverse()
+    return step, shape[0] * rows, orc.threads()
+
+
+def cpu_baseline(spec, budget_s=12.0):
+    step, cells, cores = cpu_life_step_factory(1024, spec)
+    step()  # warm-up (thread pool, page faults)
+    t0 = time.perf_counter()
+    n = 0
+    while True:
+        step()
+        n += 1
+        el = time.perf_counter() - t0
+        if el >= budget_s or n >= 2000:
+            break
+    return {"value": cells * n / el / 1e9, "unit": "Gcell-updates/s", "cores": cores, "kind": "port",
+            "sample": f"Life on a 16384x1024 torus slab of the same field, {n} generations in {el:.1f} s, "
+                      f"OpenMP static over columns, {cores} threads (CPU oracle: C restatement of Stencils.jl's CPU path; "
+                      "the Julia reference itself cannot run in this image)"}
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    spec = workloads()["life"]
+    # size the sample so that (warmup + steps) generations take about 100 s
+    step, cells, cores = cpu_life_step_factory(256, spec)
+    step()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        step()
+    rate = cells * 3 / (time.perf_counter() - t0)
+    total = max(args.steps + args.warmup, 1)
+    rows = int(rate * 100.0 / total / spec["shape"][0])
+    rows = max(64, min(spec["shape"][1], rows // 64 * 64))
+    step, cells, cores = cpu_life_step_factory(rows, spec)
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    el = time.perf_counter() - t0
+    val = cells * args.steps / el / 1e9
+    sample = (f"each step = one Life generation on a 16384x{rows} torus slab of the synthetic field "
+              f"(bounded sample of the 16384x16384 grid), {cores} OpenMP threads")
+    line = {"impl": "reference", "metric": "gcell_updates_per_s", "value": val, "unit": "Gcell-updates/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": el / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": spec["desc"], "sample": sample},
+            "cpu_baseline": {"value": val, "unit": "Gcell-updates/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": "Gcell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------ main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=None)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="life")
+    ap.add_argument("--no-extras", action="store_true", help="skip the secondary configs / cpu baseline / e2e legs")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    spec = workloads()[args.workload]
+    if args.steps is None:
+        args.steps = 1000 if args.workload == "life" else (100 if spec["iterated"] else 20)
+    if args.warmup is None:
+        args.warmup = 10 if spec["iterated"] else 3
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        return run_reference(args, rank)
+
+    import torch
+    import stencils_b200 as sb
+    from stencils_b200 import _abi as A
+    torch.cuda.set_device(local_rank)
+    barrier = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        barrier = dist.barrier
+    lib = A.lib()
+    peak, peak_src = measured_peak()
+
+    if world > 1:
+        from stencils_b200 import slab
+        res = slab.bench_weak(args.workload, spec, args.steps, args.warmup, synth)
+        ms, cells_total, launches, kernel, extra_cfg = res
+    else:
+        st, run, cells_total = make_sweep(args.workload, spec, torch, sb)
+        run(1)
+        torch.cuda.synchronize()
+        kernel = lib.sb200_last_kernel().decode()
+        with ClockSampler(local_rank) as cs:
+            ms = time_steps(torch, run, args.steps, args.warmup, barrier, on_warm=lambda: lib.sb200_launch_count(1))
+        launches = lib.sb200_launch_count(1)  # kernels launched by libstencils_b200 inside the timed region
+        extra_cfg = {}
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        cs = ClockSampler(local_rank)
+
+    value = cells_total * args.steps / (ms * 1e-3) / 1e9
+    achieved = value * spec["bytes_per_cell"] / max(world, 1)  # GB/s per GPU, algorithmic bytes
+    line = {
+        "metric": "gcell_updates_per_s", "value": value, "unit": "Gcell-updates/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": {"uint8": "u8", "float64": "f64", "float32": "f32"}[np.dtype(spec["dtype"]).name],
+        "data": "synthetic (splitmix64 hash of the linear index, SURVEY 8d)",
+        "config": {"workload": spec["desc"], "grid_per_gpu": list(spec["shape"]), "parallelism": f"slab{world}",
+                   "l2": "state per GPU (>= 256 MiB) is larger than the 126 MB L2; no flush needed", **extra_cfg},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": ncu_traffic(args.workload), "peak_source": peak_src, "kernel": kernel,
+                     "algorithmic_bytes_per_cell": spec["bytes_per_cell"],
+                     "how": "algorithmic bytes per launch / mean launch duration (CUDA events on the launching stream "
+                            "around the K back-to-back launches of the timed region)"},
+        "gpu_launches": int(launches),
+        "clocks": cs.summary(),
+    }
+
+    if rank == 0 and world == 1 and not args.no_extras:
+        # ---- e2e: the reference-facing call with HOST buffers, copies inside the timed region ----
+        try:
+            line["e2e"] = e2e_host(torch, sb, lib, args.workload, spec)
+        except Exception as e:  # pragma: no cover
+            line["e2e"] = {"error": repr(e)}
+        # ---- the other BASELINE configs, same measurement, for context ----
+        del st, run
+        torch.cuda.empty_cache()
+        also = {}
+        for name in ("mean", "mean1000", "kernel", "circle", "scatter", "diffusion"):
+            if name == args.workload:
+                continue
+            try:
+                sp = workloads()[name]
+                st2, run2, cells2 = make_sweep(name, sp, torch, sb)
+                k = 20 if not sp["iterated"] else 50
+                if name == "mean1000":
+                    k = 200
+                run2(1)
+                torch.cuda.synchronize()
+                kn = lib.sb200_last_kernel().decode()
+                ms2 = time_steps(torch, run2, k, 3)
+                v = cells2 * k / (ms2 * 1e-3) / 1e9
+                also[name] = {"value": v, "unit": "Gcell-updates/s", "ms_per_step": ms2 / k, "kernel": kn,
+                              "roofline_frac": v * sp["bytes_per_cell"] / peak, "workload": sp["desc"]}
+                del st2, run2
+                torch.cuda.empty_cache()
+            except Exception as e:  # pragma: no cover
+                also[name] = {"error": repr(e)}
+        line["other_configs"] = also
+        try:
+            line["cpu_baseline"] = cpu_baseline(spec) if args.workload == "life" else None
+        except Exception as e:  # pragma: no cover
+            line["cpu_baseline"] = {"error": repr(e)}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+def e2e_host(torch, sb, lib, workload, spec):
+    """Same metric through the C-ABI entry point a host-array StencilArray lowers to (sb200_gather_host):
+    pinned host source -> HBM -> sweep -> pinned host dest, every step."""
+    from stencils_b200.array import _torch_dtype
+    shape = spec["shape"]
+    if workload != "life":
+        return None
+    host = torch.empty(tuple(reversed(shape)), dtype=_torch_dtype(spec["dtype"]), pin_memory=True)
+    host.copy_(torch.from_numpy(np.ascontiguousarray(synth(shape, spec["dtype"], spec["seed"]).T)))
+    out = torch.empty_like(host, pin_memory=True)
+    a = sb.StencilArray(host.numpy().T, sb.Moore(1), boundary=sb.Wrap())
+    dst = out.numpy().T
+    sb.mapstencil_(sb.Life(), dst, a)  # warm-up (allocates the device scratch)
+    sb.mapstencil_(sb.Life(), dst, a)
+    n = 5
+    t0 = time.perf_counter()
+    for _ in range(n):
+        sb.mapstencil_(sb.Life(), dst, a)  # blocking call: returns when dst is on the host
+    el = time.perf_counter() - t0
+    nbytes = int(np.prod(shape)) * np.dtype(spec["dtype"]).itemsize
+    return {"value": int(np.prod(shape)) * n / el / 1e9, "unit": "Gcell-updates/s", "h2d_bytes_per_step": nbytes,
+            "d2h_bytes_per_step": nbytes, "steps": n,
+            "how": "mapstencil_(Life(), dest, StencilArray(host array)) -> sb200_gather_host; wall clock around "
+                   "blocking calls, pinned host buffers, H2D + sweep + D2H inside every step"}
+
+
+if __name__ == "__main__":
+    main()

@@ -479,8 +479,8 @@ int32_t sb200_gather_host(const sb200_desc* d, const void* src_host, void* dst_h
     const long long nlast = d->size[last];
     size_t plane_src = elsize(d->eltype), plane_dst = elsize(d->out_eltype);
     for (int a = 0; a < last; a++) { plane_src *= (size_t)d->src_ext[a]; plane_dst *= (size_t)d->dst_ext[a]; }
-    const bool chunkable = !has_region && !needs_halo(d) && d->ndim >= 2 &&
-                           (d->src_off[last] > 0 || d->boundary[last] == SB200_REMOVE) && nlast >= 64 &&
+    const bool wrap_last = d->src_off[last] == 0 && d->boundary[last] == SB200_WRAP;
+    const bool chunkable = !has_region && !needs_halo(d) && d->ndim >= 2 && nlast >= 64 &&
                            sb_ >= (size_t)(8u << 20) && d->dst_off[last] == 0 && d->dst_ext[last] == d->size[last];
     if (!chunkable) {
         cudaStream_t st = g_hs.st[0];
@@ -499,6 +499,11 @@ int32_t sb200_gather_host(const sb200_desc* d, const void* src_host, void* dst_h
     const int R = d->radius, off = d->src_off[last];
     long long sent_hi = 0;  // source planes [0, sent_hi) of the parent are on the device
     const long long src_planes = d->src_ext[last];
+    // Wrap on the slowest axis: the first chunk also reads the last R planes (Reflect mirrors into planes the
+    // chunk owns anyway, Remove reads padval).
+    if (wrap_last && nchunks > 1)
+        SB_CUDA(cudaMemcpyAsync((char*)g_hs.a + (src_planes - R) * plane_src, (const char*)src_host + (src_planes - R) * plane_src,
+                                (size_t)R * plane_src, cudaMemcpyHostToDevice, g_hs.st[0]));
     for (int c = 0; c < nchunks; c++) {
         const long long lo = nlast * c / nchunks, hi = nlast * (c + 1) / nchunks;
         // source planes this chunk reads: parent planes [lo+off-R, hi+off+R) clipped

@@ -1,0 +1,202 @@
+"""GPU tests through the public host API (the Python mirror of the Julia API), written to read like the
+reference's own test/array.jl and test/stencils.jl, plus the host-buffer C-ABI entry points."""
+import operator
+
+import numpy as np
+import pytest
+
+import stencils_b200 as sb
+from oracle import np_restatement as npr
+from stencils_b200 import _abi as A
+from stencils_b200.synth import synth_np, synth_torch
+from tests.util import bits_equal
+
+pytestmark = pytest.mark.gpu
+
+
+def dev(a):
+    import torch
+    a = np.asfortranarray(a)
+    return torch.from_numpy(np.ascontiguousarray(a.T)).cuda().permute(*reversed(range(a.ndim)))
+
+
+def host(t):
+    return np.asarray(t.cpu().numpy() if hasattr(t, "cpu") else t)
+
+
+def r2d():
+    return np.outer(np.arange(1.0, 6.0), np.arange(100.0, 106.0))  # (1.0:5.0) * (100.0:105.0)'
+
+
+def _check(got, g):
+    want = np.array(g["v"])
+    if g["approx"]:
+        np.testing.assert_allclose(host(got), want, rtol=1e-8)
+    else:
+        np.testing.assert_array_equal(host(got), want)
+
+
+@pytest.mark.parametrize("where", ["device", "host"])
+def test_mapstencil_remove_use(goldens, where):
+    """test/array.jl:121-162"""
+    put = dev if where == "device" else np.asfortranarray
+    M = goldens["mapstencil"]
+    r = r2d()
+    W = sb.Window(1, 2)
+    A_ = sb.StencilArray(put(r), W, padding=sb.Conditional(), boundary=sb.Remove(0.0))
+    B = sb.StencilArray(put(r), W, padding=sb.Halo("out"), boundary=sb.Remove(0.0))
+    C = sb.StencilArray(put(r.copy()), W, padding=sb.Halo("in"), boundary=sb.Use())
+    SA = sb.SwitchingStencilArray(put(r.copy()), W, padding=sb.Conditional(), boundary=sb.Remove(0.0))
+    SB = sb.SwitchingStencilArray(put(r.copy()), W, padding=sb.Halo("out"), boundary=sb.Remove(0.0))
+    SC = sb.SwitchingStencilArray(put(r.copy()), W, padding=sb.Halo("in"), boundary=sb.Use())
+    A1, B1, C1 = sb.mapstencil(sb.mean, A_), sb.mapstencil(sb.mean, B), sb.mapstencil(sb.mean, C)
+    SA1, SB1, SC1 = sb.mapstencil_(sb.mean, SA), sb.mapstencil_(sb.mean, SB), sb.mapstencil_(sb.mean, SC)
+    assert SA1 is not SA and SA1.source is SA.dest  # switch(A) swaps the buffers, src/array.jl:610-611
+    for x in (B1, SA1, SB1):
+        np.testing.assert_array_equal(host(A1), np.asarray(x))
+    _check(A1, M["remove_mean_2d"])
+    np.testing.assert_array_equal(host(C1), np.asarray(SC1))
+    np.testing.assert_array_equal(host(A1)[1:-1, 1:-1], host(C1))
+    np.testing.assert_array_equal(host(C1), r[1:-1, 1:-1])
+    A1, B1, C1 = sb.mapstencil(sb.sum, A_), sb.mapstencil(sb.sum, B), sb.mapstencil(sb.sum, C)
+    np.testing.assert_array_equal(host(A1), host(B1))
+    _check(C1, M["remove_sum_2d_interior"])
+    np.testing.assert_array_equal(host(A1)[1:-1, 1:-1], host(C1))
+
+
+@pytest.mark.parametrize("bc,key", [(sb.Wrap, "wrap"), (sb.Reflect, "reflect")])
+def test_mapstencil_wrap_reflect(goldens, bc, key):
+    """test/array.jl:164-259"""
+    M = goldens["mapstencil"]
+    x = np.arange(1.0, 6.0)
+    s1 = sb.Window(1, 1)
+    A1 = sb.mapstencil(sb.mean, sb.StencilArray(dev(x), s1, padding=sb.Conditional(), boundary=bc()))
+    B1 = sb.mapstencil(sb.mean, sb.StencilArray(dev(x), s1, padding=sb.Halo("out"), boundary=bc()))
+    C1 = sb.mapstencil(sb.mean, sb.StencilArray(dev(x.copy()), s1, padding=sb.Halo("in"), boundary=bc()))
+    SC1 = sb.mapstencil_(sb.mean, sb.SwitchingStencilArray(dev(x.copy()), s1, padding=sb.Halo("in"), boundary=bc()))
+    np.testing.assert_array_equal(host(A1), host(B1))
+    _check(A1, M[f"{key}_mean_1d"])
+    _check(C1, M[f"{key}_mean_1d_halo_in"])
+    np.testing.assert_array_equal(host(C1), np.asarray(SC1))
+    r = r2d()
+    s2 = sb.Window(1, 2)
+    A1 = sb.mapstencil(sb.mean, sb.StencilArray(dev(r), s2, padding=sb.Conditional(), boundary=bc()))
+    B1 = sb.mapstencil(sb.mean, sb.StencilArray(dev(r), s2, padding=sb.Halo("out"), boundary=bc()))
+    SB1 = sb.mapstencil_(sb.mean, sb.SwitchingStencilArray(dev(r.copy()), s2, padding=sb.Halo("out"), boundary=bc()))
+    np.testing.assert_array_equal(host(A1), host(B1))
+    np.testing.assert_array_equal(host(A1), np.asarray(SB1))
+    _check(A1, M[f"{key}_mean_2d"])
+    # mapstencil(f, hood, A; kw...) form incl. the shrunken Halo{:in} dest (src/gatherstencil.jl:22-39)
+    res_in = sb.mapstencil(sb.mean, s2, dev(r.copy()), boundary=bc(), padding=sb.Halo("in"))
+    assert tuple(res_in.shape) == (3, 4)
+    np.testing.assert_array_equal(host(sb.mapstencil(sb.mean, s2, dev(r), boundary=bc())), host(A1))
+
+
+def test_lower_dim_stencils_and_named_maps(goldens):
+    """test/array.jl:81-86,109-118; test/stencils.jl:205-239"""
+    rng = np.random.default_rng(0)
+    r = rng.random((100, 100))
+    a = sb.mapstencil(sb.sum, sb.StencilArray(dev(r), sb.Vertical(1, 2), boundary=sb.Remove(0.0)))
+    b = sb.mapstencil(sb.sum, sb.StencilArray(dev(r), sb.Window(1, 1), boundary=sb.Remove(0.0)))
+    np.testing.assert_array_equal(host(a), host(b))
+    r3 = rng.random((40, 30, 20))
+    pos = sb.Positional((-1, -1, 0), (0, -1, 0), (1, -1, 0), (-1, 0, 0), (0, 0, 0), (1, 0, 0), (-1, 1, 0), (0, 1, 0), (1, 1, 0))
+    np.testing.assert_array_equal(host(sb.mapstencil(sb.sum, sb.StencilArray(dev(r3), sb.Window(1, 2), boundary=sb.Remove(0.0)))),
+                                  host(sb.mapstencil(sb.sum, sb.StencilArray(dev(r3), pos, boundary=sb.Remove(0.0)))))
+    win = np.array(goldens["fills"]["win_5x5"]["v"], dtype=np.int64)
+    N = goldens["named_maps"]
+    g = N["n_plus_w_plus_center"]  # s.n + s.w + center(s)
+    out = sb.mapstencil(sb.sum, sb.StencilArray(dev(win), sb.NamedStencil(n=(-1, 0), w=(1, 0), c=(0, 0))))
+    np.testing.assert_array_equal(host(out), np.array(g["golden_minus_input"]) + win)
+    ns = sb.NamedStencil(sb.Cardinal(1))  # s.W + s.S
+    sel = sb.NamedStencil(W=ns.offsets()[ns.names.index("W")], S=ns.offsets()[ns.names.index("S")])
+    np.testing.assert_array_equal(host(sb.mapstencil(sb.sum, sb.StencilArray(dev(win), sel))), np.array(N["cardinal_W_plus_S"]["v"]))
+    ns = sb.NamedStencil(sb.Ordinal(1))  # s.NE + s.NW
+    sel = sb.NamedStencil(NE=ns.offsets()[ns.names.index("NE")], NW=ns.offsets()[ns.names.index("NW")])
+    np.testing.assert_array_equal(host(sb.mapstencil(sb.sum, sb.StencilArray(dev(win), sel))), np.array(N["ordinal_NE_plus_NW"]["v"]))
+
+
+def test_kernelproduct(goldens):
+    """test/stencils.jl:268-304 and the README sharpen example (README.md:205-228)."""
+    hood = np.arange(1, 10, dtype=np.int64).reshape(3, 3, order="F")
+    k = sb.Kernel(sb.Window(1, 2), np.arange(1, 10).reshape(3, 3, order="F"))
+    out = sb.mapstencil(sb.kernelproduct, sb.StencilArray(dev(hood), k))
+    assert host(out)[1, 1] == 285
+    k = sb.Kernel(sb.Positional((0, -1), (-1, 0), (1, 0), (0, 1)), np.arange(1, 5))
+    assert host(sb.mapstencil(sb.kernelproduct, sb.StencilArray(dev(hood), k)))[1, 1] == 60
+    rng = np.random.default_rng(1)
+    r = rng.random((200, 150))
+    sharpen = np.array([[0, -1, 0], [-1, 5, -1], [0, -1, 0]], dtype=np.float64)
+    out = host(sb.mapstencil(sb.kernelproduct, sb.StencilArray(dev(r), sb.Kernel(sb.Window(1), sharpen))))
+    want = npr.gather(r, npr.offsets("Window", 1, 2), 1, "remove", "cond", "kerneldot", weights=sharpen)
+    bits_equal(np.asfortranarray(out), np.asfortranarray(want))
+
+
+def test_scatterstencil(goldens):
+    """test/array.jl:385-493"""
+    src = np.ones((5, 5))
+    d = sb.scatterstencil_(sb.ScatterWeights(0.1), operator.add, dev(np.zeros((5, 5))),
+                           sb.StencilArray(dev(src), sb.Moore(1), boundary=sb.Remove(0.0)))
+    d = host(d)
+    assert d[2, 2] == pytest.approx(0.8) and d[0, 2] == pytest.approx(0.5) and d[2, 0] == pytest.approx(0.5)
+    assert d[0, 0] == pytest.approx(0.3) and d[4, 4] == pytest.approx(0.3)
+    src = np.fromfunction(lambda i, j: i + j + 2.0, (5, 5))
+    d = host(sb.scatterstencil_(sb.ScatterCenterWeights(1.0), max, dev(np.zeros((5, 5))),
+                                sb.StencilArray(dev(src), sb.Moore(1), boundary=sb.Remove(0.0))))
+    assert d[2, 2] == 8.0 and d[0, 0] == 4.0
+    d = host(sb.scatterstencil_(sb.ScatterWeights(0.25), operator.add, dev(np.zeros((5, 5))),
+                                sb.StencilArray(dev(np.ones((5, 5))), sb.VonNeumann(1), boundary=sb.Remove(0.0))))
+    assert d[2, 2] == pytest.approx(1.0) and d[0, 2] == pytest.approx(0.75) and d[0, 0] == pytest.approx(0.5)
+    d = host(sb.scatterstencil_(sb.ScatterWeights(0.01), operator.add, dev(np.zeros((7, 7))),
+                                sb.StencilArray(dev(np.ones((7, 7))), sb.Moore(2), boundary=sb.Remove(0.0))))
+    assert d[3, 3] == pytest.approx(0.24)
+    ssa = sb.SwitchingStencilArray(dev(np.ones((5, 5))), sb.Moore(1), boundary=sb.Remove(0.0))
+    res = sb.scatterstencil_(sb.ScatterWeights(0.1), operator.add, ssa)
+    assert res is not ssa and np.asarray(res)[2, 2] == pytest.approx(0.8)
+
+
+def test_unsupported_function_raises_on_gpu_box_too():
+    a = sb.StencilArray(dev(np.zeros((8, 8))), sb.Window(1))
+    with pytest.raises(sb.ArgumentError, match="no fallback"):
+        sb.mapstencil(lambda h: 0.0, a)
+
+
+def test_synth_generators_agree():
+    for dt in (np.uint8, np.float32, np.float64):
+        a = synth_np((300, 70), dt, 0x5EED0002, lo=999)
+        b = synth_torch((300, 70), dt, 0x5EED0002, "cuda", lo=999)
+        bits_equal(np.asfortranarray(host(b)), a)
+
+
+@pytest.mark.parametrize("bc", [A.REMOVE, A.WRAP, A.REFLECT])
+def test_gather_host_chunked_pipeline(orc, bc):
+    """sb200_gather_host (H2D -> sweep -> D2H pipelined over 16 chunks of the slowest axis) == oracle."""
+    import torch
+    from stencils_b200._desc import build_desc
+    W, H = 4096, 2304  # 9 MiB of uint8: above the 8 MiB chunking threshold
+    g = synth_np((W, H), np.uint8, 7)
+    h = build_desc(size=(W, H), eltype=A.U8, out_eltype=A.U8, offsets=npr.offsets("Moore", 1, 2), radius=1,
+                   boundary=bc, reducer=A.LIFE)
+    want = orc.gather(h, g)
+    src = torch.from_numpy(np.ascontiguousarray(g.T)).pin_memory()
+    dst = torch.zeros_like(src).pin_memory()
+    A.check(A.lib().sb200_gather_host(h.ptr(), src.data_ptr(), dst.data_ptr()))
+    bits_equal(np.asfortranarray(dst.numpy().T), want)
+    f = synth_np((1024, 1200), np.float64, 8)
+    h = build_desc(size=f.shape, eltype=A.F64, out_eltype=A.F64, offsets=npr.offsets("Window", 1, 2), radius=1,
+                   boundary=bc, reducer=A.MEAN)
+    want = orc.gather(h, f)
+    out = np.zeros_like(f, order="F")
+    A.check(A.lib().sb200_gather_host(h.ptr(), f.ctypes.data, out.ctypes.data))  # pageable host memory works too
+    bits_equal(out, want)
+
+
+def test_iterate_host(orc):
+    from stencils_b200._desc import build_desc
+    g = synth_np((512, 300), np.uint8, 9)
+    S = sb.SwitchingStencilArray(g.copy(order="F"), sb.Moore(1), boundary=sb.Wrap())
+    S = sb.iterate_(sb.Life(), S, 7)
+    h = build_desc(size=g.shape, eltype=A.U8, out_eltype=A.U8, offsets=npr.offsets("Moore", 1, 2), radius=1,
+                   boundary=A.WRAP, reducer=A.LIFE)
+    want = orc.iterate(h, g.copy(order="F"), np.zeros_like(g, order="F"), 7)
+    bits_equal(np.asfortranarray(np.asarray(S)), want)
