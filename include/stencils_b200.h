@@ -157,6 +157,7 @@ typedef struct sb200_desc {
 #define SB200_FLAG_FORCE_GENERIC 1 /* bypass specialised kernels (testing: generic vs fast parity) */
 #define SB200_FLAG_ZERO_DEST 2     /* scatter: treat dest as zero-filled (Switching forms, src/scatterstencil.jl:119,130) */
 #define SB200_FLAG_NO_TMA 4        /* testing: use the non-TMA variant of a specialised kernel */
+#define SB200_FLAG_CELLS_01 8      /* LIFE on UInt8: the caller guarantees every source cell is 0 or 1 */
 
 /* ---- library ---- */
 int32_t sb200_version(void);

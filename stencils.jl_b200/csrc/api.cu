@@ -428,10 +428,15 @@ int32_t sb200_iterate(const sb200_desc* d, void* buf_a, void* buf_b, int32_t nst
     if (d->eltype != d->out_eltype) { set_error("iterated sweeps need a reducer that preserves the element type"); return SB200_EUNSUPPORTED; }
     void *s = buf_a, *t = buf_b;
     const bool halo = needs_halo(d);
+    // After the first Life step on UInt8 the source is the kernel's own 0/1 output: later steps may skip the
+    // "cell != 0" normalisation (the Remove padval is normalised separately, and rings only exist on axes the
+    // packed kernel does not accept).
+    sb200_desc later = *d;
+    if (d->reducer == SB200_LIFE && d->eltype == SB200_U8) later.flags |= SB200_FLAG_CELLS_01;
     for (int i = 0; i < nsteps; i++) {
         int rc;
         if (halo && (rc = sb200_update_halo(d, s, stream))) return rc;
-        if ((rc = do_gather(d, s, t, (cudaStream_t)stream))) return rc;
+        if ((rc = do_gather(i == 0 ? d : &later, s, t, (cudaStream_t)stream))) return rc;
         void* tmp = s; s = t; t = tmp;
     }
     return SB200_OK;

@@ -2,15 +2,19 @@
 //
 // Reference path being replaced: gatherstencil_kernel! (src/gatherstencil.jl:105-109) applied with a
 // Moore{1,2} stencil (src/stencils/moore.jl) to a UInt8/Bool grid, one work-item per cell, 8 scattered loads
-// each. Here one thread owns 16 consecutive cells (one 128-bit load / store per row) and walks down a band
-// of rows keeping the horizontal 3-sums of the previous two rows in registers, so every source row is
-// loaded once per band. Cells stay packed four to a 32-bit word: byte-wise sums never exceed 9, so plain
-// integer adds cannot carry between bytes. Left/right neighbours come from funnel shifts; the words of the
-// neighbouring threads come from warp shuffles. Algorithmic traffic: 1 B read + 1 B written per cell.
+// each. Here one thread owns 16 consecutive cells (one 128-bit load / store per row) and walks down a run of
+// rows keeping the horizontal 3-sums of the previous two rows in registers, so every source row is loaded
+// once per run. Cells stay packed four to a 32-bit word: byte-wise sums never exceed 9, so plain integer
+// adds cannot carry between bytes. Left/right neighbours come from funnel shifts (ptxas fuses shift+add into
+// LEA.HI); the words of the neighbouring threads come from warp shuffles; only lanes 0 and 31 touch memory
+// for their outer neighbour (one byte). The next row is prefetched while the current one is evaluated.
+// Work is split into equal runs of rows per warp over the linearised (column group, row) space, so all
+// resident warps finish together. Algorithmic traffic: 1 B read + 1 B written per cell.
 //
-// Handles: eltype Bool/UInt8, 2-D, any of Remove/Wrap/Reflect on the fly (Conditional) or a ring/ghost rows
+// Handles: eltype Bool/UInt8, 2-D, any of Remove/Wrap/Reflect on the fly (Conditional) or a ring / ghost rows
 // (src_off > 0) on axis 1; axis 0 must be unpadded with 16-byte-aligned rows. Everything else is declined
 // and goes to gather_generic.
+#include <algorithm>
 #include "common.cuh"
 
 namespace sb {
@@ -21,12 +25,12 @@ struct LifeParams {
     long long spitch, dpitch;  // bytes per row of the parents
     int W, H;                  // logical size (axis 0 = W contiguous)
     int ncols;                 // W / 16
+    int colgroups;             // ceil(ncols / 32)
     int soff1, doff1;          // ring / ghost rows on axis 1
     int bc0, bc1;              // boundary per axis
     unsigned pad01;            // Remove: (padval != 0)
-    int y_lo, y_hi;            // output rows [y_lo, y_hi)
-    int RY;                    // rows per band
-    int nbands;
+    int y_lo, rows;            // output rows [y_lo, y_lo + rows)
+    int nruns;                 // the rows are split into nruns equal runs; a warp owns one (column group, run)
     unsigned born, survive;
 };
 
@@ -34,60 +38,81 @@ struct LifeParams {
 __device__ __forceinline__ unsigned nz_bytes(unsigned w) {
     return ((((w & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | w) >> 7) & 0x01010101u;
 }
-// 0/1 per byte: byte == 0, valid for bytes <= 0x70
-__device__ __forceinline__ unsigned eqz_small(unsigned x) {
-    return (((x + 0x0F0F0F0Fu) >> 4) & 0x01010101u) ^ 0x01010101u;
-}
+// 0/1 per byte: byte == 0, valid for bytes <= 0x10
+__device__ __forceinline__ unsigned eqz_small(unsigned x) { return ((0x10101010u - x) >> 4) & 0x01010101u; }
 
 struct Row {
-    unsigned h[4];  // horizontal 3-sums (left + centre + right), per byte
-    unsigned c[4];  // centre cells as 0/1
+    unsigned h0, h1, h2, h3;  // horizontal 3-sums (left + centre + right), per byte
+    unsigned c0, c1, c2, c3;  // centre cells as 0/1
+};
+struct Raw {
+    uint4 v;
+    unsigned bl, br;  // the cells left of byte 0 and right of byte 15 (raw bytes)
 };
 
-template <bool IS_BOOL>
-__device__ __forceinline__ void load_row(const LifeParams& p, int r, int col, bool active, int lane, Row& out) {
-    // map the source row
-    bool oob_row = false;
+// Per-thread constants of the column this thread owns (hoisted out of the row loops).
+struct Col {
+    long long x_off;     // byte offset of the thread's 16 cells in a row
+    int l_edge, r_edge;  // array-edge columns under Wrap / Reflect: byte offset in the row of the outer neighbour
+    bool active;         // column exists (inactive lanes shadow the last column and do not store)
+    bool first, last;    // first / last column of the array
+    bool edge_mem;       // Wrap / Reflect on axis 0: the array-edge neighbour is a cell of the same row
+    bool edge_warp;      // warp-uniform: this column group contains the first or the last column
+    unsigned pad;        // outer neighbour when it is the Remove padval
+};
+
+// tp = row pointer + x_off (per thread); rowp = row pointer (warp-uniform). Every thread loads its 16 cells and
+// its two outer neighbour bytes (same cache lines, L1 hits), so the steady state needs no cross-lane traffic.
+__device__ __forceinline__ Raw load_raw(const uint8_t* __restrict__ tp, const uint8_t* __restrict__ rowp, const Col& c) {
+    Raw r;
+    r.v = __ldg(reinterpret_cast<const uint4*>(tp));
+    r.bl = c.pad; r.br = c.pad;
+    if (!c.first) r.bl = __ldg(tp - 1);
+    if (!c.last) r.br = __ldg(tp + 16);
+    if (c.edge_warp && c.edge_mem) {  // warp-uniform branch
+        if (c.first) r.bl = __ldg(rowp + c.l_edge);
+        if (c.last) r.br = __ldg(rowp + c.r_edge);
+    }
+    return r;
+}
+
+template <bool CELLS01>
+__device__ __forceinline__ Row finish_row(const Raw& r, const Col& c) {
+    unsigned w0 = r.v.x, w1 = r.v.y, w2 = r.v.z, w3 = r.v.w, bl = r.bl, br = r.br;
+    if (!CELLS01) {
+        w0 = nz_bytes(w0); w1 = nz_bytes(w1); w2 = nz_bytes(w2); w3 = nz_bytes(w3);
+        bl = min(bl, 1u); br = min(br, 1u);
+    }
+    Row o;
+    o.c0 = w0; o.c1 = w1; o.c2 = w2; o.c3 = w3;
+    o.h0 = ((w0 << 8) + bl) + w0 + __funnelshift_r(w0, w1, 8);
+    o.h1 = __funnelshift_l(w0, w1, 8) + w1 + __funnelshift_r(w1, w2, 8);
+    o.h2 = __funnelshift_l(w1, w2, 8) + w2 + __funnelshift_r(w2, w3, 8);
+    o.h3 = __funnelshift_l(w2, w3, 8) + w3 + __funnelshift_r(w3, br, 8);
+    return o;
+}
+
+// A source row addressed through the boundary condition of axis 1 (used for the first and last row of a run).
+template <bool CELLS01>
+__device__ __forceinline__ Row mapped_row(const LifeParams& p, int r, const Col& c) {
     long long prow;
     if (p.soff1 > 0) {
-        prow = (long long)r + p.soff1;
+        prow = (long long)r + p.soff1;  // ring / ghost rows: read straight through
     } else if (r < 0 || r >= p.H) {
         if (p.bc1 == SB200_WRAP) prow = r < 0 ? r + p.H : r - p.H;
         else if (p.bc1 == SB200_REFLECT) prow = r < 0 ? -r : 2 * (p.H - 1) - r;
-        else { prow = 0; oob_row = true; }
+        else {  // Remove: the whole row, and what lies left and right of it, is padval
+            const unsigned pv = p.pad01 * 0x01010101u;
+            Row o;
+            o.c0 = o.c1 = o.c2 = o.c3 = pv;
+            o.h0 = o.h1 = o.h2 = o.h3 = pv * 3u;
+            return o;
+        }
     } else {
         prow = r;
     }
-    unsigned w0 = 0, w1 = 0, w2 = 0, w3 = 0, wl = 0, wr = 0;
-    if (oob_row) {  // Remove: the whole row (and what lies left/right of it) is padval
-        const unsigned pv = p.pad01 * 0x01010101u;
-        out.c[0] = out.c[1] = out.c[2] = out.c[3] = pv;
-        out.h[0] = out.h[1] = out.h[2] = out.h[3] = pv * 3u;
-        return;
-    }
     const uint8_t* rowp = p.src + prow * p.spitch;
-    const bool first = col == 0, last = col == p.ncols - 1;
-    if (active) {
-        const uint4 v = __ldg(reinterpret_cast<const uint4*>(rowp) + col);
-        w0 = v.x; w1 = v.y; w2 = v.z; w3 = v.w;
-        // words owned by another warp (or across the array edge)
-        if (lane == 0 && !first) wl = __ldg(reinterpret_cast<const unsigned*>(rowp) + col * 4 - 1);
-        if ((lane == 31 || last) && !last) wr = __ldg(reinterpret_cast<const unsigned*>(rowp) + col * 4 + 4);
-        if (first && p.bc0 == SB200_WRAP) wl = __ldg(reinterpret_cast<const unsigned*>(rowp) + p.ncols * 4 - 1);
-        if (last && p.bc0 == SB200_WRAP) wr = __ldg(reinterpret_cast<const unsigned*>(rowp));
-    }
-    if (!IS_BOOL) { w0 = nz_bytes(w0); w1 = nz_bytes(w1); w2 = nz_bytes(w2); w3 = nz_bytes(w3); wl = nz_bytes(wl); wr = nz_bytes(wr); }
-    const unsigned sl = __shfl_up_sync(0xffffffffu, w3, 1);
-    const unsigned sr = __shfl_down_sync(0xffffffffu, w0, 1);
-    if (lane != 0) wl = sl;
-    if (lane != 31 && !last) wr = sr;
-    if (first && p.bc0 != SB200_WRAP) wl = (p.bc0 == SB200_REFLECT) ? (w0 << 16) & 0xFF000000u : p.pad01 << 24;
-    if (last && p.bc0 != SB200_WRAP) wr = (p.bc0 == SB200_REFLECT) ? (w3 >> 16) & 0xFFu : p.pad01;
-    out.c[0] = w0; out.c[1] = w1; out.c[2] = w2; out.c[3] = w3;
-    out.h[0] = __funnelshift_l(wl, w0, 8) + w0 + __funnelshift_r(w0, w1, 8);
-    out.h[1] = __funnelshift_l(w0, w1, 8) + w1 + __funnelshift_r(w1, w2, 8);
-    out.h[2] = __funnelshift_l(w1, w2, 8) + w2 + __funnelshift_r(w2, w3, 8);
-    out.h[3] = __funnelshift_l(w2, w3, 8) + w3 + __funnelshift_r(w3, wr, 8);
+    return finish_row<CELLS01>(load_raw(rowp + c.x_off, rowp, c), c);
 }
 
 // CONWAY: B3/S23 via the (n | c) == 3 identity; otherwise the general born/survive table.
@@ -108,36 +133,110 @@ __device__ __forceinline__ unsigned rule(unsigned t, unsigned c, unsigned born, 
     return out;
 }
 
-template <bool IS_BOOL, bool CONWAY>
-__global__ void __launch_bounds__(256) life_swar_kernel(LifeParams p) {
+// out(row of b) from the rows above (a), at (b) and below (n); tp = dest row pointer + x_off.
+template <bool CONWAY>
+__device__ __forceinline__ void emit(const LifeParams& p, const Col& c, uint8_t* __restrict__ tp, const Row& a,
+                                     const Row& b, const Row& n) {
+    uint4 o;
+    o.x = rule<CONWAY>(a.h0 + b.h0 + n.h0, b.c0, p.born, p.survive);
+    o.y = rule<CONWAY>(a.h1 + b.h1 + n.h1, b.c1, p.born, p.survive);
+    o.z = rule<CONWAY>(a.h2 + b.h2 + n.h2, b.c2, p.born, p.survive);
+    o.w = rule<CONWAY>(a.h3 + b.h3 + n.h3, b.c3, p.born, p.survive);
+    if (c.active) *reinterpret_cast<uint4*>(tp) = o;
+}
+
+template <bool CELLS01, bool CONWAY>
+__global__ void __launch_bounds__(256) life_swar_kernel(const LifeParams p) {
     const int lane = threadIdx.x & 31;
-    const int warps_per_block = blockDim.x >> 5;
-    const int colgroups = (p.ncols + 31) >> 5;
-    const long long ntasks = (long long)colgroups * p.nbands;
-    for (long long task = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5); task < ntasks;
-         task += (long long)gridDim.x * warps_per_block) {
-        const int cg = (int)(task % colgroups), band = (int)(task / colgroups);
-        const int col = cg * 32 + lane;
-        const bool active = col < p.ncols;
-        const int y0 = p.y_lo + band * p.RY;
-        const int y1 = min(y0 + p.RY, p.y_hi);
-        Row prev, cur, next;
-        load_row<IS_BOOL>(p, y0 - 1, col, active, lane, prev);
-        load_row<IS_BOOL>(p, y0, col, active, lane, cur);
-#pragma unroll 2
-        for (int y = y0; y < y1; y++) {
-            load_row<IS_BOOL>(p, y + 1, col, active, lane, next);
-            uint4 o;
-            o.x = rule<CONWAY>(prev.h[0] + cur.h[0] + next.h[0], cur.c[0], p.born, p.survive);
-            o.y = rule<CONWAY>(prev.h[1] + cur.h[1] + next.h[1], cur.c[1], p.born, p.survive);
-            o.z = rule<CONWAY>(prev.h[2] + cur.h[2] + next.h[2], cur.c[2], p.born, p.survive);
-            o.w = rule<CONWAY>(prev.h[3] + cur.h[3] + next.h[3], cur.c[3], p.born, p.survive);
-            if (active)
-                *(reinterpret_cast<uint4*>(p.dst + (long long)(y + p.doff1) * p.dpitch) + col) = o;
-            prev = cur;
-            cur = next;
+    const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    // Neighbouring warps own neighbouring column groups of the SAME run of rows, so at any moment the machine
+    // streams whole rows (contiguous DRAM pages); runs are equal, so all resident warps finish together.
+    const int run = (int)(warp / p.colgroups);
+    for (int cg = (int)(warp % p.colgroups); cg < p.colgroups && run < p.nruns; cg += p.colgroups) {
+        const int y0 = p.y_lo + (int)((long long)p.rows * run / p.nruns);
+        const int y1 = p.y_lo + (int)((long long)p.rows * (run + 1) / p.nruns);
+        if (y0 >= y1) break;
+
+        Col c;
+        const int col_raw = cg * 32 + lane;
+        c.active = col_raw < p.ncols;
+        const int col = c.active ? col_raw : p.ncols - 1;
+        c.first = col == 0;
+        c.last = col == p.ncols - 1;
+        c.x_off = (long long)col * 16;
+        c.edge_warp = cg == 0 || cg == p.colgroups - 1;
+        c.edge_mem = p.bc0 != SB200_REMOVE;
+        c.l_edge = p.bc0 == SB200_WRAP ? p.W - 1 : 1;
+        c.r_edge = p.bc0 == SB200_WRAP ? 0 : p.W - 2;
+        c.pad = p.pad01;
+
+        // Rows A, B, C rotate through the roles (above, centre, below) so the steady state moves no registers.
+        Row A = mapped_row<CELLS01>(p, y0 - 1, c);
+        Row B = mapped_row<CELLS01>(p, y0, c);
+        Row C;
+        const uint8_t* __restrict__ sp = p.src + (long long)(y0 + 1 + p.soff1) * p.spitch;  // row y+1 (uniform)
+        const uint8_t* __restrict__ st = sp + c.x_off;                                       // same, this thread
+        uint8_t* __restrict__ dt = p.dst + (long long)(y0 + p.doff1) * p.dpitch + c.x_off;  // dest row y, this thread
+        int n = y1 - 1 - y0;  // rows y0+1 .. y1-1 are ordinary in-run rows
+        if (n > 0) {
+            Raw r0 = load_raw(st, sp, c), r1, r2;
+            // steady state: three rows per trip, the load of row y+2 is in flight while row y is evaluated
+            while (n > 3) {
+                sp += p.spitch; st += p.spitch;
+                r1 = load_raw(st, sp, c);
+                C = finish_row<CELLS01>(r0, c);
+                emit<CONWAY>(p, c, dt, A, B, C);
+                dt += p.dpitch;
+                sp += p.spitch; st += p.spitch;
+                r2 = load_raw(st, sp, c);
+                A = finish_row<CELLS01>(r1, c);
+                emit<CONWAY>(p, c, dt, B, C, A);
+                dt += p.dpitch;
+                sp += p.spitch; st += p.spitch;
+                r0 = load_raw(st, sp, c);
+                B = finish_row<CELLS01>(r2, c);
+                emit<CONWAY>(p, c, dt, C, A, B);
+                dt += p.dpitch;
+                n -= 3;
+            }
+            // 1..3 ordinary rows left; r0 holds the first of them
+            while (true) {
+                const bool more = n > 1;
+                if (more) { sp += p.spitch; st += p.spitch; r1 = load_raw(st, sp, c); }
+                C = finish_row<CELLS01>(r0, c);
+                emit<CONWAY>(p, c, dt, A, B, C);
+                dt += p.dpitch;
+                A = B; B = C; r0 = r1;
+                if (!more) break;
+                n--;
+            }
         }
+        C = mapped_row<CELLS01>(p, y1, c);
+        emit<CONWAY>(p, c, dt, A, B, C);
     }
+}
+
+template <bool CELLS01, bool CONWAY> static int resident_blocks() {
+    static thread_local int cached_dev = -1, cached = 0;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev != cached_dev) {
+        int per_sm = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, life_swar_kernel<CELLS01, CONWAY>, 256, 0) != cudaSuccess || per_sm < 1)
+            per_sm = 4;
+        cached = per_sm * num_sms();
+        cached_dev = dev;
+    }
+    return cached;
+}
+
+template <bool CELLS01, bool CONWAY> static void launch(LifeParams& p, cudaStream_t st) {
+    const long long warps = (long long)resident_blocks<CELLS01, CONWAY>() * 8;
+    long long nruns = std::max<long long>(1, warps / p.colgroups);
+    nruns = std::min<long long>(nruns, std::max(1, p.rows / 8));  // at least 8 rows per run
+    p.nruns = (int)nruns;
+    const long long blocks = (nruns * p.colgroups + 7) / 8;
+    life_swar_kernel<CELLS01, CONWAY><<<(unsigned)blocks, 256, 0, st>>>(p);
 }
 
 int try_life_swar(const Plan& pl, const void* src, void* dst, cudaStream_t st) {
@@ -157,41 +256,21 @@ int try_life_swar(const Plan& pl, const void* src, void* dst, cudaStream_t st) {
     p.src = (const uint8_t*)src; p.dst = (uint8_t*)dst;
     p.spitch = d.src_ext[0]; p.dpitch = d.dst_ext[0];
     p.W = (int)d.size[0]; p.H = (int)d.size[1]; p.ncols = p.W / 16;
+    p.colgroups = (p.ncols + 31) / 32;
     p.soff1 = d.src_off[1]; p.doff1 = d.dst_off[1];
     p.bc0 = d.boundary[0]; p.bc1 = d.boundary[1];
     p.pad01 = (d.padval_bits & 0xFF) != 0;
-    p.y_lo = (int)pl.dd.lo[1]; p.y_hi = (int)(pl.dd.lo[1] + pl.dd.n[1]);
+    p.y_lo = (int)pl.dd.lo[1]; p.rows = (int)pl.dd.n[1];
     p.born = d.born_mask; p.survive = d.survive_mask;
     const bool conway = d.born_mask == (1u << 3) && d.survive_mask == ((1u << 2) | (1u << 3));
-    const bool is_bool = d.eltype == SB200_BOOL;
-
-    // Band height: trade halo re-reads (2 extra rows per band) against the tail of the last wave.
-    const int colgroups = (p.ncols + 31) / 32;
-    const int rows = p.y_hi - p.y_lo;
-    const long long resident = (long long)num_sms() * 48;  // warps in flight at ~40 registers/thread
-    int best_ry = 16;
-    double best_cost = 1e300;
-    for (int ry : {64, 48, 32, 24, 16, 8}) {
-        const long long tasks = (long long)colgroups * ((rows + ry - 1) / ry);
-        const long long waves = (tasks + resident - 1) / resident;
-        const double cost = (double)waves * (ry + 2);
-        if (cost < best_cost) { best_cost = cost; best_ry = ry; }
-    }
-    p.RY = best_ry;
-    p.nbands = (rows + p.RY - 1) / p.RY;
-    const long long ntasks = (long long)colgroups * p.nbands;
-    const int wpb = 8;
-    long long blocks = (ntasks + wpb - 1) / wpb;
-    blocks = std::min<long long>(blocks, (long long)num_sms() * 8);
-    if (is_bool) {
-        if (conway) life_swar_kernel<true, true><<<(unsigned)blocks, wpb * 32, 0, st>>>(p);
-        else life_swar_kernel<true, false><<<(unsigned)blocks, wpb * 32, 0, st>>>(p);
-    } else {
-        if (conway) life_swar_kernel<false, true><<<(unsigned)blocks, wpb * 32, 0, st>>>(p);
-        else life_swar_kernel<false, false><<<(unsigned)blocks, wpb * 32, 0, st>>>(p);
-    }
+    // Bool cells are 0/1 by type; UInt8 cells are 0/1 when the caller says so (sb200_iterate does for every
+    // step after the first, because the source is then this kernel's own output).
+    const bool cells01 = d.eltype == SB200_BOOL || (d.flags & SB200_FLAG_CELLS_01);
+    if (cells01) { if (conway) launch<true, true>(p, st); else launch<true, false>(p, st); }
+    else { if (conway) launch<false, true>(p, st); else launch<false, false>(p, st); }
     SB_LAUNCH_CHECK();
-    set_kernel_name(conway ? "life_swar_kernel<conway>" : "life_swar_kernel<table>");
+    set_kernel_name(conway ? (cells01 ? "life_swar_kernel<cells01,conway>" : "life_swar_kernel<u8,conway>")
+                           : (cells01 ? "life_swar_kernel<cells01,table>" : "life_swar_kernel<u8,table>"));
     return SB200_OK;
 }
 

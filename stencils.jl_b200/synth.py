@@ -1,6 +1,6 @@
 """Deterministic synthetic fields for benchmarks and parity tests: the value at linear
 (column-major) index i is hash-to-uniform(splitmix64(seed ^ i)). The NumPy and the torch (device) generators
-produce bit-identical values, so a full-size device field can be spot-checked against the CPU oracle."""
+produce bit-identical values, so tiles of a full-size device field can be regenerated on the host."""
 from __future__ import annotations
 
 import numpy as np
