@@ -16,6 +16,7 @@
 // and goes to gather_generic.
 #include <algorithm>
 #include "common.cuh"
+#include "tma.cuh"
 
 namespace sb {
 
@@ -239,6 +240,185 @@ template <bool CELLS01, bool CONWAY> static void launch(LifeParams& p, cudaStrea
     life_swar_kernel<CELLS01, CONWAY><<<(unsigned)blocks, 256, 0, st>>>(p);
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// TMA-fed variant. A CTA owns a strip of LT_WARPS*512 bytes of columns and streams down a run of rows. One
+// producer thread issues bulk copies (cp.async.bulk -> UBLKCP) of LT_CH source rows per stage into a ring of
+// LT_STAGES shared-memory stages and resolves the row boundary (Wrap / Reflect / ghost rows) and the Wrap
+// column halo purely by choosing source addresses; full/empty mbarriers hand stages back and forth. The
+// consumer warps read their 16 cells + 2 neighbour bytes from shared memory, keep the rolling 3-row state in
+// registers and store results with 128-bit coalesced stores. Bytes in flight are set by the ring
+// (LT_STAGES * LT_CH * 4 KiB per CTA), not by registers.
+constexpr int LT_WARPS = 8;                    // consumer warps per CTA
+constexpr int LT_BXB = LT_WARPS * 32 * 16;     // strip width in bytes (4096)
+constexpr int LT_ROWB = LT_BXB + 32;           // shared-memory row: 16 B left halo | strip | 16 B right halo
+constexpr int LT_CH = 6;                       // source rows per stage (multiple of 3: the row rotation closes)
+constexpr int LT_STAGES = 4;
+constexpr int LT_SMEM = 128 + LT_STAGES * LT_CH * LT_ROWB;
+
+struct LifeTmaParams {
+    LifeParams lp;
+    int nstrips, nruns;
+};
+
+// source row r (logical) -> parent row, or -1 for a Remove pad row
+__device__ __forceinline__ long long life_map_row(const LifeParams& p, int r) {
+    if (p.soff1 > 0) return (long long)r + p.soff1;
+    if (r >= 0 && r < p.H) return r;
+    if (p.bc1 == SB200_WRAP) return r < 0 ? r + p.H : r - p.H;
+    if (p.bc1 == SB200_REFLECT) return r < 0 ? -r : 2 * (p.H - 1) - r;
+    return -1;
+}
+
+template <bool CELLS01, bool CONWAY>
+__global__ void __launch_bounds__((LT_WARPS + 1) * 32) life_tma_kernel(const LifeTmaParams q) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const LifeParams& p = q.lp;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem);
+    uint64_t* empty = full + LT_STAGES;
+    uint8_t* ring = smem + 128;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < LT_STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], LT_WARPS); }
+        mbar_fence_init();
+    }
+    __syncthreads();
+    const int ntasks = q.nstrips * q.nruns;
+    unsigned k = 0;  // stage-use counter, advances identically in the producer and in every consumer
+    for (int task = blockIdx.x; task < ntasks; task += gridDim.x) {
+        const int strip = task % q.nstrips, run = task / q.nstrips;
+        const int x0 = strip * LT_BXB;
+        const int wbytes = min(LT_BXB, p.W - x0);
+        const int y0 = p.y_lo + (int)((long long)p.rows * run / q.nruns);
+        const int y1 = p.y_lo + (int)((long long)p.rows * (run + 1) / q.nruns);
+        const int nsrc = y1 - y0 + 2;  // source rows y0-1 .. y1
+        const int nchunks = (nsrc + LT_CH - 1) / LT_CH;
+        if (warp == LT_WARPS) {
+            // ---------------- producer ----------------
+            if (lane == 0) {
+                const bool lh = x0 > 0 || p.bc0 == SB200_WRAP;              // left halo comes from memory
+                const bool rh = x0 + wbytes < p.W || p.bc0 == SB200_WRAP;   // right halo comes from memory
+                const int lx = x0 > 0 ? x0 - 16 : p.W - 16;
+                const int rx = x0 + wbytes < p.W ? x0 + wbytes : 0;
+                for (int c = 0; c < nchunks; c++, k++) {
+                    const int slot = k % LT_STAGES;
+                    mbar_wait(&empty[slot], ((k / LT_STAGES) & 1) ^ 1);
+                    uint8_t* sbase = ring + slot * (LT_CH * LT_ROWB);
+                    unsigned bytes = 0;
+                    long long prow[LT_CH];
+#pragma unroll
+                    for (int j = 0; j < LT_CH; j++) {
+                        const int i = c * LT_CH + j;
+                        prow[j] = i < nsrc ? life_map_row(p, y0 - 1 + i) : -1;
+                        if (prow[j] >= 0) bytes += wbytes + (lh ? 16 : 0) + (rh ? 16 : 0);
+                    }
+                    mbar_arrive_expect_tx(&full[slot], bytes);
+#pragma unroll
+                    for (int j = 0; j < LT_CH; j++) {
+                        if (prow[j] < 0) continue;
+                        const uint8_t* g = p.src + prow[j] * p.spitch;
+                        uint8_t* srow = sbase + j * LT_ROWB;
+                        bulk_g2s(srow + 16, g + x0, wbytes, &full[slot]);
+                        if (lh) bulk_g2s(srow, g + lx, 16, &full[slot]);
+                        if (rh) bulk_g2s(srow + 16 + wbytes, g + rx, 16, &full[slot]);
+                    }
+                }
+            } else {
+                k += nchunks;
+            }
+            continue;
+        }
+        // ---------------- consumers ----------------
+        const int xt = (warp * 32 + lane) * 16;  // byte offset of this thread's cells inside the strip
+        const bool active = xt < wbytes;
+        const bool first = x0 + xt == 0, last = x0 + xt + 16 == p.W;
+        const bool lfix = first && p.bc0 != SB200_WRAP, rfix = last && p.bc0 != SB200_WRAP;
+        const bool reflect = p.bc0 == SB200_REFLECT;
+        uint8_t* __restrict__ dt = p.dst + (long long)(y0 + p.doff1) * p.dpitch + x0 + xt;
+        const unsigned padrow = p.pad01 * 0x01010101u;
+        Row A, B, C;
+        A.h0 = A.h1 = A.h2 = A.h3 = B.h0 = B.h1 = B.h2 = B.h3 = 0;
+        B.c0 = B.c1 = B.c2 = B.c3 = 0;
+        // One source row: build its Row from shared memory (or the Remove pad row).
+        auto take = [&](const uint8_t* srow, bool is_pad, Row& o) {
+            if (is_pad) {
+                o.c0 = o.c1 = o.c2 = o.c3 = padrow;
+                o.h0 = o.h1 = o.h2 = o.h3 = padrow * 3u;
+                return;
+            }
+            const uint8_t* t = srow + 16 + xt;
+            const uint4 v = *reinterpret_cast<const uint4*>(t);
+            unsigned w0 = v.x, w1 = v.y, w2 = v.z, w3 = v.w, bl = t[-1], br = t[16];
+            if (lfix) bl = reflect ? (w0 >> 8) & 0xFFu : p.pad01;
+            if (rfix) br = reflect ? (w3 >> 16) & 0xFFu : p.pad01;
+            if (!CELLS01) {
+                w0 = nz_bytes(w0); w1 = nz_bytes(w1); w2 = nz_bytes(w2); w3 = nz_bytes(w3);
+                bl = min(bl, 1u); br = min(br, 1u);
+            }
+            o.c0 = w0; o.c1 = w1; o.c2 = w2; o.c3 = w3;
+            o.h0 = ((w0 << 8) + bl) + w0 + __funnelshift_r(w0, w1, 8);
+            o.h1 = __funnelshift_l(w0, w1, 8) + w1 + __funnelshift_r(w1, w2, 8);
+            o.h2 = __funnelshift_l(w1, w2, 8) + w2 + __funnelshift_r(w2, w3, 8);
+            o.h3 = __funnelshift_l(w2, w3, 8) + w3 + __funnelshift_r(w3, br, 8);
+        };
+        auto put = [&](int i, const Row& a, const Row& b, const Row& n) {  // i = index of the newest source row
+            if (i >= 2 && i < nsrc) {
+                uint4 o;
+                o.x = rule<CONWAY>(a.h0 + b.h0 + n.h0, b.c0, p.born, p.survive);
+                o.y = rule<CONWAY>(a.h1 + b.h1 + n.h1, b.c1, p.born, p.survive);
+                o.z = rule<CONWAY>(a.h2 + b.h2 + n.h2, b.c2, p.born, p.survive);
+                o.w = rule<CONWAY>(a.h3 + b.h3 + n.h3, b.c3, p.born, p.survive);
+                if (active) *reinterpret_cast<uint4*>(dt) = o;
+                dt += p.dpitch;
+            }
+        };
+        const bool may_pad = p.soff1 == 0 && p.bc1 == SB200_REMOVE;
+        for (int c = 0; c < nchunks; c++, k++) {
+            const int slot = k % LT_STAGES;
+            mbar_wait(&full[slot], (k / LT_STAGES) & 1);
+            const uint8_t* sbase = ring + slot * (LT_CH * LT_ROWB);
+            const int i0 = c * LT_CH;
+            // pad rows can only be the first row of the first chunk or the last source row
+            const bool pad_first = may_pad && c == 0 && y0 - 1 < 0;
+            const int pad_last_i = (may_pad && y1 >= p.H) ? nsrc - 1 : -1;
+#pragma unroll
+            for (int j = 0; j < LT_CH; j += 3) {
+                take(sbase + (j + 0) * LT_ROWB, (j == 0 && pad_first) || i0 + j + 0 == pad_last_i, C);
+                put(i0 + j + 0, A, B, C);
+                take(sbase + (j + 1) * LT_ROWB, i0 + j + 1 == pad_last_i, A);
+                put(i0 + j + 1, B, C, A);
+                take(sbase + (j + 2) * LT_ROWB, i0 + j + 2 == pad_last_i, B);
+                put(i0 + j + 2, C, A, B);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[slot]);
+        }
+    }
+}
+
+template <bool CELLS01, bool CONWAY> static int launch_tma(const LifeParams& p, cudaStream_t st) {
+    static thread_local int cfg_dev = -1, ctas_per_sm = 0;
+    int dev = 0;
+    SB_CUDA(cudaGetDevice(&dev));
+    if (dev != cfg_dev) {
+        SB_CUDA(cudaFuncSetAttribute(life_tma_kernel<CELLS01, CONWAY>, cudaFuncAttributeMaxDynamicSharedMemorySize, LT_SMEM));
+        int per_sm = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, life_tma_kernel<CELLS01, CONWAY>, (LT_WARPS + 1) * 32, LT_SMEM) != cudaSuccess || per_sm < 1)
+            per_sm = 1;
+        ctas_per_sm = per_sm;
+        cfg_dev = dev;
+    }
+    LifeTmaParams q;
+    q.lp = p;
+    q.nstrips = (p.W + LT_BXB - 1) / LT_BXB;
+    const long long ctas = (long long)ctas_per_sm * num_sms();
+    long long nruns = std::max<long long>(1, ctas / q.nstrips);
+    nruns = std::min<long long>(nruns, std::max(1, p.rows / 16));  // at least 16 rows per run
+    q.nruns = (int)nruns;
+    const long long grid = std::min<long long>(ctas, (long long)q.nstrips * q.nruns);
+    life_tma_kernel<CELLS01, CONWAY><<<(unsigned)grid, (LT_WARPS + 1) * 32, LT_SMEM, st>>>(q);
+    return SB200_OK;
+}
+
 int try_life_swar(const Plan& pl, const void* src, void* dst, cudaStream_t st) {
     const sb200_desc& d = pl.d;
     if (d.reducer != SB200_LIFE || d.ndim != 2) return -1;
@@ -266,6 +446,17 @@ int try_life_swar(const Plan& pl, const void* src, void* dst, cudaStream_t st) {
     // Bool cells are 0/1 by type; UInt8 cells are 0/1 when the caller says so (sb200_iterate does for every
     // step after the first, because the source is then this kernel's own output).
     const bool cells01 = d.eltype == SB200_BOOL || (d.flags & SB200_FLAG_CELLS_01);
+    const bool use_tma = !(d.flags & SB200_FLAG_NO_TMA) && p.W >= 512 && p.rows >= 16;
+    if (use_tma) {
+        int rc;
+        if (cells01) rc = conway ? launch_tma<true, true>(p, st) : launch_tma<true, false>(p, st);
+        else rc = conway ? launch_tma<false, true>(p, st) : launch_tma<false, false>(p, st);
+        if (rc) return rc;
+        SB_LAUNCH_CHECK();
+        set_kernel_name(conway ? (cells01 ? "life_tma_kernel<cells01,conway>" : "life_tma_kernel<u8,conway>")
+                               : (cells01 ? "life_tma_kernel<cells01,table>" : "life_tma_kernel<u8,table>"));
+        return SB200_OK;
+    }
     if (cells01) { if (conway) launch<true, true>(p, st); else launch<true, false>(p, st); }
     else { if (conway) launch<false, true>(p, st); else launch<false, false>(p, st); }
     SB_LAUNCH_CHECK();

@@ -233,15 +233,18 @@ def test_life_swar_paths(orc, dt, bc):
     rng = np.random.default_rng(21)
     l = A.lib()
     moore = npr.offsets("Moore", 1, 2)
-    for (W, H) in [(16, 5), (32, 33), (512, 70), (528, 64), (1040, 129), (4096, 40)]:
+    for (W, H) in [(16, 5), (32, 33), (512, 70), (528, 64), (1040, 129), (4096, 40), (4112, 17), (8192 + 512, 50)]:
         g = (rng.random((W, H)) < 0.4)
         g = g.astype(dt) if dt == np.bool_ else (g * rng.integers(1, 255, size=(W, H))).astype(np.uint8)
         g = np.asfortranarray(g)
         for born, surv in ((1 << 3, 0b1100), (0b101001000, 0b100111110), (1, 0b111111111)):
             for pv in (0, 1):
                 both(orc, g, moore, 1, bc, "cond", "life", born_mask=born, survive_mask=surv, padval=pv)
-                if W >= 512 and born == 8 and pv == 0:
-                    assert b"life_swar" in l.sb200_last_kernel()
+                if W >= 512 and H >= 16:
+                    assert b"life_tma" in l.sb200_last_kernel()    # bulk-copy fed variant
+                both(orc, g, moore, 1, bc, "cond", "life", born_mask=born, survive_mask=surv, padval=pv,
+                     flags=A.FLAG_NO_TMA)
+                assert b"life_swar" in l.sb200_last_kernel()       # register-prefetch variant
 
 
 def test_life_swar_ghost_rows_and_regions(orc):
@@ -252,7 +255,7 @@ def test_life_swar_ghost_rows_and_regions(orc):
     W, H, G = 1024, 96, 4
     parent = np.asfortranarray((rng.random((W, H + 2 * G)) < 0.35).astype(np.uint8))
     for region in (None, ((0, 0, 0), (W, 7, 0)), ((0, 7, 0), (W, H - 5, 0)), ((0, H - 5, 0), (W, H, 0))):
-        for flags in (0, A.FLAG_FORCE_GENERIC):
+        for flags in (0, A.FLAG_NO_TMA, A.FLAG_FORCE_GENERIC):
             h = build_desc(size=(W, H), eltype=A.U8, out_eltype=A.U8, offsets=moore, radius=1,
                            boundary=(A.WRAP, A.USE), reducer=A.LIFE, src_off=(0, G), dst_off=(0, G), src_ext=parent.shape,
                            dst_ext=parent.shape, region=region, flags=flags)
