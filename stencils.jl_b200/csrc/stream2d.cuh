@@ -1,0 +1,381 @@
+// stream2d.cuh — 2-D gather for Float32/Float64 over compile-time stencil shapes, TMA-fed row streaming.
+//
+// Replaces gatherstencil_kernel! (src/gatherstencil.jl:105-109) + the neighbour read path (src/array.jl:91-138)
+// for the named 2-D shapes (src/stencils/*.jl) and the reducers sum / mean / minimum / maximum / kernelproduct /
+// diffusion. Structure (same ring as life.cu):
+//   * a CTA owns a strip of S2_WARPS*512 bytes of columns and streams down a run of rows;
+//   * one producer thread issues cp.async.bulk (UBLKCP) copies of CH source rows per stage into a ring of shared
+//     memory stages and resolves the row boundary (Wrap / Reflect / ring rows) and the Wrap column halo by
+//     choosing source addresses; full/empty mbarriers recycle the stages;
+//   * every consumer thread owns VX = 16/sizeof(T) consecutive cells (one 128-bit store per output row). Each
+//     source row is read from shared memory once (its 16 bytes + R halo cells per side) and folded into the
+//     2R+1 output rows it belongs to: accumulators rotate through registers with a period of 2R+1 rows, so the
+//     fold of one output visits its taps in exactly the reference's offset order (row by row, first axis
+//     fastest) — bit-identical to the left fold of StaticArrays — with no contraction (explicit *_rn ops).
+// Algorithmic traffic: sizeof(T) read + sizeof(T) written per cell; each source row is fetched from HBM once
+// per run (+2R rows per run of rows).
+#pragma once
+#include <algorithm>
+#include "common.cuh"
+#include "tma.cuh"
+
+namespace sb {
+
+constexpr int S2_WARPS = 8;
+constexpr int S2_BXB = S2_WARPS * 32 * 16;  // strip width in bytes
+
+// 2-D shape predicates (same as shape_keep in api.cu for N = 2), usable at compile time.
+__host__ __device__ constexpr int s2_abs(int v) { return v < 0 ? -v : v; }
+__host__ __device__ constexpr bool s2_has(int shape, int R, int dx, int dy) {
+    const int ax = s2_abs(dx), ay = s2_abs(dy), manh = ax + ay, mx = ax > ay ? ax : ay, sq = dx * dx + dy * dy;
+    switch (shape) {
+    case SB200_WINDOW: return true;
+    case SB200_MOORE: return manh != 0;
+    case SB200_VONNEUMANN: return manh >= 1 && manh <= R;
+    case SB200_CROSS: return dx == 0 || dy == 0;
+    case SB200_DIAMOND: return manh <= R;
+    case SB200_CIRCLE: return 4 * sq < (2 * R + 1) * (2 * R + 1);  // sqrt(sq) < R + 0.5
+    case SB200_CARDINAL: return manh == R && mx == R;
+    case SB200_ORDINAL: return manh == 2 * R && mx == R;
+    default: return false;
+    }
+}
+// index of tap (dx,dy) in the reference's offset order (dy-major, dx fastest)
+__host__ __device__ constexpr int s2_tap_index(int shape, int R, int dx, int dy) {
+    int k = 0;
+    for (int y = -R; y <= R; y++)
+        for (int x = -R; x <= R; x++) {
+            if (y == dy && x == dx) return k;
+            if (s2_has(shape, R, x, y)) k++;
+        }
+    return k;
+}
+__host__ __device__ constexpr int s2_count(int shape, int R) { return s2_tap_index(shape, R, R + 1, R); }
+// does stream row-offset dy hold the first / last tap of the fold?
+__host__ __device__ constexpr int s2_first_dy(int shape, int R) {
+    for (int y = -R; y <= R; y++)
+        for (int x = -R; x <= R; x++)
+            if (s2_has(shape, R, x, y)) return y;
+    return 0;
+}
+__host__ __device__ constexpr int s2_last_dy(int shape, int R) {
+    for (int y = R; y >= -R; y--)
+        for (int x = -R; x <= R; x++)
+            if (s2_has(shape, R, x, y)) return y;
+    return 0;
+}
+
+template <typename T> struct S2Params {
+    const T* src;
+    T* dst;
+    long long spitch, dpitch;  // elements per row
+    int W, H;                  // logical size, axis 0 = W
+    int soff1, doff0, doff1;
+    int bc0, bc1;
+    T pad;
+    int y_lo, rows;
+    int nstrips, nruns;
+    T alpha;
+    T weights[81];             // KERNELDOT: in offset order (kernel parameter space = constant bank operands)
+};
+
+template <typename T, int R> struct S2Cfg {
+    static constexpr int VX = 16 / (int)sizeof(T);
+    static constexpr int HLB = ((R * (int)sizeof(T) + 15) / 16) * 16;   // halo bytes per side in a shared-memory row
+    static constexpr int HL = HLB / (int)sizeof(T);                      // ... in elements
+    static constexpr int ROWB = S2_BXB + 2 * HLB;
+    static constexpr int P = 2 * R + 1;                                   // accumulator rotation period
+    static constexpr int CH = P * ((R == 1) ? 2 : 1);                     // source rows per stage
+    static constexpr int STAGES = (CH * ROWB * 4 + 128 <= 110 * 1024) ? 4 : 3;
+    static constexpr int SMEM = 128 + STAGES * CH * ROWB;
+    static constexpr int SEG = VX + 2 * R;
+};
+
+template <typename T> __device__ __forceinline__ T s2_ldvec(const unsigned char* p, T* out);
+template <> __device__ __forceinline__ float s2_ldvec<float>(const unsigned char* p, float* out) {
+    const float4 v = *reinterpret_cast<const float4*>(p);
+    out[0] = v.x; out[1] = v.y; out[2] = v.z; out[3] = v.w;
+    return 0.f;
+}
+template <> __device__ __forceinline__ double s2_ldvec<double>(const unsigned char* p, double* out) {
+    const double2 v = *reinterpret_cast<const double2*>(p);
+    out[0] = v.x; out[1] = v.y;
+    return 0.0;
+}
+__device__ __forceinline__ void s2_stvec(float* p, const float* v) { *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]); }
+__device__ __forceinline__ void s2_stvec(double* p, const double* v) { *reinterpret_cast<double2*>(p) = make_double2(v[0], v[1]); }
+
+template <typename T> __device__ __forceinline__ long long s2_map_row(const S2Params<T>& p, int r) {
+    if (p.soff1 > 0) return (long long)r + p.soff1;
+    if (r >= 0 && r < p.H) return r;
+    if (p.bc1 == SB200_WRAP) return r < 0 ? r + p.H : r - p.H;
+    if (p.bc1 == SB200_REFLECT) return r < 0 ? -r : 2 * (p.H - 1) - r;
+    return -1;
+}
+
+// Per-thread constants of one (strip, run) task.
+template <typename T> struct S2Thread {
+    int xtb;        // byte offset of the thread's cells inside the strip
+    int x0b;        // byte offset of the strip in the row
+    int gx;         // global column of the thread's first cell
+    int y0, nout;   // first output row of the run, number of output rows
+    bool active, edge_l, edge_r, may_pad;
+    T* dt;          // dest pointer of (row y0, column gx)
+};
+
+// Fold source row J of the current stage (stream index i0 + J) into the 2R+1 outputs it belongs to.
+template <typename T, int SHAPE, int R, int RED, int J>
+__device__ __forceinline__ void s2_row(const S2Params<T>& p, const S2Thread<T>& th, const unsigned char* sbase, int i0,
+                                       T (&acc)[2 * R + 1][16 / sizeof(T)], T (&cen)[2 * R + 1][16 / sizeof(T)]) {
+    using C = S2Cfg<T, R>;
+    constexpr int VX = C::VX, P = C::P, SEG = C::SEG, L = s2_count(SHAPE, R);
+    constexpr int DY0 = s2_first_dy(SHAPE, R), DY1 = s2_last_dy(SHAPE, R);
+    const int i = i0 + J;            // stream index of this source row
+    const int r = th.y0 - R + i;     // logical source row
+    // ---- segment: cells gx-R .. gx+VX-1+R of the row ----
+    T seg[SEG];
+    if (th.may_pad && (r < 0 || r >= p.H)) {
+#pragma unroll
+        for (int e = 0; e < SEG; e++) seg[e] = p.pad;
+    } else {
+        const unsigned char* t = sbase + J * C::ROWB + C::HLB + th.xtb;
+        s2_ldvec<T>(t, &seg[R]);
+#pragma unroll
+        for (int e = 0; e < R; e++) {
+            seg[e] = *reinterpret_cast<const T*>(t - (R - e) * (int)sizeof(T));
+            seg[R + VX + e] = *reinterpret_cast<const T*>(t + (VX + e) * (int)sizeof(T));
+        }
+        if (th.edge_l || th.edge_r) {
+            const unsigned char* row0 = sbase + J * C::ROWB + C::HLB - th.x0b;  // address of global column 0
+#pragma unroll
+            for (int e = 0; e < SEG; e++) {
+                const int x = th.gx - R + e;
+                if (x < 0 || x >= p.W) {
+                    if (p.bc0 == SB200_REFLECT) {
+                        const int xm = x < 0 ? -x : 2 * (p.W - 1) - x;
+                        seg[e] = *reinterpret_cast<const T*>(row0 + (long long)xm * (int)sizeof(T));
+                    } else {
+                        seg[e] = p.pad;
+                    }
+                }
+            }
+        }
+    }
+    // ---- fold into the outputs o = i - d, d = dy + R ----
+#pragma unroll
+    for (int d = 0; d < P; d++) {
+        const int dy = d - R;
+        if (dy < DY0 || dy > DY1) continue;
+        const int s = ((J - d) % P + P) % P;  // compile-time: stages hold a multiple of P rows
+        if (RED == SB200_DIFFUSION && dy == 0) {
+#pragma unroll
+            for (int v = 0; v < VX; v++) cen[s][v] = seg[R + v];
+        }
+#pragma unroll
+        for (int dx = -R; dx <= R; dx++) {
+            if (!s2_has(SHAPE, R, dx, dy)) continue;
+            const int kk = s2_tap_index(SHAPE, R, dx, dy);
+#pragma unroll
+            for (int v = 0; v < VX; v++) {
+                const T x = seg[R + v + dx];
+                if (RED == SB200_SUM || RED == SB200_MEAN || RED == SB200_DIFFUSION) acc[s][v] = kk == 0 ? x : add_rn(acc[s][v], x);
+                else if (RED == SB200_MAX) acc[s][v] = kk == 0 ? x : jl_max(acc[s][v], x);
+                else if (RED == SB200_MIN) acc[s][v] = kk == 0 ? x : jl_min(acc[s][v], x);
+                else if (RED == SB200_KERNELDOT) acc[s][v] = add_rn(kk == 0 ? T(0) : acc[s][v], mul_rn(x, p.weights[kk]));
+            }
+        }
+        if (dy == DY1) {  // last row of the fold: output o = i - d is complete
+            const int o = i - d;
+            T out[VX];
+#pragma unroll
+            for (int v = 0; v < VX; v++) {
+                if (RED == SB200_MEAN) out[v] = div_rn(acc[s][v], (T)L);
+                else if (RED == SB200_DIFFUSION) {
+                    const T cc = cen[s][v];
+                    out[v] = add_rn(cc, mul_rn(p.alpha, sub_rn(acc[s][v], mul_rn((T)L, cc))));
+                } else out[v] = acc[s][v];
+            }
+            if (o >= 0 && o < th.nout && th.active) s2_stvec(th.dt + (long long)o * p.dpitch, out);
+        }
+    }
+}
+
+template <typename T, int SHAPE, int R, int RED, int J> struct S2Rows {
+    static __device__ __forceinline__ void run(const S2Params<T>& p, const S2Thread<T>& th, const unsigned char* sbase, int i0,
+                                               T (&acc)[2 * R + 1][16 / sizeof(T)], T (&cen)[2 * R + 1][16 / sizeof(T)]) {
+        s2_row<T, SHAPE, R, RED, J>(p, th, sbase, i0, acc, cen);
+        if constexpr (J + 1 < S2Cfg<T, R>::CH) S2Rows<T, SHAPE, R, RED, J + 1>::run(p, th, sbase, i0, acc, cen);
+    }
+};
+
+template <typename T, int SHAPE, int R, int RED>
+__global__ void __launch_bounds__((S2_WARPS + 1) * 32) stream2d_kernel(const __grid_constant__ S2Params<T> p) {
+    using C = S2Cfg<T, R>;
+    constexpr int VX = C::VX, P = C::P, CH = C::CH;
+    extern __shared__ __align__(128) unsigned char smem[];
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem);
+    uint64_t* empty = full + C::STAGES;
+    unsigned char* ring = smem + 128;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < C::STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], S2_WARPS); }
+        mbar_fence_init();
+    }
+    __syncthreads();
+    const int ntasks = p.nstrips * p.nruns;
+    const int Wb = p.W * (int)sizeof(T);
+    unsigned k = 0;
+    for (int task = blockIdx.x; task < ntasks; task += gridDim.x) {
+        const int strip = task % p.nstrips, run = task / p.nstrips;
+        const int x0b = strip * S2_BXB;
+        const int wbytes = min(S2_BXB, Wb - x0b);
+        const int y0 = p.y_lo + (int)((long long)p.rows * run / p.nruns);
+        const int y1 = p.y_lo + (int)((long long)p.rows * (run + 1) / p.nruns);
+        const int nout = y1 - y0;
+        const int nsrc = nout + 2 * R;  // source rows y0-R .. y1-1+R
+        const int nchunks = (nsrc + CH - 1) / CH;
+        if (warp == S2_WARPS) {
+            // ---------------- producer ----------------
+            if (lane == 0) {
+                const bool lh = x0b > 0 || p.bc0 == SB200_WRAP;
+                const bool rh = x0b + wbytes < Wb || p.bc0 == SB200_WRAP;
+                const int lxb = x0b > 0 ? x0b - C::HLB : Wb - C::HLB;
+                const int rxb = x0b + wbytes < Wb ? x0b + wbytes : 0;
+                const int rbytes = rh ? min(C::HLB, Wb - rxb) : 0;  // a narrow last strip may end inside the halo
+                for (int c = 0; c < nchunks; c++, k++) {
+                    const int slot = k % C::STAGES;
+                    mbar_wait(&empty[slot], ((k / C::STAGES) & 1) ^ 1);
+                    unsigned char* sbase = ring + slot * (CH * C::ROWB);
+                    unsigned bytes = 0;
+                    long long prow[CH];
+#pragma unroll
+                    for (int j = 0; j < CH; j++) {
+                        const int i = c * CH + j;
+                        prow[j] = i < nsrc ? s2_map_row(p, y0 - R + i) : -1;
+                        if (prow[j] >= 0) bytes += wbytes + (lh ? C::HLB : 0) + rbytes;
+                    }
+                    mbar_arrive_expect_tx(&full[slot], bytes);
+#pragma unroll
+                    for (int j = 0; j < CH; j++) {
+                        if (prow[j] < 0) continue;
+                        const unsigned char* g = reinterpret_cast<const unsigned char*>(p.src + prow[j] * p.spitch);
+                        unsigned char* srow = sbase + j * C::ROWB;
+                        bulk_g2s(srow + C::HLB, g + x0b, wbytes, &full[slot]);
+                        if (lh) bulk_g2s(srow, g + lxb, C::HLB, &full[slot]);
+                        if (rbytes) bulk_g2s(srow + C::HLB + wbytes, g + rxb, rbytes, &full[slot]);
+                    }
+                }
+            } else {
+                k += nchunks;
+            }
+            continue;
+        }
+        // ---------------- consumers ----------------
+        S2Thread<T> th;
+        th.xtb = (warp * 32 + lane) * 16;
+        th.x0b = x0b;
+        th.active = th.xtb < wbytes;
+        th.gx = (x0b + th.xtb) / (int)sizeof(T);
+        // Threads whose segment crosses the array edge under Remove / Reflect patch their halo cells themselves
+        // (under Wrap the producer already copied the wrapped columns).
+        th.edge_l = th.active && p.bc0 != SB200_WRAP && th.gx - R < 0;
+        th.edge_r = th.active && p.bc0 != SB200_WRAP && th.gx + VX - 1 + R >= p.W;
+        th.y0 = y0; th.nout = nout;
+        th.may_pad = p.soff1 == 0 && p.bc1 == SB200_REMOVE;
+        th.dt = p.dst + (long long)(y0 + p.doff1) * p.dpitch + p.doff0 + th.gx;
+        T acc[P][VX];
+        T cen[P][VX];
+#pragma unroll
+        for (int s = 0; s < P; s++)
+#pragma unroll
+            for (int v = 0; v < VX; v++) { acc[s][v] = T(0); cen[s][v] = T(0); }
+        for (int c = 0; c < nchunks; c++, k++) {
+            const int slot = k % C::STAGES;
+            mbar_wait(&full[slot], (k / C::STAGES) & 1);
+            const unsigned char* sbase = ring + slot * (CH * C::ROWB);
+            S2Rows<T, SHAPE, R, RED, 0>::run(p, th, sbase, c * CH, acc, cen);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[slot]);
+        }
+    }
+}
+
+// Launch one instantiation; returns SB200_OK or an error.
+template <typename T, int SHAPE, int R, int RED>
+int s2_launch(const S2Params<T>& p0, cudaStream_t st) {
+    using C = S2Cfg<T, R>;
+    static thread_local int cfg_dev = -1, ctas_per_sm = 0;
+    int dev = 0;
+    SB_CUDA(cudaGetDevice(&dev));
+    if (dev != cfg_dev) {
+        SB_CUDA(cudaFuncSetAttribute(stream2d_kernel<T, SHAPE, R, RED>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+        int per_sm = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, stream2d_kernel<T, SHAPE, R, RED>, (S2_WARPS + 1) * 32, C::SMEM) != cudaSuccess || per_sm < 1)
+            per_sm = 1;
+        ctas_per_sm = per_sm;
+        cfg_dev = dev;
+    }
+    S2Params<T> p = p0;
+    const int Wb = p.W * (int)sizeof(T);
+    p.nstrips = (Wb + S2_BXB - 1) / S2_BXB;
+    const long long ctas = (long long)ctas_per_sm * num_sms();
+    long long nruns = std::max<long long>(1, ctas / p.nstrips);
+    nruns = std::min<long long>(nruns, std::max(1, p.rows / (4 * C::P)));  // keep the 2R re-read rows per run small
+    p.nruns = (int)nruns;
+    const long long grid = std::min<long long>(ctas, (long long)p.nstrips * p.nruns);
+    stream2d_kernel<T, SHAPE, R, RED><<<(unsigned)grid, (S2_WARPS + 1) * 32, C::SMEM, st>>>(p);
+    SB_LAUNCH_CHECK();
+    return SB200_OK;
+}
+
+// Fill the parameters from a plan; false when the plan is outside what the streaming kernels accept.
+template <typename T> bool s2_accepts(const Plan& pl, const void* src, void* dst, S2Params<T>& p) {
+    const sb200_desc& d = pl.d;
+    if (d.ndim != 2 || pl.shape_tag < 0 || pl.shape_ndim != 2) return false;
+    if (d.src_off[0] != 0) return false;                         // axis 0 must be unpadded (ring rows on axis 1 are fine)
+    if ((d.size[0] * sizeof(T)) % 16 || (d.src_ext[0] * sizeof(T)) % 16) return false;
+    if ((d.dst_ext[0] * sizeof(T)) % 16 || (d.dst_off[0] * sizeof(T)) % 16) return false;
+    if (((uintptr_t)src | (uintptr_t)dst) & 15) return false;
+    if (d.size[0] > (1LL << 28) || d.size[1] > (1LL << 30)) return false;
+    if (d.size[0] * (long long)sizeof(T) < 16 * 2) return false;
+    if (pl.dd.lo[0] != 0 || pl.dd.n[0] != d.size[0]) return false;  // regions only along axis 1
+    if (d.src_off[1] == 0 && d.boundary[1] == SB200_USE) return false;
+    if (d.boundary[0] == SB200_USE) return false;
+    if (d.radius >= d.size[0]) return false;
+    const long long Wb_ = d.size[0] * (long long)sizeof(T);
+    if (Wb_ < 64) return false;
+    if (Wb_ > S2_BXB && (Wb_ % S2_BXB) != 0 && (Wb_ % S2_BXB) < 64) return false;  // last strip narrower than a halo
+    p.src = (const T*)src; p.dst = (T*)dst;
+    p.spitch = d.src_ext[0]; p.dpitch = d.dst_ext[0];
+    p.W = (int)d.size[0]; p.H = (int)d.size[1];
+    p.soff1 = d.src_off[1]; p.doff0 = d.dst_off[0]; p.doff1 = d.dst_off[1];
+    p.bc0 = d.boundary[0]; p.bc1 = d.boundary[1];
+    memcpy(&p.pad, &d.padval_bits, sizeof(T));
+    p.y_lo = (int)pl.dd.lo[1]; p.rows = (int)pl.dd.n[1];
+    p.alpha = (T)d.alpha;
+    if (d.reducer == SB200_KERNELDOT) {
+        if (d.noffsets > 81) return false;
+        memcpy(p.weights, d.weights_host, sizeof(T) * d.noffsets);
+    }
+    return true;
+}
+
+// One dispatcher per (shape, R) group, defined in stream2d_*.cu; returns -1 when the reducer is not compiled.
+template <typename T, int SHAPE, int R> int s2_dispatch_reducer(const S2Params<T>& p, int reducer, cudaStream_t st) {
+    switch (reducer) {
+    case SB200_SUM: return s2_launch<T, SHAPE, R, SB200_SUM>(p, st);
+    case SB200_MEAN: return s2_launch<T, SHAPE, R, SB200_MEAN>(p, st);
+    case SB200_MIN: return s2_launch<T, SHAPE, R, SB200_MIN>(p, st);
+    case SB200_MAX: return s2_launch<T, SHAPE, R, SB200_MAX>(p, st);
+    case SB200_KERNELDOT: return s2_launch<T, SHAPE, R, SB200_KERNELDOT>(p, st);
+    case SB200_DIFFUSION: return s2_launch<T, SHAPE, R, SB200_DIFFUSION>(p, st);
+    default: return -1;
+    }
+}
+
+int s2_group_a(const Plan& pl, const void* src, void* dst, cudaStream_t st);  // Window R=1..3
+int s2_group_b(const Plan& pl, const void* src, void* dst, cudaStream_t st);  // Moore, VonNeumann, Cross, Diamond R=1..2
+int s2_group_c(const Plan& pl, const void* src, void* dst, cudaStream_t st);  // Circle R=2..4
+int s2_group_d(const Plan& pl, const void* src, void* dst, cudaStream_t st);  // Cross, Diamond R=1..2
+
+}  // namespace sb

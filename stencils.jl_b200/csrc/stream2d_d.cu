@@ -1,0 +1,22 @@
+// stream2d_d.cu — instantiations of the streaming 2-D gather (stream2d.cuh): Cross, Diamond R=1..2.
+#include "stream2d.cuh"
+
+namespace sb {
+
+template <typename T> static int group_t(const Plan& pl, const void* src, void* dst, cudaStream_t st) {
+    S2Params<T> p;
+    if (!s2_accepts<T>(pl, src, dst, p)) return -1;
+    if (pl.shape_tag == SB200_CROSS && pl.d.radius == 1) return s2_dispatch_reducer<T, SB200_CROSS, 1>(p, pl.d.reducer, st);
+    if (pl.shape_tag == SB200_CROSS && pl.d.radius == 2) return s2_dispatch_reducer<T, SB200_CROSS, 2>(p, pl.d.reducer, st);
+    if (pl.shape_tag == SB200_DIAMOND && pl.d.radius == 1) return s2_dispatch_reducer<T, SB200_DIAMOND, 1>(p, pl.d.reducer, st);
+    if (pl.shape_tag == SB200_DIAMOND && pl.d.radius == 2) return s2_dispatch_reducer<T, SB200_DIAMOND, 2>(p, pl.d.reducer, st);
+    return -1;
+}
+
+int s2_group_d(const Plan& pl, const void* src, void* dst, cudaStream_t st) {
+    if (pl.d.eltype == SB200_F32) return group_t<float>(pl, src, dst, st);
+    if (pl.d.eltype == SB200_F64) return group_t<double>(pl, src, dst, st);
+    return -1;
+}
+
+}  // namespace sb

@@ -262,3 +262,53 @@ def test_life_swar_ghost_rows_and_regions(orc):
             want = orc.gather(h, parent, dst_like(h, 9))
             got, _ = gpu_gather(h, parent, dst_like(h, 9))
             bits_equal(got, want)
+
+
+S2_SHAPES = [("Window", 1), ("Window", 2), ("Window", 3), ("Moore", 1), ("Moore", 2), ("VonNeumann", 1), ("VonNeumann", 2),
+             ("Circle", 2), ("Circle", 3), ("Circle", 4), ("Cross", 1), ("Cross", 2), ("Diamond", 1), ("Diamond", 2)]
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+@pytest.mark.parametrize("bc", ["remove", "wrap", "reflect"])
+def test_stream2d_kernels(orc, dt, bc):
+    """The TMA-fed streaming kernels (csrc/stream2d.cuh): every compiled (shape, R) x reducer, 1..3 strips, ragged
+    last strip, runs shorter and longer than a stage, against the oracle, bit-exact."""
+    rng = np.random.default_rng(31)
+    l = A.lib()
+    es = np.dtype(dt).itemsize
+    sizes = [(4096 // es + 64, 37), (64 // es * 4, 100), (2 * 4096 // es + 4096 // es // 2, 23)]
+    for si, (shape, R) in enumerate(S2_SHAPES):
+        offs = npr.offsets(shape, R, 2)
+        W, H = sizes[si % len(sizes)]
+        r = rand_array(rng, (W, H), dt)
+        w = rng.random(len(offs))
+        for red in ("sum", "mean", "min", "max", "kerneldot", "diffusion"):
+            if red == "kerneldot" and len(offs) > 81:
+                continue
+            both(orc, r, offs, R, bc, "cond", red, padval=1.25, weights=w, alpha=0.07)
+            assert b"stream2d" in l.sb200_last_kernel(), (shape, R, red, l.sb200_last_kernel())
+
+
+def test_stream2d_ring_rows_regions_specials(orc):
+    rng = np.random.default_rng(32)
+    l = A.lib()
+    W, H, G = 1536, 60, 4
+    for dt in (np.float32, np.float64):
+        parent = rand_array(rng, (W, H + 2 * G), dt)
+        parent[rng.random(parent.shape) < 0.03] = np.nan
+        parent[rng.random(parent.shape) < 0.1] = -0.0
+        parent[rng.random(parent.shape) < 0.1] = 0.0
+        et = A.ELTYPE_OF_DTYPE[np.dtype(dt)]
+        for shape, R, red in (("VonNeumann", 1, A.DIFFUSION), ("Window", 1, A.MEAN), ("Circle", 4, A.MAX), ("Circle", 3, A.MIN),
+                              ("Window", 3, A.KERNELDOT)):
+            offs = npr.offsets(shape, R, 2)
+            w = rng.random(len(offs))
+            for region in (None, ((0, 0, 0), (W, 9, 0)), ((0, 9, 0), (W, H - 3, 0)), ((0, H - 3, 0), (W, H, 0))):
+                for bc0 in (A.WRAP, A.REMOVE, A.REFLECT):
+                    h = build_desc(size=(W, H), eltype=et, out_eltype=et, offsets=offs, radius=R, boundary=(bc0, A.USE),
+                                   reducer=red, src_off=(0, G), dst_off=(0, G), src_ext=parent.shape, dst_ext=parent.shape,
+                                   region=region, weights=w, alpha=0.1, padval=-2.5)
+                    want = orc.gather(h, parent, dst_like(h, 9))
+                    got, _ = gpu_gather(h, parent, dst_like(h, 9))
+                    bits_equal(got, want)
+                    assert b"stream2d" in l.sb200_last_kernel()
