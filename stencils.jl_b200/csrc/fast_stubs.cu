@@ -1,6 +1,5 @@
 // Temporary: specialised kernels not built yet decline every plan.
 #include "common.cuh"
 namespace sb {
-int try_diffusion3d(const Plan&, const void*, void*, cudaStream_t) { return -1; }
 int try_scatter_fast(const Plan&, const void*, void*, cudaStream_t) { return -1; }
 }

@@ -312,3 +312,35 @@ def test_stream2d_ring_rows_regions_specials(orc):
                     got, _ = gpu_gather(h, parent, dst_like(h, 9))
                     bits_equal(got, want)
                     assert b"stream2d" in l.sb200_last_kernel()
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+@pytest.mark.parametrize("bc", ["remove", "wrap", "reflect"])
+def test_stream3d_vonneumann(orc, dt, bc):
+    """The 2.5-D streaming kernel (csrc/stream3d.cu) for VonNeumann{1,3}: ragged tiles, several x tiles, short z."""
+    rng = np.random.default_rng(41)
+    l = A.lib()
+    es = np.dtype(dt).itemsize
+    offs = npr.offsets("VonNeumann", 1, 3)
+    for (X, Y, Z) in [(1024 // es + 32 // es * 2, 21, 9), (32 // es, 40, 12), (2048 // es, 16, 3), (64, 5, 70)]:
+        r = rand_array(rng, (X, Y, Z), dt)
+        for red in ("diffusion", "sum", "mean", "max", "min"):
+            both(orc, r, offs, 1, bc, "cond", red, padval=0.75, alpha=0.1)
+            assert b"stream3d" in l.sb200_last_kernel(), (X, Y, Z, red, l.sb200_last_kernel())
+
+
+def test_stream3d_ghost_planes_and_regions(orc):
+    rng = np.random.default_rng(42)
+    l = A.lib()
+    X, Y, Z, G = 320, 37, 20, 3
+    offs = npr.offsets("VonNeumann", 1, 3)
+    parent = rand_array(rng, (X, Y, Z + 2 * G), np.float32)
+    for region in (None, ((0, 0, 0), (X, Y, 2)), ((0, 0, 2), (X, Y, Z - 1)), ((0, 0, Z - 1), (X, Y, Z))):
+        for bcs in ((A.WRAP, A.WRAP, A.USE), (A.REMOVE, A.REFLECT, A.USE)):
+            h = build_desc(size=(X, Y, Z), eltype=A.F32, out_eltype=A.F32, offsets=offs, radius=1, boundary=bcs,
+                           reducer=A.DIFFUSION, src_off=(0, 0, G), dst_off=(0, 0, G), src_ext=parent.shape, dst_ext=parent.shape,
+                           region=region, alpha=0.1, padval=1.5)
+            want = orc.gather(h, parent, dst_like(h, 9))
+            got, _ = gpu_gather(h, parent, dst_like(h, 9))
+            bits_equal(got, want)
+            assert b"stream3d" in l.sb200_last_kernel()
