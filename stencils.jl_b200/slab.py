@@ -1,0 +1,248 @@
+"""Slab-partitioned iterated sweeps over the GPUs of one box (one process per GPU).
+
+The global array is split into contiguous slabs along its LAST (slowest) axis; rank r owns slab r. Every rank
+keeps G >= R ghost planes on each side of its slab inside the same parent buffer, so the sweep kernels read
+them straight through (`boundary = USE`, `src_off = R` on the split axis — the per-axis form of sb200_desc),
+while the other axes keep the array's own boundary condition, resolved inside the kernels.
+
+Ghost planes are exchanged once every k = G // R steps ("wide halo"): after an exchange the ghost planes are
+exact copies of the neighbours' cells, and step s of the cycle recomputes the planes that are still exact
+([R*s, ext - R*s) of the parent), so after k steps exactly the owned planes are valid again. The results are
+bit-identical to the single-domain sweep for any number of ranks and any G. (The global ends of the split axis
+under Remove / Reflect are re-imposed by the end ranks after every step: a recomputed mirror image would fold
+its neighbours in the opposite order and differ in the last bit.)
+
+During the last step of a cycle the planes the neighbours need are computed first; their exchange (NCCL
+send/recv over NVLink, on a side stream) overlaps the interior update.
+
+The same class runs on CPU tensors with the gloo backend and an injected `compute` callable — that is how the
+decomposition / exchange logic is tested without GPUs (tests/test_slab_gloo.py).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import _abi as A
+from ._desc import build_desc
+
+
+class SlabIterator:
+    def __init__(self, local_owned, *, offsets, radius, reducer, boundary, eltype, ghost=None, rank=0, world=1,
+                 compute=None, reducer_kwargs=None, padval=0):
+        """local_owned: torch tensor holding this rank's slab in column-major layout, i.e. a C-contiguous torch
+        tensor of shape reversed(logical shape) (split axis first). boundary: per-axis sb200 enums of the GLOBAL
+        array. compute(desc_handle, src_tensor, dst_tensor): sweep backend; None = libstencils_b200 on the
+        current CUDA stream."""
+        import torch
+        self.torch = torch
+        self.rank, self.world = rank, world
+        self.R = int(radius)
+        self.G = int(ghost) if ghost is not None else self.R
+        if self.G < self.R or self.G % max(self.R, 1):
+            raise A.ArgumentError("ghost thickness must be a positive multiple of the radius")
+        self.k = self.G // self.R
+        t = local_owned
+        self.nd = t.dim()
+        self.n_local = t.shape[0]
+        if self.n_local < self.G:
+            raise A.ArgumentError("slab thinner than the ghost zone")
+        self.logical_rest = tuple(reversed(t.shape[1:]))          # sizes of axes 0..nd-2
+        self.bcs = tuple(boundary)
+        self.bc_split = self.bcs[-1]
+        self.padval = padval
+        ext = self.n_local + 2 * self.G
+        self.ext = ext
+        self.bufs = [torch.empty((ext,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device) for _ in range(2)]
+        self.bufs[0][self.G:self.G + self.n_local].copy_(t)
+        self.cur = 0
+        self.eltype = eltype
+        self.compute = compute or self._compute_cuda
+        size = self.logical_rest + (ext - 2 * self.R,)
+        off = (0,) * (self.nd - 1) + (self.R,)
+        ext_all = self.logical_rest + (ext,)
+        self._mk = lambda region, flags: build_desc(
+            size=size, eltype=eltype, out_eltype=eltype, offsets=offsets, radius=self.R,
+            boundary=self.bcs[:-1] + (A.USE,), reducer=reducer, src_off=off, dst_off=off, src_ext=ext_all, dst_ext=ext_all,
+            padval=padval, region=region, flags=flags, **(reducer_kwargs or {}))
+        # Life on UInt8: after the first sweep every cell this rank reads is a 0/1 output of the kernel (own cells or
+        # exchanged ghosts); stale ghost planes outside the still-exact region only feed outputs that are discarded.
+        self._later_flags = A.FLAG_CELLS_01 if (reducer == A.LIFE and eltype == A.U8) else 0
+        self._nsweeps = 0
+        self._descs = {}
+        self.is_cuda = t.is_cuda
+        if self.is_cuda:
+            self.comm_stream = torch.cuda.Stream(device=t.device)
+        self.steps_since_exchange = self.k  # ghosts are not valid yet
+        self.launches = 0
+
+    # ---- helpers ----
+    def _desc(self, lo_plane, hi_plane):
+        """descriptor whose output region is parent planes [lo_plane, hi_plane) of the split axis"""
+        flags = self._later_flags if self._nsweeps > 0 else 0
+        key = (lo_plane, hi_plane, flags)
+        if key not in self._descs:
+            lo = (0,) * (self.nd - 1) + (lo_plane - self.R,)
+            hi = self.logical_rest + (hi_plane - self.R,)
+            lo, hi = lo + (0,) * (3 - self.nd), hi + (0,) * (3 - self.nd)
+            self._descs[key] = self._mk((lo, hi), flags)
+        return self._descs[key]
+
+    def _compute_cuda(self, h, src, dst):
+        stream = self.torch.cuda.current_stream().cuda_stream
+        A.check(A.lib().sb200_gather(h.ptr(), src.data_ptr(), dst.data_ptr(), stream))
+
+    def _sweep(self, lo_plane, hi_plane):
+        if hi_plane > lo_plane:
+            self.compute(self._desc(lo_plane, hi_plane), self.bufs[self.cur], self.bufs[1 - self.cur])
+            self.launches += 1
+
+    @property
+    def state(self):
+        """The owned planes of the current state (torch tensor view, split axis first)."""
+        return self.bufs[self.cur][self.G:self.G + self.n_local]
+
+    # ---- ghost exchange ----
+    def _fill_end_ghosts(self, buf):
+        """Global ends of the split axis under Remove / Reflect are local operations."""
+        G, n = self.G, self.n_local
+        if self.bc_split == A.WRAP:
+            return
+        first, last = self.rank == 0, self.rank == self.world - 1
+        if self.bc_split == A.REMOVE:
+            if first:
+                buf[:G] = self.padval
+            if last:
+                buf[G + n:] = self.padval
+        elif self.bc_split == A.REFLECT:  # i<0 -> -i ; i>=s -> 2(s-1)-i, mirror without repeating the edge
+            if first:
+                buf[:G] = buf[G + 1:2 * G + 1].flip(0)
+            if last:
+                buf[G + n:] = buf[n - 1:G + n - 1].flip(0)
+        else:
+            raise A.ArgumentError("the split axis needs Wrap, Remove or Reflect")
+
+    def _exchange_ops(self, buf):
+        import torch.distributed as dist
+        G, n, r, w = self.G, self.n_local, self.rank, self.world
+        wrap = self.bc_split == A.WRAP
+        up, down = (r + 1) % w, (r - 1) % w       # up = owner of the planes above mine
+        ops = []
+        if wrap or r < w - 1:
+            ops.append(dist.P2POp(dist.isend, buf[n:n + G], up))           # my top owned planes -> up's bottom ghost
+        if wrap or r > 0:
+            ops.append(dist.P2POp(dist.irecv, buf[:G], down))              # my bottom ghost <- down's top planes
+        if wrap or r > 0:
+            ops.append(dist.P2POp(dist.isend, buf[G:2 * G], down))         # my bottom owned planes -> down's top ghost
+        if wrap or r < w - 1:
+            ops.append(dist.P2POp(dist.irecv, buf[G + n:], up))            # my top ghost <- up's bottom planes
+        return ops
+
+    def _exchange(self, buf):
+        """Refresh the ghost planes of `buf` (blocking w.r.t. the stream it is called on)."""
+        import torch.distributed as dist
+        if self.world == 1:
+            G, n = self.G, self.n_local
+            if self.bc_split == A.WRAP:
+                buf[:G].copy_(buf[n:n + G])
+                buf[G + n:].copy_(buf[G:2 * G])
+        else:
+            ops = self._exchange_ops(buf)
+            if ops:
+                for req in dist.batch_isend_irecv(ops):
+                    req.wait()
+        self._fill_end_ghosts(buf)
+
+    # ---- stepping ----
+    def step(self, nsteps=1):
+        torch = self.torch
+        for _ in range(nsteps):
+            self._step_one(torch)
+            self._nsweeps += 1
+
+    def _step_one(self, torch):
+        if True:
+            if self.steps_since_exchange >= self.k:
+                self._exchange(self.bufs[self.cur])
+                self.steps_since_exchange = 0
+            s = self.steps_since_exchange + 1                 # 1..k
+            lo, hi = self.R * s, self.ext - self.R * s        # parent planes that are still exact after this step
+            last_of_cycle = s == self.k
+            if last_of_cycle and self.is_cuda and self.world > 1:
+                # boundary planes first, their exchange overlaps the interior update
+                # (one extra plane per side: a Reflect end mirrors planes G+1 .. 2G of the new state)
+                G, n = self.G + 1, self.n_local
+                self._sweep(lo, min(lo + G, hi))
+                self._sweep(max(hi - G, lo + G), hi)
+                ev = torch.cuda.Event()
+                ev.record()
+                nxt = self.bufs[1 - self.cur]
+                with torch.cuda.stream(self.comm_stream):
+                    self.comm_stream.wait_event(ev)
+                    self._exchange(nxt)
+                    done = torch.cuda.Event()
+                    done.record()
+                self._sweep(lo + G, hi - G)
+                torch.cuda.current_stream().wait_event(done)
+                self.cur = 1 - self.cur
+                self.steps_since_exchange = 0
+                return
+            self._sweep(lo, hi)
+            # Remove / Reflect at the global ends hold at EVERY step (the recomputed ghost planes of an end rank are
+            # not the boundary values), so the end ranks refresh them after each sweep; Wrap needs nothing.
+            self._fill_end_ghosts(self.bufs[1 - self.cur])
+            self.cur = 1 - self.cur
+            self.steps_since_exchange = s
+
+
+def split_axis_last(shape_global, world, rank):
+    """Planes [lo, hi) of the last axis owned by `rank` (equal slabs, remainder to the first ranks)."""
+    n = shape_global[-1]
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def bench_weak(workload, spec, steps, warmup, synth=None):
+    """Weak-scaling benchmark body used by bench.py under torchrun: every rank owns a slab of spec['shape'];
+    returns (ms on this rank, total owned cells over all ranks, launches in the timed region, kernel, config)."""
+    import torch
+    import torch.distributed as dist
+    from .stencils import Moore, VonNeumann
+    from .synth import synth_torch
+    rank, world = dist.get_rank(), dist.get_world_size()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    shape = tuple(spec["shape"])
+    cells_local = int(np.prod(shape))
+    # rank r's slab is planes [r*n, (r+1)*n) of the global field -> linear index offset r * cells_local
+    field = synth_torch(shape, spec["dtype"], spec["seed"], dev, lo=rank * cells_local)
+    t = field.permute(*reversed(range(len(shape)))).contiguous()
+    del field
+    if workload == "life":
+        st, red, kw, et, R, ghost = Moore(1), A.LIFE, dict(born_mask=1 << 3, survive_mask=0b1100), A.U8, 1, 16
+        bcs = (A.WRAP, A.WRAP)
+    elif workload == "diffusion":
+        st, red, kw, et, R, ghost = VonNeumann(1, 3), A.DIFFUSION, dict(alpha=0.1), A.F32, 1, 4
+        bcs = (A.WRAP, A.WRAP, A.WRAP)
+    else:
+        raise SystemExit(f"workload {workload} is not an iterated (slab-partitioned) configuration")
+    it = SlabIterator(t, offsets=st.offsets(), radius=R, reducer=red, boundary=bcs, eltype=et, ghost=ghost, rank=rank,
+                      world=world, reducer_kwargs=kw)
+    del t
+    lib = A.lib()
+    it.step(warmup)
+    torch.cuda.synchronize()
+    kernel = lib.sb200_last_kernel().decode()
+    dist.barrier()
+    torch.cuda.synchronize()
+    lib.sb200_launch_count(1)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    it.step(steps)
+    e1.record()
+    torch.cuda.synchronize()
+    dist.barrier()
+    ms = e0.elapsed_time(e1)
+    launches = lib.sb200_launch_count(1)
+    cfg = {"ghost_planes": ghost, "steps_per_exchange": ghost // R, "exchange": "NCCL send/recv on a side stream, "
+           "overlapped with the interior update of the last step of each cycle", "global_grid": list(shape[:-1]) + [shape[-1] * world]}
+    return ms, cells_local * world, launches, kernel, cfg
