@@ -144,6 +144,8 @@ __device__ __forceinline__ long long bounded(long long j, long long s, int bc) {
 int launch_generic_gather(const Plan& pl, const void* src, void* dst, cudaStream_t st);
 int launch_update_halo(const Plan& pl, void* parent, cudaStream_t st);
 int launch_generic_scatter(const Plan& pl, const void* src, void* dst, cudaStream_t st);
+int launch_generic_scatter_rect(const Plan& pl, const void* src, void* dst, cudaStream_t st, long long lo0, long long hi0,
+                                long long lo1, long long hi1);
 // Specialised kernels return SB200_OK when they handled the sweep, -1 when the plan is not theirs.
 int try_life_swar(const Plan& pl, const void* src, void* dst, cudaStream_t st);
 int try_tile2d(const Plan& pl, const void* src, void* dst, cudaStream_t st);

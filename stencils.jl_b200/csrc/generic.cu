@@ -254,13 +254,13 @@ template <typename T>
 __global__ void __launch_bounds__(256) scatter_generic(DevDesc p, const int* __restrict__ order,
                                                        const T* __restrict__ src, T* __restrict__ dst) {
     const long long ny = p.size[0], nx = p.size[1];
-    const long long total = ny * nx;
+    const long long total = p.n[0] * p.n[1];  // destination rectangle [lo, lo + n) (whole array by default)
     const int S = 2 * p.R + 1;
     const T* __restrict__ w = (const T*)p.weights;
     const bool zero = p.flags & SB200_FLAG_ZERO_DEST;
     for (long long id = blockIdx.x * (long long)blockDim.x + threadIdx.x; id < total;
          id += (long long)gridDim.x * blockDim.x) {
-        const long long ni = id % ny, nj = id / ny;
+        const long long ni = p.lo[0] + id % p.n[0], nj = p.lo[1] + id / p.n[0];
         T* cell = &dst[(ni + p.doff[0]) * p.dstr[0] + (nj + p.doff[1]) * p.dstr[1]];
         T acc = zero ? T(0) : *cell;
         // cells that a wrapped (raw -j -> s-j, raw s-1+j -> j-1) or reflected (raw -j -> j, raw s-1+j -> s-1-j)
@@ -315,9 +315,12 @@ __global__ void __launch_bounds__(256) scatter_generic(DevDesc p, const int* __r
     }
 }
 
-int launch_generic_scatter(const Plan& pl, const void* src, void* dst, cudaStream_t st) {
-    const DevDesc& p = pl.dd;
-    const long long total = p.size[0] * p.size[1];
+int launch_generic_scatter_rect(const Plan& pl, const void* src, void* dst, cudaStream_t st, long long lo0, long long hi0,
+                                long long lo1, long long hi1) {
+    DevDesc p = pl.dd;
+    p.lo[0] = lo0; p.n[0] = hi0 - lo0; p.lo[1] = lo1; p.n[1] = hi1 - lo1;
+    if (p.n[0] <= 0 || p.n[1] <= 0) return SB200_OK;
+    const long long total = p.n[0] * p.n[1];
     long long blocks = (total + 255) / 256;
     const long long cap = (long long)num_sms() * 32;
     if (blocks > cap) blocks = cap;
@@ -333,6 +336,10 @@ int launch_generic_scatter(const Plan& pl, const void* src, void* dst, cudaStrea
     SB_LAUNCH_CHECK();
     set_kernel_name("scatter_generic");
     return SB200_OK;
+}
+
+int launch_generic_scatter(const Plan& pl, const void* src, void* dst, cudaStream_t st) {
+    return launch_generic_scatter_rect(pl, src, dst, st, 0, pl.dd.size[0], 0, pl.dd.size[1]);
 }
 
 }  // namespace sb

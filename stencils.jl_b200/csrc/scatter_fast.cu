@@ -1,0 +1,142 @@
+// scatter_fast.cu — scatterstencil! (src/scatterstencil.jl:36-112) for the cells whose fold order is static.
+//
+// The reference makes 2R+1 passes over source columns offset:2R+1:nx, rows ascending, k ascending, and folds each
+// value into dest[I + o_k] with `op`. Read per destination cell that is: visit the L sources I - o_k in the order
+// (pass of the source column, source row, k), which for a whole destination column nj depends only on nj mod (2R+1)
+// — the table `order` built at plan time (api.cu). So every thread owns VX consecutive destination cells of one
+// column (one 128-bit read-modify-write), the fold order is warp-uniform, there are no atomics and the result is
+// the reference's serial result bit for bit. Sources that do not exist (out of bounds under Remove / Use) are
+// skipped. Cells a wrapped or reflected target can land on (edge bands under Wrap / Reflect) are left to
+// scatter_generic, which enumerates pre-images explicitly.
+// Algorithmic traffic: source read + dest read + dest write (dest read dropped with SB200_FLAG_ZERO_DEST).
+#include <algorithm>
+#include "common.cuh"
+
+namespace sb {
+
+constexpr int SF_MAXL = 64;
+
+template <typename T> struct SfVec;
+template <> struct SfVec<float> { using type = float4; static constexpr int VX = 4; };
+template <> struct SfVec<int32_t> { using type = int4; static constexpr int VX = 4; };
+template <> struct SfVec<double> { using type = double2; static constexpr int VX = 2; };
+template <> struct SfVec<int64_t> { using type = longlong2; static constexpr int VX = 2; };
+
+template <typename T> __device__ __forceinline__ T sf_fold(T acc, T val, int op) {
+    if (op == SB200_OP_ADD) return add_rn(acc, val);
+    if (op == SB200_OP_MAX) return jl_max(acc, val);
+    return jl_min(acc, val);
+}
+
+template <typename T, bool VEC>
+__global__ void __launch_bounds__(256) scatter_fast_kernel(DevDesc p, const int* __restrict__ order, const T* __restrict__ src,
+                                                           T* __restrict__ dst, int x_lo, int x_hi, int y_lo, int y_hi) {
+    constexpr int VX = SfVec<T>::VX;
+    __shared__ int s_o0[SF_MAXL], s_o1[SF_MAXL];
+    __shared__ T s_w[SF_MAXL];
+    __shared__ int s_ord[SF_MAXL * 9];
+    const int L = p.L, S = 2 * p.R + 1;
+    for (int k = threadIdx.x; k < L; k += blockDim.x) {
+        s_o0[k] = p.offs[3 * k];
+        s_o1[k] = p.offs[3 * k + 1];
+        s_w[k] = ((const T*)p.weights)[k];
+    }
+    for (int q = threadIdx.x; q < S * L; q += blockDim.x) s_ord[q] = order[q];
+    __syncthreads();
+    const int ny = (int)p.size[0], nx = (int)p.size[1];
+    const int nchunk = (x_hi - x_lo + VX - 1) / VX;
+    const long long total = (long long)nchunk * (y_hi - y_lo);
+    const bool zero = p.flags & SB200_FLAG_ZERO_DEST;
+    const bool mulc = p.scatter_rule == SB200_SCATTER_CENTER_WEIGHTS;
+    for (long long id = blockIdx.x * (long long)blockDim.x + threadIdx.x; id < total; id += (long long)gridDim.x * blockDim.x) {
+        const int y = y_lo + (int)(id / nchunk);
+        const int x0 = x_lo + (int)(id % nchunk) * VX;
+        T* drow = dst + (long long)(y + p.doff[1]) * p.dstr[1] + p.doff[0];
+        T acc[VX];
+        const bool full = x0 + VX <= x_hi;
+        if (zero) {
+#pragma unroll
+            for (int v = 0; v < VX; v++) acc[v] = T(0);
+        } else if (VEC && full) {
+            const typename SfVec<T>::type q = *reinterpret_cast<const typename SfVec<T>::type*>(drow + x0);
+            if constexpr (VX == 4) { acc[0] = q.x; acc[1] = q.y; acc[2] = q.z; acc[3] = q.w; }
+            else { acc[0] = q.x; acc[1] = q.y; }
+        } else {
+#pragma unroll
+            for (int v = 0; v < VX; v++) acc[v] = x0 + v < x_hi ? drow[x0 + v] : T(0);
+        }
+        const int* ord = s_ord + (y % S) * L;
+        for (int q = 0; q < L; q++) {
+            const int k = ord[q];
+            const int sj = y - s_o1[k];
+            if (sj < 0 || sj >= nx) continue;  // that source column does not exist
+            const int o0 = s_o0[k];
+            const T wk = s_w[k];
+            const T* srow = src + (long long)(sj + p.soff[1]) * p.sstr[1] + p.soff[0] - o0;
+#pragma unroll
+            for (int v = 0; v < VX; v++) {
+                const int si = x0 + v - o0;
+                if (si >= 0 && si < ny && x0 + v < x_hi) {
+                    const T val = mulc ? mul_rn(__ldg(srow + x0 + v), wk) : wk;
+                    acc[v] = sf_fold(acc[v], val, p.scatter_op);
+                }
+            }
+        }
+        if (VEC && full) {
+            typename SfVec<T>::type q;
+            if constexpr (VX == 4) { q.x = acc[0]; q.y = acc[1]; q.z = acc[2]; q.w = acc[3]; }
+            else { q.x = acc[0]; q.y = acc[1]; }
+            *reinterpret_cast<typename SfVec<T>::type*>(drow + x0) = q;
+        } else {
+#pragma unroll
+            for (int v = 0; v < VX; v++)
+                if (x0 + v < x_hi) drow[x0 + v] = acc[v];
+        }
+    }
+}
+
+template <typename T> static int sf_run(const Plan& pl, const void* src, void* dst, cudaStream_t st) {
+    constexpr int VX = SfVec<T>::VX;
+    const DevDesc& p = pl.dd;
+    const int ny = (int)p.size[0], nx = (int)p.size[1], R = p.R;
+    // edge bands under Wrap / Reflect go to the generic kernel (pre-image enumeration)
+    auto band = [&](int bc) { return bc == SB200_WRAP ? R : (bc == SB200_REFLECT ? R + 1 : 0); };
+    const int b0 = std::min(band(p.bc[0]), ny / 2), b1 = std::min(band(p.bc[1]), nx / 2);
+    int x_lo = b0, x_hi = ny - b0, y_lo = b1, y_hi = nx - b1;
+    // start the interior on a vector boundary so the bulk of the accesses are 128-bit
+    const bool vec = ((uintptr_t)dst % 16 == 0) && (p.dstr[1] % VX == 0) && (p.doff[0] % VX == 0);
+    if (vec && x_lo % VX) x_lo = std::min(x_hi, (x_lo + VX - 1) / VX * VX);
+    int rc;
+    if (x_hi > x_lo && y_hi > y_lo) {
+        const long long total = (long long)((x_hi - x_lo + VX - 1) / VX) * (y_hi - y_lo);
+        const long long blocks = std::min<long long>((total + 255) / 256, (long long)num_sms() * 16);
+        if (vec) scatter_fast_kernel<T, true><<<(unsigned)blocks, 256, 0, st>>>(p, pl.scatter_order_dev, (const T*)src, (T*)dst, x_lo, x_hi, y_lo, y_hi);
+        else scatter_fast_kernel<T, false><<<(unsigned)blocks, 256, 0, st>>>(p, pl.scatter_order_dev, (const T*)src, (T*)dst, x_lo, x_hi, y_lo, y_hi);
+        SB_LAUNCH_CHECK();
+    } else {
+        x_lo = x_hi = 0;
+        y_lo = 0; y_hi = nx;  // nothing static: one generic pass over everything below
+    }
+    // bands: rows below / above the interior (full width), then the left / right columns of the interior rows
+    if ((rc = launch_generic_scatter_rect(pl, src, dst, st, 0, ny, 0, y_lo))) return rc;
+    if ((rc = launch_generic_scatter_rect(pl, src, dst, st, 0, ny, y_hi, nx))) return rc;
+    if ((rc = launch_generic_scatter_rect(pl, src, dst, st, 0, x_lo, y_lo, y_hi))) return rc;
+    if ((rc = launch_generic_scatter_rect(pl, src, dst, st, x_hi, ny, y_lo, y_hi))) return rc;
+    set_kernel_name("scatter_fast_kernel");
+    return SB200_OK;
+}
+
+int try_scatter_fast(const Plan& pl, const void* src, void* dst, cudaStream_t st) {
+    const sb200_desc& d = pl.d;
+    if (d.noffsets > SF_MAXL || d.radius > 4) return -1;
+    if (d.size[0] >= (1LL << 30) || d.size[1] >= (1LL << 30)) return -1;
+    switch (d.eltype) {
+    case SB200_F32: return sf_run<float>(pl, src, dst, st);
+    case SB200_F64: return sf_run<double>(pl, src, dst, st);
+    case SB200_I32: return sf_run<int32_t>(pl, src, dst, st);
+    case SB200_I64: return sf_run<int64_t>(pl, src, dst, st);
+    default: return -1;
+    }
+}
+
+}  // namespace sb
