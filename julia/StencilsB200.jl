@@ -1,0 +1,214 @@
+# StencilsB200.jl — Julia shim: lowers the mutating entry points of rafaqz/Stencils.jl onto the C ABI of
+# libstencils_b200.so (include/stencils_b200.h).
+#
+# STATUS: written against the header, NOT executed (no `julia` in the build image or on the GPU box). The
+# executable consumer of the same ABI is the Python mirror in `stencils.jl_b200/` (ctypes), which the tests drive;
+# this file is kept line-for-line equivalent to `stencils.jl_b200/ops.py` + `_desc.py`.
+#
+# What it overrides (signatures unchanged, see SURVEY §8b):
+#   gatherstencil!(f, dest, source::AbstractStencilArray)      src/gatherstencil.jl:89-103  -> sb200_update_halo + sb200_gather
+#   gatherstencil!(f, A::SwitchingStencilArray)                 src/gatherstencil.jl:77-83   -> same, then switch(A)
+#   update_boundary!(A)                                         src/array.jl:195-233         -> sb200_update_halo
+#   scatterstencil!(f, op, dest, source)                        src/scatterstencil.jl:36-45  -> sb200_scatter
+# for parents that are `B200Array`s (device buffers owned through sb200_malloc) or plain `Array`s
+# (host buffers -> sb200_gather_host). `mapstencil`/`gatherstencil` (allocating) keep the reference code and
+# reach these methods through dispatch.
+module StencilsB200
+
+using Stencils
+using Stencils: AbstractStencilArray, SwitchingStencilArray, StencilArray, Stencil, Kernel, Halo, Conditional,
+                Remove, Wrap, Reflect, Use, boundary, padding, stencil, radius, offsets, source, dest, switch, kernel
+using Statistics: mean
+
+const LIB = joinpath(@__DIR__, "..", "stencils.jl_b200", "lib", "libstencils_b200.so")
+
+# ---- enums (include/stencils_b200.h) ----
+const ELTYPE = Dict(Bool => 0, UInt8 => 1, Int32 => 2, Int64 => 3, Float32 => 4, Float64 => 5)
+const SB_REMOVE, SB_WRAP, SB_REFLECT, SB_USE = Int32(0), Int32(1), Int32(2), Int32(3)
+const SB_SUM, SB_MEAN, SB_MIN, SB_MAX, SB_KERNELDOT, SB_LIFE, SB_DIFFUSION = Int32.(0:6)
+const SB_EUNSUPPORTED, SB_ESIZE = 2, 3
+
+# struct sb200_desc — field order and sizes must match the header (248 bytes).
+struct Desc
+    struct_size::Int32
+    ndim::Int32
+    size::NTuple{3,Int64}
+    src_ext::NTuple{3,Int64}
+    dst_ext::NTuple{3,Int64}
+    src_off::NTuple{3,Int32}
+    dst_off::NTuple{3,Int32}
+    boundary::NTuple{3,Int32}
+    eltype::Int32
+    out_eltype::Int32
+    padval_bits::UInt64
+    radius::Int32
+    noffsets::Int32
+    offsets_host::Ptr{Int32}
+    reducer::Int32
+    scatter_op::Int32
+    scatter_rule::Int32
+    born_mask::UInt32
+    survive_mask::UInt32
+    reserved0::Int32
+    weights_host::Ptr{Cvoid}
+    alpha::Float64
+    region_lo::NTuple{3,Int64}
+    region_hi::NTuple{3,Int64}
+    flags::Int32
+    reserved1::Int32
+end
+
+# ---- reducer menu: the only user functions that lower to CUDA kernels ----
+struct Life
+    born_mask::UInt32
+    survive_mask::UInt32
+end
+Life(; born=(3,), survive=(2, 3)) = Life(reduce(|, (UInt32(1) << b for b in born)), reduce(|, (UInt32(1) << s for s in survive)))
+struct Diffusion
+    alpha::Float64
+end
+
+reducer_enum(::typeof(sum)) = SB_SUM
+reducer_enum(::typeof(mean)) = SB_MEAN
+reducer_enum(::typeof(minimum)) = SB_MIN
+reducer_enum(::typeof(maximum)) = SB_MAX
+reducer_enum(::typeof(Stencils.kernelproduct)) = SB_KERNELDOT
+reducer_enum(::Life) = SB_LIFE
+reducer_enum(::Diffusion) = SB_DIFFUSION
+reducer_enum(f) = throw(ArgumentError("unsupported user function $f: only sum, mean, minimum, maximum, kernelproduct, " *
+                                      "Life(...) and Diffusion(α) lower to CUDA kernels; there is no fallback path"))
+
+bc_enum(::Remove) = SB_REMOVE
+bc_enum(::Wrap) = SB_WRAP
+bc_enum(::Reflect) = SB_REFLECT
+bc_enum(::Use) = SB_USE
+
+function check(status)
+    status == 0 && return nothing
+    msg = unsafe_string(ccall((:sb200_last_error, LIB), Cstring, ()))
+    status in (1, SB_EUNSUPPORTED, SB_ESIZE) ? throw(ArgumentError(msg)) : error("libstencils_b200 status $status: $msg")
+end
+
+"Device buffer owned through the C ABI (column-major, like Array)."
+mutable struct B200Array{T,N} <: AbstractArray{T,N}
+    ptr::Ptr{Cvoid}
+    dims::NTuple{N,Int}
+    function B200Array{T}(::UndefInitializer, dims::NTuple{N,Int}) where {T,N}
+        p = Ref{Ptr{Cvoid}}()
+        check(ccall((:sb200_malloc, LIB), Int32, (Ptr{Ptr{Cvoid}}, Csize_t), p, prod(dims) * sizeof(T)))
+        A = new{T,N}(p[], dims)
+        finalizer(a -> ccall((:sb200_free, LIB), Int32, (Ptr{Cvoid},), a.ptr), A)
+    end
+end
+Base.size(A::B200Array) = A.dims
+Base.similar(A::B200Array, ::Type{T}, dims::Dims) where T = B200Array{T}(undef, dims)
+function B200Array(h::Array{T,N}) where {T,N}
+    A = B200Array{T}(undef, size(h))
+    check(ccall((:sb200_memcpy_h2d, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Csize_t, Ptr{Cvoid}), A.ptr, h, sizeof(h), C_NULL))
+    A
+end
+function Base.Array(A::B200Array{T,N}) where {T,N}
+    h = Array{T,N}(undef, size(A))
+    check(ccall((:sb200_memcpy_d2h, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Csize_t, Ptr{Cvoid}), h, A.ptr, sizeof(h), C_NULL))
+    check(ccall((:sb200_stream_sync, LIB), Int32, (Ptr{Cvoid},), C_NULL))
+    h
+end
+
+pad3(t, fill) = ntuple(i -> i <= length(t) ? t[i] : fill, 3)
+
+"Descriptor from a StencilArray pair; `keep` holds the arrays the pointers refer to."
+function make_desc(f, dst_parent, dst_halo::Int, src::AbstractStencilArray{R,T,N}, src_parent; flags=Int32(0)) where {R,T,N}
+    st = stencil(src)
+    offs = zeros(Int32, 3, length(st))
+    for (k, o) in enumerate(offsets(st)), a in 1:length(o)
+        offs[a, k] = o[a]
+    end
+    sh = padding(src) isa Halo ? R : 0
+    red = reducer_enum(f)
+    out = Ref{Int32}()
+    check(ccall((:sb200_out_eltype, LIB), Int32, (Int32, Int32, Ptr{Int32}), red, ELTYPE[T], out))
+    w = st isa Kernel ? collect(T, vec(kernel(st))) : T[]
+    bc = boundary(src)
+    pv = bc isa Remove ? padbits(T, Stencils.padval(bc)) : UInt64(0)   # Remove() without padval (nothing) -> MethodError
+    d = Desc(sizeof(Desc), N, pad3(size(src), 1), pad3(size(src_parent), 1), pad3(size(dst_parent), 1),
+             pad3(ntuple(_ -> Int32(sh), N), Int32(0)), pad3(ntuple(_ -> Int32(dst_halo), N), Int32(0)),
+             pad3(ntuple(_ -> bc_enum(bc), N), SB_REMOVE), ELTYPE[T], out[], pv, R, length(st), pointer(offs), red, 0, 0,
+             f isa Life ? f.born_mask : UInt32(8), f isa Life ? f.survive_mask : UInt32(12), 0,
+             isempty(w) ? C_NULL : pointer(w), f isa Diffusion ? f.alpha : 0.0, (0, 0, 0), (0, 0, 0), flags, 0)
+    return Ref(d), (offs, w)
+end
+unsigned_of(::Type{T}) where T = sizeof(T) == 1 ? UInt8 : sizeof(T) == 4 ? UInt32 : UInt64
+padbits(::Type{T}, v::Number) where T = UInt64(reinterpret(unsigned_of(T), convert(T, v)))
+"Copy of a descriptor with some fields replaced."
+with(d::Desc; kw...) = Desc((haskey(kw, k) ? kw[k] : getfield(d, k) for k in fieldnames(Desc))...)
+
+dataptr(A::B200Array) = A.ptr
+dataptr(A::Array) = Ptr{Cvoid}(pointer(A))
+
+# gatherstencil!(f, dest, source) — src/gatherstencil.jl:89-103
+function Stencils.gatherstencil!(f::F, dst, src::AbstractStencilArray{R,T,N,<:Union{B200Array,Array}}) where {F,R,T,N}
+    Stencils._checksizes((dst, src))
+    dpar, dh = dst isa AbstractStencilArray ? (parent(dst), padding(dst) isa Halo ? R : 0) : (dst, 0)
+    d, keep = make_desc(f, dpar, dh, src, parent(src))
+    GC.@preserve keep begin
+        if parent(src) isa B200Array
+            needs_halo = padding(src) isa Halo && !(boundary(src) isa Use)
+            needs_halo && check(ccall((:sb200_update_halo, LIB), Int32, (Ref{Desc}, Ptr{Cvoid}, Ptr{Cvoid}), d, dataptr(parent(src)), C_NULL))
+            check(ccall((:sb200_gather, LIB), Int32, (Ref{Desc}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}), d, dataptr(parent(src)), dataptr(dpar), C_NULL))
+            check(ccall((:sb200_stream_sync, LIB), Int32, (Ptr{Cvoid},), C_NULL))   # the reference call is synchronous (:100)
+        else
+            check(ccall((:sb200_gather_host, LIB), Int32, (Ref{Desc}, Ptr{Cvoid}, Ptr{Cvoid}), d, dataptr(parent(src)), dataptr(dpar)))
+        end
+    end
+    return dst
+end
+
+# gatherstencil!(f, A::SwitchingStencilArray) — src/gatherstencil.jl:77-83
+function Stencils.gatherstencil!(f::F, A::SwitchingStencilArray{R,T,N,<:Union{B200Array,Array}}) where {F,R,T,N}
+    pd = padding(A) isa Halo ? Halo{:in}() : padding(A)
+    src = StencilArray(source(A), stencil(A), boundary(A), pd)
+    dst = StencilArray(dest(A), stencil(A), boundary(A), pd)
+    Stencils.gatherstencil!(f, dst, src)
+    return switch(A)
+end
+
+"`for _ in 1:n; A = mapstencil!(f, A); end` as one stream-ordered call (no host sync between steps)."
+function iterate!(f, A::SwitchingStencilArray{R,T,N,<:B200Array}, nsteps::Integer) where {R,T,N}
+    pd = padding(A) isa Halo ? Halo{:in}() : padding(A)
+    src = StencilArray(source(A), stencil(A), boundary(A), pd)
+    d, keep = make_desc(f, dest(A), padding(A) isa Halo ? R : 0, src, source(A))
+    GC.@preserve keep check(ccall((:sb200_iterate, LIB), Int32, (Ref{Desc}, Ptr{Cvoid}, Ptr{Cvoid}, Int32, Ptr{Cvoid}),
+                                  d, dataptr(source(A)), dataptr(dest(A)), nsteps, C_NULL))
+    check(ccall((:sb200_stream_sync, LIB), Int32, (Ptr{Cvoid},), C_NULL))
+    return iseven(nsteps) ? A : switch(A)
+end
+
+# update_boundary!(A) — src/array.jl:195-233
+function Stencils.update_boundary!(A::AbstractStencilArray{R,T,N,<:B200Array}) where {R,T,N}
+    (padding(A) isa Halo && !(boundary(A) isa Use)) || return A
+    d, keep = make_desc(sum, parent(A), R, A, parent(A))
+    GC.@preserve keep check(ccall((:sb200_update_halo, LIB), Int32, (Ref{Desc}, Ptr{Cvoid}, Ptr{Cvoid}), d, dataptr(parent(A)), C_NULL))
+    return A
+end
+
+# scatterstencil!(f, op, dest, source) — src/scatterstencil.jl:36-45. `f` must be one of the value rules below.
+struct ScatterWeights{W}; w::W; end          # val_k = w_k
+struct ScatterCenterWeights{W}; w::W; end    # val_k = center(hood) * w_k
+scatter_op(::typeof(+)) = Int32(0)
+scatter_op(::typeof(max)) = Int32(1)
+scatter_op(::typeof(min)) = Int32(2)
+scatter_op(op) = throw(ArgumentError("unsupported scatter op $op: use +, max or min"))
+function Stencils.scatterstencil!(f::Union{ScatterWeights,ScatterCenterWeights}, op, dst::B200Array{T,2},
+                                  src::AbstractStencilArray{R,T,2,<:B200Array}) where {R,T}
+    Stencils._checksizes((dst, src))
+    d, keep = make_desc(sum, dst, 0, src, parent(src))
+    w = collect(T, f.w isa Number ? fill(f.w, length(stencil(src))) : f.w)
+    rule = f isa ScatterWeights ? Int32(0) : Int32(1)
+    d[] = with(d[]; scatter_op=scatter_op(op), scatter_rule=rule, weights_host=Ptr{Cvoid}(pointer(w)), out_eltype=ELTYPE[T])
+    GC.@preserve keep w check(ccall((:sb200_scatter, LIB), Int32, (Ref{Desc}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}),
+                                     d, dataptr(parent(src)), dataptr(dst), C_NULL))
+    check(ccall((:sb200_stream_sync, LIB), Int32, (Ptr{Cvoid},), C_NULL))
+    return dst
+end
+
+end # module

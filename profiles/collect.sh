@@ -1,0 +1,15 @@
+#!/bin/bash
+# Run on the GPU box (under gpurun): ncu launch list of the default bench command + one `--set full` capture
+# of each dominant kernel. Outputs go to gpurun_out/; summarise here with `python profiles/summarize.py`.
+set -x
+mkdir -p gpurun_out
+R=${1:-r01}
+ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/${R}_launches_life.csv \
+    python bench.py --steps 20 --warmup 3 --no-extras > gpurun_out/${R}_launches_life.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:life_tma -s 6 -c 1 -o gpurun_out/${R}_life \
+    python bench.py --steps 10 --warmup 3 --no-extras > /dev/null 2>&1
+for wl in mean kernel circle scatter diffusion; do
+  ncu --set full --clock-control none --import-source on -k regex:"stream2d|stream3d|scatter_fast" -s 3 -c 1 -o gpurun_out/${R}_${wl} \
+      python bench.py --workload ${wl} --steps 4 --warmup 3 --no-extras > /dev/null 2>&1
+done
+ls -la gpurun_out
