@@ -65,6 +65,22 @@ __host__ __device__ constexpr int s2_last_dy(int shape, int R) {
     return 0;
 }
 
+// Half-width of row dy when the row is one contiguous symmetric segment [-hw, hw] (else -1): Window, Circle, Diamond.
+__host__ __device__ constexpr int s2_row_halfwidth(int shape, int R, int dy) {
+    int hw = -1;
+    for (int x = 0; x <= R; x++)
+        if (s2_has(shape, R, x, dy)) hw = x;
+    if (hw < 0) return -1;
+    for (int x = -R; x <= R; x++)
+        if (s2_has(shape, R, x, dy) != (s2_abs(x) <= hw)) return -1;
+    return hw;
+}
+__host__ __device__ constexpr bool s2_convex_rows(int shape, int R) {
+    for (int y = -R; y <= R; y++)
+        if (s2_row_halfwidth(shape, R, y) < 0) return false;
+    return true;
+}
+
 template <typename T> struct S2Params {
     const T* src;
     T* dst;
@@ -83,10 +99,12 @@ template <typename T, int R> struct S2Cfg {
     static constexpr int VX = 16 / (int)sizeof(T);
     static constexpr int HLB = ((R * (int)sizeof(T) + 15) / 16) * 16;   // halo bytes per side in a shared-memory row
     static constexpr int HL = HLB / (int)sizeof(T);                      // ... in elements
-    static constexpr int ROWB = S2_BXB + 2 * HLB;
+    static constexpr int LEFT = 128;   // margin (halo at its end): global and shared addresses of every copy agree mod 128
+    static constexpr int ROWB = LEFT + S2_BXB + 128;
     static constexpr int P = 2 * R + 1;                                   // accumulator rotation period
     static constexpr int CH = P * ((R == 1) ? 2 : 1);                     // source rows per stage
-    static constexpr int STAGES = (CH * ROWB * 4 + 128 <= 110 * 1024) ? 4 : 3;
+    static constexpr int FIT = (113 * 1024 - 128) / (CH * ROWB);          // stages that still allow 2 CTAs per SM
+    static constexpr int STAGES = FIT >= 4 ? 4 : (FIT < 2 ? 2 : FIT);
     static constexpr int SMEM = 128 + STAGES * CH * ROWB;
     static constexpr int SEG = VX + 2 * R;
 };
@@ -138,7 +156,7 @@ __device__ __forceinline__ void s2_row(const S2Params<T>& p, const S2Thread<T>& 
 #pragma unroll
         for (int e = 0; e < SEG; e++) seg[e] = p.pad;
     } else {
-        const unsigned char* t = sbase + J * C::ROWB + C::HLB + th.xtb;
+        const unsigned char* t = sbase + J * C::ROWB + C::LEFT + th.xtb;
         s2_ldvec<T>(t, &seg[R]);
 #pragma unroll
         for (int e = 0; e < R; e++) {
@@ -146,7 +164,7 @@ __device__ __forceinline__ void s2_row(const S2Params<T>& p, const S2Thread<T>& 
             seg[R + VX + e] = *reinterpret_cast<const T*>(t + (VX + e) * (int)sizeof(T));
         }
         if (th.edge_l || th.edge_r) {
-            const unsigned char* row0 = sbase + J * C::ROWB + C::HLB - th.x0b;  // address of global column 0
+            const unsigned char* row0 = sbase + J * C::ROWB + C::LEFT - th.x0b;  // address of global column 0
 #pragma unroll
             for (int e = 0; e < SEG; e++) {
                 const int x = th.gx - R + e;
@@ -161,12 +179,37 @@ __device__ __forceinline__ void s2_row(const S2Params<T>& p, const S2Thread<T>& 
             }
         }
     }
+    // ---- maximum / minimum over shapes whose rows are contiguous segments: the fold is exact in any order, so the
+    // running extrema m[w] over [-w, w] are built once per source row (2 ops per width) and every output takes the
+    // one matching its row of the shape: 2R + (2R+1) ops per cell instead of L.
+    constexpr bool NESTED = (RED == SB200_MAX || RED == SB200_MIN) && s2_convex_rows(SHAPE, R);
+    T m[NESTED ? R + 1 : 1][VX];
+    if (NESTED) {
+#pragma unroll
+        for (int v = 0; v < VX; v++) {
+            m[0][v] = seg[R + v];
+#pragma unroll
+            for (int w_ = 1; w_ <= (NESTED ? R : 0); w_++) {
+                const T lo_ = seg[R + v - w_], hi_ = seg[R + v + w_];
+                m[w_][v] = RED == SB200_MAX ? jl_max(jl_max(m[w_ - 1][v], lo_), hi_) : jl_min(jl_min(m[w_ - 1][v], lo_), hi_);
+            }
+        }
+    }
     // ---- fold into the outputs o = i - d, d = dy + R ----
 #pragma unroll
     for (int d = 0; d < P; d++) {
         const int dy = d - R;
         if (dy < DY0 || dy > DY1) continue;
         const int s = ((J - d) % P + P) % P;  // compile-time: stages hold a multiple of P rows
+        if (NESTED) {
+            const int hw = s2_row_halfwidth(SHAPE, R, dy);
+#pragma unroll
+            for (int v = 0; v < VX; v++) {
+                const T x = m[hw < 0 ? 0 : hw][v];
+                acc[s][v] = dy == DY0 ? x : (RED == SB200_MAX ? jl_max(acc[s][v], x) : jl_min(acc[s][v], x));
+            }
+        } else
+        {
         if (RED == SB200_DIFFUSION && dy == 0) {
 #pragma unroll
             for (int v = 0; v < VX; v++) cen[s][v] = seg[R + v];
@@ -183,6 +226,7 @@ __device__ __forceinline__ void s2_row(const S2Params<T>& p, const S2Thread<T>& 
                 else if (RED == SB200_MIN) acc[s][v] = kk == 0 ? x : jl_min(acc[s][v], x);
                 else if (RED == SB200_KERNELDOT) acc[s][v] = add_rn(kk == 0 ? T(0) : acc[s][v], mul_rn(x, p.weights[kk]));
             }
+        }
         }
         if (dy == DY1) {  // last row of the fold: output o = i - d is complete
             const int o = i - d;
@@ -209,7 +253,7 @@ template <typename T, int SHAPE, int R, int RED, int J> struct S2Rows {
 };
 
 template <typename T, int SHAPE, int R, int RED>
-__global__ void __launch_bounds__((S2_WARPS + 1) * 32) stream2d_kernel(const __grid_constant__ S2Params<T> p) {
+__global__ void __launch_bounds__((S2_WARPS + 1) * 32, (RED == SB200_KERNELDOT && R >= 3) ? 1 : 2) stream2d_kernel(const __grid_constant__ S2Params<T> p) {
     using C = S2Cfg<T, R>;
     constexpr int VX = C::VX, P = C::P, CH = C::CH;
     extern __shared__ __align__(128) unsigned char smem[];
@@ -237,11 +281,16 @@ __global__ void __launch_bounds__((S2_WARPS + 1) * 32) stream2d_kernel(const __g
         if (warp == S2_WARPS) {
             // ---------------- producer ----------------
             if (lane == 0) {
-                const bool lh = x0b > 0 || p.bc0 == SB200_WRAP;
-                const bool rh = x0b + wbytes < Wb || p.bc0 == SB200_WRAP;
-                const int lxb = x0b > 0 ? x0b - C::HLB : Wb - C::HLB;
-                const int rxb = x0b + wbytes < Wb ? x0b + wbytes : 0;
-                const int rbytes = rh ? min(C::HLB, Wb - rxb) : 0;  // a narrow last strip may end inside the halo
+                // One bulk copy per row covers the strip plus the halo cells that are ordinary neighbours in the row
+                // (a narrow last strip may end inside the right halo); only the wrapped halo of an array-edge strip
+                // needs its own copy.
+                const bool l_in = x0b > 0, r_in = x0b + wbytes < Wb;
+                const bool l_wrap = !l_in && p.bc0 == SB200_WRAP, r_wrap = !r_in && p.bc0 == SB200_WRAP;
+                const int r_in_bytes = r_in ? min(C::HLB, Wb - (x0b + wbytes)) : 0;
+                const int mstart = x0b - (l_in ? C::HLB : 0), mdst = C::LEFT - (l_in ? C::HLB : 0);
+                const unsigned mlen = wbytes + (l_in ? C::HLB : 0) + r_in_bytes;
+                const int wrap_bytes = min(C::HLB, Wb);
+                const unsigned rowbytes = mlen + (l_wrap ? wrap_bytes : 0) + (r_wrap ? wrap_bytes : 0);
                 for (int c = 0; c < nchunks; c++, k++) {
                     const int slot = k % C::STAGES;
                     mbar_wait(&empty[slot], ((k / C::STAGES) & 1) ^ 1);
@@ -252,7 +301,7 @@ __global__ void __launch_bounds__((S2_WARPS + 1) * 32) stream2d_kernel(const __g
                     for (int j = 0; j < CH; j++) {
                         const int i = c * CH + j;
                         prow[j] = i < nsrc ? s2_map_row(p, y0 - R + i) : -1;
-                        if (prow[j] >= 0) bytes += wbytes + (lh ? C::HLB : 0) + rbytes;
+                        if (prow[j] >= 0) bytes += rowbytes;
                     }
                     mbar_arrive_expect_tx(&full[slot], bytes);
 #pragma unroll
@@ -260,9 +309,9 @@ __global__ void __launch_bounds__((S2_WARPS + 1) * 32) stream2d_kernel(const __g
                         if (prow[j] < 0) continue;
                         const unsigned char* g = reinterpret_cast<const unsigned char*>(p.src + prow[j] * p.spitch);
                         unsigned char* srow = sbase + j * C::ROWB;
-                        bulk_g2s(srow + C::HLB, g + x0b, wbytes, &full[slot]);
-                        if (lh) bulk_g2s(srow, g + lxb, C::HLB, &full[slot]);
-                        if (rbytes) bulk_g2s(srow + C::HLB + wbytes, g + rxb, rbytes, &full[slot]);
+                        bulk_g2s(srow + mdst, g + mstart, mlen, &full[slot]);
+                        if (l_wrap) bulk_g2s(srow + C::LEFT - wrap_bytes, g + Wb - wrap_bytes, wrap_bytes, &full[slot]);
+                        if (r_wrap) bulk_g2s(srow + C::LEFT + wbytes, g, wrap_bytes, &full[slot]);
                     }
                 }
             } else {

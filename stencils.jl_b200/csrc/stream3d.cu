@@ -5,7 +5,7 @@
 // rows and marches along z. The 32 lanes of a producer warp issue cp.async.bulk (UBLKCP) copies of one z-plane
 // of the tile (+1 halo row above/below, +16 B halo left/right) per stage into a ring of shared-memory stages;
 // every boundary (Wrap / Reflect on y and z, ghost planes, the Wrap column halo) is resolved by the producer
-// choosing source addresses. A consumer thread owns 16 bytes of x by 4 rows and keeps, per cell, the centre value
+// choosing source addresses. A consumer thread owns 16 bytes of x by S3_RT rows and keeps, per cell, the centre value
 // of the previous plane and the partial fold (((zm + ym) + xm) + xp) + yp of the previous plane in registers; when
 // plane z+1 arrives it adds zp and stores plane z. The fold order is the reference's offset order, every
 // operation rounded separately (bit-identical to the Julia left fold).
@@ -21,9 +21,10 @@ constexpr int S3_WARPS = S3_WX * S3_WY;
 constexpr int S3_TXB = S3_WX * 512;             // tile width in bytes
 constexpr int S3_RT = 4;                        // rows per thread
 constexpr int S3_TY = S3_WY * S3_RT;            // tile height in rows
-constexpr int S3_ROWB = S3_TXB + 32;            // shared-memory row: 16 B halo | tile | 16 B halo
+constexpr int S3_LEFT = 128;                    // margin (halo at its end): global and shared addresses agree mod 128
+constexpr int S3_ROWB = S3_LEFT + S3_TXB + 128;  // shared-memory row: margin | tile | margin
 constexpr int S3_STAGE = (S3_TY + 2) * S3_ROWB;
-constexpr int S3_STAGES = 5;
+constexpr int S3_STAGES = 4;
 constexpr int S3_SMEM = 128 + S3_STAGES * S3_STAGE;
 
 template <typename T> struct S3Params {
@@ -82,11 +83,14 @@ __global__ void __launch_bounds__((S3_WARPS + 1) * 32) stream3d_kernel(const __g
         const int nsrc = z1 - z0 + 2;  // source planes z0-1 .. z1
         if (warp == S3_WARPS) {
             // ---------------- producer warp: lane j copies row j of the plane ----------------
-            const bool lh = x0b > 0 || p.bc0 == SB200_WRAP;
-            const bool rh = x0b + wbytes < Xb || p.bc0 == SB200_WRAP;
-            const int lxb = x0b > 0 ? x0b - 16 : Xb - 16;
-            const int rxb = x0b + wbytes < Xb ? x0b + wbytes : 0;
-            const unsigned rowbytes = wbytes + (lh ? 16 : 0) + (rh ? 16 : 0);
+            // One bulk copy per row covers the tile plus the halo cells that are ordinary neighbours in the row; only
+            // the wrapped halo of an array-edge tile needs its own (16-byte) copy.
+            const bool l_in = x0b > 0, r_in = x0b + wbytes < Xb;
+            const bool l_wrap = !l_in && p.bc0 == SB200_WRAP, r_wrap = !r_in && p.bc0 == SB200_WRAP;
+            const int mstart = x0b - (l_in ? 16 : 0);
+            const unsigned mlen = wbytes + (l_in ? 16 : 0) + (r_in ? 16 : 0);
+            const int mdst = S3_LEFT - (l_in ? 16 : 0);
+            const unsigned rowbytes = mlen + (l_wrap ? 16 : 0) + (r_wrap ? 16 : 0);
             // Lane j owns shared-memory row j = logical row y0-1+j (same mapping for every plane). Rows below the
             // halo row of a ragged last tile are never read.
             long long yrow = -1;
@@ -106,9 +110,9 @@ __global__ void __launch_bounds__((S3_WARPS + 1) * 32) stream3d_kernel(const __g
                 if (zpl >= 0 && yrow >= 0) {
                     const unsigned char* g = reinterpret_cast<const unsigned char*>(p.src + zpl * p.sp2 + yrow * p.sp1);
                     unsigned char* srow = ring + slot * S3_STAGE + lane * S3_ROWB;
-                    bulk_g2s(srow + 16, g + x0b, wbytes, &full[slot]);
-                    if (lh) bulk_g2s(srow, g + lxb, 16, &full[slot]);
-                    if (rh) bulk_g2s(srow + 16 + wbytes, g + rxb, 16, &full[slot]);
+                    bulk_g2s(srow + mdst, g + mstart, mlen, &full[slot]);
+                    if (l_wrap) bulk_g2s(srow + S3_LEFT - 16, g + Xb - 16, 16, &full[slot]);
+                    if (r_wrap) bulk_g2s(srow + S3_LEFT + wbytes, g, 16, &full[slot]);
                 }
             }
             continue;
@@ -134,7 +138,7 @@ __global__ void __launch_bounds__((S3_WARPS + 1) * 32) stream3d_kernel(const __g
             const int z = z0 - 1 + i;                  // logical plane held by this stage
             const bool zpad = pad2 && (z < 0 || z >= p.Z);
             mbar_wait(&full[slot], (k / S3_STAGES) & 1);
-            const unsigned char* sb_ = ring + slot * S3_STAGE + 16 + xtb;
+            const unsigned char* sb_ = ring + slot * S3_STAGE + S3_LEFT + xtb;
             // rows ry0-1 .. ry0+RT of the tile  (shared-memory row index = tile row + 1)
             T rowv[S3_RT + 2][VX];
             T xl[S3_RT], xr[S3_RT];
