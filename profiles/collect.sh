@@ -9,7 +9,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file
 ncu --set full --clock-control none --import-source on -k regex:life_tma -s 6 -c 1 -o gpurun_out/${R}_life \
     python bench.py --steps 10 --warmup 3 --no-extras > /dev/null 2>&1
 for wl in mean kernel circle scatter diffusion; do
-  ncu --set full --clock-control none --import-source on -k regex:"stream2d|stream3d|scatter_fast" -s 3 -c 1 -o gpurun_out/${R}_${wl} \
+  ncu --set full --clock-control none --import-source on -k regex:"stream2d|stream3d|scatter_fast|scatter_stream" -s 3 -c 1 -o gpurun_out/${R}_${wl} \
       python bench.py --workload ${wl} --steps 4 --warmup 3 --no-extras > /dev/null 2>&1
 done
 ls -la gpurun_out

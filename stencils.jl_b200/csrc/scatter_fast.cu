@@ -107,7 +107,10 @@ template <typename T> static int sf_run(const Plan& pl, const void* src, void* d
     const bool vec = ((uintptr_t)dst % 16 == 0) && (p.dstr[1] % VX == 0) && (p.doff[0] % VX == 0);
     if (vec && x_lo % VX) x_lo = std::min(x_hi, (x_lo + VX - 1) / VX * VX);
     int rc;
-    if (x_hi > x_lo && y_hi > y_lo) {
+    bool streamed = false;
+    if (x_hi > x_lo && y_hi > y_lo && try_scatter_stream(pl, src, dst, st, x_lo, x_hi, y_lo, y_hi) == SB200_OK) {
+        streamed = true;  // interior done by the TMA-fed streaming kernel (scatter_stream.cu)
+    } else if (x_hi > x_lo && y_hi > y_lo) {
         const long long total = (long long)((x_hi - x_lo + VX - 1) / VX) * (y_hi - y_lo);
         const long long blocks = std::min<long long>((total + 255) / 256, (long long)num_sms() * 16);
         if (vec) scatter_fast_kernel<T, true><<<(unsigned)blocks, 256, 0, st>>>(p, pl.scatter_order_dev, (const T*)src, (T*)dst, x_lo, x_hi, y_lo, y_hi);
@@ -122,7 +125,7 @@ template <typename T> static int sf_run(const Plan& pl, const void* src, void* d
     if ((rc = launch_generic_scatter_rect(pl, src, dst, st, 0, ny, y_hi, nx))) return rc;
     if ((rc = launch_generic_scatter_rect(pl, src, dst, st, 0, x_lo, y_lo, y_hi))) return rc;
     if ((rc = launch_generic_scatter_rect(pl, src, dst, st, x_hi, ny, y_lo, y_hi))) return rc;
-    set_kernel_name("scatter_fast_kernel");
+    set_kernel_name(streamed ? "scatter_stream_kernel" : "scatter_fast_kernel");
     return SB200_OK;
 }
 

@@ -141,13 +141,20 @@ template <typename T> struct S2Thread {
     T* dt;          // dest pointer of (row y0, column gx)
 };
 
+// Large folds (R >= 2) keep ONE copy of the row code and shift the accumulators through registers after every row
+// (2R+1 register moves per cell against L folds): the fully unrolled rotation of a 7x7 or Circle(4) fold is > 100 KB
+// of SASS and stalls on instruction fetch. R == 1 keeps the rotation by renaming (period-P unrolled rows).
+template <int R> struct S2Roll { static constexpr bool value = R >= 2; };
+
 // Fold source row J of the current stage (stream index i0 + J) into the 2R+1 outputs it belongs to.
-template <typename T, int SHAPE, int R, int RED, int J>
+template <typename T, int SHAPE, int R, int RED, int J_>
 __device__ __forceinline__ void s2_row(const S2Params<T>& p, const S2Thread<T>& th, const unsigned char* sbase, int i0,
-                                       T (&acc)[2 * R + 1][16 / sizeof(T)], T (&cen)[2 * R + 1][16 / sizeof(T)]) {
+                                       T (&acc)[2 * R + 1][16 / sizeof(T)], T (&cen)[2 * R + 1][16 / sizeof(T)], int jrt = 0) {
     using C = S2Cfg<T, R>;
     constexpr int VX = C::VX, P = C::P, SEG = C::SEG, L = s2_count(SHAPE, R);
     constexpr int DY0 = s2_first_dy(SHAPE, R), DY1 = s2_last_dy(SHAPE, R);
+    constexpr bool ROLL = S2Roll<R>::value;
+    const int J = ROLL ? jrt : J_;   // row of the stage: run time in the rolled form
     const int i = i0 + J;            // stream index of this source row
     const int r = th.y0 - R + i;     // logical source row
     // ---- segment: cells gx-R .. gx+VX-1+R of the row ----
@@ -200,7 +207,9 @@ __device__ __forceinline__ void s2_row(const S2Params<T>& p, const S2Thread<T>& 
     for (int d = 0; d < P; d++) {
         const int dy = d - R;
         if (dy < DY0 || dy > DY1) continue;
-        const int s = ((J - d) % P + P) % P;  // compile-time: stages hold a multiple of P rows
+        // accumulator of output o = i - d: slot d when the accumulators are shifted after every row, else the
+        // compile-time rotation (stages hold a multiple of P rows)
+        const int s = ROLL ? d : ((J_ - d) % P + P) % P;
         if (NESTED) {
             const int hw = s2_row_halfwidth(SHAPE, R, dy);
 #pragma unroll
@@ -242,13 +251,27 @@ __device__ __forceinline__ void s2_row(const S2Params<T>& p, const S2Thread<T>& 
             if (o >= 0 && o < th.nout && th.active) s2_stvec(th.dt + (long long)o * p.dpitch, out);
         }
     }
+    if (ROLL) {
+#pragma unroll
+        for (int d = P - 1; d >= 1; d--)
+#pragma unroll
+            for (int v = 0; v < VX; v++) {
+                acc[d][v] = acc[d - 1][v];
+                if (RED == SB200_DIFFUSION) cen[d][v] = cen[d - 1][v];
+            }
+    }
 }
 
 template <typename T, int SHAPE, int R, int RED, int J> struct S2Rows {
     static __device__ __forceinline__ void run(const S2Params<T>& p, const S2Thread<T>& th, const unsigned char* sbase, int i0,
                                                T (&acc)[2 * R + 1][16 / sizeof(T)], T (&cen)[2 * R + 1][16 / sizeof(T)]) {
-        s2_row<T, SHAPE, R, RED, J>(p, th, sbase, i0, acc, cen);
-        if constexpr (J + 1 < S2Cfg<T, R>::CH) S2Rows<T, SHAPE, R, RED, J + 1>::run(p, th, sbase, i0, acc, cen);
+        if constexpr (S2Roll<R>::value) {
+#pragma unroll 1
+            for (int j = 0; j < S2Cfg<T, R>::CH; j++) s2_row<T, SHAPE, R, RED, 0>(p, th, sbase, i0, acc, cen, j);
+        } else {
+            s2_row<T, SHAPE, R, RED, J>(p, th, sbase, i0, acc, cen);
+            if constexpr (J + 1 < S2Cfg<T, R>::CH) S2Rows<T, SHAPE, R, RED, J + 1>::run(p, th, sbase, i0, acc, cen);
+        }
     }
 };
 

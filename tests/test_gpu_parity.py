@@ -183,6 +183,27 @@ def test_scatter(orc, bc, op, dt):
                     bits_equal(gpu_scatter(h, src, dest0.copy(order="F")), want)
 
 
+@pytest.mark.parametrize("bc", ["remove", "wrap", "reflect"])
+@pytest.mark.parametrize("dt", [np.float32, np.float64, np.int64])
+def test_scatter_stream_strips_and_runs(orc, bc, dt):
+    """Several strips (ragged last one), several runs per strip, taps crossing strip edges: the TMA-fed kernel."""
+    rng = np.random.default_rng(24)
+    for offs, R, (ny, nx) in [([(-1, 1), (-2, -1), (1, 0), (-2, 2)], 2, (2600, 75)),
+                              (npr.offsets("Window", 1, 2), 1, (1028, 300)),
+                              (npr.offsets("Circle", 3, 2), 3, (1100, 63))]:
+        src = rand_array(rng, (ny, nx), dt)
+        w = (rng.random(len(offs)) if np.dtype(dt).kind == "f" else rng.integers(1, 5, len(offs))).astype(dt)
+        dest0 = rand_array(rng, (ny, nx), dt)
+        et = A.ELTYPE_OF_DTYPE[np.dtype(dt)]
+        for op, rule, flags in [(A.OP_ADD, A.SCATTER_CENTER_WEIGHTS, 0), (A.OP_MAX, A.SCATTER_CENTER_WEIGHTS, A.FLAG_ZERO_DEST),
+                                (A.OP_MIN, A.SCATTER_WEIGHTS, 0)]:
+            h = build_desc(size=(ny, nx), eltype=et, out_eltype=et, offsets=offs, radius=R, boundary=BC[bc], weights=w,
+                           scatter_op=op, scatter_rule=rule, flags=flags)
+            want = orc.scatter(h, src, dest0.copy(order="F"))
+            bits_equal(gpu_scatter(h, src, dest0.copy(order="F")), want)
+            assert A.lib().sb200_last_kernel().decode() == "scatter_stream_kernel"
+
+
 def test_iterate_life_and_diffusion(orc):
     from tests.util import stream, sync, to_dev, to_host
     rng = np.random.default_rng(15)
