@@ -138,13 +138,17 @@ template <typename T> struct S2Thread {
     int gx;         // global column of the thread's first cell
     int y0, nout;   // first output row of the run, number of output rows
     bool active, edge_l, edge_r, may_pad;
+    int nl, rlim;   // Remove on axis 0: halo cells e < nl (left) and e >= rlim (right) of the segment are out of bounds
     T* dt;          // dest pointer of (row y0, column gx)
 };
 
 // Large folds (R >= 2) keep ONE copy of the row code and shift the accumulators through registers after every row
 // (2R+1 register moves per cell against L folds): the fully unrolled rotation of a 7x7 or Circle(4) fold is > 100 KB
 // of SASS and stalls on instruction fetch. R == 1 keeps the rotation by renaming (period-P unrolled rows).
-template <int R> struct S2Roll { static constexpr bool value = R >= 2; };
+template <int SHAPE, int R, int RED> struct S2Roll {
+    static constexpr bool nested = (RED == SB200_MAX || RED == SB200_MIN) && s2_convex_rows(SHAPE, R);  // small code
+    static constexpr bool value = R >= 2 && !nested;
+};
 
 // Fold source row J of the current stage (stream index i0 + J) into the 2R+1 outputs it belongs to.
 template <typename T, int SHAPE, int R, int RED, int J_>
@@ -153,7 +157,7 @@ __device__ __forceinline__ void s2_row(const S2Params<T>& p, const S2Thread<T>& 
     using C = S2Cfg<T, R>;
     constexpr int VX = C::VX, P = C::P, SEG = C::SEG, L = s2_count(SHAPE, R);
     constexpr int DY0 = s2_first_dy(SHAPE, R), DY1 = s2_last_dy(SHAPE, R);
-    constexpr bool ROLL = S2Roll<R>::value;
+    constexpr bool ROLL = S2Roll<SHAPE, R, RED>::value;
     const int J = ROLL ? jrt : J_;   // row of the stage: run time in the rolled form
     const int i = i0 + J;            // stream index of this source row
     const int r = th.y0 - R + i;     // logical source row
@@ -170,7 +174,14 @@ __device__ __forceinline__ void s2_row(const S2Params<T>& p, const S2Thread<T>& 
             seg[e] = *reinterpret_cast<const T*>(t - (R - e) * (int)sizeof(T));
             seg[R + VX + e] = *reinterpret_cast<const T*>(t + (VX + e) * (int)sizeof(T));
         }
-        if (th.edge_l || th.edge_r) {
+        if (p.bc0 == SB200_REMOVE) {
+            // branch-free: a divergent patch loop on the one edge warp would pace its whole CTA
+#pragma unroll
+            for (int e = 0; e < R; e++) {
+                seg[e] = e < th.nl ? p.pad : seg[e];
+                seg[R + VX + e] = e >= th.rlim ? p.pad : seg[R + VX + e];
+            }
+        } else if (th.edge_l || th.edge_r) {
             const unsigned char* row0 = sbase + J * C::ROWB + C::LEFT - th.x0b;  // address of global column 0
 #pragma unroll
             for (int e = 0; e < SEG; e++) {
@@ -265,7 +276,7 @@ __device__ __forceinline__ void s2_row(const S2Params<T>& p, const S2Thread<T>& 
 template <typename T, int SHAPE, int R, int RED, int J> struct S2Rows {
     static __device__ __forceinline__ void run(const S2Params<T>& p, const S2Thread<T>& th, const unsigned char* sbase, int i0,
                                                T (&acc)[2 * R + 1][16 / sizeof(T)], T (&cen)[2 * R + 1][16 / sizeof(T)]) {
-        if constexpr (S2Roll<R>::value) {
+        if constexpr (S2Roll<SHAPE, R, RED>::value) {
 #pragma unroll 1
             for (int j = 0; j < S2Cfg<T, R>::CH; j++) s2_row<T, SHAPE, R, RED, 0>(p, th, sbase, i0, acc, cen, j);
         } else {
@@ -352,6 +363,8 @@ __global__ void __launch_bounds__((S2_WARPS + 1) * 32, (RED == SB200_KERNELDOT &
         // (under Wrap the producer already copied the wrapped columns).
         th.edge_l = th.active && p.bc0 != SB200_WRAP && th.gx - R < 0;
         th.edge_r = th.active && p.bc0 != SB200_WRAP && th.gx + VX - 1 + R >= p.W;
+        th.nl = R - th.gx;                 // > 0 only next to the left edge
+        th.rlim = p.W - th.gx - VX;        // < R only next to the right edge
         th.y0 = y0; th.nout = nout;
         th.may_pad = p.soff1 == 0 && p.bc1 == SB200_REMOVE;
         th.dt = p.dst + (long long)(y0 + p.doff1) * p.dpitch + p.doff0 + th.gx;
@@ -391,7 +404,8 @@ int s2_launch(const S2Params<T>& p0, cudaStream_t st) {
     const int Wb = p.W * (int)sizeof(T);
     p.nstrips = (Wb + S2_BXB - 1) / S2_BXB;
     const long long ctas = (long long)ctas_per_sm * num_sms();
-    long long nruns = std::max<long long>(1, ctas / p.nstrips);
+    // four tasks per CTA, interleaved: every SM stays busy and the tail is a quarter of a task
+    long long nruns = std::max<long long>(1, (4 * ctas + p.nstrips - 1) / p.nstrips);
     nruns = std::min<long long>(nruns, std::max(1, p.rows / (4 * C::P)));  // keep the 2R re-read rows per run small
     p.nruns = (int)nruns;
     const long long grid = std::min<long long>(ctas, (long long)p.nstrips * p.nruns);

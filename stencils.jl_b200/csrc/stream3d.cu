@@ -37,6 +37,7 @@ template <typename T> struct S3Params {
     T pad, alpha;
     int z_lo, zn;                  // output planes [z_lo, z_lo + zn)
     int ntx, nty, nzruns;
+    int ty;                        // rows per tile (<= S3_TY): chosen so that the tiles fill whole waves of CTAs
 };
 
 __device__ __forceinline__ long long s3_map(int r, int n, int off, int bc) {
@@ -76,7 +77,7 @@ __global__ void __launch_bounds__((S3_WARPS + 1) * 32) stream3d_kernel(const __g
     unsigned k = 0;
     for (int task = blockIdx.x; task < ntasks; task += gridDim.x) {
         const int tile = task % ntiles, zrun = task / ntiles;
-        const int x0b = (tile % p.ntx) * S3_TXB, y0 = (tile / p.ntx) * S3_TY;
+        const int x0b = (tile % p.ntx) * S3_TXB, y0 = (tile / p.ntx) * p.ty;
         const int wbytes = min(S3_TXB, Xb - x0b);
         const int z0 = p.z_lo + (int)((long long)p.zn * zrun / p.nzruns);
         const int z1 = p.z_lo + (int)((long long)p.zn * (zrun + 1) / p.nzruns);
@@ -94,7 +95,7 @@ __global__ void __launch_bounds__((S3_WARPS + 1) * 32) stream3d_kernel(const __g
             // Lane j owns shared-memory row j = logical row y0-1+j (same mapping for every plane). Rows below the
             // halo row of a ragged last tile are never read.
             long long yrow = -1;
-            if (lane < S3_TY + 2) {
+            if (lane < p.ty + 2) {
                 const int y = y0 - 1 + lane;
                 if (y <= p.Y) yrow = s3_map(y, p.Y, p.so1, p.bc1);
             }
@@ -157,9 +158,16 @@ __global__ void __launch_bounds__((S3_WARPS + 1) * 32) stream3d_kernel(const __g
                 if (r >= 1 && r <= S3_RT) {
                     if (ypad) { xl[r - 1] = p.pad; xr[r - 1] = p.pad; }
                     else {
+                        // x neighbours across the 16-byte vectors come from the adjacent lanes (a scalar shared-memory
+                        // read with a 16-byte lane stride would be a 4-way bank conflict); only the warp's two end
+                        // lanes read the halo cells. ypad is warp-uniform, so every lane takes part in the shuffles.
                         const unsigned char* t = sb_ + (ry0 + r) * S3_ROWB;
-                        xl[r - 1] = *reinterpret_cast<const T*>(t - sizeof(T));
-                        xr[r - 1] = *reinterpret_cast<const T*>(t + 16);
+                        T l_ = __shfl_up_sync(0xffffffffu, rowv[r][VX - 1], 1);
+                        T r_ = __shfl_down_sync(0xffffffffu, rowv[r][0], 1);
+                        if (lane == 0) l_ = *reinterpret_cast<const T*>(t - sizeof(T));
+                        if (lane == 31) r_ = *reinterpret_cast<const T*>(t + 16);
+                        xl[r - 1] = l_;
+                        xr[r - 1] = r_;
                         if (edge_l) xl[r - 1] = p.bc0 == SB200_REFLECT ? rowv[r][1] : p.pad;
                         if (edge_r) xr[r - 1] = p.bc0 == SB200_REFLECT ? rowv[r][VX - 2] : p.pad;
                     }
@@ -190,7 +198,7 @@ __global__ void __launch_bounds__((S3_WARPS + 1) * 32) stream3d_kernel(const __g
                     cprev[r][v] = c;
                 }
                 const int y = y0 + ry0 + r;
-                if (store && xact && y < p.Y) {
+                if (store && xact && y < p.Y && ry0 + r < p.ty) {
                     T* d = dbase + (long long)(zo + p.do2) * p.dp2 + (long long)r * p.dp1;
                     if constexpr (VX == 4) *reinterpret_cast<float4*>(d) = make_float4(out[0], out[1], out[2], out[3]);
                     else *reinterpret_cast<double2*>(d) = make_double2(out[0], out[1]);
@@ -215,17 +223,23 @@ template <typename T, int RED> static int s3_launch(S3Params<T>& p, cudaStream_t
         cfg_dev = dev;
     }
     const long long ctas = (long long)ctas_per_sm * num_sms();
-    const long long ntiles = (long long)p.ntx * p.nty;
-    // z-runs: trade the 2 re-read planes per run against the idle tail of the last wave of tasks
-    int best = 1;
+    // Tile height and z-runs: a task loads (ty + 2) rows x (zn / nz + 2) planes; pick the pair that minimises
+    // waves x rows loaded per task (the idle tail of a partial last wave against re-read halo rows / planes).
+    int best_ty = S3_TY, best = 1;
     double best_cost = 1e300;
-    for (int nz = 1; nz <= 64 && nz <= std::max(1, p.zn / 4); nz++) {
-        const long long tasks = ntiles * nz;
-        const long long waves = (tasks + ctas - 1) / ctas;
-        const double cost = (double)waves * ((double)p.zn / nz + 2.0);
-        if (cost < best_cost * 0.999) { best_cost = cost; best = nz; }
+    for (int ty = S3_TY; ty >= S3_TY / 2; ty--) {
+        const long long nty = (p.Y + ty - 1) / ty;
+        for (int nz = 1; nz <= 64 && nz <= std::max(1, p.zn / 4); nz++) {
+            const long long tasks = (long long)p.ntx * nty * nz;
+            const long long waves = (tasks + ctas - 1) / ctas;
+            const double cost = (double)waves * (ty + 2.0) * ((double)p.zn / nz + 2.0);
+            if (cost < best_cost * 0.999) { best_cost = cost; best = nz; best_ty = ty; }
+        }
     }
+    p.ty = best_ty;
+    p.nty = (p.Y + best_ty - 1) / best_ty;
     p.nzruns = best;
+    const long long ntiles = (long long)p.ntx * p.nty;
     const long long grid = std::min<long long>(ctas, ntiles * p.nzruns);
     stream3d_kernel<T, RED><<<(unsigned)grid, (S3_WARPS + 1) * 32, S3_SMEM, st>>>(p);
     SB_LAUNCH_CHECK();
