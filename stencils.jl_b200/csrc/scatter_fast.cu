@@ -108,8 +108,12 @@ template <typename T> static int sf_run(const Plan& pl, const void* src, void* d
     if (vec && x_lo % VX) x_lo = std::min(x_hi, (x_lo + VX - 1) / VX * VX);
     int rc;
     bool streamed = false;
-    if (x_hi > x_lo && y_hi > y_lo && try_scatter_stream(pl, src, dst, st, x_lo, x_hi, y_lo, y_hi) == SB200_OK) {
+    // The streaming kernel also leaves the R cells next to each end of axis 0 to the band kernel: then every tap of
+    // every cell it owns exists and no warp runs a slower edge path that would pace its whole CTA.
+    const int sb0 = std::min(std::max(b0, R), ny / 2);
+    if (ny - 2 * sb0 > 0 && y_hi > y_lo && try_scatter_stream(pl, src, dst, st, sb0, ny - sb0, y_lo, y_hi) == SB200_OK) {
         streamed = true;  // interior done by the TMA-fed streaming kernel (scatter_stream.cu)
+        x_lo = sb0; x_hi = ny - sb0;
     } else if (x_hi > x_lo && y_hi > y_lo) {
         const long long total = (long long)((x_hi - x_lo + VX - 1) / VX) * (y_hi - y_lo);
         const long long blocks = std::min<long long>((total + 255) / 256, (long long)num_sms() * 16);

@@ -26,7 +26,9 @@ constexpr int SS_HDR = 256;                   // mbarriers
 constexpr int SS_TAB = 448;                  // (2R+1)*L entries of the ordered tap table (7 x 64)
 constexpr int SS_SMEM = SS_HDR + SS_TAB * 16 + SS_NS * SS_STAGE;
 
-template <typename T> struct SsTap { int o0, o1; T w; };  // padded to 16 bytes in shared memory
+// One ordered tap, 16 bytes in shared memory: byte shift of the source cell inside its column segment (-o0 cells),
+// ring distance of its source column from the oldest resident one (R - o1 stages), the offset itself, the weight.
+template <typename T> struct SsTap { short boff, d1, o0, o1; T w; };
 
 template <typename T> struct SsParams {
     const T* src;
@@ -69,8 +71,10 @@ __global__ void __launch_bounds__((SS_WARPS + 1) * 32, 2) scatter_stream_kernel(
     for (int e = threadIdx.x; e < S * L; e += blockDim.x) {
         const int k = p.order[e];
         SsTap<T>* t = reinterpret_cast<SsTap<T>*>(tabraw + e * 16);
-        t->o0 = p.offs[3 * k];
-        t->o1 = p.offs[3 * k + 1];
+        t->o0 = (short)p.offs[3 * k];
+        t->o1 = (short)p.offs[3 * k + 1];
+        t->boff = (short)(-p.offs[3 * k] * (int)sizeof(T));
+        t->d1 = (short)(R - p.offs[3 * k + 1]);
         t->w = p.weights[k];
     }
     __syncthreads();
@@ -124,7 +128,7 @@ __global__ void __launch_bounds__((SS_WARPS + 1) * 32, 2) scatter_stream_kernel(
         for (int v = 0; v < VX; v++) {
             const int x = gx0 + v * 32;
             inr[v] = x >= p.x_lo && x < p.x_hi;
-            plain = plain && inr[v] && x - R >= 0 && x + R < p.W;
+            plain = plain && (!inr[v] || (x - R >= 0 && x + R < p.W));  // cells outside the range are computed but never stored
         }
         const bool warp_plain = __all_sync(0xffffffffu, plain);
         // wait for the first 2R stages (source columns y0-R .. y0+R-1)
@@ -132,32 +136,40 @@ __global__ void __launch_bounds__((SS_WARPS + 1) * 32, 2) scatter_stream_kernel(
             const unsigned k = kb + i;
             mbar_wait(&full[k % SS_NS], (k / SS_NS) & 1);
         }
+        const unsigned char* mine = ring + SS_LEFT + e0 * (int)sizeof(T);   // this lane's first cell in slot 0
+        unsigned slot_t = kb % SS_NS;                                      // slot of stage t (source column y - R)
+        unsigned slot_d = (kb + 2 * R) % SS_NS;                            // slot of stage t + 2R (destination column y)
+        unsigned par_d = ((kb + 2 * R) / SS_NS) & 1;
         for (int t = 0; t < nout; t++) {
             const int y = y0 + t;
-            {
-                const unsigned k = kb + t + 2 * R;
-                mbar_wait(&full[k % SS_NS], (k / SS_NS) & 1);
-            }
-            const unsigned char* dseg = ring + ((kb + t + 2 * R) % SS_NS) * SS_STAGE + SS_SROWB;
+            mbar_wait(&full[slot_d], par_d);
             T acc[VX];
 #pragma unroll
             for (int v = 0; v < VX; v++)
-                acc[v] = p.zero_dest ? T(0) : *reinterpret_cast<const T*>(dseg + (e0 + v * 32) * (int)sizeof(T));
+                acc[v] = p.zero_dest ? T(0) : *reinterpret_cast<const T*>(ring + slot_d * SS_STAGE + SS_SROWB + (e0 + v * 32) * (int)sizeof(T));
             const unsigned char* tab = tabraw + (y % S) * L * 16;
-            for (int q = 0; q < L; q++) {
-                const SsTap<T> tp = *reinterpret_cast<const SsTap<T>*>(tab + q * 16);
-                const int sj = y - tp.o1;
-                if (sj < 0 || sj >= p.H) continue;  // that source column does not exist
-                // stage of source column sj: i = sj - (y0 - R) = t + R - o1
-                const unsigned k = kb + t + R - tp.o1;
-                const T* srow = reinterpret_cast<const T*>(ring + (k % SS_NS) * SS_STAGE + SS_LEFT) + e0 - tp.o0;
-                if (warp_plain) {
+            if (warp_plain && y - R >= 0 && y + R < p.H) {
+                // every source of every tap exists: no per-tap tests, loads of four taps in flight
+#pragma unroll 4
+                for (int q = 0; q < L; q++) {
+                    const SsTap<T> tp = *reinterpret_cast<const SsTap<T>*>(tab + q * 16);
+                    unsigned sl = slot_t + tp.d1;
+                    sl = sl >= SS_NS ? sl - SS_NS : sl;
+                    const T* srow = reinterpret_cast<const T*>(mine + sl * SS_STAGE + tp.boff);
 #pragma unroll
                     for (int v = 0; v < VX; v++) {
                         const T val = MULC ? mul_rn(srow[v * 32], tp.w) : tp.w;
                         acc[v] = ss_fold<T, OP>(acc[v], val);
                     }
-                } else {
+                }
+            } else {
+                for (int q = 0; q < L; q++) {
+                    const SsTap<T> tp = *reinterpret_cast<const SsTap<T>*>(tab + q * 16);
+                    const int sj = y - tp.o1;
+                    if (sj < 0 || sj >= p.H) continue;  // that source column does not exist
+                    unsigned sl = slot_t + tp.d1;
+                    sl = sl >= SS_NS ? sl - SS_NS : sl;
+                    const T* srow = reinterpret_cast<const T*>(mine + sl * SS_STAGE + tp.boff);
 #pragma unroll
                     for (int v = 0; v < VX; v++) {
                         const int si = gx0 + v * 32 - tp.o0;
@@ -173,7 +185,9 @@ __global__ void __launch_bounds__((SS_WARPS + 1) * 32, 2) scatter_stream_kernel(
             for (int v = 0; v < VX; v++)
                 if (inr[v]) drow[v * 32] = acc[v];
             __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[(kb + t) % SS_NS]);  // source column y-R is done
+            if (lane == 0) mbar_arrive(&empty[slot_t]);  // source column y-R is done
+            if (++slot_t == SS_NS) slot_t = 0;
+            if (++slot_d == SS_NS) { slot_d = 0; par_d ^= 1; }
         }
         // release the 2R trailing stages
         __syncwarp();
