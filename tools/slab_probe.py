@@ -18,13 +18,14 @@ def t_iter(n):
     e0.record(); S = sb.iterate_(sb.Life(), S, n); e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / n
 t_iter(20)
-print('sb200_iterate          ms/step', t_iter(1000))
+N = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
+print("sb200_iterate          ms/step", t_iter(N))
 t = field.permute(1, 0).contiguous()
-for G in (1, 16, 64):
+for G in ((1, 16, 64) if N > 100 else (16,)):
     it = SlabIterator(t, offsets=Moore(1).offsets(), radius=1, reducer=A.LIFE, boundary=(A.WRAP, A.WRAP), eltype=A.U8, ghost=G,
                       rank=0, world=1, reducer_kwargs=dict(born_mask=8, survive_mask=12))
     it.step(2 * G + 4); torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    w0 = time.perf_counter(); e0.record(); it.step(1024); e1.record(); w1 = time.perf_counter(); torch.cuda.synchronize()
-    print(f'slab world=1 G={G:3d}     ms/step', e0.elapsed_time(e1) / 1024, ' host enqueue ms/step', (w1 - w0) / 1024 * 1e3, A.lib().sb200_last_kernel().decode())
+    w0 = time.perf_counter(); e0.record(); it.step(N); e1.record(); w1 = time.perf_counter(); torch.cuda.synchronize()
+    print(f'slab world=1 G={G:3d}     ms/step', e0.elapsed_time(e1) / N, ' host enqueue ms/step', (w1 - w0) / N * 1e3, A.lib().sb200_last_kernel().decode())
     del it
