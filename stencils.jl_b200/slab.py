@@ -21,15 +21,113 @@ decomposition / exchange logic is tested without GPUs (tests/test_slab_gloo.py).
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 
 from . import _abi as A
 from ._desc import build_desc
 
 
+class PeerMailbox:
+    """Ghost-plane exchange over peer memory (NVLink P2P stores) instead of NCCL send/recv.
+
+    Every rank owns one device allocation (sb200_malloc, exported with a CUDA IPC handle and opened by its two
+    neighbours): two flag words and, per side (0 = planes arriving from the rank below, 1 = from the rank above),
+    two landing slots of G planes used alternately. An exchange is, per neighbour, ONE kernel on the sender
+    (sb200_push_planes: 128-bit stores of its boundary planes straight into the neighbour's landing slot, then a
+    system-scope release of the neighbour's flag) and a stream-ordered acquire wait + local copy on the receiver
+    (sb200_wait_flag, sb200_memcpy_d2d). Two slots suffice without credits: a rank can only start exchange c + 2
+    after it has received its neighbour's planes of exchange c + 1, which the neighbour sent after it had emptied
+    slot c."""
+    FLAGS = 256  # bytes reserved for the flag words
+
+    def __init__(self, plane_bytes, G, rank, world, wrap):
+        import ctypes as C
+        import torch.distributed as dist
+        self.C = C
+        self.lib = A.lib()
+        self.nbytes = int(plane_bytes) * G            # one landing slot
+        self.rank, self.world = rank, world
+        total = self.FLAGS + 4 * self.nbytes
+        self.base, self.peer, self.seq = 0, {}, 0
+        self.up = (rank + 1) % world if (wrap or rank < world - 1) else None
+        self.down = (rank - 1) % world if (wrap or rank > 0) else None
+        # every rank takes part in both collectives below whatever happens locally, so a rank whose driver refuses
+        # IPC cannot leave the others waiting; `ok` is agreed on by all ranks (SlabIterator falls back to NCCL)
+        mine = None
+        try:
+            base = C.c_void_p()
+            A.check(self.lib.sb200_malloc(C.byref(base), total))
+            self.base = base.value
+            A.check(self.lib.sb200_memset(base, 0, total, None))
+            A.check(self.lib.sb200_stream_sync(None))
+            handle = (C.c_ubyte * 64)()
+            A.check(self.lib.sb200_ipc_export(base, handle))
+            mine = bytes(handle)
+        except Exception:
+            mine = None
+        handles = [None] * world
+        dist.all_gather_object(handles, mine)
+        good = all(h is not None for h in handles)
+        if good:
+            try:
+                for r in {self.up, self.down} - {None}:
+                    if r == rank:
+                        self.peer[r] = self.base
+                        continue
+                    ptr = C.c_void_p()
+                    buf = (C.c_ubyte * 64).from_buffer_copy(handles[r])
+                    A.check(self.lib.sb200_ipc_import(buf, C.byref(ptr)))
+                    self.peer[r] = ptr.value
+            except Exception:
+                good = False
+        votes = [None] * world
+        dist.all_gather_object(votes, good)
+        self.ok = all(votes)
+        if not self.ok:
+            self.close()
+
+    def slot(self, base, side, parity):
+        return base + self.FLAGS + (2 * side + parity) * self.nbytes
+
+    def flag(self, base, side):
+        return base + 4 * side
+
+    def push(self, top_ptr, bottom_ptr, stream):
+        """Send my top owned planes up and my bottom owned planes down (exchange number self.seq + 1)."""
+        self.seq += 1
+        par = self.seq & 1
+        if self.up is not None:   # arrives at `up` from below: side 0
+            pb = self.peer[self.up]
+            A.check(self.lib.sb200_push_planes(top_ptr, self.slot(pb, 0, par), self.nbytes, self.flag(pb, 0), self.seq, stream))
+        if self.down is not None:  # arrives at `down` from above: side 1
+            pb = self.peer[self.down]
+            A.check(self.lib.sb200_push_planes(bottom_ptr, self.slot(pb, 1, par), self.nbytes, self.flag(pb, 1), self.seq, stream))
+
+    def pull(self, ghost_bottom_ptr, ghost_top_ptr, stream):
+        """Wait for exchange self.seq from both neighbours and move the planes into my ghost zones."""
+        par = self.seq & 1
+        if self.down is not None:  # planes from below -> my bottom ghost
+            A.check(self.lib.sb200_wait_flag(self.flag(self.base, 0), self.seq, stream))
+            A.check(self.lib.sb200_memcpy_d2d(ghost_bottom_ptr, self.slot(self.base, 0, par), self.nbytes, stream))
+        if self.up is not None:    # planes from above -> my top ghost
+            A.check(self.lib.sb200_wait_flag(self.flag(self.base, 1), self.seq, stream))
+            A.check(self.lib.sb200_memcpy_d2d(ghost_top_ptr, self.slot(self.base, 1, par), self.nbytes, stream))
+
+    def close(self):
+        for r, ptr in self.peer.items():
+            if r != self.rank:
+                self.lib.sb200_ipc_close(ptr)
+        self.peer = {}
+        if self.base:
+            self.lib.sb200_free(self.base)
+            self.base = 0
+
+
 class SlabIterator:
     def __init__(self, local_owned, *, offsets, radius, reducer, boundary, eltype, ghost=None, rank=0, world=1,
-                 compute=None, reducer_kwargs=None, padval=0):
+                 compute=None, reducer_kwargs=None, padval=0, exchange="auto"):
         """local_owned: torch tensor holding this rank's slab in column-major layout, i.e. a C-contiguous torch
         tensor of shape reversed(logical shape) (split axis first). boundary: per-axis sb200 enums of the GLOBAL
         array. compute(desc_handle, src_tensor, dst_tensor): sweep backend; None = libstencils_b200 on the
@@ -77,6 +175,16 @@ class SlabIterator:
             self.comm_stream = torch.cuda.Stream(device=t.device)
         self.steps_since_exchange = self.k  # ghosts are not valid yet
         self.launches = 0
+        # ghost exchange: peer-memory stores over NVLink when the ranks can open each other's memory, else NCCL
+        self.mailbox = None
+        self.exchange = "local" if world == 1 else ("nccl" if self.is_cuda else "gloo")
+        if world > 1 and self.is_cuda and exchange in ("auto", "p2p"):
+            plane_bytes = t[0].numel() * t.element_size()
+            mb = PeerMailbox(plane_bytes, self.G, rank, world, self.bc_split == A.WRAP)
+            if mb.ok:
+                self.mailbox, self.exchange = mb, "p2p"
+            elif exchange == "p2p":
+                raise A.SB200Error(A.ECUDA, "CUDA IPC peer access is not available between the ranks")
 
     # ---- helpers ----
     def _desc(self, lo_plane, hi_plane):
@@ -148,6 +256,11 @@ class SlabIterator:
             if self.bc_split == A.WRAP:
                 buf[:G].copy_(buf[n:n + G])
                 buf[G + n:].copy_(buf[G:2 * G])
+        elif self.mailbox is not None:
+            G, n = self.G, self.n_local
+            stream = self.torch.cuda.current_stream().cuda_stream
+            self.mailbox.push(buf[n:n + G].data_ptr(), buf[G:2 * G].data_ptr(), stream)
+            self.mailbox.pull(buf[:G].data_ptr(), buf[G + n:].data_ptr(), stream)
         else:
             ops = self._exchange_ops(buf)
             if ops:
@@ -229,7 +342,7 @@ def bench_weak(workload, spec, steps, warmup, synth=None):
     else:
         raise SystemExit(f"workload {workload} is not an iterated (slab-partitioned) configuration")
     it = SlabIterator(t, offsets=st.offsets(), radius=R, reducer=red, boundary=bcs, eltype=et, ghost=ghost, rank=rank,
-                      world=world, reducer_kwargs=kw)
+                      world=world, reducer_kwargs=kw, exchange=os.environ.get("SB200_EXCHANGE", "auto"))
     del t
     lib = A.lib()
     it.step(warmup)
@@ -246,6 +359,8 @@ def bench_weak(workload, spec, steps, warmup, synth=None):
     dist.barrier()
     ms = e0.elapsed_time(e1)
     launches = lib.sb200_launch_count(1)
-    cfg = {"ghost_planes": ghost, "steps_per_exchange": ghost // R, "exchange": "NCCL send/recv on a side stream, "
-           "overlapped with the interior update of the last step of each cycle", "global_grid": list(shape[:-1]) + [shape[-1] * world]}
+    how = {"p2p": "peer-memory stores over NVLink (sb200_push_planes + release/acquire flags) on a side stream",
+           "nccl": "NCCL send/recv on a side stream"}[it.exchange]
+    cfg = {"ghost_planes": ghost, "steps_per_exchange": ghost // R, "exchange": how + ", overlapped with the interior "
+           "update of the last step of each cycle", "global_grid": list(shape[:-1]) + [shape[-1] * world]}
     return ms, cells_local * world, launches, kernel, cfg
