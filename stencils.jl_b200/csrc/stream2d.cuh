@@ -287,7 +287,7 @@ template <typename T, int SHAPE, int R, int RED, int J> struct S2Rows {
 };
 
 template <typename T, int SHAPE, int R, int RED>
-__global__ void __launch_bounds__((S2_WARPS + 1) * 32, (RED == SB200_KERNELDOT && R >= 3) ? 1 : 2) stream2d_kernel(const __grid_constant__ S2Params<T> p) {
+__global__ void __launch_bounds__((S2_WARPS + 1) * 32, 2) stream2d_kernel(const __grid_constant__ S2Params<T> p) {
     using C = S2Cfg<T, R>;
     constexpr int VX = C::VX, P = C::P, CH = C::CH;
     extern __shared__ __align__(128) unsigned char smem[];
