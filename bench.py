@@ -2,7 +2,7 @@
 """bench.py — headline benchmark of the stencil sweep (BASELINE.json metric: Gcell-updates/s and fraction of the
 HBM roofline per stencil config).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload life|mean|kernel|circle|scatter|diffusion]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload life|mean|mean1000|kernel|circle|positional|scatter|diffusion]
     python bench.py --impl reference ...        # the reference algorithm on the host cores (CPU oracle)
 
 One "step" is one sweep of the hot path over the whole grid. The default workload is BASELINE.json configs[1]:
@@ -120,6 +120,9 @@ def workloads():
                        shape=(32768, 32768), dtype=np.float32, bytes_per_cell=8, iterated=False, seed=0x5EED0004),
         "scatter": dict(desc="scatterstencil!(+) Positional((-1,1),(-2,-1),(1,0),(-2,2)), val=centre*w, Float32 32768x32768 (configs[3]b)",
                         shape=(32768, 32768), dtype=np.float32, bytes_per_cell=12, iterated=False, seed=0x5EED0004),
+        "positional": dict(desc="mapstencil(sum, Positional((-1,1),(-2,-1),(1,0),(-2,2))) Float32 16384x16384, Wrap "
+                                "(run-time offset table; README.md:102 stencil)",
+                           shape=(16384, 16384), dtype=np.float32, bytes_per_cell=8, iterated=False, seed=0x5EED0006),
         "diffusion": dict(desc="3-D diffusion: VonNeumann(1,3) Float32 1024^3, Wrap, iterated (configs[4])",
                           shape=(1024, 1024, 1024), dtype=np.float32, bytes_per_cell=8, iterated=True, seed=0x5EED0005),
     }
@@ -168,6 +171,13 @@ def make_sweep(name, spec, torch, sb, shape=None):
         def run(n):
             for _ in range(n):
                 sb.mapstencil_(sb.maximum, dst, a)
+    elif name == "positional":
+        a = sb.StencilArray(src, sb.Positional((-1, 1), (-2, -1), (1, 0), (-2, 2)), boundary=sb.Wrap())
+        dst = sb.colmajor_empty(shape, torch.float32, dev)
+
+        def run(n):
+            for _ in range(n):
+                sb.mapstencil_(sb.sum, dst, a)
     elif name == "scatter":
         a = sb.StencilArray(src, sb.Positional((-1, 1), (-2, -1), (1, 0), (-2, 2)), boundary=sb.Remove(np.float32(0)))
         dst = sb.colmajor_empty(shape, torch.float32, dev)
@@ -356,7 +366,7 @@ def main():
         del st, run
         torch.cuda.empty_cache()
         also = {}
-        for name in ("mean", "mean1000", "kernel", "circle", "scatter", "diffusion"):
+        for name in ("mean", "mean1000", "kernel", "circle", "positional", "scatter", "diffusion"):
             if name == args.workload:
                 continue
             try:

@@ -303,6 +303,8 @@ static int do_gather(const sb200_desc* d, const void* src, void* dst, cudaStream
         if (rc >= 0) return rc;
         rc = try_tile2d(*pl, src, dst, st);
         if (rc >= 0) return rc;
+        rc = try_gather_stream(*pl, src, dst, st);
+        if (rc >= 0) return rc;
     }
     return launch_generic_gather(*pl, src, dst, st);
 }

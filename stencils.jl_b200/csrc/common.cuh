@@ -150,6 +150,7 @@ int launch_generic_scatter_rect(const Plan& pl, const void* src, void* dst, cuda
 int try_life_swar(const Plan& pl, const void* src, void* dst, cudaStream_t st);
 int try_tile2d(const Plan& pl, const void* src, void* dst, cudaStream_t st);
 int try_diffusion3d(const Plan& pl, const void* src, void* dst, cudaStream_t st);
+int try_gather_stream(const Plan& pl, const void* src, void* dst, cudaStream_t st);
 int try_scatter_fast(const Plan& pl, const void* src, void* dst, cudaStream_t st);
 int try_scatter_stream(const Plan& pl, const void* src, void* dst, cudaStream_t st, int x_lo, int x_hi, int y_lo, int y_hi);
 

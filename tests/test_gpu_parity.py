@@ -335,6 +335,64 @@ def test_stream2d_ring_rows_regions_specials(orc):
                     assert b"stream2d" in l.sb200_last_kernel()
 
 
+GS_TABLES = [
+    ([(-1, 1), (-2, -1), (1, 0), (-2, 2)], 2),                                  # Positional, README.md:102
+    ([(-1, 0), (0, -1), (1, 0), (0, 1)], 1),                                    # NamedStencil n,e,w,s (test/stencils.jl:193)
+    ([(i, j) for j in range(-2, 2) for i in range(-1, 1)], 2),                  # Rectangle((-1,0),(-2,1))
+    ([(3, -3)], 3),
+    ("Annulus", 3, 1), ("Cardinal", 2, 0), ("Ordinal", 2, 0), ("AngledCross", 2, 0), ("BackSlash", 3, 0),
+    ("ForwardSlash", 2, 0), ("Vertical", 3, 0), ("Horizontal", 4, 0), ("Window", 4, 0), ("Moore", 3, 0),
+]
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64, np.int32, np.int64])
+@pytest.mark.parametrize("bc", ["remove", "wrap", "reflect"])
+def test_gather_stream_any_table(orc, dt, bc):
+    """The run-time-table streaming gather (csrc/gather_stream.cu): Positional / Named / Rectangle tables and the named
+    shapes without a compile-time instantiation, 1..3 strips with a ragged last one, every reducer, bit-exact."""
+    rng = np.random.default_rng(41)
+    l = A.lib()
+    es = np.dtype(dt).itemsize
+    sizes = [(4096 // es + 64, 37), (64 // es * 4, 100), (2 * 4096 // es + 4096 // es // 2, 23)]
+    isf = np.dtype(dt).kind == "f"
+    for ti, tab in enumerate(GS_TABLES):
+        if isinstance(tab[0], str):
+            name, R, RI = tab
+            offs = npr.offsets(name, R, 2, RI)
+        else:
+            offs, R = tab
+        W, H = sizes[ti % len(sizes)]
+        r = rand_array(rng, (W, H), dt)
+        w = rng.random(len(offs)) if isf else rng.integers(1, 5, len(offs))
+        for red in (("sum", "mean", "min", "max", "kerneldot", "diffusion") if isf else ("sum", "min", "max", "kerneldot")):
+            both(orc, r, offs, R, bc, "cond", red, padval=1.25 if isf else 3, weights=w, alpha=0.07)
+            assert l.sb200_last_kernel() == b"gather_stream_kernel", (tab, red, l.sb200_last_kernel())
+
+
+def test_gather_stream_ring_rows_regions_specials(orc):
+    rng = np.random.default_rng(42)
+    l = A.lib()
+    W, H, G = 1536, 60, 4
+    for dt in (np.float32, np.float64):
+        parent = rand_array(rng, (W, H + 2 * G), dt)
+        parent[rng.random(parent.shape) < 0.03] = np.nan
+        parent[rng.random(parent.shape) < 0.1] = -0.0
+        parent[rng.random(parent.shape) < 0.1] = 0.0
+        et = A.ELTYPE_OF_DTYPE[np.dtype(dt)]
+        for offs, R, red in (([(-1, 1), (-2, -1), (1, 0), (-2, 2)], 2, A.MAX), (npr.offsets("Annulus", 3, 2, 1), 3, A.MIN),
+                             (npr.offsets("Cardinal", 2, 2), 2, A.DIFFUSION), (npr.offsets("Window", 4, 2), 4, A.KERNELDOT)):
+            w = rng.random(len(offs))
+            for region in (None, ((0, 0, 0), (W, 9, 0)), ((0, 9, 0), (W, H - 3, 0)), ((0, H - 3, 0), (W, H, 0))):
+                for bc0 in (A.WRAP, A.REMOVE, A.REFLECT):
+                    h = build_desc(size=(W, H), eltype=et, out_eltype=et, offsets=offs, radius=R, boundary=(bc0, A.USE),
+                                   reducer=red, src_off=(0, G), dst_off=(0, G), src_ext=parent.shape, dst_ext=parent.shape,
+                                   region=region, weights=w, alpha=0.1, padval=-2.5)
+                    want = orc.gather(h, parent, dst_like(h, 9))
+                    got, _ = gpu_gather(h, parent, dst_like(h, 9))
+                    bits_equal(got, want)
+                    assert l.sb200_last_kernel() == b"gather_stream_kernel"
+
+
 @pytest.mark.parametrize("dt", [np.float32, np.float64])
 @pytest.mark.parametrize("bc", ["remove", "wrap", "reflect"])
 def test_stream3d_vonneumann(orc, dt, bc):
