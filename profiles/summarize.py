@@ -55,7 +55,7 @@ def main():
     rnd = sys.argv[1] if len(sys.argv) > 1 else "r01"
     out_dir = os.path.join(ROOT, "gpurun_out")
     summary = {}
-    for wl in ("life", "mean", "kernel", "circle", "scatter", "diffusion"):
+    for wl in ("life", "mean", "kernel", "circle", "positional", "scatter", "diffusion"):
         rep = os.path.join(out_dir, f"{rnd}_{wl}.ncu-rep")
         if not os.path.exists(rep):
             continue
