@@ -13,6 +13,7 @@
  *   sb200_scatter      <- scatterstencil!(f, op, dest, source)           src/scatterstencil.jl:36-112
  *   sb200_iterate      <- loop of gatherstencil!(f, A::SwitchingStencilArray) + switch(A)
  *                                                                        src/gatherstencil.jl:77-83, src/array.jl:610-611
+ *   sb200_gather_multi <- gatherstencil!(f, dest, A1, A2, ...) extra-array forms   src/gatherstencil.jl:84-88,112-113
  *   sb200_stencil_offsets <- offsets(::Type{<:Stencil})                  src/stencils/{*}.jl
  *   sb200_out_eltype   <- _return_type                                   src/gatherstencil.jl:41-59
  *
@@ -181,6 +182,27 @@ size_t sb200_sizeof(int32_t eltype);
 int32_t sb200_gather(const sb200_desc* d, const void* src_parent, void* dst_parent, void* stream);
 int32_t sb200_update_halo(const sb200_desc* d, void* src_parent, void* stream);
 int32_t sb200_scatter(const sb200_desc* d, const void* src_parent, void* dst_parent, void* stream);
+/*
+ * Multi-array gather: gatherstencil!(f, dest, A1, A2, ...) (src/gatherstencil.jl:84-88, 95, 107, 112-113; reference
+ * tests test/array.jl:312-383) for user functions of the form
+ *     f(hood_1, hood_2, ...) = c_1*g_1(hood_1) + c_2*g_2(hood_2) + ...
+ * evaluated left to right, every multiplication and addition rounded separately (what Julia evaluates for
+ * `center(a) + 0.1 * sum(neighbors(b))`). Each argument carries its own sweep descriptor (stencil table, boundary,
+ * padding; reducer g_j from the menu). `center(hood)` is the one-offset table {0}; a plain array argument
+ * (indexed, not stencilled: _getarg, src/gatherstencil.jl:112-113) is the same with Conditional padding.
+ * All descriptors must agree on size, dest layout and element type (Float32 / Float64), out_eltype == eltype.
+ * `scratch` holds one dest-parent-sized temporary (NULL = library-owned, grown on demand).
+ */
+typedef struct sb200_term {
+    const sb200_desc* desc;  /* sweep of this argument (region fields are ignored) */
+    const void* src_parent;  /* device pointer */
+    int32_t has_coef;        /* 0: term = g(hood); 1: term = coef * g(hood) */
+    int32_t reserved;
+    double coef;             /* converted to the element type before use */
+} sb200_term;
+#define SB200_MAX_TERMS 8
+int32_t sb200_gather_multi(const sb200_term* terms, int32_t nterms, void* dst_parent, void* scratch, void* stream);
+
 /* nsteps x { update_halo(src) if the source has a ring and boundary != USE; gather(src->dst); swap }.
    buf_a holds the state on entry; the final state is in buf_a if nsteps is even, else buf_b. */
 int32_t sb200_iterate(const sb200_desc* d, void* buf_a, void* buf_b, int32_t nsteps, void* stream);

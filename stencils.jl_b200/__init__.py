@@ -14,7 +14,7 @@ from .stencils import (Annulus, AngledCross, BackSlash, Cardinal, Circle, Cross,
 from .array import (AbstractStencilArray, BoundaryCondition, Conditional, Halo, Padding, Reflect, Remove,
                     StencilArray, SwitchingStencilArray, Use, Wrap, boundary, colmajor_empty, dest, padding, padval,
                     source, stencil, switch)
-from .ops import (Diffusion, Life, ScatterCenterWeights, ScatterWeights, gatherstencil, gatherstencil_, iterate_,
+from .ops import (Diffusion, Life, LinearCombination, ScatterCenterWeights, ScatterWeights, gatherstencil, gatherstencil_, iterate_,
                   kernelproduct, mapstencil, mapstencil_, maximum, mean, minimum, scatterstencil_, update_boundary_)
 from .ops import sum  # noqa: A004  (Julia's `sum` applied to a stencil)
 

@@ -57,6 +57,12 @@ class SB200Error(RuntimeError):
         self.status = status
 
 
+class Term(C.Structure):
+    """sb200_term (include/stencils_b200.h)"""
+    _fields_ = [("desc", C.POINTER(Desc)), ("src_parent", C.c_void_p), ("has_coef", C.c_int32), ("reserved", C.c_int32),
+                ("coef", C.c_double)]
+
+
 class ArgumentError(ValueError):
     """Julia's ArgumentError: unsupported user function / eltype / shape, size mismatch."""
 
@@ -75,6 +81,7 @@ _SIGS = {
     "sb200_gather": (C.c_int32, [C.POINTER(Desc), C.c_void_p, C.c_void_p, C.c_void_p]),
     "sb200_update_halo": (C.c_int32, [C.POINTER(Desc), C.c_void_p, C.c_void_p]),
     "sb200_scatter": (C.c_int32, [C.POINTER(Desc), C.c_void_p, C.c_void_p, C.c_void_p]),
+    "sb200_gather_multi": (C.c_int32, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "sb200_iterate": (C.c_int32, [C.POINTER(Desc), C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "sb200_gather_host": (C.c_int32, [C.POINTER(Desc), C.c_void_p, C.c_void_p]),
     "sb200_iterate_host": (C.c_int32, [C.POINTER(Desc), C.c_void_p, C.c_int32]),

@@ -362,6 +362,37 @@ __global__ void wait_flag_kernel(const uint32_t* flag, uint32_t value) {
     } while (true);
 }
 
+// ---- multi-array gather: dest = t_1 + t_2 + ... over the logical box of the dest parent ----
+// MODE 0: d = c*s   MODE 1: d = d + s   MODE 2: d = d + c*s   (every operation rounded separately)
+template <typename T, int MODE>
+__global__ void __launch_bounds__(256) combine_kernel(T* __restrict__ d, const T* __restrict__ s, T c, long long n0, long long n1,
+                                                      long long n2, long long e0, long long e1, int o0, int o1, int o2) {
+    const long long total = n0 * n1 * n2;
+    for (long long id = blockIdx.x * (long long)blockDim.x + threadIdx.x; id < total; id += (long long)gridDim.x * blockDim.x) {
+        const long long i0 = id % n0, r = id / n0, i1 = r % n1, i2 = r / n1;
+        const long long idx = (i0 + o0) + e0 * ((i1 + o1) + e1 * (i2 + o2));
+        const T x = s[idx];
+        if (MODE == 0) d[idx] = mul_rn(c, x);
+        else if (MODE == 1) d[idx] = add_rn(d[idx], x);
+        else d[idx] = add_rn(d[idx], mul_rn(c, x));
+    }
+}
+template <typename T> static int launch_combine(int mode, void* d, const void* s, double c, const sb200_desc* ds, cudaStream_t st) {
+    const long long n0 = ds->size[0], n1 = ds->ndim > 1 ? ds->size[1] : 1, n2 = ds->ndim > 2 ? ds->size[2] : 1;
+    const long long e0 = ds->dst_ext[0], e1 = ds->ndim > 1 ? ds->dst_ext[1] : 1;
+    const int o0 = ds->dst_off[0], o1 = ds->ndim > 1 ? ds->dst_off[1] : 0, o2 = ds->ndim > 2 ? ds->dst_off[2] : 0;
+    const long long total = n0 * n1 * n2;
+    if (total == 0) return SB200_OK;
+    const unsigned blocks = (unsigned)std::min<long long>((total + 255) / 256, (long long)num_sms() * 16);
+    if (mode == 0) combine_kernel<T, 0><<<blocks, 256, 0, st>>>((T*)d, (const T*)s, (T)c, n0, n1, n2, e0, e1, o0, o1, o2);
+    else if (mode == 1) combine_kernel<T, 1><<<blocks, 256, 0, st>>>((T*)d, (const T*)s, (T)c, n0, n1, n2, e0, e1, o0, o1, o2);
+    else combine_kernel<T, 2><<<blocks, 256, 0, st>>>((T*)d, (const T*)s, (T)c, n0, n1, n2, e0, e1, o0, o1, o2);
+    SB_LAUNCH_CHECK();
+    return SB200_OK;
+}
+static thread_local void* g_multi_scratch = nullptr;
+static thread_local size_t g_multi_scratch_bytes = 0;
+
 static thread_local unsigned int* g_done_ctr = nullptr;  // 64 counters, one per in-flight push
 static thread_local unsigned g_push_seq = 0;
 
@@ -417,6 +448,53 @@ int32_t sb200_scatter(const sb200_desc* d, const void* src, void* dst, void* str
         if (rc >= 0) return rc;
     }
     return launch_generic_scatter(*pl, src, dst, (cudaStream_t)stream);
+}
+
+static size_t parent_bytes(const sb200_desc* d, bool src);
+int32_t sb200_gather_multi(const sb200_term* terms, int32_t nterms, void* dst, void* scratch, void* stream) {
+    if (!terms || nterms < 1 || nterms > SB200_MAX_TERMS || !dst) { set_error("sb200_gather_multi: 1..%d terms and a dest are required", SB200_MAX_TERMS); return SB200_EINVAL; }
+    cudaStream_t st = (cudaStream_t)stream;
+    const sb200_desc* d0 = terms[0].desc;
+    for (int j = 0; j < nterms; j++) {
+        const sb200_desc* d = terms[j].desc;
+        if (!d || !terms[j].src_parent) { set_error("sb200_gather_multi: term %d has no descriptor / source", j); return SB200_EINVAL; }
+        if (d->eltype != d0->eltype || d->out_eltype != d->eltype || (d->eltype != SB200_F32 && d->eltype != SB200_F64)) {
+            set_error("sb200_gather_multi supports Float32 / Float64 arguments of one element type");
+            return SB200_EUNSUPPORTED;
+        }
+        if (d->ndim != d0->ndim) { set_error("Source array sizes must match (dimension of argument %d)", j); return SB200_ESIZE; }
+        for (int a = 0; a < d->ndim; a++)
+            if (d->size[a] != d0->size[a] || d->dst_ext[a] != d0->dst_ext[a] || d->dst_off[a] != d0->dst_off[a]) {
+                set_error("Source array sizes must match. Found a different size / dest layout for argument %d on axis %d", j, a);  // _checksizes
+                return SB200_ESIZE;
+            }
+    }
+    const size_t db = parent_bytes(d0, false);
+    const bool need_scratch = nterms > 1 || terms[0].has_coef;
+    if (need_scratch && !scratch) {
+        if (g_multi_scratch_bytes < db) {
+            if (g_multi_scratch) cudaFree(g_multi_scratch);
+            g_multi_scratch = nullptr; g_multi_scratch_bytes = 0;
+            SB_CUDA(cudaMalloc(&g_multi_scratch, db));
+            g_multi_scratch_bytes = db;
+        }
+        scratch = g_multi_scratch;
+    }
+    int rc;
+    for (int j = 0; j < nterms; j++) {
+        sb200_desc d = *terms[j].desc;
+        memset(d.region_lo, 0, sizeof(d.region_lo)); memset(d.region_hi, 0, sizeof(d.region_hi));
+        void* src = const_cast<void*>(terms[j].src_parent);
+        if (needs_halo(&d) && (rc = do_halo(&d, src, st))) return rc;   // update_boundary!(source), src/gatherstencil.jl:93-95
+        const bool direct = j == 0 && !terms[0].has_coef;
+        if ((rc = do_gather(&d, src, direct ? dst : scratch, st))) return rc;
+        if (direct) continue;
+        const int mode = j == 0 ? 0 : (terms[j].has_coef ? 2 : 1);
+        rc = d.eltype == SB200_F32 ? launch_combine<float>(mode, dst, scratch, terms[j].coef, &d, st)
+                                   : launch_combine<double>(mode, dst, scratch, terms[j].coef, &d, st);
+        if (rc) return rc;
+    }
+    return SB200_OK;
 }
 
 int32_t sb200_iterate(const sb200_desc* d, void* buf_a, void* buf_b, int32_t nsteps, void* stream) {

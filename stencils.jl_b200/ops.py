@@ -99,6 +99,24 @@ def _stream():
 
 def _desc_for(red: Reducer, src_parent, src_halo: int, dst_parent, dst_halo: int, st: Stencil, bc, *,
               flags=0, region=None, scatter=None) -> DescHandle:
+    """Descriptor of one sweep. Small grids are launch-bound (README benchmark: 1000 x 1000), so the descriptor of a
+    repeated call is built once and kept on the stencil object (keyed by everything else that enters it)."""
+    if scatter is None and region is None:
+        key = (type(red), getattr(red, "enum", None), getattr(red, "born_mask", None), getattr(red, "survive_mask", None),
+               getattr(red, "alpha", None), tuple(src_parent.shape), src_halo, tuple(dst_parent.shape), dst_halo,
+               str(_np_dtype(src_parent)), str(_np_dtype(dst_parent)), type(bc), getattr(bc, "padval", None), flags)
+        cache = st.__dict__.setdefault("_desc_cache", {})
+        h = cache.get(key)
+        if h is None:
+            h = cache[key] = _desc_build(red, src_parent, src_halo, dst_parent, dst_halo, st, bc, flags=flags)
+            if len(cache) > 64:
+                cache.pop(next(iter(cache)))
+        return h
+    return _desc_build(red, src_parent, src_halo, dst_parent, dst_halo, st, bc, flags=flags, region=region, scatter=scatter)
+
+
+def _desc_build(red: Reducer, src_parent, src_halo: int, dst_parent, dst_halo: int, st: Stencil, bc, *,
+                flags=0, region=None, scatter=None) -> DescHandle:
     et = A.ELTYPE_OF_DTYPE.get(_np_dtype(src_parent))
     if et is None:
         raise A.ArgumentError(f"unsupported element type {_np_dtype(src_parent)}")
@@ -170,9 +188,77 @@ def _gather_into(red: Reducer, dst_parent, dst_halo, src_parent, src_halo, st, b
     return dst_parent
 
 
+class LinearCombination(Reducer):
+    """f(hood_1, hood_2, ...) = c_1*g_1(hood_1) + c_2*g_2(hood_2) + ... evaluated left to right, every operation
+    rounded separately — the multi-array user functions of test/array.jl:312-383, e.g.
+    `center(a) + 0.1 * sum(neighbors(b))` is LinearCombination(center, (0.1, sum)).
+    One term per array argument, in order: `g` or `(coef, g)` with g in {center, sum, mean, minimum, maximum,
+    kernelproduct}. A plain (non-stencil) array argument is indexed, not stencilled (src/gatherstencil.jl:112-113):
+    its term must be `center`."""
+
+    def __init__(self, *terms):
+        from .stencils import center as _center
+        self.terms = []
+        for t in terms:
+            coef, g = (None, t) if not isinstance(t, (tuple, list)) else (float(t[0]), t[1])
+            if g is _center or g == "center":
+                g = "center"
+            else:
+                g = resolve_reducer(g)
+                if g.enum not in (A.SUM, A.MEAN, A.MIN, A.MAX, A.KERNELDOT):
+                    raise A.ArgumentError(f"{g!r} cannot be a term of a LinearCombination")
+            self.terms.append((coef, g))
+
+    def __repr__(self):
+        return "LinearCombination(" + ", ".join(f"{c}*{g}" if c is not None else f"{g}" for c, g in self.terms) + ")"
+
+
+def gather_multi_(f: LinearCombination, dst, *srcs):
+    """gatherstencil!(f, dest, A1, A2, ...) with several array arguments -> sb200_gather_multi."""
+    if len(srcs) != len(f.terms):
+        raise A.ArgumentError(f"{f!r} has {len(f.terms)} terms but {len(srcs)} array arguments were passed")
+    if isinstance(dst, AbstractStencilArray):
+        dst_parent, dst_halo = dst.parent, dst.halo
+    else:
+        dst_parent, dst_halo = dst, 0
+    terms = (A.Term * len(srcs))()
+    keep = []
+    for j, (src, (coef, g)) in enumerate(zip(srcs, f.terms)):
+        if isinstance(src, AbstractStencilArray):
+            par, halo, st, bc = src.parent, src.halo, src.stencil, src.boundary
+        else:
+            if g != "center":
+                raise A.ArgumentError("a plain array argument is indexed, not stencilled: its term must be `center`")
+            from .stencils import Positional
+            par, halo, st, bc = src, 0, Positional(*[(0,) * len(src.shape)]), Remove(0)
+        if not is_device(par) or not is_device(dst_parent):
+            raise A.ArgumentError("multi-array gathers need device arrays")
+        if g == "center":
+            from .stencils import Positional
+            one = Positional(*[(0,) * st.ndims])
+            one.radius = st.radius          # the parent's ring thickness is the array's stencil radius
+            h = _desc_build(sum, par, halo, dst_parent, dst_halo, one, bc)
+        else:
+            h = _desc_build(g, par, halo, dst_parent, dst_halo, st, bc)
+        keep.append(h)
+        terms[j].desc = C.pointer(h.desc)
+        terms[j].src_parent = data_ptr(par)
+        terms[j].has_coef = 0 if coef is None else 1
+        terms[j].coef = 0.0 if coef is None else coef
+    A.check(A.lib().sb200_gather_multi(C.cast(terms, C.c_void_p), len(srcs), data_ptr(dst_parent), None, _stream()))
+    return dst
+
+
 def gatherstencil_(f, *args, flags=0):
     """gatherstencil!(f, dest, source) / gatherstencil!(f, A::SwitchingStencilArray) (src/gatherstencil.jl:77-103).
     Returns dest, or the switched array for a SwitchingStencilArray (the caller must rebind it)."""
+    if isinstance(f, LinearCombination):
+        if isinstance(args[0], SwitchingStencilArray) and len(args) == len(f.terms):
+            S = args[0]   # gatherstencil!(f, A::SwitchingStencilArray, args...): source(A) is the first argument
+            first = StencilArray(S.source, S.stencil, S.boundary, S.padding, _padded=True)
+            gather_multi_(f, StencilArray(S.dest, S.stencil, S.boundary, S.padding, _padded=True), first, *args[1:])
+            return S.switch()
+        return gather_multi_(f, args[0], *args[1:])
     red = resolve_reducer(f)
     if len(args) == 1 and isinstance(args[0], SwitchingStencilArray):
         S = args[0]
@@ -194,6 +280,13 @@ def gatherstencil_(f, *args, flags=0):
 
 def gatherstencil(f, *args, boundary=None, padding=None, flags=0):
     """gatherstencil(f, A::StencilArray) / gatherstencil(f, stencil, A; boundary, padding) (src/gatherstencil.jl:14-39)."""
+    if isinstance(f, LinearCombination):
+        first = args[0]
+        if not isinstance(first, AbstractStencilArray):
+            raise A.ArgumentError("the first argument of a multi-array gather must be a StencilArray")
+        et = A.ELTYPE_OF_DTYPE.get(first.dtype)
+        dst = similar(first.parent, A.DTYPE_OF_ELTYPE[et], first.shape)
+        return gather_multi_(f, dst, *args)
     red = resolve_reducer(f)
     if isinstance(args[0], Stencil):
         if len(args) != 2:

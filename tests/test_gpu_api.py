@@ -230,3 +230,58 @@ def test_slab_iterator_single_gpu_matches_iterate():
         torch.cuda.synchronize()
         ref = a if nsteps % 2 == 0 else b
         assert torch.equal(it.state.view(torch.uint8), ref.view(torch.uint8)), (name, shape, bcs)
+
+
+def test_multi_stencilarray_mapstencil(orc):
+    """test/array.jl:312-383 (multi-StencilArray mapstencil), with the user functions written as LinearCombination."""
+    from stencils_b200._desc import build_desc
+    Am = np.array([[1., 2, 3], [4, 5, 6], [7, 8, 9]])
+    Bm = np.array([[10., 20, 30], [40, 50, 60], [70, 80, 90]])
+    sa_A, sa_B = sb.StencilArray(dev(Am), sb.Moore(1)), sb.StencilArray(dev(Bm), sb.Moore(1))
+    # "two StencilArrays": center(hood_a) + center(hood_b) == A .+ B
+    res = sb.mapstencil(sb.LinearCombination(sb.center, sb.center), sa_A, sa_B)
+    np.testing.assert_array_equal(host(res), Am + Bm)
+    # sum(neighbors(hood_a)) + sum(neighbors(hood_b))
+    res2 = sb.mapstencil(sb.LinearCombination(sb.sum, sb.sum), sa_A, sa_B)
+    assert host(res2).shape == Am.shape
+    offs = npr.offsets("Moore", 1, 2)
+
+    def nsum(x, bc=A.REMOVE):
+        return orc.stencil_array_sweep(np.asfortranarray(x), offs, 1, bc, "cond", A.SUM, padval=0.0)
+    bits_equal(host(res2), nsum(Am) + nsum(Bm))
+    # "SwitchingStencilArray with StencilArray": c + 0.1 * sum(neighbors(hood_r)), three sweeps
+    mutable_arr = np.array([[0., 0, 0], [0, 1, 0], [0, 0, 0]])
+    readonly_arr = np.array([[1., 1, 1], [1, 0, 1], [1, 1, 1]])
+    ssa = sb.SwitchingStencilArray(dev(mutable_arr), sb.Moore(1))
+    sa = sb.StencilArray(dev(readonly_arr), sb.Moore(1))
+    f = sb.LinearCombination(sb.center, (0.1, sb.sum))
+    want = mutable_arr.copy()
+    for _ in range(3):
+        ssa = sb.mapstencil_(f, ssa, sa)
+        want = want + 0.1 * nsum(readonly_arr)
+    result = np.asarray(ssa)
+    assert result.shape == mutable_arr.shape and result[1, 1] > mutable_arr[1, 1]
+    bits_equal(result, want)
+    # "three StencilArrays"
+    sas = [sb.StencilArray(dev(k * np.ones((5, 5))), sb.Moore(1)) for k in (1.0, 2.0, 3.0)]
+    res3 = sb.mapstencil(sb.LinearCombination(sb.center, sb.center, sb.center), *sas)
+    assert np.all(host(res3)[1:4, 1:4] == 6.0)
+    # "mixed StencilArray and regular array": center(hood_a) + b_val == A .+ B
+    res4 = sb.mapstencil(sb.LinearCombination(sb.center, sb.center), sa_A, dev(Bm))
+    np.testing.assert_array_equal(host(res4), Am + Bm)
+    with pytest.raises(sb.ArgumentError):
+        sb.mapstencil(sb.LinearCombination(sb.center, sb.sum), sa_A, dev(Bm))  # plain arrays are indexed, not stencilled
+    # random fields, Float32, different stencils / boundaries / paddings per argument, coefficients on every term
+    rng = np.random.default_rng(5)
+    X, Y, Z = (np.asfortranarray(rng.random((200, 96)).astype(np.float32) - 0.4) for _ in range(3))
+    w = rng.random((3, 3)).astype(np.float32)
+    sx = sb.StencilArray(dev(X), sb.Window(1), boundary=sb.Wrap(), padding=sb.Halo("out"))
+    sy = sb.StencilArray(dev(Y), sb.Kernel(sb.Window(1), w), boundary=sb.Reflect())
+    sz = sb.StencilArray(dev(Z), sb.Positional((-1, 1), (-2, -1), (1, 0), (-2, 2)), boundary=sb.Remove(np.float32(0.5)))
+    got = sb.mapstencil(sb.LinearCombination((0.25, sb.mean), sb.kernelproduct, (-1.5, sb.maximum)), sx, sy, sz)
+    t1 = orc.stencil_array_sweep(X, npr.offsets("Window", 1, 2), 1, A.WRAP, "cond", A.MEAN)
+    t2 = orc.stencil_array_sweep(Y, npr.offsets("Window", 1, 2), 1, A.REFLECT, "cond", A.KERNELDOT, weights=w)
+    t3 = orc.stencil_array_sweep(Z, [(-1, 1), (-2, -1), (1, 0), (-2, 2)], 2, A.REMOVE, "cond", A.MAX, padval=0.5)
+    want = (np.float32(0.25) * t1 + t2) + np.float32(-1.5) * t3
+    assert want.dtype == np.float32
+    bits_equal(host(got), want)
