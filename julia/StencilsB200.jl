@@ -163,6 +163,47 @@ function Stencils.gatherstencil!(f::F, dst, src::AbstractStencilArray{R,T,N,<:Un
     return dst
 end
 
+# gatherstencil!(f, dest, A1, A2, ...) with extra array arguments — src/gatherstencil.jl:84-88, 95, 107, 112-113.
+# The user function is spelled as a LinearCombination: f(h1, h2, ...) = c1*g1(h1) + c2*g2(h2) + ... (left to right,
+# every operation rounded separately); `center` terms and plain-array arguments use the one-offset table {0}.
+struct Term
+    desc::Ptr{Desc}
+    src_parent::Ptr{Cvoid}
+    has_coef::Int32
+    reserved::Int32
+    coef::Float64
+end
+struct LinearCombination{T<:Tuple}
+    terms::T            # one per array argument: g or (coef, g), g in (center, sum, mean, minimum, maximum, kernelproduct)
+end
+LinearCombination(terms...) = LinearCombination(terms)
+term_parts(t::Tuple) = (true, Float64(t[1]), t[2])
+term_parts(g) = (false, 0.0, g)
+
+function Stencils.gatherstencil!(f::LinearCombination, dst, A1::AbstractStencilArray{R,T,N,<:B200Array}, args...) where {R,T,N}
+    srcs = (A1, args...)
+    length(srcs) == length(f.terms) || throw(ArgumentError("$(length(f.terms)) terms but $(length(srcs)) array arguments"))
+    Stencils._checksizes((dst, srcs...))
+    dpar, dh = dst isa AbstractStencilArray ? (parent(dst), padding(dst) isa Halo ? R : 0) : (dst, 0)
+    descs = Vector{Base.RefValue{Desc}}(); keeps = Any[]; terms = Term[]
+    for (src, t) in zip(srcs, f.terms)
+        has, c, g = term_parts(t)
+        sa = src isa AbstractStencilArray ? src : StencilArray(src, Positional(ntuple(_ -> 0, N)); boundary=Remove(zero(T)))
+        src isa AbstractStencilArray || g === center || throw(ArgumentError("a plain array argument is indexed, not stencilled"))
+        sa = g === center ? StencilArray(parent(sa), Positional(ntuple(_ -> 0, N)), boundary(sa), padding(sa)) : sa
+        d, keep = make_desc(g === center ? sum : g, dpar, dh, sa, parent(sa))
+        g === center && (d = with(d; radius=Int32(R)))          # ring thickness of the parent = the array's stencil radius
+        push!(descs, Ref(d)); push!(keeps, keep)
+        push!(terms, Term(Base.unsafe_convert(Ptr{Desc}, descs[end]), dataptr(parent(sa)), Int32(has), Int32(0), c))
+    end
+    GC.@preserve descs keeps terms begin
+        check(ccall((:sb200_gather_multi, LIB), Int32, (Ptr{Term}, Int32, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}),
+                    terms, length(terms), dataptr(dpar), C_NULL, C_NULL))
+        check(ccall((:sb200_stream_sync, LIB), Int32, (Ptr{Cvoid},), C_NULL))
+    end
+    return dst
+end
+
 # gatherstencil!(f, A::SwitchingStencilArray) — src/gatherstencil.jl:77-83
 function Stencils.gatherstencil!(f::F, A::SwitchingStencilArray{R,T,N,<:Union{B200Array,Array}}) where {F,R,T,N}
     pd = padding(A) isa Halo ? Halo{:in}() : padding(A)
