@@ -320,7 +320,8 @@ def main():
 
     if world > 1:
         from stencils_b200 import slab
-        res = slab.bench_weak(args.workload, spec, args.steps, args.warmup, synth)
+        with ClockSampler(local_rank) as cs:
+            res = slab.bench_weak(args.workload, spec, args.steps, args.warmup, synth)
         ms, cells_total, launches, kernel, extra_cfg = res
     else:
         st, run, cells_total = make_sweep(args.workload, spec, torch, sb)
@@ -336,7 +337,6 @@ def main():
         t = torch.tensor([ms], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-        cs = ClockSampler(local_rank)
 
     value = cells_total * args.steps / (ms * 1e-3) / 1e9
     achieved = value * spec["bytes_per_cell"] / max(world, 1)  # GB/s per GPU, algorithmic bytes
@@ -356,6 +356,20 @@ def main():
         "clocks": cs.summary(),
     }
 
+    if world > 1 and not args.no_extras and args.workload == "life":
+        # e2e at N GPUs: every rank pushes its own slab through the host-buffer entry point concurrently
+        # (one generation per call: H2D + sweep + D2H inside every step); whole-job value = sum over ranks
+        import torch.distributed as dist
+        try:
+            e = e2e_host(torch, sb, lib, args.workload, spec, barrier=dist.barrier)
+            v = torch.tensor([e["value"]], device="cuda", dtype=torch.float64)
+            dist.all_reduce(v)
+            e.update(value=float(v.item()), h2d_bytes_per_step=e["h2d_bytes_per_step"] * world,
+                     d2h_bytes_per_step=e["d2h_bytes_per_step"] * world,
+                     how=e["how"] + f"; {world} ranks concurrently, one slab each, values summed")
+            line["e2e"] = e
+        except Exception as ex:  # pragma: no cover
+            line["e2e"] = {"error": repr(ex)}
     if rank == 0 and world == 1 and not args.no_extras:
         # ---- e2e: the reference-facing call with HOST buffers, copies inside the timed region ----
         try:
@@ -398,7 +412,7 @@ def main():
         dist.destroy_process_group()
 
 
-def e2e_host(torch, sb, lib, workload, spec):
+def e2e_host(torch, sb, lib, workload, spec, barrier=None):
     """Same metric through the C-ABI entry point a host-array StencilArray lowers to (sb200_gather_host):
     pinned host source -> HBM -> sweep -> pinned host dest, every step."""
     from stencils_b200.array import _torch_dtype
@@ -413,6 +427,8 @@ def e2e_host(torch, sb, lib, workload, spec):
     sb.mapstencil_(sb.Life(), dst, a)  # warm-up (allocates the device scratch)
     sb.mapstencil_(sb.Life(), dst, a)
     n = 5
+    if barrier:
+        barrier()
     t0 = time.perf_counter()
     for _ in range(n):
         sb.mapstencil_(sb.Life(), dst, a)  # blocking call: returns when dst is on the host

@@ -153,6 +153,14 @@ typedef struct sb200_desc {
     int64_t region_hi[SB200_MAX_DIMS];
     int32_t flags;       /* SB200_FLAG_* */
     int32_t reserved1;
+    /* Fused ghost-plane push (slab-partitioned runs): output planes [mirror_lo, mirror_hi) of the LAST axis (logical
+       coordinates) are ALSO stored, by the sweep kernel itself, to `mirror_parent` — plane mirror_lo first, planes
+       packed with the dest parent's plane pitch. `mirror_parent` is normally a neighbour GPU's landing slot opened with
+       sb200_ipc_import, so the boundary planes cross NVLink as they are produced; publish them with sb200_signal_flag.
+       NULL = off. Kernels without the fused store fall back to a stream-ordered copy inside the call. */
+    void* mirror_parent;
+    int64_t mirror_lo;
+    int64_t mirror_hi;
 } sb200_desc;
 
 #define SB200_FLAG_FORCE_GENERIC 1 /* bypass specialised kernels (testing: generic vs fast parity) */
@@ -236,6 +244,9 @@ int32_t sb200_ipc_close(void* p);
    then publish `value` to a flag word in the peer's memory with system-scope release semantics. */
 int32_t sb200_push_planes(const void* src, void* peer_dst, size_t bytes, uint32_t* peer_flag, uint32_t value,
                           void* stream);
+/* Stream-ordered system-scope release store of `value` to a flag word (normally in a peer's memory): everything the
+   stream wrote before — including the fused mirror stores of a sweep — is visible to a peer that acquires the flag. */
+int32_t sb200_signal_flag(uint32_t* peer_flag, uint32_t value, void* stream);
 /* Stream-ordered wait until *flag >= value (acquire). */
 int32_t sb200_wait_flag(const uint32_t* flag, uint32_t value, void* stream);
 

@@ -56,6 +56,9 @@ struct Desc
     region_hi::NTuple{3,Int64}
     flags::Int32
     reserved1::Int32
+    mirror_parent::Ptr{Cvoid}   # fused ghost-plane push (slab runs): NULL = off
+    mirror_lo::Int64
+    mirror_hi::Int64
 end
 
 # ---- reducer menu: the only user functions that lower to CUDA kernels ----
@@ -134,7 +137,8 @@ function make_desc(f, dst_parent, dst_halo::Int, src::AbstractStencilArray{R,T,N
              pad3(ntuple(_ -> Int32(sh), N), Int32(0)), pad3(ntuple(_ -> Int32(dst_halo), N), Int32(0)),
              pad3(ntuple(_ -> bc_enum(bc), N), SB_REMOVE), ELTYPE[T], out[], pv, R, length(st), pointer(offs), red, 0, 0,
              f isa Life ? f.born_mask : UInt32(8), f isa Life ? f.survive_mask : UInt32(12), 0,
-             isempty(w) ? C_NULL : pointer(w), f isa Diffusion ? f.alpha : 0.0, (0, 0, 0), (0, 0, 0), flags, 0)
+             isempty(w) ? C_NULL : pointer(w), f isa Diffusion ? f.alpha : 0.0, (0, 0, 0), (0, 0, 0), flags, 0,
+             C_NULL, 0, 0)
     return Ref(d), (offs, w)
 end
 unsigned_of(::Type{T}) where T = sizeof(T) == 1 ? UInt8 : sizeof(T) == 4 ? UInt32 : UInt64

@@ -48,6 +48,7 @@ class Desc(C.Structure):
         ("alpha", C.c_double),
         ("region_lo", C.c_int64 * 3), ("region_hi", C.c_int64 * 3),
         ("flags", C.c_int32), ("reserved1", C.c_int32),
+        ("mirror_parent", C.c_void_p), ("mirror_lo", C.c_int64), ("mirror_hi", C.c_int64),
     ]
 
 
@@ -100,6 +101,7 @@ _SIGS = {
     "sb200_ipc_import": (C.c_int32, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "sb200_ipc_close": (C.c_int32, [C.c_void_p]),
     "sb200_push_planes": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_uint32, C.c_void_p]),
+    "sb200_signal_flag": (C.c_int32, [C.c_void_p, C.c_uint32, C.c_void_p]),
     "sb200_wait_flag": (C.c_int32, [C.c_void_p, C.c_uint32, C.c_void_p]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGS)

@@ -1,6 +1,7 @@
 // api.cu — the extern "C" surface of libstencils_b200.so (include/stencils_b200.h): validation, the plan
 // cache (device copies of offset/weight tables + dispatch), host-buffer entry points and memory helpers.
 #include <algorithm>
+#include <cstdlib>
 #include <array>
 #include <cstdarg>
 #include <cmath>
@@ -177,6 +178,7 @@ static int validate(const sb200_desc* d, int kind) {
 }
 
 static std::mutex g_plan_mu;
+thread_local MirrorReq g_mirror;
 static std::unordered_map<std::string, Plan*> g_plans;
 
 static std::string plan_key(const sb200_desc* d, int kind, int dev) {
@@ -184,6 +186,7 @@ static std::string plan_key(const sb200_desc* d, int kind, int dev) {
     sb200_desc c = *d;
     c.offsets_host = nullptr;
     c.weights_host = nullptr;
+    c.mirror_parent = nullptr; c.mirror_lo = c.mirror_hi = 0;  // per-call, not part of the plan
     k.append((const char*)&kind, sizeof(kind));
     k.append((const char*)&dev, sizeof(dev));
     k.append((const char*)&c, sizeof(c));
@@ -296,17 +299,33 @@ static int do_gather(const sb200_desc* d, const void* src, void* dst, cudaStream
     Plan* pl = nullptr;
     int rc = get_plan(d, PK_GATHER, &pl);
     if (rc) return rc;
+    g_mirror = MirrorReq();
+    if (d->mirror_parent && d->mirror_hi > d->mirror_lo) {
+        const int last = d->ndim - 1;
+        const long long lo = pl->dd.lo[last], hi = lo + pl->dd.n[last];
+        if (d->mirror_lo < lo || d->mirror_hi > hi) { set_error("mirror planes [%lld,%lld) lie outside the output region", (long long)d->mirror_lo, (long long)d->mirror_hi); return SB200_EINVAL; }
+        for (int a = 0; a < last; a++)
+            if (d->dst_off[a] != 0 || pl->dd.lo[a] != 0 || pl->dd.n[a] != d->size[a]) { set_error("mirror needs whole, unpadded dest planes"); return SB200_EUNSUPPORTED; }
+        g_mirror.ptr = d->mirror_parent; g_mirror.lo = d->mirror_lo; g_mirror.hi = d->mirror_hi;
+    }
+    rc = -1;
     if (!(d->flags & SB200_FLAG_FORCE_GENERIC)) {
         rc = try_life_swar(*pl, src, dst, st);
-        if (rc >= 0) return rc;
-        rc = try_diffusion3d(*pl, src, dst, st);
-        if (rc >= 0) return rc;
-        rc = try_tile2d(*pl, src, dst, st);
-        if (rc >= 0) return rc;
-        rc = try_gather_stream(*pl, src, dst, st);
-        if (rc >= 0) return rc;
+        if (rc < 0) rc = try_diffusion3d(*pl, src, dst, st);
+        if (rc < 0) rc = try_tile2d(*pl, src, dst, st);
+        if (rc < 0) rc = try_gather_stream(*pl, src, dst, st);
     }
-    return launch_generic_gather(*pl, src, dst, st);
+    if (rc < 0) rc = launch_generic_gather(*pl, src, dst, st);
+    if (rc == SB200_OK && g_mirror.ptr && !g_mirror.honoured) {
+        // no fused store in the kernel that ran: copy the planes after the sweep (same stream)
+        const int last = d->ndim - 1;
+        size_t plane = elsize(d->out_eltype);
+        for (int a = 0; a < last; a++) plane *= (size_t)d->dst_ext[a];
+        const char* from = (const char*)dst + (size_t)(g_mirror.lo + d->dst_off[last]) * plane;
+        SB_CUDA(cudaMemcpyAsync(g_mirror.ptr, from, (size_t)(g_mirror.hi - g_mirror.lo) * plane, cudaMemcpyDeviceToDevice, st));
+    }
+    g_mirror = MirrorReq();
+    return rc;
 }
 
 static int do_halo(const sb200_desc* d, void* parent, cudaStream_t st) {
@@ -351,6 +370,11 @@ __global__ void push_planes_kernel(const uint4* __restrict__ src, uint4* __restr
             }
         }
     }
+}
+
+__global__ void signal_flag_kernel(uint32_t* flag, uint32_t value) {
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(value) : "memory");
 }
 
 __global__ void wait_flag_kernel(const uint32_t* flag, uint32_t value) {
@@ -533,7 +557,7 @@ struct HostScratch {
     void* a = nullptr; size_t a_bytes = 0;
     void* b = nullptr; size_t b_bytes = 0;
     cudaStream_t st[3] = {nullptr, nullptr, nullptr};
-    cudaEvent_t ev[64];
+    cudaEvent_t ev[128];
     bool init = false;
 };
 static thread_local HostScratch g_hs;
@@ -541,7 +565,7 @@ static thread_local HostScratch g_hs;
 static int ensure_scratch(size_t ab, size_t bb) {
     if (!g_hs.init) {
         for (int i = 0; i < 3; i++) SB_CUDA(cudaStreamCreateWithFlags(&g_hs.st[i], cudaStreamNonBlocking));
-        for (int i = 0; i < 64; i++) SB_CUDA(cudaEventCreateWithFlags(&g_hs.ev[i], cudaEventDisableTiming));
+        for (int i = 0; i < 128; i++) SB_CUDA(cudaEventCreateWithFlags(&g_hs.ev[i], cudaEventDisableTiming));
         g_hs.init = true;
     }
     if (g_hs.a_bytes < ab) { if (g_hs.a) cudaFree(g_hs.a); g_hs.a = nullptr; g_hs.a_bytes = 0; SB_CUDA(cudaMalloc(&g_hs.a, ab)); g_hs.a_bytes = ab; }
@@ -580,6 +604,7 @@ int32_t sb200_gather_host(const sb200_desc* d, const void* src_host, void* dst_h
         return SB200_OK;
     }
     int nchunks = 16;
+    if (const char* e = getenv("SB200_HOST_CHUNKS")) nchunks = std::max(1, std::min(64, atoi(e)));  // tuning knob (events: 2 per chunk)
     if (nlast / nchunks < 2 * (long long)d->radius + 1) nchunks = 1;
     const int R = d->radius, off = d->src_off[last];
     long long sent_hi = 0;  // source planes [0, sent_hi) of the parent are on the device
@@ -677,6 +702,13 @@ int32_t sb200_push_planes(const void* src, void* peer_dst, size_t bytes, uint32_
     push_planes_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
         (const uint4*)src, (uint4*)peer_dst, n16, (const unsigned char*)src, (unsigned char*)peer_dst, tail0, bytes,
         peer_flag, value, g_done_ctr + (g_push_seq++ % 64));
+    SB_LAUNCH_CHECK();
+    return SB200_OK;
+}
+
+int32_t sb200_signal_flag(uint32_t* flag, uint32_t value, void* stream) {
+    if (!flag) return SB200_EINVAL;
+    signal_flag_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(flag, value);
     SB_LAUNCH_CHECK();
     return SB200_OK;
 }

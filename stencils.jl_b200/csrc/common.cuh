@@ -140,6 +140,15 @@ __device__ __forceinline__ long long bounded(long long j, long long s, int bc) {
 }
 #endif  // __CUDACC__
 
+// Fused ghost-plane push requested by the current sweep (sb200_desc.mirror_*): set by do_gather around the dispatch.
+// A kernel that stores the planes itself sets `honoured`; otherwise do_gather copies them after the sweep.
+struct MirrorReq {
+    void* ptr = nullptr;       // plane `lo` lands here; plane pitch = dest parent's
+    long long lo = 0, hi = 0;  // logical planes [lo, hi) of the last axis
+    bool honoured = false;
+};
+extern thread_local MirrorReq g_mirror;
+
 // ---------------------------------------------------------------- kernel families (one .cu each)
 int launch_generic_gather(const Plan& pl, const void* src, void* dst, cudaStream_t st);
 int launch_update_halo(const Plan& pl, void* parent, cudaStream_t st);

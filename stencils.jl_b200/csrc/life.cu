@@ -28,6 +28,8 @@ struct LifeParams {
     int ncols;                 // W / 16
     int colgroups;             // ceil(ncols / 32)
     int soff1, doff1;          // ring / ghost rows on axis 1
+    uint8_t* mirror;           // fused ghost push: rows [m_lo, m_hi) are also stored here (row m_lo first), or null
+    int m_lo, m_hi;
     int bc0, bc1;              // boundary per axis
     unsigned pad01;            // Remove: (padval != 0)
     int y_lo, rows;            // output rows [y_lo, y_lo + rows)
@@ -269,7 +271,8 @@ __device__ __forceinline__ long long life_map_row(const LifeParams& p, int r) {
     return -1;
 }
 
-template <bool CELLS01, bool CONWAY>
+// MIRROR: the fused ghost-row push (LifeParams::mirror) is compiled in only for the boundary sweeps of slab runs.
+template <bool CELLS01, bool CONWAY, bool MIRROR>
 __global__ void __launch_bounds__((LT_WARPS + 1) * 32) life_tma_kernel(const LifeTmaParams q) {
     extern __shared__ __align__(128) uint8_t smem[];
     const LifeParams& p = q.lp;
@@ -334,6 +337,8 @@ __global__ void __launch_bounds__((LT_WARPS + 1) * 32) life_tma_kernel(const Lif
         const bool lfix = first && p.bc0 != SB200_WRAP, rfix = last && p.bc0 != SB200_WRAP;
         const bool reflect = p.bc0 == SB200_REFLECT;
         uint8_t* __restrict__ dt = p.dst + (long long)(y0 + p.doff1) * p.dpitch + x0 + xt;
+        long long moff = (long long)(y0 - p.m_lo) * p.dpitch + x0 + xt;  // offset of output row y0 in the mirror
+        int yout = y0;
         const unsigned padrow = p.pad01 * 0x01010101u;
         Row A, B, C;
         A.h0 = A.h1 = A.h2 = A.h3 = B.h0 = B.h1 = B.h2 = B.h3 = 0;
@@ -368,6 +373,11 @@ __global__ void __launch_bounds__((LT_WARPS + 1) * 32) life_tma_kernel(const Lif
                 o.z = rule<CONWAY>(a.h2 + b.h2 + n.h2, b.c2, p.born, p.survive);
                 o.w = rule<CONWAY>(a.h3 + b.h3 + n.h3, b.c3, p.born, p.survive);
                 if (active) *reinterpret_cast<uint4*>(dt) = o;
+                if (MIRROR) {
+                    if (active && yout >= p.m_lo && yout < p.m_hi)   // boundary rows cross NVLink as they are produced
+                        *reinterpret_cast<uint4*>(p.mirror + moff) = o;
+                    moff += p.dpitch; yout++;
+                }
                 dt += p.dpitch;
             }
         };
@@ -395,14 +405,14 @@ __global__ void __launch_bounds__((LT_WARPS + 1) * 32) life_tma_kernel(const Lif
     }
 }
 
-template <bool CELLS01, bool CONWAY> static int launch_tma(const LifeParams& p, cudaStream_t st) {
+template <bool CELLS01, bool CONWAY, bool MIRROR> static int launch_tma_m(const LifeParams& p, cudaStream_t st) {
     static thread_local int cfg_dev = -1, ctas_per_sm = 0;
     int dev = 0;
     SB_CUDA(cudaGetDevice(&dev));
     if (dev != cfg_dev) {
-        SB_CUDA(cudaFuncSetAttribute(life_tma_kernel<CELLS01, CONWAY>, cudaFuncAttributeMaxDynamicSharedMemorySize, LT_SMEM));
+        SB_CUDA(cudaFuncSetAttribute(life_tma_kernel<CELLS01, CONWAY, MIRROR>, cudaFuncAttributeMaxDynamicSharedMemorySize, LT_SMEM));
         int per_sm = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, life_tma_kernel<CELLS01, CONWAY>, (LT_WARPS + 1) * 32, LT_SMEM) != cudaSuccess || per_sm < 1)
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, life_tma_kernel<CELLS01, CONWAY, MIRROR>, (LT_WARPS + 1) * 32, LT_SMEM) != cudaSuccess || per_sm < 1)
             per_sm = 1;
         ctas_per_sm = per_sm;
         cfg_dev = dev;
@@ -415,8 +425,11 @@ template <bool CELLS01, bool CONWAY> static int launch_tma(const LifeParams& p, 
     nruns = std::min<long long>(nruns, std::max(1, p.rows / 16));  // at least 16 rows per run
     q.nruns = (int)nruns;
     const long long grid = std::min<long long>(ctas, (long long)q.nstrips * q.nruns);
-    life_tma_kernel<CELLS01, CONWAY><<<(unsigned)grid, (LT_WARPS + 1) * 32, LT_SMEM, st>>>(q);
+    life_tma_kernel<CELLS01, CONWAY, MIRROR><<<(unsigned)grid, (LT_WARPS + 1) * 32, LT_SMEM, st>>>(q);
     return SB200_OK;
+}
+template <bool CELLS01, bool CONWAY> static int launch_tma(const LifeParams& p, cudaStream_t st) {
+    return p.mirror ? launch_tma_m<CELLS01, CONWAY, true>(p, st) : launch_tma_m<CELLS01, CONWAY, false>(p, st);
 }
 
 int try_life_swar(const Plan& pl, const void* src, void* dst, cudaStream_t st) {
@@ -447,6 +460,11 @@ int try_life_swar(const Plan& pl, const void* src, void* dst, cudaStream_t st) {
     // step after the first, because the source is then this kernel's own output).
     const bool cells01 = d.eltype == SB200_BOOL || (d.flags & SB200_FLAG_CELLS_01);
     const bool use_tma = !(d.flags & SB200_FLAG_NO_TMA) && p.W >= 512 && p.rows >= 16;
+    p.mirror = nullptr; p.m_lo = p.m_hi = 0;
+    if (use_tma && g_mirror.ptr && d.dst_ext[0] == d.size[0]) {
+        p.mirror = (uint8_t*)g_mirror.ptr; p.m_lo = (int)g_mirror.lo; p.m_hi = (int)g_mirror.hi;
+        g_mirror.honoured = true;
+    }
     if (use_tma) {
         int rc;
         if (cells01) rc = conway ? launch_tma<true, true>(p, st) : launch_tma<true, false>(p, st);

@@ -37,6 +37,8 @@ template <typename T> struct S3Params {
     T pad, alpha;
     int z_lo, zn;                  // output planes [z_lo, z_lo + zn)
     int ntx, nty, nzruns;
+    T* mirror;                     // fused ghost push: planes [m_lo, m_hi) are also stored here (plane m_lo first), or null
+    int m_lo, m_hi;
     int ty;                        // rows per tile (<= S3_TY): chosen so that the tiles fill whole waves of CTAs
 };
 
@@ -58,7 +60,8 @@ template <typename T> struct S3Vec;
 template <> struct S3Vec<float> { using type = float4; };
 template <> struct S3Vec<double> { using type = double2; };
 
-template <typename T, int RED>
+// MIRROR: the fused ghost-plane push (S3Params::mirror) is compiled in only for the boundary sweeps of slab runs.
+template <typename T, int RED, bool MIRROR>
 __global__ void __launch_bounds__((S3_WARPS + 1) * 32) stream3d_kernel(const __grid_constant__ S3Params<T> p) {
     constexpr int VX = 16 / (int)sizeof(T);
     extern __shared__ __align__(128) unsigned char smem[];
@@ -202,6 +205,11 @@ __global__ void __launch_bounds__((S3_WARPS + 1) * 32) stream3d_kernel(const __g
                     T* d = dbase + (long long)(zo + p.do2) * p.dp2 + (long long)r * p.dp1;
                     if constexpr (VX == 4) *reinterpret_cast<float4*>(d) = make_float4(out[0], out[1], out[2], out[3]);
                     else *reinterpret_cast<double2*>(d) = make_double2(out[0], out[1]);
+                    if (MIRROR && zo >= p.m_lo && zo < p.m_hi) {  // boundary planes cross NVLink as they are produced
+                        T* m = p.mirror + (long long)(zo - p.m_lo) * p.dp2 + (long long)(y0 + ry0 + r) * p.dp1 + gx;
+                        if constexpr (VX == 4) *reinterpret_cast<float4*>(m) = make_float4(out[0], out[1], out[2], out[3]);
+                        else *reinterpret_cast<double2*>(m) = make_double2(out[0], out[1]);
+                    }
                 }
             }
             __syncwarp();
@@ -210,14 +218,14 @@ __global__ void __launch_bounds__((S3_WARPS + 1) * 32) stream3d_kernel(const __g
     }
 }
 
-template <typename T, int RED> static int s3_launch(S3Params<T>& p, cudaStream_t st) {
+template <typename T, int RED, bool MIRROR> static int s3_launch_m(S3Params<T>& p, cudaStream_t st) {
     static thread_local int cfg_dev = -1, ctas_per_sm = 0;
     int dev = 0;
     SB_CUDA(cudaGetDevice(&dev));
     if (dev != cfg_dev) {
-        SB_CUDA(cudaFuncSetAttribute(stream3d_kernel<T, RED>, cudaFuncAttributeMaxDynamicSharedMemorySize, S3_SMEM));
+        SB_CUDA(cudaFuncSetAttribute(stream3d_kernel<T, RED, MIRROR>, cudaFuncAttributeMaxDynamicSharedMemorySize, S3_SMEM));
         int per_sm = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, stream3d_kernel<T, RED>, (S3_WARPS + 1) * 32, S3_SMEM) != cudaSuccess || per_sm < 1)
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, stream3d_kernel<T, RED, MIRROR>, (S3_WARPS + 1) * 32, S3_SMEM) != cudaSuccess || per_sm < 1)
             per_sm = 1;
         ctas_per_sm = per_sm;
         cfg_dev = dev;
@@ -241,9 +249,12 @@ template <typename T, int RED> static int s3_launch(S3Params<T>& p, cudaStream_t
     p.nzruns = best;
     const long long ntiles = (long long)p.ntx * p.nty;
     const long long grid = std::min<long long>(ctas, ntiles * p.nzruns);
-    stream3d_kernel<T, RED><<<(unsigned)grid, (S3_WARPS + 1) * 32, S3_SMEM, st>>>(p);
+    stream3d_kernel<T, RED, MIRROR><<<(unsigned)grid, (S3_WARPS + 1) * 32, S3_SMEM, st>>>(p);
     SB_LAUNCH_CHECK();
     return SB200_OK;
+}
+template <typename T, int RED> static int s3_launch(S3Params<T>& p, cudaStream_t st) {
+    return p.mirror ? s3_launch_m<T, RED, true>(p, st) : s3_launch_m<T, RED, false>(p, st);
 }
 
 template <typename T> static int s3_try(const Plan& pl, const void* src, void* dst, cudaStream_t st) {
@@ -269,6 +280,12 @@ template <typename T> static int s3_try(const Plan& pl, const void* src, void* d
     memcpy(&p.pad, &d.padval_bits, sizeof(T));
     p.alpha = (T)d.alpha;
     p.z_lo = (int)pl.dd.lo[2]; p.zn = (int)pl.dd.n[2];
+    p.mirror = nullptr; p.m_lo = p.m_hi = 0;
+    if (g_mirror.ptr && d.dst_off[0] == 0 && d.dst_off[1] == 0 && d.dst_ext[0] == d.size[0] && d.dst_ext[1] == d.size[1] &&
+        (d.reducer == SB200_DIFFUSION || d.reducer == SB200_SUM || d.reducer == SB200_MEAN || d.reducer == SB200_MAX || d.reducer == SB200_MIN)) {
+        p.mirror = (T*)g_mirror.ptr; p.m_lo = (int)g_mirror.lo; p.m_hi = (int)g_mirror.hi;
+        g_mirror.honoured = true;
+    }
     const long long Xb = d.size[0] * (long long)sizeof(T);
     p.ntx = (int)((Xb + S3_TXB - 1) / S3_TXB);
     p.nty = (int)((d.size[1] + S3_TY - 1) / S3_TY);

@@ -105,6 +105,14 @@ class PeerMailbox:
             pb = self.peer[self.down]
             A.check(self.lib.sb200_push_planes(bottom_ptr, self.slot(pb, 1, par), self.nbytes, self.flag(pb, 1), self.seq, stream))
 
+    def signal(self, seq, stream):
+        """Publish exchange `seq` whose planes the sweep kernels already stored into the neighbours' slots."""
+        self.seq = seq
+        if self.up is not None:
+            A.check(self.lib.sb200_signal_flag(self.flag(self.peer[self.up], 0), seq, stream))
+        if self.down is not None:
+            A.check(self.lib.sb200_signal_flag(self.flag(self.peer[self.down], 1), seq, stream))
+
     def pull(self, ghost_bottom_ptr, ghost_top_ptr, stream):
         """Wait for exchange self.seq from both neighbours and move the planes into my ghost zones."""
         par = self.seq & 1
@@ -177,6 +185,7 @@ class SlabIterator:
         self.launches = 0
         # ghost exchange: peer-memory stores over NVLink when the ranks can open each other's memory, else NCCL
         self.mailbox = None
+        self.fused = os.environ.get("SB200_FUSED_PUSH", "1") != "0"
         self.exchange = "local" if world == 1 else ("nccl" if self.is_cuda else "gloo")
         if world > 1 and self.is_cuda and exchange in ("auto", "p2p"):
             plane_bytes = t[0].numel() * t.element_size()
@@ -187,24 +196,28 @@ class SlabIterator:
                 raise A.SB200Error(A.ECUDA, "CUDA IPC peer access is not available between the ranks")
 
     # ---- helpers ----
-    def _desc(self, lo_plane, hi_plane):
-        """descriptor whose output region is parent planes [lo_plane, hi_plane) of the split axis"""
+    def _desc(self, lo_plane, hi_plane, mirror=None):
+        """descriptor whose output region is parent planes [lo_plane, hi_plane) of the split axis; mirror =
+        (peer pointer, first plane, end plane): those planes are also stored into the peer's landing slot by the sweep"""
         flags = self._later_flags if self._nsweeps > 0 else 0
-        key = (lo_plane, hi_plane, flags)
+        key = (lo_plane, hi_plane, flags, mirror)
         if key not in self._descs:
             lo = (0,) * (self.nd - 1) + (lo_plane,)
             hi = self.logical_rest + (hi_plane,)
             lo, hi = lo + (0,) * (3 - self.nd), hi + (0,) * (3 - self.nd)
-            self._descs[key] = self._mk((lo, hi), flags)
+            h = self._mk((lo, hi), flags)
+            if mirror is not None:
+                h = h.copy(mirror_parent=mirror[0], mirror_lo=mirror[1], mirror_hi=mirror[2])
+            self._descs[key] = h
         return self._descs[key]
 
     def _compute_cuda(self, h, src, dst):
         stream = self.torch.cuda.current_stream().cuda_stream
         A.check(A.lib().sb200_gather(h.ptr(), src.data_ptr(), dst.data_ptr(), stream))
 
-    def _sweep(self, lo_plane, hi_plane):
+    def _sweep(self, lo_plane, hi_plane, mirror=None):
         if hi_plane > lo_plane:
-            self.compute(self._desc(lo_plane, hi_plane), self.bufs[self.cur], self.bufs[1 - self.cur])
+            self.compute(self._desc(lo_plane, hi_plane, mirror), self.bufs[self.cur], self.bufs[1 - self.cur])
             self.launches += 1
 
     @property
@@ -287,14 +300,32 @@ class SlabIterator:
                 # boundary planes first, their exchange overlaps the interior update
                 # (one extra plane per side: a Reflect end mirrors planes G+1 .. 2G of the new state)
                 G, n = self.G + 1, self.n_local
-                self._sweep(lo, min(lo + G, hi))
-                self._sweep(max(hi - G, lo + G), hi)
+                nxt = self.bufs[1 - self.cur]
+                mb = self.mailbox
+                fused = mb is not None and self.fused and n >= 2 * self.G + 2
+                if fused:
+                    # the boundary sweeps store the planes the neighbours need straight into their landing slots
+                    # (peer memory, NVLink) while they compute them; two 1-thread kernels publish the flags
+                    stream = torch.cuda.current_stream().cuda_stream
+                    seq = mb.seq + 1
+                    par = seq & 1
+                    m_dn = (mb.slot(mb.peer[mb.down], 1, par), self.G, 2 * self.G) if mb.down is not None else None
+                    m_up = (mb.slot(mb.peer[mb.up], 0, par), n, n + self.G) if mb.up is not None else None
+                    self._sweep(lo, min(lo + G, hi), m_dn)
+                    self._sweep(max(hi - G, lo + G), hi, m_up)
+                    mb.signal(seq, stream)
+                else:
+                    self._sweep(lo, min(lo + G, hi))
+                    self._sweep(max(hi - G, lo + G), hi)
                 ev = torch.cuda.Event()
                 ev.record()
-                nxt = self.bufs[1 - self.cur]
                 with torch.cuda.stream(self.comm_stream):
                     self.comm_stream.wait_event(ev)
-                    self._exchange(nxt)
+                    if fused:
+                        mb.pull(nxt[:self.G].data_ptr(), nxt[self.G + n:].data_ptr(), self.comm_stream.cuda_stream)
+                        self._fill_end_ghosts(nxt)
+                    else:
+                        self._exchange(nxt)
                     done = torch.cuda.Event()
                     done.record()
                 self._sweep(lo + G, hi - G)
@@ -359,7 +390,9 @@ def bench_weak(workload, spec, steps, warmup, synth=None):
     dist.barrier()
     ms = e0.elapsed_time(e1)
     launches = lib.sb200_launch_count(1)
-    how = {"p2p": "peer-memory stores over NVLink (sb200_push_planes + release/acquire flags) on a side stream",
+    how = {"p2p": ("peer-memory stores over NVLink fused into the boundary sweeps (sb200_desc.mirror_*, sb200_signal_flag)"
+                   if it.fused else "peer-memory stores over NVLink (sb200_push_planes + release/acquire flags)") +
+                  ", acquire wait + ghost copy on a side stream",
            "nccl": "NCCL send/recv on a side stream"}[it.exchange]
     cfg = {"ghost_planes": ghost, "steps_per_exchange": ghost // R, "exchange": how + ", overlapped with the interior "
            "update of the last step of each cycle", "global_grid": list(shape[:-1]) + [shape[-1] * world]}

@@ -34,7 +34,7 @@ def main():
         ("diffusion", (256, 192, 64 * world), np.float32, (A.WRAP, A.WRAP, A.WRAP), 4, 22),
         ("diffusion", (128, 100, 40 * world + 1), np.float32, (A.REMOVE, A.WRAP, A.REFLECT), 2, 7),
     ]
-    cases = [c + (ex,) for ex in ("p2p", "nccl") for c in cases]
+    cases = [c + (ex,) for ex in ("p2p-fused", "p2p", "nccl") for c in cases]
     for name, shape, dt, bcs, ghost, nsteps, ex in cases:
         full = synth_torch(shape, dt, 0xABC, dev)                      # logical (column-major) view
         if name == "life":
@@ -45,7 +45,8 @@ def main():
         lo, hi = split_axis_last(shape, world, rank)
         tfull = full.permute(*reversed(range(len(shape))))             # split axis first, C-contiguous
         it = SlabIterator(tfull[lo:hi].contiguous(), offsets=st.offsets(), radius=1, reducer=red, boundary=bcs, eltype=et,
-                          ghost=ghost, rank=rank, world=world, reducer_kwargs=kw, padval=0, exchange=ex)
+                          ghost=ghost, rank=rank, world=world, reducer_kwargs=kw, padval=0, exchange=ex.split("-")[0])
+        it.fused = ex == "p2p-fused"
         it.step(nsteps)
         # single-domain reference on this GPU (per-axis boundaries -> descriptor directly)
         from stencils_b200._desc import build_desc
@@ -59,7 +60,7 @@ def main():
         bad = (it.state.view(torch.uint8) != ref[lo:hi].view(torch.uint8)).sum()
         dist.all_reduce(bad)
         if rank == 0:
-            print(f"{name} {shape} bcs={bcs} ghost={ghost} steps={nsteps} exchange={it.exchange}: mismatching bytes = {int(bad)}", flush=True)
+            print(f"{name} {shape} bcs={bcs} ghost={ghost} steps={nsteps} exchange={ex}: mismatching bytes = {int(bad)}", flush=True)
         bad_total += int(bad)
     dist.destroy_process_group()
     if bad_total:
