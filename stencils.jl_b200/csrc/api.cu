@@ -299,6 +299,10 @@ static int do_gather(const sb200_desc* d, const void* src, void* dst, cudaStream
     Plan* pl = nullptr;
     int rc = get_plan(d, PK_GATHER, &pl);
     if (rc) return rc;
+    if ((d->flags & SB200_FLAG_DOUBLE_STEP) && !life2_accepts(*d, *pl)) {
+        set_error("SB200_FLAG_DOUBLE_STEP: only Life / Moore(1) on an unpadded Bool or UInt8 grid with Wrap on axis 0");
+        return SB200_EUNSUPPORTED;
+    }
     g_mirror = MirrorReq();
     if (d->mirror_parent && d->mirror_hi > d->mirror_lo) {
         const int last = d->ndim - 1;
@@ -537,10 +541,26 @@ int32_t sb200_iterate(const sb200_desc* d, void* buf_a, void* buf_b, int32_t nst
     // packed kernel does not accept).
     sb200_desc later = *d;
     if (d->reducer == SB200_LIFE && d->eltype == SB200_U8) later.flags |= SB200_FLAG_CELLS_01;
-    for (int i = 0; i < nsteps; i++) {
+    // Life: two generations per launch where the kernel supports it (half the HBM traffic per generation). The number
+    // of single-generation launches in front is chosen so that the final buffer is the one the contract names.
+    int singles = nsteps;
+    if (d->reducer == SB200_LIFE && nsteps >= 4 && !halo && !(d->flags & SB200_FLAG_DOUBLE_STEP)) {
+        Plan* pl = nullptr;
+        sb200_desc probe = *d;
+        probe.flags |= SB200_FLAG_DOUBLE_STEP;
+        if (get_plan(&probe, PK_GATHER, &pl) == SB200_OK && life2_accepts(probe, *pl))
+            for (singles = nsteps & 1; singles < nsteps; singles += 2)
+                if (((singles + (nsteps - singles) / 2) & 1) == (nsteps & 1)) break;
+    }
+    int done = 0;
+    for (int i = 0; done < nsteps; i++) {
         int rc;
+        const bool dbl = done >= singles;
         if (halo && (rc = sb200_update_halo(d, s, stream))) return rc;
-        if ((rc = do_gather(i == 0 ? d : &later, s, t, (cudaStream_t)stream))) return rc;
+        sb200_desc cur = i == 0 ? *d : later;
+        if (dbl) cur.flags |= SB200_FLAG_DOUBLE_STEP;
+        if ((rc = do_gather(&cur, s, t, (cudaStream_t)stream))) return rc;
+        done += dbl ? 2 : 1;
         void* tmp = s; s = t; t = tmp;
     }
     return SB200_OK;

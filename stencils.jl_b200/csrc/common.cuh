@@ -157,6 +157,7 @@ int launch_generic_scatter_rect(const Plan& pl, const void* src, void* dst, cuda
                                 long long lo1, long long hi1);
 // Specialised kernels return SB200_OK when they handled the sweep, -1 when the plan is not theirs.
 int try_life_swar(const Plan& pl, const void* src, void* dst, cudaStream_t st);
+bool life2_accepts(const sb200_desc& d, const Plan& pl);  // SB200_FLAG_DOUBLE_STEP
 int try_tile2d(const Plan& pl, const void* src, void* dst, cudaStream_t st);
 int try_diffusion3d(const Plan& pl, const void* src, void* dst, cudaStream_t st);
 int try_gather_stream(const Plan& pl, const void* src, void* dst, cudaStream_t st);

@@ -260,6 +260,7 @@ constexpr int LT_SMEM = 128 + LT_STAGES * LT_CH * LT_ROWB;
 struct LifeTmaParams {
     LifeParams lp;
     int nstrips, nruns;
+    int outb;   // life_tma2_kernel: final cells per strip row (<= LT2_OUTB, a multiple of 128: equal strips)
 };
 
 // source row r (logical) -> parent row, or -1 for a Remove pad row
@@ -432,6 +433,186 @@ template <bool CELLS01, bool CONWAY> static int launch_tma(const LifeParams& p, 
     return p.mirror ? launch_tma_m<CELLS01, CONWAY, true>(p, st) : launch_tma_m<CELLS01, CONWAY, false>(p, st);
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Two generations per sweep (SB200_FLAG_DOUBLE_STEP): dest = step(step(src)) with ONE read and ONE write of the grid.
+// Same TMA ring as life_tma_kernel. A warp's 32 lanes hold 512 consecutive cells of the first-generation row; the
+// left / right neighbour bytes of that intermediate row come from the adjacent lanes by warp shuffle, so only lanes
+// 1..30 own final cells: warps overlap by two lanes and a strip is LT2_WARPS * 480 bytes wide (6 % recomputation).
+// The intermediate generation lives only in registers (three rolling rows per thread), never in memory.
+// Supported where evolving the halo equals the boundary rule: Wrap on axis 0, Wrap / Reflect (or a region that stays
+// inside the parent) on axis 1, no ring. Algorithmic traffic: 1 B read + 1 B written per cell per TWO generations.
+constexpr int LT2_WARPS = 8;
+constexpr int LT2_OUTB = LT2_WARPS * 480;      // final cells per strip row
+constexpr int LT2_D0 = 96;                     // data start inside a shared-memory row: global x0-32 is 96 mod 128
+constexpr int LT2_ROWB = 4096;                 // 96 + 32 + 3840 + 32 = 4000, padded
+constexpr int LT2_CH = 6;
+constexpr int LT2_STAGES = 4;
+constexpr int LT2_SMEM = 128 + LT2_STAGES * LT2_CH * LT2_ROWB;
+
+__device__ __forceinline__ Row row_of_words(unsigned w0, unsigned w1, unsigned w2, unsigned w3, unsigned bl, unsigned br) {
+    Row o;
+    o.c0 = w0; o.c1 = w1; o.c2 = w2; o.c3 = w3;
+    o.h0 = ((w0 << 8) + bl) + w0 + __funnelshift_r(w0, w1, 8);
+    o.h1 = __funnelshift_l(w0, w1, 8) + w1 + __funnelshift_r(w1, w2, 8);
+    o.h2 = __funnelshift_l(w1, w2, 8) + w2 + __funnelshift_r(w2, w3, 8);
+    o.h3 = __funnelshift_l(w2, w3, 8) + w3 + __funnelshift_r(w3, br, 8);
+    return o;
+}
+
+template <bool CELLS01, bool CONWAY>
+__global__ void __launch_bounds__((LT2_WARPS + 1) * 32, 2) life_tma2_kernel(const LifeTmaParams q) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const LifeParams& p = q.lp;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem);
+    uint64_t* empty = full + LT2_STAGES;
+    uint8_t* ring = smem + 128;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < LT2_STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], LT2_WARPS); }
+        mbar_fence_init();
+    }
+    __syncthreads();
+    const int ntasks = q.nstrips * q.nruns;
+    unsigned k = 0;
+    for (int task = blockIdx.x; task < ntasks; task += gridDim.x) {
+        const int strip = task % q.nstrips, run = task / q.nstrips;
+        const int x0 = strip * q.outb;
+        const int wout = min(q.outb, p.W - x0);
+        const int y0 = p.y_lo + (int)((long long)p.rows * run / q.nruns);
+        const int y1 = p.y_lo + (int)((long long)p.rows * (run + 1) / q.nruns);
+        const int nsrc = y1 - y0 + 4;  // source rows y0-2 .. y1+1
+        const int nchunks = (nsrc + LT2_CH - 1) / LT2_CH;
+        if (warp == LT2_WARPS) {
+            // ---------------- producer: shared-memory row byte b <-> global column x0 - 32 + b (mod W) ----------------
+            if (lane == 0) {
+                const int lin = x0 >= 32 ? 32 : 0;                       // left halo bytes that are ordinary cells
+                const int rin = min(32, p.W - (x0 + wout));              // right halo bytes that are ordinary cells
+                const unsigned mlen = lin + wout + rin;                  // one contiguous copy
+                const unsigned rowbytes = 64 + wout;
+                for (int c = 0; c < nchunks; c++, k++) {
+                    const int slot = k % LT2_STAGES;
+                    mbar_wait(&empty[slot], ((k / LT2_STAGES) & 1) ^ 1);
+                    uint8_t* sbase = ring + slot * (LT2_CH * LT2_ROWB);
+                    const int nrows = min(LT2_CH, nsrc - c * LT2_CH);
+                    mbar_arrive_expect_tx(&full[slot], nrows * rowbytes);
+                    for (int j = 0; j < nrows; j++) {
+                        const uint8_t* g = p.src + life_map_row(p, y0 - 2 + c * LT2_CH + j) * p.spitch;
+                        uint8_t* srow = sbase + j * LT2_ROWB + LT2_D0;
+                        bulk_g2s(srow + 32 - lin, g + x0 - lin, mlen, &full[slot]);
+                        if (!lin) bulk_g2s(srow, g + p.W - 32, 32, &full[slot]);                        // wrapped left halo
+                        if (rin < 32) bulk_g2s(srow + 32 + wout + rin, g, 32 - rin, &full[slot]);       // wrapped right halo
+                    }
+                }
+            } else {
+                k += nchunks;
+            }
+            continue;
+        }
+        // ---------------- consumers ----------------
+        const int cell0 = warp * 480 + (lane - 1) * 16;          // first final cell of this lane inside the strip (may be < 0)
+        const bool active = lane >= 1 && lane <= 30 && cell0 < wout;
+        uint8_t* __restrict__ dt = p.dst + (long long)(y0 + p.doff1) * p.dpitch + x0 + cell0;
+        const int soff = LT2_D0 + 32 + cell0;                    // offset of the lane's 16 cells in a shared-memory row
+        Row S0, S1, S2, T0, T1, T2;
+        S0 = S1 = S2 = T0 = T1 = T2 = Row{0, 0, 0, 0, 0, 0, 0, 0};
+        auto take = [&](const uint8_t* srow, Row& o) {
+            const uint8_t* t = srow + soff;
+            const uint4 v = *reinterpret_cast<const uint4*>(t);
+            unsigned w0 = v.x, w1 = v.y, w2 = v.z, w3 = v.w, bl = t[-1], br = t[16];
+            if (!CELLS01) {
+                w0 = nz_bytes(w0); w1 = nz_bytes(w1); w2 = nz_bytes(w2); w3 = nz_bytes(w3);
+                bl = min(bl, 1u); br = min(br, 1u);
+            }
+            o = row_of_words(w0, w1, w2, w3, bl, br);
+        };
+        // first generation of the row of `b` from source rows a, b, n; neighbour bytes from the adjacent lanes
+        auto gen1 = [&](const Row& a, const Row& b, const Row& n, Row& o) {
+            const unsigned x0_ = rule<CONWAY>(a.h0 + b.h0 + n.h0, b.c0, p.born, p.survive);
+            const unsigned x1_ = rule<CONWAY>(a.h1 + b.h1 + n.h1, b.c1, p.born, p.survive);
+            const unsigned x2_ = rule<CONWAY>(a.h2 + b.h2 + n.h2, b.c2, p.born, p.survive);
+            const unsigned x3_ = rule<CONWAY>(a.h3 + b.h3 + n.h3, b.c3, p.born, p.survive);
+            const unsigned bl = __shfl_up_sync(0xffffffffu, x3_, 1) >> 24;
+            const unsigned br = __shfl_down_sync(0xffffffffu, x0_, 1) & 0xFFu;
+            o = row_of_words(x0_, x1_, x2_, x3_, bl, br);
+        };
+        auto gen2 = [&](int i, const Row& a, const Row& b, const Row& n) {  // i = stream index of the newest source row
+            if (i >= 4 && i < nsrc) {
+                uint4 o;
+                o.x = rule<CONWAY>(a.h0 + b.h0 + n.h0, b.c0, p.born, p.survive);
+                o.y = rule<CONWAY>(a.h1 + b.h1 + n.h1, b.c1, p.born, p.survive);
+                o.z = rule<CONWAY>(a.h2 + b.h2 + n.h2, b.c2, p.born, p.survive);
+                o.w = rule<CONWAY>(a.h3 + b.h3 + n.h3, b.c3, p.born, p.survive);
+                if (active) *reinterpret_cast<uint4*>(dt) = o;
+                dt += p.dpitch;
+            }
+        };
+        for (int c = 0; c < nchunks; c++, k++) {
+            const int slot = k % LT2_STAGES;
+            mbar_wait(&full[slot], (k / LT2_STAGES) & 1);
+            const uint8_t* sbase = ring + slot * (LT2_CH * LT2_ROWB);
+            const int i0 = c * LT2_CH;
+            // stream index i: S_i -> slot i%3;  T_{i-1} = gen1(S_{i-2}, S_{i-1}, S_i) -> slot (i-1)%3;  out(i-2) = gen2(T_{i-3}, T_{i-2}, T_{i-1})
+#pragma unroll
+            for (int j = 0; j < LT2_CH; j += 3) {
+                take(sbase + (j + 0) * LT2_ROWB, S0);   // i % 3 == 0
+                gen1(S1, S2, S0, T2);                   // T_{i-1}, (i-1) % 3 == 2
+                gen2(i0 + j + 0, T0, T1, T2);
+                take(sbase + (j + 1) * LT2_ROWB, S1);   // i % 3 == 1
+                gen1(S2, S0, S1, T0);
+                gen2(i0 + j + 1, T1, T2, T0);
+                take(sbase + (j + 2) * LT2_ROWB, S2);   // i % 3 == 2
+                gen1(S0, S1, S2, T1);
+                gen2(i0 + j + 2, T2, T0, T1);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[slot]);
+        }
+    }
+}
+
+// Can this sweep run two generations per launch?
+bool life2_accepts(const sb200_desc& d, const Plan& pl) {
+    if (d.reducer != SB200_LIFE || d.ndim != 2 || (d.eltype != SB200_BOOL && d.eltype != SB200_U8)) return false;
+    if (pl.shape_tag != SB200_MOORE || pl.shape_ndim != 2 || d.radius != 1 || d.noffsets != 8) return false;
+    if (d.flags & (SB200_FLAG_NO_TMA | SB200_FLAG_FORCE_GENERIC)) return false;
+    for (int a = 0; a < 2; a++)
+        if (d.src_off[a] != 0 || d.dst_off[a] != 0) return false;
+    if (d.size[0] % 16 || d.src_ext[0] % 16 || d.dst_ext[0] % 16 || d.size[0] < 512 || d.size[0] > (1LL << 30) || d.size[1] > (1LL << 30)) return false;
+    if (d.boundary[0] != SB200_WRAP) return false;
+    if (pl.dd.lo[0] != 0 || pl.dd.n[0] != d.size[0] || pl.dd.n[1] < 16) return false;
+    const long long lo = pl.dd.lo[1], hi = lo + pl.dd.n[1];
+    const bool inside = lo >= 2 && hi + 2 <= d.size[1];  // never leaves the parent: the boundary rule of axis 1 is not exercised
+    if (!inside && d.boundary[1] != SB200_WRAP && d.boundary[1] != SB200_REFLECT) return false;
+    if (d.size[1] < 4) return false;
+    return true;
+}
+
+template <bool CELLS01, bool CONWAY> static int launch_tma2(const LifeParams& p, cudaStream_t st) {
+    static thread_local int cfg_dev = -1, ctas_per_sm = 0;
+    int dev = 0;
+    SB_CUDA(cudaGetDevice(&dev));
+    if (dev != cfg_dev) {
+        SB_CUDA(cudaFuncSetAttribute(life_tma2_kernel<CELLS01, CONWAY>, cudaFuncAttributeMaxDynamicSharedMemorySize, LT2_SMEM));
+        int per_sm = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, life_tma2_kernel<CELLS01, CONWAY>, (LT2_WARPS + 1) * 32, LT2_SMEM) != cudaSuccess || per_sm < 1)
+            per_sm = 1;
+        ctas_per_sm = per_sm;
+        cfg_dev = dev;
+    }
+    LifeTmaParams q;
+    q.lp = p;
+    q.nstrips = (p.W + LT2_OUTB - 1) / LT2_OUTB;
+    q.outb = std::min(LT2_OUTB, ((p.W + q.nstrips - 1) / q.nstrips + 127) / 128 * 128);  // equal strips
+    q.nstrips = (p.W + q.outb - 1) / q.outb;
+    const long long ctas = (long long)ctas_per_sm * num_sms();
+    long long nruns = std::max<long long>(1, (2 * ctas + q.nstrips - 1) / q.nstrips);
+    nruns = std::min<long long>(nruns, std::max(1, p.rows / 32));  // at least 32 rows per run (4 are re-read)
+    q.nruns = (int)nruns;
+    const long long grid = std::min<long long>(ctas, (long long)q.nstrips * q.nruns);
+    life_tma2_kernel<CELLS01, CONWAY><<<(unsigned)grid, (LT2_WARPS + 1) * 32, LT2_SMEM, st>>>(q);
+    return SB200_OK;
+}
+
 int try_life_swar(const Plan& pl, const void* src, void* dst, cudaStream_t st) {
     const sb200_desc& d = pl.d;
     if (d.reducer != SB200_LIFE || d.ndim != 2) return -1;
@@ -459,6 +640,18 @@ int try_life_swar(const Plan& pl, const void* src, void* dst, cudaStream_t st) {
     // Bool cells are 0/1 by type; UInt8 cells are 0/1 when the caller says so (sb200_iterate does for every
     // step after the first, because the source is then this kernel's own output).
     const bool cells01 = d.eltype == SB200_BOOL || (d.flags & SB200_FLAG_CELLS_01);
+    if (d.flags & SB200_FLAG_DOUBLE_STEP) {
+        if (!life2_accepts(d, pl)) { set_error("two generations per sweep: layout / boundary not supported"); return SB200_EUNSUPPORTED; }
+        p.mirror = nullptr; p.m_lo = p.m_hi = 0;
+        int rc;
+        if (cells01) rc = conway ? launch_tma2<true, true>(p, st) : launch_tma2<true, false>(p, st);
+        else rc = conway ? launch_tma2<false, true>(p, st) : launch_tma2<false, false>(p, st);
+        if (rc) return rc;
+        SB_LAUNCH_CHECK();
+        set_kernel_name(conway ? (cells01 ? "life_tma2_kernel<cells01,conway>" : "life_tma2_kernel<u8,conway>")
+                               : (cells01 ? "life_tma2_kernel<cells01,table>" : "life_tma2_kernel<u8,table>"));
+        return SB200_OK;
+    }
     const bool use_tma = !(d.flags & SB200_FLAG_NO_TMA) && p.W >= 512 && p.rows >= 16;
     p.mirror = nullptr; p.m_lo = p.m_hi = 0;
     if (use_tma && g_mirror.ptr && d.dst_ext[0] == d.size[0]) {

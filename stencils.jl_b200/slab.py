@@ -176,6 +176,11 @@ class SlabIterator:
         # Life on UInt8: after the first sweep every cell this rank reads is a 0/1 output of the kernel (own cells or
         # exchanged ghosts); stale ghost planes outside the still-exact region only feed outputs that are discarded.
         self._later_flags = A.FLAG_CELLS_01 if (reducer == A.LIFE and eltype == A.U8) else 0
+        # two generations per launch: Life on a device grid whose split axis is a ring (Remove / Reflect ends must be
+        # re-imposed after every single generation) — the library has the last word (life2_accepts, csrc/life.cu)
+        self._gen = 1
+        self.double_ok = (reducer == A.LIFE and t.is_cuda and compute is None and self.bc_split == A.WRAP and self.k >= 2 and
+                          self.n_local >= 4 * self.G + 64 and os.environ.get("SB200_DOUBLE_STEP", "1") != "0")
         self._nsweeps = 0
         self._descs = {}
         self.is_cuda = t.is_cuda
@@ -199,7 +204,7 @@ class SlabIterator:
     def _desc(self, lo_plane, hi_plane, mirror=None):
         """descriptor whose output region is parent planes [lo_plane, hi_plane) of the split axis; mirror =
         (peer pointer, first plane, end plane): those planes are also stored into the peer's landing slot by the sweep"""
-        flags = self._later_flags if self._nsweeps > 0 else 0
+        flags = (self._later_flags if self._nsweeps > 0 else 0) | (A.FLAG_DOUBLE_STEP if self._gen == 2 else 0)
         key = (lo_plane, hi_plane, flags, mirror)
         if key not in self._descs:
             lo = (0,) * (self.nd - 1) + (lo_plane,)
@@ -284,17 +289,29 @@ class SlabIterator:
     # ---- stepping ----
     def step(self, nsteps=1):
         torch = self.torch
-        for _ in range(nsteps):
-            self._step_one(torch)
-            self._nsweeps += 1
-
-    def _step_one(self, torch):
-        if True:
+        left = int(nsteps)
+        while left > 0:
             if self.steps_since_exchange >= self.k:
                 self._exchange(self.bufs[self.cur])
                 self.steps_since_exchange = 0
-            s = self.steps_since_exchange + 1                 # 1..k
-            lo, hi = self.R * s, self.ext - self.R * s        # parent planes that are still exact after this step
+            # Life: two generations per launch (SB200_FLAG_DOUBLE_STEP) while the cycle has room for them
+            m = 2 if (self.double_ok and left >= 2 and self.k - self.steps_since_exchange >= 2) else 1
+            if m == 2:
+                try:
+                    self._step_one(torch, 2)
+                except A.ArgumentError:   # the library declined this layout: single generations from now on
+                    self.double_ok = False
+                    continue
+            else:
+                self._step_one(torch, 1)
+            self._nsweeps += 1
+            left -= m
+
+    def _step_one(self, torch, m=1):
+        self._gen = m
+        if True:
+            s = self.steps_since_exchange + m                 # generations since the exchange once this sweep is done
+            lo, hi = self.R * s, self.ext - self.R * s        # parent planes that are still exact after this sweep
             last_of_cycle = s == self.k
             if last_of_cycle and self.is_cuda and self.world > 1:
                 # boundary planes first, their exchange overlaps the interior update

@@ -423,3 +423,46 @@ def test_stream3d_ghost_planes_and_regions(orc):
             got, _ = gpu_gather(h, parent, dst_like(h, 9))
             bits_equal(got, want)
             assert b"stream3d" in l.sb200_last_kernel()
+
+
+@pytest.mark.parametrize("dt", [np.uint8, np.bool_])
+def test_life_two_generations_per_launch(orc, dt):
+    """SB200_FLAG_DOUBLE_STEP (csrc/life.cu: life_tma2_kernel): dest = step(step(src)) against two oracle sweeps, and
+    sb200_iterate (which uses it by itself) against the oracle for step counts of every residue mod 4."""
+    from tests.util import stream, sync, to_dev, to_host
+    rng = np.random.default_rng(51)
+    l = A.lib()
+    moore = npr.offsets("Moore", 1, 2)
+    for (W, H), bc1 in [((512, 40), A.WRAP), ((3840 + 512, 67), A.WRAP), ((4096, 33), A.REFLECT), ((8192 + 1024, 130), A.WRAP),
+                        ((1040, 50), A.REFLECT)]:
+        g = (rng.random((W, H)) < 0.4)
+        g = g.astype(dt) if dt == np.bool_ else (g * rng.integers(1, 255, size=(W, H))).astype(np.uint8)
+        g = np.asfortranarray(g)
+        et = A.ELTYPE_OF_DTYPE[np.dtype(dt)]
+        for born, surv in ((1 << 3, 0b1100), (0b101001000, 0b100111110)):
+            kw = dict(size=(W, H), eltype=et, out_eltype=et, offsets=moore, radius=1, boundary=(A.WRAP, bc1), reducer=A.LIFE,
+                      born_mask=born, survive_mask=surv)
+            h1 = build_desc(**kw)
+            mid = orc.gather(h1, g, dst_like(h1))
+            want = orc.gather(h1, mid, dst_like(h1))
+            h2 = build_desc(flags=A.FLAG_DOUBLE_STEP, **kw)
+            got, _ = gpu_gather(h2, g, dst_like(h2))
+            bits_equal(got, want)
+            assert l.sb200_last_kernel().startswith(b"life_tma2_kernel")
+            # a region that stays inside the parent (what the slab iterator asks for)
+            hr = build_desc(flags=A.FLAG_DOUBLE_STEP, region=((0, 2, 0), (W, H - 2, 0)), **kw)
+            got, _ = gpu_gather(hr, g, dst_like(hr, 7))
+            want_r = dst_like(hr, 7)
+            want_r[:, 2:H - 2] = want[:, 2:H - 2]
+            bits_equal(got, want_r)
+        for n in (4, 5, 6, 7, 9):
+            want = orc.iterate(h1, g.copy(order="F"), np.zeros_like(g, order="F"), n)
+            ta, tb = to_dev(g), to_dev(np.zeros_like(g, order="F"))
+            A.check(l.sb200_iterate(h1.ptr(), ta.data_ptr(), tb.data_ptr(), n, stream()))
+            sync()
+            bits_equal(to_host(ta if n % 2 == 0 else tb, g.shape, g.dtype), want)
+    # not supported -> status code, no silent single step
+    hbad = build_desc(size=(512, 40), eltype=A.U8, out_eltype=A.U8, offsets=moore, radius=1, boundary=A.REMOVE, reducer=A.LIFE,
+                      flags=A.FLAG_DOUBLE_STEP)
+    t = to_dev(np.zeros((512, 40), dtype=np.uint8, order="F"))
+    assert l.sb200_gather(hbad.ptr(), t.data_ptr(), to_dev(np.zeros((512, 40), dtype=np.uint8, order="F")).data_ptr(), None) == A.EUNSUPPORTED
