@@ -331,6 +331,7 @@ def main():
         with ClockSampler(local_rank) as cs:
             ms = time_steps(torch, run, args.steps, args.warmup, barrier, on_warm=lambda: lib.sb200_launch_count(1))
         launches = lib.sb200_launch_count(1)  # kernels launched by libstencils_b200 inside the timed region
+        kernel = lib.sb200_last_kernel().decode()  # the kernel of the timed region (iterated Life fuses two generations)
         extra_cfg = {}
     if world > 1:
         import torch.distributed as dist
@@ -340,6 +341,12 @@ def main():
 
     value = cells_total * args.steps / (ms * 1e-3) / 1e9
     achieved = value * spec["bytes_per_cell"] / max(world, 1)  # GB/s per GPU, algorithmic bytes
+    traffic = ncu_traffic(args.workload)
+    per_rank_launches = max(int(launches), 1)
+    sweeps_per_launch = args.steps / per_rank_launches if spec["iterated"] else 1.0
+    dram_frac = None
+    if traffic and world == 1:
+        dram_frac = traffic * per_rank_launches / (ms * 1e-3) / 1e9 / peak
     line = {
         "metric": "gcell_updates_per_s", "value": value, "unit": "Gcell-updates/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -348,8 +355,13 @@ def main():
         "config": {"workload": spec["desc"], "grid_per_gpu": list(spec["shape"]), "parallelism": f"slab{world}",
                    "l2": "state per GPU (>= 256 MiB) is larger than the 126 MB L2; no flush needed", **extra_cfg},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": ncu_traffic(args.workload), "peak_source": peak_src, "kernel": kernel,
+                     "traffic": traffic, "peak_source": peak_src, "kernel": kernel,
                      "algorithmic_bytes_per_cell": spec["bytes_per_cell"],
+                     "sweeps_per_launch": sweeps_per_launch, "dram_frac": dram_frac,
+                     "note": ("frac counts the ALGORITHMIC bytes of every sweep (SURVEY 8d: read once + write once per "
+                              "cell-update); a launch that fuses two generations moves the grid through HBM once for two "
+                              "sweeps, so frac > 1 means the one-sweep HBM roofline is beaten by temporal fusion; "
+                              "dram_frac = measured DRAM bytes per launch (ncu, `traffic`) x launches / time / peak"),
                      "how": "algorithmic bytes per launch / mean launch duration (CUDA events on the launching stream "
                             "around the K back-to-back launches of the timed region)"},
         "gpu_launches": int(launches),
