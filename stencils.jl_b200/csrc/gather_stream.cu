@@ -234,7 +234,7 @@ template <typename T, int RED> static int gs_launch(GsParams<T>& p, cudaStream_t
         cfg_dev = dev;
     }
     const long long ctas = (long long)ctas_per_sm * num_sms();
-    long long nruns = std::max<long long>(1, (4 * ctas + p.nstrips - 1) / p.nstrips);
+    long long nruns = std::max<long long>(1, 4 * ctas / p.nstrips);
     nruns = std::min<long long>(nruns, std::max(1, p.rows / (4 * (2 * p.R + 1))));
     p.nruns = (int)nruns;
     const long long grid = std::min<long long>(ctas, (long long)p.nstrips * p.nruns);

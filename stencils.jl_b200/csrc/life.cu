@@ -511,6 +511,16 @@ __global__ void __launch_bounds__((LT2_WARPS + 1) * 32, 2) life_tma2_kernel(cons
         // ---------------- consumers ----------------
         const int cell0 = warp * 480 + (lane - 1) * 16;          // first final cell of this lane inside the strip (may be < 0)
         const bool active = lane >= 1 && lane <= 30 && cell0 < wout;
+        if (warp * 480 >= wout) {
+            // no final cell in this warp (strips are W / nstrips wide, not always 8 x 480): keep the ring protocol only
+            for (int c = 0; c < nchunks; c++, k++) {
+                const int slot = k % LT2_STAGES;
+                mbar_wait(&full[slot], (k / LT2_STAGES) & 1);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty[slot]);
+            }
+            continue;
+        }
         uint8_t* __restrict__ dt = p.dst + (long long)(y0 + p.doff1) * p.dpitch + x0 + cell0;
         const int soff = LT2_D0 + 32 + cell0;                    // offset of the lane's 16 cells in a shared-memory row
         Row S0, S1, S2, T0, T1, T2;
@@ -605,7 +615,7 @@ template <bool CELLS01, bool CONWAY> static int launch_tma2(const LifeParams& p,
     q.outb = std::min(LT2_OUTB, ((p.W + q.nstrips - 1) / q.nstrips + 127) / 128 * 128);  // equal strips
     q.nstrips = (p.W + q.outb - 1) / q.outb;
     const long long ctas = (long long)ctas_per_sm * num_sms();
-    long long nruns = std::max<long long>(1, (2 * ctas + q.nstrips - 1) / q.nstrips);
+    long long nruns = std::max<long long>(1, 2 * ctas / q.nstrips);  // at most two tasks per CTA: no straggler third task
     nruns = std::min<long long>(nruns, std::max(1, p.rows / 32));  // at least 32 rows per run (4 are re-read)
     q.nruns = (int)nruns;
     const long long grid = std::min<long long>(ctas, (long long)q.nstrips * q.nruns);

@@ -405,7 +405,7 @@ int s2_launch(const S2Params<T>& p0, cudaStream_t st) {
     p.nstrips = (Wb + S2_BXB - 1) / S2_BXB;
     const long long ctas = (long long)ctas_per_sm * num_sms();
     // four tasks per CTA, interleaved: every SM stays busy and the tail is a quarter of a task
-    long long nruns = std::max<long long>(1, (4 * ctas + p.nstrips - 1) / p.nstrips);
+    long long nruns = std::max<long long>(1, 4 * ctas / p.nstrips);
     nruns = std::min<long long>(nruns, std::max(1, p.rows / (4 * C::P)));  // keep the 2R re-read rows per run small
     p.nruns = (int)nruns;
     const long long grid = std::min<long long>(ctas, (long long)p.nstrips * p.nruns);
