@@ -12,6 +12,10 @@
 // table order (the reference's offset order): bit-identical to the StaticArrays left fold.
 // The R cells next to each end of axis 0 under Remove / Reflect go to gather_generic as two thin bands, so no warp
 // of this kernel runs an edge path (a slower edge warp would pace its whole CTA).
+// Two producers feed the same ring: bulk copies (TMA engine) when rows are 16-byte aligned and axis 0 is unpadded, and
+// element-granular cp.async (LDGSTS, completion counted on the same mbarriers) for everything else — Halo padding
+// (the ring of axis 0 is read straight through: parent index = logical + R, src/array.jl:367-377), odd widths, pitches
+// that are not multiples of 16 bytes. The consumers never notice: their lane-strided scalar accesses have no alignment.
 // Algorithmic traffic: sizeof(T) read + sizeof(T) written per cell.
 #include <algorithm>
 #include <type_traits>
@@ -39,7 +43,8 @@ template <typename T> struct GsParams {
     T* dst;
     long long spitch, dpitch;   // elements per column (axis-1 stride)
     int W, H;                   // logical size: W along the contiguous axis
-    int soff1, doff0, doff1;
+    int soff0, soff1, doff0, doff1;
+    int cpasync;                // 1: element-granular cp.async producer (unaligned / padded axis 0), 0: bulk copies
     int bc0, bc1;
     T pad, alpha;
     int x_lo, x_hi;             // destination cells handled here along axis 0 (edge bands are gather_generic's)
@@ -49,6 +54,18 @@ template <typename T> struct GsParams {
     const int* offs;            // [L][3]
     const T* weights;           // [L] (KERNELDOT) or null
 };
+
+// cp.async of one element (4 or 8 bytes) and the arrive-on-completion that ties a lane's copies to an mbarrier
+template <typename T> __device__ __forceinline__ void cp_async_elem(T* dst_smem, const T* src_gmem) {
+    static_assert(sizeof(T) == 4 || sizeof(T) == 8, "cp.async sizes");
+    if constexpr (sizeof(T) == 4)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
+    else
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 
 template <typename T> __device__ __forceinline__ long long gs_map_row(const GsParams<T>& p, int r) {
     if (p.soff1 > 0) return (long long)r + p.soff1;
@@ -81,7 +98,8 @@ __global__ void __launch_bounds__((GS_WARPS + 1) * 32, 2) gather_stream_kernel(c
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int R = p.R, L = p.L;
     if (threadIdx.x == 0) {
-        for (int s = 0; s < GS_NS; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], GS_WARPS); }
+        // full: one arrive.expect_tx (bulk copies) or one arrive-on-completion per producer lane (cp.async)
+        for (int s = 0; s < GS_NS; s++) { mbar_init(&full[s], p.cpasync ? 32 : 1); mbar_init(&empty[s], GS_WARPS); }
         mbar_fence_init();
     }
     for (int k = threadIdx.x; k < L; k += blockDim.x) {
@@ -96,6 +114,7 @@ __global__ void __launch_bounds__((GS_WARPS + 1) * 32, 2) gather_stream_kernel(c
     const int ntasks = p.nstrips * p.nruns;
     const int Wb = p.W * (int)sizeof(T);
     const int HLB = ((R * (int)sizeof(T) + 15) / 16) * 16;
+    constexpr int EWS = GS_BXB / (int)sizeof(T);   // cells per strip
     const bool rows_can_pad = p.soff1 == 0 && p.bc1 == SB200_REMOVE;
     unsigned kb = 0;  // ring position of stage 0 of the current task
     for (int task = blockIdx.x; task < ntasks; task += gridDim.x) {
@@ -106,8 +125,36 @@ __global__ void __launch_bounds__((GS_WARPS + 1) * 32, 2) gather_stream_kernel(c
         const int y1 = p.y_lo + (int)((long long)p.rows * (run + 1) / p.nruns);
         const int nout = y1 - y0;
         const int nst = nout + 2 * R;  // stage i holds source column y0 - R + i
+        if (warp == GS_WARPS && p.cpasync) {
+            // ---------------- producer, element-granular: lane l copies cells l, l+32, ... of every segment ----------------
+            const int xs = strip * EWS, wc = min(EWS, p.W - xs);            // strip cells [xs, xs + wc)
+            const bool ring0 = p.soff0 > 0;                                  // axis 0 has a ring: every neighbour is in the parent
+            const int lA = (xs > 0 || ring0) ? R : 0;
+            const int rA = ring0 ? R : min(R, p.W - (xs + wc));
+            const bool wrap0 = !ring0 && p.bc0 == SB200_WRAP;
+            for (int i = 0; i < nst; i++) {
+                const unsigned k = kb + i;
+                const int slot = k % GS_NS;
+                mbar_wait(&empty[slot], ((k / GS_NS) & 1) ^ 1);
+                T* srow = reinterpret_cast<T*>(ring + slot * GS_STAGE + GS_LEFT);   // strip cell 0
+                const long long prow = gs_map_row(p, y0 - R + i);
+                if (prow >= 0) {
+                    const T* g = p.src + prow * p.spitch + p.soff0;                  // logical cell 0 of the row
+                    for (int e = lane - lA; e < wc + rA; e += 32) cp_async_elem(srow + e, g + xs + e);
+                    if (wrap0 && lA == 0)
+                        for (int e = lane; e < R; e += 32) cp_async_elem(srow - R + e, g + p.W - R + e);
+                    if (wrap0 && rA < R)
+                        for (int e = lane; e < R - rA; e += 32) cp_async_elem(srow + wc + rA + e, g + e);
+                    cp_async_arrive_noinc(&full[slot]);
+                } else {
+                    mbar_arrive(&full[slot]);
+                }
+            }
+            kb += nst;
+            continue;
+        }
         if (warp == GS_WARPS) {
-            // ---------------- producer ----------------
+            // ---------------- producer, bulk copies ----------------
             if (lane == 0) {
                 const bool l_in = x0b > 0, r_in = x0b + wbytes < Wb;
                 const bool l_wrap = !l_in && p.bc0 == SB200_WRAP, r_wrap = !r_in && p.bc0 == SB200_WRAP;
@@ -250,13 +297,15 @@ template <typename T> static int gs_try(const Plan& pl, const void* src, void* d
     if (R < 1 || R > GS_MAXR || L < 1 || L > GS_TAB) return -1;
     for (int k = 0; k < L; k++)
         if (d.offsets_host[3 * k + 2] != 0) return -1;
-    if (d.src_off[0] != 0 || d.boundary[0] == SB200_USE) return -1;            // axis 0 must be unpadded
+    if (d.src_off[0] == 0 && d.boundary[0] == SB200_USE) return -1;
     if (d.src_off[1] == 0 && d.boundary[1] == SB200_USE) return -1;
     const long long Wb = d.size[0] * (long long)sizeof(T);
-    if (Wb % 16 || Wb < 64 || d.size[0] <= 4 * R) return -1;
-    if (Wb > GS_BXB && (Wb % GS_BXB) != 0 && (Wb % GS_BXB) < 64) return -1;    // last strip narrower than a wrap halo
-    if ((d.src_ext[0] * sizeof(T)) % 16 || (d.dst_ext[0] * sizeof(T)) % 16 || (d.dst_off[0] * sizeof(T)) % 16) return -1;
-    if (((uintptr_t)src | (uintptr_t)dst) & 15) return -1;
+    if (Wb < 64 || d.size[0] <= 4 * R) return -1;
+    // bulk copies need 16-byte aligned rows, an unpadded axis 0 and a last strip at least as wide as a wrap halo;
+    // otherwise the element-granular producer
+    const bool narrow_last = Wb > GS_BXB && (Wb % GS_BXB) != 0 && (Wb % GS_BXB) < 64;
+    const bool aligned = d.src_off[0] == 0 && Wb % 16 == 0 && (d.src_ext[0] * sizeof(T)) % 16 == 0 && ((uintptr_t)src & 15) == 0 && !narrow_last;
+    if (((uintptr_t)src | (uintptr_t)dst) % sizeof(T)) return -1;
     if (d.size[0] > (1LL << 28) || d.size[1] > (1LL << 30) || R >= d.size[1]) return -1;
     if (dd.lo[0] != 0 || dd.n[0] != d.size[0]) return -1;                       // regions only along axis 1
     if (dd.n[1] == 0) return SB200_OK;
@@ -264,11 +313,12 @@ template <typename T> static int gs_try(const Plan& pl, const void* src, void* d
     p.src = (const T*)src; p.dst = (T*)dst;
     p.spitch = d.src_ext[0]; p.dpitch = d.dst_ext[0];
     p.W = (int)d.size[0]; p.H = (int)d.size[1];
-    p.soff1 = d.src_off[1]; p.doff0 = d.dst_off[0]; p.doff1 = d.dst_off[1];
+    p.soff0 = d.src_off[0]; p.soff1 = d.src_off[1]; p.doff0 = d.dst_off[0]; p.doff1 = d.dst_off[1];
+    p.cpasync = aligned ? 0 : 1;
     p.bc0 = d.boundary[0]; p.bc1 = d.boundary[1];
     memcpy(&p.pad, &d.padval_bits, sizeof(T));
     p.alpha = (T)d.alpha;
-    const int band = d.boundary[0] == SB200_WRAP ? 0 : R;
+    const int band = (d.boundary[0] == SB200_WRAP || d.src_off[0] > 0) ? 0 : R;
     p.x_lo = band; p.x_hi = p.W - band;
     p.y_lo = (int)dd.lo[1]; p.rows = (int)dd.n[1];
     p.nstrips = (int)((Wb + GS_BXB - 1) / GS_BXB);

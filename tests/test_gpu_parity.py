@@ -369,6 +369,33 @@ def test_gather_stream_any_table(orc, dt, bc):
             assert l.sb200_last_kernel() == b"gather_stream_kernel", (tab, red, l.sb200_last_kernel())
 
 
+@pytest.mark.parametrize("dt", [np.float32, np.float64, np.int32])
+@pytest.mark.parametrize("pad", ["out", "in", "cond-odd"])
+def test_gather_stream_halo_padding_and_odd_widths(orc, dt, pad):
+    """Halo padding (ring on every axis, parent index = logical + R) and rows that are not 16-byte multiples: the
+    element-granular cp.async producer of csrc/gather_stream.cu. Named shapes that stream2d declines come here too."""
+    rng = np.random.default_rng(43)
+    l = A.lib()
+    isf = np.dtype(dt).kind == "f"
+    tables = [([(-1, 1), (-2, -1), (1, 0), (-2, 2)], 2), ("Window", 1, 0), ("Moore", 2, 0), ("Circle", 3, 0), ("Annulus", 4, 2),
+              ("VonNeumann", 1, 0)]
+    sizes = [(1030, 41), (2051, 37), (517, 64)] if pad == "cond-odd" else [(1040, 41), (2100, 37), (520, 64)]
+    for ti, tab in enumerate(tables):
+        if isinstance(tab[0], str):
+            name, R, RI = tab
+            offs = npr.offsets(name, R, 2, RI)
+        else:
+            offs, R = tab
+        W, H = sizes[ti % len(sizes)]
+        r = rand_array(rng, (W, H), dt)
+        w = rng.random(len(offs)) if isf else rng.integers(1, 5, len(offs))
+        for bc in ("remove", "wrap", "reflect"):
+            for red in (("sum", "mean", "max", "kerneldot", "diffusion") if isf else ("sum", "min", "kerneldot")):
+                both(orc, r, offs, R, bc, "cond" if pad == "cond-odd" else pad, red, padval=1.25 if isf else 3, weights=w, alpha=0.07,
+                     switching=(pad == "out" and red == "sum"))
+                assert l.sb200_last_kernel() == b"gather_stream_kernel", (tab, bc, red, l.sb200_last_kernel())
+
+
 def test_gather_stream_ring_rows_regions_specials(orc):
     rng = np.random.default_rng(42)
     l = A.lib()
