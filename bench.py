@@ -114,6 +114,9 @@ def workloads():
                      shape=(16384, 16384), dtype=np.float64, bytes_per_cell=16, iterated=False, seed=0x5EED0001),
         "mean1000": dict(desc="mapstencil(mean, Window(1)) Float64 1000x1000, Remove(0) (configs[0], README size)",
                          shape=(1000, 1000), dtype=np.float64, bytes_per_cell=16, iterated=False, seed=0x5EED0001),
+        "mean_halo": dict(desc="mapstencil(mean, Window(1)) Float64 16384x16384, Remove(0), padding=Halo{:out} (ring refresh + "
+                               "sweep per call; rows of the padded parent are not 16-byte multiples)",
+                          shape=(16384, 16384), dtype=np.float64, bytes_per_cell=16, iterated=False, seed=0x5EED0001),
         "kernel": dict(desc="kernelproduct, Kernel(Window(3), 7x7 Float32) 16384x16384, Remove(0)/Conditional (configs[2])",
                        shape=(16384, 16384), dtype=np.float32, bytes_per_cell=8, iterated=False, seed=0x5EED0003),
         "circle": dict(desc="maximum over Circle(4), Float32 32768x32768, Remove(0) (configs[3]a)",
@@ -150,6 +153,13 @@ def make_sweep(name, spec, torch, sb, shape=None):
             st["S"] = sb.iterate_(sb.Diffusion(0.1), st["S"], n)
     elif name in ("mean", "mean1000"):
         a = sb.StencilArray(src, sb.Window(1), boundary=sb.Remove(0.0))
+        dst = sb.colmajor_empty(shape, torch.float64, dev)
+
+        def run(n):
+            for _ in range(n):
+                sb.mapstencil_(sb.mean, dst, a)
+    elif name == "mean_halo":
+        a = sb.StencilArray(src, sb.Window(1), boundary=sb.Remove(0.0), padding=sb.Halo("out"))
         dst = sb.colmajor_empty(shape, torch.float64, dev)
 
         def run(n):
@@ -392,7 +402,7 @@ def main():
         del st, run
         torch.cuda.empty_cache()
         also = {}
-        for name in ("mean", "mean1000", "kernel", "circle", "positional", "scatter", "diffusion"):
+        for name in ("mean", "mean_halo", "mean1000", "kernel", "circle", "positional", "scatter", "diffusion"):
             if name == args.workload:
                 continue
             try:

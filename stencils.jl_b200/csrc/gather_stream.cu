@@ -24,7 +24,8 @@
 
 namespace sb {
 
-constexpr int GS_WARPS = 8;
+constexpr int GS_WARPS = 8;                   // consumer warps
+constexpr int GS_PW = 4;                      // producer warps (cp.async mode: stage i belongs to warp i % GS_PW; bulk mode: warp 0)
 constexpr int GS_BXB = GS_WARPS * 512;        // strip width in bytes
 constexpr int GS_LEFT = 128;                  // margin: global and shared addresses of the main copy agree mod 128
 constexpr int GS_STAGE = GS_LEFT + GS_BXB + 128;
@@ -87,7 +88,7 @@ template <typename T, int RED> __device__ __forceinline__ T gs_first(T v, T w) {
 }
 
 template <typename T, int RED>
-__global__ void __launch_bounds__((GS_WARPS + 1) * 32, 2) gather_stream_kernel(const __grid_constant__ GsParams<T> p) {
+__global__ void __launch_bounds__((GS_WARPS + GS_PW) * 32, 2) gather_stream_kernel(const __grid_constant__ GsParams<T> p) {
     constexpr int VX = 16 / (int)sizeof(T);
     constexpr int EW = 512 / (int)sizeof(T);   // elements per warp
     extern __shared__ __align__(128) unsigned char smem[];
@@ -125,14 +126,14 @@ __global__ void __launch_bounds__((GS_WARPS + 1) * 32, 2) gather_stream_kernel(c
         const int y1 = p.y_lo + (int)((long long)p.rows * (run + 1) / p.nruns);
         const int nout = y1 - y0;
         const int nst = nout + 2 * R;  // stage i holds source column y0 - R + i
-        if (warp == GS_WARPS && p.cpasync) {
+        if (warp >= GS_WARPS && p.cpasync) {
             // ---------------- producer, element-granular: lane l copies cells l, l+32, ... of every segment ----------------
             const int xs = strip * EWS, wc = min(EWS, p.W - xs);            // strip cells [xs, xs + wc)
             const bool ring0 = p.soff0 > 0;                                  // axis 0 has a ring: every neighbour is in the parent
             const int lA = (xs > 0 || ring0) ? R : 0;
             const int rA = ring0 ? R : min(R, p.W - (xs + wc));
             const bool wrap0 = !ring0 && p.bc0 == SB200_WRAP;
-            for (int i = 0; i < nst; i++) {
+            for (int i = warp - GS_WARPS; i < nst; i += GS_PW) {
                 const unsigned k = kb + i;
                 const int slot = k % GS_NS;
                 mbar_wait(&empty[slot], ((k / GS_NS) & 1) ^ 1);
@@ -153,9 +154,9 @@ __global__ void __launch_bounds__((GS_WARPS + 1) * 32, 2) gather_stream_kernel(c
             kb += nst;
             continue;
         }
-        if (warp == GS_WARPS) {
+        if (warp >= GS_WARPS) {
             // ---------------- producer, bulk copies ----------------
-            if (lane == 0) {
+            if (warp == GS_WARPS && lane == 0) {
                 const bool l_in = x0b > 0, r_in = x0b + wbytes < Wb;
                 const bool l_wrap = !l_in && p.bc0 == SB200_WRAP, r_wrap = !r_in && p.bc0 == SB200_WRAP;
                 const int r_in_bytes = r_in ? min(HLB, Wb - (x0b + wbytes)) : 0;
@@ -275,7 +276,7 @@ template <typename T, int RED> static int gs_launch(GsParams<T>& p, cudaStream_t
     if (dev != cfg_dev) {
         SB_CUDA(cudaFuncSetAttribute(gather_stream_kernel<T, RED>, cudaFuncAttributeMaxDynamicSharedMemorySize, GS_SMEM));
         int per_sm = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gather_stream_kernel<T, RED>, (GS_WARPS + 1) * 32, GS_SMEM) != cudaSuccess || per_sm < 1)
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gather_stream_kernel<T, RED>, (GS_WARPS + GS_PW) * 32, GS_SMEM) != cudaSuccess || per_sm < 1)
             per_sm = 1;
         ctas_per_sm = per_sm;
         cfg_dev = dev;
@@ -285,7 +286,7 @@ template <typename T, int RED> static int gs_launch(GsParams<T>& p, cudaStream_t
     nruns = std::min<long long>(nruns, std::max(1, p.rows / (4 * (2 * p.R + 1))));
     p.nruns = (int)nruns;
     const long long grid = std::min<long long>(ctas, (long long)p.nstrips * p.nruns);
-    gather_stream_kernel<T, RED><<<(unsigned)grid, (GS_WARPS + 1) * 32, GS_SMEM, st>>>(p);
+    gather_stream_kernel<T, RED><<<(unsigned)grid, (GS_WARPS + GS_PW) * 32, GS_SMEM, st>>>(p);
     SB_LAUNCH_CHECK();
     return SB200_OK;
 }
