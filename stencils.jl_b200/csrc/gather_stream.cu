@@ -56,18 +56,6 @@ template <typename T> struct GsParams {
     const T* weights;           // [L] (KERNELDOT) or null
 };
 
-// cp.async of one element (4 or 8 bytes) and the arrive-on-completion that ties a lane's copies to an mbarrier
-template <typename T> __device__ __forceinline__ void cp_async_elem(T* dst_smem, const T* src_gmem) {
-    static_assert(sizeof(T) == 4 || sizeof(T) == 8, "cp.async sizes");
-    if constexpr (sizeof(T) == 4)
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
-    else
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
-}
-__device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
-    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-
 template <typename T> __device__ __forceinline__ long long gs_map_row(const GsParams<T>& p, int r) {
     if (p.soff1 > 0) return (long long)r + p.soff1;
     if (r >= 0 && r < p.H) return r;

@@ -86,7 +86,8 @@ template <typename T> struct S2Params {
     T* dst;
     long long spitch, dpitch;  // elements per row
     int W, H;                  // logical size, axis 0 = W
-    int soff1, doff0, doff1;
+    int soff0, soff1, doff0, doff1;
+    int cpasync;               // 1: element-granular cp.async producer (Halo ring on axis 0 / rows not 16-byte aligned)
     int bc0, bc1;
     T pad;
     int y_lo, rows;
@@ -296,7 +297,7 @@ __global__ void __launch_bounds__((S2_WARPS + 1) * 32, 2) stream2d_kernel(const 
     unsigned char* ring = smem + 128;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
-        for (int s = 0; s < C::STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], S2_WARPS); }
+        for (int s = 0; s < C::STAGES; s++) { mbar_init(&full[s], p.cpasync ? 32 : 1); mbar_init(&empty[s], S2_WARPS); }
         mbar_fence_init();
     }
     __syncthreads();
@@ -312,6 +313,33 @@ __global__ void __launch_bounds__((S2_WARPS + 1) * 32, 2) stream2d_kernel(const 
         const int nout = y1 - y0;
         const int nsrc = nout + 2 * R;  // source rows y0-R .. y1-1+R
         const int nchunks = (nsrc + CH - 1) / CH;
+        if (warp == S2_WARPS && p.cpasync) {
+            // ---------------- producer, element-granular (same shared-memory layout: strip cell 0 at LEFT) ----------------
+            const int xs = x0b / (int)sizeof(T), wc = wbytes / (int)sizeof(T);
+            const bool ring0 = p.soff0 > 0;                       // axis 0 has a ring: every neighbour is a cell of the parent
+            const int lA = (xs > 0 || ring0) ? R : 0;
+            const int rA = ring0 ? R : min(R, p.W - (xs + wc));
+            const bool wrap0 = !ring0 && p.bc0 == SB200_WRAP;
+            for (int c = 0; c < nchunks; c++, k++) {
+                const int slot = k % C::STAGES;
+                mbar_wait(&empty[slot], ((k / C::STAGES) & 1) ^ 1);
+                unsigned char* sbase = ring + slot * (CH * C::ROWB);
+                for (int j = 0; j < CH; j++) {
+                    const int i = c * CH + j;
+                    const long long prow = i < nsrc ? s2_map_row(p, y0 - R + i) : -1;
+                    if (prow < 0) continue;
+                    const T* g = p.src + prow * p.spitch + p.soff0;                        // logical cell 0 of the row
+                    T* srow = reinterpret_cast<T*>(sbase + j * C::ROWB + C::LEFT);          // strip cell 0
+                    for (int e = lane - lA; e < wc + rA; e += 32) cp_async_elem(srow + e, g + xs + e);
+                    if (wrap0 && lA == 0)
+                        for (int e = lane; e < R; e += 32) cp_async_elem(srow - R + e, g + p.W - R + e);
+                    if (wrap0 && rA < R)
+                        for (int e = lane; e < R - rA; e += 32) cp_async_elem(srow + wc + rA + e, g + e);
+                }
+                cp_async_arrive_noinc(&full[slot]);
+            }
+            continue;
+        }
         if (warp == S2_WARPS) {
             // ---------------- producer ----------------
             if (lane == 0) {
@@ -361,10 +389,11 @@ __global__ void __launch_bounds__((S2_WARPS + 1) * 32, 2) stream2d_kernel(const 
         th.gx = (x0b + th.xtb) / (int)sizeof(T);
         // Threads whose segment crosses the array edge under Remove / Reflect patch their halo cells themselves
         // (under Wrap the producer already copied the wrapped columns).
-        th.edge_l = th.active && p.bc0 != SB200_WRAP && th.gx - R < 0;
-        th.edge_r = th.active && p.bc0 != SB200_WRAP && th.gx + VX - 1 + R >= p.W;
-        th.nl = R - th.gx;                 // > 0 only next to the left edge
-        th.rlim = p.W - th.gx - VX;        // < R only next to the right edge
+        const bool ring0 = p.soff0 > 0;   // neighbours beyond the logical edge are ring cells the producer copied
+        th.edge_l = th.active && !ring0 && p.bc0 != SB200_WRAP && th.gx - R < 0;
+        th.edge_r = th.active && !ring0 && p.bc0 != SB200_WRAP && th.gx + VX - 1 + R >= p.W;
+        th.nl = ring0 ? 0 : R - th.gx;                 // > 0 only next to the left edge
+        th.rlim = ring0 ? R : p.W - th.gx - VX;        // < R only next to the right edge
         th.y0 = y0; th.nout = nout;
         th.may_pad = p.soff1 == 0 && p.bc1 == SB200_REMOVE;
         th.dt = p.dst + (long long)(y0 + p.doff1) * p.dpitch + p.doff0 + th.gx;
@@ -418,15 +447,16 @@ int s2_launch(const S2Params<T>& p0, cudaStream_t st) {
 template <typename T> bool s2_accepts(const Plan& pl, const void* src, void* dst, S2Params<T>& p) {
     const sb200_desc& d = pl.d;
     if (d.ndim != 2 || pl.shape_tag < 0 || pl.shape_ndim != 2) return false;
-    if (d.src_off[0] != 0) return false;                         // axis 0 must be unpadded (ring rows on axis 1 are fine)
-    if ((d.size[0] * sizeof(T)) % 16 || (d.src_ext[0] * sizeof(T)) % 16) return false;
-    if ((d.dst_ext[0] * sizeof(T)) % 16 || (d.dst_off[0] * sizeof(T)) % 16) return false;
-    if (((uintptr_t)src | (uintptr_t)dst) & 15) return false;
+    // bulk copies need an unpadded axis 0 and 16-byte aligned source rows; a Halo ring on axis 0 or unaligned rows take
+    // the element-granular producer. The consumers' 128-bit stores need aligned dest rows either way.
+    const bool aligned = d.src_off[0] == 0 && (d.src_ext[0] * sizeof(T)) % 16 == 0 && ((uintptr_t)src & 15) == 0;
+    if ((d.size[0] * sizeof(T)) % 16 || ((uintptr_t)src % sizeof(T))) return false;
+    if ((d.dst_ext[0] * sizeof(T)) % 16 || (d.dst_off[0] * sizeof(T)) % 16 || ((uintptr_t)dst & 15)) return false;
     if (d.size[0] > (1LL << 28) || d.size[1] > (1LL << 30)) return false;
     if (d.size[0] * (long long)sizeof(T) < 16 * 2) return false;
     if (pl.dd.lo[0] != 0 || pl.dd.n[0] != d.size[0]) return false;  // regions only along axis 1
     if (d.src_off[1] == 0 && d.boundary[1] == SB200_USE) return false;
-    if (d.boundary[0] == SB200_USE) return false;
+    if (d.src_off[0] == 0 && d.boundary[0] == SB200_USE) return false;
     if (d.radius >= d.size[0]) return false;
     const long long Wb_ = d.size[0] * (long long)sizeof(T);
     if (Wb_ < 64) return false;
@@ -434,7 +464,8 @@ template <typename T> bool s2_accepts(const Plan& pl, const void* src, void* dst
     p.src = (const T*)src; p.dst = (T*)dst;
     p.spitch = d.src_ext[0]; p.dpitch = d.dst_ext[0];
     p.W = (int)d.size[0]; p.H = (int)d.size[1];
-    p.soff1 = d.src_off[1]; p.doff0 = d.dst_off[0]; p.doff1 = d.dst_off[1];
+    p.soff0 = d.src_off[0]; p.soff1 = d.src_off[1]; p.doff0 = d.dst_off[0]; p.doff1 = d.dst_off[1];
+    p.cpasync = aligned ? 0 : 1;
     p.bc0 = d.boundary[0]; p.bc1 = d.boundary[1];
     memcpy(&p.pad, &d.padval_bits, sizeof(T));
     p.y_lo = (int)pl.dd.lo[1]; p.rows = (int)pl.dd.n[1];

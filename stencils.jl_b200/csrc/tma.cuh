@@ -44,6 +44,20 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
                  : "memory");
 }
 
+// Element-granular asynchronous copy (LDGSTS) of one 4- or 8-byte element, for layouts the bulk-copy engine cannot
+// address (rows that are not 16-byte aligned, Halo padding), and the arrive-on-completion that ties all prior cp.async
+// of the executing thread to an mbarrier (.noinc: the arrival is part of the barrier's expected count).
+template <typename T> __device__ __forceinline__ void cp_async_elem(T* dst_smem, const T* src_gmem) {
+    static_assert(sizeof(T) == 4 || sizeof(T) == 8, "cp.async sizes");
+    if constexpr (sizeof(T) == 4)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
+    else
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
 // Tiled copies through a tensor map (coordinates in elements, innermost first; OOB elements arrive as zero).
 __device__ __forceinline__ void tma_load_2d(void* dst_smem, const void* tmap, int c0, int c1, uint64_t* bar) {
     asm volatile(

@@ -382,7 +382,7 @@ def bench_weak(workload, spec, steps, warmup, synth=None):
     t = field.permute(*reversed(range(len(shape)))).contiguous()
     del field
     if workload == "life":
-        st, red, kw, et, R, ghost = Moore(1), A.LIFE, dict(born_mask=1 << 3, survive_mask=0b1100), A.U8, 1, 16
+        st, red, kw, et, R, ghost = Moore(1), A.LIFE, dict(born_mask=1 << 3, survive_mask=0b1100), A.U8, 1, 32
         bcs = (A.WRAP, A.WRAP)
     elif workload == "diffusion":
         st, red, kw, et, R, ghost = VonNeumann(1, 3), A.DIFFUSION, dict(alpha=0.1), A.F32, 1, 4

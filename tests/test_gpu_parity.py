@@ -393,7 +393,12 @@ def test_gather_stream_halo_padding_and_odd_widths(orc, dt, pad):
             for red in (("sum", "mean", "max", "kerneldot", "diffusion") if isf else ("sum", "min", "kerneldot")):
                 both(orc, r, offs, R, bc, "cond" if pad == "cond-odd" else pad, red, padval=1.25 if isf else 3, weights=w, alpha=0.07,
                      switching=(pad == "out" and red == "sum"))
-                assert l.sb200_last_kernel() == b"gather_stream_kernel", (tab, bc, red, l.sb200_last_kernel())
+                # streaming either way: the compile-time kernels take the named shapes they instantiate (Halo rings and
+                # unaligned source rows through their cp.async producer), the run-time-table kernel everything else
+                assert l.sb200_last_kernel() in (b"gather_stream_kernel", b"stream2d_kernel"), (tab, bc, red, l.sb200_last_kernel())
+                if isf and pad == "out" and isinstance(tab[0], str) and tab[0] in ("Window", "Moore", "Circle", "VonNeumann") \
+                        and not (pad == "out" and red == "sum"):
+                    assert l.sb200_last_kernel() == b"stream2d_kernel", (tab, bc, red, pad)
 
 
 def test_gather_stream_ring_rows_regions_specials(orc):
