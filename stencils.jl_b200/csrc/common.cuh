@@ -112,6 +112,18 @@ __device__ __forceinline__ float jl_min(float a, float b) {
     asm("min.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
     return r;
 }
+// Three-input forms (sm_100 FMNMX3, same issue rate as FMNMX: two comparisons per slot). Maximum / minimum with these
+// semantics (NaN wins, +0 > -0) do not depend on the order of the operands.
+__device__ __forceinline__ float jl_max3(float a, float b, float c) {
+    float r;
+    asm("max.NaN.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+}
+__device__ __forceinline__ float jl_min3(float a, float b, float c) {
+    float r;
+    asm("min.NaN.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+}
 __device__ __forceinline__ double jl_max(double a, double b) {
     if (a != a || b != b) return __longlong_as_double(0x7ff8000000000000LL);
     if (a > b) return a;
@@ -124,6 +136,8 @@ __device__ __forceinline__ double jl_min(double a, double b) {
     if (a > b) return b;
     return (__double_as_longlong(a) < 0) ? a : b;  // equal: prefer -0.0
 }
+__device__ __forceinline__ double jl_max3(double a, double b, double c) { return jl_max(jl_max(a, b), c); }
+__device__ __forceinline__ double jl_min3(double a, double b, double c) { return jl_min(jl_min(a, b), c); }
 __device__ __forceinline__ uint8_t jl_max(uint8_t a, uint8_t b) { return a > b ? a : b; }
 __device__ __forceinline__ uint8_t jl_min(uint8_t a, uint8_t b) { return a < b ? a : b; }
 __device__ __forceinline__ int32_t jl_max(int32_t a, int32_t b) { return a > b ? a : b; }

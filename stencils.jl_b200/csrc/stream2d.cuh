@@ -210,7 +210,7 @@ __device__ __forceinline__ void s2_row(const S2Params<T>& p, const S2Thread<T>& 
 #pragma unroll
             for (int w_ = 1; w_ <= (NESTED ? R : 0); w_++) {
                 const T lo_ = seg[R + v - w_], hi_ = seg[R + v + w_];
-                m[w_][v] = RED == SB200_MAX ? jl_max(jl_max(m[w_ - 1][v], lo_), hi_) : jl_min(jl_min(m[w_ - 1][v], lo_), hi_);
+                m[w_][v] = RED == SB200_MAX ? jl_max3(m[w_ - 1][v], lo_, hi_) : jl_min3(m[w_ - 1][v], lo_, hi_);
             }
         }
     }
@@ -227,7 +227,12 @@ __device__ __forceinline__ void s2_row(const S2Params<T>& p, const S2Thread<T>& 
 #pragma unroll
             for (int v = 0; v < VX; v++) {
                 const T x = m[hw < 0 ? 0 : hw][v];
-                acc[s][v] = dy == DY0 ? x : (RED == SB200_MAX ? jl_max(acc[s][v], x) : jl_min(acc[s][v], x));
+                // rows fold in pairs: the row's extremum waits in `cen` (unused by max / min) until the next row arrives
+                // and both enter one three-input instruction; convex shapes span 2R+1 rows, so the last row is a pair's end
+                const int q = dy - DY0;
+                if (q == 0) acc[s][v] = x;
+                else if (q & 1) cen[s][v] = x;
+                else acc[s][v] = RED == SB200_MAX ? jl_max3(acc[s][v], cen[s][v], x) : jl_min3(acc[s][v], cen[s][v], x);
             }
         } else
         {

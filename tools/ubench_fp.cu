@@ -61,6 +61,16 @@ template <int MODE> __global__ void k(float* out, const float* in, int iters) {
         }
         float s = 0; for (int i = 0; i < ILP; i++) s += acc[i];
         out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+    } else if (MODE == 8) {   // 3-input FMNMX3 chain (counted as 2 ops each)
+        float acc[ILP];
+        for (int i = 0; i < ILP; i++) acc[i] = in[i];
+        for (int it = 0; it < iters; it++) {
+#pragma unroll
+            for (int i = 0; i < ILP; i++) asm("max.NaN.f32 %0, %0, %1, %2;" : "+f"(acc[i]) : "f"((i & 1) ? x0 : x1), "f"((i & 2) ? x1 : x0));
+            x0 += 1.0f; x1 += 1.0f;
+        }
+        float s = 0; for (int i = 0; i < ILP; i++) s += acc[i];
+        out[blockIdx.x * blockDim.x + threadIdx.x] = s;
     } else if (MODE == 4) {   // scalar FADD only
         float acc[ILP];
         for (int i = 0; i < ILP; i++) acc[i] = in[i];
@@ -145,6 +155,7 @@ int main() {
         run<5>("add.f32x2", out, in, warps);
         run<6>("fma2(x,w,-0)+add2", out, in, warps);
         run<7>("FMUL + add2", out, in, warps);
+        run<8>("FMNMX3 (x0.5: 16/iter)", out, in, warps);
     }
     return 0;
 }
