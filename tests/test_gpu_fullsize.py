@@ -1,0 +1,191 @@
+"""GPU tests at the FULL sizes of BASELINE.json (SURVEY §8d tier T3). The oracle cannot sweep 10^9 cells in seconds, so
+each configuration is checked three ways: (1) the oracle on sampled windows of the same field (corners, edges across
+the wrap, interior), compared on the cells whose whole dependence cone lies inside the window; (2) bit-for-bit equality
+of the streaming kernel with an independent kernel of this library (the one-thread-per-cell generic kernel, the
+single-generation Life kernel, the non-TMA scatter) over the whole grid; (3) a size-independent property of the
+operation (monotone maps commute with maximum, ...)."""
+import numpy as np
+import pytest
+
+from oracle import np_restatement as npr
+from stencils_b200 import _abi as A
+from stencils_b200._desc import build_desc
+from stencils_b200.synth import synth_torch
+from tests.util import bits_equal
+
+pytestmark = pytest.mark.gpu
+
+
+def _stream():
+    import torch
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _window(t, lo, n, wrap):
+    """Logical window [lo, lo+n) per axis of the column-major tensor `t` as an F-ordered NumPy array; indices wrap
+    around the array when `wrap`, else the window must lie inside."""
+    import torch
+    v = t
+    for ax, (l, m) in enumerate(zip(lo, n)):
+        idx = torch.arange(l, l + m, device=t.device)
+        if wrap:
+            idx = idx % t.shape[ax]
+        v = v.index_select(ax, idx)
+    return np.asfortranarray(v.cpu().numpy())
+
+
+def _gather(h, src, dst):
+    A.check(A.lib().sb200_gather(h.ptr(), src.data_ptr(), dst.data_ptr(), _stream()))
+
+
+def _biteq(x, y):
+    """bit-for-bit equality of two column-major tensors"""
+    import torch
+    it = {1: torch.uint8, 4: torch.int32, 8: torch.int64}[x.element_size()]
+    rev = tuple(reversed(range(x.dim())))
+    return torch.equal(x.permute(*rev).view(it), y.permute(*rev).view(it))
+
+
+def _colmajor(shape, dtype, device):
+    from stencils_b200.array import colmajor_empty
+    return colmajor_empty(shape, dtype, device)
+
+
+def _check_windows(orc, src, out, kw, cone, windows, wrap, steps=1):
+    """kw: build_desc arguments without size; cone: cells of margin whose values depend on data outside the window."""
+    nd = src.dim()
+    for lo, n in windows:
+        w = _window(src, lo, n, wrap)
+        h = build_desc(size=w.shape, **kw)
+        a = w.copy(order="F")
+        b = np.zeros_like(a, order="F")
+        if steps == 1:
+            want = orc.gather(h, a, b)
+        else:
+            want = orc.iterate(h, a, b, steps)
+        got = _window(out, lo, n, wrap)
+        inner = []
+        for ax in range(nd):
+            at_lo = (not wrap) and lo[ax] == 0                    # the window starts at the array edge: exact there
+            at_hi = (not wrap) and lo[ax] + n[ax] == src.shape[ax]
+            inner.append(slice(0 if at_lo else cone, n[ax] if at_hi else n[ax] - cone))
+        bits_equal(np.ascontiguousarray(got[tuple(inner)]), np.ascontiguousarray(want[tuple(inner)]))
+
+
+def test_life_16384_two_generation_kernel_vs_single_and_oracle(orc):
+    """configs[1]: Moore(1) Life, UInt8 16384x16384, Wrap."""
+    import torch
+    W = H = 16384
+    steps = 10
+    src = synth_torch((W, H), np.uint8, 0x5EED0002, "cuda")
+    kw = dict(eltype=A.U8, out_eltype=A.U8, offsets=npr.offsets("Moore", 1, 2), radius=1, boundary=A.WRAP, reducer=A.LIFE)
+    h = build_desc(size=(W, H), **kw)
+    a, b = src.clone(), torch.empty_like(src)
+    A.check(A.lib().sb200_iterate(h.ptr(), a.data_ptr(), b.data_ptr(), steps, _stream()))
+    assert A.lib().sb200_last_kernel().startswith(b"life_tma2_kernel")
+    # the same ten generations, one launch of the single-generation kernel each
+    c, d = src.clone(), torch.empty_like(src)
+    h1 = build_desc(size=(W, H), flags=A.FLAG_CELLS_01, **kw)
+    for _ in range(steps):
+        _gather(h1, c, d)
+        c, d = d, c
+    assert A.lib().sb200_last_kernel().startswith(b"life_tma_kernel")
+    torch.cuda.synchronize()
+    assert torch.equal(a, c)
+    assert 0 < int(a.sum()) < W * H // 2
+    wins = [((-300, -300), (600, 600)), ((W - 250, 7000), (500, 400)), ((3840 - 200, 100), (400, 300)), ((9000, H - 180), (300, 360))]
+    _check_windows(orc, src, a, kw, cone=steps, windows=wins, wrap=True, steps=steps)
+
+
+def test_mean_f64_16384_and_kernelproduct_f32_16384(orc):
+    """configs[0] at roofline size and configs[2]."""
+    import torch
+    W = H = 16384
+    for dt, tdt, shape_name, R, red, et in ((np.float64, torch.float64, "Window", 1, A.MEAN, A.F64),
+                                            (np.float32, torch.float32, "Window", 3, A.KERNELDOT, A.F32)):
+        src = synth_torch((W, H), dt, 0x5EED0001, "cuda")
+        offs = npr.offsets(shape_name, R, 2)
+        w = np.random.default_rng(3).random(len(offs)).astype(dt)
+        kw = dict(eltype=et, out_eltype=et, offsets=offs, radius=R, boundary=A.REMOVE, reducer=red, padval=0, weights=w)
+        out = _colmajor((W, H), tdt, "cuda")
+        _gather(build_desc(size=(W, H), **kw), src, out)
+        assert A.lib().sb200_last_kernel() == b"stream2d_kernel"
+        ref = _colmajor((W, H), tdt, "cuda")
+        _gather(build_desc(size=(W, H), flags=A.FLAG_FORCE_GENERIC, **kw), src, ref)
+        assert A.lib().sb200_last_kernel() == b"gather_generic"
+        torch.cuda.synchronize()
+        assert _biteq(out, ref)
+        wins = [((0, 0), (300, 200)), ((W - 260, H - 300), (260, 300)), ((4096 // np.dtype(dt).itemsize - 100, 5000), (200, 150)),
+                ((0, 8000), (128, 256))]
+        _check_windows(orc, src, out, kw, cone=R, windows=wins, wrap=False)
+        del src, out, ref
+
+
+def test_circle4_max_and_positional_scatter_32768(orc):
+    """configs[3]: maximum over Circle(4) and scatterstencil!(+) over a Positional stencil, Float32 32768x32768."""
+    import torch
+    W = H = 32768
+    src = synth_torch((W, H), np.float32, 0x5EED0004, "cuda")
+    offs = npr.offsets("Circle", 4, 2)
+    kw = dict(eltype=A.F32, out_eltype=A.F32, offsets=offs, radius=4, boundary=A.REMOVE, reducer=A.MAX, padval=0)
+    out = _colmajor((W, H), torch.float32, "cuda")
+    _gather(build_desc(size=(W, H), **kw), src, out)
+    assert A.lib().sb200_last_kernel() == b"stream2d_kernel"
+    torch.cuda.synchronize()
+    assert bool((out >= src).all())                       # the centre is one of the 69 taps
+    wins = [((0, 0), (200, 220)), ((W - 210, H - 190), (210, 190)), ((1024 - 64, 20000), (160, 128)), ((17000, 0), (96, 300))]
+    _check_windows(orc, src, out, kw, cone=4, windows=wins, wrap=False)
+    # maximum commutes with a monotone map that is exact in floating point
+    src2 = src * 2.0
+    out2 = _colmajor((W, H), torch.float32, "cuda")
+    _gather(build_desc(size=(W, H), **kw), src2, out2)
+    torch.cuda.synchronize()
+    assert torch.equal(out2, out * 2.0)
+    del src2, out2, out
+    # Positional scatter with val_k = centre * w_k, op = +, dest pre-filled
+    soffs = [(-1, 1), (-2, -1), (1, 0), (-2, 2)]
+    w = np.array([0.4, 0.3, 0.2, 0.1], dtype=np.float32)
+    skw = dict(eltype=A.F32, out_eltype=A.F32, offsets=soffs, radius=2, boundary=A.REMOVE, weights=w, scatter_op=A.OP_ADD,
+               scatter_rule=A.SCATTER_CENTER_WEIGHTS)
+    dest0 = synth_torch((W, H), np.float32, 0x5EED0014, "cuda")
+    d1, d2 = dest0.clone(), dest0.clone()
+    A.check(A.lib().sb200_scatter(build_desc(size=(W, H), **skw).ptr(), src.data_ptr(), d1.data_ptr(), _stream()))
+    assert A.lib().sb200_last_kernel() == b"scatter_stream_kernel"
+    A.check(A.lib().sb200_scatter(build_desc(size=(W, H), flags=A.FLAG_NO_TMA, **skw).ptr(), src.data_ptr(), d2.data_ptr(), _stream()))
+    assert A.lib().sb200_last_kernel() == b"scatter_fast_kernel"
+    torch.cuda.synchronize()
+    assert _biteq(d1, d2)
+    for lo, n in [((0, 0), (150, 130)), ((W - 140, H - 120), (140, 120)), ((1024 - 50, 9000), (100, 90))]:
+        sw, dw = _window(src, lo, n, False), _window(dest0, lo, n, False)
+        want = orc.scatter(build_desc(size=sw.shape, **skw), sw, dw.copy(order="F"))
+        got = _window(d1, lo, n, False)
+        inner = tuple(slice(0 if lo[ax] == 0 else 2, n[ax] if lo[ax] + n[ax] == (W, H)[ax] else n[ax] - 2) for ax in range(2))
+        # the fold order of a destination cell depends on its column residue mod 2R+1: keep the window's phase
+        if lo[1] % 5 == 0:
+            bits_equal(np.ascontiguousarray(got[inner]), np.ascontiguousarray(want[inner]))
+        else:
+            np.testing.assert_allclose(got[inner], want[inner], rtol=1e-6)
+
+
+def test_diffusion_1024_cubed(orc):
+    """configs[4]: VonNeumann(1,3) diffusion, Float32 1024^3, Wrap, three steps."""
+    import torch
+    n = 1024
+    steps = 3
+    src = synth_torch((n, n, n), np.float32, 0x5EED0005, "cuda")
+    kw = dict(eltype=A.F32, out_eltype=A.F32, offsets=npr.offsets("VonNeumann", 1, 3), radius=1, boundary=A.WRAP,
+              reducer=A.DIFFUSION, alpha=0.1)
+    h = build_desc(size=(n, n, n), **kw)
+    a, b = src.clone(), torch.empty_like(src)
+    A.check(A.lib().sb200_iterate(h.ptr(), a.data_ptr(), b.data_ptr(), steps, _stream()))
+    assert A.lib().sb200_last_kernel() == b"stream3d_kernel"
+    res = b if steps % 2 else a
+    # one step: the 2.5-D streaming kernel against the one-thread-per-cell kernel over the whole grid
+    o1, o2 = torch.empty_like(src), torch.empty_like(src)
+    _gather(h, src, o1)
+    _gather(build_desc(size=(n, n, n), flags=A.FLAG_FORCE_GENERIC, **kw), src, o2)
+    assert A.lib().sb200_last_kernel() == b"gather_generic"
+    torch.cuda.synchronize()
+    assert _biteq(o1, o2)
+    wins = [((-20, -20, -20), (48, 44, 40)), ((1000, 500, 1010), (40, 36, 44)), ((250, 1016, 300), (36, 40, 32))]
+    _check_windows(orc, src, res, kw, cone=steps, windows=wins, wrap=True, steps=steps)
