@@ -126,6 +126,8 @@ def workloads():
         "positional": dict(desc="mapstencil(sum, Positional((-1,1),(-2,-1),(1,0),(-2,2))) Float32 16384x16384, Wrap "
                                 "(run-time offset table; README.md:102 stencil)",
                            shape=(16384, 16384), dtype=np.float32, bytes_per_cell=8, iterated=False, seed=0x5EED0006),
+        "window3d": dict(desc="mapstencil(mean, Window(1,3)) Float32 768^3, Wrap (27-point 3-D table at run time)",
+                         shape=(768, 768, 768), dtype=np.float32, bytes_per_cell=8, iterated=False, seed=0x5EED0007),
         "diffusion": dict(desc="3-D diffusion: VonNeumann(1,3) Float32 1024^3, Wrap, iterated (configs[4])",
                           shape=(1024, 1024, 1024), dtype=np.float32, bytes_per_cell=8, iterated=True, seed=0x5EED0005),
     }
@@ -188,6 +190,13 @@ def make_sweep(name, spec, torch, sb, shape=None):
         def run(n):
             for _ in range(n):
                 sb.mapstencil_(sb.sum, dst, a)
+    elif name == "window3d":
+        a = sb.StencilArray(src, sb.Window(1, 3), boundary=sb.Wrap())
+        dst = sb.colmajor_empty(shape, torch.float32, dev)
+
+        def run(n):
+            for _ in range(n):
+                sb.mapstencil_(sb.mean, dst, a)
     elif name == "scatter":
         a = sb.StencilArray(src, sb.Positional((-1, 1), (-2, -1), (1, 0), (-2, 2)), boundary=sb.Remove(np.float32(0)))
         dst = sb.colmajor_empty(shape, torch.float32, dev)
@@ -402,7 +411,7 @@ def main():
         del st, run
         torch.cuda.empty_cache()
         also = {}
-        for name in ("mean", "mean_halo", "mean1000", "kernel", "circle", "positional", "scatter", "diffusion"):
+        for name in ("mean", "mean_halo", "mean1000", "kernel", "circle", "positional", "scatter", "window3d", "diffusion"):
             if name == args.workload:
                 continue
             try:

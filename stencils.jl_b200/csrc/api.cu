@@ -318,6 +318,7 @@ static int do_gather(const sb200_desc* d, const void* src, void* dst, cudaStream
         if (rc < 0) rc = try_diffusion3d(*pl, src, dst, st);
         if (rc < 0) rc = try_tile2d(*pl, src, dst, st);
         if (rc < 0) rc = try_gather_stream(*pl, src, dst, st);
+        if (rc < 0) rc = try_gather_stream3d(*pl, src, dst, st);
     }
     if (rc < 0) rc = launch_generic_gather(*pl, src, dst, st);
     if (rc == SB200_OK && g_mirror.ptr && !g_mirror.honoured) {

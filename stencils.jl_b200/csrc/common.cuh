@@ -175,6 +175,7 @@ bool life2_accepts(const sb200_desc& d, const Plan& pl);  // SB200_FLAG_DOUBLE_S
 int try_tile2d(const Plan& pl, const void* src, void* dst, cudaStream_t st);
 int try_diffusion3d(const Plan& pl, const void* src, void* dst, cudaStream_t st);
 int try_gather_stream(const Plan& pl, const void* src, void* dst, cudaStream_t st);
+int try_gather_stream3d(const Plan& pl, const void* src, void* dst, cudaStream_t st);
 int try_scatter_fast(const Plan& pl, const void* src, void* dst, cudaStream_t st);
 int try_scatter_stream(const Plan& pl, const void* src, void* dst, cudaStream_t st, int x_lo, int x_hi, int y_lo, int y_hi);
 

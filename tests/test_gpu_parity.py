@@ -457,6 +457,53 @@ def test_stream3d_ghost_planes_and_regions(orc):
             assert b"stream3d" in l.sb200_last_kernel()
 
 
+G3_TABLES = [("Window", 1), ("Moore", 1), ("VonNeumann", 2), ("Cross", 2), ("Circle", 2), ("Window", 2),
+             [(0, 0, -1), (1, -1, 0), (-2, 0, 2), (0, 2, 1), (1, 1, 1)]]
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64, np.int32])
+@pytest.mark.parametrize("bc", ["remove", "wrap", "reflect"])
+def test_gather_stream3d_any_table(orc, dt, bc):
+    """The run-time-table 3-D streaming gather (csrc/gather_stream3d.cu): named 3-D shapes other than VonNeumann(1,3)
+    and a Positional table, several tiles in x and y with ragged last ones, z runs, every reducer, bit-exact."""
+    rng = np.random.default_rng(61)
+    l = A.lib()
+    es = np.dtype(dt).itemsize
+    isf = np.dtype(dt).kind == "f"
+    sizes = [(512 // es + 32, 37, 21), (64 // es * 3, 20, 40), (2 * 512 // es, 16, 19)]
+    for ti, tab in enumerate(G3_TABLES):
+        if isinstance(tab, tuple):
+            offs, R = npr.offsets(tab[0], tab[1], 3), tab[1]
+        else:
+            offs, R = tab, 2
+        shape = sizes[ti % len(sizes)]
+        r = rand_array(rng, shape, dt)
+        w = rng.random(len(offs)) if isf else rng.integers(1, 5, len(offs))
+        for red in (("sum", "mean", "max", "kerneldot", "diffusion") if isf else ("sum", "min", "kerneldot")):
+            both(orc, r, offs, R, bc, "cond", red, padval=1.25 if isf else 3, weights=w, alpha=0.07)
+            assert l.sb200_last_kernel() == b"gather_stream3d_kernel", (tab, red, l.sb200_last_kernel())
+
+
+def test_gather_stream3d_ghost_planes_regions_specials(orc):
+    rng = np.random.default_rng(62)
+    l = A.lib()
+    X, Y, Z, G = 192, 24, 30, 3
+    parent = rand_array(rng, (X, Y, Z + 2 * G), np.float32)
+    parent[rng.random(parent.shape) < 0.03] = np.nan
+    parent[rng.random(parent.shape) < 0.1] = -0.0
+    for offs, R, red in ((npr.offsets("Window", 1, 3), 1, A.MAX), (npr.offsets("Moore", 1, 3), 1, A.SUM),
+                         (npr.offsets("VonNeumann", 2, 3), 2, A.DIFFUSION)):
+        for region in (None, ((0, 0, 0), (X, Y, 7)), ((0, 0, 7), (X, Y, Z - 2)), ((0, 0, Z - 2), (X, Y, Z))):
+            for bc0, bc1 in ((A.WRAP, A.REFLECT), (A.REMOVE, A.WRAP), (A.REFLECT, A.REMOVE)):
+                h = build_desc(size=(X, Y, Z), eltype=A.F32, out_eltype=A.F32, offsets=offs, radius=R, boundary=(bc0, bc1, A.USE),
+                               reducer=red, src_off=(0, 0, G), dst_off=(0, 0, G), src_ext=parent.shape, dst_ext=parent.shape,
+                               region=region, alpha=0.1, padval=-2.5)
+                want = orc.gather(h, parent, dst_like(h, 9))
+                got, _ = gpu_gather(h, parent, dst_like(h, 9))
+                bits_equal(got, want)
+                assert l.sb200_last_kernel() == b"gather_stream3d_kernel"
+
+
 @pytest.mark.parametrize("dt", [np.uint8, np.bool_])
 def test_life_two_generations_per_launch(orc, dt):
     """SB200_FLAG_DOUBLE_STEP (csrc/life.cu: life_tma2_kernel): dest = step(step(src)) against two oracle sweeps, and
