@@ -25,7 +25,7 @@
 namespace sb {
 
 constexpr int GS_WARPS = 8;                   // consumer warps
-constexpr int GS_PW = 4;                      // producer warps (cp.async mode: stage i belongs to warp i % GS_PW; bulk mode: warp 0)
+constexpr int GS_PW = 1;                      // producer warps (more did not help the cp.async mode and cost the bulk mode 4 %)
 constexpr int GS_BXB = GS_WARPS * 512;        // strip width in bytes
 constexpr int GS_LEFT = 128;                  // margin: global and shared addresses of the main copy agree mod 128
 constexpr int GS_STAGE = GS_LEFT + GS_BXB + 128;

@@ -225,6 +225,12 @@ class SlabIterator:
             self.compute(self._desc(lo_plane, hi_plane, mirror), self.bufs[self.cur], self.bufs[1 - self.cur])
             self.launches += 1
 
+    def close(self):
+        """Release the peer-memory mailbox (IPC mappings + the device allocation)."""
+        if self.mailbox is not None:
+            self.mailbox.close()
+            self.mailbox = None
+
     @property
     def state(self):
         """The owned planes of the current state (torch tensor view, split axis first)."""
@@ -407,10 +413,13 @@ def bench_weak(workload, spec, steps, warmup, synth=None):
     dist.barrier()
     ms = e0.elapsed_time(e1)
     launches = lib.sb200_launch_count(1)
+    exchange, fused = it.exchange, it.fused
+    dist.barrier()
+    it.close()
     how = {"p2p": ("peer-memory stores over NVLink fused into the boundary sweeps (sb200_desc.mirror_*, sb200_signal_flag)"
-                   if it.fused else "peer-memory stores over NVLink (sb200_push_planes + release/acquire flags)") +
+                   if fused else "peer-memory stores over NVLink (sb200_push_planes + release/acquire flags)") +
                   ", acquire wait + ghost copy on a side stream",
-           "nccl": "NCCL send/recv on a side stream"}[it.exchange]
+           "nccl": "NCCL send/recv on a side stream"}[exchange]
     cfg = {"ghost_planes": ghost, "steps_per_exchange": ghost // R, "exchange": how + ", overlapped with the interior "
            "update of the last step of each cycle", "global_grid": list(shape[:-1]) + [shape[-1] * world]}
     return ms, cells_local * world, launches, kernel, cfg
