@@ -545,7 +545,7 @@ int32_t sb200_iterate(const sb200_desc* d, void* buf_a, void* buf_b, int32_t nst
     // Life: two generations per launch where the kernel supports it (half the HBM traffic per generation). The number
     // of single-generation launches in front is chosen so that the final buffer is the one the contract names.
     int singles = nsteps;
-    if (d->reducer == SB200_LIFE && nsteps >= 4 && !halo && !(d->flags & SB200_FLAG_DOUBLE_STEP)) {
+    if (d->reducer == SB200_LIFE && nsteps >= 4 && !halo && !(d->flags & SB200_FLAG_DOUBLE_STEP) && !getenv("SB200_NO_DOUBLE_STEP")) {
         Plan* pl = nullptr;
         sb200_desc probe = *d;
         probe.flags |= SB200_FLAG_DOUBLE_STEP;

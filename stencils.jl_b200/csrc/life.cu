@@ -446,7 +446,7 @@ constexpr int LT2_OUTB = LT2_WARPS * 480;      // final cells per strip row
 constexpr int LT2_D0 = 96;                     // data start inside a shared-memory row: global x0-32 is 96 mod 128
 constexpr int LT2_ROWB = 4096;                 // 96 + 32 + 3840 + 32 = 4000, padded
 constexpr int LT2_CH = 6;
-constexpr int LT2_STAGES = 4;
+constexpr int LT2_STAGES = 3;
 constexpr int LT2_SMEM = 128 + LT2_STAGES * LT2_CH * LT2_ROWB;
 
 __device__ __forceinline__ Row row_of_words(unsigned w0, unsigned w1, unsigned w2, unsigned w3, unsigned bl, unsigned br) {
@@ -460,7 +460,7 @@ __device__ __forceinline__ Row row_of_words(unsigned w0, unsigned w1, unsigned w
 }
 
 template <bool CELLS01, bool CONWAY>
-__global__ void __launch_bounds__((LT2_WARPS + 1) * 32, 2) life_tma2_kernel(const LifeTmaParams q) {
+__global__ void __launch_bounds__((LT2_WARPS + 1) * 32, 3) life_tma2_kernel(const LifeTmaParams q) {
     extern __shared__ __align__(128) uint8_t smem[];
     const LifeParams& p = q.lp;
     uint64_t* full = reinterpret_cast<uint64_t*>(smem);
