@@ -29,7 +29,7 @@ constexpr int GS_PW = 1;                      // producer warps (more did not he
 constexpr int GS_BXB = GS_WARPS * 512;        // strip width in bytes
 constexpr int GS_LEFT = 128;                  // margin: global and shared addresses of the main copy agree mod 128
 constexpr int GS_STAGE = GS_LEFT + GS_BXB + 128;
-constexpr int GS_NS = 20;                     // ring slots: 2R+1 resident columns + prefetch
+constexpr int GS_NS = 13;                     // ring slots: 2R+1 resident columns + prefetch (three CTAs per SM)
 constexpr int GS_HDR = 512;                   // mbarriers
 constexpr int GS_TAB = 256;                   // taps
 constexpr int GS_SMEM = GS_HDR + GS_TAB * 16 + GS_NS * GS_STAGE;
@@ -76,7 +76,7 @@ template <typename T, int RED> __device__ __forceinline__ T gs_first(T v, T w) {
 }
 
 template <typename T, int RED>
-__global__ void __launch_bounds__((GS_WARPS + GS_PW) * 32, 2) gather_stream_kernel(const __grid_constant__ GsParams<T> p) {
+__global__ void __launch_bounds__((GS_WARPS + GS_PW) * 32, 3) gather_stream_kernel(const __grid_constant__ GsParams<T> p) {
     constexpr int VX = 16 / (int)sizeof(T);
     constexpr int EW = 512 / (int)sizeof(T);   // elements per warp
     extern __shared__ __align__(128) unsigned char smem[];
