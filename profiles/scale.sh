@@ -4,7 +4,7 @@
 R=${1:-r01}
 mkdir -p gpurun_out
 port=29600
-for wl in life diffusion; do
+for wl in ${WORKLOADS:-life diffusion}; do
   steps=1000; [ $wl = diffusion ] && steps=100
   for n in 1 2 4 8; do
     port=$((port+1))
