@@ -553,15 +553,63 @@ int32_t sb200_iterate(const sb200_desc* d, void* buf_a, void* buf_b, int32_t nst
             for (singles = nsteps & 1; singles < nsteps; singles += 2)
                 if (((singles + (nsteps - singles) / 2) & 1) == (nsteps & 1)) break;
     }
-    int done = 0;
-    for (int i = 0; done < nsteps; i++) {
+    // One launch of the loop body: [ring refresh] + sweep s -> t (one or two generations).
+    auto body = [&](int i, bool dbl, void* from, void* to) -> int {
         int rc;
-        const bool dbl = done >= singles;
-        if (halo && (rc = sb200_update_halo(d, s, stream))) return rc;
+        if (halo && (rc = sb200_update_halo(d, from, stream))) return rc;
         sb200_desc cur = i == 0 ? *d : later;
         if (dbl) cur.flags |= SB200_FLAG_DOUBLE_STEP;
-        if ((rc = do_gather(&cur, s, t, (cudaStream_t)stream))) return rc;
-        done += dbl ? 2 : 1;
+        return do_gather(&cur, from, to, (cudaStream_t)stream);
+    };
+    int done = 0, i = 0;
+    // Small grids are launch-bound (a 1000 x 1000 sweep takes ~3 us of GPU time): once the plans exist, the steady part of
+    // the loop is captured ONCE as a CUDA graph of GRAPH_CHUNK launches and replayed, so the per-launch CPU + driver cost
+    // is paid per chunk. Capture needs a real stream (not the legacy default stream) and an even chunk (same buffer roles).
+    long long cells = 1;
+    for (int a = 0; a < d->ndim; a++) cells *= d->size[a];
+    constexpr int GRAPH_CHUNK = 32;
+    bool want_graph = stream != nullptr && cells <= (4LL << 20) && !getenv("SB200_NO_GRAPH");
+    bool warm[2] = {false, false};   // a direct launch with the steady-state descriptor has created this mode's plan
+    for (; done < nsteps; i++) {
+        const bool dbl = done >= singles;
+        const int per = dbl ? 2 : 1;
+        const int left_launches = (nsteps - done) / per;
+        if (want_graph && warm[dbl] && left_launches >= 2 * GRAPH_CHUNK && (dbl || singles == nsteps)) {
+            cudaStream_t cs = (cudaStream_t)stream;
+            cudaGraph_t graph = nullptr;
+            cudaGraphExec_t exec = nullptr;
+            bool ok = cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+            int rc = SB200_OK;
+            if (ok) {
+                void *cs_ = s, *ct_ = t;
+                for (int j = 0; j < GRAPH_CHUNK && rc == SB200_OK; j++) {
+                    rc = body(i + j, dbl, cs_, ct_);
+                    void* tmp = cs_; cs_ = ct_; ct_ = tmp;
+                }
+                ok = cudaStreamEndCapture(cs, &graph) == cudaSuccess && rc == SB200_OK && graph != nullptr;
+            }
+            if (ok) ok = cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess;
+            if (ok) {
+                const int chunks = left_launches / GRAPH_CHUNK;
+                for (int c = 0; c < chunks && ok; c++) ok = cudaGraphLaunch(exec, cs) == cudaSuccess;
+                if (ok) {
+                    done += chunks * GRAPH_CHUNK * per;
+                    i += chunks * GRAPH_CHUNK - 1;      // the buffer roles are unchanged after an even number of launches
+                    count_launch(chunks * GRAPH_CHUNK - GRAPH_CHUNK);  // the captured launches were counted once already
+                }
+            }
+            if (exec) cudaGraphExecDestroy(exec);
+            if (graph) cudaGraphDestroy(graph);
+            if (ok) continue;
+            cudaGetLastError();   // capture unavailable (e.g. an enclosing capture): plain launches from here on
+            i--;                   // nothing was enqueued: redo this iteration without the graph
+            want_graph = false;
+            continue;
+        }
+        int rc;
+        if ((rc = body(i, dbl, s, t))) return rc;
+        if (i >= 1) warm[dbl] = true;
+        done += per;
         void* tmp = s; s = t; t = tmp;
     }
     return SB200_OK;

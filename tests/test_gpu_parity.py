@@ -545,3 +545,31 @@ def test_life_two_generations_per_launch(orc, dt):
                       flags=A.FLAG_DOUBLE_STEP)
     t = to_dev(np.zeros((512, 40), dtype=np.uint8, order="F"))
     assert l.sb200_gather(hbad.ptr(), t.data_ptr(), to_dev(np.zeros((512, 40), dtype=np.uint8, order="F")).data_ptr(), None) == A.EUNSUPPORTED
+
+
+def test_iterate_small_grids_replay_a_cuda_graph(orc):
+    """sb200_iterate on launch-bound grids captures 32 launches as a CUDA graph and replays it; results and the launch
+    count are those of the plain loop (Life with two generations per launch, Life single, diffusion with a ring)."""
+    import torch
+    from tests.util import to_dev, to_host
+    rng = np.random.default_rng(71)
+    l = A.lib()
+    st = torch.cuda.Stream()
+    cases = []
+    g = np.asfortranarray((rng.random((1024, 96)) < 0.4).astype(np.uint8))
+    moore = npr.offsets("Moore", 1, 2)
+    cases.append((g, build_desc(size=g.shape, eltype=A.U8, out_eltype=A.U8, offsets=moore, radius=1, boundary=A.WRAP, reducer=A.LIFE), 331))
+    cases.append((g, build_desc(size=g.shape, eltype=A.U8, out_eltype=A.U8, offsets=moore, radius=1, boundary=A.REFLECT, reducer=A.LIFE), 150))
+    f = rand_array(rng, (256, 64), np.float32)
+    cases.append((f, build_desc(size=f.shape, eltype=A.F32, out_eltype=A.F32, offsets=npr.offsets("VonNeumann", 1, 2), radius=1,
+                                boundary=A.WRAP, reducer=A.DIFFUSION, alpha=0.1), 200))
+    for a0, h, n in cases:
+        want = orc.iterate(h, a0.copy(order="F"), np.zeros_like(a0, order="F"), n)
+        ta, tb = to_dev(a0), to_dev(np.zeros_like(a0, order="F"))
+        l.sb200_launch_count(1)
+        with torch.cuda.stream(st):
+            A.check(l.sb200_iterate(h.ptr(), ta.data_ptr(), tb.data_ptr(), n, st.cuda_stream))
+        st.synchronize()
+        launches = l.sb200_launch_count(1)
+        bits_equal(to_host(ta if n % 2 == 0 else tb, a0.shape, a0.dtype), want)
+        assert n // 2 <= launches <= n
