@@ -167,6 +167,8 @@ typedef struct sb200_desc {
 #define SB200_FLAG_ZERO_DEST 2     /* scatter: treat dest as zero-filled (Switching forms, src/scatterstencil.jl:119,130) */
 #define SB200_FLAG_NO_TMA 4        /* testing: use the non-TMA variant of a specialised kernel */
 #define SB200_FLAG_CELLS_01 8      /* LIFE on UInt8: the caller guarantees every source cell is 0 or 1 */
+#define SB200_FLAG_QUAD_STEP 32   /* dest = f(f(f(f(src)))): four generations per launch (B3/S23 Life, axis 0 a multiple of 32
+                                     cells, otherwise as SB200_FLAG_DOUBLE_STEP); the bit-sliced kernel */
 #define SB200_FLAG_DOUBLE_STEP 16 /* dest = f(f(src)): two sweeps fused in one launch, the intermediate state never touches
                                      memory (LIFE, Moore(1), unpadded, Wrap on axis 0; else SB200_EUNSUPPORTED).
                                      sb200_iterate uses it by itself where it applies. */

@@ -299,6 +299,10 @@ static int do_gather(const sb200_desc* d, const void* src, void* dst, cudaStream
     Plan* pl = nullptr;
     int rc = get_plan(d, PK_GATHER, &pl);
     if (rc) return rc;
+    if ((d->flags & SB200_FLAG_QUAD_STEP) && ((d->flags & SB200_FLAG_DOUBLE_STEP) || !life_multi_accepts(*d, *pl, 4))) {
+        set_error("SB200_FLAG_QUAD_STEP: only B3/S23 Life / Moore(1) on an unpadded Bool or UInt8 grid, Wrap on axis 0, width % 32 == 0");
+        return SB200_EUNSUPPORTED;
+    }
     if ((d->flags & SB200_FLAG_DOUBLE_STEP) && !life2_accepts(*d, *pl)) {
         set_error("SB200_FLAG_DOUBLE_STEP: only Life / Moore(1) on an unpadded Bool or UInt8 grid with Wrap on axis 0");
         return SB200_EUNSUPPORTED;
@@ -544,21 +548,37 @@ int32_t sb200_iterate(const sb200_desc* d, void* buf_a, void* buf_b, int32_t nst
     if (d->reducer == SB200_LIFE && d->eltype == SB200_U8) later.flags |= SB200_FLAG_CELLS_01;
     // Life: two generations per launch where the kernel supports it (half the HBM traffic per generation). The number
     // of single-generation launches in front is chosen so that the final buffer is the one the contract names.
-    int singles = nsteps;
-    if (d->reducer == SB200_LIFE && nsteps >= 4 && !halo && !(d->flags & SB200_FLAG_DOUBLE_STEP) && !getenv("SB200_NO_DOUBLE_STEP")) {
+    int singles = nsteps, doubles = 0;   // launches of 1 and 2 generations in front; the rest of the run is 4 (or 2) per launch
+    int steady = 1;
+    if (d->reducer == SB200_LIFE && nsteps >= 4 && !halo && !(d->flags & (SB200_FLAG_DOUBLE_STEP | SB200_FLAG_QUAD_STEP)) &&
+        !getenv("SB200_NO_DOUBLE_STEP")) {
         Plan* pl = nullptr;
         sb200_desc probe = *d;
         probe.flags |= SB200_FLAG_DOUBLE_STEP;
-        if (get_plan(&probe, PK_GATHER, &pl) == SB200_OK && life2_accepts(probe, *pl))
-            for (singles = nsteps & 1; singles < nsteps; singles += 2)
-                if (((singles + (nsteps - singles) / 2) & 1) == (nsteps & 1)) break;
+        if (get_plan(&probe, PK_GATHER, &pl) == SB200_OK && life2_accepts(probe, *pl)) {
+            steady = 2;
+            probe.flags = d->flags | SB200_FLAG_QUAD_STEP;
+            Plan* pl4 = nullptr;
+            if (nsteps >= 16 && get_plan(&probe, PK_GATHER, &pl4) == SB200_OK && life_multi_accepts(probe, *pl4, 4) && !getenv("SB200_NO_QUAD_STEP"))
+                steady = 4;
+            // fewest launches in front such that the rest divides by `steady` and the launch count has the parity of nsteps
+            bool found = false;
+            for (int tot = 0; tot <= 8 && !found; tot++)
+                for (int dd2 = steady == 4 ? tot : 0; dd2 >= 0 && !found; dd2--) {
+                    const int ss = tot - dd2, rest = nsteps - ss - 2 * dd2;
+                    if (rest < 0 || rest % steady) continue;
+                    if (((ss + dd2 + rest / steady) & 1) == (nsteps & 1)) { singles = ss; doubles = dd2; found = true; }
+                }
+            if (!found) { singles = nsteps; doubles = 0; steady = 1; }
+        }
     }
     // One launch of the loop body: [ring refresh] + sweep s -> t (one or two generations).
-    auto body = [&](int i, bool dbl, void* from, void* to) -> int {
+    auto body = [&](int i, int gens, void* from, void* to) -> int {
         int rc;
         if (halo && (rc = sb200_update_halo(d, from, stream))) return rc;
         sb200_desc cur = i == 0 ? *d : later;
-        if (dbl) cur.flags |= SB200_FLAG_DOUBLE_STEP;
+        if (gens == 2) cur.flags |= SB200_FLAG_DOUBLE_STEP;
+        if (gens == 4) cur.flags |= SB200_FLAG_QUAD_STEP;
         return do_gather(&cur, from, to, (cudaStream_t)stream);
     };
     int done = 0, i = 0;
@@ -569,12 +589,12 @@ int32_t sb200_iterate(const sb200_desc* d, void* buf_a, void* buf_b, int32_t nst
     for (int a = 0; a < d->ndim; a++) cells *= d->size[a];
     constexpr int GRAPH_CHUNK = 32;
     bool want_graph = stream != nullptr && cells <= (4LL << 20) && !getenv("SB200_NO_GRAPH");
-    bool warm[2] = {false, false};   // a direct launch with the steady-state descriptor has created this mode's plan
+    bool warm[5] = {false, false, false, false, false};   // a direct launch with the steady-state descriptor has created this mode's plan
     for (; done < nsteps; i++) {
-        const bool dbl = done >= singles;
-        const int per = dbl ? 2 : 1;
+        const int per = steady == 1 ? 1 : (i < singles ? 1 : (i < singles + doubles ? 2 : steady));
+        const bool in_steady = steady == 1 || i >= singles + doubles;
         const int left_launches = (nsteps - done) / per;
-        if (want_graph && warm[dbl] && left_launches >= 2 * GRAPH_CHUNK && (dbl || singles == nsteps)) {
+        if (want_graph && warm[per] && in_steady && left_launches >= 2 * GRAPH_CHUNK) {
             cudaStream_t cs = (cudaStream_t)stream;
             cudaGraph_t graph = nullptr;
             cudaGraphExec_t exec = nullptr;
@@ -583,7 +603,7 @@ int32_t sb200_iterate(const sb200_desc* d, void* buf_a, void* buf_b, int32_t nst
             if (ok) {
                 void *cs_ = s, *ct_ = t;
                 for (int j = 0; j < GRAPH_CHUNK && rc == SB200_OK; j++) {
-                    rc = body(i + j, dbl, cs_, ct_);
+                    rc = body(i + j, per, cs_, ct_);
                     void* tmp = cs_; cs_ = ct_; ct_ = tmp;
                 }
                 ok = cudaStreamEndCapture(cs, &graph) == cudaSuccess && rc == SB200_OK && graph != nullptr;
@@ -607,8 +627,8 @@ int32_t sb200_iterate(const sb200_desc* d, void* buf_a, void* buf_b, int32_t nst
             continue;
         }
         int rc;
-        if ((rc = body(i, dbl, s, t))) return rc;
-        if (i >= 1) warm[dbl] = true;
+        if ((rc = body(i, per, s, t))) return rc;
+        if (i >= 1) warm[per] = true;
         done += per;
         void* tmp = s; s = t; t = tmp;
     }

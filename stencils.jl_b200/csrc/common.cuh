@@ -172,6 +172,7 @@ int launch_generic_scatter_rect(const Plan& pl, const void* src, void* dst, cuda
 // Specialised kernels return SB200_OK when they handled the sweep, -1 when the plan is not theirs.
 int try_life_swar(const Plan& pl, const void* src, void* dst, cudaStream_t st);
 bool life2_accepts(const sb200_desc& d, const Plan& pl);  // SB200_FLAG_DOUBLE_STEP
+bool life_multi_accepts(const sb200_desc& d, const Plan& pl, int gens);  // gens = 2 (DOUBLE_STEP) or 4 (QUAD_STEP)
 int try_tile2d(const Plan& pl, const void* src, void* dst, cudaStream_t st);
 int try_diffusion3d(const Plan& pl, const void* src, void* dst, cudaStream_t st);
 int try_gather_stream(const Plan& pl, const void* src, void* dst, cudaStream_t st);

@@ -15,6 +15,7 @@
 // (src_off > 0) on axis 1; axis 0 must be unpadded with 16-byte-aligned rows. Everything else is declined
 // and goes to gather_generic.
 #include <algorithm>
+#include <cstdlib>
 #include "common.cuh"
 #include "tma.cuh"
 
@@ -580,8 +581,217 @@ __global__ void __launch_bounds__((LT2_WARPS + 1) * 32, 3) life_tma2_kernel(cons
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Bit-sliced Conway kernel: G generations per launch with the cells of a row packed ONE BIT each inside the kernel.
+// Memory keeps the reference's one byte per cell; a lane loads 32 cells (two 128-bit shared-memory loads), packs them
+// into one 32-bit word with four multiplies (w * 0x10204080 gathers the four 0/1 bytes of a word into its top nibble),
+// and every logic instruction then advances 32 cells: the horizontal 3-sum of a row is two LOP3 (xor3, majority) on the
+// word and its two one-bit shifts, the 3-row total a 4-bit carry-save sum (8 LOP3/LOP), B3/S23 four more — about 20
+// instructions per 32 cells and generation against ~18 per FOUR cells in the byte-SWAR kernels. The shifted-in edge bits
+// of an intermediate generation come from the adjacent lanes by warp shuffle, so lanes G-1 .. 32-G of a warp own final
+// cells (warps overlap by 2(G-1) lanes). Same TMA ring, same boundary support as life_tma2_kernel; B3/S23 only.
+constexpr int LB_WARPS = 6;
+constexpr int LB_CH = 3;
+constexpr int LB_STAGES = 4;
+constexpr int LB_ROWB = 6144;
+constexpr int LB_SMEM = 128 + LB_STAGES * LB_CH * LB_ROWB;
+template <int G> struct LbCfg {
+    static constexpr int VALID = 32 - 2 * (G - 1);           // lanes of a warp that own final cells
+    static constexpr int WO = VALID * 32;                     // final cells per warp row
+    static constexpr int CAP = LB_WARPS * WO;                 // final cells per strip row (multiple of 128)
+    static constexpr int HL = (G - 1) * 32 + 16;              // halo bytes per side of a shared-memory row
+    static constexpr int D0 = (128 - HL % 128) % 128;         // data start in a row: global x0 - HL is D0 mod 128
+    static_assert(D0 + 2 * HL + CAP <= LB_ROWB, "row does not fit");
+};
+
+struct BRow { unsigned c, s0, s1; };  // 32 cells, and their horizontal 3-sums (left + centre + right) as two bit planes
+
+__device__ __forceinline__ unsigned lop3_xor3(unsigned a, unsigned b, unsigned c) {
+    unsigned r;
+    asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
+__device__ __forceinline__ unsigned lop3_maj(unsigned a, unsigned b, unsigned c) {
+    unsigned r;
+    asm("lop3.b32 %0, %1, %2, %3, 0xE8;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
+__device__ __forceinline__ BRow brow(unsigned w, unsigned lbit, unsigned rbit) {
+    const unsigned L = (w << 1) | lbit, R = (w >> 1) | (rbit << 31);
+    return BRow{w, lop3_xor3(L, w, R), lop3_maj(L, w, R)};
+}
+// B3/S23 from the rows above, at and below: T = 3x3 total including the centre; alive' = (T == 3) | (centre & T == 4)
+__device__ __forceinline__ unsigned conway_bits(const BRow& a, const BRow& b, const BRow& n) {
+    const unsigned t0 = lop3_xor3(a.s0, b.s0, n.s0), c0 = lop3_maj(a.s0, b.s0, n.s0);
+    const unsigned u1 = lop3_xor3(a.s1, b.s1, n.s1), c1 = lop3_maj(a.s1, b.s1, n.s1);
+    const unsigned t1 = u1 ^ c0, k1 = u1 & c0;
+    const unsigned t2 = c1 ^ k1, t3 = c1 & k1;
+    const unsigned x = ~t2 & t1 & t0, y = t2 & ~t1 & ~t0;
+    return (x | (y & b.c)) & ~t3;
+}
+template <bool CELLS01> __device__ __forceinline__ unsigned pack32(const uint4& lo, const uint4& hi) {
+    unsigned w[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+    unsigned acc = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const unsigned v = CELLS01 ? w[k] : nz_bytes(w[k]);
+        acc = (acc >> 4) | ((v * 0x10204080u) & 0xF0000000u);
+    }
+    return acc;
+}
+__device__ __forceinline__ unsigned unpack4(unsigned bits, int k) {  // cells 4k .. 4k+3 as four 0/1 bytes
+    return (((bits >> (4 * k)) & 0xFu) * 0x00204081u) & 0x01010101u;
+}
+
+template <int G, bool CELLS01>
+__global__ void __launch_bounds__((LB_WARPS + 1) * 32, 3) life_bit_kernel(const LifeTmaParams q) {
+    using C = LbCfg<G>;
+    extern __shared__ __align__(128) uint8_t smem[];
+    const LifeParams& p = q.lp;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem);
+    uint64_t* empty = full + LB_STAGES;
+    uint8_t* ring = smem + 128;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < LB_STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], LB_WARPS); }
+        mbar_fence_init();
+    }
+    __syncthreads();
+    const int ntasks = q.nstrips * q.nruns;
+    unsigned k = 0;
+    for (int task = blockIdx.x; task < ntasks; task += gridDim.x) {
+        const int strip = task % q.nstrips, run = task / q.nstrips;
+        const int x0 = strip * q.outb;
+        const int wout = min(q.outb, p.W - x0);
+        const int y0 = p.y_lo + (int)((long long)p.rows * run / q.nruns);
+        const int y1 = p.y_lo + (int)((long long)p.rows * (run + 1) / q.nruns);
+        const int nsrc = y1 - y0 + 2 * G;  // source rows y0-G .. y1+G-1
+        const int nchunks = (nsrc + LB_CH - 1) / LB_CH;
+        if (warp == LB_WARPS) {
+            // ---------------- producer: shared-memory row byte b <-> global column x0 - HL + b (mod W) ----------------
+            if (lane == 0) {
+                const int lin = x0 >= C::HL ? C::HL : 0;
+                const int rin = min(C::HL, p.W - (x0 + wout));
+                const unsigned mlen = lin + wout + rin;
+                const unsigned rowbytes = 2 * C::HL + wout;
+                for (int c = 0; c < nchunks; c++, k++) {
+                    const int slot = k % LB_STAGES;
+                    mbar_wait(&empty[slot], ((k / LB_STAGES) & 1) ^ 1);
+                    uint8_t* sbase = ring + slot * (LB_CH * LB_ROWB);
+                    const int nrows = min(LB_CH, nsrc - c * LB_CH);
+                    mbar_arrive_expect_tx(&full[slot], nrows * rowbytes);
+                    for (int j = 0; j < nrows; j++) {
+                        const uint8_t* g = p.src + life_map_row(p, y0 - G + c * LB_CH + j) * p.spitch;
+                        uint8_t* srow = sbase + j * LB_ROWB + C::D0;
+                        bulk_g2s(srow + C::HL - lin, g + x0 - lin, mlen, &full[slot]);
+                        if (!lin) bulk_g2s(srow, g + p.W - C::HL, C::HL, &full[slot]);                           // wrapped left halo
+                        if (rin < C::HL) bulk_g2s(srow + C::HL + wout + rin, g, C::HL - rin, &full[slot]);        // wrapped right halo
+                    }
+                }
+            } else {
+                k += nchunks;
+            }
+            continue;
+        }
+        // ---------------- consumers ----------------
+        if (warp * C::WO >= wout) {   // no final cell in this warp: keep the ring protocol only
+            for (int c = 0; c < nchunks; c++, k++) {
+                const int slot = k % LB_STAGES;
+                mbar_wait(&full[slot], (k / LB_STAGES) & 1);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty[slot]);
+            }
+            continue;
+        }
+        const int cell0 = warp * C::WO + (lane - (G - 1)) * 32;   // first final cell of this lane inside the strip
+        const bool active = lane >= G - 1 && lane <= 32 - G && cell0 < wout;
+        const unsigned act_mask = __ballot_sync(0xffffffffu, active);
+        // destination of the cells of lane 0 (a halo lane: never stored) in output row y0
+        uint8_t* __restrict__ wp = p.dst + (long long)(y0 + p.doff1) * p.dpitch + x0 + warp * C::WO - (G - 1) * 32;
+        const int soff = C::D0 + C::HL + cell0;
+        BRow lv[G][3];
+#pragma unroll
+        for (int a = 0; a < G; a++)
+#pragma unroll
+            for (int b = 0; b < 3; b++) lv[a][b] = BRow{0, 0, 0};
+        for (int c = 0; c < nchunks; c++, k++) {
+            const int slot = k % LB_STAGES;
+            mbar_wait(&full[slot], (k / LB_STAGES) & 1);
+            const uint8_t* sbase = ring + slot * (LB_CH * LB_ROWB);
+#pragma unroll
+            for (int J = 0; J < LB_CH; J++) {      // stream index i = c * LB_CH + J, i % 3 == J
+                const int i = c * LB_CH + J;
+                {   // level 0: pack the source row
+                    const uint8_t* t = sbase + J * LB_ROWB + soff;
+                    const uint4 lo = *reinterpret_cast<const uint4*>(t), hi = *reinterpret_cast<const uint4*>(t + 16);
+                    const unsigned w = pack32<CELLS01>(lo, hi);
+                    // edge bits from the adjacent lanes' packed words; only the warp's end lanes read a halo byte
+                    unsigned lb = __shfl_up_sync(0xffffffffu, w, 1) >> 31, rb = __shfl_down_sync(0xffffffffu, w, 1) & 1u;
+                    if (lane == 0) lb = t[-1] != 0;
+                    if (lane == 31) rb = t[32] != 0;
+                    lv[0][J] = brow(w, lb, rb);
+                }
+#pragma unroll
+                for (int g = 1; g < G; g++) {  // generation g of row i - g from generation g-1 of rows i-g-1, i-g, i-g+1
+                    const unsigned x = conway_bits(lv[g - 1][(J - g - 1 + 9) % 3], lv[g - 1][(J - g + 9) % 3], lv[g - 1][(J - g + 1 + 9) % 3]);
+                    const unsigned lb = __shfl_up_sync(0xffffffffu, x, 1) >> 31, rb = __shfl_down_sync(0xffffffffu, x, 1) & 1u;
+                    lv[g][(J - g + 9) % 3] = brow(x, lb, rb);
+                }
+                if (i >= 2 * G && i < nsrc) {   // generation G of row i - G: the output row y0 + i - 2G
+                    const unsigned y = conway_bits(lv[G - 1][(J - G - 1 + 9) % 3], lv[G - 1][(J - G + 9) % 3], lv[G - 1][(J - G + 1 + 9) % 3]);
+                    // two fully coalesced 512-byte stores per warp row: lane l writes 16 bytes at 16 l of the first / second
+                    // half of the warp's 1 KiB, i.e. half (l & 1) of the cells of lane l/2 resp. 16 + l/2
+#pragma unroll
+                    for (int hb = 0; hb < 2; hb++) {
+                        const int sl = hb * 16 + (lane >> 1);
+                        const unsigned h16 = __shfl_sync(0xffffffffu, y, sl) >> (16 * (lane & 1));
+                        if ((act_mask >> sl) & 1u)
+                            *reinterpret_cast<uint4*>(wp + hb * 512 + lane * 16) =
+                                make_uint4(unpack4(h16, 0), unpack4(h16, 1), unpack4(h16, 2), unpack4(h16, 3));
+                    }
+                    wp += p.dpitch;
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[slot]);
+        }
+    }
+}
+
+template <int G, bool CELLS01> static int launch_bit(const LifeParams& p, cudaStream_t st) {
+    using C = LbCfg<G>;
+    static thread_local int cfg_dev = -1, ctas_per_sm = 0;
+    int dev = 0;
+    SB_CUDA(cudaGetDevice(&dev));
+    if (dev != cfg_dev) {
+        SB_CUDA(cudaFuncSetAttribute(life_bit_kernel<G, CELLS01>, cudaFuncAttributeMaxDynamicSharedMemorySize, LB_SMEM));
+        int per_sm = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, life_bit_kernel<G, CELLS01>, (LB_WARPS + 1) * 32, LB_SMEM) != cudaSuccess || per_sm < 1)
+            per_sm = 1;
+        ctas_per_sm = per_sm;
+        cfg_dev = dev;
+    }
+    LifeTmaParams q;
+    q.lp = p;
+    q.nstrips = (p.W + C::CAP - 1) / C::CAP;
+    q.outb = std::min(C::CAP, ((p.W + q.nstrips - 1) / q.nstrips + 127) / 128 * 128);  // equal strips
+    q.nstrips = (p.W + q.outb - 1) / q.outb;
+    const long long ctas = (long long)ctas_per_sm * num_sms();
+    const int tpc = getenv("SB200_LB_TASKS") ? atoi(getenv("SB200_LB_TASKS")) : 2;
+    long long nruns = std::max<long long>(1, tpc * ctas / q.nstrips);
+    nruns = std::min<long long>(nruns, std::max(1, p.rows / (16 * G)));  // at least 16 G rows per run (2 G are re-read)
+    q.nruns = (int)nruns;
+    const long long grid = std::min<long long>(ctas, (long long)q.nstrips * q.nruns);
+    life_bit_kernel<G, CELLS01><<<(unsigned)grid, (LB_WARPS + 1) * 32, LB_SMEM, st>>>(q);
+    return SB200_OK;
+}
+
 // Can this sweep run two generations per launch?
-bool life2_accepts(const sb200_desc& d, const Plan& pl) {
+bool life2_accepts(const sb200_desc& d, const Plan& pl) { return life_multi_accepts(d, pl, 2); }
+
+bool life_multi_accepts(const sb200_desc& d, const Plan& pl, int gens) {
+    if (gens == 4 && (d.born_mask != (1u << 3) || d.survive_mask != ((1u << 2) | (1u << 3)) || d.size[0] % 32 || getenv("SB200_NO_BITSLICE")))
+        return false;   // four generations: the bit-sliced B3/S23 kernel only
     if (d.reducer != SB200_LIFE || d.ndim != 2 || (d.eltype != SB200_BOOL && d.eltype != SB200_U8)) return false;
     if (pl.shape_tag != SB200_MOORE || pl.shape_ndim != 2 || d.radius != 1 || d.noffsets != 8) return false;
     if (d.flags & (SB200_FLAG_NO_TMA | SB200_FLAG_FORCE_GENERIC)) return false;
@@ -591,9 +801,9 @@ bool life2_accepts(const sb200_desc& d, const Plan& pl) {
     if (d.boundary[0] != SB200_WRAP) return false;
     if (pl.dd.lo[0] != 0 || pl.dd.n[0] != d.size[0] || pl.dd.n[1] < 16) return false;
     const long long lo = pl.dd.lo[1], hi = lo + pl.dd.n[1];
-    const bool inside = lo >= 2 && hi + 2 <= d.size[1];  // never leaves the parent: the boundary rule of axis 1 is not exercised
+    const bool inside = lo >= gens && hi + gens <= d.size[1];  // never leaves the parent: the boundary rule of axis 1 is not exercised
     if (!inside && d.boundary[1] != SB200_WRAP && d.boundary[1] != SB200_REFLECT) return false;
-    if (d.size[1] < 4) return false;
+    if (d.size[1] < 2 * gens) return false;
     return true;
 }
 
@@ -650,10 +860,27 @@ int try_life_swar(const Plan& pl, const void* src, void* dst, cudaStream_t st) {
     // Bool cells are 0/1 by type; UInt8 cells are 0/1 when the caller says so (sb200_iterate does for every
     // step after the first, because the source is then this kernel's own output).
     const bool cells01 = d.eltype == SB200_BOOL || (d.flags & SB200_FLAG_CELLS_01);
+    if (d.flags & SB200_FLAG_QUAD_STEP) {
+        if (!life_multi_accepts(d, pl, 4)) { set_error("four generations per sweep: layout / boundary / rule not supported"); return SB200_EUNSUPPORTED; }
+        p.mirror = nullptr; p.m_lo = p.m_hi = 0;
+        const int rc = cells01 ? launch_bit<4, true>(p, st) : launch_bit<4, false>(p, st);
+        if (rc) return rc;
+        SB_LAUNCH_CHECK();
+        set_kernel_name(cells01 ? "life_bit_kernel<4,cells01>" : "life_bit_kernel<4,u8>");
+        return SB200_OK;
+    }
     if (d.flags & SB200_FLAG_DOUBLE_STEP) {
         if (!life2_accepts(d, pl)) { set_error("two generations per sweep: layout / boundary not supported"); return SB200_EUNSUPPORTED; }
         p.mirror = nullptr; p.m_lo = p.m_hi = 0;
         int rc;
+        if (conway && p.W % 32 == 0 && !getenv("SB200_NO_BITSLICE")) {
+            // B3/S23: the bit-sliced kernel (one bit per cell inside the kernel)
+            rc = cells01 ? launch_bit<2, true>(p, st) : launch_bit<2, false>(p, st);
+            if (rc) return rc;
+            SB_LAUNCH_CHECK();
+            set_kernel_name(cells01 ? "life_bit_kernel<2,cells01>" : "life_bit_kernel<2,u8>");
+            return SB200_OK;
+        }
         if (cells01) rc = conway ? launch_tma2<true, true>(p, st) : launch_tma2<true, false>(p, st);
         else rc = conway ? launch_tma2<false, true>(p, st) : launch_tma2<false, false>(p, st);
         if (rc) return rc;

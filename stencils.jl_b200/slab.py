@@ -181,6 +181,7 @@ class SlabIterator:
         self._gen = 1
         self.double_ok = (reducer == A.LIFE and t.is_cuda and compute is None and self.bc_split == A.WRAP and self.k >= 2 and
                           self.n_local >= 4 * self.G + 64 and os.environ.get("SB200_DOUBLE_STEP", "1") != "0")
+        self.quad_ok = self.double_ok and self.k >= 4 and os.environ.get("SB200_QUAD_STEP", "1") != "0"
         self._nsweeps = 0
         self._descs = {}
         self.is_cuda = t.is_cuda
@@ -210,7 +211,7 @@ class SlabIterator:
     def _desc(self, lo_plane, hi_plane, mirror=None):
         """descriptor whose output region is parent planes [lo_plane, hi_plane) of the split axis; mirror =
         (peer pointer, first plane, end plane): those planes are also stored into the peer's landing slot by the sweep"""
-        flags = (self._later_flags if self._nsweeps > 0 else 0) | (A.FLAG_DOUBLE_STEP if self._gen == 2 else 0)
+        flags = (self._later_flags if self._nsweeps > 0 else 0) | {1: 0, 2: A.FLAG_DOUBLE_STEP, 4: A.FLAG_QUAD_STEP}[self._gen]
         key = (lo_plane, hi_plane, flags, mirror)
         if key not in self._descs:
             lo = (0,) * (self.nd - 1) + (lo_plane,)
@@ -306,13 +307,17 @@ class SlabIterator:
             if self.steps_since_exchange >= self.k:
                 self._exchange(self.bufs[self.cur])
                 self.steps_since_exchange = 0
-            # Life: two generations per launch (SB200_FLAG_DOUBLE_STEP) while the cycle has room for them
-            m = 2 if (self.double_ok and left >= 2 and self.k - self.steps_since_exchange >= 2) else 1
-            if m == 2:
+            # Life: four / two generations per launch (SB200_FLAG_QUAD_STEP / _DOUBLE_STEP) while the cycle has room
+            room = self.k - self.steps_since_exchange
+            m = 4 if (self.quad_ok and left >= 4 and room >= 4) else (2 if (self.double_ok and left >= 2 and room >= 2) else 1)
+            if m > 1:
                 try:
-                    self._step_one(torch, 2)
-                except A.ArgumentError:   # the library declined this layout: single generations from now on
-                    self.double_ok = False
+                    self._step_one(torch, m)
+                except A.ArgumentError:   # the library declined this layout / rule: fewer generations per launch from now on
+                    if m == 4:
+                        self.quad_ok = False
+                    else:
+                        self.double_ok = False
                     continue
             else:
                 self._step_one(torch, 1)
