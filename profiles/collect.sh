@@ -5,9 +5,10 @@ set -x
 mkdir -p gpurun_out
 R=${1:-r01}
 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/${R}_launches_life.csv \
-    python bench.py --steps 20 --warmup 3 --no-extras > gpurun_out/${R}_launches_life.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:life_tma -s 6 -c 1 -o gpurun_out/${R}_life \
-    python bench.py --steps 10 --warmup 3 --no-extras > /dev/null 2>&1
+    python bench.py --steps 64 --warmup 16 --no-extras > gpurun_out/${R}_launches_life.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:life_bit -s 6 -c 1 -o gpurun_out/${R}_life \
+    python bench.py --steps 64 --warmup 16 --no-extras > /dev/null 2>&1
+[ "$ONLY_LIFE" = 1 ] && exit 0
 for wl in mean kernel circle positional scatter diffusion; do
   ncu --set full --clock-control none --import-source on -k regex:"stream2d|stream3d|scatter_fast|scatter_stream|gather_stream" -s 3 -c 1 -o gpurun_out/${R}_${wl} \
       python bench.py --workload ${wl} --steps 4 --warmup 3 --no-extras > /dev/null 2>&1

@@ -6,7 +6,7 @@ mkdir -p gpurun_out
 port=29600
 for wl in ${WORKLOADS:-life diffusion}; do
   steps=1000; [ $wl = diffusion ] && steps=100
-  for n in 1 2 4 8; do
+  for n in ${NGPUS:-1 2 4 8}; do
     port=$((port+1))
     if [ $n = 1 ]; then
       python bench.py --gpus 1 --workload $wl --steps $steps --warmup 16 --no-extras 2>/dev/null | tail -1 > gpurun_out/scale_${R}_${wl}_$n.json
