@@ -24,6 +24,9 @@ OP_ADD, OP_MAX, OP_MIN = range(3)
 SCATTER_WEIGHTS, SCATTER_CENTER_WEIGHTS = range(2)
 FLAG_FORCE_GENERIC, FLAG_ZERO_DEST, FLAG_NO_TMA, FLAG_CELLS_01, FLAG_DOUBLE_STEP, FLAG_QUAD_STEP = 1, 2, 4, 8, 16, 32
 MAX_OFFSETS = 1024
+# default of SB200_DIFFUSION_DOUBLE_STEP (two diffusion steps per launch in iterated runs); must agree with
+# kDiffusionDoubleStepDefault in csrc/api.cu
+DIFFUSION_DOUBLE_STEP_DEFAULT = "0"
 
 ELTYPE_OF_DTYPE = {
     np.dtype(np.bool_): BOOL, np.dtype(np.uint8): U8, np.dtype(np.int32): I32,

@@ -303,8 +303,9 @@ static int do_gather(const sb200_desc* d, const void* src, void* dst, cudaStream
         set_error("SB200_FLAG_QUAD_STEP: only B3/S23 Life / Moore(1) on an unpadded Bool or UInt8 grid, Wrap on axis 0, width % 32 == 0");
         return SB200_EUNSUPPORTED;
     }
-    if ((d->flags & SB200_FLAG_DOUBLE_STEP) && !life2_accepts(*d, *pl)) {
-        set_error("SB200_FLAG_DOUBLE_STEP: only Life / Moore(1) on an unpadded Bool or UInt8 grid with Wrap on axis 0");
+    if ((d->flags & SB200_FLAG_DOUBLE_STEP) && !life2_accepts(*d, *pl) && !diffusion2_accepts(*d, *pl)) {
+        set_error("SB200_FLAG_DOUBLE_STEP: only Life / Moore(1) on an unpadded Bool or UInt8 grid with Wrap on axis 0, or "
+                  "Diffusion / VonNeumann(1,3) on an unpadded Float32 / Float64 grid with Wrap on axes 0 and 1");
         return SB200_EUNSUPPORTED;
     }
     g_mirror = MirrorReq();
@@ -530,6 +531,9 @@ int32_t sb200_gather_multi(const sb200_term* terms, int32_t nterms, void* dst, v
     return SB200_OK;
 }
 
+// sb200_iterate schedules two diffusion steps per launch by itself when this is true (SB200_DIFFUSION_DOUBLE_STEP overrides).
+static constexpr bool kDiffusionDoubleStepDefault = false;
+
 int32_t sb200_iterate(const sb200_desc* d, void* buf_a, void* buf_b, int32_t nsteps, void* stream) {
     if (nsteps < 0) { set_error("negative step count"); return SB200_EINVAL; }
     if (!d) { set_error("descriptor is NULL"); return SB200_EINVAL; }
@@ -550,16 +554,20 @@ int32_t sb200_iterate(const sb200_desc* d, void* buf_a, void* buf_b, int32_t nst
     // of single-generation launches in front is chosen so that the final buffer is the one the contract names.
     int singles = nsteps, doubles = 0;   // launches of 1 and 2 generations in front; the rest of the run is 4 (or 2) per launch
     int steady = 1;
-    if (d->reducer == SB200_LIFE && nsteps >= 4 && !halo && !(d->flags & (SB200_FLAG_DOUBLE_STEP | SB200_FLAG_QUAD_STEP)) &&
+    const bool life = d->reducer == SB200_LIFE;
+    // Diffusion: two steps per launch (stream3d2.cu). Opt-in until it has been measured: SB200_DIFFUSION_DOUBLE_STEP=1.
+    const char* e_d2 = getenv("SB200_DIFFUSION_DOUBLE_STEP");
+    const bool diff2 = d->reducer == SB200_DIFFUSION && (e_d2 ? atoi(e_d2) != 0 : kDiffusionDoubleStepDefault);
+    if ((life || diff2) && nsteps >= 4 && !halo && !(d->flags & (SB200_FLAG_DOUBLE_STEP | SB200_FLAG_QUAD_STEP)) &&
         !getenv("SB200_NO_DOUBLE_STEP")) {
         Plan* pl = nullptr;
         sb200_desc probe = *d;
         probe.flags |= SB200_FLAG_DOUBLE_STEP;
-        if (get_plan(&probe, PK_GATHER, &pl) == SB200_OK && life2_accepts(probe, *pl)) {
+        if (get_plan(&probe, PK_GATHER, &pl) == SB200_OK && (life ? life2_accepts(probe, *pl) : diffusion2_accepts(probe, *pl))) {
             steady = 2;
             probe.flags = d->flags | SB200_FLAG_QUAD_STEP;
             Plan* pl4 = nullptr;
-            if (nsteps >= 16 && get_plan(&probe, PK_GATHER, &pl4) == SB200_OK && life_multi_accepts(probe, *pl4, 4) && !getenv("SB200_NO_QUAD_STEP"))
+            if (life && nsteps >= 16 && get_plan(&probe, PK_GATHER, &pl4) == SB200_OK && life_multi_accepts(probe, *pl4, 4) && !getenv("SB200_NO_QUAD_STEP"))
                 steady = 4;
             // fewest launches in front such that the rest divides by `steady` and the launch count has the parity of nsteps
             bool found = false;

@@ -1,0 +1,308 @@
+// stream3d2.cu — TWO diffusion steps per launch for 3-D VonNeumann(1) (SB200_FLAG_DOUBLE_STEP with SB200_DIFFUSION):
+// dest = f(f(src)), the intermediate state never touches memory, so an iterated run (SwitchingStencilArray,
+// src/gatherstencil.jl:77-83 called in a loop) moves half the HBM bytes per step.
+//
+// Same 2.5-D streaming structure as stream3d.cu: a CTA owns an (x,y) tile and marches along z; a producer warp feeds
+// whole source rows (tile + 2 halo rows above / below, + 16 B halo left / right) through a ring of shared-memory
+// stages with cp.async.bulk. Every consumer WARP is independent: a thread owns 16 bytes of x by D2_RT rows of the
+// final state and computes the intermediate state for those cells plus one row above and below (the rows its final
+// cells fold), keeping for both time levels the centre of the previous plane and the partial fold
+// (((zm + ym) + xm) + xp) + yp in registers, exactly like stream3d.cu does for one level. Intermediate x-neighbours
+// come from the adjacent lanes by shuffle; the two cells just outside a warp's 512-byte span are computed by its end
+// lanes from shared memory. Fold order = the reference's offset order (src/stencils/vonneumman.jl:5-15), every
+// operation rounded separately: bit-identical to two single sweeps.
+//
+// Accepted: unpadded Float32 / Float64 parents, Wrap on axes 0 and 1, axis 2 Wrap or an output region that stays two
+// planes inside the parent (slab runs). Wrapped halo cells of the intermediate state are recomputed from wrapped source
+// cells in the same order, so they equal the cells they stand for bit for bit (a Reflect image would fold its
+// neighbours in the opposite order, which is why Reflect is not accepted; Remove would need padval selects).
+// Algorithmic traffic: sizeof(T) read + sizeof(T) written per cell per TWO steps.
+#include <algorithm>
+#include "common.cuh"
+#include "tma.cuh"
+
+namespace sb {
+
+constexpr int D2_WX = 2, D2_WY = 7;               // consumer warps across x and y
+constexpr int D2_WARPS = D2_WX * D2_WY;
+constexpr int D2_TXB = D2_WX * 512;               // tile width in bytes
+constexpr int D2_RT = 2;                          // final rows per thread
+constexpr int D2_TY = D2_WY * D2_RT;              // tile height in rows (14: 1024 rows = 74 tiles = whole waves of 148)
+constexpr int D2_LEFT = 128;                      // margin (halo at its end): global and shared addresses agree mod 128
+constexpr int D2_ROWB = D2_LEFT + D2_TXB + 128;   // shared-memory row: margin | tile | margin
+constexpr int D2_ROWS = D2_TY + 4;                // tile rows + two halo rows on each side
+constexpr int D2_STAGE = D2_ROWS * D2_ROWB;
+constexpr int D2_STAGES = 8;
+constexpr int D2_SMEM = 128 + D2_STAGES * D2_STAGE;
+static_assert(D2_SMEM <= 227 * 1024, "ring does not fit");
+static_assert(D2_ROWS <= 32, "one producer lane per row");
+
+template <typename T> struct D2Params {
+    const T* src;
+    T* dst;
+    long long p1, p2;        // pitches (elements) of axes 1 and 2 (source and dest parents have the same layout)
+    int X, Y, Z;
+    int bc2;                 // boundary of axis 2 (axes 0 and 1 are Wrap)
+    T alpha;
+    int z_lo, zn;            // output planes [z_lo, z_lo + zn)
+    int ntx, nty, nzruns, ty;
+};
+
+__device__ __forceinline__ long long d2_wrap(int r, int n) { return r < 0 ? r + n : (r >= n ? r - n : r); }
+
+template <typename T> struct D2Vec;
+template <> struct D2Vec<float> { using type = float4; };
+template <> struct D2Vec<double> { using type = double2; };
+
+// one diffusion update, every operation rounded separately:  c + alpha * (s - 6 c)
+template <typename T> __device__ __forceinline__ T d2_update(T s, T c, T alpha) {
+    return add_rn(c, mul_rn(alpha, sub_rn(s, mul_rn((T)6, c))));
+}
+
+template <typename T>
+__global__ void __launch_bounds__((D2_WARPS + 1) * 32, 1) stream3d2_kernel(const __grid_constant__ D2Params<T> p) {
+    constexpr int VX = 16 / (int)sizeof(T);
+    extern __shared__ __align__(128) unsigned char smem[];
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem);
+    uint64_t* empty = full + D2_STAGES;
+    unsigned char* ring = smem + 128;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < D2_STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], D2_WARPS); }
+        mbar_fence_init();
+    }
+    __syncthreads();
+    const int ntiles = p.ntx * p.nty;
+    const int ntasks = ntiles * p.nzruns;
+    const int Xb = p.X * (int)sizeof(T);
+    unsigned k = 0;
+    for (int task = blockIdx.x; task < ntasks; task += gridDim.x) {
+        const int tile = task % ntiles, zrun = task / ntiles;
+        const int x0b = (tile % p.ntx) * D2_TXB, y0 = (tile / p.ntx) * p.ty;
+        const int wbytes = min(D2_TXB, Xb - x0b);
+        const int z0 = p.z_lo + (int)((long long)p.zn * zrun / p.nzruns);
+        const int z1 = p.z_lo + (int)((long long)p.zn * (zrun + 1) / p.nzruns);
+        const int nsrc = z1 - z0 + 4;  // source planes z0-2 .. z1+1
+        if (warp == D2_WARPS) {
+            // ---------------- producer warp: lane j copies shared-memory row j = logical row y0-2+j ----------------
+            const bool l_in = x0b > 0, r_in = x0b + wbytes < Xb;   // else: the Wrap image of the other array edge
+            const int mstart = x0b - (l_in ? 16 : 0);
+            const unsigned mlen = wbytes + (l_in ? 16 : 0) + (r_in ? 16 : 0);
+            const int mdst = D2_LEFT - (l_in ? 16 : 0);
+            const unsigned rowbytes = wbytes + 32;
+            long long yrow = -1;
+            if (lane < p.ty + 4) {
+                const int y = y0 - 2 + lane;
+                if (y <= p.Y + 1) yrow = d2_wrap(y, p.Y);
+            }
+            const unsigned nrows = __popc(__ballot_sync(0xffffffffu, yrow >= 0));
+            for (int i = 0; i < nsrc; i++, k++) {
+                const int slot = k % D2_STAGES;
+                int zl = z0 - 2 + i;
+                if (p.bc2 == SB200_WRAP) zl = (int)d2_wrap(zl, p.Z);
+                if (lane == 0) {
+                    mbar_wait(&empty[slot], ((k / D2_STAGES) & 1) ^ 1);
+                    mbar_arrive_expect_tx(&full[slot], nrows * rowbytes);
+                }
+                __syncwarp();
+                if (yrow >= 0) {
+                    const unsigned char* g = reinterpret_cast<const unsigned char*>(p.src + (long long)zl * p.p2 + yrow * p.p1);
+                    unsigned char* srow = ring + slot * D2_STAGE + lane * D2_ROWB;
+                    bulk_g2s(srow + mdst, g + mstart, mlen, &full[slot]);
+                    if (!l_in) bulk_g2s(srow + D2_LEFT - 16, g + Xb - 16, 16, &full[slot]);
+                    if (!r_in) bulk_g2s(srow + D2_LEFT + wbytes, g, 16, &full[slot]);
+                }
+            }
+            continue;
+        }
+        // ---------------- consumers ----------------
+        const int wx = warp % D2_WX, wy = warp / D2_WX;
+        const int xtb = (wx * 32 + lane) * 16;         // byte offset inside the tile
+        const int ry0 = wy * D2_RT;                    // first final tile row of this thread
+        const bool xact = xtb < wbytes;
+        const int gx = (x0b + xtb) / (int)sizeof(T);
+        const bool endlane = lane == 0 || lane == 31;
+        const int xe = lane == 0 ? -(int)sizeof(T) : 16;   // the cell just outside the warp's span, relative to this thread's 16 bytes
+        // level 1 (intermediate state): rows ry0-1 .. ry0+RT ; level 2 (final state): rows ry0 .. ry0+RT-1
+        T c1[D2_RT + 2][VX], q1[D2_RT + 2][VX], c2[D2_RT][VX], q2[D2_RT][VX];
+        T c1e[D2_RT], q1e[D2_RT];                      // level-1 state of the end lanes' outside cell
+#pragma unroll
+        for (int r = 0; r < D2_RT + 2; r++)
+#pragma unroll
+            for (int v = 0; v < VX; v++) { c1[r][v] = T(0); q1[r][v] = T(0); }
+#pragma unroll
+        for (int r = 0; r < D2_RT; r++) {
+            c1e[r] = T(0); q1e[r] = T(0);
+#pragma unroll
+            for (int v = 0; v < VX; v++) { c2[r][v] = T(0); q2[r][v] = T(0); }
+        }
+        T* __restrict__ dbase = p.dst + (long long)(y0 + ry0) * p.p1 + gx;
+        for (int i = 0; i < nsrc; i++, k++) {
+            const int slot = k % D2_STAGES;
+            mbar_wait(&full[slot], (k / D2_STAGES) & 1);
+            // this thread's 16 bytes in shared-memory row 0; tile row t lives in shared-memory row t + 2
+            const unsigned char* sb_ = ring + slot * D2_STAGE + D2_LEFT + xtb;
+            // source rows ry0-2 .. ry0+RT+1  (shared-memory rows ry0 .. ry0+RT+3)
+            T rowv[D2_RT + 4][VX];
+#pragma unroll
+            for (int q = 0; q < D2_RT + 4; q++) {
+                const typename D2Vec<T>::type w = *reinterpret_cast<const typename D2Vec<T>::type*>(sb_ + (ry0 + q) * D2_ROWB);
+                if constexpr (VX == 4) { rowv[q][0] = w.x; rowv[q][1] = w.y; rowv[q][2] = w.z; rowv[q][3] = w.w; }
+                else { rowv[q][0] = w.x; rowv[q][1] = w.y; }
+            }
+            // ---- level 1: the plane that arrived (source plane s) completes intermediate plane s-1 ----
+            T mid[D2_RT + 2][VX];
+#pragma unroll
+            for (int j = 0; j < D2_RT + 2; j++) {      // intermediate row ry0-1+j, its source centre row is rowv[j+1]
+                const unsigned char* t = sb_ + (ry0 + j + 1) * D2_ROWB;
+                T l_ = __shfl_up_sync(0xffffffffu, rowv[j + 1][VX - 1], 1);
+                T r_ = __shfl_down_sync(0xffffffffu, rowv[j + 1][0], 1);
+                if (lane == 0) l_ = *reinterpret_cast<const T*>(t - sizeof(T));
+                if (lane == 31) r_ = *reinterpret_cast<const T*>(t + 16);
+#pragma unroll
+                for (int v = 0; v < VX; v++) {
+                    const T c = rowv[j + 1][v];
+                    const T cc = c1[j][v];
+                    mid[j][v] = d2_update(add_rn(q1[j][v], c), cc, p.alpha);
+                    const T xm = v == 0 ? l_ : rowv[j + 1][v == 0 ? 0 : v - 1];
+                    const T xp = v == VX - 1 ? r_ : rowv[j + 1][v == VX - 1 ? v : v + 1];
+                    T a = add_rn(cc, rowv[j][v]);
+                    a = add_rn(a, xm);
+                    a = add_rn(a, xp);
+                    a = add_rn(a, rowv[j + 2][v]);
+                    q1[j][v] = a;
+                    c1[j][v] = c;
+                }
+            }
+            // the intermediate cell just outside the span (left of lane 0, right of lane 31), final rows only
+            T mide[D2_RT];
+#pragma unroll
+            for (int r = 0; r < D2_RT; r++) mide[r] = T(0);
+            if (endlane) {
+#pragma unroll
+                for (int r = 0; r < D2_RT; r++) {
+                    const unsigned char* t = sb_ + (ry0 + r + 2) * D2_ROWB + xe;
+                    const T c = *reinterpret_cast<const T*>(t);
+                    const T cc = c1e[r];
+                    mide[r] = d2_update(add_rn(q1e[r], c), cc, p.alpha);
+                    T a = add_rn(cc, *reinterpret_cast<const T*>(t - D2_ROWB));
+                    a = add_rn(a, *reinterpret_cast<const T*>(t - sizeof(T)));
+                    a = add_rn(a, *reinterpret_cast<const T*>(t + sizeof(T)));
+                    a = add_rn(a, *reinterpret_cast<const T*>(t + D2_ROWB));
+                    q1e[r] = a;
+                    c1e[r] = c;
+                }
+            }
+            // ---- level 2: intermediate plane m = s-1 completes final plane m-1 = s-2 ----
+            const int zo = z0 - 4 + i;
+            const bool store = i >= 4;
+#pragma unroll
+            for (int r = 0; r < D2_RT; r++) {          // final row ry0+r, its intermediate centre row is mid[r+1]
+                T l_ = __shfl_up_sync(0xffffffffu, mid[r + 1][VX - 1], 1);
+                T r_ = __shfl_down_sync(0xffffffffu, mid[r + 1][0], 1);
+                if (lane == 0) l_ = mide[r];
+                if (lane == 31) r_ = mide[r];
+                T out[VX];
+#pragma unroll
+                for (int v = 0; v < VX; v++) {
+                    const T c = mid[r + 1][v];
+                    const T cc = c2[r][v];
+                    out[v] = d2_update(add_rn(q2[r][v], c), cc, p.alpha);
+                    const T xm = v == 0 ? l_ : mid[r + 1][v == 0 ? 0 : v - 1];
+                    const T xp = v == VX - 1 ? r_ : mid[r + 1][v == VX - 1 ? v : v + 1];
+                    T a = add_rn(cc, mid[r][v]);
+                    a = add_rn(a, xm);
+                    a = add_rn(a, xp);
+                    a = add_rn(a, mid[r + 2][v]);
+                    q2[r][v] = a;
+                    c2[r][v] = c;
+                }
+                if (store && xact && y0 + ry0 + r < p.Y && ry0 + r < p.ty) {
+                    T* d = dbase + (long long)zo * p.p2 + (long long)r * p.p1;
+                    if constexpr (VX == 4) *reinterpret_cast<float4*>(d) = make_float4(out[0], out[1], out[2], out[3]);
+                    else *reinterpret_cast<double2*>(d) = make_double2(out[0], out[1]);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[slot]);
+        }
+    }
+}
+
+template <typename T> static int d2_launch(D2Params<T>& p, cudaStream_t st) {
+    static thread_local int cfg_dev = -1;
+    int dev = 0;
+    SB_CUDA(cudaGetDevice(&dev));
+    if (dev != cfg_dev) {
+        SB_CUDA(cudaFuncSetAttribute(stream3d2_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, D2_SMEM));
+        cfg_dev = dev;
+    }
+    const long long ctas = num_sms();   // one CTA per SM (the ring takes most of the shared memory)
+    // Tile height and z-runs: a task loads (ty + 4) rows x (zn / nz + 4) planes; pick the pair that minimises
+    // waves x rows loaded per task (idle tail of a partial last wave against re-read halo rows / planes).
+    int best_ty = D2_TY, best = 1;
+    double best_cost = 1e300;
+    for (int ty = D2_TY; ty >= D2_TY / 2; ty -= D2_RT) {
+        const long long nty = (p.Y + ty - 1) / ty;
+        for (int nz = 1; nz <= 64 && nz <= std::max(1, p.zn / 8); nz++) {
+            const long long tasks = (long long)p.ntx * nty * nz;
+            const long long waves = (tasks + ctas - 1) / ctas;
+            const double cost = (double)waves * (ty + 4.0) * ((double)p.zn / nz + 4.0);
+            if (cost < best_cost * 0.999) { best_cost = cost; best = nz; best_ty = ty; }
+        }
+    }
+    p.ty = best_ty;
+    p.nty = (p.Y + best_ty - 1) / best_ty;
+    p.nzruns = best;
+    const long long ntasks = (long long)p.ntx * p.nty * p.nzruns;
+    const long long grid = std::min<long long>(ctas, ntasks);
+    stream3d2_kernel<T><<<(unsigned)grid, (D2_WARPS + 1) * 32, D2_SMEM, st>>>(p);
+    SB_LAUNCH_CHECK();
+    return SB200_OK;
+}
+
+// Can this sweep run two diffusion steps per launch?
+bool diffusion2_accepts(const sb200_desc& d, const Plan& pl) {
+    if (d.reducer != SB200_DIFFUSION || d.ndim != 3 || (d.eltype != SB200_F32 && d.eltype != SB200_F64)) return false;
+    if (pl.shape_tag != SB200_VONNEUMANN || pl.shape_ndim != 3 || d.radius != 1 || d.noffsets != 6) return false;
+    if (d.flags & (SB200_FLAG_NO_TMA | SB200_FLAG_FORCE_GENERIC | SB200_FLAG_QUAD_STEP)) return false;
+    const long long es = (long long)elsize(d.eltype);
+    for (int a = 0; a < 3; a++) {
+        if (d.src_off[a] != 0 || d.dst_off[a] != 0 || d.dst_ext[a] != d.size[a] || d.src_ext[a] != d.size[a]) return false;
+        if (d.size[a] < 4 || d.size[a] > (1 << 28)) return false;
+    }
+    if ((d.size[0] * es) % 16 || d.size[0] * es < 64) return false;
+    if (d.boundary[0] != SB200_WRAP || d.boundary[1] != SB200_WRAP) return false;
+    if (pl.dd.lo[0] != 0 || pl.dd.n[0] != d.size[0] || pl.dd.lo[1] != 0 || pl.dd.n[1] != d.size[1]) return false;  // z regions only
+    const long long lo = pl.dd.lo[2], hi = lo + pl.dd.n[2];
+    const bool inside = lo >= 2 && hi + 2 <= d.size[2];   // never leaves the parent: the boundary rule of axis 2 is not exercised
+    if (!inside && d.boundary[2] != SB200_WRAP) return false;
+    return true;
+}
+
+template <typename T> static int d2_try(const Plan& pl, const void* src, void* dst, cudaStream_t st) {
+    const sb200_desc& d = pl.d;
+    if (((uintptr_t)src | (uintptr_t)dst) & 15) return -1;
+    if (pl.dd.n[2] == 0) return SB200_OK;
+    D2Params<T> p;
+    p.src = (const T*)src; p.dst = (T*)dst;
+    p.p1 = d.size[0]; p.p2 = d.size[0] * d.size[1];
+    p.X = (int)d.size[0]; p.Y = (int)d.size[1]; p.Z = (int)d.size[2];
+    p.bc2 = d.boundary[2];
+    p.alpha = (T)d.alpha;
+    p.z_lo = (int)pl.dd.lo[2]; p.zn = (int)pl.dd.n[2];
+    const long long Xb = d.size[0] * (long long)sizeof(T);
+    p.ntx = (int)((Xb + D2_TXB - 1) / D2_TXB);
+    p.nty = 0; p.nzruns = 1; p.ty = D2_TY;
+    return d2_launch<T>(p, st);
+}
+
+int try_diffusion3d_double(const Plan& pl, const void* src, void* dst, cudaStream_t st) {
+    const sb200_desc& d = pl.d;
+    if (!diffusion2_accepts(d, pl)) return -1;
+    int rc = d.eltype == SB200_F32 ? d2_try<float>(pl, src, dst, st) : d2_try<double>(pl, src, dst, st);
+    if (rc == SB200_OK) set_kernel_name("stream3d2_kernel");
+    return rc;
+}
+
+}  // namespace sb

@@ -26,7 +26,7 @@ from stencils_b200 import _abi as A  # noqa: E402
 from stencils_b200._desc import build_desc  # noqa: E402
 
 WANT = ["life_bit_kernel<4", "life_bit_kernel<2", "life_tma2_kernel", "life_tma_kernel", "life_swar_kernel",
-        "stream2d_kernel", "stream3d_kernel", "gather_stream_kernel", "gather_stream3d_kernel", "gather_generic",
+        "stream2d_kernel", "stream3d_kernel", "stream3d2_kernel", "gather_stream_kernel", "gather_stream3d_kernel", "gather_generic",
         "scatter_stream_kernel", "scatter_fast_kernel", "halo_kernel"]
 seen = {}
 DRY = False  # --dry: no device calls, only the oracle side (checks the case table itself on a box without a GPU)
@@ -232,9 +232,12 @@ def main():
     v = rand(rng, (64, 40, 24), np.float32)
     vn3 = npr.offsets("VonNeumann", 1, 3)
     gather_case("VonNeumann(1,3) diffusion F32 wrap", v, vn3, 1, WR, A.DIFFUSION, alpha=0.1)
+    gather_case("VonNeumann(1,3) diffusion F32 wrap, two steps per launch", v, vn3, 1, WR, A.DIFFUSION, alpha=0.1, flags=A.FLAG_DOUBLE_STEP)
     gather_case("Window(1,3) mean F32 wrap (run-time table)", v, npr.offsets("Window", 1, 3), 1, WR, A.MEAN)
     if full:
         gather_case("VonNeumann(1,3) diffusion F32 remove/reflect/wrap", v, vn3, 1, (RE, RF, WR), A.DIFFUSION, alpha=0.1, padval=0.25)
+        gather_case("VonNeumann(1,3) diffusion F64 300x17x12 two steps, region z 2..10", rand(rng, (300, 17, 12), np.float64), vn3, 1, (WR, WR, RE), A.DIFFUSION,
+                    alpha=0.1, flags=A.FLAG_DOUBLE_STEP, region=((0, 0, 2), (300, 17, 10)))
         gather_case("VonNeumann(1,3) diffusion F32 iterate x5", v, vn3, 1, WR, A.DIFFUSION, alpha=0.1, nsteps=5)
         gather_case("VonNeumann(1,3) sum F64 reflect, region z 3..20", rand(rng, (36, 21, 24), np.float64), vn3, 1, RF, A.SUM, region=((0, 0, 3), (36, 21, 20)))
         gather_case("Moore(1,3) max F64 remove", rand(rng, (36, 21, 13), np.float64), npr.offsets("Moore", 1, 3), 1, RE, A.MAX, padval=-3.0)

@@ -592,3 +592,68 @@ def test_iterate_small_grids_replay_a_cuda_graph(orc):
         launches = l.sb200_launch_count(1)
         bits_equal(to_host(ta if n % 2 == 0 else tb, a0.shape, a0.dtype), want)
         assert n // 4 <= launches <= n
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+def test_diffusion_two_steps_per_launch(orc, dt, monkeypatch):
+    """SB200_FLAG_DOUBLE_STEP with the Diffusion reducer (csrc/stream3d2.cu: stream3d2_kernel): dest = step(step(src))
+    against two oracle sweeps bit for bit (tile edges, ragged tiles, z-runs, Wrap seams, interior regions), and
+    sb200_iterate with SB200_DIFFUSION_DOUBLE_STEP=1 against the oracle for odd and even step counts."""
+    from tests.util import stream, sync, to_dev, to_host
+    rng = np.random.default_rng(91)
+    l = A.lib()
+    offs = npr.offsets("VonNeumann", 1, 3)
+    es = np.dtype(dt).itemsize
+    shapes = [(64, 20, 9), (160, 17, 8), (300, 16, 8), (1024 // es + 8, 33, 21), (512, 40, 70), (16, 4, 4)]
+    for shape in shapes:
+        g = rand_array(rng, shape, dt)
+        et = A.ELTYPE_OF_DTYPE[np.dtype(dt)]
+        kw = dict(size=shape, eltype=et, out_eltype=et, offsets=offs, radius=1, reducer=A.DIFFUSION, alpha=0.1)
+        h1 = build_desc(boundary=A.WRAP, **kw)
+        want = orc.gather(h1, orc.gather(h1, g, dst_like(h1)), dst_like(h1))
+        h2 = build_desc(boundary=A.WRAP, flags=A.FLAG_DOUBLE_STEP, **kw)
+        got, _ = gpu_gather(h2, g, dst_like(h2))
+        assert l.sb200_last_kernel() == b"stream3d2_kernel"
+        bits_equal(got, want)
+        # an output region that stays two planes inside the parent (what the slab iterator asks for): the boundary rule
+        # named for axis 2 is never exercised, everything outside the region keeps its old dest value
+        Z = shape[2]
+        if Z >= 8:
+            for bc2, lo, hi in ((A.REMOVE, 2, Z - 2), (A.REFLECT, 3, Z - 3), (A.WRAP, 0, 3), (A.WRAP, Z - 3, Z)):
+                hr = build_desc(boundary=(A.WRAP, A.WRAP, bc2), flags=A.FLAG_DOUBLE_STEP, region=((0, 0, lo), (shape[0], shape[1], hi)), **kw)
+                got, _ = gpu_gather(hr, g, dst_like(hr, 7))
+                assert l.sb200_last_kernel() == b"stream3d2_kernel"
+                want_r = dst_like(hr, 7)
+                want_r[:, :, lo:hi] = want[:, :, lo:hi]
+                bits_equal(got, want_r)
+    # NaN / Inf / signed zeros travel through both levels like through two sweeps
+    g = rand_array(rng, (128, 18, 10), dt)
+    g[rng.random(g.shape) < 0.02] = np.nan
+    g[rng.random(g.shape) < 0.02] = np.inf
+    g[rng.random(g.shape) < 0.1] = -0.0
+    kw = dict(size=g.shape, eltype=A.ELTYPE_OF_DTYPE[np.dtype(dt)], out_eltype=A.ELTYPE_OF_DTYPE[np.dtype(dt)], offsets=offs, radius=1,
+              reducer=A.DIFFUSION, alpha=0.25, boundary=A.WRAP)
+    h1 = build_desc(**kw)
+    with np.errstate(all="ignore"):
+        want = orc.gather(h1, orc.gather(h1, g, dst_like(h1)), dst_like(h1))
+    got, _ = gpu_gather(build_desc(flags=A.FLAG_DOUBLE_STEP, **kw), g, dst_like(h1))
+    bits_equal(got, want)
+    # sb200_iterate schedules the pairs by itself when asked to
+    monkeypatch.setenv("SB200_DIFFUSION_DOUBLE_STEP", "1")
+    g = rand_array(rng, (96, 30, 22), dt)
+    kw["size"] = g.shape
+    h1 = build_desc(**kw)
+    for n in (4, 5, 6, 7, 11):
+        want = orc.iterate(h1, g.copy(order="F"), np.zeros_like(g, order="F"), n)
+        ta, tb = to_dev(g), to_dev(np.zeros_like(g, order="F"))
+        l.sb200_launch_count(1)
+        A.check(l.sb200_iterate(h1.ptr(), ta.data_ptr(), tb.data_ptr(), n, stream()))
+        sync()
+        assert l.sb200_launch_count(1) < n, "no pair of steps was fused"
+        bits_equal(to_host(ta if n % 2 == 0 else tb, g.shape, g.dtype), want)
+    monkeypatch.delenv("SB200_DIFFUSION_DOUBLE_STEP")
+    # layouts the kernel does not take -> status code, never a silent single step
+    for bad in (dict(boundary=A.REFLECT), dict(boundary=A.REMOVE), dict(boundary=(A.WRAP, A.REFLECT, A.WRAP))):
+        hb = build_desc(flags=A.FLAG_DOUBLE_STEP, **dict(kw, **bad))
+        t = to_dev(g)
+        assert l.sb200_gather(hb.ptr(), t.data_ptr(), to_dev(g).data_ptr(), None) == A.EUNSUPPORTED
