@@ -422,8 +422,8 @@ def main():
                     k = 200
                 run2(1)
                 torch.cuda.synchronize()
-                kn = lib.sb200_last_kernel().decode()
                 ms2 = time_steps(torch, run2, k, 3)
+                kn = lib.sb200_last_kernel().decode()  # the kernel of the timed region (iterated runs may fuse steps)
                 v = cells2 * k / (ms2 * 1e-3) / 1e9
                 also[name] = {"value": v, "unit": "Gcell-updates/s", "ms_per_step": ms2 / k, "kernel": kn,
                               "roofline_frac": v * sp["bytes_per_cell"] / peak, "workload": sp["desc"]}

@@ -189,3 +189,28 @@ def test_diffusion_1024_cubed(orc):
     assert _biteq(o1, o2)
     wins = [((-20, -20, -20), (48, 44, 40)), ((1000, 500, 1010), (40, 36, 44)), ((250, 1016, 300), (36, 40, 32))]
     _check_windows(orc, src, res, kw, cone=steps, windows=wins, wrap=True, steps=steps)
+
+
+def test_diffusion_1024_cubed_two_steps_per_launch():
+    """configs[4] through SB200_FLAG_DOUBLE_STEP (stream3d2_kernel): whole-grid bit equality with two launches of the
+    single-step streaming kernel (itself checked against the oracle above), and a slab-style interior region."""
+    import torch
+    n = 1024
+    src = synth_torch((n, n, n), np.float32, 0x5EED0005, "cuda")
+    kw = dict(eltype=A.F32, out_eltype=A.F32, offsets=npr.offsets("VonNeumann", 1, 3), radius=1, boundary=A.WRAP,
+              reducer=A.DIFFUSION, alpha=0.1)
+    h = build_desc(size=(n, n, n), **kw)
+    mid, want, got = torch.empty_like(src), torch.empty_like(src), torch.empty_like(src)
+    _gather(h, src, mid)
+    _gather(h, mid, want)
+    assert A.lib().sb200_last_kernel() == b"stream3d_kernel"
+    _gather(build_desc(size=(n, n, n), flags=A.FLAG_DOUBLE_STEP, **kw), src, got)
+    assert A.lib().sb200_last_kernel() == b"stream3d2_kernel"
+    torch.cuda.synchronize()
+    assert _biteq(got, want)
+    # planes [4, n-4) only (what a slab sweep asks for): the rest of dest keeps its old value
+    mid.fill_(7.0)
+    _gather(build_desc(size=(n, n, n), flags=A.FLAG_DOUBLE_STEP, region=((0, 0, 4), (n, n, n - 4)), **kw), src, mid)
+    torch.cuda.synchronize()
+    assert _biteq(mid[:, :, 4:n - 4], want[:, :, 4:n - 4])
+    assert bool((mid[:, :, :4] == 7.0).all()) and bool((mid[:, :, n - 4:] == 7.0).all())
