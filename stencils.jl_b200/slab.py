@@ -443,3 +443,99 @@ def bench_weak(workload, spec, steps, warmup, synth=None):
     cfg = {"ghost_planes": ghost, "steps_per_exchange": ghost // R, "exchange": how,
            "global_grid": list(shape[:-1]) + [shape[-1] * world]}
     return ms, cells_local * world, launches, kernel, cfg
+
+
+# ------------------------------------------------------------------------------------------------ one-shot sweeps
+def slab_gather(local_owned, *, offsets, radius, reducer, boundary, eltype, rank, world, compute=None,
+                reducer_kwargs=None, padval=0, exchange="auto"):
+    """One-shot (non-iterated) gather over slabs — `mapstencil(f, A)` with A split along its last axis (SURVEY §8e:
+    BASELINE configs 1, 3, 4a at N GPUs): ONE pre-exchange of R ghost planes, then one sweep of the owned planes.
+    Returns this rank's slab of the result (torch tensor, split axis first). Reducers that change the element type
+    (mean / sum of Bool, mean of integers) are not taken here: the state buffers are typed like the source."""
+    if reducer in (A.SUM, A.MEAN) and eltype in (A.BOOL,) or (reducer == A.MEAN and eltype not in (A.F32, A.F64)):
+        raise A.ArgumentError("slab_gather needs a reducer whose result has the element type of the source")
+    it = SlabIterator(local_owned, offsets=offsets, radius=radius, reducer=reducer, boundary=boundary, eltype=eltype,
+                      ghost=max(int(radius), 1), rank=rank, world=world, compute=compute, reducer_kwargs=reducer_kwargs,
+                      padval=padval, exchange=exchange, overlap=False)
+    try:
+        it.step(1)
+        return it.state.clone()
+    finally:
+        it.close()
+
+
+def split_columns_for_scatter(ncols, world, rank, radius):
+    """Columns [lo, hi) of the last axis owned by `rank` for slab_scatter: slab boundaries are multiples of the pass
+    stride 2R+1 of _scatterstencil_cpu! (src/scatterstencil.jl:53-58), so a column's pass number is the same in the
+    slab's local numbering as in the global one."""
+    S = 2 * int(radius) + 1
+    units = -(-int(ncols) // S)
+    base, rem = divmod(units, world)
+    lo_u = rank * base + min(rank, rem)
+    hi_u = lo_u + base + (1 if rank < rem else 0)
+    return min(lo_u * S, ncols), min(hi_u * S, ncols)
+
+
+def slab_scatter(local_src, local_dst, *, ncols_global, offsets, radius, weights, boundary, eltype, rank, world,
+                 scatter_op=A.OP_ADD, scatter_rule=A.SCATTER_CENTER_WEIGHTS, flags=0, compute=None):
+    """scatterstencil!(f, op, dest, source) (src/scatterstencil.jl:36-112) with source and dest split along the last
+    axis into the column ranges of split_columns_for_scatter (SURVEY §8e, config 4b at N GPUs).
+
+    A destination cell folds, in the reference's (pass, row, k) order, the values scattered to it by the source
+    columns within R of its own column. Every rank therefore receives 2R+1 ghost SOURCE columns from each neighbour
+    (one point-to-point exchange; a ring when the split axis wraps), runs the ordinary single-domain scatter over
+    [ghost | owned | ghost] and keeps the owned destination columns: the ghost destination columns collect partial
+    folds and are dropped. Because slab boundaries and the ghost thickness are multiples of 2R+1, local and global
+    pass numbers agree and the result is bit-identical to the single-domain scatter. At the global ends of a Remove /
+    Reflect axis the parent simply ends (no ghost), so the end rank applies the real boundary rule; interior parent
+    ends use the same rule, which only ever touches ghost destination columns. local_src / local_dst: torch tensors of
+    shape (owned columns, rows), C-contiguous (= column-major (rows, columns)); local_dst is updated in place."""
+    import torch
+    import torch.distributed as dist
+    R = int(radius)
+    S = 2 * R + 1
+    G = S
+    bc0, bc_split = boundary
+    wrap = bc_split == A.WRAP
+    n = local_src.shape[0]
+    if local_dst.shape != local_src.shape:
+        raise A.ArgumentError("Source array sizes must match: dest slab and source slab differ")
+    if wrap and ncols_global % S:
+        raise A.ArgumentError(f"slab_scatter with Wrap on the split axis needs a column count that is a multiple of 2R+1 = {S} "
+                              "(the reference's pass order at the wrap seam is only defined then)")
+    has_lo, has_hi = wrap or rank > 0, wrap or rank < world - 1
+    if world > 1 and n < G:
+        raise A.ArgumentError(f"slab of {n} columns is thinner than the ghost zone ({G})")
+    glo, ghi = (G if has_lo else 0), (G if has_hi else 0)
+    ext = glo + n + ghi
+    src = torch.empty((ext,) + tuple(local_src.shape[1:]), dtype=local_src.dtype, device=local_src.device)
+    dst = torch.zeros_like(src)
+    src[glo:glo + n].copy_(local_src)
+    dst[glo:glo + n].copy_(local_dst)
+    if world > 1:
+        up, down = (rank + 1) % world, (rank - 1) % world
+        ops = []
+        if has_hi:
+            ops.append(dist.P2POp(dist.isend, src[glo + n - G:glo + n], up))
+        if has_lo:
+            ops.append(dist.P2POp(dist.irecv, src[:G], down))
+        if has_lo:
+            ops.append(dist.P2POp(dist.isend, src[glo:glo + G], down))
+        if has_hi:
+            ops.append(dist.P2POp(dist.irecv, src[glo + n:], up))
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+    elif wrap:
+        src[:G].copy_(local_src[n - G:])
+        src[glo + n:].copy_(local_src[:G])
+    rows = int(local_src.shape[1])
+    local_bc = A.REFLECT if bc_split == A.REFLECT else A.REMOVE
+    h = build_desc(size=(rows, ext), eltype=eltype, out_eltype=eltype, offsets=offsets, radius=R, boundary=(bc0, local_bc),
+                   weights=weights, scatter_op=scatter_op, scatter_rule=scatter_rule, flags=flags)
+    if compute is None:
+        stream = torch.cuda.current_stream().cuda_stream
+        A.check(A.lib().sb200_scatter(h.ptr(), src.data_ptr(), dst.data_ptr(), stream))
+    else:
+        compute(h, src, dst)
+    local_dst.copy_(dst[glo:glo + n])
+    return local_dst
