@@ -2,15 +2,21 @@
 // dest = f(f(src)), the intermediate state never touches memory, so an iterated run (SwitchingStencilArray,
 // src/gatherstencil.jl:77-83 called in a loop) moves half the HBM bytes per step.
 //
-// Same 2.5-D streaming structure as stream3d.cu: a CTA owns an (x,y) tile and marches along z; a producer warp feeds
+// Same 2.5-D streaming structure as stream3d.cu: a CTA owns an (x,y) tile and marches along z; two producer warps feed
 // whole source rows (tile + 2 halo rows above / below, + 16 B halo left / right) through a ring of shared-memory
-// stages with cp.async.bulk. Every consumer WARP is independent: a thread owns 16 bytes of x by D2_RT rows of the
-// final state and computes the intermediate state for those cells plus one row above and below (the rows its final
-// cells fold), keeping for both time levels the centre of the previous plane and the partial fold
-// (((zm + ym) + xm) + xp) + yp in registers, exactly like stream3d.cu does for one level. Intermediate x-neighbours
-// come from the adjacent lanes by shuffle; the two cells just outside a warp's 512-byte span are computed by its end
-// lanes from shared memory. Fold order = the reference's offset order (src/stencils/vonneumman.jl:5-15), every
-// operation rounded separately: bit-identical to two single sweeps.
+// stages with cp.async.bulk. Per arriving source plane the 16 consumer warps
+//   level 1: complete one plane of the INTERMEDIATE state over the tile plus a one-cell rim (every cell once: a thread
+//            owns 16 bytes of x by 2 rows, the two rim columns are computed by the end lanes of the edge warps) and
+//            put it into a double-buffered shared-memory plane,
+//   (one named barrier)
+//   level 2: complete one plane of the FINAL state from that plane (own rows from registers, the rows of the
+//            neighbouring warp from shared memory, x-neighbours by shuffle) and store it.
+// Both levels keep, per cell, the centre of the previous plane and the partial fold (((zm + ym) + xm) + xp) + yp in
+// registers, exactly like stream3d.cu does for one level, so a plane costs 9 flops per cell per level and nothing is
+// recomputed except the rim. (r01g measured the first version of this kernel, warp-private with a recomputed rim per
+// warp: 27 instructions per cell-update, issue-bound, 3 % SLOWER than two single sweeps.)
+// Fold order = the reference's offset order (src/stencils/vonneumman.jl:5-15), every operation rounded separately:
+// bit-identical to two single sweeps.
 //
 // Accepted: unpadded Float32 / Float64 parents, Wrap on axes 0 and 1, axis 2 Wrap or an output region that stays two
 // planes inside the parent (slab runs). Wrapped halo cells of the intermediate state are recomputed from wrapped source
@@ -23,19 +29,25 @@
 
 namespace sb {
 
-constexpr int D2_WX = 2, D2_WY = 7;               // consumer warps across x and y
+constexpr int D2_WX = 2, D2_WY = 8;               // consumer warps across x and y
 constexpr int D2_WARPS = D2_WX * D2_WY;
+constexpr int D2_PRODUCERS = 2;                   // producer warps (even / odd rows of a stage)
+constexpr int D2_THREADS = (D2_WARPS + D2_PRODUCERS) * 32;
 constexpr int D2_TXB = D2_WX * 512;               // tile width in bytes
-constexpr int D2_RT = 2;                          // final rows per thread
-constexpr int D2_TY = D2_WY * D2_RT;              // tile height in rows (14: 1024 rows = 74 tiles = whole waves of 148)
+constexpr int D2_RT = 2;                          // rows per thread and level
+constexpr int D2_TY = (D2_WY - 1) * D2_RT;        // final rows per tile (14: 1024 rows = 74 tiles = whole waves of 148);
+                                                  // level 1 covers D2_TY + 2 = D2_WY * D2_RT rows
 constexpr int D2_LEFT = 128;                      // margin (halo at its end): global and shared addresses agree mod 128
 constexpr int D2_ROWB = D2_LEFT + D2_TXB + 128;   // shared-memory row: margin | tile | margin
-constexpr int D2_ROWS = D2_TY + 4;                // tile rows + two halo rows on each side
+constexpr int D2_ROWS = D2_TY + 4;                // source rows of a stage: tile rows + two halo rows on each side
 constexpr int D2_STAGE = D2_ROWS * D2_ROWB;
-constexpr int D2_STAGES = 8;
-constexpr int D2_SMEM = 128 + D2_STAGES * D2_STAGE;
+constexpr int D2_STAGES = 6;
+constexpr int D2_MROWS = D2_TY + 2;               // intermediate plane: tile rows + one rim row on each side
+constexpr int D2_MSTAGE = D2_MROWS * D2_ROWB;
+constexpr int D2_SMEM = 128 + D2_STAGES * D2_STAGE + 2 * D2_MSTAGE;
 static_assert(D2_SMEM <= 227 * 1024, "ring does not fit");
-static_assert(D2_ROWS <= 32, "one producer lane per row");
+static_assert(D2_ROWS <= 32 * D2_PRODUCERS, "one producer lane per row");
+static_assert(2 * D2_STAGES * 8 <= 128, "barrier header");
 
 template <typename T> struct D2Params {
     const T* src;
@@ -59,13 +71,44 @@ template <typename T> __device__ __forceinline__ T d2_update(T s, T c, T alpha) 
     return add_rn(c, mul_rn(alpha, sub_rn(s, mul_rn((T)6, c))));
 }
 
+template <typename T, int VX> __device__ __forceinline__ void d2_lds(T (&v)[VX], const unsigned char* p) {
+    const typename D2Vec<T>::type w = *reinterpret_cast<const typename D2Vec<T>::type*>(p);
+    if constexpr (VX == 4) { v[0] = w.x; v[1] = w.y; v[2] = w.z; v[3] = w.w; }
+    else { v[0] = w.x; v[1] = w.y; }
+}
+template <typename T, int VX> __device__ __forceinline__ void d2_st(void* p, const T (&v)[VX]) {
+    if constexpr (VX == 4) *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    else *reinterpret_cast<double2*>(p) = make_double2(v[0], v[1]);
+}
+
+// One plane of one level for one row of a thread: `c` = this plane's centre cells, ym / yp = the rows above / below,
+// l_ / r_ = the cells left of c[0] / right of c[VX-1]. Completes the previous plane (returned in `done`) and starts this one.
+template <typename T, int VX>
+__device__ __forceinline__ void d2_plane(T (&done)[VX], T (&cprev)[VX], T (&part)[VX], const T (&c)[VX], const T (&ym)[VX],
+                                         const T (&yp)[VX], T l_, T r_, T alpha) {
+#pragma unroll
+    for (int v = 0; v < VX; v++) {
+        const T cc = cprev[v];
+        done[v] = d2_update(add_rn(part[v], c[v]), cc, alpha);
+        const T xm = v == 0 ? l_ : c[v == 0 ? 0 : v - 1];
+        const T xp = v == VX - 1 ? r_ : c[v == VX - 1 ? v : v + 1];
+        T a = add_rn(cc, ym[v]);
+        a = add_rn(a, xm);
+        a = add_rn(a, xp);
+        a = add_rn(a, yp[v]);
+        part[v] = a;
+        cprev[v] = c[v];
+    }
+}
+
 template <typename T>
-__global__ void __launch_bounds__((D2_WARPS + 1) * 32, 1) stream3d2_kernel(const __grid_constant__ D2Params<T> p) {
+__global__ void __launch_bounds__(D2_THREADS, 1) stream3d2_kernel(const __grid_constant__ D2Params<T> p) {
     constexpr int VX = 16 / (int)sizeof(T);
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem);
     uint64_t* empty = full + D2_STAGES;
     unsigned char* ring = smem + 128;
+    unsigned char* mbuf = ring + D2_STAGES * D2_STAGE;   // two intermediate planes
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         for (int s = 0; s < D2_STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], D2_WARPS); }
@@ -83,31 +126,33 @@ __global__ void __launch_bounds__((D2_WARPS + 1) * 32, 1) stream3d2_kernel(const
         const int z0 = p.z_lo + (int)((long long)p.zn * zrun / p.nzruns);
         const int z1 = p.z_lo + (int)((long long)p.zn * (zrun + 1) / p.nzruns);
         const int nsrc = z1 - z0 + 4;  // source planes z0-2 .. z1+1
-        if (warp == D2_WARPS) {
-            // ---------------- producer warp: lane j copies shared-memory row j = logical row y0-2+j ----------------
+        if (warp >= D2_WARPS) {
+            // ---------------- producer warps: lane j of producer w copies shared-memory row 2j+w = logical row y0-2+2j+w ----------------
+            const int pw = warp - D2_WARPS;
             const bool l_in = x0b > 0, r_in = x0b + wbytes < Xb;   // else: the Wrap image of the other array edge
             const int mstart = x0b - (l_in ? 16 : 0);
             const unsigned mlen = wbytes + (l_in ? 16 : 0) + (r_in ? 16 : 0);
             const int mdst = D2_LEFT - (l_in ? 16 : 0);
             const unsigned rowbytes = wbytes + 32;
+            const int srow_i = D2_PRODUCERS * lane + pw;
             long long yrow = -1;
-            if (lane < p.ty + 4) {
-                const int y = y0 - 2 + lane;
+            if (srow_i < p.ty + 4) {
+                const int y = y0 - 2 + srow_i;
                 if (y <= p.Y + 1) yrow = d2_wrap(y, p.Y);
             }
-            const unsigned nrows = __popc(__ballot_sync(0xffffffffu, yrow >= 0));
+            const unsigned nrows = (unsigned)min(p.ty + 4, p.Y + 4 - y0);   // rows of the stage that are copied (both producers)
             for (int i = 0; i < nsrc; i++, k++) {
                 const int slot = k % D2_STAGES;
                 int zl = z0 - 2 + i;
                 if (p.bc2 == SB200_WRAP) zl = (int)d2_wrap(zl, p.Z);
                 if (lane == 0) {
                     mbar_wait(&empty[slot], ((k / D2_STAGES) & 1) ^ 1);
-                    mbar_arrive_expect_tx(&full[slot], nrows * rowbytes);
+                    if (pw == 0) mbar_arrive_expect_tx(&full[slot], nrows * rowbytes);
                 }
                 __syncwarp();
                 if (yrow >= 0) {
                     const unsigned char* g = reinterpret_cast<const unsigned char*>(p.src + (long long)zl * p.p2 + yrow * p.p1);
-                    unsigned char* srow = ring + slot * D2_STAGE + lane * D2_ROWB;
+                    unsigned char* srow = ring + slot * D2_STAGE + srow_i * D2_ROWB;
                     bulk_g2s(srow + mdst, g + mstart, mlen, &full[slot]);
                     if (!l_in) bulk_g2s(srow + D2_LEFT - 16, g + Xb - 16, 16, &full[slot]);
                     if (!r_in) bulk_g2s(srow + D2_LEFT + wbytes, g, 16, &full[slot]);
@@ -118,113 +163,88 @@ __global__ void __launch_bounds__((D2_WARPS + 1) * 32, 1) stream3d2_kernel(const
         // ---------------- consumers ----------------
         const int wx = warp % D2_WX, wy = warp / D2_WX;
         const int xtb = (wx * 32 + lane) * 16;         // byte offset inside the tile
-        const int ry0 = wy * D2_RT;                    // first final tile row of this thread
+        const int r1 = wy * D2_RT;                     // level 1: tile rows r1-1, r1 (intermediate-plane rows r1, r1+1); level 2: tile rows r1, r1+1
         const bool xact = xtb < wbytes;
         const int gx = (x0b + xtb) / (int)sizeof(T);
-        const bool endlane = lane == 0 || lane == 31;
-        const int xe = lane == 0 ? -(int)sizeof(T) : 16;   // the cell just outside the warp's span, relative to this thread's 16 bytes
-        // level 1 (intermediate state): rows ry0-1 .. ry0+RT ; level 2 (final state): rows ry0 .. ry0+RT-1
-        T c1[D2_RT + 2][VX], q1[D2_RT + 2][VX], c2[D2_RT][VX], q2[D2_RT][VX];
-        T c1e[D2_RT], q1e[D2_RT];                      // level-1 state of the end lanes' outside cell
-#pragma unroll
-        for (int r = 0; r < D2_RT + 2; r++)
-#pragma unroll
-            for (int v = 0; v < VX; v++) { c1[r][v] = T(0); q1[r][v] = T(0); }
+        const bool rim = (wx == 0 && lane == 0) || (wx == D2_WX - 1 && lane == 31);   // computes the rim column next to the tile
+        const int xe = lane == 0 ? -(int)sizeof(T) : 16;   // the rim cell, relative to this thread's 16 bytes
+        const bool lvl2 = wy < D2_WY - 1;
+        T c1[D2_RT][VX], q1[D2_RT][VX], c2[D2_RT][VX], q2[D2_RT][VX];
+        T c1e[D2_RT], q1e[D2_RT];                      // level-1 state of the rim cells
 #pragma unroll
         for (int r = 0; r < D2_RT; r++) {
             c1e[r] = T(0); q1e[r] = T(0);
 #pragma unroll
-            for (int v = 0; v < VX; v++) { c2[r][v] = T(0); q2[r][v] = T(0); }
+            for (int v = 0; v < VX; v++) { c1[r][v] = T(0); q1[r][v] = T(0); c2[r][v] = T(0); q2[r][v] = T(0); }
         }
-        T* __restrict__ dbase = p.dst + (long long)(y0 + ry0) * p.p1 + gx;
+        T* __restrict__ dbase = p.dst + (long long)(y0 + r1) * p.p1 + gx;
         for (int i = 0; i < nsrc; i++, k++) {
             const int slot = k % D2_STAGES;
             mbar_wait(&full[slot], (k / D2_STAGES) & 1);
-            // this thread's 16 bytes in shared-memory row 0; tile row t lives in shared-memory row t + 2
+            // this thread's 16 bytes in shared-memory row 0; tile row t lives in source row t + 2 and intermediate row t + 1
             const unsigned char* sb_ = ring + slot * D2_STAGE + D2_LEFT + xtb;
-            // source rows ry0-2 .. ry0+RT+1  (shared-memory rows ry0 .. ry0+RT+3)
-            T rowv[D2_RT + 4][VX];
+            unsigned char* mb_ = mbuf + (k & 1) * D2_MSTAGE + D2_LEFT + xtb;
+            // ---- level 1: source plane s completes intermediate plane s-1 on tile rows r1-1, r1 ----
+            T rowv[D2_RT + 2][VX];                     // source tile rows r1-2 .. r1+1 = source rows r1 .. r1+3
 #pragma unroll
-            for (int q = 0; q < D2_RT + 4; q++) {
-                const typename D2Vec<T>::type w = *reinterpret_cast<const typename D2Vec<T>::type*>(sb_ + (ry0 + q) * D2_ROWB);
-                if constexpr (VX == 4) { rowv[q][0] = w.x; rowv[q][1] = w.y; rowv[q][2] = w.z; rowv[q][3] = w.w; }
-                else { rowv[q][0] = w.x; rowv[q][1] = w.y; }
-            }
-            // ---- level 1: the plane that arrived (source plane s) completes intermediate plane s-1 ----
-            T mid[D2_RT + 2][VX];
+            for (int q = 0; q < D2_RT + 2; q++) d2_lds<T, VX>(rowv[q], sb_ + (r1 + q) * D2_ROWB);
+            T mid[D2_RT][VX], mide[D2_RT];
 #pragma unroll
-            for (int j = 0; j < D2_RT + 2; j++) {      // intermediate row ry0-1+j, its source centre row is rowv[j+1]
-                const unsigned char* t = sb_ + (ry0 + j + 1) * D2_ROWB;
+            for (int j = 0; j < D2_RT; j++) {
+                const unsigned char* t = sb_ + (r1 + j + 1) * D2_ROWB;   // source centre row of intermediate tile row r1-1+j
                 T l_ = __shfl_up_sync(0xffffffffu, rowv[j + 1][VX - 1], 1);
                 T r_ = __shfl_down_sync(0xffffffffu, rowv[j + 1][0], 1);
                 if (lane == 0) l_ = *reinterpret_cast<const T*>(t - sizeof(T));
                 if (lane == 31) r_ = *reinterpret_cast<const T*>(t + 16);
-#pragma unroll
-                for (int v = 0; v < VX; v++) {
-                    const T c = rowv[j + 1][v];
-                    const T cc = c1[j][v];
-                    mid[j][v] = d2_update(add_rn(q1[j][v], c), cc, p.alpha);
-                    const T xm = v == 0 ? l_ : rowv[j + 1][v == 0 ? 0 : v - 1];
-                    const T xp = v == VX - 1 ? r_ : rowv[j + 1][v == VX - 1 ? v : v + 1];
-                    T a = add_rn(cc, rowv[j][v]);
-                    a = add_rn(a, xm);
-                    a = add_rn(a, xp);
-                    a = add_rn(a, rowv[j + 2][v]);
-                    q1[j][v] = a;
-                    c1[j][v] = c;
-                }
+                d2_plane<T, VX>(mid[j], c1[j], q1[j], rowv[j + 1], rowv[j], rowv[j + 2], l_, r_, p.alpha);
+                mide[j] = T(0);
             }
-            // the intermediate cell just outside the span (left of lane 0, right of lane 31), final rows only
-            T mide[D2_RT];
+            if (rim) {
 #pragma unroll
-            for (int r = 0; r < D2_RT; r++) mide[r] = T(0);
-            if (endlane) {
-#pragma unroll
-                for (int r = 0; r < D2_RT; r++) {
-                    const unsigned char* t = sb_ + (ry0 + r + 2) * D2_ROWB + xe;
+                for (int j = 0; j < D2_RT; j++) {
+                    const unsigned char* t = sb_ + (r1 + j + 1) * D2_ROWB + xe;
                     const T c = *reinterpret_cast<const T*>(t);
-                    const T cc = c1e[r];
-                    mide[r] = d2_update(add_rn(q1e[r], c), cc, p.alpha);
+                    const T cc = c1e[j];
+                    mide[j] = d2_update(add_rn(q1e[j], c), cc, p.alpha);
                     T a = add_rn(cc, *reinterpret_cast<const T*>(t - D2_ROWB));
                     a = add_rn(a, *reinterpret_cast<const T*>(t - sizeof(T)));
                     a = add_rn(a, *reinterpret_cast<const T*>(t + sizeof(T)));
                     a = add_rn(a, *reinterpret_cast<const T*>(t + D2_ROWB));
-                    q1e[r] = a;
-                    c1e[r] = c;
-                }
-            }
-            // ---- level 2: intermediate plane m = s-1 completes final plane m-1 = s-2 ----
-            const int zo = z0 - 4 + i;
-            const bool store = i >= 4;
-#pragma unroll
-            for (int r = 0; r < D2_RT; r++) {          // final row ry0+r, its intermediate centre row is mid[r+1]
-                T l_ = __shfl_up_sync(0xffffffffu, mid[r + 1][VX - 1], 1);
-                T r_ = __shfl_down_sync(0xffffffffu, mid[r + 1][0], 1);
-                if (lane == 0) l_ = mide[r];
-                if (lane == 31) r_ = mide[r];
-                T out[VX];
-#pragma unroll
-                for (int v = 0; v < VX; v++) {
-                    const T c = mid[r + 1][v];
-                    const T cc = c2[r][v];
-                    out[v] = d2_update(add_rn(q2[r][v], c), cc, p.alpha);
-                    const T xm = v == 0 ? l_ : mid[r + 1][v == 0 ? 0 : v - 1];
-                    const T xp = v == VX - 1 ? r_ : mid[r + 1][v == VX - 1 ? v : v + 1];
-                    T a = add_rn(cc, mid[r][v]);
-                    a = add_rn(a, xm);
-                    a = add_rn(a, xp);
-                    a = add_rn(a, mid[r + 2][v]);
-                    q2[r][v] = a;
-                    c2[r][v] = c;
-                }
-                if (store && xact && y0 + ry0 + r < p.Y && ry0 + r < p.ty) {
-                    T* d = dbase + (long long)zo * p.p2 + (long long)r * p.p1;
-                    if constexpr (VX == 4) *reinterpret_cast<float4*>(d) = make_float4(out[0], out[1], out[2], out[3]);
-                    else *reinterpret_cast<double2*>(d) = make_double2(out[0], out[1]);
+                    q1e[j] = a;
+                    c1e[j] = c;
                 }
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[slot]);
+            if (lane == 0) mbar_arrive(&empty[slot]);   // every read of the source stage is done
+#pragma unroll
+            for (int j = 0; j < D2_RT; j++) {
+                d2_st<T, VX>(mb_ + (r1 + j) * D2_ROWB, mid[j]);
+                if (rim) *reinterpret_cast<T*>(mb_ + (r1 + j) * D2_ROWB + xe) = mide[j];
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(D2_WARPS * 32) : "memory");
+            // ---- level 2: intermediate plane m = s-1 completes final plane m-1 = s-2 on tile rows r1, r1+1 ----
+            if (lvl2) {
+                T m2[VX], m3[VX];                       // intermediate tile rows r1+1, r1+2 (owned by the warp below)
+                d2_lds<T, VX>(m2, mb_ + (r1 + 2) * D2_ROWB);
+                d2_lds<T, VX>(m3, mb_ + (r1 + 3) * D2_ROWB);
+                const int zo = z0 - 4 + i;
+                const bool store = i >= 4;
+#pragma unroll
+                for (int r = 0; r < D2_RT; r++) {      // final tile row r1+r: centre = intermediate row r1+r+1
+                    const T(&ym)[VX] = r == 0 ? mid[0] : mid[1];
+                    const T(&cc)[VX] = r == 0 ? mid[1] : m2;
+                    const T(&yp)[VX] = r == 0 ? m2 : m3;
+                    const unsigned char* t = mb_ + (r1 + r + 1) * D2_ROWB;
+                    T l_ = __shfl_up_sync(0xffffffffu, cc[VX - 1], 1);
+                    T r_ = __shfl_down_sync(0xffffffffu, cc[0], 1);
+                    if (lane == 0) l_ = *reinterpret_cast<const T*>(t - sizeof(T));
+                    if (lane == 31) r_ = *reinterpret_cast<const T*>(t + 16);
+                    T out[VX];
+                    d2_plane<T, VX>(out, c2[r], q2[r], cc, ym, yp, l_, r_, p.alpha);
+                    if (store && xact && y0 + r1 + r < p.Y && r1 + r < p.ty)
+                        d2_st<T, VX>(dbase + (long long)zo * p.p2 + (long long)r * p.p1, out);
+                }
+            }
         }
     }
 }
@@ -256,7 +276,7 @@ template <typename T> static int d2_launch(D2Params<T>& p, cudaStream_t st) {
     p.nzruns = best;
     const long long ntasks = (long long)p.ntx * p.nty * p.nzruns;
     const long long grid = std::min<long long>(ctas, ntasks);
-    stream3d2_kernel<T><<<(unsigned)grid, (D2_WARPS + 1) * 32, D2_SMEM, st>>>(p);
+    stream3d2_kernel<T><<<(unsigned)grid, D2_THREADS, D2_SMEM, st>>>(p);
     SB_LAUNCH_CHECK();
     return SB200_OK;
 }

@@ -9,12 +9,13 @@ import sys
 
 import numpy as np
 
-WX, WY, RT = 2, 7, 2
+WX, WY, RT = 2, 8, 2
 WARPS = WX * WY
-TXB, TY, LEFT = WX * 512, WY * RT, 128
+TXB, TY, LEFT = WX * 512, (WY - 1) * RT, 128
 ROWB = LEFT + TXB + 128
 ROWS = TY + 4
-STAGES = 8
+MROWS = TY + 2
+STAGES = 6
 
 
 def wrap(r, n):
@@ -74,6 +75,7 @@ def model(src, alpha, z_lo, zn, wrap_z, ctas=3, force_nz=None, force_ty=None):
     lanes = np.arange(32)
     for block in range(grid):
         ring = np.full((STAGES, ROWS, ROWB), 0xFF, dtype=np.uint8)  # all-ones bytes = NaN
+        mbuf = np.full((2, MROWS, ROWB), 0xFF, dtype=np.uint8)
         k = 0
         for task in range(block, ntasks, grid):
             tile, zrun = task % ntiles, task // ntiles
@@ -85,12 +87,13 @@ def model(src, alpha, z_lo, zn, wrap_z, ctas=3, force_nz=None, force_ty=None):
             # consumer state per warp
             st = {}
             for w in range(WARPS):
-                st[w] = dict(c1=np.zeros((RT + 2, VX, 32), T), q1=np.zeros((RT + 2, VX, 32), T), c2=np.zeros((RT, VX, 32), T),
+                st[w] = dict(c1=np.zeros((RT, VX, 32), T), q1=np.zeros((RT, VX, 32), T), c2=np.zeros((RT, VX, 32), T),
                              q2=np.zeros((RT, VX, 32), T), c1e=np.zeros((RT, 32), T), q1e=np.zeros((RT, 32), T))
             for i in range(nsrc):
                 slot = k % STAGES
+                par = k & 1
                 k += 1
-                # ---- producer ----
+                # ---- producers (lane j of producer w copies row 2j+w) ----
                 ring[slot] = 0xFF
                 l_in, r_in = x0b > 0, x0b + wbytes < Xb
                 mstart = x0b - (16 if l_in else 0)
@@ -100,99 +103,121 @@ def model(src, alpha, z_lo, zn, wrap_z, ctas=3, force_nz=None, force_ty=None):
                 if wrap_z:
                     zl = wrap(zl, Z)
                 assert 0 <= zl < Z
-                for lane in range(32):
-                    if lane < ty + 4:
-                        y = y0 - 2 + lane
-                        if y <= Y + 1:
-                            g = flat[zl, wrap(y, Y)]
-                            ring[slot, lane, mdst:mdst + mlen] = g[mstart:mstart + mlen]
-                            if not l_in:
-                                ring[slot, lane, LEFT - 16:LEFT] = g[Xb - 16:Xb]
-                            if not r_in:
-                                ring[slot, lane, LEFT + wbytes:LEFT + wbytes + 16] = g[0:16]
-                # ---- consumers ----
-                for w in range(WARPS):
-                    S = st[w]
+                copied = 0
+                for pw in range(2):
+                    for lane in range(32):
+                        row = 2 * lane + pw
+                        if row < ty + 4:
+                            y = y0 - 2 + row
+                            if y <= Y + 1:
+                                g = flat[zl, wrap(y, Y)]
+                                ring[slot, row, mdst:mdst + mlen] = g[mstart:mstart + mlen]
+                                if not l_in:
+                                    ring[slot, row, LEFT - 16:LEFT] = g[Xb - 16:Xb]
+                                if not r_in:
+                                    ring[slot, row, LEFT + wbytes:LEFT + wbytes + 16] = g[0:16]
+                                copied += 1
+                assert copied == min(ty + 4, Y + 4 - y0), "expect_tx row count"
+                mbuf[par] = 0xFF
+
+                def geom(w):
                     wx, wy = w % WX, w // WX
-                    xtb = (wx * 32 + lanes) * 16
-                    ry0 = wy * RT
-                    xact = xtb < wbytes
-                    gx = (x0b + xtb) // es
+                    return wx, wy, (wx * 32 + lanes) * 16, wy * RT
 
-                    def lds_vec(row):      # [VX, 32]
-                        out = np.empty((VX, 32), T)
-                        for l in range(32):
-                            o = LEFT + xtb[l]
-                            out[:, l] = ring[slot, row, o:o + 16].view(T)
-                        return out
+                def lds_vec(buf, row, xtb):      # [VX, 32]
+                    out = np.empty((VX, 32), T)
+                    for l in range(32):
+                        o = LEFT + xtb[l]
+                        out[:, l] = buf[row, o:o + 16].view(T)
+                    return out
 
-                    def lds(row, off):     # per-lane scalar at byte offset `off[l]` relative to the thread's 16 bytes
-                        out = np.empty(32, T)
-                        for l in range(32):
-                            o = LEFT + xtb[l] + off[l]
-                            out[l] = ring[slot, row, o:o + es].view(T)[0]
-                        return out
+                def lds(buf, row, xtb, off):     # per-lane scalar at byte offset off[l] relative to the thread's 16 bytes
+                    out = np.empty(32, T)
+                    for l in range(32):
+                        o = LEFT + xtb[l] + off[l]
+                        out[l] = buf[row, o:o + es].view(T)[0]
+                    return out
 
-                    rowv = [lds_vec(ry0 + q) for q in range(RT + 4)]
-                    mid = np.empty((RT + 2, VX, 32), T)
-                    with np.errstate(invalid="ignore", over="ignore"):
-                        for j in range(RT + 2):
-                            row = ry0 + j + 1
+                def plane(cprev, part, c, ym, yp, l_, r_):
+                    done = np.empty((VX, 32), T)
+                    for v in range(VX):
+                        cc = cprev[v].copy()
+                        done[v] = update((part[v] + c[v]).astype(T), cc, alpha, T)
+                        xm = l_ if v == 0 else c[v - 1]
+                        xp = r_ if v == VX - 1 else c[v + 1]
+                        a = (cc + ym[v]).astype(T)
+                        a = (a + xm).astype(T)
+                        a = (a + xp).astype(T)
+                        a = (a + yp[v]).astype(T)
+                        part[v] = a
+                        cprev[v] = c[v].copy()
+                    return done
+
+                mids = {}
+                with np.errstate(invalid="ignore", over="ignore"):
+                    # ---- level 1 (all warps), then the named barrier ----
+                    for w in range(WARPS):
+                        S = st[w]
+                        wx, wy, xtb, r1 = geom(w)
+                        src_ = ring[slot]
+                        rowv = [lds_vec(src_, r1 + q, xtb) for q in range(RT + 2)]
+                        mid = np.empty((RT, VX, 32), T)
+                        for j in range(RT):
+                            row = r1 + j + 1
                             l_ = np.concatenate([rowv[j + 1][VX - 1][:1], rowv[j + 1][VX - 1][:-1]])
                             r_ = np.concatenate([rowv[j + 1][0][1:], rowv[j + 1][0][-1:]])
-                            l_[0] = lds(row, np.full(32, -es))[0]
-                            r_[31] = lds(row, np.full(32, 16))[31]
-                            for v in range(VX):
-                                c = rowv[j + 1][v]
-                                cc = S["c1"][j, v]
-                                mid[j, v] = update((S["q1"][j, v] + c).astype(T), cc, alpha, T)
-                                xm = l_ if v == 0 else rowv[j + 1][v - 1]
-                                xp = r_ if v == VX - 1 else rowv[j + 1][v + 1]
-                                a = (cc + rowv[j][v]).astype(T)
-                                a = (a + xm).astype(T)
-                                a = (a + xp).astype(T)
-                                a = (a + rowv[j + 2][v]).astype(T)
-                                S["q1"][j, v] = a
-                                S["c1"][j, v] = c.copy()
-                        mide = np.zeros((RT, 32), T)
+                            l_[0] = lds(src_, row, xtb, np.full(32, -es))[0]
+                            r_[31] = lds(src_, row, xtb, np.full(32, 16))[31]
+                            mid[j] = plane(S["c1"][j], S["q1"][j], rowv[j + 1], rowv[j], rowv[j + 2], l_, r_)
+                        rim = ((lanes == 0) & (wx == 0)) | ((lanes == 31) & (wx == WX - 1))
                         xe = np.where(lanes == 0, -es, 16)
+                        for j in range(RT):
+                            row = r1 + j + 1
+                            c = lds(src_, row, xtb, xe)
+                            cc = S["c1e"][j]
+                            m = update((S["q1e"][j] + c).astype(T), cc, alpha, T)
+                            a = (cc + lds(src_, row - 1, xtb, xe)).astype(T)
+                            a = (a + lds(src_, row, xtb, xe - es)).astype(T)
+                            a = (a + lds(src_, row, xtb, xe + es)).astype(T)
+                            a = (a + lds(src_, row + 1, xtb, xe)).astype(T)
+                            S["q1e"][j] = np.where(rim, a, S["q1e"][j])
+                            S["c1e"][j] = np.where(rim, c, S["c1e"][j])
+                            for l in range(32):
+                                o = LEFT + xtb[l]
+                                mbuf[par, r1 + j, o:o + 16] = np.ascontiguousarray(mid[j][:, l]).view(np.uint8)
+                            for l in range(32):
+                                if rim[l]:
+                                    o = LEFT + xtb[l] + xe[l]
+                                    mbuf[par, r1 + j, o:o + es] = np.array([m[l]], T).view(np.uint8)
+                        mids[w] = mid
+                    # ---- level 2 ----
+                    zo = z0 - 4 + i
+                    for w in range(WARPS):
+                        S = st[w]
+                        wx, wy, xtb, r1 = geom(w)
+                        if wy >= WY - 1:
+                            continue
+                        xact = xtb < wbytes
+                        gx = (x0b + xtb) // es
+                        M = mbuf[par]
+                        m2 = lds_vec(M, r1 + 2, xtb)
+                        m3 = lds_vec(M, r1 + 3, xtb)
+                        mid = mids[w]
                         for r in range(RT):
-                            row = ry0 + r + 2
-                            c = lds(row, xe)
-                            cc = S["c1e"][r]
-                            m = update((S["q1e"][r] + c).astype(T), cc, alpha, T)
-                            a = (cc + lds(row - 1, xe)).astype(T)
-                            a = (a + lds(row, xe - es)).astype(T)
-                            a = (a + lds(row, xe + es)).astype(T)
-                            a = (a + lds(row + 1, xe)).astype(T)
-                            end = (lanes == 0) | (lanes == 31)
-                            mide[r] = np.where(end, m, 0)
-                            S["q1e"][r] = np.where(end, a, S["q1e"][r])
-                            S["c1e"][r] = np.where(end, c, S["c1e"][r])
-                        zo = z0 - 4 + i
-                        for r in range(RT):
-                            l_ = np.concatenate([mid[r + 1, VX - 1][:1], mid[r + 1, VX - 1][:-1]])
-                            r_ = np.concatenate([mid[r + 1, 0][1:], mid[r + 1, 0][-1:]])
-                            l_[0] = mide[r][0]
-                            r_[31] = mide[r][31]
-                            out = np.empty((VX, 32), T)
-                            for v in range(VX):
-                                c = mid[r + 1, v]
-                                cc = S["c2"][r, v]
-                                out[v] = update((S["q2"][r, v] + c).astype(T), cc, alpha, T)
-                                xm = l_ if v == 0 else mid[r + 1, v - 1]
-                                xp = r_ if v == VX - 1 else mid[r + 1, v + 1]
-                                a = (cc + mid[r, v]).astype(T)
-                                a = (a + xm).astype(T)
-                                a = (a + xp).astype(T)
-                                a = (a + mid[r + 2, v]).astype(T)
-                                S["q2"][r, v] = a
-                                S["c2"][r, v] = c.copy()
-                            if i >= 4 and y0 + ry0 + r < Y and ry0 + r < ty:
+                            ym = mid[0] if r == 0 else mid[1]
+                            cc = mid[1] if r == 0 else m2
+                            yp = m2 if r == 0 else m3
+                            row = r1 + r + 1
+                            l_ = np.concatenate([cc[VX - 1][:1], cc[VX - 1][:-1]])
+                            r_ = np.concatenate([cc[0][1:], cc[0][-1:]])
+                            l_[0] = lds(M, row, xtb, np.full(32, -es))[0]
+                            r_[31] = lds(M, row, xtb, np.full(32, 16))[31]
+                            out = plane(S["c2"][r], S["q2"][r], cc, ym, yp, l_, r_)
+                            if i >= 4 and y0 + r1 + r < Y and r1 + r < ty:
                                 for l in range(32):
                                     if xact[l]:
-                                        assert np.isnan(dst[gx[l], y0 + ry0 + r, zo]), "cell stored twice"
-                                        dst[gx[l]:gx[l] + VX, y0 + ry0 + r, zo] = out[:, l]
+                                        assert np.isnan(dst[gx[l], y0 + r1 + r, zo]), "cell stored twice"
+                                        dst[gx[l]:gx[l] + VX, y0 + r1 + r, zo] = out[:, l]
     return dst, (ntx, nty, ty, nzruns)
 
 
