@@ -6,15 +6,18 @@
 // whole source rows (tile + 2 halo rows above / below, + 16 B halo left / right) through a ring of shared-memory
 // stages with cp.async.bulk. Per arriving source plane the 16 consumer warps
 //   level 1: complete one plane of the INTERMEDIATE state over the tile plus a one-cell rim (every cell once: a thread
-//            owns 16 bytes of x by 2 rows, the two rim columns are computed by the end lanes of the edge warps) and
-//            put it into a double-buffered shared-memory plane,
+//            owns 16 bytes of x by 2 rows; the two rim columns, 2 x 16 cells, are one lane each of a 17th "rim" warp)
+//            and put it into a double-buffered shared-memory plane,
 //   (one named barrier)
 //   level 2: complete one plane of the FINAL state from that plane (own rows from registers, the rows of the
 //            neighbouring warp from shared memory, x-neighbours by shuffle) and store it.
 // Both levels keep, per cell, the centre of the previous plane and the partial fold (((zm + ym) + xm) + xp) + yp in
 // registers, exactly like stream3d.cu does for one level, so a plane costs 9 flops per cell per level and nothing is
-// recomputed except the rim. (r01g measured the first version of this kernel, warp-private with a recomputed rim per
-// warp: 27 instructions per cell-update, issue-bound, 3 % SLOWER than two single sweeps.)
+// recomputed except the rim. The end lanes of a warp fetch the cells next to its span with predicated loads (inline
+// PTX: no divergent branch), ring cursor and dest pointer advance incrementally: 256 instructions per source plane and
+// warp, 144 of them the flops. (Measured: r01g, first version, warp-private with a rim recomputed per warp: 27
+// instructions per cell-update, issue-bound, 3 % SLOWER than two single sweeps; r01h, shared intermediate plane: 855
+// Gcell-updates/s against 635 for single sweeps.)
 // Fold order = the reference's offset order (src/stencils/vonneumman.jl:5-15), every operation rounded separately:
 // bit-identical to two single sweeps.
 //
@@ -32,7 +35,9 @@ namespace sb {
 constexpr int D2_WX = 2, D2_WY = 8;               // consumer warps across x and y
 constexpr int D2_WARPS = D2_WX * D2_WY;
 constexpr int D2_PRODUCERS = 2;                   // producer warps (even / odd rows of a stage)
-constexpr int D2_THREADS = (D2_WARPS + D2_PRODUCERS) * 32;
+constexpr int D2_RIMWARP = D2_WARPS;               // one more consumer warp: the rim columns of the intermediate plane, one cell per lane
+constexpr int D2_CONSUMERS = D2_WARPS + 1;
+constexpr int D2_THREADS = (D2_CONSUMERS + D2_PRODUCERS) * 32;
 constexpr int D2_TXB = D2_WX * 512;               // tile width in bytes
 constexpr int D2_RT = 2;                          // rows per thread and level
 constexpr int D2_TY = (D2_WY - 1) * D2_RT;        // final rows per tile (14: 1024 rows = 74 tiles = whole waves of 148);
@@ -81,6 +86,21 @@ template <typename T, int VX> __device__ __forceinline__ void d2_st(void* p, con
     else *reinterpret_cast<double2*>(p) = make_double2(v[0], v[1]);
 }
 
+// Predicated shared-memory accesses as single instructions (`@p LDS` / `@p STS`): the end lanes of a warp fetch the cells
+// next to its span without a divergent branch (ptxas turns `if (lane == 0) x = *p;` into BSSY / BRA / BSYNC sequences).
+__device__ __forceinline__ void d2_lds_if(float& v, const void* p, bool pred) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %2, 0;\n\t@q ld.shared.f32 %0, [%1];\n\t}" : "+f"(v) : "r"(smem_u32(p)), "r"((int)pred) : "memory");
+}
+__device__ __forceinline__ void d2_lds_if(double& v, const void* p, bool pred) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %2, 0;\n\t@q ld.shared.f64 %0, [%1];\n\t}" : "+d"(v) : "r"(smem_u32(p)), "r"((int)pred) : "memory");
+}
+__device__ __forceinline__ void d2_sts_if(void* p, float v, bool pred) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %2, 0;\n\t@q st.shared.f32 [%0], %1;\n\t}" ::"r"(smem_u32(p)), "f"(v), "r"((int)pred) : "memory");
+}
+__device__ __forceinline__ void d2_sts_if(void* p, double v, bool pred) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %2, 0;\n\t@q st.shared.f64 [%0], %1;\n\t}" ::"r"(smem_u32(p)), "d"(v), "r"((int)pred) : "memory");
+}
+
 // One plane of one level for one row of a thread: `c` = this plane's centre cells, ym / yp = the rows above / below,
 // l_ / r_ = the cells left of c[0] / right of c[VX-1]. Completes the previous plane (returned in `done`) and starts this one.
 template <typename T, int VX>
@@ -111,7 +131,7 @@ __global__ void __launch_bounds__(D2_THREADS, 1) stream3d2_kernel(const __grid_c
     unsigned char* mbuf = ring + D2_STAGES * D2_STAGE;   // two intermediate planes
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
-        for (int s = 0; s < D2_STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], D2_WARPS); }
+        for (int s = 0; s < D2_STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], D2_CONSUMERS); }
         mbar_fence_init();
     }
     __syncthreads();
@@ -126,9 +146,9 @@ __global__ void __launch_bounds__(D2_THREADS, 1) stream3d2_kernel(const __grid_c
         const int z0 = p.z_lo + (int)((long long)p.zn * zrun / p.nzruns);
         const int z1 = p.z_lo + (int)((long long)p.zn * (zrun + 1) / p.nzruns);
         const int nsrc = z1 - z0 + 4;  // source planes z0-2 .. z1+1
-        if (warp >= D2_WARPS) {
+        if (warp >= D2_CONSUMERS) {
             // ---------------- producer warps: lane j of producer w copies shared-memory row 2j+w = logical row y0-2+2j+w ----------------
-            const int pw = warp - D2_WARPS;
+            const int pw = warp - D2_CONSUMERS;
             const bool l_in = x0b > 0, r_in = x0b + wbytes < Xb;   // else: the Wrap image of the other array edge
             const int mstart = x0b - (l_in ? 16 : 0);
             const unsigned mlen = wbytes + (l_in ? 16 : 0) + (r_in ? 16 : 0);
@@ -160,91 +180,104 @@ __global__ void __launch_bounds__(D2_THREADS, 1) stream3d2_kernel(const __grid_c
             }
             continue;
         }
+        if (warp == D2_RIMWARP) {
+            // ---------------- rim warp: level 1 of the two columns next to the tile (x = -1 and x = tile width) ----------------
+            // lane = 16 * side + intermediate row; only level 2 of the tile's first / last cell of a row reads these cells
+            static_assert(D2_MROWS == 16, "one lane per rim cell");
+            const int mrow = lane & 15;
+            const int pos = (lane >> 4) ? D2_LEFT + D2_TXB : D2_LEFT - (int)sizeof(T);
+            T ce = T(0), qe = T(0);
+            int slot = k % D2_STAGES;
+            unsigned phase = (k / D2_STAGES) & 1;
+            for (int i = 0; i < nsrc; i++, k++) {
+                mbar_wait(&full[slot], phase);
+                const unsigned char* t = ring + slot * D2_STAGE + (mrow + 1) * D2_ROWB + pos;   // intermediate row m <-> source row m + 1
+                const T c = *reinterpret_cast<const T*>(t);
+                const T m = d2_update(add_rn(qe, c), ce, p.alpha);
+                T a = add_rn(ce, *reinterpret_cast<const T*>(t - D2_ROWB));
+                a = add_rn(a, *reinterpret_cast<const T*>(t - sizeof(T)));
+                a = add_rn(a, *reinterpret_cast<const T*>(t + sizeof(T)));
+                a = add_rn(a, *reinterpret_cast<const T*>(t + D2_ROWB));
+                qe = a;
+                ce = c;
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty[slot]);
+                *reinterpret_cast<T*>(mbuf + (k & 1) * D2_MSTAGE + mrow * D2_ROWB + pos) = m;
+                asm volatile("bar.sync 1, %0;" ::"n"(D2_CONSUMERS * 32) : "memory");
+                if (++slot == D2_STAGES) { slot = 0; phase ^= 1; }
+            }
+            continue;
+        }
         // ---------------- consumers ----------------
         const int wx = warp % D2_WX, wy = warp / D2_WX;
         const int xtb = (wx * 32 + lane) * 16;         // byte offset inside the tile
         const int r1 = wy * D2_RT;                     // level 1: tile rows r1-1, r1 (intermediate-plane rows r1, r1+1); level 2: tile rows r1, r1+1
         const bool xact = xtb < wbytes;
         const int gx = (x0b + xtb) / (int)sizeof(T);
-        const bool rim = (wx == 0 && lane == 0) || (wx == D2_WX - 1 && lane == 31);   // computes the rim column next to the tile
-        const int xe = lane == 0 ? -(int)sizeof(T) : 16;   // the rim cell, relative to this thread's 16 bytes
         const bool lvl2 = wy < D2_WY - 1;
         T c1[D2_RT][VX], q1[D2_RT][VX], c2[D2_RT][VX], q2[D2_RT][VX];
-        T c1e[D2_RT], q1e[D2_RT];                      // level-1 state of the rim cells
 #pragma unroll
         for (int r = 0; r < D2_RT; r++) {
-            c1e[r] = T(0); q1e[r] = T(0);
 #pragma unroll
             for (int v = 0; v < VX; v++) { c1[r][v] = T(0); q1[r][v] = T(0); c2[r][v] = T(0); q2[r][v] = T(0); }
         }
-        T* __restrict__ dbase = p.dst + (long long)(y0 + r1) * p.p1 + gx;
+        // per-thread constants of the march: store predicates, the running dest pointer (plane z0-4 at i = 0), ring cursor
+        bool rowok[D2_RT];
+#pragma unroll
+        for (int r = 0; r < D2_RT; r++) rowok[r] = lvl2 && xact && y0 + r1 + r < p.Y && r1 + r < p.ty;
+        T* __restrict__ dptr = p.dst + (long long)(y0 + r1) * p.p1 + gx + (long long)(z0 - 4) * p.p2;
+        const bool l0 = lane == 0, l31 = lane == 31;
+        int slot = k % D2_STAGES;
+        unsigned phase = (k / D2_STAGES) & 1;
         for (int i = 0; i < nsrc; i++, k++) {
-            const int slot = k % D2_STAGES;
-            mbar_wait(&full[slot], (k / D2_STAGES) & 1);
+            mbar_wait(&full[slot], phase);
             // this thread's 16 bytes in shared-memory row 0; tile row t lives in source row t + 2 and intermediate row t + 1
-            const unsigned char* sb_ = ring + slot * D2_STAGE + D2_LEFT + xtb;
-            unsigned char* mb_ = mbuf + (k & 1) * D2_MSTAGE + D2_LEFT + xtb;
+            const unsigned char* sb_ = ring + slot * D2_STAGE + D2_LEFT + xtb + r1 * D2_ROWB;   // source row r1
+            unsigned char* mb_ = mbuf + (k & 1) * D2_MSTAGE + D2_LEFT + xtb + r1 * D2_ROWB;    // intermediate row r1
             // ---- level 1: source plane s completes intermediate plane s-1 on tile rows r1-1, r1 ----
             T rowv[D2_RT + 2][VX];                     // source tile rows r1-2 .. r1+1 = source rows r1 .. r1+3
 #pragma unroll
-            for (int q = 0; q < D2_RT + 2; q++) d2_lds<T, VX>(rowv[q], sb_ + (r1 + q) * D2_ROWB);
-            T mid[D2_RT][VX], mide[D2_RT];
+            for (int q = 0; q < D2_RT + 2; q++) d2_lds<T, VX>(rowv[q], sb_ + q * D2_ROWB);
+            T mid[D2_RT][VX];
 #pragma unroll
             for (int j = 0; j < D2_RT; j++) {
-                const unsigned char* t = sb_ + (r1 + j + 1) * D2_ROWB;   // source centre row of intermediate tile row r1-1+j
+                const unsigned char* t = sb_ + (j + 1) * D2_ROWB;   // source centre row of intermediate tile row r1-1+j
                 T l_ = __shfl_up_sync(0xffffffffu, rowv[j + 1][VX - 1], 1);
                 T r_ = __shfl_down_sync(0xffffffffu, rowv[j + 1][0], 1);
-                if (lane == 0) l_ = *reinterpret_cast<const T*>(t - sizeof(T));
-                if (lane == 31) r_ = *reinterpret_cast<const T*>(t + 16);
+                d2_lds_if(l_, t - sizeof(T), l0);
+                d2_lds_if(r_, t + 16, l31);
                 d2_plane<T, VX>(mid[j], c1[j], q1[j], rowv[j + 1], rowv[j], rowv[j + 2], l_, r_, p.alpha);
-                mide[j] = T(0);
-            }
-            if (rim) {
-#pragma unroll
-                for (int j = 0; j < D2_RT; j++) {
-                    const unsigned char* t = sb_ + (r1 + j + 1) * D2_ROWB + xe;
-                    const T c = *reinterpret_cast<const T*>(t);
-                    const T cc = c1e[j];
-                    mide[j] = d2_update(add_rn(q1e[j], c), cc, p.alpha);
-                    T a = add_rn(cc, *reinterpret_cast<const T*>(t - D2_ROWB));
-                    a = add_rn(a, *reinterpret_cast<const T*>(t - sizeof(T)));
-                    a = add_rn(a, *reinterpret_cast<const T*>(t + sizeof(T)));
-                    a = add_rn(a, *reinterpret_cast<const T*>(t + D2_ROWB));
-                    q1e[j] = a;
-                    c1e[j] = c;
-                }
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[slot]);   // every read of the source stage is done
+            if (l0) mbar_arrive(&empty[slot]);          // every read of the source stage is done
 #pragma unroll
             for (int j = 0; j < D2_RT; j++) {
-                d2_st<T, VX>(mb_ + (r1 + j) * D2_ROWB, mid[j]);
-                if (rim) *reinterpret_cast<T*>(mb_ + (r1 + j) * D2_ROWB + xe) = mide[j];
+                d2_st<T, VX>(mb_ + j * D2_ROWB, mid[j]);
             }
-            asm volatile("bar.sync 1, %0;" ::"n"(D2_WARPS * 32) : "memory");
+            asm volatile("bar.sync 1, %0;" ::"n"(D2_CONSUMERS * 32) : "memory");
             // ---- level 2: intermediate plane m = s-1 completes final plane m-1 = s-2 on tile rows r1, r1+1 ----
             if (lvl2) {
                 T m2[VX], m3[VX];                       // intermediate tile rows r1+1, r1+2 (owned by the warp below)
-                d2_lds<T, VX>(m2, mb_ + (r1 + 2) * D2_ROWB);
-                d2_lds<T, VX>(m3, mb_ + (r1 + 3) * D2_ROWB);
-                const int zo = z0 - 4 + i;
+                d2_lds<T, VX>(m2, mb_ + 2 * D2_ROWB);
+                d2_lds<T, VX>(m3, mb_ + 3 * D2_ROWB);
                 const bool store = i >= 4;
 #pragma unroll
                 for (int r = 0; r < D2_RT; r++) {      // final tile row r1+r: centre = intermediate row r1+r+1
                     const T(&ym)[VX] = r == 0 ? mid[0] : mid[1];
                     const T(&cc)[VX] = r == 0 ? mid[1] : m2;
                     const T(&yp)[VX] = r == 0 ? m2 : m3;
-                    const unsigned char* t = mb_ + (r1 + r + 1) * D2_ROWB;
+                    const unsigned char* t = mb_ + (r + 1) * D2_ROWB;
                     T l_ = __shfl_up_sync(0xffffffffu, cc[VX - 1], 1);
                     T r_ = __shfl_down_sync(0xffffffffu, cc[0], 1);
-                    if (lane == 0) l_ = *reinterpret_cast<const T*>(t - sizeof(T));
-                    if (lane == 31) r_ = *reinterpret_cast<const T*>(t + 16);
+                    d2_lds_if(l_, t - sizeof(T), l0);
+                    d2_lds_if(r_, t + 16, l31);
                     T out[VX];
                     d2_plane<T, VX>(out, c2[r], q2[r], cc, ym, yp, l_, r_, p.alpha);
-                    if (store && xact && y0 + r1 + r < p.Y && r1 + r < p.ty)
-                        d2_st<T, VX>(dbase + (long long)zo * p.p2 + (long long)r * p.p1, out);
+                    if (store && rowok[r]) d2_st<T, VX>(dptr + (long long)r * p.p1, out);
                 }
             }
+            dptr += p.p2;
+            if (++slot == D2_STAGES) { slot = 0; phase ^= 1; }
         }
     }
 }
