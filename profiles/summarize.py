@@ -55,7 +55,7 @@ def main():
     rnd = sys.argv[1] if len(sys.argv) > 1 else "r01"
     out_dir = os.path.join(ROOT, "gpurun_out")
     summary = {}
-    for wl in ("life", "mean", "kernel", "circle", "positional", "scatter", "diffusion"):
+    for wl in ("life", "mean", "kernel", "circle", "positional", "scatter", "diffusion", "diffusion2"):
         rep = os.path.join(out_dir, f"{rnd}_{wl}.ncu-rep")
         if not os.path.exists(rep):
             continue
@@ -66,7 +66,11 @@ def main():
         k["dram_bytes_per_launch"] = (k.get("dram_read_MB", 0) + k.get("dram_write_MB", 0)) * 1e6
         summary[wl] = k
     json.dump(summary, open(os.path.join(ROOT, "profiles", f"{rnd}_ncu_summary.json"), "w"), indent=1)
-    json.dump(summary, open(os.path.join(ROOT, "profiles", "ncu_summary.json"), "w"), indent=1)
+    # profiles/ncu_summary.json (read by bench.py for `roofline.traffic`) keeps the latest capture of every workload
+    latest_path = os.path.join(ROOT, "profiles", "ncu_summary.json")
+    latest = json.load(open(latest_path)) if os.path.exists(latest_path) else {}
+    latest.update(summary)
+    json.dump(latest, open(latest_path, "w"), indent=1)
     with open(os.path.join(ROOT, "profiles", f"{rnd}_ncu_summary.md"), "w") as f:
         f.write(f"# ncu --set full summaries ({rnd}); one launch per workload, cold cache, serialised\n\n")
         f.write("| workload | kernel | duration µs | DRAM read MB | DRAM write MB | DRAM % of peak | regs | grid x block | warps active % | issue active % | L2 hit % |\n")

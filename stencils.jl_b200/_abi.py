@@ -11,7 +11,8 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libstencils_b200.so")
+# SB200_LIB: another build of the same library (A/B runs of kernel variants on the GPU box, tools/build_variant.sh)
+LIB_PATH = os.environ.get("SB200_LIB") or os.path.join(HERE, "lib", "libstencils_b200.so")
 
 # ---- enums (include/stencils_b200.h) ----
 OK, EINVAL, EUNSUPPORTED, ESIZE, ECUDA, ENOMEM = range(6)
@@ -26,7 +27,7 @@ FLAG_FORCE_GENERIC, FLAG_ZERO_DEST, FLAG_NO_TMA, FLAG_CELLS_01, FLAG_DOUBLE_STEP
 MAX_OFFSETS = 1024
 # default of SB200_DIFFUSION_DOUBLE_STEP (two diffusion steps per launch in iterated runs); must agree with
 # kDiffusionDoubleStepDefault in csrc/api.cu
-DIFFUSION_DOUBLE_STEP_DEFAULT = "0"
+DIFFUSION_DOUBLE_STEP_DEFAULT = "1"
 
 ELTYPE_OF_DTYPE = {
     np.dtype(np.bool_): BOOL, np.dtype(np.uint8): U8, np.dtype(np.int32): I32,

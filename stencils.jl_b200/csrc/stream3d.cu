@@ -18,6 +18,14 @@ namespace sb {
 
 constexpr int S3_WX = 2, S3_WY = 4;             // consumer warps across x and y
 constexpr int S3_WARPS = S3_WX * S3_WY;
+#ifndef SB200_S3_PRODUCERS
+#define SB200_S3_PRODUCERS 2
+#endif
+// producer warps (the rows of a stage dealt round-robin). One producer warp per CTA was the bottleneck: every bulk copy costs
+// ~14 issue slots of lane-by-lane serialisation (ELECT / R2UR / UBLKCP / BRA.U.ANY), 16-18 copies per plane. Measured on
+// 1024^3 Float32 diffusion (r01k): 1 producer 637, 2 producers 763 Gcell-updates/s (0.79 -> 0.94 of the HBM roofline).
+constexpr int S3_PRODUCERS = SB200_S3_PRODUCERS;
+constexpr int S3_THREADS = (S3_WARPS + S3_PRODUCERS) * 32;
 constexpr int S3_TXB = S3_WX * 512;             // tile width in bytes
 constexpr int S3_RT = 4;                        // rows per thread
 constexpr int S3_TY = S3_WY * S3_RT;            // tile height in rows
@@ -62,7 +70,7 @@ template <> struct S3Vec<double> { using type = double2; };
 
 // MIRROR: the fused ghost-plane push (S3Params::mirror) is compiled in only for the boundary sweeps of slab runs.
 template <typename T, int RED, bool MIRROR>
-__global__ void __launch_bounds__((S3_WARPS + 1) * 32) stream3d_kernel(const __grid_constant__ S3Params<T> p) {
+__global__ void __launch_bounds__(S3_THREADS) stream3d_kernel(const __grid_constant__ S3Params<T> p) {
     constexpr int VX = 16 / (int)sizeof(T);
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem);
@@ -85,8 +93,9 @@ __global__ void __launch_bounds__((S3_WARPS + 1) * 32) stream3d_kernel(const __g
         const int z0 = p.z_lo + (int)((long long)p.zn * zrun / p.nzruns);
         const int z1 = p.z_lo + (int)((long long)p.zn * (zrun + 1) / p.nzruns);
         const int nsrc = z1 - z0 + 2;  // source planes z0-1 .. z1
-        if (warp == S3_WARPS) {
-            // ---------------- producer warp: lane j copies row j of the plane ----------------
+        if (warp >= S3_WARPS) {
+            // ---------------- producer warps: lane j of producer w copies row P*j+w of the plane ----------------
+            const int pw = warp - S3_WARPS;
             // One bulk copy per row covers the tile plus the halo cells that are ordinary neighbours in the row; only
             // the wrapped halo of an array-edge tile needs its own (16-byte) copy.
             const bool l_in = x0b > 0, r_in = x0b + wbytes < Xb;
@@ -97,23 +106,28 @@ __global__ void __launch_bounds__((S3_WARPS + 1) * 32) stream3d_kernel(const __g
             const unsigned rowbytes = mlen + (l_wrap ? 16 : 0) + (r_wrap ? 16 : 0);
             // Lane j owns shared-memory row j = logical row y0-1+j (same mapping for every plane). Rows below the
             // halo row of a ragged last tile are never read.
-            long long yrow = -1;
+            long long yrow = -1, yany = -1;   // yany: row `lane` of the stage (every producer counts all rows for expect_tx)
             if (lane < p.ty + 2) {
                 const int y = y0 - 1 + lane;
+                if (y <= p.Y) yany = s3_map(y, p.Y, p.so1, p.bc1);
+            }
+            const unsigned nrows = __popc(__ballot_sync(0xffffffffu, yany >= 0));
+            const int srow_i = S3_PRODUCERS * lane + pw;
+            if (srow_i < p.ty + 2) {
+                const int y = y0 - 1 + srow_i;
                 if (y <= p.Y) yrow = s3_map(y, p.Y, p.so1, p.bc1);
             }
-            const unsigned nrows = __popc(__ballot_sync(0xffffffffu, yrow >= 0));
             for (int i = 0; i < nsrc; i++, k++) {
                 const int slot = k % S3_STAGES;
                 const long long zpl = s3_map(z0 - 1 + i, p.Z, p.so2, p.bc2);
                 if (lane == 0) {
                     mbar_wait(&empty[slot], ((k / S3_STAGES) & 1) ^ 1);
-                    mbar_arrive_expect_tx(&full[slot], zpl >= 0 ? nrows * rowbytes : 0u);
+                    if (pw == 0) mbar_arrive_expect_tx(&full[slot], zpl >= 0 ? nrows * rowbytes : 0u);
                 }
                 __syncwarp();
                 if (zpl >= 0 && yrow >= 0) {
                     const unsigned char* g = reinterpret_cast<const unsigned char*>(p.src + zpl * p.sp2 + yrow * p.sp1);
-                    unsigned char* srow = ring + slot * S3_STAGE + lane * S3_ROWB;
+                    unsigned char* srow = ring + slot * S3_STAGE + srow_i * S3_ROWB;
                     bulk_g2s(srow + mdst, g + mstart, mlen, &full[slot]);
                     if (l_wrap) bulk_g2s(srow + S3_LEFT - 16, g + Xb - 16, 16, &full[slot]);
                     if (r_wrap) bulk_g2s(srow + S3_LEFT + wbytes, g, 16, &full[slot]);
@@ -225,7 +239,7 @@ template <typename T, int RED, bool MIRROR> static int s3_launch_m(S3Params<T>& 
     if (dev != cfg_dev) {
         SB_CUDA(cudaFuncSetAttribute(stream3d_kernel<T, RED, MIRROR>, cudaFuncAttributeMaxDynamicSharedMemorySize, S3_SMEM));
         int per_sm = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, stream3d_kernel<T, RED, MIRROR>, (S3_WARPS + 1) * 32, S3_SMEM) != cudaSuccess || per_sm < 1)
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, stream3d_kernel<T, RED, MIRROR>, S3_THREADS, S3_SMEM) != cudaSuccess || per_sm < 1)
             per_sm = 1;
         ctas_per_sm = per_sm;
         cfg_dev = dev;
@@ -249,7 +263,7 @@ template <typename T, int RED, bool MIRROR> static int s3_launch_m(S3Params<T>& 
     p.nzruns = best;
     const long long ntiles = (long long)p.ntx * p.nty;
     const long long grid = std::min<long long>(ctas, ntiles * p.nzruns);
-    stream3d_kernel<T, RED, MIRROR><<<(unsigned)grid, (S3_WARPS + 1) * 32, S3_SMEM, st>>>(p);
+    stream3d_kernel<T, RED, MIRROR><<<(unsigned)grid, S3_THREADS, S3_SMEM, st>>>(p);
     SB_LAUNCH_CHECK();
     return SB200_OK;
 }

@@ -34,7 +34,16 @@ namespace sb {
 
 constexpr int D2_WX = 2, D2_WY = 8;               // consumer warps across x and y
 constexpr int D2_WARPS = D2_WX * D2_WY;
-constexpr int D2_PRODUCERS = 2;                   // producer warps (even / odd rows of a stage)
+#ifndef SB200_D2_PRODUCERS
+#define SB200_D2_PRODUCERS 3
+#endif
+#ifndef SB200_D2_STAGES
+#define SB200_D2_STAGES 6
+#endif
+// producer warps (the rows of a stage dealt round-robin). Measured on 1024^3 Float32 (r01j): 2 producers 935, 3 producers
+// 1092, 4 producers (register cap 80) 1073 Gcell-updates/s: with two, the consumers waited for data 23 % of the time
+// (each bulk copy costs ~14 issue slots of lane-by-lane serialisation: ELECT / R2UR / UBLKCP / BRA.U.ANY).
+constexpr int D2_PRODUCERS = SB200_D2_PRODUCERS;
 constexpr int D2_RIMWARP = D2_WARPS;               // one more consumer warp: the rim columns of the intermediate plane, one cell per lane
 constexpr int D2_CONSUMERS = D2_WARPS + 1;
 constexpr int D2_THREADS = (D2_CONSUMERS + D2_PRODUCERS) * 32;
@@ -46,7 +55,7 @@ constexpr int D2_LEFT = 128;                      // margin (halo at its end): g
 constexpr int D2_ROWB = D2_LEFT + D2_TXB + 128;   // shared-memory row: margin | tile | margin
 constexpr int D2_ROWS = D2_TY + 4;                // source rows of a stage: tile rows + two halo rows on each side
 constexpr int D2_STAGE = D2_ROWS * D2_ROWB;
-constexpr int D2_STAGES = 6;
+constexpr int D2_STAGES = SB200_D2_STAGES;
 constexpr int D2_MROWS = D2_TY + 2;               // intermediate plane: tile rows + one rim row on each side
 constexpr int D2_MSTAGE = D2_MROWS * D2_ROWB;
 constexpr int D2_SMEM = 128 + D2_STAGES * D2_STAGE + 2 * D2_MSTAGE;
@@ -147,7 +156,7 @@ __global__ void __launch_bounds__(D2_THREADS, 1) stream3d2_kernel(const __grid_c
         const int z1 = p.z_lo + (int)((long long)p.zn * (zrun + 1) / p.nzruns);
         const int nsrc = z1 - z0 + 4;  // source planes z0-2 .. z1+1
         if (warp >= D2_CONSUMERS) {
-            // ---------------- producer warps: lane j of producer w copies shared-memory row 2j+w = logical row y0-2+2j+w ----------------
+            // ---------------- producer warps: lane j of producer w copies shared-memory row P*j+w = logical row y0-2+P*j+w ----------------
             const int pw = warp - D2_CONSUMERS;
             const bool l_in = x0b > 0, r_in = x0b + wbytes < Xb;   // else: the Wrap image of the other array edge
             const int mstart = x0b - (l_in ? 16 : 0);

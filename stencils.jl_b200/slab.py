@@ -182,7 +182,7 @@ class SlabIterator:
         self.double_ok = (reducer == A.LIFE and t.is_cuda and compute is None and self.bc_split == A.WRAP and self.k >= 2 and
                           self.n_local >= 4 * self.G + 64 and os.environ.get("SB200_DOUBLE_STEP", "1") != "0")
         self.quad_ok = self.double_ok and self.k >= 4 and os.environ.get("SB200_QUAD_STEP", "1") != "0"
-        # two diffusion steps per launch (csrc/stream3d2.cu): same schedule, opt-in like in sb200_iterate
+        # two diffusion steps per launch (csrc/stream3d2.cu): same schedule; SB200_DIFFUSION_DOUBLE_STEP=0 turns it off
         if (reducer == A.DIFFUSION and t.is_cuda and compute is None and self.bc_split == A.WRAP and self.k >= 2 and
                 self.n_local >= 4 * self.G and os.environ.get("SB200_DIFFUSION_DOUBLE_STEP", A.DIFFUSION_DOUBLE_STEP_DEFAULT) != "0"):
             self.double_ok = True
