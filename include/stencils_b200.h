@@ -170,7 +170,9 @@ typedef struct sb200_desc {
 #define SB200_FLAG_QUAD_STEP 32   /* dest = f(f(f(f(src)))): four generations per launch (B3/S23 Life, axis 0 a multiple of 32
                                      cells, otherwise as SB200_FLAG_DOUBLE_STEP); the bit-sliced kernel */
 #define SB200_FLAG_DOUBLE_STEP 16 /* dest = f(f(src)): two sweeps fused in one launch, the intermediate state never touches
-                                     memory (LIFE, Moore(1), unpadded, Wrap on axis 0; else SB200_EUNSUPPORTED).
+                                     memory. LIFE: Moore(1), unpadded, Wrap on axis 0. DIFFUSION: VonNeumann(1,3), unpadded
+                                     Float32 / Float64, Wrap on axes 0 and 1, axis 2 Wrap or an output region two planes
+                                     inside the parent. Anything else: SB200_EUNSUPPORTED (never a silent single sweep).
                                      sb200_iterate uses it by itself where it applies. */
 
 /* ---- library ---- */

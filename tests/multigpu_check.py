@@ -2,7 +2,7 @@
 """N-GPU == 1-GPU bitwise check for the slab iterator (run under torchrun on a multi-GPU box):
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
-        tests/multigpu_check.py
+        tests/multigpu_check.py [--quick]
 
 Every rank also runs the whole domain on its own GPU through sb200_iterate and compares its slab bit for bit.
 """
@@ -86,6 +86,8 @@ def main():
         ("diffusion", (128, 100, 40 * world + 1), np.float32, (A.REMOVE, A.WRAP, A.REFLECT), 2, 7),
     ]
     cases = [c + (ex,) for ex in ("p2p-fused", "p2p", "nccl") for c in cases]
+    if "--quick" in sys.argv:   # one Life and one diffusion ring over fused peer stores, then the one-shot sweeps
+        cases = [cases[0], cases[2], cases[3]]
     for name, shape, dt, bcs, ghost, nsteps, ex in cases:
         full = synth_torch(shape, dt, 0xABC, dev)                      # logical (column-major) view
         if name == "life":
