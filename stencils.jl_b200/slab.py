@@ -432,7 +432,12 @@ def bench_weak(workload, spec, steps, warmup, synth=None):
     exchange, fused, it_overlap = it.exchange, it.fused, it.overlap
     dist.barrier()
     it.close()
-    if exchange == "p2p" and fused and it_overlap:
+    kernel = lib.sb200_last_kernel().decode()   # the kernel of the timed region (iterated runs may fuse steps)
+    if exchange == "p2p" and it_overlap and "stream3d2" in kernel:
+        how = ("boundary planes computed first (two-step sweeps), copied into the neighbour's landing slot by a stream-ordered "
+               "peer copy over NVLink inside the call (stream3d2_kernel has no fused store yet), sb200_signal_flag, acquire wait "
+               "+ ghost copy on a side stream, overlapped with the interior update of the last sweep of each cycle")
+    elif exchange == "p2p" and fused and it_overlap:
         how = ("peer-memory stores over NVLink fused into the boundary sweeps (sb200_desc.mirror_*, sb200_signal_flag), acquire wait "
                "+ ghost copy on a side stream, overlapped with the interior update of the last sweep of each cycle")
     elif exchange == "p2p":
