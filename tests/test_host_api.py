@@ -156,3 +156,40 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in txt.lower().replace("not a cpu fallback", ""), os.path.join(dirpath, f)
+
+
+def test_scatter_slab_boundaries_are_pass_aligned():
+    """split_columns_for_scatter: contiguous cover of the columns, every interior boundary a multiple of the pass stride
+    2R+1 (so a column's pass number in _scatterstencil_cpu!, src/scatterstencil.jl:53-58, is the same in local and global
+    numbering), remainder units to the first ranks."""
+    from stencils_b200.slab import split_columns_for_scatter
+    for ncols in (1, 5, 33, 37, 45, 1000, 32768):
+        for R in (1, 2, 3, 4):
+            S = 2 * R + 1
+            for world in (1, 2, 3, 8):
+                parts = [split_columns_for_scatter(ncols, world, r, R) for r in range(world)]
+                assert parts[0][0] == 0 and parts[-1][1] == ncols
+                for (lo, hi), (lo2, _) in zip(parts, parts[1:]):
+                    assert hi == lo2 and lo <= hi
+                    assert hi % S == 0 or hi == ncols
+                units = -(-ncols // S)
+                assert max(hi - lo for lo, hi in parts) <= -(-units // world) * S   # remainder units go to the first ranks
+
+
+def test_slab_scatter_rejects_what_it_cannot_do_exactly():
+    """Wrap on the split axis with a column count that is not a multiple of 2R+1 has no defined pass order at the seam
+    (SURVEY Appendix A): ArgumentError, not an approximate result."""
+    import numpy as np
+    import torch
+    from stencils_b200 import _abi as A
+    from stencils_b200.slab import slab_gather, slab_scatter
+    src = torch.zeros((37, 16), dtype=torch.float32)
+    with pytest.raises(A.ArgumentError):
+        slab_scatter(src, src.clone(), ncols_global=37, offsets=[(0, 1), (1, 0)], radius=1, weights=np.ones(2, np.float32),
+                     boundary=(A.WRAP, A.WRAP), eltype=A.F32, rank=0, world=1, compute=lambda *a: None)
+    with pytest.raises(A.ArgumentError):
+        slab_scatter(src, torch.zeros((36, 16)), ncols_global=36, offsets=[(0, 1)], radius=1, weights=np.ones(1, np.float32),
+                     boundary=(A.REMOVE, A.REMOVE), eltype=A.F32, rank=0, world=1, compute=lambda *a: None)
+    with pytest.raises(A.ArgumentError):   # mean of UInt8 changes the element type
+        slab_gather(torch.zeros((8, 8), dtype=torch.uint8), offsets=[(0, 1)], radius=1, reducer=A.MEAN, boundary=(A.WRAP, A.WRAP),
+                    eltype=A.U8, rank=0, world=1, compute=lambda *a: None)
