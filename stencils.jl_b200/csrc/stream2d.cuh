@@ -22,6 +22,16 @@
 namespace sb {
 
 constexpr int S2_WARPS = 8;
+// EXPERIMENT (default 1 = the measured kernels; not yet run on a GPU with another value): producer warps of the element-granular
+// cp.async mode (Halo rings / unaligned rows, mean F64 + Halo{:out} 0.74 of peak). One warp issues 16-32 LDGSTS per lane and
+// row; the 3-D kernels were producer-bound with far less (lesson 3). Each producer warp copies every
+// S2_PRODUCERS-th group of 32 elements of a row; the bulk-copy mode keeps using one lane of the first producer warp.
+#ifndef SB200_S2_PRODUCERS
+#define SB200_S2_PRODUCERS 1
+#endif
+constexpr int S2_PRODUCERS = SB200_S2_PRODUCERS;
+constexpr int S2_THREADS = (S2_WARPS + S2_PRODUCERS) * 32;
+__device__ __forceinline__ bool s2_is_producer(int warp) { return S2_PRODUCERS == 1 ? warp == S2_WARPS : warp >= S2_WARPS; }
 constexpr int S2_BXB = S2_WARPS * 32 * 16;  // strip width in bytes
 
 // 2-D shape predicates (same as shape_keep in api.cu for N = 2), usable at compile time.
@@ -293,7 +303,7 @@ template <typename T, int SHAPE, int R, int RED, int J> struct S2Rows {
 };
 
 template <typename T, int SHAPE, int R, int RED>
-__global__ void __launch_bounds__((S2_WARPS + 1) * 32, 2) stream2d_kernel(const __grid_constant__ S2Params<T> p) {
+__global__ void __launch_bounds__(S2_THREADS, 2) stream2d_kernel(const __grid_constant__ S2Params<T> p) {
     using C = S2Cfg<T, R>;
     constexpr int VX = C::VX, P = C::P, CH = C::CH;
     extern __shared__ __align__(128) unsigned char smem[];
@@ -302,7 +312,7 @@ __global__ void __launch_bounds__((S2_WARPS + 1) * 32, 2) stream2d_kernel(const 
     unsigned char* ring = smem + 128;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
-        for (int s = 0; s < C::STAGES; s++) { mbar_init(&full[s], p.cpasync ? 32 : 1); mbar_init(&empty[s], S2_WARPS); }
+        for (int s = 0; s < C::STAGES; s++) { mbar_init(&full[s], p.cpasync ? 32 * S2_PRODUCERS : 1); mbar_init(&empty[s], S2_WARPS); }
         mbar_fence_init();
     }
     __syncthreads();
@@ -318,7 +328,7 @@ __global__ void __launch_bounds__((S2_WARPS + 1) * 32, 2) stream2d_kernel(const 
         const int nout = y1 - y0;
         const int nsrc = nout + 2 * R;  // source rows y0-R .. y1-1+R
         const int nchunks = (nsrc + CH - 1) / CH;
-        if (warp == S2_WARPS && p.cpasync) {
+        if (s2_is_producer(warp) && p.cpasync) {
             // ---------------- producer, element-granular (same shared-memory layout: strip cell 0 at LEFT) ----------------
             const int xs = x0b / (int)sizeof(T), wc = wbytes / (int)sizeof(T);
             const bool ring0 = p.soff0 > 0;                       // axis 0 has a ring: every neighbour is a cell of the parent
@@ -335,7 +345,8 @@ __global__ void __launch_bounds__((S2_WARPS + 1) * 32, 2) stream2d_kernel(const 
                     if (prow < 0) continue;
                     const T* g = p.src + prow * p.spitch + p.soff0;                        // logical cell 0 of the row
                     T* srow = reinterpret_cast<T*>(sbase + j * C::ROWB + C::LEFT);          // strip cell 0
-                    for (int e = lane - lA; e < wc + rA; e += 32) cp_async_elem(srow + e, g + xs + e);
+                    for (int e = lane - lA + 32 * (warp - S2_WARPS); e < wc + rA; e += 32 * S2_PRODUCERS) cp_async_elem(srow + e, g + xs + e);
+                    if (S2_PRODUCERS > 1 && warp != S2_WARPS) continue;   // the wrapped halo cells: first producer warp only
                     if (wrap0 && lA == 0)
                         for (int e = lane; e < R; e += 32) cp_async_elem(srow - R + e, g + p.W - R + e);
                     if (wrap0 && rA < R)
@@ -345,9 +356,9 @@ __global__ void __launch_bounds__((S2_WARPS + 1) * 32, 2) stream2d_kernel(const 
             }
             continue;
         }
-        if (warp == S2_WARPS) {
+        if (s2_is_producer(warp)) {
             // ---------------- producer ----------------
-            if (lane == 0) {
+            if (lane == 0 && (S2_PRODUCERS == 1 || warp == S2_WARPS)) {
                 // One bulk copy per row covers the strip plus the halo cells that are ordinary neighbours in the row
                 // (a narrow last strip may end inside the right halo); only the wrapped halo of an array-edge strip
                 // needs its own copy.
@@ -429,7 +440,7 @@ int s2_launch(const S2Params<T>& p0, cudaStream_t st) {
     if (dev != cfg_dev) {
         SB_CUDA(cudaFuncSetAttribute(stream2d_kernel<T, SHAPE, R, RED>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
         int per_sm = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, stream2d_kernel<T, SHAPE, R, RED>, (S2_WARPS + 1) * 32, C::SMEM) != cudaSuccess || per_sm < 1)
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, stream2d_kernel<T, SHAPE, R, RED>, S2_THREADS, C::SMEM) != cudaSuccess || per_sm < 1)
             per_sm = 1;
         ctas_per_sm = per_sm;
         cfg_dev = dev;
@@ -443,7 +454,7 @@ int s2_launch(const S2Params<T>& p0, cudaStream_t st) {
     nruns = std::min<long long>(nruns, std::max(1, p.rows / (4 * C::P)));  // keep the 2R re-read rows per run small
     p.nruns = (int)nruns;
     const long long grid = std::min<long long>(ctas, (long long)p.nstrips * p.nruns);
-    stream2d_kernel<T, SHAPE, R, RED><<<(unsigned)grid, (S2_WARPS + 1) * 32, C::SMEM, st>>>(p);
+    stream2d_kernel<T, SHAPE, R, RED><<<(unsigned)grid, S2_THREADS, C::SMEM, st>>>(p);
     SB_LAUNCH_CHECK();
     return SB200_OK;
 }

@@ -40,6 +40,9 @@ constexpr int D2_WARPS = D2_WX * D2_WY;
 #ifndef SB200_D2_STAGES
 #define SB200_D2_STAGES 6
 #endif
+#ifndef SB200_D2_PACKED
+#define SB200_D2_PACKED 0
+#endif
 // producer warps (the rows of a stage dealt round-robin). Measured on 1024^3 Float32 (r01j): 2 producers 935, 3 producers
 // 1092, 4 producers (register cap 80) 1073 Gcell-updates/s: with two, the consumers waited for data 23 % of the time
 // (each bulk copy costs ~14 issue slots of lane-by-lane serialisation: ELECT / R2UR / UBLKCP / BRA.U.ANY).
@@ -136,6 +139,60 @@ __device__ __forceinline__ void d2_plane(T (&done)[VX], T (&cprev)[VX], T (&part
 __device__ __noinline__ void d2_level_barrier() {
     asm volatile("bar.sync 1, %0;" ::"n"(D2_CONSUMERS * 32) : "memory");
 }
+
+#if SB200_D2_PACKED
+// EXPERIMENT (off by default, not yet run on a GPU; build with tools/build_variant.sh ... -DSB200_D2_PACKED=1): the same plane
+// step for Float32 with packed add / mul / fma.rn.f32x2 (SASS FADD2 / FMUL2 / FFMA2): the kernel is bound by issue slots
+// (65 % busy, FMA pipe 34 %), and a packed instruction advances two cells per slot. Every lane of a packed instruction rounds
+// like the scalar one. Products are written as fma(x, w, -0.0) == rn(x * w) (exact product plus -0 changes nothing, signed
+// zeros and NaN included) so that ptxas cannot contract a multiply with the following add / subtract into one FFMA2 (single
+// rounding), which it does for mul.rn.f32x2 + add.rn.f32x2 (measured on the 7x7 kernelproduct).
+__device__ __forceinline__ unsigned long long d2_pk(float lo, float hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void d2_upk(unsigned long long v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ unsigned long long d2_add2(unsigned long long a, unsigned long long b) {
+    unsigned long long r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ unsigned long long d2_sub2(unsigned long long a, unsigned long long b) {
+    unsigned long long r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ unsigned long long d2_mul2_opaque(unsigned long long a, unsigned long long b) {   // rn(a * b), never contracted
+    unsigned long long r;
+    const unsigned long long nz = 0x8000000080000000ull;   // (-0.0f, -0.0f)
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(nz));
+    return r;
+}
+template <>
+__device__ __forceinline__ void d2_plane<float, 4>(float (&done)[4], float (&cprev)[4], float (&part)[4], const float (&c)[4],
+                                                   const float (&ym)[4], const float (&yp)[4], float l_, float r_, float alpha) {
+    const unsigned long long six = d2_pk(6.0f, 6.0f), al = d2_pk(alpha, alpha);
+    const unsigned long long mid12 = d2_pk(c[1], c[2]);                      // xp of cells 0,1 and xm of cells 2,3
+    const unsigned long long xm[2] = {d2_pk(l_, c[0]), mid12}, xp[2] = {mid12, d2_pk(c[3], r_)};
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        const unsigned long long cc = d2_pk(cprev[2 * h], cprev[2 * h + 1]), cv = d2_pk(c[2 * h], c[2 * h + 1]);
+        // done = cc + alpha * ((part + c) - 6 * cc), every operation rounded separately
+        const unsigned long long s = d2_add2(d2_pk(part[2 * h], part[2 * h + 1]), cv);
+        const unsigned long long u = d2_sub2(s, d2_mul2_opaque(six, cc));
+        d2_upk(d2_add2(cc, d2_mul2_opaque(al, u)), done[2 * h], done[2 * h + 1]);
+        // part = (((cc + ym) + xm) + xp) + yp
+        unsigned long long a = d2_add2(cc, d2_pk(ym[2 * h], ym[2 * h + 1]));
+        a = d2_add2(a, xm[h]);
+        a = d2_add2(a, xp[h]);
+        a = d2_add2(a, d2_pk(yp[2 * h], yp[2 * h + 1]));
+        d2_upk(a, part[2 * h], part[2 * h + 1]);
+        cprev[2 * h] = c[2 * h];
+        cprev[2 * h + 1] = c[2 * h + 1];
+    }
+}
+#endif
 
 template <typename T>
 __global__ void __launch_bounds__(D2_THREADS, 1) stream3d2_kernel(const __grid_constant__ D2Params<T> p) {
