@@ -18,7 +18,7 @@ for v in 1 0; do
       > $O/bench_diffusion_ds$v.json 2> $O/bench_diffusion_ds$v.err; echo "bench diffusion ds$v rc=$?" >> $S
 done
 timeout 400 python bench.py > $O/bench_default.json 2> $O/bench_default.err; echo "bench default rc=$?" >> $S
-ncu --metrics gpu__time_duration.sum --clock-control none -c 40 --csv --log-file $O/launches_diffusion.csv \
+ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"stream3d|halo|push|wait|signal" -c 40 --csv --log-file $O/launches_diffusion.csv \
     python bench.py --workload diffusion --steps 24 --warmup 4 --no-extras > $O/launches_diffusion.log 2>&1
 SB200_DIFFUSION_DOUBLE_STEP=0 timeout 150 ncu --set full --import-source on --clock-control none -k regex:stream3d -s 3 -c 1 -f -o gpurun_out/r01l_diffusion \
     python bench.py --workload diffusion --steps 4 --warmup 4 --no-extras > $O/ncu_diffusion.log 2>&1; echo "ncu diffusion rc=$?" >> $S
