@@ -2,7 +2,7 @@
 """bench.py — headline benchmark of the stencil sweep (BASELINE.json metric: Gcell-updates/s and fraction of the
 HBM roofline per stencil config).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload life|mean|mean1000|kernel|circle|positional|scatter|diffusion]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--strong] [--workload life|mean|mean1000|kernel|circle|positional|scatter|diffusion]
     python bench.py --impl reference ...        # the reference algorithm on the host cores (CPU oracle)
 
 One "step" is one sweep of the hot path over the whole grid. The default workload is BASELINE.json configs[1]:
@@ -312,6 +312,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="life")
     ap.add_argument("--no-extras", action="store_true", help="skip the secondary configs / cpu baseline / e2e legs")
+    ap.add_argument("--strong", action="store_true",
+                    help="N > 1: split the ONE-GPU grid over the ranks (strong scaling) instead of one full grid per rank (weak, default)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -340,7 +342,7 @@ def main():
     if world > 1:
         from stencils_b200 import slab
         with ClockSampler(local_rank) as cs:
-            res = slab.bench_weak(args.workload, spec, args.steps, args.warmup, synth)
+            res = slab.bench_weak(args.workload, spec, args.steps, args.warmup, synth, strong=args.strong)
         ms, cells_total, launches, kernel, extra_cfg = res
     else:
         st, run, cells_total = make_sweep(args.workload, spec, torch, sb)
@@ -368,10 +370,13 @@ def main():
         dram_frac = traffic * per_rank_launches / (ms * 1e-3) / 1e9 / peak
     line = {
         "metric": "gcell_updates_per_s", "value": value, "unit": "Gcell-updates/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "strong" if (args.strong and world > 1) else "weak",
         "vs_baseline": None, "dtype": {"uint8": "u8", "float64": "f64", "float32": "f32"}[np.dtype(spec["dtype"]).name],
         "data": "synthetic (splitmix64 hash of the linear index, SURVEY 8d)",
-        "config": {"workload": spec["desc"], "grid_per_gpu": list(spec["shape"]), "parallelism": f"slab{world}",
+        "config": {"workload": spec["desc"],
+                   "grid_per_gpu": list(spec["shape"][:-1]) + [spec["shape"][-1] // world if (args.strong and world > 1) else spec["shape"][-1]],
+                   "parallelism": f"slab{world}",
                    "l2": "state per GPU (>= 256 MiB) is larger than the 126 MB L2; no flush needed", **extra_cfg},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "peak_source": peak_src, "kernel": kernel,

@@ -387,8 +387,9 @@ def split_axis_last(shape_global, world, rank):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
-def bench_weak(workload, spec, steps, warmup, synth=None):
-    """Weak-scaling benchmark body used by bench.py under torchrun: every rank owns a slab of spec['shape'];
+def bench_weak(workload, spec, steps, warmup, synth=None, strong=False):
+    """Scaling benchmark body used by bench.py under torchrun: every rank owns a slab of spec['shape'] (weak scaling), or,
+    with strong=True, 1/world of spec['shape'] along the last axis (strong scaling: the one-GPU problem split over the ranks);
     returns (ms on this rank, total owned cells over all ranks, launches in the timed region, kernel, config)."""
     import torch
     import torch.distributed as dist
@@ -397,6 +398,10 @@ def bench_weak(workload, spec, steps, warmup, synth=None):
     rank, world = dist.get_rank(), dist.get_world_size()
     dev = torch.device("cuda", torch.cuda.current_device())
     shape = tuple(spec["shape"])
+    if strong:
+        if shape[-1] % world:
+            raise SystemExit(f"--strong needs the last axis ({shape[-1]}) to be a multiple of the number of GPUs ({world})")
+        shape = shape[:-1] + (shape[-1] // world,)
     cells_local = int(np.prod(shape))
     # rank r's slab is planes [r*n, (r+1)*n) of the global field -> linear index offset r * cells_local
     field = synth_torch(shape, spec["dtype"], spec["seed"], dev, lo=rank * cells_local)
