@@ -397,7 +397,7 @@ bool diffusion2_accepts(const sb200_desc& d, const Plan& pl) {
         if (d.src_off[a] != 0 || d.dst_off[a] != 0 || d.dst_ext[a] != d.size[a] || d.src_ext[a] != d.size[a]) return false;
         if (d.size[a] < 4 || d.size[a] > (1 << 28)) return false;
     }
-    if ((d.size[0] * es) % 16 || d.size[0] * es < 64) return false;
+    if ((d.size[0] * es) % 16 || d.size[0] * es < 64 || d.size[0] * es >= (1LL << 30)) return false;   // row bytes are held in an int
     if (d.boundary[0] != SB200_WRAP || d.boundary[1] != SB200_WRAP) return false;
     if (pl.dd.lo[0] != 0 || pl.dd.n[0] != d.size[0] || pl.dd.lo[1] != 0 || pl.dd.n[1] != d.size[1]) return false;  // z regions only
     const long long lo = pl.dd.lo[2], hi = lo + pl.dd.n[2];
