@@ -462,7 +462,8 @@ def slab_gather(local_owned, *, offsets, radius, reducer, boundary, eltype, rank
     BASELINE configs 1, 3, 4a at N GPUs): ONE pre-exchange of R ghost planes, then one sweep of the owned planes.
     Returns this rank's slab of the result (torch tensor, split axis first). Reducers that change the element type
     (mean / sum of Bool, mean of integers) are not taken here: the state buffers are typed like the source."""
-    if reducer in (A.SUM, A.MEAN) and eltype in (A.BOOL,) or (reducer == A.MEAN and eltype not in (A.F32, A.F64)):
+    changes_eltype = (reducer == A.SUM and eltype == A.BOOL) or (reducer == A.MEAN and eltype not in (A.F32, A.F64))
+    if changes_eltype:   # sum(Bool) -> Int64, mean(integer) -> Float64 (src/gatherstencil.jl:41-59)
         raise A.ArgumentError("slab_gather needs a reducer whose result has the element type of the source")
     it = SlabIterator(local_owned, offsets=offsets, radius=radius, reducer=reducer, boundary=boundary, eltype=eltype,
                       ghost=max(int(radius), 1), rank=rank, world=world, compute=compute, reducer_kwargs=reducer_kwargs,
