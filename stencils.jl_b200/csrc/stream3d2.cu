@@ -27,6 +27,7 @@
 // neighbours in the opposite order, which is why Reflect is not accepted; Remove would need padval selects).
 // Algorithmic traffic: sizeof(T) read + sizeof(T) written per cell per TWO steps.
 #include <algorithm>
+#include <cstdlib>
 #include "common.cuh"
 #include "tma.cuh"
 
@@ -75,6 +76,9 @@ template <typename T> struct D2Params {
     T alpha;
     int z_lo, zn;            // output planes [z_lo, z_lo + zn)
     int ntx, nty, nzruns, ty;
+    // PAD kernel only (appended so that the Wrap kernel's parameter layout is unchanged)
+    int bc0, bc1;            // boundaries of axes 0 and 1: SB200_WRAP or SB200_REMOVE
+    T pad;                   // Remove(padval)
 };
 
 __device__ __forceinline__ long long d2_wrap(int r, int n) { return r < 0 ? r + n : (r >= n ? r - n : r); }
@@ -194,9 +198,14 @@ __device__ __forceinline__ void d2_plane<float, 4>(float (&done)[4], float (&cpr
 }
 #endif
 
-template <typename T>
+// PAD = true: EXPERIMENT (not yet run on a GPU; SB200_D2_REMOVE=1 lets diffusion2_accepts take Remove axes): out-of-bounds
+// source cells AND out-of-bounds cells of the intermediate state read padval (Remove boundary: the second sweep sees
+// padval outside the array, not an update of it). Rows / planes / edge halos outside the array are not copied; the values
+// are substituted by selects. PAD = false is the measured Wrap kernel, its code is untouched (if constexpr).
+template <typename T, bool PAD>
 __global__ void __launch_bounds__(D2_THREADS, 1) stream3d2_kernel(const __grid_constant__ D2Params<T> p) {
     constexpr int VX = 16 / (int)sizeof(T);
+    const bool padx = PAD && p.bc0 == SB200_REMOVE, pady = PAD && p.bc1 == SB200_REMOVE, padz = PAD && p.bc2 == SB200_REMOVE;
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem);
     uint64_t* empty = full + D2_STAGES;
@@ -226,29 +235,34 @@ __global__ void __launch_bounds__(D2_THREADS, 1) stream3d2_kernel(const __grid_c
             const int mstart = x0b - (l_in ? 16 : 0);
             const unsigned mlen = wbytes + (l_in ? 16 : 0) + (r_in ? 16 : 0);
             const int mdst = D2_LEFT - (l_in ? 16 : 0);
-            const unsigned rowbytes = wbytes + 32;
+            unsigned rowbytes = wbytes + 32;
+            if constexpr (PAD) if (padx) rowbytes = mlen;   // no Wrap image at an array edge
             const int srow_i = D2_PRODUCERS * lane + pw;
             long long yrow = -1;
             if (srow_i < p.ty + 4) {
                 const int y = y0 - 2 + srow_i;
                 if (y <= p.Y + 1) yrow = d2_wrap(y, p.Y);
+                if constexpr (PAD) if (pady) yrow = (y >= 0 && y < p.Y) ? y : -1;
             }
-            const unsigned nrows = (unsigned)min(p.ty + 4, p.Y + 4 - y0);   // rows of the stage that are copied (both producers)
+            unsigned nrows = (unsigned)min(p.ty + 4, p.Y + 4 - y0);   // rows of the stage that are copied (both producers)
+            if constexpr (PAD) if (pady) nrows = (unsigned)(min(p.Y - 1, y0 + p.ty + 1) - max(0, y0 - 2) + 1);
             for (int i = 0; i < nsrc; i++, k++) {
                 const int slot = k % D2_STAGES;
                 int zl = z0 - 2 + i;
                 if (p.bc2 == SB200_WRAP) zl = (int)d2_wrap(zl, p.Z);
+                bool zin = true;
+                if constexpr (PAD) zin = !(padz && (zl < 0 || zl >= p.Z));   // a plane outside the array is not copied
                 if (lane == 0) {
                     mbar_wait(&empty[slot], ((k / D2_STAGES) & 1) ^ 1);
-                    if (pw == 0) mbar_arrive_expect_tx(&full[slot], nrows * rowbytes);
+                    if (pw == 0) mbar_arrive_expect_tx(&full[slot], zin ? nrows * rowbytes : 0u);
                 }
                 __syncwarp();
-                if (yrow >= 0) {
+                if (yrow >= 0 && zin) {
                     const unsigned char* g = reinterpret_cast<const unsigned char*>(p.src + (long long)zl * p.p2 + yrow * p.p1);
                     unsigned char* srow = ring + slot * D2_STAGE + srow_i * D2_ROWB;
                     bulk_g2s(srow + mdst, g + mstart, mlen, &full[slot]);
-                    if (!l_in) bulk_g2s(srow + D2_LEFT - 16, g + Xb - 16, 16, &full[slot]);
-                    if (!r_in) bulk_g2s(srow + D2_LEFT + wbytes, g, 16, &full[slot]);
+                    if (!l_in && !padx) bulk_g2s(srow + D2_LEFT - 16, g + Xb - 16, 16, &full[slot]);
+                    if (!r_in && !padx) bulk_g2s(srow + D2_LEFT + wbytes, g, 16, &full[slot]);
                 }
             }
             continue;
@@ -262,15 +276,30 @@ __global__ void __launch_bounds__(D2_THREADS, 1) stream3d2_kernel(const __grid_c
             T ce = T(0), qe = T(0);
             int slot = k % D2_STAGES;
             unsigned phase = (k / D2_STAGES) & 1;
+            // PAD: which of this rim cell's inputs lie outside the array (task constants; the plane test is per iteration)
+            const int yr = y0 - 1 + mrow;
+            const bool x_oob = padx && ((lane >> 4) ? x0b + wbytes == Xb : x0b == 0);
+            const bool row_oob = pady && (yr < 0 || yr >= p.Y), up_oob = pady && (yr - 1 < 0 || yr - 1 >= p.Y), dn_oob = pady && (yr + 1 < 0 || yr + 1 >= p.Y);
             for (int i = 0; i < nsrc; i++, k++) {
                 mbar_wait(&full[slot], phase);
                 const unsigned char* t = ring + slot * D2_STAGE + (mrow + 1) * D2_ROWB + pos;   // intermediate row m <-> source row m + 1
-                const T c = *reinterpret_cast<const T*>(t);
-                const T m = d2_update(add_rn(qe, c), ce, p.alpha);
-                T a = add_rn(ce, *reinterpret_cast<const T*>(t - D2_ROWB));
+                T c = *reinterpret_cast<const T*>(t);
+                T yu = *reinterpret_cast<const T*>(t - D2_ROWB), yd = *reinterpret_cast<const T*>(t + D2_ROWB);
+                bool m_oob = false;
+                if constexpr (PAD) {
+                    const int sz = z0 - 2 + i;                       // source plane of this stage; it completes intermediate plane sz - 1
+                    const bool zs_oob = padz && (sz < 0 || sz >= p.Z);
+                    m_oob = x_oob || row_oob || (padz && (sz - 1 < 0 || sz - 1 >= p.Z));
+                    if (zs_oob || row_oob) c = p.pad;
+                    if (zs_oob || up_oob) yu = p.pad;
+                    if (zs_oob || dn_oob) yd = p.pad;
+                }
+                T m = d2_update(add_rn(qe, c), ce, p.alpha);
+                if constexpr (PAD) if (m_oob) m = p.pad;
+                T a = add_rn(ce, yu);
                 a = add_rn(a, *reinterpret_cast<const T*>(t - sizeof(T)));
                 a = add_rn(a, *reinterpret_cast<const T*>(t + sizeof(T)));
-                a = add_rn(a, *reinterpret_cast<const T*>(t + D2_ROWB));
+                a = add_rn(a, yd);
                 qe = a;
                 ce = c;
                 __syncwarp();
@@ -302,6 +331,14 @@ __global__ void __launch_bounds__(D2_THREADS, 1) stream3d2_kernel(const __grid_c
         const bool l0 = lane == 0, l31 = lane == 31;
         int slot = k % D2_STAGES;
         unsigned phase = (k / D2_STAGES) & 1;
+        // PAD: out-of-bounds tests that do not depend on the plane
+        const bool xoob = padx && gx >= p.X;                              // lanes past the right array edge of a ragged edge tile
+        const bool edge_l = padx && gx == 0, edge_r = padx && gx + VX == p.X;
+        bool srow_oob[D2_RT + 2], mrow_oob[D2_RT];
+#pragma unroll
+        for (int q = 0; q < D2_RT + 2; q++) srow_oob[q] = pady && (y0 + r1 - 2 + q < 0 || y0 + r1 - 2 + q >= p.Y);
+#pragma unroll
+        for (int j = 0; j < D2_RT; j++) mrow_oob[j] = xoob || (pady && (y0 + r1 - 1 + j < 0 || y0 + r1 - 1 + j >= p.Y));
         for (int i = 0; i < nsrc; i++, k++) {
             mbar_wait(&full[slot], phase);
             // this thread's 16 bytes in shared-memory row 0; tile row t lives in source row t + 2 and intermediate row t + 1
@@ -311,6 +348,18 @@ __global__ void __launch_bounds__(D2_THREADS, 1) stream3d2_kernel(const __grid_c
             T rowv[D2_RT + 2][VX];                     // source tile rows r1-2 .. r1+1 = source rows r1 .. r1+3
 #pragma unroll
             for (int q = 0; q < D2_RT + 2; q++) d2_lds<T, VX>(rowv[q], sb_ + q * D2_ROWB);
+            bool zs_oob = false, zm_oob = false;       // PAD: source plane s / intermediate plane s-1 outside the array
+            if constexpr (PAD) {
+                const int sz = z0 - 2 + i;
+                zs_oob = padz && (sz < 0 || sz >= p.Z);
+                zm_oob = padz && (sz - 1 < 0 || sz - 1 >= p.Z);
+#pragma unroll
+                for (int q = 0; q < D2_RT + 2; q++)
+                    if (zs_oob || srow_oob[q]) {
+#pragma unroll
+                        for (int v = 0; v < VX; v++) rowv[q][v] = p.pad;
+                    }
+            }
             T mid[D2_RT][VX];
 #pragma unroll
             for (int j = 0; j < D2_RT; j++) {
@@ -319,7 +368,16 @@ __global__ void __launch_bounds__(D2_THREADS, 1) stream3d2_kernel(const __grid_c
                 T r_ = __shfl_down_sync(0xffffffffu, rowv[j + 1][0], 1);
                 d2_lds_if(l_, t - sizeof(T), l0);
                 d2_lds_if(r_, t + 16, l31);
+                if constexpr (PAD) {
+                    if (zs_oob || srow_oob[j + 1] || edge_l) l_ = p.pad;
+                    if (zs_oob || srow_oob[j + 1] || edge_r) r_ = p.pad;
+                }
                 d2_plane<T, VX>(mid[j], c1[j], q1[j], rowv[j + 1], rowv[j], rowv[j + 2], l_, r_, p.alpha);
+                if constexpr (PAD)
+                    if (zm_oob || mrow_oob[j]) {
+#pragma unroll
+                        for (int v = 0; v < VX; v++) mid[j][v] = p.pad;
+                    }
             }
             __syncwarp();
             if (l0) mbar_arrive(&empty[slot]);          // every read of the source stage is done
@@ -355,12 +413,12 @@ __global__ void __launch_bounds__(D2_THREADS, 1) stream3d2_kernel(const __grid_c
     }
 }
 
-template <typename T> static int d2_launch(D2Params<T>& p, cudaStream_t st) {
+template <typename T, bool PAD> static int d2_launch(D2Params<T>& p, cudaStream_t st) {
     static thread_local int cfg_dev = -1;
     int dev = 0;
     SB_CUDA(cudaGetDevice(&dev));
     if (dev != cfg_dev) {
-        SB_CUDA(cudaFuncSetAttribute(stream3d2_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, D2_SMEM));
+        SB_CUDA(cudaFuncSetAttribute(stream3d2_kernel<T, PAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, D2_SMEM));
         cfg_dev = dev;
     }
     const long long ctas = num_sms();   // one CTA per SM (the ring takes most of the shared memory)
@@ -382,7 +440,7 @@ template <typename T> static int d2_launch(D2Params<T>& p, cudaStream_t st) {
     p.nzruns = best;
     const long long ntasks = (long long)p.ntx * p.nty * p.nzruns;
     const long long grid = std::min<long long>(ctas, ntasks);
-    stream3d2_kernel<T><<<(unsigned)grid, D2_THREADS, D2_SMEM, st>>>(p);
+    stream3d2_kernel<T, PAD><<<(unsigned)grid, D2_THREADS, D2_SMEM, st>>>(p);
     SB_LAUNCH_CHECK();
     return SB200_OK;
 }
@@ -398,11 +456,14 @@ bool diffusion2_accepts(const sb200_desc& d, const Plan& pl) {
         if (d.size[a] < 4 || d.size[a] > (1 << 28)) return false;
     }
     if ((d.size[0] * es) % 16 || d.size[0] * es < 64 || d.size[0] * es >= (1LL << 30)) return false;   // row bytes are held in an int
-    if (d.boundary[0] != SB200_WRAP || d.boundary[1] != SB200_WRAP) return false;
+    // Remove axes run the PAD variant of the kernel, which has not been on a GPU yet: opt-in with SB200_D2_REMOVE=1
+    const bool remove_ok = getenv("SB200_D2_REMOVE") != nullptr;
+    for (int a = 0; a < 2; a++)
+        if (d.boundary[a] != SB200_WRAP && !(remove_ok && d.boundary[a] == SB200_REMOVE)) return false;
     if (pl.dd.lo[0] != 0 || pl.dd.n[0] != d.size[0] || pl.dd.lo[1] != 0 || pl.dd.n[1] != d.size[1]) return false;  // z regions only
     const long long lo = pl.dd.lo[2], hi = lo + pl.dd.n[2];
     const bool inside = lo >= 2 && hi + 2 <= d.size[2];   // never leaves the parent: the boundary rule of axis 2 is not exercised
-    if (!inside && d.boundary[2] != SB200_WRAP) return false;
+    if (!inside && d.boundary[2] != SB200_WRAP && !(remove_ok && d.boundary[2] == SB200_REMOVE)) return false;
     return true;
 }
 
@@ -420,7 +481,12 @@ template <typename T> static int d2_try(const Plan& pl, const void* src, void* d
     const long long Xb = d.size[0] * (long long)sizeof(T);
     p.ntx = (int)((Xb + D2_TXB - 1) / D2_TXB);
     p.nty = 0; p.nzruns = 1; p.ty = D2_TY;
-    return d2_launch<T>(p, st);
+    p.bc0 = d.boundary[0]; p.bc1 = d.boundary[1];
+    memcpy(&p.pad, &d.padval_bits, sizeof(T));
+    const long long lo = pl.dd.lo[2], hi = lo + pl.dd.n[2];
+    const bool z_remove = d.boundary[2] == SB200_REMOVE && !(lo >= 2 && hi + 2 <= d.size[2]);
+    if (d.boundary[0] == SB200_REMOVE || d.boundary[1] == SB200_REMOVE || z_remove) return d2_launch<T, true>(p, st);
+    return d2_launch<T, false>(p, st);
 }
 
 int try_diffusion3d_double(const Plan& pl, const void* src, void* dst, cudaStream_t st) {

@@ -657,3 +657,27 @@ def test_diffusion_two_steps_per_launch(orc, dt, monkeypatch):
         hb = build_desc(flags=A.FLAG_DOUBLE_STEP, **dict(kw, **bad))
         t = to_dev(g)
         assert l.sb200_gather(hb.ptr(), t.data_ptr(), to_dev(g).data_ptr(), None) == A.EUNSUPPORTED
+
+
+@pytest.mark.skipif(not __import__("os").environ.get("SB200_EXPERIMENTS"),
+                    reason="experiments prepared without GPU time left in round 1 (set SB200_EXPERIMENTS=1): the PAD variant of "
+                           "stream3d2_kernel (Remove axes) has only been checked against tools/model_stream3d2.py so far")
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+def test_diffusion_two_steps_per_launch_remove_axes(orc, dt, monkeypatch):
+    """SB200_D2_REMOVE=1: two diffusion steps per launch with Remove(padval) on any subset of the axes — out-of-bounds cells
+    read padval at BOTH time levels — against two oracle sweeps, bit for bit."""
+    monkeypatch.setenv("SB200_D2_REMOVE", "1")
+    rng = np.random.default_rng(92)
+    l = A.lib()
+    offs = npr.offsets("VonNeumann", 1, 3)
+    et = A.ELTYPE_OF_DTYPE[np.dtype(dt)]
+    for shape in [(64, 20, 9), (160, 17, 8), (300, 30, 8), (512, 15, 12), (1024 // np.dtype(dt).itemsize + 8, 33, 21)]:
+        g = rand_array(rng, shape, dt)
+        for bcs in [(A.REMOVE,) * 3, (A.REMOVE, A.WRAP, A.REMOVE), (A.WRAP, A.REMOVE, A.WRAP), (A.REMOVE, A.REMOVE, A.WRAP)]:
+            kw = dict(size=shape, eltype=et, out_eltype=et, offsets=offs, radius=1, reducer=A.DIFFUSION, alpha=0.1, boundary=bcs,
+                      padval=0.25)
+            h1 = build_desc(**kw)
+            want = orc.gather(h1, orc.gather(h1, g, dst_like(h1)), dst_like(h1))
+            got, _ = gpu_gather(build_desc(flags=A.FLAG_DOUBLE_STEP, **kw), g, dst_like(h1))
+            assert l.sb200_last_kernel() == b"stream3d2_kernel"
+            bits_equal(got, want)

@@ -26,15 +26,20 @@ def update(s, c, alpha, T):
     return (c + (alpha * (s - (T(6) * c)).astype(T)).astype(T)).astype(T)
 
 
-def reference_step(a, alpha, wrap_z=True):
-    """One sweep, offsets (0,0,-1),(0,-1,0),(-1,0,0),(1,0,0),(0,1,0),(0,0,1); array indexed [x, y, z]."""
+def reference_step(a, alpha, bcs=("wrap", "wrap", "wrap"), pad=0.0):
+    """One sweep, offsets (0,0,-1),(0,-1,0),(-1,0,0),(1,0,0),(0,1,0),(0,0,1); array indexed [x, y, z]; per-axis Wrap or
+    Remove(pad) (out-of-bounds neighbours read pad)."""
     T = a.dtype.type
-    s = np.roll(a, 1, 2)
-    s = (s + np.roll(a, 1, 1)).astype(T)
-    s = (s + np.roll(a, 1, 0)).astype(T)
-    s = (s + np.roll(a, -1, 0)).astype(T)
-    s = (s + np.roll(a, -1, 1)).astype(T)
-    s = (s + np.roll(a, -1, 2)).astype(T)
+    g = a
+    for ax, bc in enumerate(bcs):
+        w = [(0, 0)] * 3
+        w[ax] = (1, 1)
+        g = np.pad(g, w, mode="wrap") if bc == "wrap" else np.pad(g, w, mode="constant", constant_values=T(pad))
+    X, Y, Z = a.shape
+    c = lambda dx, dy, dz: g[1 + dx:1 + dx + X, 1 + dy:1 + dy + Y, 1 + dz:1 + dz + Z]  # noqa: E731
+    s = c(0, 0, -1)
+    for d in ((0, -1, 0), (-1, 0, 0), (1, 0, 0), (0, 1, 0), (0, 0, 1)):
+        s = (s + c(*d)).astype(T)
     return update(s, a, T(alpha), T)
 
 
@@ -54,7 +59,7 @@ def launch_cfg(X, Y, zn, es, ctas):
     return ntx, best[1], best[2]
 
 
-def model(src, alpha, z_lo, zn, wrap_z, ctas=3, force_nz=None, force_ty=None):
+def model(src, alpha, z_lo, zn, wrap_z, ctas=3, force_nz=None, force_ty=None, bcs=("wrap", "wrap", None), pad=0.0):
     T = src.dtype.type
     es = src.dtype.itemsize
     VX = 16 // es
@@ -73,6 +78,10 @@ def model(src, alpha, z_lo, zn, wrap_z, ctas=3, force_nz=None, force_ty=None):
     grid = min(ctas, ntasks)
     alpha = T(alpha)
     lanes = np.arange(32)
+    # the PAD variant of the kernel (Remove axes): bcs[2] None = "as wrap_z says"
+    padx, pady = bcs[0] == "remove", bcs[1] == "remove"
+    padz = bcs[2] == "remove"
+    pad = T(pad)
     for block in range(grid):
         ring = np.full((STAGES, ROWS, ROWB), 0xFF, dtype=np.uint8)  # all-ones bytes = NaN
         mbuf = np.full((2, MROWS, ROWB), 0xFF, dtype=np.uint8)
@@ -100,24 +109,36 @@ def model(src, alpha, z_lo, zn, wrap_z, ctas=3, force_nz=None, force_ty=None):
                 mlen = wbytes + (16 if l_in else 0) + (16 if r_in else 0)
                 mdst = LEFT - (16 if l_in else 0)
                 zl = z0 - 2 + i
-                if wrap_z:
+                if wrap_z and not padz:
                     zl = wrap(zl, Z)
-                assert 0 <= zl < Z
+                zin = not (padz and (zl < 0 or zl >= Z))
+                assert (0 <= zl < Z) or not zin
                 copied = 0
                 for pw in range(2):
                     for lane in range(32):
                         row = 2 * lane + pw
                         if row < ty + 4:
                             y = y0 - 2 + row
-                            if y <= Y + 1:
-                                g = flat[zl, wrap(y, Y)]
-                                ring[slot, row, mdst:mdst + mlen] = g[mstart:mstart + mlen]
-                                if not l_in:
-                                    ring[slot, row, LEFT - 16:LEFT] = g[Xb - 16:Xb]
-                                if not r_in:
-                                    ring[slot, row, LEFT + wbytes:LEFT + wbytes + 16] = g[0:16]
+                            yrow = wrap(y, Y) if y <= Y + 1 else -1
+                            if pady:
+                                yrow = y if 0 <= y < Y else -1
+                            if yrow >= 0:
                                 copied += 1
-                assert copied == min(ty + 4, Y + 4 - y0), "expect_tx row count"
+                                if not zin:
+                                    continue
+                                g = flat[zl, yrow]
+                                ring[slot, row, mdst:mdst + mlen] = g[mstart:mstart + mlen]
+                                if not l_in and not padx:
+                                    ring[slot, row, LEFT - 16:LEFT] = g[Xb - 16:Xb]
+                                if not r_in and not padx:
+                                    ring[slot, row, LEFT + wbytes:LEFT + wbytes + 16] = g[0:16]
+                nrows = min(ty + 4, Y + 4 - y0)
+                if pady:
+                    nrows = min(Y - 1, y0 + ty + 1) - max(0, y0 - 2) + 1
+                assert copied == nrows, "expect_tx row count"
+                sz = z0 - 2 + i
+                zs_oob = padz and (sz < 0 or sz >= Z)
+                zm_oob = padz and (sz - 1 < 0 or sz - 1 >= Z)
                 mbuf[par] = 0xFF
 
                 def geom(w):
@@ -161,6 +182,13 @@ def model(src, alpha, z_lo, zn, wrap_z, ctas=3, force_nz=None, force_ty=None):
                         wx, wy, xtb, r1 = geom(w)
                         src_ = ring[slot]
                         rowv = [lds_vec(src_, r1 + q, xtb) for q in range(RT + 2)]
+                        gx_ = (x0b + xtb) // es
+                        xoob = padx & (gx_ >= X)
+                        edge_l, edge_r = padx & (gx_ == 0), padx & (gx_ + VX == X)
+                        srow_oob = [pady and not (0 <= y0 + r1 - 2 + q < Y) for q in range(RT + 2)]
+                        for q in range(RT + 2):
+                            if zs_oob or srow_oob[q]:
+                                rowv[q] = np.full((VX, 32), pad, T)
                         mid = np.empty((RT, VX, 32), T)
                         for j in range(RT):
                             row = r1 + j + 1
@@ -168,18 +196,40 @@ def model(src, alpha, z_lo, zn, wrap_z, ctas=3, force_nz=None, force_ty=None):
                             r_ = np.concatenate([rowv[j + 1][0][1:], rowv[j + 1][0][-1:]])
                             l_[0] = lds(src_, row, xtb, np.full(32, -es))[0]
                             r_[31] = lds(src_, row, xtb, np.full(32, 16))[31]
+                            if zs_oob or srow_oob[j + 1]:
+                                l_[:] = pad
+                                r_[:] = pad
+                            l_ = np.where(edge_l, pad, l_)
+                            r_ = np.where(edge_r, pad, r_)
                             mid[j] = plane(S["c1"][j], S["q1"][j], rowv[j + 1], rowv[j], rowv[j + 2], l_, r_)
+                            mrow_oob = pady and not (0 <= y0 + r1 - 1 + j < Y)
+                            if zm_oob or mrow_oob:
+                                mid[j][:] = pad
+                            mid[j][:, xoob] = pad
                         rim = ((lanes == 0) & (wx == 0)) | ((lanes == 31) & (wx == WX - 1))
                         xe = np.where(lanes == 0, -es, 16)
                         for j in range(RT):
                             row = r1 + j + 1
+                            yr = y0 - 1 + (r1 + j)          # logical row of intermediate row r1 + j
+                            x_oob = padx and ((x0b == 0) if wx == 0 else (x0b + wbytes == Xb))
+                            row_oob = pady and not (0 <= yr < Y)
+                            up_oob, dn_oob = pady and not (0 <= yr - 1 < Y), pady and not (0 <= yr + 1 < Y)
                             c = lds(src_, row, xtb, xe)
+                            yu, yd = lds(src_, row - 1, xtb, xe), lds(src_, row + 1, xtb, xe)
+                            if zs_oob or row_oob:
+                                c = np.full(32, pad, T)
+                            if zs_oob or up_oob:
+                                yu = np.full(32, pad, T)
+                            if zs_oob or dn_oob:
+                                yd = np.full(32, pad, T)
                             cc = S["c1e"][j]
                             m = update((S["q1e"][j] + c).astype(T), cc, alpha, T)
-                            a = (cc + lds(src_, row - 1, xtb, xe)).astype(T)
+                            if x_oob or row_oob or zm_oob:
+                                m = np.full(32, pad, T)
+                            a = (cc + yu).astype(T)
                             a = (a + lds(src_, row, xtb, xe - es)).astype(T)
                             a = (a + lds(src_, row, xtb, xe + es)).astype(T)
-                            a = (a + lds(src_, row + 1, xtb, xe)).astype(T)
+                            a = (a + yd).astype(T)
                             S["q1e"][j] = np.where(rim, a, S["q1e"][j])
                             S["c1e"][j] = np.where(rim, c, S["c1e"][j])
                             for l in range(32):
@@ -221,17 +271,18 @@ def model(src, alpha, z_lo, zn, wrap_z, ctas=3, force_nz=None, force_ty=None):
     return dst, (ntx, nty, ty, nzruns)
 
 
-def check(shape, dtype, z_lo=0, zn=None, wrap_z=True, **kw):
+def check(shape, dtype, z_lo=0, zn=None, wrap_z=True, bcs=("wrap", "wrap", None), pad=0.0, **kw):
     rng = np.random.default_rng(sum(shape))
     a = (rng.random(shape) - 0.3).astype(dtype)
     zn = shape[2] if zn is None else zn
-    want = reference_step(reference_step(a, 0.1), 0.1)
-    got, cfg = model(a, 0.1, z_lo, zn, wrap_z, **kw)
+    ref_bcs = (bcs[0], bcs[1], bcs[2] or "wrap")
+    want = reference_step(reference_step(a, 0.1, ref_bcs, pad), 0.1, ref_bcs, pad)
+    got, cfg = model(a, 0.1, z_lo, zn, wrap_z, bcs=bcs, pad=pad, **kw)
     u = {4: np.uint32, 8: np.uint64}[a.dtype.itemsize]
     region = slice(z_lo, z_lo + zn)
     ok = np.array_equal(got[:, :, region].view(u), want[:, :, region].view(u))
     outside = np.isnan(got[:, :, :z_lo]).all() and np.isnan(got[:, :, z_lo + zn:]).all()
-    print(f"{shape} {np.dtype(dtype).name} z[{z_lo},{z_lo + zn}) wrap_z={wrap_z} cfg(ntx,nty,ty,nz)={cfg} {kw}: "
+    print(f"{shape} {np.dtype(dtype).name} z[{z_lo},{z_lo + zn}) wrap_z={wrap_z} bcs={bcs} cfg(ntx,nty,ty,nz)={cfg} {kw}: "
           f"{'OK' if ok and outside else 'MISMATCH'}")
     if not ok:
         bad = np.argwhere(got[:, :, region].view(u) != want[:, :, region].view(u))
@@ -249,6 +300,15 @@ def main():
     ok &= check((128, 14, 16), np.float32, z_lo=3, zn=9, wrap_z=False)   # interior region (slab sweep)
     ok &= check((128, 14, 16), np.float32, z_lo=0, zn=5)       # region touching the wrap seam
     ok &= check((256, 9, 6), np.float32, force_ty=8)
+    # the PAD variant (Remove axes, SB200_D2_REMOVE=1): padval outside the array at BOTH time levels
+    R, W = "remove", "wrap"
+    ok &= check((64, 20, 9), np.float32, bcs=(R, R, R), pad=0.25)
+    ok &= check((160, 17, 8), np.float32, bcs=(R, W, R), pad=-1.5)
+    ok &= check((300, 16, 8), np.float32, bcs=(W, R, None), pad=0.5, ctas=2)
+    ok &= check((300, 30, 8), np.float32, bcs=(R, R, None), pad=0.5, ctas=2, force_ty=14)
+    ok &= check((512, 15, 12), np.float32, bcs=(R, R, R), pad=2.0, force_nz=2, ctas=5)
+    ok &= check((40, 15, 12), np.float64, bcs=(R, R, R), pad=0.125)
+    ok &= check((128, 14, 16), np.float32, z_lo=3, zn=9, wrap_z=False, bcs=(R, R, None), pad=1.0)   # slab sweep, Remove on x and y
     print("model matches two reference sweeps" if ok else "MODEL MISMATCH")
     return 0 if ok else 1
 
