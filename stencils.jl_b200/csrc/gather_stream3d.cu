@@ -20,6 +20,15 @@
 namespace sb {
 
 constexpr int G3_WARPS = 8;
+// EXPERIMENT (default 1 = the measured kernel; other values have not been on a GPU yet): producer warps, the rows of a plane
+// dealt round-robin. This kernel copies 544-byte rows — one bulk copy (~14 issue slots of lane-by-lane serialisation) per 512
+// bytes of tile, twice stream3d's rate, and stream3d went from 0.79 to 0.94 of the HBM roofline with a second producer warp
+// (lesson 3).
+#ifndef SB200_G3_PRODUCERS
+#define SB200_G3_PRODUCERS 1
+#endif
+constexpr int G3_PRODUCERS = SB200_G3_PRODUCERS;
+constexpr int G3_THREADS = (G3_WARPS + G3_PRODUCERS) * 32;
 constexpr int G3_BXB = 512;                   // tile width in bytes: one lane-strided warp row
 constexpr int G3_TY = 16;                     // tile height in rows; warp w owns rows w and w + 8
 constexpr int G3_RT = G3_TY / G3_WARPS;
@@ -72,7 +81,7 @@ template <typename T, int RED> __device__ __forceinline__ T g3_first(T v, T w) {
 }
 
 template <typename T, int RED>
-__global__ void __launch_bounds__((G3_WARPS + 1) * 32, 2) gather_stream3d_kernel(const __grid_constant__ G3Params<T> p) {
+__global__ void __launch_bounds__(G3_THREADS, 2) gather_stream3d_kernel(const __grid_constant__ G3Params<T> p) {
     constexpr int VX = 16 / (int)sizeof(T);
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem);
@@ -108,8 +117,9 @@ __global__ void __launch_bounds__((G3_WARPS + 1) * 32, 2) gather_stream3d_kernel
         const int z1 = p.z_lo + (int)((long long)p.zn * (zrun + 1) / p.nzruns);
         const int nout = z1 - z0;
         const int nst = nout + 2 * R;  // stage i holds source plane z0 - R + i
-        if (warp == G3_WARPS) {
-            // ---------------- producer warp: lane j copies row j of the plane tile (logical row y0 - R + j) ----------------
+        if (G3_PRODUCERS == 1 ? warp == G3_WARPS : warp >= G3_WARPS) {
+            // ---------------- producer warps: lane j of producer w copies row P*j+w of the plane tile (logical row y0 - R + P*j+w) ----------------
+            const int pw = G3_PRODUCERS == 1 ? 0 : warp - G3_WARPS;
             const bool l_in = x0b > 0, r_in = x0b + wbytes < Xb;
             const bool l_wrap = !l_in && p.bc0 == SB200_WRAP, r_wrap = !r_in && p.bc0 == SB200_WRAP;
             const int r_in_bytes = r_in ? min(HLB, Xb - (x0b + wbytes)) : 0;
@@ -122,19 +132,28 @@ __global__ void __launch_bounds__((G3_WARPS + 1) * 32, 2) gather_stream3d_kernel
                 const int y = y0 - R + lane;
                 if (y < p.Y + R) yrow = g3_map(y, p.Y, p.so1, p.bc1);
             }
-            const unsigned nrows = __popc(__ballot_sync(0xffffffffu, yrow >= 0));
+            const unsigned nrows = __popc(__ballot_sync(0xffffffffu, yrow >= 0));   // all rows of the stage (expect_tx)
+            int srow_i = lane;
+            if constexpr (G3_PRODUCERS > 1) {   // this producer's row
+                srow_i = G3_PRODUCERS * lane + pw;
+                yrow = -1;
+                if (srow_i < G3_TY + 2 * R) {
+                    const int y = y0 - R + srow_i;
+                    if (y < p.Y + R) yrow = g3_map(y, p.Y, p.so1, p.bc1);
+                }
+            }
             for (int i = 0; i < nst; i++) {
                 const unsigned k = kb + i;
                 const int slot = k % G3_NS;
                 const long long zpl = g3_map(z0 - R + i, p.Z, p.so2, p.bc2);
                 if (lane == 0) {
                     mbar_wait(&empty[slot], ((k / G3_NS) & 1) ^ 1);
-                    mbar_arrive_expect_tx(&full[slot], zpl >= 0 ? nrows * rowbytes : 0u);
+                    if (pw == 0) mbar_arrive_expect_tx(&full[slot], zpl >= 0 ? nrows * rowbytes : 0u);
                 }
                 __syncwarp();
                 if (zpl >= 0 && yrow >= 0) {
                     const unsigned char* g = reinterpret_cast<const unsigned char*>(p.src + zpl * p.sp2 + yrow * p.sp1);
-                    unsigned char* srow = ring + slot * G3_PLANE + lane * G3_ROWB;
+                    unsigned char* srow = ring + slot * G3_PLANE + srow_i * G3_ROWB;
                     bulk_g2s(srow + mdst, g + mstart, mlen, &full[slot]);
                     if (l_wrap) bulk_g2s(srow + G3_LEFT - wrap_bytes, g + Xb - wrap_bytes, wrap_bytes, &full[slot]);
                     if (r_wrap) bulk_g2s(srow + G3_LEFT + wbytes, g, wrap_bytes, &full[slot]);
@@ -243,7 +262,7 @@ template <typename T, int RED> static int g3_launch(G3Params<T>& p, cudaStream_t
     if (dev != cfg_dev) {
         SB_CUDA(cudaFuncSetAttribute(gather_stream3d_kernel<T, RED>, cudaFuncAttributeMaxDynamicSharedMemorySize, G3_SMEM));
         int per_sm = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gather_stream3d_kernel<T, RED>, (G3_WARPS + 1) * 32, G3_SMEM) != cudaSuccess || per_sm < 1)
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gather_stream3d_kernel<T, RED>, G3_THREADS, G3_SMEM) != cudaSuccess || per_sm < 1)
             per_sm = 1;
         ctas_per_sm = per_sm;
         cfg_dev = dev;
@@ -261,7 +280,7 @@ template <typename T, int RED> static int g3_launch(G3Params<T>& p, cudaStream_t
     }
     p.nzruns = best;
     const long long grid = std::min<long long>(ctas, ntiles * p.nzruns);
-    gather_stream3d_kernel<T, RED><<<(unsigned)grid, (G3_WARPS + 1) * 32, G3_SMEM, st>>>(p);
+    gather_stream3d_kernel<T, RED><<<(unsigned)grid, G3_THREADS, G3_SMEM, st>>>(p);
     SB_LAUNCH_CHECK();
     return SB200_OK;
 }
