@@ -595,11 +595,20 @@ constexpr int LB_CH = 3;
 constexpr int LB_STAGES = 4;
 constexpr int LB_ROWB = 6144;
 constexpr int LB_SMEM = 128 + LB_STAGES * LB_CH * LB_ROWB;
+// EXPERIMENT (default 0 = the measured kernel; not yet on a GPU): ONE halo lane per side instead of G - 1. A wrong edge bit
+// enters an end lane at one cell per generation, so after G <= 32 generations only the end lanes themselves hold wrong cells
+// (tools/model_life_bit_lanes.py emulates the scheme: lanes 1 .. 30 are exact for G = 2 .. 31). With G = 4 that is 30 instead
+// of 26 useful lanes per warp (+15 % cells per instruction) and smaller halos, and it is what makes 8 generations per launch
+// worthwhile (18 useful lanes with G - 1 halo lanes).
+#ifndef SB200_LB_ONE_HALO_LANE
+#define SB200_LB_ONE_HALO_LANE 0
+#endif
 template <int G> struct LbCfg {
-    static constexpr int VALID = 32 - 2 * (G - 1);           // lanes of a warp that own final cells
+    static constexpr int HLN = SB200_LB_ONE_HALO_LANE ? 1 : G - 1;   // halo lanes per side of a warp
+    static constexpr int VALID = 32 - 2 * HLN;               // lanes of a warp that own final cells
     static constexpr int WO = VALID * 32;                     // final cells per warp row
     static constexpr int CAP = LB_WARPS * WO;                 // final cells per strip row (multiple of 128)
-    static constexpr int HL = (G - 1) * 32 + 16;              // halo bytes per side of a shared-memory row
+    static constexpr int HL = HLN * 32 + 16;                  // halo bytes per side of a shared-memory row
     static constexpr int D0 = (128 - HL % 128) % 128;         // data start in a row: global x0 - HL is D0 mod 128
     static_assert(D0 + 2 * HL + CAP <= LB_ROWB, "row does not fit");
 };
@@ -703,11 +712,11 @@ __global__ void __launch_bounds__((LB_WARPS + 1) * 32, 3) life_bit_kernel(const 
             }
             continue;
         }
-        const int cell0 = warp * C::WO + (lane - (G - 1)) * 32;   // first final cell of this lane inside the strip
-        const bool active = lane >= G - 1 && lane <= 32 - G && cell0 < wout;
+        const int cell0 = warp * C::WO + (lane - C::HLN) * 32;   // first final cell of this lane inside the strip
+        const bool active = lane >= C::HLN && lane <= 31 - C::HLN && cell0 < wout;
         const unsigned act_mask = __ballot_sync(0xffffffffu, active);
         // destination of the cells of lane 0 (a halo lane: never stored) in output row y0
-        uint8_t* __restrict__ wp = p.dst + (long long)(y0 + p.doff1) * p.dpitch + x0 + warp * C::WO - (G - 1) * 32;
+        uint8_t* __restrict__ wp = p.dst + (long long)(y0 + p.doff1) * p.dpitch + x0 + warp * C::WO - C::HLN * 32;
         const int soff = C::D0 + C::HL + cell0;
         BRow lv[G][3];
 #pragma unroll
