@@ -169,6 +169,8 @@ typedef struct sb200_desc {
 #define SB200_FLAG_CELLS_01 8      /* LIFE on UInt8: the caller guarantees every source cell is 0 or 1 */
 #define SB200_FLAG_QUAD_STEP 32   /* dest = f(f(f(f(src)))): four generations per launch (B3/S23 Life, axis 0 a multiple of 32
                                      cells, otherwise as SB200_FLAG_DOUBLE_STEP); the bit-sliced kernel */
+#define SB200_FLAG_OCT_STEP 64    /* EXPERIMENT: eight generations per launch (as SB200_FLAG_QUAD_STEP; needs a library built with
+                                     -DSB200_LB_ONE_HALO_LANE=1, otherwise SB200_EUNSUPPORTED) */
 #define SB200_FLAG_DOUBLE_STEP 16 /* dest = f(f(src)): two sweeps fused in one launch, the intermediate state never touches
                                      memory. LIFE: Moore(1), unpadded, Wrap on axis 0. DIFFUSION: VonNeumann(1,3), unpadded
                                      Float32 / Float64, Wrap on axes 0 and 1, axis 2 Wrap or an output region two planes

@@ -303,6 +303,10 @@ static int do_gather(const sb200_desc* d, const void* src, void* dst, cudaStream
         set_error("SB200_FLAG_QUAD_STEP: only B3/S23 Life / Moore(1) on an unpadded Bool or UInt8 grid, Wrap on axis 0, width % 32 == 0");
         return SB200_EUNSUPPORTED;
     }
+    if ((d->flags & SB200_FLAG_OCT_STEP) && ((d->flags & (SB200_FLAG_DOUBLE_STEP | SB200_FLAG_QUAD_STEP)) || !life_multi_accepts(*d, *pl, 8))) {
+        set_error("SB200_FLAG_OCT_STEP: experiment, needs a library built with -DSB200_LB_ONE_HALO_LANE=1 and the SB200_FLAG_QUAD_STEP layout");
+        return SB200_EUNSUPPORTED;
+    }
     if ((d->flags & SB200_FLAG_DOUBLE_STEP) && !life2_accepts(*d, *pl) && !diffusion2_accepts(*d, *pl)) {
         set_error("SB200_FLAG_DOUBLE_STEP: only Life / Moore(1) on an unpadded Bool or UInt8 grid with Wrap on axis 0, or "
                   "Diffusion / VonNeumann(1,3) on an unpadded Float32 / Float64 grid with Wrap on axes 0 and 1");
@@ -552,6 +556,27 @@ int32_t sb200_iterate(const sb200_desc* d, void* buf_a, void* buf_b, int32_t nst
     if (d->reducer == SB200_LIFE && d->eltype == SB200_U8) later.flags |= SB200_FLAG_CELLS_01;
     // Life: two generations per launch where the kernel supports it (half the HBM traffic per generation). The number
     // of single-generation launches in front is chosen so that the final buffer is the one the contract names.
+    // EXPERIMENT (SB200_OCT_STEP=1 and a library built with -DSB200_LB_ONE_HALO_LANE=1): the bulk of a long Life run as an EVEN
+    // number of eight-generation launches up front (the buffer roles are then those of a fresh call), the rest as below.
+    bool fresh = true;   // the next launch is the first one of the call (UInt8 cells not yet known to be 0/1)
+    if (d->reducer == SB200_LIFE && nsteps >= 48 && !halo && !(d->flags & (SB200_FLAG_DOUBLE_STEP | SB200_FLAG_QUAD_STEP | SB200_FLAG_OCT_STEP)) &&
+        getenv("SB200_OCT_STEP") && !getenv("SB200_NO_DOUBLE_STEP")) {
+        Plan* pl8 = nullptr;
+        sb200_desc probe = *d;
+        probe.flags |= SB200_FLAG_OCT_STEP;
+        if (get_plan(&probe, PK_GATHER, &pl8) == SB200_OK && life_multi_accepts(probe, *pl8, 8)) {
+            const int pairs = (nsteps - 16) / 16;   // keep at least 16 steps for the schedule below
+            for (int j = 0; j < 2 * pairs; j++) {
+                sb200_desc cur = fresh ? *d : later;
+                cur.flags |= SB200_FLAG_OCT_STEP;
+                const int rc = do_gather(&cur, s, t, (cudaStream_t)stream);
+                if (rc) return rc;
+                fresh = false;
+                void* tmp = s; s = t; t = tmp;
+            }
+            nsteps -= 16 * pairs;
+        }
+    }
     int singles = nsteps, doubles = 0;   // launches of 1 and 2 generations in front; the rest of the run is 4 (or 2) per launch
     int steady = 1;
     const bool life = d->reducer == SB200_LIFE;
@@ -584,7 +609,7 @@ int32_t sb200_iterate(const sb200_desc* d, void* buf_a, void* buf_b, int32_t nst
     auto body = [&](int i, int gens, void* from, void* to) -> int {
         int rc;
         if (halo && (rc = sb200_update_halo(d, from, stream))) return rc;
-        sb200_desc cur = i == 0 ? *d : later;
+        sb200_desc cur = (i == 0 && fresh) ? *d : later;
         if (gens == 2) cur.flags |= SB200_FLAG_DOUBLE_STEP;
         if (gens == 4) cur.flags |= SB200_FLAG_QUAD_STEP;
         return do_gather(&cur, from, to, (cudaStream_t)stream);

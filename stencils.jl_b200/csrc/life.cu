@@ -799,8 +799,9 @@ template <int G, bool CELLS01> static int launch_bit(const LifeParams& p, cudaSt
 bool life2_accepts(const sb200_desc& d, const Plan& pl) { return life_multi_accepts(d, pl, 2); }
 
 bool life_multi_accepts(const sb200_desc& d, const Plan& pl, int gens) {
-    if (gens == 4 && (d.born_mask != (1u << 3) || d.survive_mask != ((1u << 2) | (1u << 3)) || d.size[0] % 32 || getenv("SB200_NO_BITSLICE")))
-        return false;   // four generations: the bit-sliced B3/S23 kernel only
+    if (gens >= 4 && (d.born_mask != (1u << 3) || d.survive_mask != ((1u << 2) | (1u << 3)) || d.size[0] % 32 || getenv("SB200_NO_BITSLICE")))
+        return false;   // four (eight) generations: the bit-sliced B3/S23 kernel only
+    if (gens == 8 && !SB200_LB_ONE_HALO_LANE) return false;   // eight generations need the one-halo-lane layout (experiment)
     if (d.reducer != SB200_LIFE || d.ndim != 2 || (d.eltype != SB200_BOOL && d.eltype != SB200_U8)) return false;
     if (pl.shape_tag != SB200_MOORE || pl.shape_ndim != 2 || d.radius != 1 || d.noffsets != 8) return false;
     if (d.flags & (SB200_FLAG_NO_TMA | SB200_FLAG_FORCE_GENERIC)) return false;
@@ -869,6 +870,17 @@ int try_life_swar(const Plan& pl, const void* src, void* dst, cudaStream_t st) {
     // Bool cells are 0/1 by type; UInt8 cells are 0/1 when the caller says so (sb200_iterate does for every
     // step after the first, because the source is then this kernel's own output).
     const bool cells01 = d.eltype == SB200_BOOL || (d.flags & SB200_FLAG_CELLS_01);
+    if (d.flags & SB200_FLAG_OCT_STEP) {   // EXPERIMENT, only in builds with -DSB200_LB_ONE_HALO_LANE=1
+        if (!life_multi_accepts(d, pl, 8)) { set_error("eight generations per sweep: not supported by this build / layout / rule"); return SB200_EUNSUPPORTED; }
+#if SB200_LB_ONE_HALO_LANE
+        p.mirror = nullptr; p.m_lo = p.m_hi = 0;
+        const int rc = cells01 ? launch_bit<8, true>(p, st) : launch_bit<8, false>(p, st);
+        if (rc) return rc;
+        SB_LAUNCH_CHECK();
+        set_kernel_name(cells01 ? "life_bit_kernel<8,cells01>" : "life_bit_kernel<8,u8>");
+        return SB200_OK;
+#endif
+    }
     if (d.flags & SB200_FLAG_QUAD_STEP) {
         if (!life_multi_accepts(d, pl, 4)) { set_error("four generations per sweep: layout / boundary / rule not supported"); return SB200_EUNSUPPORTED; }
         p.mirror = nullptr; p.m_lo = p.m_hi = 0;

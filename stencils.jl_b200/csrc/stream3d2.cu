@@ -449,7 +449,7 @@ template <typename T, bool PAD> static int d2_launch(D2Params<T>& p, cudaStream_
 bool diffusion2_accepts(const sb200_desc& d, const Plan& pl) {
     if (d.reducer != SB200_DIFFUSION || d.ndim != 3 || (d.eltype != SB200_F32 && d.eltype != SB200_F64)) return false;
     if (pl.shape_tag != SB200_VONNEUMANN || pl.shape_ndim != 3 || d.radius != 1 || d.noffsets != 6) return false;
-    if (d.flags & (SB200_FLAG_NO_TMA | SB200_FLAG_FORCE_GENERIC | SB200_FLAG_QUAD_STEP)) return false;
+    if (d.flags & (SB200_FLAG_NO_TMA | SB200_FLAG_FORCE_GENERIC | SB200_FLAG_QUAD_STEP | SB200_FLAG_OCT_STEP)) return false;
     const long long es = (long long)elsize(d.eltype);
     for (int a = 0; a < 3; a++) {
         if (d.src_off[a] != 0 || d.dst_off[a] != 0 || d.dst_ext[a] != d.size[a] || d.src_ext[a] != d.size[a]) return false;

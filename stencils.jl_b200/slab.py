@@ -182,6 +182,8 @@ class SlabIterator:
         self.double_ok = (reducer == A.LIFE and t.is_cuda and compute is None and self.bc_split == A.WRAP and self.k >= 2 and
                           self.n_local >= 4 * self.G + 64 and os.environ.get("SB200_DOUBLE_STEP", "1") != "0")
         self.quad_ok = self.double_ok and self.k >= 4 and os.environ.get("SB200_QUAD_STEP", "1") != "0"
+        # EXPERIMENT: eight generations per launch (library built with -DSB200_LB_ONE_HALO_LANE=1), opt-in
+        self.oct_ok = self.quad_ok and self.k >= 8 and os.environ.get("SB200_OCT_STEP", "0") == "1"
         # two diffusion steps per launch (csrc/stream3d2.cu): same schedule; SB200_DIFFUSION_DOUBLE_STEP=0 turns it off
         if (reducer == A.DIFFUSION and t.is_cuda and compute is None and self.bc_split == A.WRAP and self.k >= 2 and
                 self.n_local >= 4 * self.G and os.environ.get("SB200_DIFFUSION_DOUBLE_STEP", A.DIFFUSION_DOUBLE_STEP_DEFAULT) != "0"):
@@ -215,7 +217,7 @@ class SlabIterator:
     def _desc(self, lo_plane, hi_plane, mirror=None):
         """descriptor whose output region is parent planes [lo_plane, hi_plane) of the split axis; mirror =
         (peer pointer, first plane, end plane): those planes are also stored into the peer's landing slot by the sweep"""
-        flags = (self._later_flags if self._nsweeps > 0 else 0) | {1: 0, 2: A.FLAG_DOUBLE_STEP, 4: A.FLAG_QUAD_STEP}[self._gen]
+        flags = (self._later_flags if self._nsweeps > 0 else 0) | {1: 0, 2: A.FLAG_DOUBLE_STEP, 4: A.FLAG_QUAD_STEP, 8: A.FLAG_OCT_STEP}[self._gen]
         key = (lo_plane, hi_plane, flags, mirror)
         if key not in self._descs:
             lo = (0,) * (self.nd - 1) + (lo_plane,)
@@ -314,11 +316,15 @@ class SlabIterator:
             # Life: four / two generations per launch (SB200_FLAG_QUAD_STEP / _DOUBLE_STEP) while the cycle has room
             room = self.k - self.steps_since_exchange
             m = 4 if (self.quad_ok and left >= 4 and room >= 4) else (2 if (self.double_ok and left >= 2 and room >= 2) else 1)
+            if self.oct_ok and left >= 8 and room >= 8:
+                m = 8
             if m > 1:
                 try:
                     self._step_one(torch, m)
                 except A.ArgumentError:   # the library declined this layout / rule: fewer generations per launch from now on
-                    if m == 4:
+                    if m == 8:
+                        self.oct_ok = False
+                    elif m == 4:
                         self.quad_ok = False
                     else:
                         self.double_ok = False

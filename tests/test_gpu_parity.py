@@ -681,3 +681,38 @@ def test_diffusion_two_steps_per_launch_remove_axes(orc, dt, monkeypatch):
             got, _ = gpu_gather(build_desc(flags=A.FLAG_DOUBLE_STEP, **kw), g, dst_like(h1))
             assert l.sb200_last_kernel() == b"stream3d2_kernel"
             bits_equal(got, want)
+
+
+@pytest.mark.skipif(not __import__("os").environ.get("SB200_EXPERIMENTS"),
+                    reason="experiment prepared without GPU time left in round 1: needs SB200_EXPERIMENTS=1 and SB200_LIB pointing at a "
+                           "library built with tools/build_variant.sh hl1 life.cu -DSB200_LB_ONE_HALO_LANE=1")
+def test_life_eight_generations_per_launch(orc, monkeypatch):
+    """SB200_FLAG_OCT_STEP (one-halo-lane build of life_bit_kernel): dest = step^8(src) against eight oracle sweeps, an interior
+    region, and sb200_iterate with SB200_OCT_STEP=1 for step counts of every residue mod 16."""
+    from tests.util import stream, sync, to_dev, to_host
+    rng = np.random.default_rng(53)
+    l = A.lib()
+    moore = npr.offsets("Moore", 1, 2)
+    for (W, H), bc1 in [((1024, 96), A.WRAP), ((3840 + 512, 67), A.WRAP), ((4096, 40), A.REFLECT), ((8192 + 1024, 130), A.WRAP)]:
+        g = np.asfortranarray(((rng.random((W, H)) < 0.4) * rng.integers(1, 255, size=(W, H))).astype(np.uint8))
+        kw = dict(size=(W, H), eltype=A.U8, out_eltype=A.U8, offsets=moore, radius=1, boundary=(A.WRAP, bc1), reducer=A.LIFE)
+        h1 = build_desc(**kw)
+        want = g
+        for _ in range(8):
+            want = orc.gather(h1, want, dst_like(h1))
+        got, _ = gpu_gather(build_desc(flags=A.FLAG_OCT_STEP, **kw), g, dst_like(h1))
+        assert l.sb200_last_kernel().startswith(b"life_bit_kernel<8")
+        bits_equal(got, want)
+        hr = build_desc(flags=A.FLAG_OCT_STEP, region=((0, 8, 0), (W, H - 8, 0)), **kw)
+        got, _ = gpu_gather(hr, g, dst_like(hr, 7))
+        want_r = dst_like(hr, 7)
+        want_r[:, 8:H - 8] = want[:, 8:H - 8]
+        bits_equal(got, want_r)
+        monkeypatch.setenv("SB200_OCT_STEP", "1")
+        for n in (48, 49, 50, 55, 63, 64, 65, 79, 80, 97):
+            want_n = orc.iterate(h1, g.copy(order="F"), np.zeros_like(g, order="F"), n)
+            ta, tb = to_dev(g), to_dev(np.zeros_like(g, order="F"))
+            A.check(l.sb200_iterate(h1.ptr(), ta.data_ptr(), tb.data_ptr(), n, stream()))
+            sync()
+            bits_equal(to_host(ta if n % 2 == 0 else tb, g.shape, g.dtype), want_n)
+        monkeypatch.delenv("SB200_OCT_STEP")
