@@ -2,7 +2,7 @@
 // dest = f(f(src)), the intermediate state never touches memory, so an iterated run (SwitchingStencilArray,
 // src/gatherstencil.jl:77-83 called in a loop) moves half the HBM bytes per step.
 //
-// Same 2.5-D streaming structure as stream3d.cu: a CTA owns an (x,y) tile and marches along z; two producer warps feed
+// Same 2.5-D streaming structure as stream3d.cu: a CTA owns an (x,y) tile and marches along z; three producer warps feed
 // whole source rows (tile + 2 halo rows above / below, + 16 B halo left / right) through a ring of shared-memory
 // stages with cp.async.bulk. Per arriving source plane the 16 consumer warps
 //   level 1: complete one plane of the INTERMEDIATE state over the tile plus a one-cell rim (every cell once: a thread
@@ -17,14 +17,16 @@
 // PTX: no divergent branch), ring cursor and dest pointer advance incrementally: 256 instructions per source plane and
 // warp, 144 of them the flops. (Measured: r01g, first version, warp-private with a rim recomputed per warp: 27
 // instructions per cell-update, issue-bound, 3 % SLOWER than two single sweeps; r01h, shared intermediate plane: 855
-// Gcell-updates/s against 635 for single sweeps.)
+// Gcell-updates/s against 635 for single sweeps; r01i rim warp + predicated loads 938; r01j three producer warps 1092;
+// r01l final build 1095 Gcell-updates/s on 1024^3 Float32 = 1.36x the one-sweep HBM roofline.)
 // Fold order = the reference's offset order (src/stencils/vonneumman.jl:5-15), every operation rounded separately:
 // bit-identical to two single sweeps.
 //
 // Accepted: unpadded Float32 / Float64 parents, Wrap on axes 0 and 1, axis 2 Wrap or an output region that stays two
 // planes inside the parent (slab runs). Wrapped halo cells of the intermediate state are recomputed from wrapped source
 // cells in the same order, so they equal the cells they stand for bit for bit (a Reflect image would fold its
-// neighbours in the opposite order, which is why Reflect is not accepted; Remove would need padval selects).
+// neighbours in the opposite order, which is why Reflect is not accepted). Remove axes: the PAD instantiation below
+// (padval selects at both time levels), prepared but not yet run on a GPU, opt-in with SB200_D2_REMOVE=1.
 // Algorithmic traffic: sizeof(T) read + sizeof(T) written per cell per TWO steps.
 #include <algorithm>
 #include <cstdlib>
