@@ -1,0 +1,60 @@
+"""CPU models of kernel index logic (tools/model_*.py) as regression tests: the models transliterate the kernels' task / ring /
+lane arithmetic thread for thread and are compared with plain NumPy sweeps; here we also check that the constants the models
+use are the ones in the CUDA sources, so a kernel change without a model change fails on a box without a GPU."""
+import importlib.util
+import os
+import re
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _load(name):
+    spec = importlib.util.spec_from_file_location(name, os.path.join(ROOT, "tools", name + ".py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def _cu_const(text, name):
+    m = re.search(r"constexpr int (?:[A-Z0-9_]+ = [^,;]+, )?" + name + r" = ([^;,]+)[;,]", text)
+    assert m, name
+    return m.group(1).strip()
+
+
+def test_stream3d2_model_uses_the_kernel_constants():
+    m = _load("model_stream3d2")
+    cu = open(os.path.join(ROOT, "stencils.jl_b200", "csrc", "stream3d2.cu")).read()
+    assert re.search(r"constexpr int D2_WX = (\d+), D2_WY = (\d+);", cu).groups() == (str(m.WX), str(m.WY))
+    assert _cu_const(cu, "D2_RT") == str(m.RT)
+    assert _cu_const(cu, "D2_TY") == "(D2_WY - 1) * D2_RT" and m.TY == (m.WY - 1) * m.RT
+    assert _cu_const(cu, "D2_LEFT") == str(m.LEFT)
+    assert _cu_const(cu, "D2_ROWB") == "D2_LEFT + D2_TXB + 128" and m.ROWB == m.LEFT + m.TXB + 128
+    assert _cu_const(cu, "D2_ROWS") == "D2_TY + 4" and m.ROWS == m.TY + 4
+    assert _cu_const(cu, "D2_MROWS") == "D2_TY + 2" and m.MROWS == m.TY + 2
+    assert re.search(r"#define SB200_D2_STAGES (\d+)", cu).group(1) == str(m.STAGES)
+
+
+def test_stream3d2_model_matches_two_sweeps():
+    m = _load("model_stream3d2")
+    R, W = "remove", "wrap"
+    assert m.check((160, 17, 8), np.float32)                                   # Wrap, second x-warp partly active, ragged y
+    assert m.check((64, 30, 20), np.float32, ctas=4, force_nz=2)               # z-runs
+    assert m.check((40, 15, 12), np.float64)
+    assert m.check((128, 14, 16), np.float32, z_lo=3, zn=9, wrap_z=False)      # interior region (slab sweep)
+    assert m.check((300, 30, 8), np.float32, bcs=(R, R, None), pad=0.5, ctas=2, force_ty=14)   # PAD variant
+    assert m.check((64, 20, 9), np.float64, bcs=(R, W, R), pad=0.25)
+
+
+def test_life_bit_lane_scheme_needs_one_halo_lane():
+    m = _load("model_life_bit_lanes")
+    rng = np.random.default_rng(2)
+    for G in (2, 4, 8):
+        f = (rng.random((40, 1024 + 256)) < 0.4).astype(np.uint8)
+        want = f
+        for _ in range(G):
+            want = m.true_life(want)
+        got = m.scheme(f, G, 128)
+        exact = (got == want[:, 128:128 + 1024]).all(0).reshape(32, 32).all(1)
+        assert exact[1:31].all()            # lanes 1 .. 30 are exact whatever G
