@@ -117,6 +117,59 @@ function Base.Array(A::B200Array{T,N}) where {T,N}
     h
 end
 
+# ---- array plumbing (SURVEY §8f.3): what StencilArray / SwitchingStencilArray need from their parent ----
+# The reference only ever calls size / similar / copyto! / fill! / parent-indexing on the parent array
+# (src/array.jl:249-309 `similar` / `copy` rules, 367-385 halo views, 564-611 SwitchingStencilArray); scalar getindex on a
+# device buffer is allowed (tests index single cells) but goes through a one-element D2H copy.
+Base.IndexStyle(::Type{<:B200Array}) = IndexLinear()
+Base.similar(A::B200Array{T}) where T = B200Array{T}(undef, size(A))
+Base.similar(A::B200Array{T}, dims::Dims) where T = B200Array{T}(undef, dims)
+Base.similar(A::B200Array, ::Type{T}) where T = B200Array{T}(undef, size(A))
+function Base.copyto!(dst::B200Array{T}, src::Array{T}) where T
+    length(dst) == length(src) || throw(DimensionMismatch("copyto!: $(size(dst)) vs $(size(src))"))
+    check(ccall((:sb200_memcpy_h2d, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Csize_t, Ptr{Cvoid}), dst.ptr, src, sizeof(src), C_NULL))
+    check(ccall((:sb200_stream_sync, LIB), Int32, (Ptr{Cvoid},), C_NULL))
+    dst
+end
+function Base.copyto!(dst::Array{T}, src::B200Array{T}) where T
+    length(dst) == length(src) || throw(DimensionMismatch("copyto!: $(size(dst)) vs $(size(src))"))
+    check(ccall((:sb200_memcpy_d2h, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Csize_t, Ptr{Cvoid}), dst, src.ptr, sizeof(dst), C_NULL))
+    check(ccall((:sb200_stream_sync, LIB), Int32, (Ptr{Cvoid},), C_NULL))
+    dst
+end
+function Base.copyto!(dst::B200Array{T}, src::B200Array{T}) where T
+    length(dst) == length(src) || throw(DimensionMismatch("copyto!: $(size(dst)) vs $(size(src))"))
+    check(ccall((:sb200_memcpy_d2d, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Csize_t, Ptr{Cvoid}), dst.ptr, src.ptr, length(src) * sizeof(T), C_NULL))
+    dst
+end
+Base.copy(A::B200Array) = copyto!(similar(A), A)
+function Base.fill!(A::B200Array{T}, x) where T
+    v = convert(T, x)
+    if all(iszero, reinterpret(UInt8, [v]))   # the ABI has a byte memset; anything else goes through the host
+        check(ccall((:sb200_memset, LIB), Int32, (Ptr{Cvoid}, Int32, Csize_t, Ptr{Cvoid}), A.ptr, 0, length(A) * sizeof(T), C_NULL))
+    else
+        copyto!(A, fill(v, size(A)))
+    end
+    A
+end
+function Base.getindex(A::B200Array{T}, i::Int) where T   # cold path: one element over PCIe
+    @boundscheck checkbounds(A, i)
+    r = Ref{T}()
+    check(ccall((:sb200_memcpy_d2h, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Csize_t, Ptr{Cvoid}), r, A.ptr + (i - 1) * sizeof(T), sizeof(T), C_NULL))
+    check(ccall((:sb200_stream_sync, LIB), Int32, (Ptr{Cvoid},), C_NULL))
+    r[]
+end
+function Base.setindex!(A::B200Array{T}, x, i::Int) where T
+    @boundscheck checkbounds(A, i)
+    r = Ref{T}(convert(T, x))
+    check(ccall((:sb200_memcpy_h2d, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Csize_t, Ptr{Cvoid}), A.ptr + (i - 1) * sizeof(T), r, sizeof(T), C_NULL))
+    check(ccall((:sb200_stream_sync, LIB), Int32, (Ptr{Cvoid},), C_NULL))
+    x
+end
+Base.:(==)(A::B200Array, B::AbstractArray) = Array(A) == B
+Base.:(==)(A::AbstractArray, B::B200Array) = A == Array(B)
+Base.:(==)(A::B200Array, B::B200Array) = Array(A) == Array(B)
+
 pad3(t, fill) = ntuple(i -> i <= length(t) ? t[i] : fill, 3)
 
 "Descriptor from a StencilArray pair; `keep` holds the arrays the pointers refer to."
