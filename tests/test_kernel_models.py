@@ -58,3 +58,15 @@ def test_life_bit_lane_scheme_needs_one_halo_lane():
         got = m.scheme(f, G, 128)
         exact = (got == want[:, 128:128 + 1024]).all(0).reshape(32, 32).all(1)
         assert exact[1:31].all()            # lanes 1 .. 30 are exact whatever G
+
+
+def test_life_bit_strip_decomposition_covers_every_column_once():
+    """launch_bit's strips / warps / lanes for the measured layout (G - 1 halo lanes) and the one-halo-lane experiment."""
+    m = _load("model_life_bit_lanes")
+    cu = open(os.path.join(ROOT, "stencils.jl_b200", "csrc", "life.cu")).read()
+    assert "constexpr int LB_WARPS = 6;" in cu and "constexpr int LB_ROWB = 6144;" in cu
+    assert "static constexpr int HL = HLN * 32 + 16;" in cu and "static constexpr int VALID = 32 - 2 * HLN;" in cu
+    for W in (1024, 4352, 16384):
+        for G, one in ((2, False), (4, False), (4, True), (8, True)):
+            stored, inside = m.strip_cover(W, G, one)
+            assert (stored == 1).all() and inside, (W, G, one)

@@ -57,3 +57,52 @@ def main():
 
 if __name__ == "__main__":
     main()
+
+
+def strip_cover(W, G, one_halo_lane, warps=6, rowb=6144):
+    """launch_bit / life_bit_kernel's column decomposition (strips, warps, lanes): returns how often each column of a row is stored
+    and whether every active lane's inputs (its 32 cells, its neighbours' words, the end lanes' halo byte) lie inside the halo the
+    producer copies."""
+    hln = 1 if one_halo_lane else G - 1
+    valid = 32 - 2 * hln
+    wo, hl = valid * 32, hln * 32 + 16
+    cap = warps * wo
+    d0 = (128 - hl % 128) % 128
+    assert d0 + 2 * hl + cap <= rowb and cap % 128 == 0
+    nstrips = (W + cap - 1) // cap
+    outb = min(cap, ((W + nstrips - 1) // nstrips + 127) // 128 * 128)
+    nstrips = (W + outb - 1) // outb
+    stored = np.zeros(W, int)
+    inside = True
+    for strip in range(nstrips):
+        x0 = strip * outb
+        wout = min(outb, W - x0)
+        for w in range(warps):
+            if w * wo >= wout:
+                continue
+            for lane in range(32):
+                cell0 = w * wo + (lane - hln) * 32
+                if hln <= lane <= 31 - hln and cell0 < wout:
+                    stored[x0 + cell0:x0 + cell0 + 32] += 1
+            # the warp reads cells [w*wo - hln*32 - 1, w*wo + (32 - hln)*32 + 1) relative to x0; the row holds [-hl, wout + hl).
+            # Lanes whose cells start beyond wout + hl read stale shared memory, which is harmless as long as no ACTIVE lane's
+            # dependence cone (G cells to either side after G generations) reaches them.
+            last_active = max(l for l in range(32) if hln <= l <= 31 - hln and w * wo + (l - hln) * 32 < wout)
+            need_hi = w * wo + (last_active - hln) * 32 + 32 + G
+            inside &= (w * wo - hln * 32 - 1 >= -hl) and (need_hi <= wout + hl)
+    return stored, inside
+
+
+def check_strips():
+    ok = True
+    for W in (1024, 4096, 4352, 9216, 16384, 32768):
+        for G, one in ((2, False), (4, False), (2, True), (4, True), (8, True)):
+            stored, inside = strip_cover(W, G, one)
+            good = (stored == 1).all() and inside
+            ok &= good
+            print(f"W = {W:5d}, G = {G}, {'one halo lane ' if one else 'G-1 halo lanes'}: every column stored once = {(stored == 1).all()}, inputs inside the copied halo = {inside}")
+    return ok
+
+
+if __name__ == "__main__":
+    raise SystemExit(0 if check_strips() else 1)
