@@ -285,3 +285,15 @@ def test_multi_stencilarray_mapstencil(orc):
     want = (np.float32(0.25) * t1 + t2) + np.float32(-1.5) * t3
     assert want.dtype == np.float32
     bits_equal(host(got), want)
+
+
+def test_torch_free_case_table_matches_oracle():
+    """tests/sanitize_cases.py (the compute-sanitizer driver: every kernel family on exact cudaMalloc allocations, no torch)
+    as a plain parity run: every case bit-identical to the oracle."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tests", "sanitize_cases.py")], cwd=root, capture_output=True, text=True,
+                       timeout=600)
+    assert r.returncode == 0 and "all cases match the oracle" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
