@@ -81,6 +81,9 @@ template <typename T> struct D2Params {
     // PAD kernel only (appended so that the Wrap kernel's parameter layout is unchanged)
     int bc0, bc1;            // boundaries of axes 0 and 1: SB200_WRAP or SB200_REMOVE
     T pad;                   // Remove(padval)
+    // MIRROR kernel only: fused ghost-plane push, output planes [m_lo, m_hi) are also stored here (plane m_lo first)
+    T* mirror;
+    int m_lo, m_hi;
 };
 
 __device__ __forceinline__ long long d2_wrap(int r, int n) { return r < 0 ? r + n : (r >= n ? r - n : r); }
@@ -204,7 +207,10 @@ __device__ __forceinline__ void d2_plane<float, 4>(float (&done)[4], float (&cpr
 // source cells AND out-of-bounds cells of the intermediate state read padval (Remove boundary: the second sweep sees
 // padval outside the array, not an update of it). Rows / planes / edge halos outside the array are not copied; the values
 // are substituted by selects. PAD = false is the measured Wrap kernel, its code is untouched (if constexpr).
-template <typename T, bool PAD>
+// MIRROR = true: EXPERIMENT (not yet run on a GPU; SB200_D2_MIRROR=1): the planes a neighbour GPU needs are also stored into
+// its landing slot by the sweep itself (sb200_desc.mirror_*), like stream3d_kernel's MIRROR variant; without it do_gather copies
+// them after the sweep (r01m: 0.954 weak-scaling efficiency at 2 GPUs against 0.999 for the single-step kernel with fused stores).
+template <typename T, bool PAD, bool MIRROR>
 __global__ void __launch_bounds__(D2_THREADS, 1) stream3d2_kernel(const __grid_constant__ D2Params<T> p) {
     constexpr int VX = 16 / (int)sizeof(T);
     const bool padx = PAD && p.bc0 == SB200_REMOVE, pady = PAD && p.bc1 == SB200_REMOVE, padz = PAD && p.bc2 == SB200_REMOVE;
@@ -330,6 +336,8 @@ __global__ void __launch_bounds__(D2_THREADS, 1) stream3d2_kernel(const __grid_c
 #pragma unroll
         for (int r = 0; r < D2_RT; r++) rowok[r] = lvl2 && xact && y0 + r1 + r < p.Y && r1 + r < p.ty;
         T* __restrict__ dptr = p.dst + (long long)(y0 + r1) * p.p1 + gx + (long long)(z0 - 4) * p.p2;
+        T* mptr = nullptr;   // MIRROR: where output plane z0-4+i of this thread's rows lands in the neighbour's slot
+        if constexpr (MIRROR) mptr = p.mirror + (long long)(y0 + r1) * p.p1 + gx + (long long)(z0 - 4 - p.m_lo) * p.p2;
         const bool l0 = lane == 0, l31 = lane == 31;
         int slot = k % D2_STAGES;
         unsigned phase = (k / D2_STAGES) & 1;
@@ -407,20 +415,25 @@ __global__ void __launch_bounds__(D2_THREADS, 1) stream3d2_kernel(const __grid_c
                     T out[VX];
                     d2_plane<T, VX>(out, c2[r], q2[r], cc, ym, yp, l_, r_, p.alpha);
                     if (store && rowok[r]) d2_st<T, VX>(dptr + (long long)r * p.p1, out);
+                    if constexpr (MIRROR) {
+                        const int zo = z0 - 4 + i;
+                        if (store && rowok[r] && zo >= p.m_lo && zo < p.m_hi) d2_st<T, VX>(mptr + (long long)r * p.p1, out);
+                    }
                 }
             }
+            if constexpr (MIRROR) mptr += p.p2;
             dptr += p.p2;
             if (++slot == D2_STAGES) { slot = 0; phase ^= 1; }
         }
     }
 }
 
-template <typename T, bool PAD> static int d2_launch(D2Params<T>& p, cudaStream_t st) {
+template <typename T, bool PAD, bool MIRROR> static int d2_launch(D2Params<T>& p, cudaStream_t st) {
     static thread_local int cfg_dev = -1;
     int dev = 0;
     SB_CUDA(cudaGetDevice(&dev));
     if (dev != cfg_dev) {
-        SB_CUDA(cudaFuncSetAttribute(stream3d2_kernel<T, PAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, D2_SMEM));
+        SB_CUDA(cudaFuncSetAttribute(stream3d2_kernel<T, PAD, MIRROR>, cudaFuncAttributeMaxDynamicSharedMemorySize, D2_SMEM));
         cfg_dev = dev;
     }
     const long long ctas = num_sms();   // one CTA per SM (the ring takes most of the shared memory)
@@ -442,7 +455,7 @@ template <typename T, bool PAD> static int d2_launch(D2Params<T>& p, cudaStream_
     p.nzruns = best;
     const long long ntasks = (long long)p.ntx * p.nty * p.nzruns;
     const long long grid = std::min<long long>(ctas, ntasks);
-    stream3d2_kernel<T, PAD><<<(unsigned)grid, D2_THREADS, D2_SMEM, st>>>(p);
+    stream3d2_kernel<T, PAD, MIRROR><<<(unsigned)grid, D2_THREADS, D2_SMEM, st>>>(p);
     SB_LAUNCH_CHECK();
     return SB200_OK;
 }
@@ -487,8 +500,14 @@ template <typename T> static int d2_try(const Plan& pl, const void* src, void* d
     memcpy(&p.pad, &d.padval_bits, sizeof(T));
     const long long lo = pl.dd.lo[2], hi = lo + pl.dd.n[2];
     const bool z_remove = d.boundary[2] == SB200_REMOVE && !(lo >= 2 && hi + 2 <= d.size[2]);
-    if (d.boundary[0] == SB200_REMOVE || d.boundary[1] == SB200_REMOVE || z_remove) return d2_launch<T, true>(p, st);
-    return d2_launch<T, false>(p, st);
+    p.mirror = nullptr; p.m_lo = p.m_hi = 0;
+    if (d.boundary[0] == SB200_REMOVE || d.boundary[1] == SB200_REMOVE || z_remove) return d2_launch<T, true, false>(p, st);
+    if (g_mirror.ptr && getenv("SB200_D2_MIRROR")) {   // experiment: fused ghost-plane push (Wrap kernel only)
+        p.mirror = (T*)g_mirror.ptr; p.m_lo = (int)g_mirror.lo; p.m_hi = (int)g_mirror.hi;
+        g_mirror.honoured = true;
+        return d2_launch<T, false, true>(p, st);
+    }
+    return d2_launch<T, false, false>(p, st);
 }
 
 int try_diffusion3d_double(const Plan& pl, const void* src, void* dst, cudaStream_t st) {
