@@ -13,6 +13,7 @@
  *   sb200_scatter      <- scatterstencil!(f, op, dest, source)           src/scatterstencil.jl:36-112
  *   sb200_iterate      <- loop of gatherstencil!(f, A::SwitchingStencilArray) + switch(A)
  *                                                                        src/gatherstencil.jl:77-83, src/array.jl:610-611
+ *   sb200_plan_*       <- the same loop over an array split into slabs across the GPUs of one box
  *   sb200_gather_multi <- gatherstencil!(f, dest, A1, A2, ...) extra-array forms   src/gatherstencil.jl:84-88,112-113
  *   sb200_stencil_offsets <- offsets(::Type{<:Stencil})                  src/stencils/{*}.jl
  *   sb200_out_eltype   <- _return_type                                   src/gatherstencil.jl:41-59
@@ -169,8 +170,8 @@ typedef struct sb200_desc {
 #define SB200_FLAG_CELLS_01 8      /* LIFE on UInt8: the caller guarantees every source cell is 0 or 1 */
 #define SB200_FLAG_QUAD_STEP 32   /* dest = f(f(f(f(src)))): four generations per launch (B3/S23 Life, axis 0 a multiple of 32
                                      cells, otherwise as SB200_FLAG_DOUBLE_STEP); the bit-sliced kernel */
-#define SB200_FLAG_OCT_STEP 64    /* EXPERIMENT: eight generations per launch (as SB200_FLAG_QUAD_STEP; needs a library built with
-                                     -DSB200_LB_ONE_HALO_LANE=1, otherwise SB200_EUNSUPPORTED) */
+#define SB200_FLAG_OCT_STEP 64    /* eight generations per launch (as SB200_FLAG_QUAD_STEP; a library built with
+                                     -DSB200_LB_ONE_HALO_LANE=0 answers SB200_EUNSUPPORTED) */
 #define SB200_FLAG_DOUBLE_STEP 16 /* dest = f(f(src)): two sweeps fused in one launch, the intermediate state never touches
                                      memory. LIFE: Moore(1), unpadded, Wrap on axis 0. DIFFUSION: VonNeumann(1,3), unpadded
                                      Float32 / Float64, Wrap on axes 0 and 1, axis 2 Wrap or an output region two planes
@@ -258,6 +259,93 @@ int32_t sb200_push_planes(const void* src, void* peer_dst, size_t bytes, uint32_
 int32_t sb200_signal_flag(uint32_t* peer_flag, uint32_t value, void* stream);
 /* Stream-ordered wait until *flag >= value (acquire). */
 int32_t sb200_wait_flag(const uint32_t* flag, uint32_t value, void* stream);
+
+/* Releases everything the library keeps between calls on the CURRENT device and thread: cached plans (device offset / weight
+   tables), the host-buffer scratch of sb200_gather_host / sb200_iterate_host, the scratch of sb200_gather_multi. The caller
+   guarantees that no call of the library is in flight. */
+int32_t sb200_shutdown(void);
+
+/* ---- slab-partitioned iterated sweeps: the multi-GPU form of the SwitchingStencilArray loop ----
+ *
+ *   loop of  A = gatherstencil!(f, A::SwitchingStencilArray)             src/gatherstencil.jl:77-83, src/array.jl:610-611
+ *
+ * with A split into slabs along its LAST axis, one slab per GPU (the reference itself has no multi-device
+ * path). A plan owns, per slab: two parents [G ghost planes | owned planes | G ghost planes] (the double buffer of the
+ * SwitchingStencilArray), a mailbox (landing slots for the neighbours' planes + flags), two streams, events; and the cycle
+ * schedule: ghosts are exchanged every G / radius generations, the boundary planes of the last sweep of a cycle are stored
+ * straight into the neighbour's mailbox over NVLink by the sweep kernel and pulled into the ghost zones on a side stream
+ * while the interior sweep runs. Results are bit-identical to sb200_iterate on the undivided array for any number of
+ * slabs and any G.
+ *
+ * `global` describes the UNDIVIDED array: unpadded (src_off = dst_off = 0, ext = size), out_eltype == eltype, boundary
+ * per axis (Wrap / Remove / Reflect on the split axis), region / mirror fields unused.
+ *
+ * Two ways to build a plan:
+ *   sb200_plan_create       one process drives every GPU (what a Julia session does): slab i lives on devices[i]; a device
+ *                           may appear more than once (several slabs on one GPU — how the 1-GPU tests exercise the exchange).
+ *                           Neighbours are ordered by CUDA events.
+ *   sb200_plan_create_rank  one process per GPU (torchrun / MPI): this process owns slab `rank` of `world` on its current
+ *                           device; exchange sb200_plan_ipc_handle() results between the processes by any means and hand
+ *                           all of them to sb200_plan_connect(). Neighbours are ordered by system-scope flags in peer memory.
+ */
+typedef struct sb200_plan sb200_plan;
+
+#define SB200_PLAN_OVERLAP_OFF 1   /* never overlap the exchange with the interior sweep */
+#define SB200_PLAN_OVERLAP_ON 2    /* always (default: when a ghost zone is >= 1 MiB) */
+#define SB200_PLAN_SINGLE_STEP 4   /* one generation per launch only */
+#define SB200_PLAN_FLAGS_SYNC 8    /* sb200_plan_create: order neighbours with the flag protocol of the rank form (testing) */
+
+int32_t sb200_plan_create(const sb200_desc* global, int32_t nslabs, const int32_t* devices, int32_t ghost,
+                          int32_t plan_flags, sb200_plan** out);
+int32_t sb200_plan_create_rank(const sb200_desc* global, int32_t rank, int32_t world, int32_t ghost, int32_t plan_flags,
+                               sb200_plan** out);
+int32_t sb200_plan_ipc_handle(sb200_plan* p, void* handle64);
+/* handles: world x 64 bytes, handles[r] from rank r */
+int32_t sb200_plan_connect(sb200_plan* p, const void* handles);
+
+/* Slab i of THIS plan (rank form: i = 0): owned planes [*lo, *hi) of the global last axis, the device it lives on and
+   the device pointer of its first owned plane in the CURRENT state (valid until the next sb200_plan_iterate). */
+int32_t sb200_plan_nslabs(const sb200_plan* p, int32_t* n);
+int32_t sb200_plan_slab(sb200_plan* p, int32_t i, int64_t* lo, int64_t* hi, int32_t* device, void** owned);
+/* The caller has written the owned planes through the pointers of sb200_plan_slab (device-side initialisation): the ghost
+   planes are stale and UInt8 Life cells are no longer known to be 0/1. (A new plan starts in this state.) */
+int32_t sb200_plan_mark_dirty(sb200_plan* p);
+/* Copy the state in / out. `state_host` addresses the planes this plan owns, contiguous: the whole array in the
+   single-process form, the rank's slab in the rank form. Blocking. */
+int32_t sb200_plan_load_host(sb200_plan* p, const void* state_host);
+int32_t sb200_plan_store_host(sb200_plan* p, void* state_host);
+/* Enqueue nsteps generations on the plan's streams (returns at once); sb200_plan_sync waits for them and reports a
+   ghost exchange that timed out (a dead neighbour) as SB200_ECUDA instead of hanging the GPU. */
+int32_t sb200_plan_iterate(sb200_plan* p, int32_t nsteps);
+int32_t sb200_plan_sync(sb200_plan* p);
+/* sb200_plan_iterate bracketed by CUDA events on every slab's compute stream + sb200_plan_sync; *ms = the slowest slab. */
+int32_t sb200_plan_iterate_timed(sb200_plan* p, int32_t nsteps, float* ms);
+/* out[0] generations done, [1] sweep launches, [2] ghost exchanges, [3] ghost planes G, [4] generations per exchange,
+   [5] 1 if exchanges overlap the interior sweep, [6] largest generations per launch in use, [7] 1 = event-ordered, 2 = flags. */
+int32_t sb200_plan_stats(const sb200_plan* p, int64_t out[8]);
+int32_t sb200_plan_destroy(sb200_plan* p);
+
+/* The schedule a plan runs, as data (diagnostics + CPU tests: the list is interpreted there with a CPU sweep plugged in).
+   Planes: >= 0 counted from the start of a slab's parent, < 0 from its end (ext + value). */
+enum { SB200_SLAB_SWEEP = 1, SB200_SLAB_PUSH = 2, SB200_SLAB_SIGNAL = 3, SB200_SLAB_PULL = 4, SB200_SLAB_JOIN = 5,
+       SB200_SLAB_ENDFILL = 6, SB200_SLAB_SWAP = 7 };
+enum { SB200_SLAB_CUR = 0, SB200_SLAB_NXT = 1 };
+enum { SB200_SLAB_MIRROR_DOWN = 1, SB200_SLAB_MIRROR_UP = 2 };
+typedef struct sb200_slab_op {
+    int32_t kind;   /* SB200_SLAB_* */
+    int32_t gens;   /* SWEEP: generations in this launch */
+    int32_t mirror; /* SWEEP: also store owned planes [G, 2G) into the lower neighbour's slot (DOWN) / [n, n+G) into the upper's (UP) */
+    int32_t buf;    /* PUSH / PULL / ENDFILL: SB200_SLAB_CUR or SB200_SLAB_NXT */
+    int32_t async;  /* PULL: on the side stream, overlapping the next sweep, closed by JOIN */
+    int32_t first;  /* SWEEP: the very first sweep of the plan (UInt8 Life cells not yet known to be 0/1) */
+    int64_t lo, hi; /* SWEEP: parent planes [lo, hi) of the split axis (signed encoding) */
+} sb200_slab_op;
+/* Ops of `nsteps` generations for a plan with radius R, G ghost planes, `n_min` owned planes in its thinnest slab, starting
+   `since` generations after an exchange (G / R = ghosts stale). Launches of `gens` > 1 generations are taken when gens <=
+   max_gens and the sweep covers at least `min_planes_multi` planes. *since_out receives the state after the steps. */
+int32_t sb200_slab_schedule(int32_t radius, int32_t ghost, int64_t n_min, int32_t split_wrap, int32_t overlap,
+                            int32_t max_gens, int32_t min_planes_multi, int32_t since, int32_t first_sweep, int32_t nsteps,
+                            sb200_slab_op* ops, int32_t cap, int32_t* count, int32_t* since_out);
 
 #ifdef __cplusplus
 }

@@ -68,6 +68,18 @@ class Term(C.Structure):
                 ("coef", C.c_double)]
 
 
+class SlabOp(C.Structure):
+    """sb200_slab_op (include/stencils_b200.h)"""
+    _fields_ = [("kind", C.c_int32), ("gens", C.c_int32), ("mirror", C.c_int32), ("buf", C.c_int32), ("async_", C.c_int32),
+                ("first", C.c_int32), ("lo", C.c_int64), ("hi", C.c_int64)]
+
+
+SLAB_SWEEP, SLAB_PUSH, SLAB_SIGNAL, SLAB_PULL, SLAB_JOIN, SLAB_ENDFILL, SLAB_SWAP = range(1, 8)
+SLAB_CUR, SLAB_NXT = 0, 1
+SLAB_MIRROR_DOWN, SLAB_MIRROR_UP = 1, 2
+PLAN_OVERLAP_OFF, PLAN_OVERLAP_ON, PLAN_SINGLE_STEP, PLAN_FLAGS_SYNC = 1, 2, 4, 8
+
+
 class ArgumentError(ValueError):
     """Julia's ArgumentError: unsupported user function / eltype / shape, size mismatch."""
 
@@ -107,6 +119,25 @@ _SIGS = {
     "sb200_push_planes": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_uint32, C.c_void_p]),
     "sb200_signal_flag": (C.c_int32, [C.c_void_p, C.c_uint32, C.c_void_p]),
     "sb200_wait_flag": (C.c_int32, [C.c_void_p, C.c_uint32, C.c_void_p]),
+    "sb200_shutdown": (C.c_int32, []),
+    "sb200_plan_create": (C.c_int32, [C.POINTER(Desc), C.c_int32, C.POINTER(C.c_int32), C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]),
+    "sb200_plan_create_rank": (C.c_int32, [C.POINTER(Desc), C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]),
+    "sb200_plan_ipc_handle": (C.c_int32, [C.c_void_p, C.c_void_p]),
+    "sb200_plan_connect": (C.c_int32, [C.c_void_p, C.c_void_p]),
+    "sb200_plan_nslabs": (C.c_int32, [C.c_void_p, C.POINTER(C.c_int32)]),
+    "sb200_plan_slab": (C.c_int32, [C.c_void_p, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int32),
+                                    C.POINTER(C.c_void_p)]),
+    "sb200_plan_mark_dirty": (C.c_int32, [C.c_void_p]),
+    "sb200_plan_load_host": (C.c_int32, [C.c_void_p, C.c_void_p]),
+    "sb200_plan_store_host": (C.c_int32, [C.c_void_p, C.c_void_p]),
+    "sb200_plan_iterate": (C.c_int32, [C.c_void_p, C.c_int32]),
+    "sb200_plan_sync": (C.c_int32, [C.c_void_p]),
+    "sb200_plan_iterate_timed": (C.c_int32, [C.c_void_p, C.c_int32, C.POINTER(C.c_float)]),
+    "sb200_plan_stats": (C.c_int32, [C.c_void_p, C.POINTER(C.c_int64)]),
+    "sb200_plan_destroy": (C.c_int32, [C.c_void_p]),
+    "sb200_slab_schedule": (C.c_int32, [C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                        C.c_int32, C.c_int32, C.POINTER(SlabOp), C.c_int32, C.POINTER(C.c_int32),
+                                        C.POINTER(C.c_int32)]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGS)
 

@@ -42,6 +42,25 @@ def padval_bits(padval, eltype: int) -> int:
     return int.from_bytes(raw.ljust(8, b"\0"), "little")
 
 
+def require_exact(values, dt, what: str) -> None:
+    """The reference promotes: `kernelproduct` accumulates hood[i] * kernel[i] (src/stencils/kernel.jl:37-43) and the result
+    type follows typeof(padval) (_arg_return_type), so Float64 weights or a Float64 padval on an Int32 / Float32 grid give a
+    Float64 result there. The kernels here compute in the source element type, so a value that this type cannot hold exactly
+    is refused by the user-facing layer (ops.py) instead of being cast silently (0.1 on an Int32 grid used to become 0).
+    build_desc itself stays a plain cast: tests and the slab plans hand it values of the right type."""
+    v = np.asarray(values)
+    with np.errstate(all="ignore"):
+        c = v.astype(dt)
+        back = c.astype(v.dtype) if v.dtype.kind in "fiub" else c
+        same = (back == v) | ((v != v) & (back != back)) if v.dtype.kind == "f" else (back == v)
+    if dt == np.dtype(np.bool_) and v.dtype.kind != "b":
+        same = same & ((v == 0) | (v == 1))
+    if not np.all(same):
+        raise A.ArgumentError(f"{what} {v.reshape(-1)[:4].tolist()} cannot be represented exactly in the source element type "
+                              f"{np.dtype(dt).name}; the reference would promote the result type, these kernels compute in the source type "
+                              "(convert the array, or use values of its element type)")
+
+
 def build_desc(*, size, eltype, out_eltype, offsets, radius, boundary, reducer=A.SUM,
                src_off=None, dst_off=None, src_ext=None, dst_ext=None, padval=0, weights=None,
                born_mask=1 << 3, survive_mask=(1 << 2) | (1 << 3), alpha=0.0,

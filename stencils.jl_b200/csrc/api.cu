@@ -181,6 +181,15 @@ static std::mutex g_plan_mu;
 thread_local MirrorReq g_mirror;
 static std::unordered_map<std::string, Plan*> g_plans;
 
+static unsigned long long g_plan_stamp = 0;   // guarded by g_plan_mu
+
+static void free_plan(Plan* pl) {
+    cudaFree(pl->offs_dev); cudaFree(pl->weights_dev); cudaFree(pl->scatter_order_dev);
+    delete[] pl->d.offsets_host;
+    delete[] (const char*)pl->d.weights_host;
+    delete pl;
+}
+
 static std::string plan_key(const sb200_desc* d, int kind, int dev) {
     std::string k;
     sb200_desc c = *d;
@@ -205,13 +214,16 @@ static int get_plan(const sb200_desc* d, int kind, Plan** out) {
     std::string key = plan_key(d, kind, dev);
     std::lock_guard<std::mutex> lock(g_plan_mu);
     auto it = g_plans.find(key);
-    if (it != g_plans.end()) { *out = it->second; return SB200_OK; }
-    if (g_plans.size() > 4096) {  // unbounded descriptors (e.g. sliding regions): drop everything
-        for (auto& kv : g_plans) {
-            cudaFree(kv.second->offs_dev); cudaFree(kv.second->weights_dev); cudaFree(kv.second->scatter_order_dev);
-            delete kv.second;
+    if (it != g_plans.end()) { it->second->stamp = ++g_plan_stamp; *out = it->second; return SB200_OK; }
+    if (g_plans.size() > 4096) {
+        // unbounded descriptors (e.g. sliding regions): evict the plans that have not been looked up for a long time. A call
+        // holds at most a handful of plans, all of them stamped within its last few lookups, so plans in use are never freed
+        // (round 1 dropped the whole cache here, which could leave a caller with a dangling plan).
+        const unsigned long long keep_from = g_plan_stamp > 1024 ? g_plan_stamp - 1024 : 0;
+        for (auto jt = g_plans.begin(); jt != g_plans.end();) {
+            if (jt->second->stamp < keep_from) { free_plan(jt->second); jt = g_plans.erase(jt); }
+            else ++jt;
         }
-        g_plans.clear();
     }
     Plan* pl = new Plan();
     pl->d = *d;
@@ -288,17 +300,34 @@ static int get_plan(const sb200_desc* d, int kind, Plan** out) {
         SB_CUDA(cudaMalloc(&pl->scatter_order_dev, sizeof(int) * S * L));
         SB_CUDA(cudaMemcpy(pl->scatter_order_dev, order.data(), sizeof(int) * S * L, cudaMemcpyHostToDevice));
     }
+    pl->stamp = ++g_plan_stamp;
     g_plans[key] = pl;
     *out = pl;
     return SB200_OK;
 }
 
-static int do_gather(const sb200_desc* d, const void* src, void* dst, cudaStream_t st) {
+// Would a sweep with this descriptor's SB200_FLAG_*_STEP flag run as ONE multi-generation launch (16-byte aligned parents assumed)?
+bool multistep_accepts(const sb200_desc* d) {
+    Plan* pl = nullptr;
+    if (get_plan(d, PK_GATHER, &pl) != SB200_OK) return false;
+    if (d->flags & SB200_FLAG_OCT_STEP) return !(d->flags & (SB200_FLAG_DOUBLE_STEP | SB200_FLAG_QUAD_STEP)) && life_multi_accepts(*d, *pl, 8);
+    if (d->flags & SB200_FLAG_QUAD_STEP) return !(d->flags & SB200_FLAG_DOUBLE_STEP) && life_multi_accepts(*d, *pl, 4);
+    if (d->flags & SB200_FLAG_DOUBLE_STEP) return life2_accepts(*d, *pl) || diffusion2_accepts(*d, *pl);
+    return false;
+}
+
+int do_gather(const sb200_desc* d, const void* src, void* dst, cudaStream_t st) {
     if (!src || !dst) { set_error("NULL data pointer"); return SB200_EINVAL; }
     if (src == dst) { set_error("source and dest must not alias (the reference keeps distinct buffers)"); return SB200_EINVAL; }
     Plan* pl = nullptr;
     int rc = get_plan(d, PK_GATHER, &pl);
     if (rc) return rc;
+    // The multi-generation kernels need 16-byte aligned parents; anything else would fall through to a single-generation
+    // kernel with the flag ignored, so it is refused here (the header's promise: never a silent single sweep).
+    if ((d->flags & (SB200_FLAG_DOUBLE_STEP | SB200_FLAG_QUAD_STEP | SB200_FLAG_OCT_STEP)) && (((uintptr_t)src | (uintptr_t)dst) & 15)) {
+        set_error("SB200_FLAG_*_STEP: source and dest parents must be 16-byte aligned");
+        return SB200_EUNSUPPORTED;
+    }
     if ((d->flags & SB200_FLAG_QUAD_STEP) && ((d->flags & SB200_FLAG_DOUBLE_STEP) || !life_multi_accepts(*d, *pl, 4))) {
         set_error("SB200_FLAG_QUAD_STEP: only B3/S23 Life / Moore(1) on an unpadded Bool or UInt8 grid, Wrap on axis 0, width % 32 == 0");
         return SB200_EUNSUPPORTED;
@@ -556,11 +585,14 @@ int32_t sb200_iterate(const sb200_desc* d, void* buf_a, void* buf_b, int32_t nst
     if (d->reducer == SB200_LIFE && d->eltype == SB200_U8) later.flags |= SB200_FLAG_CELLS_01;
     // Life: two generations per launch where the kernel supports it (half the HBM traffic per generation). The number
     // of single-generation launches in front is chosen so that the final buffer is the one the contract names.
-    // EXPERIMENT (SB200_OCT_STEP=1 and a library built with -DSB200_LB_ONE_HALO_LANE=1): the bulk of a long Life run as an EVEN
-    // number of eight-generation launches up front (the buffer roles are then those of a fresh call), the rest as below.
+    // Eight generations per launch (one-halo-lane layout of life_bit_kernel, the default build; SB200_OCT_STEP=0 turns it off):
+    // the bulk of a long Life run as an EVEN number of eight-generation launches up front (the buffer roles are then those of a
+    // fresh call), the rest as below.
     bool fresh = true;   // the next launch is the first one of the call (UInt8 cells not yet known to be 0/1)
-    if (d->reducer == SB200_LIFE && nsteps >= 48 && !halo && !(d->flags & (SB200_FLAG_DOUBLE_STEP | SB200_FLAG_QUAD_STEP | SB200_FLAG_OCT_STEP)) &&
-        getenv("SB200_OCT_STEP") && !getenv("SB200_NO_DOUBLE_STEP")) {
+    // the multi-generation kernels need 16-byte aligned parents: other pointers run one generation per launch
+    const bool aligned16 = ((((uintptr_t)buf_a | (uintptr_t)buf_b) & 15) == 0);
+    if (aligned16 && d->reducer == SB200_LIFE && nsteps >= 48 && !halo && !(d->flags & (SB200_FLAG_DOUBLE_STEP | SB200_FLAG_QUAD_STEP | SB200_FLAG_OCT_STEP)) &&
+        !(getenv("SB200_OCT_STEP") && atoi(getenv("SB200_OCT_STEP")) == 0) && !getenv("SB200_NO_DOUBLE_STEP") && !getenv("SB200_NO_QUAD_STEP")) {
         Plan* pl8 = nullptr;
         sb200_desc probe = *d;
         probe.flags |= SB200_FLAG_OCT_STEP;
@@ -583,7 +615,7 @@ int32_t sb200_iterate(const sb200_desc* d, void* buf_a, void* buf_b, int32_t nst
     // Diffusion: two steps per launch (stream3d2.cu; 1094 vs 763 Gcell-updates/s on 1024^3 Float32). SB200_DIFFUSION_DOUBLE_STEP=0 turns it off.
     const char* e_d2 = getenv("SB200_DIFFUSION_DOUBLE_STEP");
     const bool diff2 = d->reducer == SB200_DIFFUSION && (e_d2 ? atoi(e_d2) != 0 : kDiffusionDoubleStepDefault);
-    if ((life || diff2) && nsteps >= 4 && !halo && !(d->flags & (SB200_FLAG_DOUBLE_STEP | SB200_FLAG_QUAD_STEP)) &&
+    if (aligned16 && (life || diff2) && nsteps >= 4 && !halo && !(d->flags & (SB200_FLAG_DOUBLE_STEP | SB200_FLAG_QUAD_STEP)) &&
         !getenv("SB200_NO_DOUBLE_STEP")) {
         Plan* pl = nullptr;
         sb200_desc probe = *d;
@@ -776,6 +808,29 @@ int32_t sb200_iterate_host(const sb200_desc* d, void* state_host, int32_t nsteps
     if ((rc = sb200_iterate(d, g_hs.a, g_hs.b, nsteps, st))) return rc;
     SB_CUDA(cudaMemcpyAsync(state_host, (nsteps % 2 == 0) ? g_hs.a : g_hs.b, sb_, cudaMemcpyDeviceToHost, st));
     SB_CUDA(cudaStreamSynchronize(st));
+    return SB200_OK;
+}
+
+int32_t sb200_shutdown(void) {
+    cudaDeviceSynchronize();
+    {
+        std::lock_guard<std::mutex> lock(g_plan_mu);
+        for (auto& kv : g_plans) free_plan(kv.second);
+        g_plans.clear();
+    }
+    if (g_hs.init) {
+        for (int i = 0; i < 3; i++) cudaStreamDestroy(g_hs.st[i]);
+        for (int i = 0; i < 128; i++) cudaEventDestroy(g_hs.ev[i]);
+        g_hs.init = false;
+    }
+    if (g_hs.a) cudaFree(g_hs.a);
+    if (g_hs.b) cudaFree(g_hs.b);
+    g_hs.a = g_hs.b = nullptr; g_hs.a_bytes = g_hs.b_bytes = 0;
+    if (g_multi_scratch) cudaFree(g_multi_scratch);
+    g_multi_scratch = nullptr; g_multi_scratch_bytes = 0;
+    if (g_done_ctr) cudaFree(g_done_ctr);
+    g_done_ctr = nullptr;
+    cudaGetLastError();
     return SB200_OK;
 }
 

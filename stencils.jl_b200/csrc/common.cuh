@@ -78,6 +78,7 @@ struct Plan {
     int shape_tag = -1;     // recognised named shape (sb200_shape) or -1
     int shape_ndim = 0;     // dimensionality of the recognised shape
     bool uniform_bc = true;
+    unsigned long long stamp = 0;   // last lookup (plan cache eviction)
     std::string key;
 };
 
@@ -183,5 +184,10 @@ int try_scatter_fast(const Plan& pl, const void* src, void* dst, cudaStream_t st
 int try_scatter_stream(const Plan& pl, const void* src, void* dst, cudaStream_t st, int x_lo, int x_hi, int y_lo, int y_hi);
 
 int num_sms();
+
+// api.cu: the dispatch behind sb200_gather, and the question sb200_iterate / the slab plans ask before scheduling
+// several generations per launch.
+int do_gather(const sb200_desc* d, const void* src, void* dst, cudaStream_t st);
+bool multistep_accepts(const sb200_desc* d);
 
 }  // namespace sb

@@ -595,13 +595,14 @@ constexpr int LB_CH = 3;
 constexpr int LB_STAGES = 4;
 constexpr int LB_ROWB = 6144;
 constexpr int LB_SMEM = 128 + LB_STAGES * LB_CH * LB_ROWB;
-// EXPERIMENT (default 0 = the measured kernel; not yet on a GPU): ONE halo lane per side instead of G - 1. A wrong edge bit
-// enters an end lane at one cell per generation, so after G <= 32 generations only the end lanes themselves hold wrong cells
-// (tools/model_life_bit_lanes.py emulates the scheme: lanes 1 .. 30 are exact for G = 2 .. 31). With G = 4 that is 30 instead
-// of 26 useful lanes per warp (+15 % cells per instruction) and smaller halos, and it is what makes 8 generations per launch
-// worthwhile (18 useful lanes with G - 1 halo lanes).
+// ONE halo lane per side of a warp instead of G - 1 (default since r02a; -DSB200_LB_ONE_HALO_LANE=0 restores the round-1 layout).
+// A wrong edge bit enters an end lane at one cell per generation, so after G <= 32 generations only the end lanes themselves
+// hold wrong cells (tools/model_life_bit_lanes.py emulates the scheme: lanes 1 .. 30 are exact for G = 2 .. 31). With G = 4 that
+// is 30 instead of 26 useful lanes per warp and smaller halos, and it is what makes 8 generations per launch worthwhile (18
+// useful lanes with G - 1 halo lanes). Measured r02a, 16384^2: 8508 (G - 1 halo lanes, 4 generations) -> 9843 (one halo lane,
+// one task per CTA) -> 10773 Gcell-updates/s (8 generations per launch); every Life test bit-identical to the CPU restatement.
 #ifndef SB200_LB_ONE_HALO_LANE
-#define SB200_LB_ONE_HALO_LANE 0
+#define SB200_LB_ONE_HALO_LANE 1
 #endif
 template <int G> struct LbCfg {
     static constexpr int HLN = SB200_LB_ONE_HALO_LANE ? 1 : G - 1;   // halo lanes per side of a warp
@@ -786,9 +787,19 @@ template <int G, bool CELLS01> static int launch_bit(const LifeParams& p, cudaSt
     q.outb = std::min(C::CAP, ((p.W + q.nstrips - 1) / q.nstrips + 127) / 128 * 128);  // equal strips
     q.nstrips = (p.W + q.outb - 1) / q.outb;
     const long long ctas = (long long)ctas_per_sm * num_sms();
-    const int tpc = getenv("SB200_LB_TASKS") ? atoi(getenv("SB200_LB_TASKS")) : 2;
-    long long nruns = std::max<long long>(1, tpc * ctas / q.nstrips);
-    nruns = std::min<long long>(nruns, std::max(1, p.rows / (16 * G)));  // at least 16 G rows per run (2 G are re-read)
+    // Runs per strip: strips x runs fills whole waves of the resident CTAs (t tasks per CTA); every run re-reads 2 G source
+    // rows, so pick the t that minimises waves x (rows per run + 2 G). Measured r02a (16384^2, three strips, 444 CTAs): one task
+    // per CTA 9843 Gcell-updates/s, a clipped second wave (768 tasks) 8283. SB200_LB_TASKS overrides t for A/B runs.
+    static const int tpc_env = getenv("SB200_LB_TASKS") ? atoi(getenv("SB200_LB_TASKS")) : 0;
+    long long nruns = 1;
+    double best_cost = 1e300;
+    for (int t = (tpc_env > 0 ? tpc_env : 1); t <= (tpc_env > 0 ? tpc_env : 4); t++) {
+        long long r = std::max<long long>(1, t * ctas / q.nstrips);
+        r = std::min<long long>(r, std::max(1, p.rows / (4 * G)));   // at least 4 G rows per run
+        const long long waves = (q.nstrips * r + ctas - 1) / ctas;
+        const double cost = (double)waves * ((double)p.rows / (double)r + 2.0 * G);
+        if (cost < best_cost * 0.999) { best_cost = cost; nruns = r; }
+    }
     q.nruns = (int)nruns;
     const long long grid = std::min<long long>(ctas, (long long)q.nstrips * q.nruns);
     life_bit_kernel<G, CELLS01><<<(unsigned)grid, (LB_WARPS + 1) * 32, LB_SMEM, st>>>(q);
@@ -801,7 +812,7 @@ bool life2_accepts(const sb200_desc& d, const Plan& pl) { return life_multi_acce
 bool life_multi_accepts(const sb200_desc& d, const Plan& pl, int gens) {
     if (gens >= 4 && (d.born_mask != (1u << 3) || d.survive_mask != ((1u << 2) | (1u << 3)) || d.size[0] % 32 || getenv("SB200_NO_BITSLICE")))
         return false;   // four (eight) generations: the bit-sliced B3/S23 kernel only
-    if (gens == 8 && !SB200_LB_ONE_HALO_LANE) return false;   // eight generations need the one-halo-lane layout (experiment)
+    if (gens == 8 && !SB200_LB_ONE_HALO_LANE) return false;   // eight generations need the one-halo-lane layout
     if (d.reducer != SB200_LIFE || d.ndim != 2 || (d.eltype != SB200_BOOL && d.eltype != SB200_U8)) return false;
     if (pl.shape_tag != SB200_MOORE || pl.shape_ndim != 2 || d.radius != 1 || d.noffsets != 8) return false;
     if (d.flags & (SB200_FLAG_NO_TMA | SB200_FLAG_FORCE_GENERIC)) return false;
@@ -870,7 +881,7 @@ int try_life_swar(const Plan& pl, const void* src, void* dst, cudaStream_t st) {
     // Bool cells are 0/1 by type; UInt8 cells are 0/1 when the caller says so (sb200_iterate does for every
     // step after the first, because the source is then this kernel's own output).
     const bool cells01 = d.eltype == SB200_BOOL || (d.flags & SB200_FLAG_CELLS_01);
-    if (d.flags & SB200_FLAG_OCT_STEP) {   // EXPERIMENT, only in builds with -DSB200_LB_ONE_HALO_LANE=1
+    if (d.flags & SB200_FLAG_OCT_STEP) {   // needs the one-halo-lane layout (the default build)
         if (!life_multi_accepts(d, pl, 8)) { set_error("eight generations per sweep: not supported by this build / layout / rule"); return SB200_EUNSUPPORTED; }
 #if SB200_LB_ONE_HALO_LANE
         p.mirror = nullptr; p.m_lo = p.m_hi = 0;

@@ -26,7 +26,7 @@
 // planes inside the parent (slab runs). Wrapped halo cells of the intermediate state are recomputed from wrapped source
 // cells in the same order, so they equal the cells they stand for bit for bit (a Reflect image would fold its
 // neighbours in the opposite order, which is why Reflect is not accepted). Remove axes: the PAD instantiation below
-// (padval selects at both time levels), prepared but not yet run on a GPU, opt-in with SB200_D2_REMOVE=1.
+// (padval selects at both time levels), bit-exact against two single CPU sweeps in the GPU tests (r02a), on by default.
 // Algorithmic traffic: sizeof(T) read + sizeof(T) written per cell per TWO steps.
 #include <algorithm>
 #include <cstdlib>
@@ -44,7 +44,7 @@ constexpr int D2_WARPS = D2_WX * D2_WY;
 #define SB200_D2_STAGES 6
 #endif
 #ifndef SB200_D2_PACKED
-#define SB200_D2_PACKED 0
+#define SB200_D2_PACKED 1
 #endif
 // producer warps (the rows of a stage dealt round-robin). Measured on 1024^3 Float32 (r01j): 2 producers 935, 3 producers
 // 1092, 4 producers (register cap 80) 1073 Gcell-updates/s: with two, the consumers waited for data 23 % of the time
@@ -150,12 +150,13 @@ __device__ __noinline__ void d2_level_barrier() {
 }
 
 #if SB200_D2_PACKED
-// EXPERIMENT (off by default, not yet run on a GPU; build with tools/build_variant.sh ... -DSB200_D2_PACKED=1): the same plane
-// step for Float32 with packed add / mul / fma.rn.f32x2 (SASS FADD2 / FMUL2 / FFMA2): the kernel is bound by issue slots
-// (65 % busy, FMA pipe 34 %), and a packed instruction advances two cells per slot. Every lane of a packed instruction rounds
-// like the scalar one. Products are written as fma(x, w, -0.0) == rn(x * w) (exact product plus -0 changes nothing, signed
-// zeros and NaN included) so that ptxas cannot contract a multiply with the following add / subtract into one FFMA2 (single
-// rounding), which it does for mul.rn.f32x2 + add.rn.f32x2 (measured on the 7x7 kernelproduct).
+// The same plane step for Float32 with packed add / sub / fma.rn.f32x2 (SASS FADD2 / FFMA2; default since r02b, -DSB200_D2_PACKED=0
+// restores the scalar folds): the kernel is bound by issue slots (65 % busy, FMA pipe 34 %), and a packed instruction advances
+// two cells per slot. Every lane of a packed instruction rounds like the scalar one. Products are written as
+// fma(x, w, -0.0) == rn(x * w) (exact product plus -0 changes nothing, signed zeros and NaN included) with the -0.0 pair read
+// from constant memory, so that ptxas can neither fold the fma into a multiply nor contract it with the following add /
+// subtract into one FFMA2 (single rounding) — which it does for mul.rn.f32x2 + add.rn.f32x2 and for a literal -0.0 addend.
+// Measured r02b, 1024^3 Float32: 1076 -> 1184 Gcell-updates/s, bit-identical to two single sweeps of the CPU restatement.
 __device__ __forceinline__ unsigned long long d2_pk(float lo, float hi) {
     unsigned long long r;
     asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
@@ -172,9 +173,13 @@ __device__ __forceinline__ unsigned long long d2_sub2(unsigned long long a, unsi
     asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
     return r;
 }
+// (-0.0f, -0.0f) read from constant memory: ptxas cannot know the value (the host may overwrite a __constant__), so it can
+// neither simplify fma(a, b, -0) to a multiply nor contract it with the next add. r02a: with the literal it did both —
+// `FFMA2 R26, -R74, 6, R26` = s - 6 cc in ONE rounding, 1-ulp differences in 40 % of the cells.
+__constant__ unsigned long long d2_negzero2 = 0x8000000080000000ull;
 __device__ __forceinline__ unsigned long long d2_mul2_opaque(unsigned long long a, unsigned long long b) {   // rn(a * b), never contracted
     unsigned long long r;
-    const unsigned long long nz = 0x8000000080000000ull;   // (-0.0f, -0.0f)
+    const unsigned long long nz = d2_negzero2;
     asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(nz));
     return r;
 }
@@ -203,7 +208,7 @@ __device__ __forceinline__ void d2_plane<float, 4>(float (&done)[4], float (&cpr
 }
 #endif
 
-// PAD = true: EXPERIMENT (not yet run on a GPU; SB200_D2_REMOVE=1 lets diffusion2_accepts take Remove axes): out-of-bounds
+// PAD = true (Remove axes; SB200_D2_REMOVE=0 makes diffusion2_accepts decline them): out-of-bounds
 // source cells AND out-of-bounds cells of the intermediate state read padval (Remove boundary: the second sweep sees
 // padval outside the array, not an update of it). Rows / planes / edge halos outside the array are not copied; the values
 // are substituted by selects. PAD = false is the measured Wrap kernel, its code is untouched (if constexpr).
@@ -471,8 +476,8 @@ bool diffusion2_accepts(const sb200_desc& d, const Plan& pl) {
         if (d.size[a] < 4 || d.size[a] > (1 << 28)) return false;
     }
     if ((d.size[0] * es) % 16 || d.size[0] * es < 64 || d.size[0] * es >= (1LL << 30)) return false;   // row bytes are held in an int
-    // Remove axes run the PAD variant of the kernel, which has not been on a GPU yet: opt-in with SB200_D2_REMOVE=1
-    const bool remove_ok = getenv("SB200_D2_REMOVE") != nullptr;
+    // Remove axes run the PAD variant of the kernel (bit-exact on the GPU in r02a; SB200_D2_REMOVE=0 declines them again)
+    static const bool remove_ok = !(getenv("SB200_D2_REMOVE") && atoi(getenv("SB200_D2_REMOVE")) == 0);
     for (int a = 0; a < 2; a++)
         if (d.boundary[a] != SB200_WRAP && !(remove_ok && d.boundary[a] == SB200_REMOVE)) return false;
     if (pl.dd.lo[0] != 0 || pl.dd.n[0] != d.size[0] || pl.dd.lo[1] != 0 || pl.dd.n[1] != d.size[1]) return false;  // z regions only

@@ -16,7 +16,7 @@ import statistics
 import numpy as np
 
 from . import _abi as A
-from ._desc import DescHandle, build_desc
+from ._desc import DescHandle, build_desc, require_exact
 from .array import (AbstractStencilArray, Halo, Remove, StencilArray, SwitchingStencilArray, Use, _is_torch, _np_dtype,
                     data_ptr, is_device, similar)
 from .stencils import Kernel, Stencil
@@ -146,6 +146,10 @@ def _desc_build(red: Reducer, src_parent, src_halo: int, dst_parent, dst_halo: i
     if isinstance(red, Diffusion):
         kw.update(alpha=red.alpha)
     pv = bc.padval if isinstance(bc, Remove) else 0
+    # the reference promotes on mixed types (kernel.jl:37-43, _arg_return_type); here values must fit the source element type
+    require_exact(np.array([pv]), A.DTYPE_OF_ELTYPE[et], "Remove padval")
+    if weights is not None and et not in (A.BOOL, A.U8):
+        require_exact(np.asarray(weights), A.DTYPE_OF_ELTYPE[et], "kernel / scatter weights")
     return build_desc(size=size, eltype=et, out_eltype=oet, offsets=st.offsets(), radius=st.radius,
                       boundary=_bc_enum(bc), reducer=enum, src_off=(src_halo,) * nd, dst_off=(dst_halo,) * nd,
                       src_ext=tuple(src_parent.shape), dst_ext=tuple(dst_parent.shape), padval=pv, weights=weights,
@@ -367,6 +371,7 @@ def scatterstencil_(f, op, dest_or_switching, src=None, flags=0):
     else:
         dst, source_arr, dst_halo = dest_or_switching, src, 0
     st = source_arr.stencil
+    require_exact(np.asarray(f.weights), np.dtype(source_arr.dtype), "scatter weights")
     w = np.broadcast_to(np.asarray(f.weights, dtype=source_arr.dtype), (len(st),)).copy()
     _same_place(source_arr.parent, dst)
     h = _desc_for(sum, source_arr.parent, source_arr.halo, dst, dst_halo, st, source_arr.boundary, flags=flags,

@@ -182,8 +182,8 @@ class SlabIterator:
         self.double_ok = (reducer == A.LIFE and t.is_cuda and compute is None and self.bc_split == A.WRAP and self.k >= 2 and
                           self.n_local >= 4 * self.G + 64 and os.environ.get("SB200_DOUBLE_STEP", "1") != "0")
         self.quad_ok = self.double_ok and self.k >= 4 and os.environ.get("SB200_QUAD_STEP", "1") != "0"
-        # EXPERIMENT: eight generations per launch (library built with -DSB200_LB_ONE_HALO_LANE=1), opt-in
-        self.oct_ok = self.quad_ok and self.k >= 8 and os.environ.get("SB200_OCT_STEP", "0") == "1"
+        # eight generations per launch (one-halo-lane layout of life_bit_kernel, the default build); SB200_OCT_STEP=0 turns it off
+        self.oct_ok = self.quad_ok and self.k >= 8 and os.environ.get("SB200_OCT_STEP", "1") != "0"
         # two diffusion steps per launch (csrc/stream3d2.cu): same schedule; SB200_DIFFUSION_DOUBLE_STEP=0 turns it off
         if (reducer == A.DIFFUSION and t.is_cuda and compute is None and self.bc_split == A.WRAP and self.k >= 2 and
                 self.n_local >= 4 * self.G and os.environ.get("SB200_DIFFUSION_DOUBLE_STEP", A.DIFFUSION_DOUBLE_STEP_DEFAULT) != "0"):
@@ -383,6 +383,130 @@ class SlabIterator:
             self._fill_end_ghosts(self.bufs[1 - self.cur])
             self.cur = 1 - self.cur
             self.steps_since_exchange = s
+
+
+class SlabPlan:
+    """Thin caller of the C-ABI slab plan (include/stencils_b200.h: sb200_plan_*; csrc/slab_plan.cu + slab_sched.h): the
+    library owns the slab parents, mailboxes, streams, events and the cycle schedule; this class only builds the descriptor
+    of the UNDIVIDED array and moves handles. Two forms, like the ABI:
+
+      SlabPlan(shape, ..., devices=[0, 1, ...])      one process drives every GPU (what a Julia session does)
+      SlabPlan(shape, ..., rank=r, world=w)           one process per GPU (torchrun): IPC handles travel through
+                                                      torch.distributed.all_gather_object
+
+    `shape` is the logical (column-major) shape of the undivided array; the last axis is split."""
+
+    def __init__(self, shape, *, offsets, radius, reducer, boundary, eltype, ghost=0, devices=None, rank=None, world=None,
+                 reducer_kwargs=None, padval=0, plan_flags=0):
+        import ctypes as C
+        self.C = C
+        self.lib = A.lib()
+        self.shape = tuple(int(v) for v in shape)
+        self.eltype = eltype
+        self.desc = build_desc(size=self.shape, eltype=eltype, out_eltype=eltype, offsets=offsets, radius=radius,
+                               boundary=tuple(boundary), reducer=reducer, padval=padval, **(reducer_kwargs or {}))
+        self.handle = C.c_void_p()
+        self.rank_form = devices is None
+        if devices is not None:
+            arr = (C.c_int32 * len(devices))(*devices)
+            A.check(self.lib.sb200_plan_create(self.desc.ptr(), len(devices), arr, int(ghost), int(plan_flags), C.byref(self.handle)))
+        else:
+            import torch.distributed as dist
+            A.check(self.lib.sb200_plan_create_rank(self.desc.ptr(), int(rank), int(world), int(ghost), int(plan_flags),
+                                                    C.byref(self.handle)))
+            if world > 1:
+                mine = (C.c_ubyte * 64)()
+                err = None
+                try:
+                    A.check(self.lib.sb200_plan_ipc_handle(self.handle, mine))
+                except Exception as e:   # every rank still takes part in the collectives below
+                    err = repr(e)
+                got = [None] * world
+                dist.all_gather_object(got, (bytes(mine), err))
+                bad = [f"rank {r}: {e}" for r, (_, e) in enumerate(got) if e]
+                if not bad:
+                    blob = (C.c_ubyte * (64 * world)).from_buffer_copy(b"".join(h for h, _ in got))
+                    try:
+                        A.check(self.lib.sb200_plan_connect(self.handle, blob))
+                    except Exception as e:
+                        err = repr(e)
+                votes = [None] * world
+                dist.all_gather_object(votes, err)
+                bad += [f"rank {r}: {e}" for r, e in enumerate(votes) if e]
+                if bad:
+                    self.close()
+                    raise A.SB200Error(A.ECUDA, "CUDA IPC peer access is not available between the ranks: " + "; ".join(bad))
+
+    def nslabs(self):
+        n = self.C.c_int32()
+        A.check(self.lib.sb200_plan_nslabs(self.handle, self.C.byref(n)))
+        return n.value
+
+    def slab(self, i=0):
+        """(lo, hi, device, device pointer of the first owned plane of the current state)"""
+        C = self.C
+        lo, hi, dev, ptr = C.c_int64(), C.c_int64(), C.c_int32(), C.c_void_p()
+        A.check(self.lib.sb200_plan_slab(self.handle, i, C.byref(lo), C.byref(hi), C.byref(dev), C.byref(ptr)))
+        return lo.value, hi.value, dev.value, ptr.value
+
+    def mark_dirty(self):
+        A.check(self.lib.sb200_plan_mark_dirty(self.handle))
+
+    def load(self, host_array):
+        """host_array: the planes this plan owns (whole array / the rank's slab), column-major NumPy array."""
+        a = np.asfortranarray(host_array)
+        A.check(self.lib.sb200_plan_load_host(self.handle, a.ctypes.data))
+
+    def store(self, nplanes=None):
+        dt = A.DTYPE_OF_ELTYPE[self.eltype]
+        if nplanes is None:
+            n = self.nslabs()
+            nplanes = self.slab(n - 1)[1] - self.slab(0)[0]
+        out = np.empty(self.shape[:-1] + (nplanes,), dtype=dt, order="F")
+        A.check(self.lib.sb200_plan_store_host(self.handle, out.ctypes.data))
+        return out
+
+    def iterate(self, nsteps):
+        A.check(self.lib.sb200_plan_iterate(self.handle, int(nsteps)))
+
+    def sync(self):
+        A.check(self.lib.sb200_plan_sync(self.handle))
+
+    def iterate_timed(self, nsteps):
+        ms = self.C.c_float()
+        A.check(self.lib.sb200_plan_iterate_timed(self.handle, int(nsteps), self.C.byref(ms)))
+        return ms.value
+
+    def stats(self):
+        out = (self.C.c_int64 * 8)()
+        A.check(self.lib.sb200_plan_stats(self.handle, out))
+        keys = ("generations", "launches", "exchanges", "ghost_planes", "generations_per_exchange", "overlap", "max_generations_per_launch", "sync")
+        d = dict(zip(keys, [int(v) for v in out]))
+        d["sync"] = {1: "events", 2: "flags"}.get(d["sync"], d["sync"])
+        return d
+
+    def close(self):
+        if self.handle:
+            self.lib.sb200_plan_destroy(self.handle)
+            self.handle = self.C.c_void_p()
+
+
+def slab_schedule(radius, ghost, n_min, *, split_wrap=True, overlap=False, max_gens=1, min_planes_multi=0, since=None, first_sweep=True,
+                  nsteps=1):
+    """The op list a slab plan runs for `nsteps` generations (sb200_slab_schedule: pure host logic, needs no GPU).
+    Returns (list of op dicts, generations since the last exchange afterwards)."""
+    import ctypes as C
+    lib = A.lib()
+    if since is None:
+        since = ghost // radius
+    cap = 16 * (nsteps + 2)
+    ops = (A.SlabOp * cap)()
+    count, since_out = C.c_int32(), C.c_int32()
+    A.check(lib.sb200_slab_schedule(radius, ghost, n_min, int(split_wrap), int(overlap), max_gens, min_planes_multi, since, int(first_sweep),
+                                    nsteps, ops, cap, C.byref(count), C.byref(since_out)))
+    assert count.value <= cap
+    out = [dict(kind=o.kind, gens=o.gens, mirror=o.mirror, buf=o.buf, async_=o.async_, first=o.first, lo=o.lo, hi=o.hi) for o in ops[:count.value]]
+    return out, since_out.value
 
 
 def split_axis_last(shape_global, world, rank):

@@ -193,3 +193,27 @@ def test_slab_scatter_rejects_what_it_cannot_do_exactly():
     with pytest.raises(A.ArgumentError):   # mean of UInt8 changes the element type
         slab_gather(torch.zeros((8, 8), dtype=torch.uint8), offsets=[(0, 1)], radius=1, reducer=A.MEAN, boundary=(A.WRAP, A.WRAP),
                     eltype=A.U8, rank=0, world=1, compute=lambda *a: None)
+
+
+def test_inexact_weights_and_padval_are_refused():
+    """The reference promotes (kernelproduct accumulates hood[i] * kernel[i], src/stencils/kernel.jl:37-43; the result type
+    follows typeof(padval)); these kernels compute in the source element type, so values that type cannot hold are an
+    ArgumentError in the user-facing layer instead of a silent cast (Kernel(Window(1), fill 0.1) on Int32 built an
+    all-zero table)."""
+    from stencils_b200._desc import require_exact
+    from stencils_b200.ops import _desc_for
+    for vals, dt in [(np.full(3, 0.1), np.int32), (np.full(3, 0.1), np.float32), ([0.5], np.int64), ([2], np.bool_), ([300], np.uint8),
+                     ([-1], np.uint8)]:
+        with pytest.raises(A.ArgumentError):
+            require_exact(np.asarray(vals), np.dtype(dt), "x")
+    for vals, dt in [(np.full(3, 0.1, dtype=np.float32), np.float32), (np.array([1.0, 2.0, -3.0]), np.int32), ([0.1, 0.2], np.float64),
+                     ([float("nan"), -0.0], np.float32), ([True], np.bool_), ([1], np.bool_)]:
+        require_exact(np.asarray(vals), np.dtype(dt), "x")
+    # through the descriptor builder of mapstencil / scatterstencil
+    src = np.zeros((8, 8), dtype=np.int32, order="F")
+    dst = np.zeros((8, 8), dtype=np.int32, order="F")
+    with pytest.raises(A.ArgumentError, match="cannot be represented exactly"):
+        _desc_for(sb.kernelproduct, src, 0, dst, 0, sb.Kernel(sb.Window(1), np.full((3, 3), 0.1)), sb.Remove(0))
+    with pytest.raises(A.ArgumentError, match="cannot be represented exactly"):
+        _desc_for(sb.sum, src, 0, dst, 0, sb.Window(1), sb.Remove(0.5))
+    _desc_for(sb.kernelproduct, src, 0, dst, 0, sb.Kernel(sb.Window(1), np.full((3, 3), 2.0)), sb.Remove(0))
