@@ -212,26 +212,51 @@ def make_sweep(name, spec, torch, sb, shape=None):
     return st, run, cells
 
 
-def time_steps(torch, run, steps, warmup, barrier=None, on_warm=None):
-    run(warmup)
+def time_reps(torch, run, steps, warmup, min_reps=10, min_total_ms=50.0, max_reps=200):
+    """SURVEY 8d timing: `warmup` untimed steps, then R >= 10 repetitions of the K-step region, each bracketed by CUDA events
+    on the launching stream (R is raised until the timed regions add up to >= 50 ms). Returns the list of per-repetition
+    times in ms. Nothing but the K steps of a repetition sits between its two events."""
+    run(max(warmup, 1))
     torch.cuda.synchronize()
-    if on_warm:
-        on_warm()
-    if barrier:
-        barrier()
     stream = torch.cuda.current_stream()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def one():
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        run(steps)
+        e1.record(stream)
+        return e0, e1
+
+    e0, e1 = one()   # pilot repetition (untimed): sizes R
     torch.cuda.synchronize()
-    e0.record(stream)
-    run(steps)
-    e1.record(stream)
+    pilot = max(e0.elapsed_time(e1), 1e-3)
+    reps = int(min(max_reps, max(min_reps, -(-min_total_ms // pilot))))
+    evs = [one() for _ in range(reps)]
     torch.cuda.synchronize()
-    if barrier:
-        barrier()
-    return e0.elapsed_time(e1)  # ms
+    return [a.elapsed_time(b) for a, b in evs]
+
+
+def rep_stats(ms_list, steps):
+    a = np.asarray(ms_list, dtype=np.float64)
+    return {"reps": int(a.size), "steps_per_rep": int(steps), "rep_ms_median": float(np.median(a)), "rep_ms_min": float(a.min()),
+            "rep_ms_max": float(a.max()), "timed_region_ms": float(a.sum()),
+            "how": "CUDA events on the launching stream around every repetition of the K-step region; value uses the median repetition"}
 
 
 # ------------------------------------------------------------------------------------------------ CPU baseline / reference arm
+def cpu_threads():
+    """All host cores for the CPU arm: torchrun exports OMP_NUM_THREADS=1 to its workers, which silently ran the round-1
+    reference arm on ONE core at N > 1 — the count is set explicitly here."""
+    from oracle import oracle as orc
+    n = os.cpu_count() or 1
+    try:
+        n = len(os.sched_getaffinity(0)) or n
+    except Exception:
+        pass
+    orc.set_threads(n)
+    return orc.threads()
+
+
 def cpu_life_step_factory(rows, spec):
     """Reference algorithm (CPU oracle = restatement of Stencils.jl's CPU path) on a bounded sample: a
     16384 x rows torus of the same synthetic field; per-cell work is identical to the full grid."""
@@ -239,6 +264,7 @@ def cpu_life_step_factory(rows, spec):
     from oracle import oracle as orc
     from stencils_b200 import _abi as A
     from stencils_b200._desc import build_desc
+    cores = cpu_threads()
     shape = (spec["shape"][0], rows)
     a = np.asfortranarray(synth(shape, np.uint8, spec["seed"]))
     b = np.zeros_like(a, order="F")
@@ -249,7 +275,7 @@ def cpu_life_step_factory(rows, spec):
     def step():
         orc.gather(h, bufs[0], bufs[1])
         bufs.reverse()
-    return step, shape[0] * rows, orc.threads()
+    return step, shape[0] * rows, cores
 
 
 def cpu_baseline(spec, budget_s=12.0):
@@ -303,7 +329,124 @@ def run_reference(args, rank):
     print(json.dumps(line))
 
 
+# ------------------------------------------------------------------------------------------------ slab-partitioned runs (N > 1)
+def slab_case(workload):
+    from stencils_b200 import _abi as A
+    from stencils_b200.stencils import Moore, VonNeumann
+    if workload == "life":
+        return dict(st=Moore(1), reducer=A.LIFE, kw=dict(born_mask=1 << 3, survive_mask=0b1100), eltype=A.U8, R=1, ghost=32,
+                    bcs=(A.WRAP, A.WRAP))
+    if workload == "diffusion":
+        return dict(st=VonNeumann(1, 3), reducer=A.DIFFUSION, kw=dict(alpha=0.1), eltype=A.F32, R=1, ghost=4, bcs=(A.WRAP, A.WRAP, A.WRAP))
+    raise SystemExit(f"workload {workload} is not an iterated (slab-partitioned) configuration")
+
+
+def bench_slabs(torch, dist, workload, spec, steps, warmup, strong, min_reps=10, min_total_ms=50.0):
+    """One slab per rank through the C-ABI slab plan (sb200_plan_create_rank / _connect / _iterate_timed; csrc/slab_plan.cu).
+    Weak scaling: every rank owns spec['shape'], the global last axis is world x as long; strong: spec['shape'] is split.
+    The timed region is whole exchange cycles: the step count of a repetition is rounded UP to a multiple of the steps per
+    exchange and to at least four cycles, so every repetition contains >= 4 ghost exchanges whatever --steps says.
+    Returns a dict (value over ALL ranks, per-repetition times = max over ranks)."""
+    from stencils_b200 import _abi as A
+    from stencils_b200.slab import SlabPlan
+    from stencils_b200.synth import synth_torch
+    rank, world = dist.get_rank(), dist.get_world_size()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    c = slab_case(workload)
+    if os.environ.get("SB200_PLAN_GHOST"):   # A/B knob: ghost planes per side (a multiple of the radius)
+        c["ghost"] = int(os.environ["SB200_PLAN_GHOST"])
+    shape = tuple(spec["shape"])
+    if strong:
+        if shape[-1] % world:
+            raise SystemExit(f"--strong needs the last axis ({shape[-1]}) to be a multiple of the number of GPUs ({world})")
+        gshape, local = shape, shape[:-1] + (shape[-1] // world,)
+    else:
+        gshape, local = shape[:-1] + (shape[-1] * world,), shape
+    cells_local = int(np.prod(local))
+    exchange = os.environ.get("SB200_EXCHANGE", "auto")
+    pflags = {"1": A.PLAN_OVERLAP_ON, "0": A.PLAN_OVERLAP_OFF}.get(os.environ.get("SB200_OVERLAP", ""), 0)
+    plan = SlabPlan(gshape, offsets=c["st"].offsets(), radius=c["R"], reducer=c["reducer"], boundary=c["bcs"], eltype=c["eltype"],
+                    ghost=c["ghost"], rank=rank, world=world, reducer_kwargs=c["kw"], plan_flags=pflags)
+    try:
+        lo, hi, _, ptr = plan.slab(0)
+        assert hi - lo == local[-1]
+        # rank r's slab is planes [lo, hi) of the global field -> linear index offset lo * cells per plane
+        field = synth_torch(local, spec["dtype"], spec["seed"], dev, lo=lo * int(np.prod(local[:-1])))
+        lib = A.lib()
+        A.check(lib.sb200_memcpy_d2d(ptr, field.data_ptr(), cells_local * field.element_size(), None))
+        A.check(lib.sb200_stream_sync(None))
+        del field
+        plan.mark_dirty()
+        k = c["ghost"] // c["R"]
+        steps_timed = max(-(-steps // k) * k, 4 * k)
+        plan.iterate(max(warmup, k))
+        plan.sync()
+        kernel = lib.sb200_last_kernel().decode()
+        dist.barrier()
+        pilot = torch.tensor([plan.iterate_timed(steps_timed)], device=dev, dtype=torch.float64)
+        dist.all_reduce(pilot, op=dist.ReduceOp.MAX)
+        reps = int(min(200, max(min_reps, -(-min_total_ms // max(float(pilot.item()), 1e-3)))))
+        st0 = plan.stats()
+        lib.sb200_launch_count(1)
+        times = []
+        for _ in range(reps):
+            dist.barrier()
+            times.append(plan.iterate_timed(steps_timed))
+        launches = lib.sb200_launch_count(1)
+        st1 = plan.stats()
+        t = torch.tensor(times, device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)   # every repetition: the slowest rank
+        times = [float(v) for v in t.tolist()]
+        kernel = lib.sb200_last_kernel().decode() or kernel
+        dist.barrier()
+    finally:
+        plan.close()
+    med = float(np.median(times))
+    value = cells_local * world * steps_timed / (med * 1e-3) / 1e9
+    ex_per_rep = (st1["exchanges"] - st0["exchanges"]) / reps
+    how = ("boundary planes of the last sweep of a cycle are written into the neighbour's mailbox over NVLink by the sweep itself "
+           "(sb200_desc.mirror_*; a stream-ordered peer copy inside the call for kernels without the fused store), published with a "
+           "system-scope release flag, pulled into the ghost planes on a side stream under the interior sweep"
+           if st1["overlap"] else
+           "peer copies of the boundary planes into the neighbour's mailbox over NVLink + system-scope release / acquire flags in "
+           "front of the first sweep of every cycle (ghost zones < 1 MiB: overlap does not pay)")
+    return {"value": value, "unit": "Gcell-updates/s", "ms_per_step": med / steps_timed, "steps_timed": steps_timed,
+            "exchanges_in_timed_region": ex_per_rep, "steps_per_exchange": k, "ghost_planes": c["ghost"],
+            "generations_per_launch_max": st1["max_generations_per_launch"], "launches": int(launches), "launches_per_rep": launches / reps,
+            "timing": rep_stats(times, steps_timed), "kernel": kernel, "exchange": how, "sync": st1["sync"],
+            "grid_per_gpu": list(local), "global_grid": list(gshape), "scaling": "strong" if strong else "weak",
+            "cells_total": cells_local * world, "api": "sb200_plan_create_rank / sb200_plan_connect / sb200_plan_iterate_timed (C ABI)",
+            "exchange_requested": exchange}
+
+
 # ------------------------------------------------------------------------------------------------ main
+def roofline_of(workload, spec, value_per_gpu, kernel, peak, peak_src, sweeps_per_launch, ms_total, launches):
+    """roofline object of the dominant kernel. `achieved` counts ALGORITHMIC bytes (each cell read once + written
+    once per sweep); kernels that fuse several sweeps per launch beat the one-sweep HBM roofline (frac > 1), so the line also
+    names the unit that actually binds them and the measured DRAM fraction."""
+    traffic = ncu_traffic(workload)
+    achieved = value_per_gpu * spec["bytes_per_cell"]
+    dram_frac = None
+    if traffic and launches and ms_total:
+        dram_frac = traffic * launches / (ms_total * 1e-3) / 1e9 / peak
+    binding = {"life": "alu", "kernel": "fp32_issue", "diffusion": "issue", "circle": "alu", "window3d": "fp32_issue"}.get(workload, "hbm")
+    if workload == "life" and "life_bit" not in kernel:
+        binding = "hbm"
+    if workload == "diffusion" and "stream3d2" not in kernel:
+        binding = "hbm"
+    return {"bound": "hbm", "binding": binding, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "dram_frac": dram_frac, "traffic": traffic,
+            "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel, ncu --set full capture "
+                              "committed as profiles/ncu_summary.json (not re-measured in this run)" if traffic else None,
+            "peak_source": peak_src, "kernel": kernel, "algorithmic_bytes_per_cell": spec["bytes_per_cell"],
+            "sweeps_per_launch": sweeps_per_launch,
+            "note": ("frac counts the ALGORITHMIC bytes of every sweep (read once + write once per cell-update); a launch that fuses "
+                     "several generations moves the grid through HBM once for all of them, so frac > 1 means the one-sweep HBM roofline "
+                     "is beaten by temporal fusion and `binding` names the unit that limits the kernel instead (ncu: profiles/); "
+                     "dram_frac = measured DRAM bytes per launch (`traffic`) x launches / time / peak"),
+            "how": "algorithmic bytes per launch / mean launch duration (CUDA events on the launching stream around back-to-back launches)"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -331,71 +474,80 @@ def main():
     import stencils_b200 as sb
     from stencils_b200 import _abi as A
     torch.cuda.set_device(local_rank)
-    barrier = None
+    dist = None
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-        barrier = dist.barrier
     lib = A.lib()
     peak, peak_src = measured_peak()
+    dtype_name = {"uint8": "u8", "float64": "f64", "float32": "f32"}[np.dtype(spec["dtype"]).name]
+    warnings = []
 
     if world > 1:
-        from stencils_b200 import slab
+        if not spec["iterated"]:
+            raise SystemExit("--gpus N > 1 runs the iterated (slab-partitioned) configurations: --workload life | diffusion")
         with ClockSampler(local_rank) as cs:
-            res = slab.bench_weak(args.workload, spec, args.steps, args.warmup, synth, strong=args.strong)
-        ms, cells_total, launches, kernel, extra_cfg = res
+            res = bench_slabs(torch, dist, args.workload, spec, args.steps, args.warmup, args.strong)
+        value, ms_per_step, kernel = res["value"], res["ms_per_step"], res["kernel"]
+        steps_timed, launches, timing = res["steps_timed"], res["launches"], res["timing"]
+        cells_total = res["cells_total"]
+        extra_cfg = {k: res[k] for k in ("ghost_planes", "steps_per_exchange", "exchange", "sync", "global_grid", "api")}
+        sweeps_per_launch = steps_timed / max(res["launches_per_rep"], 1)
     else:
         st, run, cells_total = make_sweep(args.workload, spec, torch, sb)
         run(1)
         torch.cuda.synchronize()
-        kernel = lib.sb200_last_kernel().decode()
         with ClockSampler(local_rank) as cs:
-            ms = time_steps(torch, run, args.steps, args.warmup, barrier, on_warm=lambda: lib.sb200_launch_count(1))
-        launches = lib.sb200_launch_count(1)  # kernels launched by libstencils_b200 inside the timed region
-        kernel = lib.sb200_last_kernel().decode()  # the kernel of the timed region (iterated Life fuses two generations)
+            lib.sb200_launch_count(1)
+            times = time_reps(torch, run, args.steps, args.warmup)
+            launches_all = lib.sb200_launch_count(1)
+        kernel = lib.sb200_last_kernel().decode()  # the kernel of the timed region (iterated runs fuse generations)
+        timing = rep_stats(times, args.steps)
+        # launches counted over warm-up + pilot + R repetitions of K steps each: per-repetition share
+        launches_per_rep = launches_all * args.steps / (args.warmup + (len(times) + 1) * args.steps) if spec["iterated"] else args.steps
+        launches = int(round(launches_per_rep * len(times)))
+        steps_timed = args.steps
+        ms_per_step = timing["rep_ms_median"] / args.steps
+        value = cells_total * args.steps / (timing["rep_ms_median"] * 1e-3) / 1e9
         extra_cfg = {}
-    if world > 1:
-        import torch.distributed as dist
-        t = torch.tensor([ms], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+        sweeps_per_launch = args.steps / max(launches_per_rep, 1e-9) if spec["iterated"] else 1.0
 
-    value = cells_total * args.steps / (ms * 1e-3) / 1e9
-    achieved = value * spec["bytes_per_cell"] / max(world, 1)  # GB/s per GPU, algorithmic bytes
-    traffic = ncu_traffic(args.workload)
-    per_rank_launches = max(int(launches), 1)
-    sweeps_per_launch = args.steps / per_rank_launches if spec["iterated"] else 1.0
-    dram_frac = None
-    if traffic and world == 1:
-        dram_frac = traffic * per_rank_launches / (ms * 1e-3) / 1e9 / peak
     line = {
         "metric": "gcell_updates_per_s", "value": value, "unit": "Gcell-updates/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "strong" if (args.strong and world > 1) else "weak",
-        "vs_baseline": None, "dtype": {"uint8": "u8", "float64": "f64", "float32": "f32"}[np.dtype(spec["dtype"]).name],
+        "vs_baseline": None, "dtype": dtype_name,
         "data": "synthetic (splitmix64 hash of the linear index, SURVEY 8d)",
+        "steps_timed": steps_timed, "timing": timing,
         "config": {"workload": spec["desc"],
                    "grid_per_gpu": list(spec["shape"][:-1]) + [spec["shape"][-1] // world if (args.strong and world > 1) else spec["shape"][-1]],
                    "parallelism": f"slab{world}",
                    "l2": "state per GPU (>= 256 MiB) is larger than the 126 MB L2; no flush needed", **extra_cfg},
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "peak_source": peak_src, "kernel": kernel,
-                     "algorithmic_bytes_per_cell": spec["bytes_per_cell"],
-                     "sweeps_per_launch": sweeps_per_launch, "dram_frac": dram_frac,
-                     "note": ("frac counts the ALGORITHMIC bytes of every sweep (SURVEY 8d: read once + write once per "
-                              "cell-update); a launch that fuses two generations moves the grid through HBM once for two "
-                              "sweeps, so frac > 1 means the one-sweep HBM roofline is beaten by temporal fusion; "
-                              "dram_frac = measured DRAM bytes per launch (ncu, `traffic`) x launches / time / peak"),
-                     "how": "algorithmic bytes per launch / mean launch duration (CUDA events on the launching stream "
-                            "around the K back-to-back launches of the timed region)"},
+        "roofline": roofline_of(args.workload, spec, value / max(world, 1), kernel, peak, peak_src, sweeps_per_launch,
+                                timing["timed_region_ms"], launches if world == 1 else None),
         "gpu_launches": int(launches),
         "clocks": cs.summary(),
     }
+    if world > 1:
+        line["exchanges_in_timed_region"] = res["exchanges_in_timed_region"]
+        line["config"]["steps_rounding"] = (f"--steps {args.steps} rounded up to {steps_timed} = whole exchange cycles (>= 4) per repetition")
+
+    # ---- BASELINE configs[4] (C5) beside the headline at every N: 3-D diffusion 1024^3 per GPU, weak scaling ----
+    if not args.no_extras and args.workload == "life":
+        try:
+            if world > 1:
+                torch.cuda.empty_cache()
+                sp5 = workloads()["diffusion"]
+                r5 = bench_slabs(torch, dist, "diffusion", sp5, 100, 8, args.strong)
+                r5["workload"] = sp5["desc"]
+                r5["roofline_frac"] = r5["value"] / world * sp5["bytes_per_cell"] / peak
+                line["c5_diffusion"] = r5
+        except Exception as ex:  # pragma: no cover
+            line["c5_diffusion"] = {"error": repr(ex)}
 
     if world > 1 and not args.no_extras and args.workload == "life":
         # e2e at N GPUs: every rank pushes its own slab through the host-buffer entry point concurrently
         # (one generation per call: H2D + sweep + D2H inside every step); whole-job value = sum over ranks
-        import torch.distributed as dist
         try:
             e = e2e_host(torch, sb, lib, args.workload, spec, barrier=dist.barrier)
             v = torch.tensor([e["value"]], device="cuda", dtype=torch.float64)
@@ -412,6 +564,14 @@ def main():
             line["e2e"] = e2e_host(torch, sb, lib, args.workload, spec)
         except Exception as e:  # pragma: no cover
             line["e2e"] = {"error": repr(e)}
+        if args.workload == "life" and args.steps != 1000:
+            # the BASELINE configuration is a 1000-step run; a short --steps K measures K-step calls (fewer 8-generation launches)
+            try:
+                t1000 = time_reps(torch, run, 1000, 3, min_reps=5)
+                line["config_run_1000_steps"] = {"value": cells_total * 1000 / (float(np.median(t1000)) * 1e-3) / 1e9, "unit": "Gcell-updates/s",
+                                                 "timing": rep_stats(t1000, 1000)}
+            except Exception as e:  # pragma: no cover
+                line["config_run_1000_steps"] = {"error": repr(e)}
         # ---- the other BASELINE configs, same measurement, for context ----
         del st, run
         torch.cuda.empty_cache()
@@ -422,29 +582,41 @@ def main():
             try:
                 sp = workloads()[name]
                 st2, run2, cells2 = make_sweep(name, sp, torch, sb)
-                k = 20 if not sp["iterated"] else 50
+                k = 5 if not sp["iterated"] else 100
                 if name == "mean1000":
                     k = 200
                 run2(1)
                 torch.cuda.synchronize()
-                ms2 = time_steps(torch, run2, k, 3)
+                with ClockSampler(local_rank) as cs2:
+                    t2 = time_reps(torch, run2, k, 3)
                 kn = lib.sb200_last_kernel().decode()  # the kernel of the timed region (iterated runs may fuse steps)
-                v = cells2 * k / (ms2 * 1e-3) / 1e9
-                also[name] = {"value": v, "unit": "Gcell-updates/s", "ms_per_step": ms2 / k, "kernel": kn,
-                              "roofline_frac": v * sp["bytes_per_cell"] / peak, "workload": sp["desc"]}
+                med2 = float(np.median(t2))
+                v = cells2 * k / (med2 * 1e-3) / 1e9
+                also[name] = {"value": v, "unit": "Gcell-updates/s", "ms_per_step": med2 / k, "kernel": kn,
+                              "roofline_frac": v * sp["bytes_per_cell"] / peak, "workload": sp["desc"],
+                              "roofline_frac_best_rep": cells2 * k / (min(t2) * 1e-3) / 1e9 * sp["bytes_per_cell"] / peak,
+                              "timing": {kk: vv for kk, vv in rep_stats(t2, k).items() if kk != "how"}, "clocks": cs2.summary()}
+                if name == "mean1000":
+                    also[name]["note"] = "8 MB grid: L2-resident and launch-bound by construction (the README's own benchmark size)"
                 del st2, run2
                 torch.cuda.empty_cache()
             except Exception as e:  # pragma: no cover
                 also[name] = {"error": repr(e)}
         line["other_configs"] = also
+        if "diffusion" in also and "value" in also["diffusion"]:
+            d5 = dict(also["diffusion"])
+            d5.update(scaling="weak", grid_per_gpu=[1024, 1024, 1024], exchanges_in_timed_region=0,
+                      api="sb200_iterate on the undivided array (the 1-GPU base of the weak-scaling series)")
+            line["c5_diffusion"] = d5
         try:
             line["cpu_baseline"] = cpu_baseline(spec) if args.workload == "life" else None
         except Exception as e:  # pragma: no cover
             line["cpu_baseline"] = {"error": repr(e)}
+    if warnings:
+        line["warnings"] = warnings
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
-        import torch.distributed as dist
         dist.destroy_process_group()
 
 

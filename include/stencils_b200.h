@@ -168,6 +168,10 @@ typedef struct sb200_desc {
 #define SB200_FLAG_ZERO_DEST 2     /* scatter: treat dest as zero-filled (Switching forms, src/scatterstencil.jl:119,130) */
 #define SB200_FLAG_NO_TMA 4        /* testing: use the non-TMA variant of a specialised kernel */
 #define SB200_FLAG_CELLS_01 8      /* LIFE on UInt8: the caller guarantees every source cell is 0 or 1 */
+#define SB200_FLAG_ALLOW_FMA 128  /* KERNELDOT: the caller allows acc = fma(v_k, w_k, acc) (one rounding per tap) instead of the
+                                     reference's separately rounded multiply and add (src/stencils/kernel.jl:37-43). A permission,
+                                     not a request: kernels without a contracted variant ignore it and stay bit-exact. Honoured by the
+                                     streaming Window(1..3) Float32 / Float64 kernels (7 x 7 Float32: FP32-issue bound, ~2x faster) */
 #define SB200_FLAG_QUAD_STEP 32   /* dest = f(f(f(f(src)))): four generations per launch (B3/S23 Life, axis 0 a multiple of 32
                                      cells, otherwise as SB200_FLAG_DOUBLE_STEP); the bit-sliced kernel */
 #define SB200_FLAG_OCT_STEP 64    /* eight generations per launch (as SB200_FLAG_QUAD_STEP; a library built with

@@ -9,8 +9,8 @@ Julia's mutating `f!` functions are spelled `f_` here (mapstencil! -> mapstencil
 from . import _abi
 from ._abi import ArgumentError, SB200Error
 from .stencils import (Annulus, AngledCross, BackSlash, Cardinal, Circle, Cross, Diamond, ForwardSlash, Horizontal,
-                       Kernel, Moore, NamedStencil, Ordinal, Positional, Rectangle, Stencil, Vertical, VonNeumann,
-                       Window, center, diameter, distance_zones, distances, indices, merge, neighbors, offsets, radius)
+                       Kernel, Layered, Moore, NamedStencil, Ordinal, Positional, Rectangle, Stencil, Vertical, VonNeumann,
+                       Window, layer, center, diameter, distance_zones, distances, indices, merge, neighbors, offsets, radius)
 from .array import (AbstractStencilArray, BoundaryCondition, Conditional, Halo, Padding, Reflect, Remove,
                     StencilArray, SwitchingStencilArray, Use, Wrap, boundary, colmajor_empty, dest, padding, padval,
                     source, stencil, switch)

@@ -23,7 +23,7 @@ REMOVE, WRAP, REFLECT, USE = range(4)
 SUM, MEAN, MIN, MAX, KERNELDOT, LIFE, DIFFUSION = range(7)
 OP_ADD, OP_MAX, OP_MIN = range(3)
 SCATTER_WEIGHTS, SCATTER_CENTER_WEIGHTS = range(2)
-FLAG_FORCE_GENERIC, FLAG_ZERO_DEST, FLAG_NO_TMA, FLAG_CELLS_01, FLAG_DOUBLE_STEP, FLAG_QUAD_STEP, FLAG_OCT_STEP = 1, 2, 4, 8, 16, 32, 64
+FLAG_FORCE_GENERIC, FLAG_ZERO_DEST, FLAG_NO_TMA, FLAG_CELLS_01, FLAG_DOUBLE_STEP, FLAG_QUAD_STEP, FLAG_OCT_STEP, FLAG_ALLOW_FMA = 1, 2, 4, 8, 16, 32, 64, 128
 MAX_OFFSETS = 1024
 # default of SB200_DIFFUSION_DOUBLE_STEP (two diffusion steps per launch in iterated runs); must agree with
 # kDiffusionDoubleStepDefault in csrc/api.cu

@@ -193,15 +193,21 @@ class AbstractStencilArray:
                 out.append(2 - i if i < 1 else (2 * s - i if i > s else i))
         return tuple(out)
 
-    def indices(self, I):
-        from .stencils import indices as st_indices
-        return tuple(self.bounded_index(J) for J in st_indices(self.stencil, tuple(I)))
+    def indices(self, I, _st=None):
+        from .stencils import Layered, indices as st_indices
+        st = self.stencil if _st is None else _st
+        if isinstance(st, Layered):
+            return tuple(self.indices(I, l) for l in st.layers)
+        return tuple(self.bounded_index(J) for J in st_indices(st, tuple(I)))
 
-    def neighbors(self, *I):
+    def neighbors(self, *I, _st=None):
         I = tuple(I[0]) if len(I) == 1 and isinstance(I[0], (tuple, list)) else tuple(I)
-        from .stencils import indices as st_indices
+        from .stencils import Layered, indices as st_indices
+        st = self.stencil if _st is None else _st
+        if isinstance(st, Layered):   # neighbors(::Layered, A, I): a tuple per layer (src/array.jl:117-120)
+            return tuple(self.neighbors(I, _st=l) for l in st.layers)
         h, par, vals = self.halo, self.parent, []
-        for J in st_indices(self.stencil, I):
+        for J in st_indices(st, I):
             if h:
                 vals.append(par[tuple(j - 1 + h for j in J)])
                 continue
@@ -215,7 +221,12 @@ class AbstractStencilArray:
     def stencil_at(self, *I):
         I = tuple(I[0]) if len(I) == 1 and isinstance(I[0], (tuple, list)) else tuple(I)
         c = self.inner()[tuple(i - 1 for i in I)]
-        return self.stencil.rebuild(self.neighbors(I), c.item() if hasattr(c, "item") else c)
+        c = c.item() if hasattr(c, "item") else c
+        from .stencils import Layered
+
+        def centers(st):   # _center(::Layered, A, I) = map over the layers (src/array.jl:33)
+            return tuple(centers(l) for l in st.layers) if isinstance(st, Layered) else c
+        return self.stencil.rebuild(self.neighbors(I), centers(self.stencil))
 
 
 def _check_radius(parent, stencil):

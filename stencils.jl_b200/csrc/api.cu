@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <array>
+#include <atomic>
 #include <cstdarg>
 #include <cmath>
 #include <mutex>
@@ -206,19 +207,52 @@ static std::string plan_key(const sb200_desc* d, int kind, int dev) {
     return k;
 }
 
+// One-entry memo per thread in front of the cache: a repeated call with the same descriptor (the launch-bound case: one
+// small sweep called in a loop) skips validation, key building, the mutex and the hash lookup. An eviction anywhere
+// invalidates every memo (g_evict_epoch).
+static std::atomic<unsigned long long> g_evict_epoch{0};
+struct PlanMemo {
+    sb200_desc d;
+    int kind = -1, dev = -1;
+    unsigned long long epoch = 0;
+    Plan* pl = nullptr;
+};
+static thread_local PlanMemo g_memo;
+
+static bool memo_hit(const sb200_desc* d, int kind, int dev) {
+    const PlanMemo& m = g_memo;
+    if (!m.pl || m.kind != kind || m.dev != dev || m.epoch != g_evict_epoch.load(std::memory_order_relaxed)) return false;
+    sb200_desc c = *d;
+    c.offsets_host = m.d.offsets_host; c.weights_host = m.d.weights_host;
+    c.mirror_parent = m.d.mirror_parent; c.mirror_lo = m.d.mirror_lo; c.mirror_hi = m.d.mirror_hi;
+    if (memcmp(&c, &m.d, sizeof(c)) != 0) return false;
+    if ((d->weights_host != nullptr) != (m.pl->d.weights_host != nullptr)) return false;
+    if (kind != PK_HALO) {
+        if (!d->offsets_host || memcmp(d->offsets_host, m.pl->d.offsets_host, sizeof(int32_t) * 3 * d->noffsets) != 0) return false;
+        if (d->weights_host && memcmp(d->weights_host, m.pl->d.weights_host, elsize(d->eltype) * d->noffsets) != 0) return false;
+    }
+    return true;
+}
+
 static int get_plan(const sb200_desc* d, int kind, Plan** out) {
-    int rc = validate(d, kind);
-    if (rc) return rc;
     int dev = 0;
     SB_CUDA(cudaGetDevice(&dev));
+    if (d && d->struct_size == (int)sizeof(sb200_desc) && memo_hit(d, kind, dev)) { *out = g_memo.pl; return SB200_OK; }
+    int rc = validate(d, kind);
+    if (rc) return rc;
     std::string key = plan_key(d, kind, dev);
     std::lock_guard<std::mutex> lock(g_plan_mu);
     auto it = g_plans.find(key);
-    if (it != g_plans.end()) { it->second->stamp = ++g_plan_stamp; *out = it->second; return SB200_OK; }
+    auto remember = [&](Plan* pl) {
+        g_memo.d = *d; g_memo.kind = kind; g_memo.dev = dev; g_memo.pl = pl;
+        g_memo.epoch = g_evict_epoch.load(std::memory_order_relaxed);
+    };
+    if (it != g_plans.end()) { it->second->stamp = ++g_plan_stamp; *out = it->second; remember(it->second); return SB200_OK; }
     if (g_plans.size() > 4096) {
         // unbounded descriptors (e.g. sliding regions): evict the plans that have not been looked up for a long time. A call
         // holds at most a handful of plans, all of them stamped within its last few lookups, so plans in use are never freed
         // (round 1 dropped the whole cache here, which could leave a caller with a dangling plan).
+        g_evict_epoch.fetch_add(1, std::memory_order_relaxed);
         const unsigned long long keep_from = g_plan_stamp > 1024 ? g_plan_stamp - 1024 : 0;
         for (auto jt = g_plans.begin(); jt != g_plans.end();) {
             if (jt->second->stamp < keep_from) { free_plan(jt->second); jt = g_plans.erase(jt); }
@@ -302,6 +336,7 @@ static int get_plan(const sb200_desc* d, int kind, Plan** out) {
     }
     pl->stamp = ++g_plan_stamp;
     g_plans[key] = pl;
+    remember(pl);
     *out = pl;
     return SB200_OK;
 }
@@ -356,6 +391,7 @@ int do_gather(const sb200_desc* d, const void* src, void* dst, cudaStream_t st) 
         if (rc < 0) rc = try_diffusion3d(*pl, src, dst, st);
         if (rc < 0) rc = try_tile2d(*pl, src, dst, st);
         if (rc < 0) rc = try_gather_stream(*pl, src, dst, st);
+        if (rc < 0) rc = try_box3d(*pl, src, dst, st);
         if (rc < 0) rc = try_gather_stream3d(*pl, src, dst, st);
     }
     if (rc < 0) rc = launch_generic_gather(*pl, src, dst, st);
@@ -583,119 +619,112 @@ int32_t sb200_iterate(const sb200_desc* d, void* buf_a, void* buf_b, int32_t nst
     // packed kernel does not accept).
     sb200_desc later = *d;
     if (d->reducer == SB200_LIFE && d->eltype == SB200_U8) later.flags |= SB200_FLAG_CELLS_01;
-    // Life: two generations per launch where the kernel supports it (half the HBM traffic per generation). The number
-    // of single-generation launches in front is chosen so that the final buffer is the one the contract names.
-    // Eight generations per launch (one-halo-lane layout of life_bit_kernel, the default build; SB200_OCT_STEP=0 turns it off):
-    // the bulk of a long Life run as an EVEN number of eight-generation launches up front (the buffer roles are then those of a
-    // fresh call), the rest as below.
-    bool fresh = true;   // the next launch is the first one of the call (UInt8 cells not yet known to be 0/1)
-    // the multi-generation kernels need 16-byte aligned parents: other pointers run one generation per launch
+    // Several generations per launch where a kernel supports it (Life: 2 / 4 / 8 with the intermediate generations in
+    // registers, life.cu; Diffusion: 2, stream3d2.cu): the run is split into launches of 8, 4, 2 and 1 generations — as few
+    // launches as possible, and an odd / even number of them for an odd / even step count, so that the final state lands in
+    // the buffer the contract names. Small launches go first; the rest of the run is launches of the largest size.
+    // SB200_NO_DOUBLE_STEP / SB200_NO_QUAD_STEP / SB200_OCT_STEP=0 / SB200_DIFFUSION_DOUBLE_STEP=0 cap the size (A/B runs).
+    // The multi-generation kernels need 16-byte aligned parents: other pointers run one generation per launch.
     const bool aligned16 = ((((uintptr_t)buf_a | (uintptr_t)buf_b) & 15) == 0);
-    if (aligned16 && d->reducer == SB200_LIFE && nsteps >= 48 && !halo && !(d->flags & (SB200_FLAG_DOUBLE_STEP | SB200_FLAG_QUAD_STEP | SB200_FLAG_OCT_STEP)) &&
-        !(getenv("SB200_OCT_STEP") && atoi(getenv("SB200_OCT_STEP")) == 0) && !getenv("SB200_NO_DOUBLE_STEP") && !getenv("SB200_NO_QUAD_STEP")) {
-        Plan* pl8 = nullptr;
-        sb200_desc probe = *d;
-        probe.flags |= SB200_FLAG_OCT_STEP;
-        if (get_plan(&probe, PK_GATHER, &pl8) == SB200_OK && life_multi_accepts(probe, *pl8, 8)) {
-            const int pairs = (nsteps - 16) / 16;   // keep at least 16 steps for the schedule below
-            for (int j = 0; j < 2 * pairs; j++) {
-                sb200_desc cur = fresh ? *d : later;
-                cur.flags |= SB200_FLAG_OCT_STEP;
-                const int rc = do_gather(&cur, s, t, (cudaStream_t)stream);
-                if (rc) return rc;
-                fresh = false;
-                void* tmp = s; s = t; t = tmp;
-            }
-            nsteps -= 16 * pairs;
-        }
-    }
-    int singles = nsteps, doubles = 0;   // launches of 1 and 2 generations in front; the rest of the run is 4 (or 2) per launch
-    int steady = 1;
     const bool life = d->reducer == SB200_LIFE;
-    // Diffusion: two steps per launch (stream3d2.cu; 1094 vs 763 Gcell-updates/s on 1024^3 Float32). SB200_DIFFUSION_DOUBLE_STEP=0 turns it off.
     const char* e_d2 = getenv("SB200_DIFFUSION_DOUBLE_STEP");
     const bool diff2 = d->reducer == SB200_DIFFUSION && (e_d2 ? atoi(e_d2) != 0 : kDiffusionDoubleStepDefault);
-    if (aligned16 && (life || diff2) && nsteps >= 4 && !halo && !(d->flags & (SB200_FLAG_DOUBLE_STEP | SB200_FLAG_QUAD_STEP)) &&
-        !getenv("SB200_NO_DOUBLE_STEP")) {
-        Plan* pl = nullptr;
-        sb200_desc probe = *d;
-        probe.flags |= SB200_FLAG_DOUBLE_STEP;
-        if (get_plan(&probe, PK_GATHER, &pl) == SB200_OK && (life ? life2_accepts(probe, *pl) : diffusion2_accepts(probe, *pl))) {
-            steady = 2;
-            probe.flags = d->flags | SB200_FLAG_QUAD_STEP;
-            Plan* pl4 = nullptr;
-            if (life && nsteps >= 16 && get_plan(&probe, PK_GATHER, &pl4) == SB200_OK && life_multi_accepts(probe, *pl4, 4) && !getenv("SB200_NO_QUAD_STEP"))
-                steady = 4;
-            // fewest launches in front such that the rest divides by `steady` and the launch count has the parity of nsteps
-            bool found = false;
-            for (int tot = 0; tot <= 8 && !found; tot++)
-                for (int dd2 = steady == 4 ? tot : 0; dd2 >= 0 && !found; dd2--) {
-                    const int ss = tot - dd2, rest = nsteps - ss - 2 * dd2;
-                    if (rest < 0 || rest % steady) continue;
-                    if (((ss + dd2 + rest / steady) & 1) == (nsteps & 1)) { singles = ss; doubles = dd2; found = true; }
-                }
-            if (!found) { singles = nsteps; doubles = 0; steady = 1; }
+    int maxg = 1;
+    if (aligned16 && (life || diff2) && nsteps >= 4 && !halo &&
+        !(d->flags & (SB200_FLAG_DOUBLE_STEP | SB200_FLAG_QUAD_STEP | SB200_FLAG_OCT_STEP)) && !getenv("SB200_NO_DOUBLE_STEP")) {
+        auto accepts = [&](int flag) {
+            sb200_desc probe = *d;
+            probe.flags |= flag;
+            return multistep_accepts(&probe);
+        };
+        if (accepts(SB200_FLAG_DOUBLE_STEP)) {
+            maxg = 2;
+            if (life && !getenv("SB200_NO_QUAD_STEP") && accepts(SB200_FLAG_QUAD_STEP)) {
+                maxg = 4;
+                if (!(getenv("SB200_OCT_STEP") && atoi(getenv("SB200_OCT_STEP")) == 0) && accepts(SB200_FLAG_OCT_STEP)) maxg = 8;
+            }
         }
     }
-    // One launch of the loop body: [ring refresh] + sweep s -> t (one or two generations).
-    auto body = [&](int i, int gens, void* from, void* to) -> int {
+    int cnt[4] = {nsteps, 0, 0, 0};   // launches of 1, 2, 4, 8 generations
+    if (maxg > 1) {
+        const int top = maxg == 8 ? 3 : maxg == 4 ? 2 : 1;   // index of the largest size
+        int best = nsteps + 1;
+        for (int ntop = nsteps >> top; ntop >= 0 && ntop >= (nsteps >> top) - 4; ntop--) {
+            const int rest = nsteps - (ntop << top);
+            int lim[3] = {3, top >= 2 ? 3 : 0, top >= 3 ? 3 : 0};   // counts of 1, 2, 4 (sizes below the top one)
+            if (top == 1) lim[0] = rest;                              // only singles below doubles
+            for (int c4 = 0; c4 <= lim[2]; c4++)
+                for (int c2 = 0; c2 <= (top >= 2 ? lim[1] : 0); c2++) {
+                    const int c1 = rest - 4 * c4 - 2 * c2;
+                    if (c1 < 0 || c1 > lim[0]) continue;
+                    int c[4] = {c1, c2, c4, 0};
+                    c[top] += ntop;
+                    const int launches = c[0] + c[1] + c[2] + c[3];
+                    if (((launches ^ nsteps) & 1) == 0 && launches < best) { best = launches; memcpy(cnt, c, sizeof(c)); }
+                }
+        }
+    }
+    // One launch of the loop body: [ring refresh] + sweep from -> to (gens generations).
+    bool fresh = true;   // the next launch is the first one of the call (UInt8 cells not yet known to be 0/1)
+    auto body = [&](int gens, void* from, void* to) -> int {
         int rc;
         if (halo && (rc = sb200_update_halo(d, from, stream))) return rc;
-        sb200_desc cur = (i == 0 && fresh) ? *d : later;
+        sb200_desc cur = fresh ? *d : later;
         if (gens == 2) cur.flags |= SB200_FLAG_DOUBLE_STEP;
         if (gens == 4) cur.flags |= SB200_FLAG_QUAD_STEP;
-        return do_gather(&cur, from, to, (cudaStream_t)stream);
+        if (gens == 8) cur.flags |= SB200_FLAG_OCT_STEP;
+        rc = do_gather(&cur, from, to, (cudaStream_t)stream);
+        if (rc == SB200_OK) fresh = false;
+        return rc;
     };
-    int done = 0, i = 0;
-    // Small grids are launch-bound (a 1000 x 1000 sweep takes ~3 us of GPU time): once the plans exist, the steady part of
-    // the loop is captured ONCE as a CUDA graph of GRAPH_CHUNK launches and replayed, so the per-launch CPU + driver cost
+    // Small grids are launch-bound (a 1000 x 1000 sweep takes ~3 us of GPU time): once the plans exist, a run of equal
+    // launches is captured ONCE as a CUDA graph of GRAPH_CHUNK launches and replayed, so the per-launch CPU + driver cost
     // is paid per chunk. Capture needs a real stream (not the legacy default stream) and an even chunk (same buffer roles).
     long long cells = 1;
     for (int a = 0; a < d->ndim; a++) cells *= d->size[a];
     constexpr int GRAPH_CHUNK = 32;
     bool want_graph = stream != nullptr && cells <= (4LL << 20) && !getenv("SB200_NO_GRAPH");
-    bool warm[5] = {false, false, false, false, false};   // a direct launch with the steady-state descriptor has created this mode's plan
-    for (; done < nsteps; i++) {
-        const int per = steady == 1 ? 1 : (i < singles ? 1 : (i < singles + doubles ? 2 : steady));
-        const bool in_steady = steady == 1 || i >= singles + doubles;
-        const int left_launches = (nsteps - done) / per;
-        if (want_graph && warm[per] && in_steady && left_launches >= 2 * GRAPH_CHUNK) {
-            cudaStream_t cs = (cudaStream_t)stream;
-            cudaGraph_t graph = nullptr;
-            cudaGraphExec_t exec = nullptr;
-            bool ok = cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
-            int rc = SB200_OK;
-            if (ok) {
-                void *cs_ = s, *ct_ = t;
-                for (int j = 0; j < GRAPH_CHUNK && rc == SB200_OK; j++) {
-                    rc = body(i + j, per, cs_, ct_);
-                    void* tmp = cs_; cs_ = ct_; ct_ = tmp;
-                }
-                ok = cudaStreamEndCapture(cs, &graph) == cudaSuccess && rc == SB200_OK && graph != nullptr;
-            }
-            if (ok) ok = cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess;
-            if (ok) {
-                const int chunks = left_launches / GRAPH_CHUNK;
-                for (int c = 0; c < chunks && ok; c++) ok = cudaGraphLaunch(exec, cs) == cudaSuccess;
+    for (int size_idx = 0; size_idx < 4; size_idx++) {
+        const int per = 1 << size_idx;
+        int left = cnt[size_idx];
+        int issued = 0;   // direct launches of this size so far (the second one runs with the steady-state descriptor: its plan exists)
+        while (left > 0) {
+            if (want_graph && issued >= 2 && !fresh && left >= 2 * GRAPH_CHUNK) {
+                cudaStream_t cs = (cudaStream_t)stream;
+                cudaGraph_t graph = nullptr;
+                cudaGraphExec_t exec = nullptr;
+                bool ok = cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+                int rc = SB200_OK;
                 if (ok) {
-                    done += chunks * GRAPH_CHUNK * per;
-                    i += chunks * GRAPH_CHUNK - 1;      // the buffer roles are unchanged after an even number of launches
-                    count_launch(chunks * GRAPH_CHUNK - GRAPH_CHUNK);  // the captured launches were counted once already
+                    void *cs_ = s, *ct_ = t;
+                    for (int j = 0; j < GRAPH_CHUNK && rc == SB200_OK; j++) {
+                        rc = body(per, cs_, ct_);
+                        void* tmp = cs_; cs_ = ct_; ct_ = tmp;
+                    }
+                    ok = cudaStreamEndCapture(cs, &graph) == cudaSuccess && rc == SB200_OK && graph != nullptr;
                 }
+                if (ok) ok = cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess;
+                if (ok) {
+                    const int chunks = left / GRAPH_CHUNK;
+                    for (int c = 0; c < chunks && ok; c++) ok = cudaGraphLaunch(exec, cs) == cudaSuccess;
+                    if (ok) {
+                        left -= chunks * GRAPH_CHUNK;                       // the buffer roles are unchanged after an even number of launches
+                        count_launch(chunks * GRAPH_CHUNK - GRAPH_CHUNK);   // the captured launches were counted once already
+                    }
+                }
+                if (exec) cudaGraphExecDestroy(exec);
+                if (graph) cudaGraphDestroy(graph);
+                if (ok) continue;
+                cudaGetLastError();   // capture unavailable (e.g. an enclosing capture): plain launches from here on
+                want_graph = false;   // nothing was enqueued
+                continue;
             }
-            if (exec) cudaGraphExecDestroy(exec);
-            if (graph) cudaGraphDestroy(graph);
-            if (ok) continue;
-            cudaGetLastError();   // capture unavailable (e.g. an enclosing capture): plain launches from here on
-            i--;                   // nothing was enqueued: redo this iteration without the graph
-            want_graph = false;
-            continue;
+            int rc;
+            if ((rc = body(per, s, t))) return rc;
+            issued++;
+            left--;
+            void* tmp = s; s = t; t = tmp;
         }
-        int rc;
-        if ((rc = body(i, per, s, t))) return rc;
-        if (i >= 1) warm[per] = true;
-        done += per;
-        void* tmp = s; s = t; t = tmp;
     }
     return SB200_OK;
 }
@@ -815,6 +844,7 @@ int32_t sb200_shutdown(void) {
     cudaDeviceSynchronize();
     {
         std::lock_guard<std::mutex> lock(g_plan_mu);
+        g_evict_epoch.fetch_add(1, std::memory_order_relaxed);
         for (auto& kv : g_plans) free_plan(kv.second);
         g_plans.clear();
     }

@@ -180,6 +180,7 @@ int try_diffusion3d_double(const Plan& pl, const void* src, void* dst, cudaStrea
 bool diffusion2_accepts(const sb200_desc& d, const Plan& pl);
 int try_gather_stream(const Plan& pl, const void* src, void* dst, cudaStream_t st);
 int try_gather_stream3d(const Plan& pl, const void* src, void* dst, cudaStream_t st);
+int try_box3d(const Plan& pl, const void* src, void* dst, cudaStream_t st);   // Window(1,3) / Moore(1,3) at compile time (box3d.cu)
 int try_scatter_fast(const Plan& pl, const void* src, void* dst, cudaStream_t st);
 int try_scatter_stream(const Plan& pl, const void* src, void* dst, cudaStream_t st, int x_lo, int x_hi, int y_lo, int y_hi);
 

@@ -17,7 +17,8 @@ int try_tile2d(const Plan& pl, const void* src, void* dst, cudaStream_t st) {
     case SB200_CROSS: case SB200_DIAMOND: rc = s2_group_d(pl, src, dst, st); break;
     default: break;
     }
-    if (rc == SB200_OK) set_kernel_name("stream2d_kernel");
+    const bool fma = d.reducer == SB200_KERNELDOT && (d.flags & SB200_FLAG_ALLOW_FMA) && pl.shape_tag == SB200_WINDOW && d.radius <= 3;
+    if (rc == SB200_OK) set_kernel_name(fma ? "stream2d_kernel<fma>" : "stream2d_kernel");
     return rc;
 }
 

@@ -22,6 +22,10 @@
 namespace sb {
 
 constexpr int S2_WARPS = 8;
+// kernelproduct with the multiply-add contracted into one FMA (SB200_FLAG_ALLOW_FMA): a reducer code of its own for the templates
+constexpr int S2_KDOT_FMA = 100;
+__device__ __forceinline__ float s2_fma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+__device__ __forceinline__ double s2_fma(double a, double b, double c) { return __fma_rn(a, b, c); }
 // EXPERIMENT (default 1 = the measured kernels; not yet run on a GPU with another value): producer warps of the element-granular
 // cp.async mode (Halo rings / unaligned rows, mean F64 + Halo{:out} 0.74 of peak). One warp issues 16-32 LDGSTS per lane and
 // row; the 3-D kernels were producer-bound with far less (lesson 3). Each producer warp copies every
@@ -261,6 +265,7 @@ __device__ __forceinline__ void s2_row(const S2Params<T>& p, const S2Thread<T>& 
                 else if (RED == SB200_MAX) acc[s][v] = kk == 0 ? x : jl_max(acc[s][v], x);
                 else if (RED == SB200_MIN) acc[s][v] = kk == 0 ? x : jl_min(acc[s][v], x);
                 else if (RED == SB200_KERNELDOT) acc[s][v] = add_rn(kk == 0 ? T(0) : acc[s][v], mul_rn(x, p.weights[kk]));
+                else if (RED == S2_KDOT_FMA) acc[s][v] = s2_fma(x, p.weights[kk], kk == 0 ? T(0) : acc[s][v]);
             }
         }
         }

@@ -19,7 +19,7 @@ from . import _abi as A
 from ._desc import DescHandle, build_desc, require_exact
 from .array import (AbstractStencilArray, Halo, Remove, StencilArray, SwitchingStencilArray, Use, _is_torch, _np_dtype,
                     data_ptr, is_device, similar)
-from .stencils import Kernel, Stencil
+from .stencils import Kernel, Layered, Stencil, layer
 
 
 # ---- the reducer menu (BASELINE.json north_star: mean, sum, min, max, Kernel dot-product, Life table; + diffusion) ----
@@ -92,8 +92,18 @@ def _bc_enum(bc):
     return bc.enum
 
 
+_raw_stream = None
+
+
 def _stream():
+    """cudaStream_t of torch's current stream on the current device (raw accessor when this torch has it: the Stream object
+    round trip costs ~2 us per call, which matters for launch-bound grids like the README's 1000 x 1000)."""
+    global _raw_stream
     import torch
+    if _raw_stream is None:
+        _raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", False)
+    if _raw_stream:
+        return _raw_stream(torch.cuda.current_device())
     return torch.cuda.current_stream().cuda_stream
 
 
@@ -178,9 +188,22 @@ def update_boundary_(A_: AbstractStencilArray, buf=None):
 
 
 def _gather_into(red: Reducer, dst_parent, dst_halo, src_parent, src_halo, st, bc, flags=0):
+    # Repeated call with the very same objects (the launch-bound case: README benchmark, 1000 x 1000): everything that was
+    # checked and built the first time is remembered on the stencil object, keyed by object identity.
+    fast = st.__dict__.get("_fast_call")
+    if (fast is not None and fast[0] is red and fast[1]() is src_parent and fast[2]() is dst_parent and fast[3] is bc and fast[4] == flags
+            and fast[5] == (src_halo, dst_halo, src_parent.shape, dst_parent.shape)):
+        rc = fast[7](fast[6], src_parent.data_ptr(), dst_parent.data_ptr(), _stream())
+        if rc:
+            A.check(rc)
+        return dst_parent
     _same_place(src_parent, dst_parent)
     h = _desc_for(red, src_parent, src_halo, dst_parent, dst_halo, st, bc, flags=flags)
     l = A.lib()
+    if is_device(src_parent) and not (src_halo and not isinstance(bc, Use)):
+        import weakref   # weak: a long-lived stencil object must not keep multi-GiB parents alive
+        st.__dict__["_fast_call"] = (red, weakref.ref(src_parent), weakref.ref(dst_parent), bc, flags,
+                                     (src_halo, dst_halo, src_parent.shape, dst_parent.shape), h.ptr(), l.sb200_gather, h)
     if is_device(src_parent):
         if src_halo and not isinstance(bc, Use):
             A.check(l.sb200_update_halo(h.ptr(), data_ptr(src_parent), _stream()))   # src/gatherstencil.jl:93
@@ -203,8 +226,13 @@ class LinearCombination(Reducer):
     def __init__(self, *terms):
         from .stencils import center as _center
         self.terms = []
+        self.layer_keys = []
         for t in terms:
             coef, g = (None, t) if not isinstance(t, (tuple, list)) else (float(t[0]), t[1])
+            key = None
+            if isinstance(g, layer):   # a term over one layer of a Layered array (src/stencils/layered.jl)
+                key, g = g.key, g.g
+            self.layer_keys.append(key)
             if g is _center or g == "center":
                 g = "center"
             else:
@@ -219,6 +247,14 @@ class LinearCombination(Reducer):
 
 def gather_multi_(f: LinearCombination, dst, *srcs):
     """gatherstencil!(f, dest, A1, A2, ...) with several array arguments -> sb200_gather_multi."""
+    keys = getattr(f, "layer_keys", [None] * len(f.terms))
+    if len(srcs) == 1 and isinstance(srcs[0], AbstractStencilArray) and isinstance(srcs[0].stencil, Layered):
+        # one Layered array: every term reads the same parent through the table of its layer
+        if any(k is None for k in keys):
+            raise A.ArgumentError("every term over a Layered array must name its layer: layer(key, g)")
+        srcs = srcs * len(f.terms)
+    elif any(k is not None for k in keys):
+        raise A.ArgumentError("layer(key, g) terms need a single StencilArray with a Layered stencil")
     if len(srcs) != len(f.terms):
         raise A.ArgumentError(f"{f!r} has {len(f.terms)} terms but {len(srcs)} array arguments were passed")
     if isinstance(dst, AbstractStencilArray):
@@ -230,6 +266,13 @@ def gather_multi_(f: LinearCombination, dst, *srcs):
     for j, (src, (coef, g)) in enumerate(zip(srcs, f.terms)):
         if isinstance(src, AbstractStencilArray):
             par, halo, st, bc = src.parent, src.halo, src.stencil, src.boundary
+            if keys[j] is not None:
+                try:
+                    st = st[keys[j]]
+                except (KeyError, IndexError, TypeError):
+                    raise A.ArgumentError(f"the Layered stencil has no layer {keys[j]!r}") from None
+            if isinstance(st, Layered):
+                raise A.ArgumentError("a term needs one stencil: pick a leaf layer with layer(key, g) (a tuple key walks nested layers)")
         else:
             if g != "center":
                 raise A.ArgumentError("a plain array argument is indexed, not stencilled: its term must be `center`")
@@ -275,9 +318,11 @@ def gatherstencil_(f, *args, flags=0):
     if isinstance(dst, AbstractStencilArray):
         _gather_into(red, dst.parent, dst.halo, src.parent, src.halo, src.stencil, src.boundary, flags)
     else:
-        from .array import as_colmajor
-        if as_colmajor(dst) is not dst:
-            raise A.ArgumentError("dest must be column-major (first axis contiguous)")
+        fast = src.stencil.__dict__.get("_fast_call")
+        if fast is None or fast[2]() is not dst:   # a dest that went through _gather_into before was checked then
+            from .array import as_colmajor
+            if as_colmajor(dst) is not dst:
+                raise A.ArgumentError("dest must be column-major (first axis contiguous)")
         _gather_into(red, dst, 0, src.parent, src.halo, src.stencil, src.boundary, flags)
     return dst
 

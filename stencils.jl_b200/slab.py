@@ -517,74 +517,6 @@ def split_axis_last(shape_global, world, rank):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
-def bench_weak(workload, spec, steps, warmup, synth=None, strong=False):
-    """Scaling benchmark body used by bench.py under torchrun: every rank owns a slab of spec['shape'] (weak scaling), or,
-    with strong=True, 1/world of spec['shape'] along the last axis (strong scaling: the one-GPU problem split over the ranks);
-    returns (ms on this rank, total owned cells over all ranks, launches in the timed region, kernel, config)."""
-    import torch
-    import torch.distributed as dist
-    from .stencils import Moore, VonNeumann
-    from .synth import synth_torch
-    rank, world = dist.get_rank(), dist.get_world_size()
-    dev = torch.device("cuda", torch.cuda.current_device())
-    shape = tuple(spec["shape"])
-    if strong:
-        if shape[-1] % world:
-            raise SystemExit(f"--strong needs the last axis ({shape[-1]}) to be a multiple of the number of GPUs ({world})")
-        shape = shape[:-1] + (shape[-1] // world,)
-    cells_local = int(np.prod(shape))
-    # rank r's slab is planes [r*n, (r+1)*n) of the global field -> linear index offset r * cells_local
-    field = synth_torch(shape, spec["dtype"], spec["seed"], dev, lo=rank * cells_local)
-    t = field.permute(*reversed(range(len(shape)))).contiguous()
-    del field
-    if workload == "life":
-        st, red, kw, et, R, ghost = Moore(1), A.LIFE, dict(born_mask=1 << 3, survive_mask=0b1100), A.U8, 1, 32
-        bcs = (A.WRAP, A.WRAP)
-    elif workload == "diffusion":
-        st, red, kw, et, R, ghost = VonNeumann(1, 3), A.DIFFUSION, dict(alpha=0.1), A.F32, 1, 4
-        bcs = (A.WRAP, A.WRAP, A.WRAP)
-    else:
-        raise SystemExit(f"workload {workload} is not an iterated (slab-partitioned) configuration")
-    it = SlabIterator(t, offsets=st.offsets(), radius=R, reducer=red, boundary=bcs, eltype=et, ghost=ghost, rank=rank,
-                      world=world, reducer_kwargs=kw, exchange=os.environ.get("SB200_EXCHANGE", "auto"),
-                      overlap={"1": True, "0": False}.get(os.environ.get("SB200_OVERLAP", ""), None))
-    del t
-    lib = A.lib()
-    it.step(warmup)
-    torch.cuda.synchronize()
-    kernel = lib.sb200_last_kernel().decode()
-    dist.barrier()
-    torch.cuda.synchronize()
-    lib.sb200_launch_count(1)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    it.step(steps)
-    e1.record()
-    torch.cuda.synchronize()
-    dist.barrier()
-    ms = e0.elapsed_time(e1)
-    launches = lib.sb200_launch_count(1)
-    exchange, fused, it_overlap = it.exchange, it.fused, it.overlap
-    dist.barrier()
-    it.close()
-    kernel = lib.sb200_last_kernel().decode()   # the kernel of the timed region (iterated runs may fuse steps)
-    if exchange == "p2p" and it_overlap and "stream3d2" in kernel:
-        how = ("boundary planes computed first (two-step sweeps), copied into the neighbour's landing slot by a stream-ordered "
-               "peer copy over NVLink inside the call (stream3d2_kernel has no fused store yet), sb200_signal_flag, acquire wait "
-               "+ ghost copy on a side stream, overlapped with the interior update of the last sweep of each cycle")
-    elif exchange == "p2p" and fused and it_overlap:
-        how = ("peer-memory stores over NVLink fused into the boundary sweeps (sb200_desc.mirror_*, sb200_signal_flag), acquire wait "
-               "+ ghost copy on a side stream, overlapped with the interior update of the last sweep of each cycle")
-    elif exchange == "p2p":
-        how = ("peer-memory stores over NVLink (sb200_push_planes + release/acquire flags) after the last sweep of each cycle"
-               if not it_overlap else "peer-memory stores over NVLink (sb200_push_planes) on a side stream under the interior update")
-    else:
-        how = "NCCL send/recv" + (" on a side stream under the interior update" if it_overlap else " after the last sweep of each cycle")
-    cfg = {"ghost_planes": ghost, "steps_per_exchange": ghost // R, "exchange": how,
-           "global_grid": list(shape[:-1]) + [shape[-1] * world]}
-    return ms, cells_local * world, launches, kernel, cfg
-
-
 # ------------------------------------------------------------------------------------------------ one-shot sweeps
 def slab_gather(local_owned, *, offsets, radius, reducer, boundary, eltype, rank, world, compute=None,
                 reducer_kwargs=None, padval=0, exchange="auto"):

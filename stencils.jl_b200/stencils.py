@@ -182,6 +182,97 @@ class Kernel(Stencil):
         self.shape_enum = st.shape_enum
 
 
+class Layered:
+    """Layered(layers...) / Layered(name=stencil, ...) / Layered(tuple_or_dict) (src/stencils/layered.jl:13-57): stencils that
+    are used together on one array. `radius` is the largest layer radius (it sizes the Halo ring), `len` and the accessor
+    functions map over the layers; layers may be Layered themselves. On the GPU a Layered array feeds multi-table gathers:
+    `LinearCombination(layer(0, sum), (-1.0, layer(1, sum)))` is the reference test's `sum(l[1]) - sum(l[2])`
+    (test/stencils.jl:242-264), one sweep of the same parent per referenced layer."""
+
+    def __init__(self, *layers, **named):
+        if named:
+            if layers:
+                raise A.ArgumentError("Layered takes positional layers or keyword layers, not both")
+            names, layers = tuple(named), tuple(named.values())
+        else:
+            names = None
+            if len(layers) == 1 and isinstance(layers[0], dict):
+                names, layers = tuple(layers[0]), tuple(layers[0].values())
+            elif len(layers) == 1 and isinstance(layers[0], (tuple, list)):
+                layers = tuple(layers[0])
+        if not layers or not all(isinstance(l, (Stencil, Layered)) for l in layers):
+            raise A.ArgumentError("Layered needs one or more stencils")
+        self.layers = tuple(layers)
+        self.names = names
+        self.ndims = layers[0].ndims                       # ndimensions(first(layers))
+        self.radius = max(l.radius for l in layers)        # maximum(map(radius, layers))
+
+    def __len__(self):
+        raise TypeError("length of a Layered is a tuple: use lengths()")
+
+    def lengths(self):
+        """Base.length(l::Layered) = map(length, layers(l))"""
+        return tuple(l.lengths() if isinstance(l, Layered) else len(l) for l in self.layers)
+
+    def _index(self, key):
+        if isinstance(key, str):
+            if self.names is None or key not in self.names:
+                raise KeyError(key)
+            return self.names.index(key)
+        return int(key)
+
+    def __getitem__(self, key):
+        if isinstance(key, tuple):   # a path through nested layers
+            cur = self
+            for k in key:
+                cur = cur[k]
+            return cur
+        return self.layers[self._index(key)]
+
+    def __getattr__(self, name):
+        names = self.__dict__.get("names")
+        if names and name in names:
+            return self.__dict__["layers"][names.index(name)]
+        raise AttributeError(name)
+
+    def __iter__(self):
+        return iter(self.layers)
+
+    def offsets(self):
+        return tuple(l.offsets() for l in self.layers)
+
+    @property
+    def neighbors(self):
+        return tuple(l.neighbors for l in self.layers)
+
+    @property
+    def center(self):
+        return tuple(l.center for l in self.layers)
+
+    def rebuild(self, layerneighbors, centers):
+        out = Layered(*[l.rebuild(n, c) for l, n, c in zip(self.layers, layerneighbors, centers)])
+        out.names = self.names
+        return out
+
+    def __eq__(self, other):
+        return isinstance(other, Layered) and self.layers == other.layers and self.names == other.names
+
+    def __hash__(self):
+        return hash((self.layers, self.names))
+
+    def __repr__(self):
+        inner = ", ".join((f"{n}=" if self.names else "") + repr(l) for n, l in zip(self.names or [None] * len(self.layers), self.layers))
+        return f"Layered{{R={self.radius},N={self.ndims}}}({inner})"
+
+
+class layer:
+    """A term of a LinearCombination over a Layered array: g applied to layer `key` (index, name, or a tuple path through
+    nested layers) — `sum(l[1])` is layer(0, sum), `sum(l.l1.b)` is layer(("l1", "b"), sum)."""
+
+    def __init__(self, key, g):
+        self.key, self.g = key, g
+
+
 # ---- free functions of the reference API ----
 def offsets(s):
     return s.offsets()
@@ -196,7 +287,7 @@ def diameter(s):
 
 
 def neighbors(s, *I):
-    if isinstance(s, Stencil):
+    if isinstance(s, (Stencil, Layered)):
         return s.neighbors
     return s.neighbors(*I)  # StencilArray
 
@@ -206,15 +297,21 @@ def center(s):
 
 
 def distances(s):
+    if isinstance(s, Layered):
+        return tuple(distances(l) for l in s.layers)
     return tuple(math.sqrt(sum(v * v for v in o)) for o in s.offsets())  # src/stencil.jl:116-120
 
 
 def distance_zones(s):
+    if isinstance(s, Layered):
+        return tuple(distance_zones(l) for l in s.layers)
     return tuple(sum(abs(v) for v in o) for o in s.offsets())  # src/stencil.jl:127-129
 
 
 def indices(s, I):
     """indices(hood, I) (src/stencil.jl:90-96) or indices(A::StencilArray, I) with the array's boundary."""
+    if isinstance(s, Layered):
+        return tuple(indices(l, I) for l in s.layers)   # indices(layered, I) = map(l -> indices(l, I), layered)
     if not isinstance(s, Stencil):
         return s.indices(I)
     I = tuple(I)

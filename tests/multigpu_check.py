@@ -73,12 +73,71 @@ def one_shot_cases(rank, world, dev):
     return bad_total
 
 
+def plan_cases(rank, world, dev):
+    """The C-ABI slab plan in its rank form (sb200_plan_create_rank / _connect: one process per GPU, IPC mailboxes, flag-ordered
+    exchange) against sb200_iterate on the undivided array on this GPU, bit for bit."""
+    from stencils_b200._desc import build_desc
+    from stencils_b200.slab import SlabPlan
+    bad_total = 0
+    cases = [
+        ("life", (4096, 1024 * world), np.uint8, (A.WRAP, A.WRAP), 0, 0, (70, 9)),                      # G = 32: 8 generations per launch
+        ("life", (2048, 512 * world + 3), np.uint8, (A.REFLECT, A.REMOVE), 2, A.PLAN_OVERLAP_ON, (9,)),  # fused mirror store, ragged
+        ("diffusion", (256, 192, 64 * world), np.float32, (A.WRAP, A.WRAP, A.WRAP), 0, 0, (22, 5)),      # G = 4, two steps per launch, overlap
+        ("diffusion", (256, 192, 64 * world), np.float32, (A.WRAP, A.WRAP, A.WRAP), 4, A.PLAN_SINGLE_STEP, (13,)),   # stream3d MIRROR store
+        ("diffusion", (128, 100, 40 * world + 1), np.float32, (A.REMOVE, A.WRAP, A.REFLECT), 2, A.PLAN_OVERLAP_ON, (7,)),
+    ]
+    for name, shape, dt, bcs, ghost, pflags, chunks in cases:
+        full = synth_torch(shape, dt, 0xABC, dev)
+        if name == "life":
+            st, red, kw, et = sb.Moore(1), A.LIFE, dict(born_mask=8, survive_mask=12), A.U8
+        else:
+            st, red, kw, et = sb.VonNeumann(1, 3), A.DIFFUSION, dict(alpha=0.1), A.F32
+        tfull = full.permute(*reversed(range(len(shape)))).contiguous()   # split axis first == column-major memory
+        plan = SlabPlan(shape, offsets=st.offsets(), radius=1, reducer=red, boundary=bcs, eltype=et, ghost=ghost, rank=rank, world=world,
+                        reducer_kwargs=kw, padval=0, plan_flags=pflags)
+        try:
+            lo, hi, _, ptr = plan.slab(0)
+            mine = tfull[lo:hi].contiguous()
+            A.check(A.lib().sb200_memcpy_d2d(ptr, mine.data_ptr(), mine.numel() * mine.element_size(), None))
+            A.check(A.lib().sb200_stream_sync(None))
+            plan.mark_dirty()
+            for n in chunks:
+                plan.iterate(n)
+            plan.sync()
+            lo, hi, _, ptr = plan.slab(0)
+            got = torch.empty_like(mine)
+            A.check(A.lib().sb200_memcpy_d2d(got.data_ptr(), ptr, got.numel() * got.element_size(), None))
+            A.check(A.lib().sb200_stream_sync(None))
+            stats = plan.stats()
+            dist.barrier()
+        finally:
+            plan.close()
+        nsteps = sum(chunks)
+        h = build_desc(size=shape, eltype=et, out_eltype=et, offsets=st.offsets(), radius=1, boundary=bcs, reducer=red, padval=0, **kw)
+        a = tfull.clone()
+        b = torch.empty_like(a)
+        A.check(A.lib().sb200_iterate(h.ptr(), a.data_ptr(), b.data_ptr(), nsteps, torch.cuda.current_stream().cuda_stream))
+        ref = a if nsteps % 2 == 0 else b
+        torch.cuda.synchronize()
+        bad = (got.view(torch.uint8) != ref[lo:hi].view(torch.uint8)).sum()
+        dist.all_reduce(bad)
+        if rank == 0:
+            print(f"plan {name} {shape} bcs={bcs} steps={chunks} {stats}: mismatching bytes = {int(bad)}", flush=True)
+        bad_total += int(bad)
+    return bad_total
+
+
 def main():
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
     dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ["LOCAL_RANK"])))
     dev = torch.device("cuda", torch.cuda.current_device())
-    bad_total = 0
+    bad_total = plan_cases(rank, world, dev)
+    if "--plan-only" in sys.argv:
+        if rank == 0:
+            print("MULTIGPU CHECK " + ("PASSED" if bad_total == 0 else f"FAILED ({bad_total} bytes)"), flush=True)
+        dist.destroy_process_group()
+        sys.exit(0 if bad_total == 0 else 1)
     cases = [
         ("life", (4096, 1024 * world), np.uint8, (A.WRAP, A.WRAP), 16, 40),
         ("life", (2048, 512 * world + 3), np.uint8, (A.REFLECT, A.REMOVE), 2, 9),

@@ -25,8 +25,8 @@ from oracle import oracle as orc  # noqa: E402
 from stencils_b200 import _abi as A  # noqa: E402
 from stencils_b200._desc import build_desc  # noqa: E402
 
-WANT = ["life_bit_kernel<4", "life_bit_kernel<2", "life_tma2_kernel", "life_tma_kernel", "life_swar_kernel",
-        "stream2d_kernel", "stream3d_kernel", "stream3d2_kernel", "gather_stream_kernel", "gather_stream3d_kernel", "gather_generic",
+WANT = ["life_bit_kernel<8", "life_bit_kernel<4", "life_bit_kernel<2", "life_tma2_kernel", "life_tma_kernel", "life_swar_kernel",
+        "stream2d_kernel", "stream3d_kernel", "stream3d2_kernel", "gather_stream_kernel", "gather_stream3d_kernel", "box3d_kernel<window>", "box3d_kernel<moore>", "gather_generic",
         "scatter_stream_kernel", "scatter_fast_kernel", "halo_kernel"]
 seen = {}
 DRY = False  # --dry: no device calls, only the oracle side (checks the case table itself on a box without a GPU)
@@ -128,7 +128,7 @@ def gather_case(what, r, offs, R, bc, red, *, pad="cond", flags=0, region=None, 
         return
     s, d = Dev(parent), Dev(dst0)
     p_cpu = parent.copy(order="F")
-    gens = 4 if flags & A.FLAG_QUAD_STEP else 2 if flags & A.FLAG_DOUBLE_STEP else 1
+    gens = 8 if flags & A.FLAG_OCT_STEP else 4 if flags & A.FLAG_QUAD_STEP else 2 if flags & A.FLAG_DOUBLE_STEP else 1
     if gens > 1:  # dest = f(f(src)) / f^4(src) on the output region, everything else of dest untouched
         A.check(l.sb200_gather(h.ptr(), s.p, d.p, None))
         A.check(l.sb200_stream_sync(None))
@@ -190,6 +190,7 @@ def main():
     gather_case("life 1040x70 wrap, two generations (SWAR)", g16, moore, 1, WR, A.LIFE, flags=A.FLAG_DOUBLE_STEP)
     gather_case("life 1024x96 wrap, two generations (bit-sliced)", g, moore, 1, WR, A.LIFE, flags=A.FLAG_DOUBLE_STEP)
     gather_case("life 1024x96 wrap, four generations (bit-sliced)", g, moore, 1, WR, A.LIFE, flags=A.FLAG_QUAD_STEP)
+    gather_case("life 1024x96 wrap, eight generations (bit-sliced, one halo lane)", g, moore, 1, WR, A.LIFE, flags=A.FLAG_OCT_STEP)
     gather_case("life 1024x96 wrap, iterate x21", g, moore, 1, WR, A.LIFE, nsteps=21)
     gather_case("life 1024x96 wrap, no TMA", g, moore, 1, WR, A.LIFE, flags=A.FLAG_NO_TMA)
     if full:
@@ -233,7 +234,9 @@ def main():
     vn3 = npr.offsets("VonNeumann", 1, 3)
     gather_case("VonNeumann(1,3) diffusion F32 wrap", v, vn3, 1, WR, A.DIFFUSION, alpha=0.1)
     gather_case("VonNeumann(1,3) diffusion F32 wrap, two steps per launch", v, vn3, 1, WR, A.DIFFUSION, alpha=0.1, flags=A.FLAG_DOUBLE_STEP)
-    gather_case("Window(1,3) mean F32 wrap (run-time table)", v, npr.offsets("Window", 1, 3), 1, WR, A.MEAN)
+    gather_case("Window(1,3) mean F32 wrap (box3d)", v, npr.offsets("Window", 1, 3), 1, WR, A.MEAN)
+    gather_case("Moore(1,3) max F32 remove/reflect/wrap (box3d)", v, npr.offsets("Moore", 1, 3), 1, (RE, RF, WR), A.MAX, padval=0.75)
+    gather_case("Circle(2,3) sum F32 wrap (run-time table)", v, npr.offsets("Circle", 2, 3), 2, WR, A.SUM)
     if full:
         gather_case("VonNeumann(1,3) diffusion F32 remove/reflect/wrap", v, vn3, 1, (RE, RF, WR), A.DIFFUSION, alpha=0.1, padval=0.25)
         gather_case("VonNeumann(1,3) diffusion F64 300x17x12 two steps, region z 2..10", rand(rng, (300, 17, 12), np.float64), vn3, 1, (WR, WR, RE), A.DIFFUSION,

@@ -287,6 +287,46 @@ def test_multi_stencilarray_mapstencil(orc):
     bits_equal(host(got), want)
 
 
+def test_layered_stencils(orc):
+    """Layered (src/stencils/layered.jl:13-57; reference test test/stencils.jl:242-264): `sum(l[1]) - sum(l[2])` and
+    `sum(l.l1.b) - sum(l.l2.a)` as multi-table gathers over ONE parent, on the reference's 5 x 5 array and on random Float32
+    fields with Halo padding (ring sized by the largest layer radius), against per-layer oracle sweeps combined left to right."""
+    p1, p2 = sb.Positional(((-1, -1), (1, 1))), sb.Positional(((-2, -2), (2, 2)))
+    arr = np.asfortranarray(np.arange(1.0, 26.0).reshape(5, 5, order="F"))
+    layered = sb.Layered(p1, p2)
+    a = sb.StencilArray(dev(arr), layered)
+    got = sb.mapstencil(sb.LinearCombination(sb.layer(0, sb.sum), (-1.0, sb.layer(1, sb.sum))), a)
+
+    def lsum(x, st, bc=A.REMOVE, pad="cond", padval=0.0):
+        return orc.stencil_array_sweep(np.asfortranarray(x), st.offsets(), st.radius, bc, pad, A.SUM, padval=padval)
+    want = lsum(arr, p1) + (-1.0) * lsum(arr, p2)
+    bits_equal(host(got), want)
+    assert host(got)[2, 2] == (7 + 19) - (1 + 25)
+    ml = sb.Layered(l1=sb.Layered(a=p1, b=p2), l2=sb.Layered(a=p1, b=p2))
+    a2 = sb.StencilArray(dev(arr), ml)
+    got2 = sb.mapstencil(sb.LinearCombination(sb.layer(("l1", "b"), sb.sum), (-1.0, sb.layer(("l2", "a"), sb.sum))), a2)
+    bits_equal(host(got2), lsum(arr, p2) + (-1.0) * lsum(arr, p1))
+    # random field, Halo{:out} ring of the LARGEST layer radius, Wrap: mean over Window(1) + 0.5 * maximum over Circle(3) - centre
+    rng = np.random.default_rng(9)
+    X = np.asfortranarray(rng.random((256, 96)).astype(np.float32) - 0.3)
+    lay = sb.Layered(near=sb.Window(1), far=sb.Circle(3))
+    for pad, padname in ((sb.Halo("out"), "cond"), (None, "cond")):
+        sx = sb.StencilArray(dev(X), lay, boundary=sb.Wrap(), padding=pad)
+        assert sx.halo == (3 if pad is not None else 0)
+        f = sb.LinearCombination(sb.layer("near", sb.mean), (0.5, sb.layer("far", sb.maximum)), (-1.0, sb.layer("near", sb.center)))
+        got3 = sb.mapstencil(f, sx)
+        t1 = orc.stencil_array_sweep(X, npr.offsets("Window", 1, 2), 1, A.WRAP, padname, A.MEAN)
+        t2 = orc.stencil_array_sweep(X, npr.offsets("Circle", 3, 2), 3, A.WRAP, padname, A.MAX)
+        want3 = (t1 + np.float32(0.5) * t2) + np.float32(-1.0) * X
+        bits_equal(host(got3), want3)
+    with pytest.raises(sb.ArgumentError):
+        sb.mapstencil(sb.LinearCombination(sb.sum, sb.sum), a)                      # terms must name their layer
+    with pytest.raises(sb.ArgumentError):
+        sb.mapstencil(sb.LinearCombination(sb.layer(5, sb.sum)), a)                 # no such layer
+    with pytest.raises(sb.ArgumentError):
+        sb.mapstencil(sb.LinearCombination(sb.layer("l1", sb.sum)), a2)             # a nested Layered is not a leaf
+
+
 def test_torch_free_case_table_matches_oracle():
     """tests/sanitize_cases.py (the compute-sanitizer driver: every kernel family on exact cudaMalloc allocations, no torch)
     as a plain parity run: every case bit-identical to the oracle."""

@@ -214,3 +214,103 @@ def test_diffusion_1024_cubed_two_steps_per_launch():
     torch.cuda.synchronize()
     assert _biteq(mid[:, :, 4:n - 4], want[:, :, 4:n - 4])
     assert bool((mid[:, :, :4] == 7.0).all()) and bool((mid[:, :, n - 4:] == 7.0).all())
+
+
+# ---- SURVEY 8d tier T3 long runs: the whole grid against the oracle over MANY schedule cycles ----
+def test_long_run_life_2048_1000_generations(orc):
+    """Life 2048 x 2048 UInt8 Wrap x 1000 generations through sb200_iterate (8 / 4 / 2 / 1 generations per launch, small-grid
+    CUDA-graph replay on a real stream) and through a three-slab plan, full grid against orc.iterate, bit for bit."""
+    import torch
+    from stencils_b200.slab import SlabPlan
+    from stencils_b200.synth import synth_np
+    shape = (2048, 2048)
+    g = np.asfortranarray(synth_np(shape, np.uint8, 0x5EED0002))
+    kw = dict(eltype=A.U8, out_eltype=A.U8, offsets=npr.offsets("Moore", 1, 2), radius=1, boundary=A.WRAP, reducer=A.LIFE)
+    h = build_desc(size=shape, **kw)
+    want = orc.iterate(h, g.copy(order="F"), np.zeros_like(g, order="F"), 1000)
+    assert 0 < int(want.sum()) < want.size
+    l = A.lib()
+    for stream in (None, torch.cuda.Stream()):
+        a = torch.from_numpy(np.ascontiguousarray(g.T)).cuda()
+        b = torch.zeros_like(a)
+        torch.cuda.synchronize()
+        l.sb200_launch_count(1)
+        A.check(l.sb200_iterate(h.ptr(), a.data_ptr(), b.data_ptr(), 1000, stream.cuda_stream if stream is not None else None))
+        torch.cuda.synchronize()
+        launches = l.sb200_launch_count(1)
+        assert launches <= 130, launches   # 124 x 8 + 2 x 4 generations
+        bits_equal(np.asfortranarray(a.cpu().numpy().T), want)
+    plan = SlabPlan(shape, offsets=npr.offsets("Moore", 1, 2), radius=1, reducer=A.LIFE, boundary=(A.WRAP, A.WRAP), eltype=A.U8, ghost=0,
+                    devices=[0, 0, 0], reducer_kwargs=dict(born_mask=8, survive_mask=12))
+    try:
+        plan.load(g)
+        for n in (333, 1, 666):
+            plan.iterate(n)
+        plan.sync()
+        bits_equal(plan.store(), want)
+    finally:
+        plan.close()
+
+
+def test_long_run_diffusion_128_500_steps(orc):
+    """3-D diffusion 128^3 Float32 Wrap x 500 steps (two steps per launch, graph replay) and a two-slab plan with overlap, full
+    grid against orc.iterate, bit for bit; plus Remove / Reflect axes for 101 steps."""
+    import torch
+    from stencils_b200.slab import SlabPlan
+    from stencils_b200.synth import synth_np
+    shape = (128, 128, 128)
+    g = np.asfortranarray(synth_np(shape, np.float32, 0x5EED0005))
+    offs = npr.offsets("VonNeumann", 1, 3)
+    kw = dict(eltype=A.F32, out_eltype=A.F32, offsets=offs, radius=1, reducer=A.DIFFUSION, alpha=0.1)
+    l = A.lib()
+    for bcs, n in (((A.WRAP, A.WRAP, A.WRAP), 500), ((A.REMOVE, A.WRAP, A.REFLECT), 101)):
+        h = build_desc(size=shape, boundary=bcs, padval=0.25, **kw)
+        want = orc.iterate(h, g.copy(order="F"), np.zeros_like(g, order="F"), n)
+        st = torch.cuda.Stream()
+        a = torch.from_numpy(np.ascontiguousarray(g.transpose(2, 1, 0))).cuda()
+        b = torch.zeros_like(a)
+        torch.cuda.synchronize()
+        A.check(l.sb200_iterate(h.ptr(), a.data_ptr(), b.data_ptr(), n, st.cuda_stream))
+        torch.cuda.synchronize()
+        got = (a if n % 2 == 0 else b).cpu().numpy().transpose(2, 1, 0)
+        bits_equal(np.asfortranarray(got), want)
+        plan = SlabPlan(shape, offsets=offs, radius=1, reducer=A.DIFFUSION, boundary=bcs, eltype=A.F32, ghost=4, devices=[0, 0],
+                        reducer_kwargs=dict(alpha=0.1), padval=0.25, plan_flags=A.PLAN_OVERLAP_ON)
+        try:
+            plan.load(g)
+            plan.iterate(n)
+            plan.sync()
+            bits_equal(plan.store(), want)
+        finally:
+            plan.close()
+
+
+def test_config0_literal_mean_1000x1000_float64_remove(orc):
+    """BASELINE configs[0] literally (README.md:142-170): mapstencil(mean, StencilArray(rand(1000, 1000), Window(1))), Float64,
+    Remove(0.0), Conditional padding — whole grid against the oracle, through the host mirror, called repeatedly (the repeated
+    call takes the remembered-descriptor fast path) and into a fresh dest."""
+    import torch
+    import stencils_b200 as sb
+    from stencils_b200.synth import synth_np
+    r = np.asfortranarray(synth_np((1000, 1000), np.float64, 0x5EED0001))
+    h = build_desc(size=r.shape, eltype=A.F64, out_eltype=A.F64, offsets=npr.offsets("Window", 1, 2), radius=1, boundary=A.REMOVE,
+                   reducer=A.MEAN, padval=0.0)
+    want = orc.gather(h, r, np.zeros_like(r, order="F"))
+    src = torch.from_numpy(np.ascontiguousarray(r.T)).cuda().T
+    a = sb.StencilArray(src, sb.Window(1), boundary=sb.Remove(0.0))
+    out = sb.mapstencil(sb.mean, a)
+    torch.cuda.synchronize()
+    bits_equal(np.asfortranarray(out.cpu().numpy()), want)
+    dst = sb.colmajor_empty((1000, 1000), torch.float64, src.device)
+    for i in range(5):
+        dst.zero_()
+        sb.mapstencil_(sb.mean, dst, a)
+        torch.cuda.synchronize()
+        bits_equal(np.asfortranarray(dst.cpu().numpy()), want)
+    # another dest, another source through the same stencil object: the remembered call must not be reused
+    r2 = np.asfortranarray(r[::-1, :].copy())
+    a2 = sb.StencilArray(torch.from_numpy(np.ascontiguousarray(r2.T)).cuda().T, a.stencil, boundary=a.boundary)
+    dst2 = sb.colmajor_empty((1000, 1000), torch.float64, src.device)
+    sb.mapstencil_(sb.mean, dst2, a2)
+    torch.cuda.synchronize()
+    bits_equal(np.asfortranarray(dst2.cpu().numpy()), orc.gather(h, r2, np.zeros_like(r2, order="F")))

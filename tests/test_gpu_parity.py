@@ -481,7 +481,10 @@ def test_gather_stream3d_any_table(orc, dt, bc):
         w = rng.random(len(offs)) if isf else rng.integers(1, 5, len(offs))
         for red in (("sum", "mean", "max", "kerneldot", "diffusion") if isf else ("sum", "min", "kerneldot")):
             both(orc, r, offs, R, bc, "cond", red, padval=1.25 if isf else 3, weights=w, alpha=0.07)
-            assert l.sb200_last_kernel() == b"gather_stream3d_kernel", (tab, red, l.sb200_last_kernel())
+            # Window(1,3) / Moore(1,3) float folds have compile-time kernels (csrc/box3d.cu); everything else is the table kernel
+            box = isf and tab in (("Window", 1), ("Moore", 1)) and red in ("sum", "mean", "max", "min")
+            want_kernel = (b"box3d_kernel<window>" if tab[0] == "Window" else b"box3d_kernel<moore>") if box else b"gather_stream3d_kernel"
+            assert l.sb200_last_kernel() == want_kernel, (tab, red, l.sb200_last_kernel())
 
 
 def test_gather_stream3d_ghost_planes_regions_specials(orc):
@@ -501,7 +504,52 @@ def test_gather_stream3d_ghost_planes_regions_specials(orc):
                 want = orc.gather(h, parent, dst_like(h, 9))
                 got, _ = gpu_gather(h, parent, dst_like(h, 9))
                 bits_equal(got, want)
-                assert l.sb200_last_kernel() == b"gather_stream3d_kernel"
+                assert l.sb200_last_kernel() == (b"gather_stream3d_kernel" if R == 2 else b"box3d_kernel<window>" if red == A.MAX else b"box3d_kernel<moore>")
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+@pytest.mark.parametrize("shape_name", ["Window", "Moore"])
+def test_box3d_compile_time_box_stencils(orc, dt, shape_name):
+    """csrc/box3d.cu: Window(1,3) / Moore(1,3) x sum / mean / minimum / maximum with the folds in registers (two running
+    chains per cell for the sums, separable extrema): several tiles in x and y with ragged last ones, z runs, every boundary
+    per axis, NaN / -0.0 / Inf cells, output regions along z, against the oracle bit for bit; and whole-grid equality with
+    the one-thread-per-cell generic kernel on a grid that fills every CTA several times."""
+    rng = np.random.default_rng(63)
+    l = A.lib()
+    es = np.dtype(dt).itemsize
+    et = A.ELTYPE_OF_DTYPE[np.dtype(dt)]
+    offs = npr.offsets(shape_name, 1, 3)
+    name = b"box3d_kernel<window>" if shape_name == "Window" else b"box3d_kernel<moore>"
+    for shape in [(1024 // es + 64 // es, 37, 21), (32 // es * 3, 20, 40), (2 * 1024 // es, 16, 9), (512 // es, 3, 5)]:
+        r = rand_array(rng, shape, dt)
+        r[rng.random(shape) < 0.02] = np.nan
+        r[rng.random(shape) < 0.05] = -0.0
+        r[rng.random(shape) < 0.01] = np.inf
+        for bcs in [(A.WRAP, A.WRAP, A.WRAP), (A.REMOVE, A.REFLECT, A.WRAP), (A.REFLECT, A.REMOVE, A.REMOVE), (A.WRAP, A.WRAP, A.REFLECT)]:
+            for red in (A.SUM, A.MEAN, A.MAX, A.MIN):
+                h = build_desc(size=shape, eltype=et, out_eltype=et, offsets=offs, radius=1, boundary=bcs, reducer=red, padval=-1.5)
+                want = orc.gather(h, r, dst_like(h))
+                got, _ = gpu_gather(h, r, dst_like(h))
+                assert l.sb200_last_kernel() == name, l.sb200_last_kernel()
+                bits_equal(got, want)
+        Z = shape[2]
+        if Z >= 9:
+            for region in (((0, 0, 0), shape[:2] + (4,)), ((0, 0, 3), shape[:2] + (Z - 2,)), ((0, 0, Z - 1), shape)):
+                h = build_desc(size=shape, eltype=et, out_eltype=et, offsets=offs, radius=1, boundary=(A.WRAP, A.REFLECT, A.REMOVE),
+                               reducer=A.SUM, padval=0.5, region=region)
+                want = orc.gather(h, r, dst_like(h, 9))
+                got, _ = gpu_gather(h, r, dst_like(h, 9))
+                assert l.sb200_last_kernel() == name
+                bits_equal(got, want)
+    big = rand_array(rng, (1536 // es * 2, 150, 70), dt)
+    for red in (A.MEAN, A.MAX):
+        h = build_desc(size=big.shape, eltype=et, out_eltype=et, offsets=offs, radius=1, boundary=A.WRAP, reducer=red)
+        got, _ = gpu_gather(h, big, dst_like(h))
+        assert l.sb200_last_kernel() == name
+        ref, _ = gpu_gather(build_desc(size=big.shape, eltype=et, out_eltype=et, offsets=offs, radius=1, boundary=A.WRAP, reducer=red,
+                                       flags=A.FLAG_FORCE_GENERIC), big, dst_like(h))
+        assert l.sb200_last_kernel() == b"gather_generic"
+        bits_equal(got, ref)
 
 
 @pytest.mark.parametrize("dt", [np.uint8, np.bool_])

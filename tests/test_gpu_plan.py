@@ -169,3 +169,20 @@ def test_plan_rank_form_world_one_and_errors(orc):
         SlabPlan((512, 64), boundary=bcs, ghost=2, devices=[99], reducer_kwargs=rkw2, padval=pv2, **rk2)
     with pytest.raises(A.ArgumentError):
         SlabPlan((512, 64), boundary=(A.WRAP, A.USE), ghost=2, devices=[0], reducer_kwargs=rkw2, padval=pv2, **rk2)
+
+
+def test_plan_rank_form_two_processes():
+    """One process per GPU (torchrun): IPC mailboxes + flag-ordered exchange, every rank compares its slab with sb200_iterate
+    on the undivided array (tests/multigpu_check.py --plan-only). Skipped below two devices."""
+    import os
+    import subprocess
+    import sys
+    n = ndev()
+    if n < 2:
+        pytest.skip("needs two or more CUDA devices")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    port = 29600 + os.getpid() % 300
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(min(n, 4)), "--master-addr", "127.0.0.1",
+           "--master-port", str(port), os.path.join(root, "tests", "multigpu_check.py"), "--plan-only"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0 and "MULTIGPU CHECK PASSED" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]

@@ -217,3 +217,27 @@ def test_inexact_weights_and_padval_are_refused():
     with pytest.raises(A.ArgumentError, match="cannot be represented exactly"):
         _desc_for(sb.sum, src, 0, dst, 0, sb.Window(1), sb.Remove(0.5))
     _desc_for(sb.kernelproduct, src, 0, dst, 0, sb.Kernel(sb.Window(1), np.full((3, 3), 2.0)), sb.Remove(0))
+
+
+def test_layered_goldens():
+    """test/stencils.jl:242-264: radius / offsets / indices / neighbors / center of a Layered stencil and nested named layers."""
+    p1, p2 = sb.Positional(((-1, -1), (1, 1))), sb.Positional(((-2, -2), (2, 2)))
+    layered = sb.Layered(p1, p2)
+    assert sb.radius(layered) == 2
+    assert sb.offsets(layered) == (((-1, -1), (1, 1)), ((-2, -2), (2, 2)))
+    assert sb.indices(layered, (1, 1)) == (((0, 0), (2, 2)), ((-1, -1), (3, 3)))
+    arr = np.asfortranarray(np.arange(1, 26).reshape(5, 5, order="F"))
+    a = sb.StencilArray(arr, layered)
+    filled = a.stencil_at(3, 3)
+    assert sb.neighbors(filled) == ((7, 19), (1, 25))
+    assert sb.center(filled) == (13, 13)
+    l1, l2 = sb.Layered(a=p1, b=p2), sb.Layered(a=p1, b=p2)
+    ml = sb.Layered(l1=l1, l2=l2)
+    filled2 = sb.StencilArray(arr, ml).stencil_at(3, 3)
+    assert filled2.l2.a.neighbors == (7, 19)
+    assert ml.lengths() == ((2, 2), (2, 2)) and ml[("l1", "b")] == p2 and sb.radius(ml) == 2
+    # Halo padding is sized by the largest layer radius (src/array.jl:471, src/padding.jl:104-110)
+    ah = sb.StencilArray(arr.astype(np.float64), layered, padding=sb.Halo("out"))
+    assert ah.parent.shape == (9, 9) and ah.shape == (5, 5)
+    with pytest.raises(sb.ArgumentError):
+        sb.Layered()
