@@ -119,6 +119,9 @@ def workloads():
                           shape=(16384, 16384), dtype=np.float64, bytes_per_cell=16, iterated=False, seed=0x5EED0001),
         "kernel": dict(desc="kernelproduct, Kernel(Window(3), 7x7 Float32) 16384x16384, Remove(0)/Conditional (configs[2])",
                        shape=(16384, 16384), dtype=np.float32, bytes_per_cell=8, iterated=False, seed=0x5EED0003),
+        "kernel_fma": dict(desc="the same with SB200_FLAG_ALLOW_FMA: acc = fma(v, w, acc), one rounding per tap (opt-in; the north star "
+                                "allows 2 ulp; max ulp against the bit-exact kernel over the whole grid is reported)",
+                           shape=(16384, 16384), dtype=np.float32, bytes_per_cell=8, iterated=False, seed=0x5EED0003),
         "circle": dict(desc="maximum over Circle(4), Float32 32768x32768, Remove(0) (configs[3]a)",
                        shape=(32768, 32768), dtype=np.float32, bytes_per_cell=8, iterated=False, seed=0x5EED0004),
         "scatter": dict(desc="scatterstencil!(+) Positional((-1,1),(-2,-1),(1,0),(-2,2)), val=centre*w, Float32 32768x32768 (configs[3]b)",
@@ -167,15 +170,24 @@ def make_sweep(name, spec, torch, sb, shape=None):
         def run(n):
             for _ in range(n):
                 sb.mapstencil_(sb.mean, dst, a)
-    elif name == "kernel":
+    elif name in ("kernel", "kernel_fma"):
+        from stencils_b200 import _abi as A_
         w = synth((7, 7), np.float32, 0x5EED1003)
         w = (w / w.sum(dtype=np.float32)).astype(np.float32)
         a = sb.StencilArray(src, sb.Kernel(sb.Window(3), w), boundary=sb.Remove(np.float32(0)))
         dst = sb.colmajor_empty(shape, torch.float32, dev)
+        fl = A_.FLAG_ALLOW_FMA if name == "kernel_fma" else 0
+        if fl:   # accuracy of the contracted fold against the bit-exact kernel of the same library, whole grid
+            exact = sb.colmajor_empty(shape, torch.float32, dev)
+            sb.mapstencil_(sb.kernelproduct, exact, a)
+            sb.mapstencil_(sb.kernelproduct, dst, a, flags=fl)
+            ia, ib = exact.T.contiguous().view(torch.int32).to(torch.int64), dst.T.contiguous().view(torch.int32).to(torch.int64)
+            st["max_ulp_vs_exact_kernel"] = int((ia - ib).abs().max().item())   # all values are positive: bit patterns are ordered
+            del exact, ia, ib
 
         def run(n):
             for _ in range(n):
-                sb.mapstencil_(sb.kernelproduct, dst, a)
+                sb.mapstencil_(sb.kernelproduct, dst, a, flags=fl)
     elif name == "circle":
         a = sb.StencilArray(src, sb.Circle(4), boundary=sb.Remove(np.float32(0)))
         dst = sb.colmajor_empty(shape, torch.float32, dev)
@@ -429,7 +441,7 @@ def roofline_of(workload, spec, value_per_gpu, kernel, peak, peak_src, sweeps_pe
     dram_frac = None
     if traffic and launches and ms_total:
         dram_frac = traffic * launches / (ms_total * 1e-3) / 1e9 / peak
-    binding = {"life": "alu", "kernel": "fp32_issue", "diffusion": "issue", "circle": "alu", "window3d": "fp32_issue"}.get(workload, "hbm")
+    binding = {"life": "alu", "kernel": "fp32_issue", "kernel_fma": "fp32_issue", "diffusion": "issue", "circle": "alu", "window3d": "fp32_issue"}.get(workload, "hbm")
     if workload == "life" and "life_bit" not in kernel:
         binding = "hbm"
     if workload == "diffusion" and "stream3d2" not in kernel:
@@ -576,7 +588,7 @@ def main():
         del st, run
         torch.cuda.empty_cache()
         also = {}
-        for name in ("mean", "mean_halo", "mean1000", "kernel", "circle", "positional", "scatter", "window3d", "diffusion"):
+        for name in ("mean", "mean_halo", "mean1000", "kernel", "kernel_fma", "circle", "positional", "scatter", "window3d", "diffusion"):
             if name == args.workload:
                 continue
             try:
@@ -596,6 +608,8 @@ def main():
                               "roofline_frac": v * sp["bytes_per_cell"] / peak, "workload": sp["desc"],
                               "roofline_frac_best_rep": cells2 * k / (min(t2) * 1e-3) / 1e9 * sp["bytes_per_cell"] / peak,
                               "timing": {kk: vv for kk, vv in rep_stats(t2, k).items() if kk != "how"}, "clocks": cs2.summary()}
+                if "max_ulp_vs_exact_kernel" in st2:
+                    also[name]["max_ulp_vs_exact_kernel"] = st2["max_ulp_vs_exact_kernel"]
                 if name == "mean1000":
                     also[name]["note"] = "8 MB grid: L2-resident and launch-bound by construction (the README's own benchmark size)"
                 del st2, run2

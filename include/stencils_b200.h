@@ -261,7 +261,8 @@ int32_t sb200_push_planes(const void* src, void* peer_dst, size_t bytes, uint32_
 /* Stream-ordered system-scope release store of `value` to a flag word (normally in a peer's memory): everything the
    stream wrote before — including the fused mirror stores of a sweep — is visible to a peer that acquires the flag. */
 int32_t sb200_signal_flag(uint32_t* peer_flag, uint32_t value, void* stream);
-/* Stream-ordered wait until *flag >= value (acquire). */
+/* Stream-ordered wait until *flag >= value (acquire). A flag that is not published within SB200_WAIT_TIMEOUT_MS (default
+   30 s) traps the kernel: the stream's next synchronisation fails instead of the GPU hanging on a dead neighbour. */
 int32_t sb200_wait_flag(const uint32_t* flag, uint32_t value, void* stream);
 
 /* Releases everything the library keeps between calls on the CURRENT device and thread: cached plans (device offset / weight

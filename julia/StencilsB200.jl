@@ -281,6 +281,56 @@ function iterate!(f, A::SwitchingStencilArray{R,T,N,<:B200Array}, nsteps::Intege
     return iseven(nsteps) ? A : switch(A)
 end
 
+# ---- the same loop over ALL the GPUs of the box: sb200_plan_* (include/stencils_b200.h, csrc/slab_plan.cu) ----
+# A Julia session is one process, so it uses the single-process form: the library splits the array into slabs along its last
+# axis, one per device, owns the slab buffers / mailboxes / streams and runs the exchange schedule (ghost planes over NVLink,
+# boundary planes first, interior sweep overlapping the exchange). Results are bit-identical to iterate! on one GPU.
+mutable struct SlabPlan
+    handle::Ptr{Cvoid}
+    size::Dims
+    eltype::DataType
+end
+
+"SlabPlan(f, A::SwitchingStencilArray over a host Array; devices = 0:ndevices-1, ghost = 0 (library default))"
+function SlabPlan(f, A::SwitchingStencilArray{R,T,N,<:Array}; devices = nothing, ghost::Integer = 0, flags::Integer = 0) where {R,T,N}
+    padding(A) isa Halo && throw(ArgumentError("slab plans take Conditional padding: the ghost planes are the plan's own ring"))
+    n = Ref{Int32}(0)
+    check(ccall((:sb200_device_count, LIB), Int32, (Ptr{Int32},), n))
+    devs = Int32.(collect(devices === nothing ? (0:n[]-1) : devices))
+    src = StencilArray(source(A), stencil(A), boundary(A), padding(A))
+    d, keep = make_desc(f, dest(A), 0, src, source(A))
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    GC.@preserve keep check(ccall((:sb200_plan_create, LIB), Int32, (Ref{Desc}, Int32, Ptr{Int32}, Int32, Int32, Ptr{Ptr{Cvoid}}),
+                                  d, length(devs), devs, ghost, flags, h))
+    plan = SlabPlan(h[], size(A), T)
+    finalizer(p -> (p.handle != C_NULL && ccall((:sb200_plan_destroy, LIB), Int32, (Ptr{Cvoid},), p.handle); p.handle = C_NULL), plan)
+    check(ccall((:sb200_plan_load_host, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}), plan.handle, source(A)))
+    return plan
+end
+
+"n generations on every GPU (returns when they are done; a dead neighbour is an error, not a hang)."
+function iterate!(plan::SlabPlan, nsteps::Integer)
+    check(ccall((:sb200_plan_iterate, LIB), Int32, (Ptr{Cvoid}, Int32), plan.handle, nsteps))
+    check(ccall((:sb200_plan_sync, LIB), Int32, (Ptr{Cvoid},), plan.handle))
+    return plan
+end
+
+"The current state as a host Array."
+function Base.Array(plan::SlabPlan)
+    out = Array{plan.eltype}(undef, plan.size)
+    check(ccall((:sb200_plan_store_host, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}), plan.handle, out))
+    return out
+end
+
+"`for _ in 1:n; A = mapstencil!(f, A); end` over every GPU of the box: A is a SwitchingStencilArray over a host Array."
+function iterate_multigpu!(f, A::SwitchingStencilArray{R,T,N,<:Array}, nsteps::Integer; kw...) where {R,T,N}
+    plan = SlabPlan(f, A; kw...)
+    iterate!(plan, nsteps)
+    copyto!(source(A), Array(plan))
+    finalize(plan)
+    return A
+end
+
 # update_boundary!(A) — src/array.jl:195-233
 function Stencils.update_boundary!(A::AbstractStencilArray{R,T,N,<:B200Array}) where {R,T,N}
     (padding(A) isa Halo && !(boundary(A) isa Use)) || return A

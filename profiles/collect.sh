@@ -3,14 +3,14 @@
 # of each dominant kernel. Outputs go to gpurun_out/; summarise here with `python profiles/summarize.py`.
 set -x
 mkdir -p gpurun_out
-R=${1:-r01}
+R=${1:-r02}
 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/${R}_launches_life.csv \
     python bench.py --steps 64 --warmup 16 --no-extras > gpurun_out/${R}_launches_life.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:life_bit -s 6 -c 1 -o gpurun_out/${R}_life \
     python bench.py --steps 64 --warmup 16 --no-extras > /dev/null 2>&1
 [ "$ONLY_LIFE" = 1 ] && exit 0
-for wl in mean kernel circle positional scatter diffusion; do
-  ncu --set full --clock-control none --import-source on -k regex:"stream2d|stream3d|scatter_fast|scatter_stream|gather_stream" -s 3 -c 1 -o gpurun_out/${R}_${wl} \
+for wl in mean mean_halo kernel kernel_fma circle positional scatter window3d diffusion; do
+  ncu --set full --clock-control none --import-source on -k regex:"stream2d|stream3d|scatter_fast|scatter_stream|gather_stream|box3d" -s 3 -c 1 -o gpurun_out/${R}_${wl} \
       python bench.py --workload ${wl} --steps 4 --warmup 3 --no-extras > /dev/null 2>&1
 done
 ls -la gpurun_out

@@ -52,10 +52,10 @@ def read(rep):
 
 
 def main():
-    rnd = sys.argv[1] if len(sys.argv) > 1 else "r01"
+    rnd = sys.argv[1] if len(sys.argv) > 1 else "r02"
     out_dir = os.path.join(ROOT, "gpurun_out")
     summary = {}
-    for wl in ("life", "mean", "kernel", "circle", "positional", "scatter", "diffusion", "diffusion2"):
+    for wl in ("life", "mean", "mean_halo", "kernel", "kernel_fma", "circle", "positional", "scatter", "window3d", "diffusion", "diffusion2"):
         rep = os.path.join(out_dir, f"{rnd}_{wl}.ncu-rep")
         if not os.path.exists(rep):
             continue

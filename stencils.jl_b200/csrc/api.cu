@@ -456,13 +456,23 @@ __global__ void signal_flag_kernel(uint32_t* flag, uint32_t value) {
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(value) : "memory");
 }
 
-__global__ void wait_flag_kernel(const uint32_t* flag, uint32_t value) {
+// Acquire spin with a deadline: a neighbour that never publishes (dead process, desynchronised schedule) must not hang the GPU
+// for good. After `timeout_ns` the kernel traps: the stream's next synchronisation returns a launch failure the caller sees.
+// (The slab plans use plan_wait_kernel, which reports through an error word instead: csrc/slab_plan.cu.)
+__global__ void wait_flag_kernel(const uint32_t* flag, uint32_t value, unsigned long long timeout_ns) {
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
     uint32_t v;
-    do {
+    for (unsigned it = 0;; it++) {
         asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
-        if ((int32_t)(v - value) >= 0) break;
+        if ((int32_t)(v - value) >= 0) return;
         __nanosleep(200);
-    } while (true);
+        if ((it & 1023) == 1023) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            if (t - t0 > timeout_ns) __trap();
+        }
+    }
 }
 
 // ---- multi-array gather: dest = t_1 + t_2 + ... over the logical box of the dest parent ----
@@ -493,8 +503,10 @@ template <typename T> static int launch_combine(int mode, void* d, const void* s
     SB_LAUNCH_CHECK();
     return SB200_OK;
 }
-static thread_local void* g_multi_scratch = nullptr;
-static thread_local size_t g_multi_scratch_bytes = 0;
+// library-owned scratch of sb200_gather_multi: one buffer per (thread, stream) — a single buffer shared by calls on different
+// streams would be a cross-stream race
+struct MultiScratch { void* p = nullptr; size_t bytes = 0; };
+static thread_local std::unordered_map<cudaStream_t, MultiScratch> g_multi_scratch;
 
 static thread_local unsigned int* g_done_ctr = nullptr;  // 64 counters, one per in-flight push
 static thread_local unsigned g_push_seq = 0;
@@ -575,13 +587,14 @@ int32_t sb200_gather_multi(const sb200_term* terms, int32_t nterms, void* dst, v
     const size_t db = parent_bytes(d0, false);
     const bool need_scratch = nterms > 1 || terms[0].has_coef;
     if (need_scratch && !scratch) {
-        if (g_multi_scratch_bytes < db) {
-            if (g_multi_scratch) cudaFree(g_multi_scratch);
-            g_multi_scratch = nullptr; g_multi_scratch_bytes = 0;
-            SB_CUDA(cudaMalloc(&g_multi_scratch, db));
-            g_multi_scratch_bytes = db;
+        MultiScratch& ms = g_multi_scratch[st];
+        if (ms.bytes < db) {
+            if (ms.p) { SB_CUDA(cudaStreamSynchronize(st)); cudaFree(ms.p); }   // the previous call on this stream may still use it
+            ms.p = nullptr; ms.bytes = 0;
+            SB_CUDA(cudaMalloc(&ms.p, db));
+            ms.bytes = db;
         }
-        scratch = g_multi_scratch;
+        scratch = ms.p;
     }
     int rc;
     for (int j = 0; j < nterms; j++) {
@@ -856,8 +869,8 @@ int32_t sb200_shutdown(void) {
     if (g_hs.a) cudaFree(g_hs.a);
     if (g_hs.b) cudaFree(g_hs.b);
     g_hs.a = g_hs.b = nullptr; g_hs.a_bytes = g_hs.b_bytes = 0;
-    if (g_multi_scratch) cudaFree(g_multi_scratch);
-    g_multi_scratch = nullptr; g_multi_scratch_bytes = 0;
+    for (auto& kv : g_multi_scratch) if (kv.second.p) cudaFree(kv.second.p);
+    g_multi_scratch.clear();
     if (g_done_ctr) cudaFree(g_done_ctr);
     g_done_ctr = nullptr;
     cudaGetLastError();
@@ -922,7 +935,9 @@ int32_t sb200_signal_flag(uint32_t* flag, uint32_t value, void* stream) {
 
 int32_t sb200_wait_flag(const uint32_t* flag, uint32_t value, void* stream) {
     if (!flag) return SB200_EINVAL;
-    wait_flag_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(flag, value);
+    static const unsigned long long timeout_ns =
+        (getenv("SB200_WAIT_TIMEOUT_MS") ? (unsigned long long)std::max(1, atoi(getenv("SB200_WAIT_TIMEOUT_MS"))) : 30000ull) * 1000000ull;
+    wait_flag_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(flag, value, timeout_ns);
     SB_LAUNCH_CHECK();
     return SB200_OK;
 }

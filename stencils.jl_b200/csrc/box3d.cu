@@ -83,8 +83,9 @@ __device__ __forceinline__ T b3_fold9(T acc, const T (&rowv)[NR][VX], const T (&
     return acc;
 }
 
-// MOORE: centre excluded. RED: SB200_SUM / SB200_MEAN / SB200_MAX / SB200_MIN.
-template <typename T, bool MOORE, int RED>
+// MOORE: centre excluded. RED: SB200_SUM / SB200_MEAN / SB200_MAX / SB200_MIN. PAD: some axis is Remove (out-of-bounds rows /
+// planes / columns read padval); the other instantiation carries no padval code at all.
+template <typename T, bool MOORE, int RED, bool PAD>
 __global__ void __launch_bounds__(B3_THREADS, 2) box3d_kernel(const __grid_constant__ B3Params<T> p) {
     constexpr int VX = 16 / (int)sizeof(T);
     constexpr int NR = B3_RT + 2;
@@ -135,7 +136,7 @@ __global__ void __launch_bounds__(B3_THREADS, 2) box3d_kernel(const __grid_const
                 const int slot = k % B3_STAGES;
                 const long long zpl = b3_map(z0 - 1 + i, p.Z, p.so2, p.bc2);
                 if (lane == 0) {
-                    mbar_wait(&empty[slot], ((k / B3_STAGES) & 1) ^ 1);
+                    mbar_wait_producer(&empty[slot], ((k / B3_STAGES) & 1) ^ 1, 200);
                     if (pw == 0) mbar_arrive_expect_tx(&full[slot], zpl >= 0 ? nrows * rowbytes : 0u);
                 }
                 __syncwarp();
@@ -157,8 +158,8 @@ __global__ void __launch_bounds__(B3_THREADS, 2) box3d_kernel(const __grid_const
         const int gx = (x0b + xtb) / (int)sizeof(T);
         const bool edge_l = xact && p.bc0 != SB200_WRAP && gx == 0;
         const bool edge_r = xact && p.bc0 != SB200_WRAP && gx + VX == p.X;
-        const bool pad1 = p.so1 == 0 && p.bc1 == SB200_REMOVE;   // OOB rows read padval
-        const bool pad2 = p.so2 == 0 && p.bc2 == SB200_REMOVE;   // OOB planes read padval
+        const bool pad1 = PAD && p.so1 == 0 && p.bc1 == SB200_REMOVE;   // OOB rows read padval
+        const bool pad2 = PAD && p.so2 == 0 && p.bc2 == SB200_REMOVE;   // OOB planes read padval
         // sums: a1 = chain of the output whose z-1 plane is folded, a2 = z-1 and z planes folded
         // extrema: a1 = box-plane extremum M of the previous plane, a2 = of the plane before; a3 (Moore) = ring of the previous plane
         T a1[B3_RT][VX], a2[B3_RT][VX], a3[MOORE && EXT ? B3_RT : 1][VX];
@@ -178,28 +179,29 @@ __global__ void __launch_bounds__(B3_THREADS, 2) box3d_kernel(const __grid_const
             T xl[NR], xr[NR];
 #pragma unroll
             for (int r = 0; r < NR; r++) {
-                const int y = y0 + ry0 - 1 + r;
-                const bool ypad = zpad || (pad1 && (y < 0 || y >= p.Y));
-                if (ypad) {
+                const unsigned char* t = sb_ + (ry0 + r) * B3_ROWB;
+                // (a row or plane outside a Remove axis was never copied: the stale shared-memory cells are read and replaced)
+                const typename B3Vec<T>::type q = *reinterpret_cast<const typename B3Vec<T>::type*>(t);
+                if constexpr (VX == 4) { rowv[r][0] = q.x; rowv[r][1] = q.y; rowv[r][2] = q.z; rowv[r][3] = q.w; }
+                else { rowv[r][0] = q.x; rowv[r][1] = q.y; }
+                // x neighbours across the 16-byte vectors come from the adjacent lanes; only the warp's end lanes read the
+                // halo cells (predicated loads: no divergent branch)
+                T l_ = __shfl_up_sync(0xffffffffu, rowv[r][VX - 1], 1);
+                T r_ = __shfl_down_sync(0xffffffffu, rowv[r][0], 1);
+                lds_if(l_, t - sizeof(T), lane == 0);
+                lds_if(r_, t + 16, lane == 31);
+                if (edge_l) l_ = p.bc0 == SB200_REFLECT ? rowv[r][1] : p.pad;
+                if (edge_r) r_ = p.bc0 == SB200_REFLECT ? rowv[r][VX - 2] : p.pad;
+                if constexpr (PAD) {
+                    const int y = y0 + ry0 - 1 + r;
+                    const bool ypad = zpad || (pad1 && (y < 0 || y >= p.Y));
 #pragma unroll
-                    for (int v = 0; v < VX; v++) rowv[r][v] = p.pad;
-                    xl[r] = p.pad; xr[r] = p.pad;
-                } else {
-                    const unsigned char* t = sb_ + (ry0 + r) * B3_ROWB;
-                    const typename B3Vec<T>::type q = *reinterpret_cast<const typename B3Vec<T>::type*>(t);
-                    if constexpr (VX == 4) { rowv[r][0] = q.x; rowv[r][1] = q.y; rowv[r][2] = q.z; rowv[r][3] = q.w; }
-                    else { rowv[r][0] = q.x; rowv[r][1] = q.y; }
-                    // x neighbours across the 16-byte vectors come from the adjacent lanes; only the warp's end lanes read
-                    // the halo cells. ypad is warp-uniform, so every lane takes part in the shuffles.
-                    T l_ = __shfl_up_sync(0xffffffffu, rowv[r][VX - 1], 1);
-                    T r_ = __shfl_down_sync(0xffffffffu, rowv[r][0], 1);
-                    if (lane == 0) l_ = *reinterpret_cast<const T*>(t - sizeof(T));
-                    if (lane == 31) r_ = *reinterpret_cast<const T*>(t + 16);
-                    if (edge_l) l_ = p.bc0 == SB200_REFLECT ? rowv[r][1] : p.pad;
-                    if (edge_r) r_ = p.bc0 == SB200_REFLECT ? rowv[r][VX - 2] : p.pad;
-                    xl[r] = l_;
-                    xr[r] = r_;
+                    for (int v = 0; v < VX; v++) rowv[r][v] = ypad ? p.pad : rowv[r][v];
+                    l_ = ypad ? p.pad : l_;
+                    r_ = ypad ? p.pad : r_;
                 }
+                xl[r] = l_;
+                xr[r] = r_;
             }
             const int zo = z - 1;  // output plane completed by this stage
             const bool store = i >= 2;
@@ -265,14 +267,14 @@ __global__ void __launch_bounds__(B3_THREADS, 2) box3d_kernel(const __grid_const
     }
 }
 
-template <typename T, bool MOORE, int RED> static int b3_launch(B3Params<T>& p, cudaStream_t st) {
+template <typename T, bool MOORE, int RED, bool PAD> static int b3_launch_p(B3Params<T>& p, cudaStream_t st) {
     static thread_local int cfg_dev = -1, ctas_per_sm = 0;
     int dev = 0;
     SB_CUDA(cudaGetDevice(&dev));
     if (dev != cfg_dev) {
-        SB_CUDA(cudaFuncSetAttribute(box3d_kernel<T, MOORE, RED>, cudaFuncAttributeMaxDynamicSharedMemorySize, B3_SMEM));
+        SB_CUDA(cudaFuncSetAttribute(box3d_kernel<T, MOORE, RED, PAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, B3_SMEM));
         int per_sm = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, box3d_kernel<T, MOORE, RED>, B3_THREADS, B3_SMEM) != cudaSuccess || per_sm < 1)
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, box3d_kernel<T, MOORE, RED, PAD>, B3_THREADS, B3_SMEM) != cudaSuccess || per_sm < 1)
             per_sm = 1;
         ctas_per_sm = per_sm;
         cfg_dev = dev;
@@ -295,9 +297,14 @@ template <typename T, bool MOORE, int RED> static int b3_launch(B3Params<T>& p, 
     p.nty = (p.Y + best_ty - 1) / best_ty;
     p.nzruns = best;
     const long long grid = std::min<long long>(ctas, (long long)p.ntx * p.nty * p.nzruns);
-    box3d_kernel<T, MOORE, RED><<<(unsigned)grid, B3_THREADS, B3_SMEM, st>>>(p);
+    box3d_kernel<T, MOORE, RED, PAD><<<(unsigned)grid, B3_THREADS, B3_SMEM, st>>>(p);
     SB_LAUNCH_CHECK();
     return SB200_OK;
+}
+
+template <typename T, bool MOORE, int RED> static int b3_launch(B3Params<T>& p, cudaStream_t st) {
+    const bool pad = p.bc0 == SB200_REMOVE || (p.so1 == 0 && p.bc1 == SB200_REMOVE) || (p.so2 == 0 && p.bc2 == SB200_REMOVE);
+    return pad ? b3_launch_p<T, MOORE, RED, true>(p, st) : b3_launch_p<T, MOORE, RED, false>(p, st);
 }
 
 template <typename T, bool MOORE> static int b3_try(const Plan& pl, const void* src, void* dst, cudaStream_t st) {

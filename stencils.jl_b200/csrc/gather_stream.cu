@@ -124,7 +124,7 @@ __global__ void __launch_bounds__((GS_WARPS + GS_PW) * 32, 3) gather_stream_kern
             for (int i = warp - GS_WARPS; i < nst; i += GS_PW) {
                 const unsigned k = kb + i;
                 const int slot = k % GS_NS;
-                mbar_wait(&empty[slot], ((k / GS_NS) & 1) ^ 1);
+                mbar_wait_producer(&empty[slot], ((k / GS_NS) & 1) ^ 1);
                 T* srow = reinterpret_cast<T*>(ring + slot * GS_STAGE + GS_LEFT);   // strip cell 0
                 const long long prow = gs_map_row(p, y0 - R + i);
                 if (prow >= 0) {
@@ -155,7 +155,7 @@ __global__ void __launch_bounds__((GS_WARPS + GS_PW) * 32, 3) gather_stream_kern
                 for (int i = 0; i < nst; i++) {
                     const unsigned k = kb + i;
                     const int slot = k % GS_NS;
-                    mbar_wait(&empty[slot], ((k / GS_NS) & 1) ^ 1);
+                    mbar_wait_producer(&empty[slot], ((k / GS_NS) & 1) ^ 1);
                     unsigned char* srow = ring + slot * GS_STAGE;
                     const long long prow = gs_map_row(p, y0 - R + i);
                     mbar_arrive_expect_tx(&full[slot], prow >= 0 ? rowbytes : 0u);

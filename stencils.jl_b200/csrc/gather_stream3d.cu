@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(G3_THREADS, 2) gather_stream3d_kernel(const __
                 const int slot = k % G3_NS;
                 const long long zpl = g3_map(z0 - R + i, p.Z, p.so2, p.bc2);
                 if (lane == 0) {
-                    mbar_wait(&empty[slot], ((k / G3_NS) & 1) ^ 1);
+                    mbar_wait_producer(&empty[slot], ((k / G3_NS) & 1) ^ 1);
                     if (pw == 0) mbar_arrive_expect_tx(&full[slot], zpl >= 0 ? nrows * rowbytes : 0u);
                 }
                 __syncwarp();

@@ -306,7 +306,7 @@ __global__ void __launch_bounds__((LT_WARPS + 1) * 32) life_tma_kernel(const Lif
                 const int rx = x0 + wbytes < p.W ? x0 + wbytes : 0;
                 for (int c = 0; c < nchunks; c++, k++) {
                     const int slot = k % LT_STAGES;
-                    mbar_wait(&empty[slot], ((k / LT_STAGES) & 1) ^ 1);
+                    mbar_wait_producer(&empty[slot], ((k / LT_STAGES) & 1) ^ 1);
                     uint8_t* sbase = ring + slot * (LT_CH * LT_ROWB);
                     unsigned bytes = 0;
                     long long prow[LT_CH];
@@ -492,7 +492,7 @@ __global__ void __launch_bounds__((LT2_WARPS + 1) * 32, 3) life_tma2_kernel(cons
                 const unsigned rowbytes = 64 + wout;
                 for (int c = 0; c < nchunks; c++, k++) {
                     const int slot = k % LT2_STAGES;
-                    mbar_wait(&empty[slot], ((k / LT2_STAGES) & 1) ^ 1);
+                    mbar_wait_producer(&empty[slot], ((k / LT2_STAGES) & 1) ^ 1);
                     uint8_t* sbase = ring + slot * (LT2_CH * LT2_ROWB);
                     const int nrows = min(LT2_CH, nsrc - c * LT2_CH);
                     mbar_arrive_expect_tx(&full[slot], nrows * rowbytes);
@@ -686,7 +686,7 @@ __global__ void __launch_bounds__((LB_WARPS + 1) * 32, 3) life_bit_kernel(const 
                 const unsigned rowbytes = 2 * C::HL + wout;
                 for (int c = 0; c < nchunks; c++, k++) {
                     const int slot = k % LB_STAGES;
-                    mbar_wait(&empty[slot], ((k / LB_STAGES) & 1) ^ 1);
+                    mbar_wait_producer(&empty[slot], ((k / LB_STAGES) & 1) ^ 1);
                     uint8_t* sbase = ring + slot * (LB_CH * LB_ROWB);
                     const int nrows = min(LB_CH, nsrc - c * LB_CH);
                     mbar_arrive_expect_tx(&full[slot], nrows * rowbytes);

@@ -100,7 +100,7 @@ __global__ void __launch_bounds__((SS_WARPS + 1) * 32, 2) scatter_stream_kernel(
                 for (int i = 0; i < nst; i++) {
                     const unsigned k = kb + i;
                     const int slot = k % SS_NS;
-                    mbar_wait(&empty[slot], ((k / SS_NS) & 1) ^ 1);
+                    mbar_wait_producer(&empty[slot], ((k / SS_NS) & 1) ^ 1);
                     unsigned char* sbase = ring + slot * SS_STAGE;
                     const int sj = y0 - R + i;
                     const bool has_src = sj >= 0 && sj < p.H;

@@ -101,7 +101,9 @@ template <typename T> struct S2Params {
     long long spitch, dpitch;  // elements per row
     int W, H;                  // logical size, axis 0 = W
     int soff0, soff1, doff0, doff1;
-    int cpasync;               // 1: element-granular cp.async producer (Halo ring on axis 0 / rows not 16-byte aligned)
+    int cpasync;               // 1: element-granular cp.async producer (rows / base not 16-byte aligned)
+    int delta;                 // bulk copies of a Halo-padded source (ring on axis 0): (src_off0 * sizeof(T)) % 16, the byte shift
+                               // of the shared-memory image that keeps global and shared addresses congruent mod 16
     int bc0, bc1;
     T pad;
     int y_lo, rows;
@@ -166,7 +168,10 @@ template <int SHAPE, int R, int RED> struct S2Roll {
 };
 
 // Fold source row J of the current stage (stream index i0 + J) into the 2R+1 outputs it belongs to.
-template <typename T, int SHAPE, int R, int RED, int J_>
+// SH: the shared-memory image is shifted by p.delta bytes (bulk copies of a Halo-padded source whose ring is not a multiple of
+// 16 bytes thick); a compile-time switch because the issue-bound folds (7 x 7 kernelproduct, Circle(4) maximum) lost 5 % to the
+// run-time form of it (r02f).
+template <typename T, int SHAPE, int R, int RED, int J_, bool SH>
 __device__ __forceinline__ void s2_row(const S2Params<T>& p, const S2Thread<T>& th, const unsigned char* sbase, int i0,
                                        T (&acc)[2 * R + 1][16 / sizeof(T)], T (&cen)[2 * R + 1][16 / sizeof(T)], int jrt = 0) {
     using C = S2Cfg<T, R>;
@@ -182,8 +187,13 @@ __device__ __forceinline__ void s2_row(const S2Params<T>& p, const S2Thread<T>& 
 #pragma unroll
         for (int e = 0; e < SEG; e++) seg[e] = p.pad;
     } else {
-        const unsigned char* t = sbase + J * C::ROWB + C::LEFT + th.xtb;
-        s2_ldvec<T>(t, &seg[R]);
+        const unsigned char* t = sbase + J * C::ROWB + C::LEFT + (SH ? p.delta : 0) + th.xtb;
+        if constexpr (!SH) {
+            s2_ldvec<T>(t, &seg[R]);
+        } else {   // ring on axis 0 whose thickness is not a multiple of 16 bytes: the thread's cells straddle two vectors
+#pragma unroll
+            for (int v = 0; v < VX; v++) seg[R + v] = *reinterpret_cast<const T*>(t + v * (int)sizeof(T));
+        }
 #pragma unroll
         for (int e = 0; e < R; e++) {
             seg[e] = *reinterpret_cast<const T*>(t - (R - e) * (int)sizeof(T));
@@ -197,7 +207,7 @@ __device__ __forceinline__ void s2_row(const S2Params<T>& p, const S2Thread<T>& 
                 seg[R + VX + e] = e >= th.rlim ? p.pad : seg[R + VX + e];
             }
         } else if (th.edge_l || th.edge_r) {
-            const unsigned char* row0 = sbase + J * C::ROWB + C::LEFT - th.x0b;  // address of global column 0
+            const unsigned char* row0 = sbase + J * C::ROWB + C::LEFT + (SH ? p.delta : 0) - th.x0b;  // address of global column 0
 #pragma unroll
             for (int e = 0; e < SEG; e++) {
                 const int x = th.gx - R + e;
@@ -294,20 +304,20 @@ __device__ __forceinline__ void s2_row(const S2Params<T>& p, const S2Thread<T>& 
     }
 }
 
-template <typename T, int SHAPE, int R, int RED, int J> struct S2Rows {
+template <typename T, int SHAPE, int R, int RED, int J, bool SH> struct S2Rows {
     static __device__ __forceinline__ void run(const S2Params<T>& p, const S2Thread<T>& th, const unsigned char* sbase, int i0,
                                                T (&acc)[2 * R + 1][16 / sizeof(T)], T (&cen)[2 * R + 1][16 / sizeof(T)]) {
         if constexpr (S2Roll<SHAPE, R, RED>::value) {
 #pragma unroll 1
-            for (int j = 0; j < S2Cfg<T, R>::CH; j++) s2_row<T, SHAPE, R, RED, 0>(p, th, sbase, i0, acc, cen, j);
+            for (int j = 0; j < S2Cfg<T, R>::CH; j++) s2_row<T, SHAPE, R, RED, 0, SH>(p, th, sbase, i0, acc, cen, j);
         } else {
-            s2_row<T, SHAPE, R, RED, J>(p, th, sbase, i0, acc, cen);
-            if constexpr (J + 1 < S2Cfg<T, R>::CH) S2Rows<T, SHAPE, R, RED, J + 1>::run(p, th, sbase, i0, acc, cen);
+            s2_row<T, SHAPE, R, RED, J, SH>(p, th, sbase, i0, acc, cen);
+            if constexpr (J + 1 < S2Cfg<T, R>::CH) S2Rows<T, SHAPE, R, RED, J + 1, SH>::run(p, th, sbase, i0, acc, cen);
         }
     }
 };
 
-template <typename T, int SHAPE, int R, int RED>
+template <typename T, int SHAPE, int R, int RED, bool SH>
 __global__ void __launch_bounds__(S2_THREADS, 2) stream2d_kernel(const __grid_constant__ S2Params<T> p) {
     using C = S2Cfg<T, R>;
     constexpr int VX = C::VX, P = C::P, CH = C::CH;
@@ -342,7 +352,7 @@ __global__ void __launch_bounds__(S2_THREADS, 2) stream2d_kernel(const __grid_co
             const bool wrap0 = !ring0 && p.bc0 == SB200_WRAP;
             for (int c = 0; c < nchunks; c++, k++) {
                 const int slot = k % C::STAGES;
-                mbar_wait(&empty[slot], ((k / C::STAGES) & 1) ^ 1);
+                mbar_wait_producer(&empty[slot], ((k / C::STAGES) & 1) ^ 1);
                 unsigned char* sbase = ring + slot * (CH * C::ROWB);
                 for (int j = 0; j < CH; j++) {
                     const int i = c * CH + j;
@@ -361,6 +371,42 @@ __global__ void __launch_bounds__(S2_THREADS, 2) stream2d_kernel(const __grid_co
             }
             continue;
         }
+        if (s2_is_producer(warp) && p.soff0 > 0) {
+            // ---------------- producer, bulk copies of a Halo-padded source (ring on axis 0: every neighbour is a parent cell) ------
+            // The cells the strip needs, logical [x0 - R, x0 + w + R), are parent columns shifted by the ring thickness; the copy
+            // is widened to 16-byte boundaries of the PARENT row and lands at LEFT + delta + ..., so that both addresses are
+            // 16-byte aligned although logical cell x0 is not (r01: this layout went through per-element cp.async at 0.73 of peak).
+            if (lane == 0 && (S2_PRODUCERS == 1 || warp == S2_WARPS)) {
+                const int es = (int)sizeof(T);
+                const int qlo = (x0b + (p.soff0 - R) * es) & ~15;
+                const int qhi = (x0b + wbytes + (p.soff0 + R) * es + 15) & ~15;
+                const unsigned mlen = qhi - qlo;
+                const int mdst = C::LEFT + p.delta + qlo - p.soff0 * es - x0b;
+                for (int c = 0; c < nchunks; c++, k++) {
+                    const int slot = k % C::STAGES;
+                    mbar_wait_producer(&empty[slot], ((k / C::STAGES) & 1) ^ 1);
+                    unsigned char* sbase = ring + slot * (CH * C::ROWB);
+                    unsigned bytes = 0;
+                    long long prow[CH];
+#pragma unroll
+                    for (int j = 0; j < CH; j++) {
+                        const int i = c * CH + j;
+                        prow[j] = i < nsrc ? s2_map_row(p, y0 - R + i) : -1;
+                        if (prow[j] >= 0) bytes += mlen;
+                    }
+                    mbar_arrive_expect_tx(&full[slot], bytes);
+#pragma unroll
+                    for (int j = 0; j < CH; j++) {
+                        if (prow[j] < 0) continue;
+                        const unsigned char* g = reinterpret_cast<const unsigned char*>(p.src + prow[j] * p.spitch);
+                        bulk_g2s(sbase + j * C::ROWB + mdst, g + qlo, mlen, &full[slot]);
+                    }
+                }
+            } else {
+                k += nchunks;
+            }
+            continue;
+        }
         if (s2_is_producer(warp)) {
             // ---------------- producer ----------------
             if (lane == 0 && (S2_PRODUCERS == 1 || warp == S2_WARPS)) {
@@ -376,7 +422,7 @@ __global__ void __launch_bounds__(S2_THREADS, 2) stream2d_kernel(const __grid_co
                 const unsigned rowbytes = mlen + (l_wrap ? wrap_bytes : 0) + (r_wrap ? wrap_bytes : 0);
                 for (int c = 0; c < nchunks; c++, k++) {
                     const int slot = k % C::STAGES;
-                    mbar_wait(&empty[slot], ((k / C::STAGES) & 1) ^ 1);
+                    mbar_wait_producer(&empty[slot], ((k / C::STAGES) & 1) ^ 1);
                     unsigned char* sbase = ring + slot * (CH * C::ROWB);
                     unsigned bytes = 0;
                     long long prow[CH];
@@ -428,7 +474,7 @@ __global__ void __launch_bounds__(S2_THREADS, 2) stream2d_kernel(const __grid_co
             const int slot = k % C::STAGES;
             mbar_wait(&full[slot], (k / C::STAGES) & 1);
             const unsigned char* sbase = ring + slot * (CH * C::ROWB);
-            S2Rows<T, SHAPE, R, RED, 0>::run(p, th, sbase, c * CH, acc, cen);
+            S2Rows<T, SHAPE, R, RED, 0, SH>::run(p, th, sbase, c * CH, acc, cen);
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[slot]);
         }
@@ -436,16 +482,16 @@ __global__ void __launch_bounds__(S2_THREADS, 2) stream2d_kernel(const __grid_co
 }
 
 // Launch one instantiation; returns SB200_OK or an error.
-template <typename T, int SHAPE, int R, int RED>
-int s2_launch(const S2Params<T>& p0, cudaStream_t st) {
+template <typename T, int SHAPE, int R, int RED, bool SH>
+int s2_launch_sh(const S2Params<T>& p0, cudaStream_t st) {
     using C = S2Cfg<T, R>;
     static thread_local int cfg_dev = -1, ctas_per_sm = 0;
     int dev = 0;
     SB_CUDA(cudaGetDevice(&dev));
     if (dev != cfg_dev) {
-        SB_CUDA(cudaFuncSetAttribute(stream2d_kernel<T, SHAPE, R, RED>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+        SB_CUDA(cudaFuncSetAttribute(stream2d_kernel<T, SHAPE, R, RED, SH>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
         int per_sm = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, stream2d_kernel<T, SHAPE, R, RED>, S2_THREADS, C::SMEM) != cudaSuccess || per_sm < 1)
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, stream2d_kernel<T, SHAPE, R, RED, SH>, S2_THREADS, C::SMEM) != cudaSuccess || per_sm < 1)
             per_sm = 1;
         ctas_per_sm = per_sm;
         cfg_dev = dev;
@@ -459,9 +505,14 @@ int s2_launch(const S2Params<T>& p0, cudaStream_t st) {
     nruns = std::min<long long>(nruns, std::max(1, p.rows / (4 * C::P)));  // keep the 2R re-read rows per run small
     p.nruns = (int)nruns;
     const long long grid = std::min<long long>(ctas, (long long)p.nstrips * p.nruns);
-    stream2d_kernel<T, SHAPE, R, RED><<<(unsigned)grid, S2_THREADS, C::SMEM, st>>>(p);
+    stream2d_kernel<T, SHAPE, R, RED, SH><<<(unsigned)grid, S2_THREADS, C::SMEM, st>>>(p);
     SB_LAUNCH_CHECK();
     return SB200_OK;
+}
+
+template <typename T, int SHAPE, int R, int RED>
+int s2_launch(const S2Params<T>& p, cudaStream_t st) {
+    return p.delta ? s2_launch_sh<T, SHAPE, R, RED, true>(p, st) : s2_launch_sh<T, SHAPE, R, RED, false>(p, st);
 }
 
 // Fill the parameters from a plan; false when the plan is outside what the streaming kernels accept.
@@ -470,7 +521,8 @@ template <typename T> bool s2_accepts(const Plan& pl, const void* src, void* dst
     if (d.ndim != 2 || pl.shape_tag < 0 || pl.shape_ndim != 2) return false;
     // bulk copies need an unpadded axis 0 and 16-byte aligned source rows; a Halo ring on axis 0 or unaligned rows take
     // the element-granular producer. The consumers' 128-bit stores need aligned dest rows either way.
-    const bool aligned = d.src_off[0] == 0 && (d.src_ext[0] * sizeof(T)) % 16 == 0 && ((uintptr_t)src & 15) == 0;
+    // (a Halo ring on axis 0 with 16-byte aligned parent rows also takes bulk copies: the shared-memory image is shifted by delta)
+    const bool aligned = (d.src_ext[0] * sizeof(T)) % 16 == 0 && ((uintptr_t)src & 15) == 0;
     if ((d.size[0] * sizeof(T)) % 16 || ((uintptr_t)src % sizeof(T))) return false;
     if ((d.dst_ext[0] * sizeof(T)) % 16 || (d.dst_off[0] * sizeof(T)) % 16 || ((uintptr_t)dst & 15)) return false;
     if (d.size[0] > (1LL << 28) || d.size[1] > (1LL << 30)) return false;
@@ -487,6 +539,7 @@ template <typename T> bool s2_accepts(const Plan& pl, const void* src, void* dst
     p.W = (int)d.size[0]; p.H = (int)d.size[1];
     p.soff0 = d.src_off[0]; p.soff1 = d.src_off[1]; p.doff0 = d.dst_off[0]; p.doff1 = d.dst_off[1];
     p.cpasync = aligned ? 0 : 1;
+    p.delta = aligned ? (int)((d.src_off[0] * sizeof(T)) % 16) : 0;
     p.bc0 = d.boundary[0]; p.bc1 = d.boundary[1];
     memcpy(&p.pad, &d.padval_bits, sizeof(T));
     p.y_lo = (int)pl.dd.lo[1]; p.rows = (int)pl.dd.n[1];

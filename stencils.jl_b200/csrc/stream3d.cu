@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(S3_THREADS) stream3d_kernel(const __grid_const
                 const int slot = k % S3_STAGES;
                 const long long zpl = s3_map(z0 - 1 + i, p.Z, p.so2, p.bc2);
                 if (lane == 0) {
-                    mbar_wait(&empty[slot], ((k / S3_STAGES) & 1) ^ 1);
+                    mbar_wait_producer(&empty[slot], ((k / S3_STAGES) & 1) ^ 1);
                     if (pw == 0) mbar_arrive_expect_tx(&full[slot], zpl >= 0 ? nrows * rowbytes : 0u);
                 }
                 __syncwarp();

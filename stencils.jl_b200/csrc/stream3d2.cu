@@ -266,7 +266,7 @@ __global__ void __launch_bounds__(D2_THREADS, 1) stream3d2_kernel(const __grid_c
                 bool zin = true;
                 if constexpr (PAD) zin = !(padz && (zl < 0 || zl >= p.Z));   // a plane outside the array is not copied
                 if (lane == 0) {
-                    mbar_wait(&empty[slot], ((k / D2_STAGES) & 1) ^ 1);
+                    mbar_wait_producer(&empty[slot], ((k / D2_STAGES) & 1) ^ 1);
                     if (pw == 0) mbar_arrive_expect_tx(&full[slot], zin ? nrows * rowbytes : 0u);
                 }
                 __syncwarp();

@@ -1,6 +1,9 @@
 // tma.cuh — mbarrier + bulk-copy (TMA engine) primitives for sm_100a, raw PTX.
-//   cp.async.bulk            -> SASS UBLKCP   (contiguous 1-D bulk copy global -> shared, completes on an mbarrier)
-//   cp.async.bulk.tensor.Nd  -> SASS UTMALDG  (tiled copy through a CUtensorMap, out-of-bounds elements zero-filled)
+//   cp.async.bulk            -> SASS UBLKCP   (contiguous 1-D bulk copy global -> shared on the TMA engine, completes on an mbarrier)
+// Tensor-map copies (cp.async.bulk.tensor, SASS UTMALDG) are deliberately not used: a box cannot wrap, zero fill only covers
+// Remove(0), box sides are capped at 256 elements (a 1 KiB + halo Float32 row needs two boxes) and the dense box layout would
+// drop the "global and shared addresses agree mod 128" placement every kernel relies on; whole-row bulk copies with
+// producer-side addressing cover every boundary with one code path and reach 0.92-0.97 of the HBM roofline.
 #pragma once
 #include <cstdint>
 
@@ -36,6 +39,28 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 
+// Producer-side wait for a free stage. A failed try_wait returns at once, so a producer whose consumers are the bottleneck
+// spins at one probe per ~10 ns and competes with them for issue slots (ncu r02e, box3d: SYNCS + YIELD + BRA of the two
+// producer warps were 17 % of all issued instructions); sleeping between probes costs nothing — the ring holds several
+// stages of slack. SB200_PRODUCER_BACKOFF_NS = 0 keeps the plain loop.
+#ifndef SB200_PRODUCER_BACKOFF_NS
+#define SB200_PRODUCER_BACKOFF_NS 0
+#endif
+__device__ __forceinline__ void mbar_wait_producer(uint64_t* bar, uint32_t parity, unsigned backoff_ns = SB200_PRODUCER_BACKOFF_NS) {
+    while (!mbar_try_wait(bar, parity)) {
+        if (backoff_ns) __nanosleep(backoff_ns);
+    }
+}
+
+// Predicated shared-memory load as ONE instruction (`@p LDS`): the end lanes of a warp fetch the cells next to its span
+// without a divergent branch (ptxas turns `if (lane == 0) x = *p;` into BSSY / BRA / BSYNC sequences).
+__device__ __forceinline__ void lds_if(float& v, const void* p, bool pred) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %2, 0;\n\t@q ld.shared.f32 %0, [%1];\n\t}" : "+f"(v) : "r"(smem_u32(p)), "r"((int)pred) : "memory");
+}
+__device__ __forceinline__ void lds_if(double& v, const void* p, bool pred) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %2, 0;\n\t@q ld.shared.f64 %0, [%1];\n\t}" : "+d"(v) : "r"(smem_u32(p)), "r"((int)pred) : "memory");
+}
+
 // Contiguous bulk copy global -> shared; bytes % 16 == 0, both addresses 16-byte aligned.
 __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
@@ -58,24 +83,6 @@ __device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-// Tiled copies through a tensor map (coordinates in elements, innermost first; OOB elements arrive as zero).
-__device__ __forceinline__ void tma_load_2d(void* dst_smem, const void* tmap, int c0, int c1, uint64_t* bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
-            smem_u32(dst_smem)),
-        "l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(bar))
-        : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(void* dst_smem, const void* tmap, int c0, int c1, int c2, uint64_t* bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
-            smem_u32(dst_smem)),
-        "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
-        : "memory");
-}
-__device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
-}
 // Order generic-proxy accesses to shared memory before subsequent async-proxy (TMA) accesses.
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 

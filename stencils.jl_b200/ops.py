@@ -176,7 +176,9 @@ def update_boundary_(A_: AbstractStencilArray, buf=None):
     if not isinstance(A_.padding, Halo) or isinstance(A_.boundary, Use):
         return A_
     par = A_.parent if buf is None else buf
-    h = _desc_for(sum, par, A_.halo, par, A_.halo, A_.stencil, A_.boundary)
+    # the halo refresh has no reducer and no dest: `minimum` keeps the element type for every eltype (sum(Bool) is Int64, which
+    # tripped the dest-eltype check for Bool parents: ADVICE r1)
+    h = _desc_for(minimum, par, A_.halo, par, A_.halo, A_.stencil, A_.boundary)
     if is_device(par):
         A.check(A.lib().sb200_update_halo(h.ptr(), data_ptr(par), _stream()))
     else:  # host parent: one round trip of the parent through the halo kernel
@@ -422,12 +424,19 @@ def scatterstencil_(f, op, dest_or_switching, src=None, flags=0):
     h = _desc_for(sum, source_arr.parent, source_arr.halo, dst, dst_halo, st, source_arr.boundary, flags=flags,
                   scatter=dict(weights=w, scatter_op=_OPS[op], scatter_rule=f.enum))
     l = A.lib()
+    refresh = source_arr.halo and not isinstance(source_arr.boundary, Use)   # update_boundary!(source), src/scatterstencil.jl:39
     if is_device(dst):
+        if refresh:
+            A.check(l.sb200_update_halo(h.ptr(), data_ptr(source_arr.parent), _stream()))
         A.check(l.sb200_scatter(h.ptr(), data_ptr(source_arr.parent), data_ptr(dst), _stream()))
     else:
         import torch
         ts = torch.from_numpy(np.ascontiguousarray(source_arr.parent.T)).cuda()
         td = torch.from_numpy(np.ascontiguousarray(dst.T)).cuda()
+        if refresh:
+            A.check(l.sb200_update_halo(h.ptr(), ts.data_ptr(), _stream()))
         A.check(l.sb200_scatter(h.ptr(), ts.data_ptr(), td.data_ptr(), _stream()))
         dst[...] = td.cpu().numpy().T
+        if refresh:
+            source_arr.parent[...] = ts.cpu().numpy().T   # the reference refreshes the caller's ring in place
     return dest_or_switching.switch() if switching else dst

@@ -157,6 +157,43 @@ def test_scatterstencil(goldens):
     assert res is not ssa and np.asarray(res)[2, 2] == pytest.approx(0.8)
 
 
+@pytest.mark.parametrize("dt", [np.bool_, np.uint8, np.int32, np.int64, np.float32, np.float64])
+def test_update_boundary_every_eltype_and_boundary(orc, dt):
+    """update_boundary_(A) (src/array.jl:195-239) through the host mirror for every element type (Bool parents used to trip the
+    dest-eltype check: ADVICE r1) x Remove / Wrap / Reflect, device and host parents, against the oracle's ring refresh; and
+    scatterstencil_ refreshing the source ring first, as the reference does (src/scatterstencil.jl:39)."""
+    from stencils_b200._desc import build_desc
+    rng = np.random.default_rng(31)
+    et = A.ELTYPE_OF_DTYPE[np.dtype(dt)]
+    inner = (rng.random((40, 24)) < 0.5) if dt == np.bool_ else (rng.random((40, 24)) * 50).astype(dt)
+    for bc, enum in ((sb.Remove(np.asarray(1, dtype=dt)[()]), A.REMOVE), (sb.Wrap(), A.WRAP), (sb.Reflect(), A.REFLECT)):
+        for R in (1, 2):
+            st = sb.Window(R)
+            for to_dev in (True, False):
+                sa = sb.StencilArray(dev(inner) if to_dev else np.asfortranarray(inner), st, boundary=bc, padding=sb.Halo("out"))
+                par0 = np.asfortranarray(host(sa.parent)).copy(order="F")
+                par0[:R, :] = 7 if dt != np.bool_ else True     # garbage in the ring: the refresh must overwrite all of it
+                par0[:, -R:] = 3 if dt != np.bool_ else False
+                if to_dev:
+                    sa.parent.copy_(dev(par0))
+                else:
+                    sa.parent[...] = par0
+                sb.update_boundary_(sa)
+                h = build_desc(size=inner.shape, eltype=et, out_eltype=et, offsets=st.offsets(), radius=R, boundary=enum,
+                               src_off=(R, R), dst_off=(R, R), padval=1, reducer=A.MIN)
+                want = orc.update_halo(h, par0.copy(order="F"))
+                bits_equal(np.asfortranarray(host(sa.parent)), want)
+    if np.dtype(dt).kind == "f":   # scatter over a Halo-padded source whose ring holds garbage: refreshed before the sweep
+        src = (rng.random((30, 20)) - 0.2).astype(dt)
+        sa = sb.StencilArray(dev(src), sb.Moore(1), boundary=sb.Wrap(), padding=sb.Halo("out"))
+        sa.parent[0, :] = 99.0
+        d = sb.scatterstencil_(sb.ScatterCenterWeights(np.asarray(0.5, dtype=dt)[()]), operator.add, dev(np.zeros((30, 20), dtype=dt)), sa)
+        ref = sb.scatterstencil_(sb.ScatterCenterWeights(np.asarray(0.5, dtype=dt)[()]), operator.add, dev(np.zeros((30, 20), dtype=dt)),
+                                 sb.StencilArray(dev(src), sb.Moore(1), boundary=sb.Wrap()))
+        bits_equal(host(d), host(ref))
+        assert float(host(sa.parent)[0, 5]) != 99.0
+
+
 def test_unsupported_function_raises_on_gpu_box_too():
     a = sb.StencilArray(dev(np.zeros((8, 8))), sb.Window(1))
     with pytest.raises(sb.ArgumentError, match="no fallback"):

@@ -757,3 +757,50 @@ def test_life_eight_generations_per_launch(orc, monkeypatch):
             sync()
             bits_equal(to_host(ta if n % 2 == 0 else tb, g.shape, g.dtype), want_n)
         monkeypatch.delenv("SB200_OCT_STEP")
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+def test_kernelproduct_allow_fma(orc, dt):
+    """SB200_FLAG_ALLOW_FMA: acc = fma(v_k, w_k, acc) instead of the reference's separately rounded multiply and add
+    (src/stencils/kernel.jl:37-43). Not bit-exact by construction, and NOT inside the 2-ulp tolerance of BASELINE.json's north
+    star either (r02e: 4 ulp on a 3 x 3 Float32 kernel, two differently rounded 9-term chains), which is why it is opt-in and the
+    default stays the bit-exact fold. Measured here against the oracle: (a) the BASELINE config's kind of data (uniform [0, 1)
+    field, weights normalised to sum 1): a few ulp, asserted <= 16 and printed; (b) adversarial cancelling weights: the error is bounded by the usual
+    dot-product bound L * eps * sum |v_k w_k| (ulps of a cancelled result are meaningless); (c) shapes without a contracted
+    kernel ignore the flag and stay bit-exact; (d) without the flag the same kernel family is bit-exact."""
+    from tests.util import max_ulp
+    rng = np.random.default_rng(97)
+    l = A.lib()
+    et = A.ELTYPE_OF_DTYPE[np.dtype(dt)]
+    eps = np.finfo(dt).eps
+    es = np.dtype(dt).itemsize
+    shape = (8192 // es + 256, 300)
+    g = np.asfortranarray(rng.random(shape).astype(dt))
+    worst = {}
+    for R in (1, 2, 3):
+        offs = npr.offsets("Window", R, 2)
+        w = rng.random(len(offs)).astype(dt)
+        w = (w / w.sum(dtype=dt)).astype(dt)
+        kw = dict(size=shape, eltype=et, out_eltype=et, offsets=offs, radius=R, boundary=A.REMOVE, reducer=A.KERNELDOT, padval=0.0)
+        want = orc.gather(build_desc(weights=w, **kw), g, dst_like(build_desc(weights=w, **kw)))
+        got, _ = gpu_gather(build_desc(weights=w, flags=A.FLAG_ALLOW_FMA, **kw), g, dst_like(build_desc(weights=w, **kw)))
+        assert l.sb200_last_kernel() == b"stream2d_kernel<fma>"
+        worst[R] = max_ulp(got, want)
+        assert worst[R] <= 16, worst
+        exact, _ = gpu_gather(build_desc(weights=w, **kw), g, dst_like(build_desc(weights=w, **kw)))
+        assert l.sb200_last_kernel() == b"stream2d_kernel"
+        bits_equal(exact, want)
+        # adversarial: alternating signs, sums cancel to ~0
+        wa = (w * np.where(np.arange(len(offs)) % 2 == 0, 1, -1)).astype(dt)
+        want_a = orc.gather(build_desc(weights=wa, **kw), g, dst_like(build_desc(weights=wa, **kw)))
+        got_a, _ = gpu_gather(build_desc(weights=wa, flags=A.FLAG_ALLOW_FMA, **kw), g, dst_like(build_desc(weights=wa, **kw)))
+        bound = len(offs) * eps * float(np.abs(wa).sum())   # |v| < 1
+        assert float(np.abs(got_a.astype(np.float64) - want_a.astype(np.float64)).max()) <= bound
+    print(f"kernelproduct with FMA, max ulp vs oracle on uniform data ({np.dtype(dt).name}): {worst}")
+    # a shape without a contracted kernel: the flag is a permission, the result stays bit-exact
+    offs = npr.offsets("Moore", 1, 2)
+    w = rng.random(len(offs)).astype(dt)
+    kw = dict(size=shape, eltype=et, out_eltype=et, offsets=offs, radius=1, boundary=A.WRAP, reducer=A.KERNELDOT, weights=w)
+    want = orc.gather(build_desc(**kw), g, dst_like(build_desc(**kw)))
+    got, _ = gpu_gather(build_desc(flags=A.FLAG_ALLOW_FMA, **kw), g, dst_like(build_desc(**kw)))
+    bits_equal(got, want)
