@@ -31,6 +31,14 @@ constexpr int B3_TXB = B3_WX * 512;             // tile width in bytes
 #ifndef SB200_B3_RT
 #define SB200_B3_RT 4
 #endif
+#ifndef SB200_B3_BACKOFF_NS
+#define SB200_B3_BACKOFF_NS 0      // producer back-off while the ring is full: measured r02g, 0 / 1000 / 4000 ns all 556-558 Gcell/s
+#endif
+#ifndef SB200_B3_PACKED
+#define SB200_B3_PACKED 0          // Float32 sums with packed add.rn.f32x2 (two cells per issue slot). Measured r02h, Window(1,3) mean
+                                   // 768^3: scalar 571 Gcell/s, packed 504 — assembling the (x-1, x) / (x+1, x+2) operand pairs costs more
+                                   // moves than the 208 saved FADD issue slots (stream3d2's pairs are register-aligned, these are not)
+#endif
 constexpr int B3_RT = SB200_B3_RT;              // rows per thread
 constexpr int B3_TY = B3_WY * B3_RT;            // tile height in rows
 constexpr int B3_LEFT = 128;                    // margin (halo at its end): global and shared addresses agree mod 128
@@ -83,6 +91,18 @@ __device__ __forceinline__ T b3_fold9(T acc, const T (&rowv)[NR][VX], const T (&
     return acc;
 }
 
+// Packed Float32 adds (SASS FADD2): each lane rounds like the scalar add, so the folds stay bit-exact.
+__device__ __forceinline__ unsigned long long b3_pk(float lo, float hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void b3_upk(unsigned long long v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ unsigned long long b3_add2(unsigned long long a, unsigned long long b) {
+    unsigned long long r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
 // MOORE: centre excluded. RED: SB200_SUM / SB200_MEAN / SB200_MAX / SB200_MIN. PAD: some axis is Remove (out-of-bounds rows /
 // planes / columns read padval); the other instantiation carries no padval code at all.
 template <typename T, bool MOORE, int RED, bool PAD>
@@ -136,7 +156,7 @@ __global__ void __launch_bounds__(B3_THREADS, 2) box3d_kernel(const __grid_const
                 const int slot = k % B3_STAGES;
                 const long long zpl = b3_map(z0 - 1 + i, p.Z, p.so2, p.bc2);
                 if (lane == 0) {
-                    mbar_wait_producer(&empty[slot], ((k / B3_STAGES) & 1) ^ 1, 200);
+                    mbar_wait_producer(&empty[slot], ((k / B3_STAGES) & 1) ^ 1, SB200_B3_BACKOFF_NS);
                     if (pw == 0) mbar_arrive_expect_tx(&full[slot], zpl >= 0 ? nrows * rowbytes : 0u);
                 }
                 __syncwarp();
@@ -167,6 +187,9 @@ __global__ void __launch_bounds__(B3_THREADS, 2) box3d_kernel(const __grid_const
         for (int r = 0; r < B3_RT; r++)
 #pragma unroll
             for (int v = 0; v < VX; v++) { a1[r][v] = T(0); a2[r][v] = T(0); if constexpr (MOORE && EXT) a3[r][v] = T(0); }
+        unsigned long long a1p[B3_RT][2], a2p[B3_RT][2];   // the same two chains as packed cell pairs (Float32 sums)
+#pragma unroll
+        for (int r = 0; r < B3_RT; r++) { a1p[r][0] = a1p[r][1] = 0ull; a2p[r][0] = a2p[r][1] = 0ull; }
         T* __restrict__ dbase = p.dst + (long long)(y0 + ry0 + p.do1) * p.dp1 + p.do0 + gx;
         for (int i = 0; i < nsrc; i++, k++) {
             const int slot = k % B3_STAGES;
@@ -239,6 +262,55 @@ __global__ void __launch_bounds__(B3_THREADS, 2) box3d_kernel(const __grid_const
                         T* d = dbase + (long long)(zo + p.do2) * p.dp2 + (long long)r * p.dp1;
                         if constexpr (VX == 4) *reinterpret_cast<float4*>(d) = make_float4(out[0], out[1], out[2], out[3]);
                         else *reinterpret_cast<double2*>(d) = make_double2(out[0], out[1]);
+                    }
+                }
+            } else if constexpr (SB200_B3_PACKED && sizeof(T) == 4) {
+                constexpr int L = MOORE ? 26 : 27;
+                // Window rows are streamed: row w is turned into its cell pairs (0,1) / (2,3) — left neighbours, centres, right
+                // neighbours — and folded at once into every chain that uses it (output rows w, w-1, w-2 x the three time levels),
+                // so only one row of pairs is live at a time. Every chain still sees its taps in offset order.
+                unsigned long long fin[B3_RT][2], n2[B3_RT][2], n1[B3_RT][2];
+#pragma unroll
+                for (int r = 0; r < B3_RT; r++)
+#pragma unroll
+                    for (int h = 0; h < 2; h++) { fin[r][h] = a2p[r][h]; n2[r][h] = a1p[r][h]; n1[r][h] = 0ull; }
+#pragma unroll
+                for (int w = 0; w < NR; w++) {
+                    const unsigned long long mid = b3_pk(rowv[w][1], rowv[w][2]);
+                    const unsigned long long pm[2] = {b3_pk(xl[w], rowv[w][0]), mid};
+                    const unsigned long long pc[2] = {b3_pk(rowv[w][0], rowv[w][1]), b3_pk(rowv[w][2], rowv[w][3])};
+                    const unsigned long long pq[2] = {mid, b3_pk(rowv[w][3], xr[w])};
+#pragma unroll
+                    for (int dy = 0; dy < 3; dy++) {
+                        const int r = w - dy;
+                        if (r < 0 || r >= B3_RT) continue;
+#pragma unroll
+                        for (int h = 0; h < 2; h++) {
+                            fin[r][h] = b3_add2(b3_add2(b3_add2(fin[r][h], pm[h]), pc[h]), pq[h]);           // plane z+1 of output z-1
+                            unsigned long long b = b3_add2(n2[r][h], pm[h]);                                  // plane z of output z
+                            if (!(MOORE && dy == 1)) b = b3_add2(b, pc[h]);
+                            n2[r][h] = b3_add2(b, pq[h]);
+                            const unsigned long long c = dy == 0 ? pm[h] : b3_add2(n1[r][h], pm[h]);        // plane z-1 of output z+1
+                            n1[r][h] = b3_add2(b3_add2(c, pc[h]), pq[h]);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int r = 0; r < B3_RT; r++) {
+                    float out[4];
+#pragma unroll
+                    for (int h = 0; h < 2; h++) {
+                        float f0, f1;
+                        b3_upk(fin[r][h], f0, f1);
+                        out[2 * h] = RED == SB200_MEAN ? div_rn(f0, (float)L) : f0;
+                        out[2 * h + 1] = RED == SB200_MEAN ? div_rn(f1, (float)L) : f1;
+                        a2p[r][h] = n2[r][h];
+                        a1p[r][h] = n1[r][h];
+                    }
+                    const int y = y0 + ry0 + r;
+                    if (store && xact && y < p.Y && ry0 + r < p.ty) {
+                        T* d = dbase + (long long)(zo + p.do2) * p.dp2 + (long long)r * p.dp1;
+                        *reinterpret_cast<float4*>(d) = make_float4(out[0], out[1], out[2], out[3]);
                     }
                 }
             } else {

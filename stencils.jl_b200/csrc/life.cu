@@ -626,18 +626,30 @@ __device__ __forceinline__ unsigned lop3_maj(unsigned a, unsigned b, unsigned c)
     asm("lop3.b32 %0, %1, %2, %3, 0xE8;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
     return r;
 }
-__device__ __forceinline__ BRow brow(unsigned w, unsigned lbit, unsigned rbit) {
-    const unsigned L = (w << 1) | lbit, R = (w >> 1) | (rbit << 31);
+// `prev` / `next` = the words of the 32 cells to the left / right (only their top / bottom bit is used): the one-bit shifts with
+// the neighbour's edge bit shifted in are single funnel shifts (SHF.L.W / SHF.R.W on two registers)
+__device__ __forceinline__ BRow brow(unsigned w, unsigned prev, unsigned next) {
+    const unsigned L = __funnelshift_l(prev, w, 1), R = __funnelshift_r(w, next, 1);
     return BRow{w, lop3_xor3(L, w, R), lop3_maj(L, w, R)};
 }
 // B3/S23 from the rows above, at and below: T = 3x3 total including the centre; alive' = (T == 3) | (centre & T == 4)
+// T = t0 + 2 (u1 + c0) + 4 c1 with t0 / c0 = sum / carry of the three low bit planes and u1 / c1 of the three high ones, so
+//   T == 3  <=>  t0 & (u1 ^ c0) & ~c1          (bit 1 set without a carry into bit 2, no c1)
+//   T == 4  <=>  ~t0 & ~(u1 ^ c0) & (u1 ^ c1)  (u1 == c0: bit 1 clear, carry = u1; exactly one of carry and c1)
+// nine 3-input logic ops instead of the twelve of the ripple form (t1, k1, t2, t3, x, y, ...): the kernel is bound by the ALU pipe.
+// tests/test_kernel_models.py checks the identity over every input combination.
+template <int IMM> __device__ __forceinline__ unsigned lop3_imm(unsigned a, unsigned b, unsigned c) {
+    unsigned r;
+    asm("lop3.b32 %0, %1, %2, %3, %4;" : "=r"(r) : "r"(a), "r"(b), "r"(c), "n"(IMM));
+    return r;
+}
 __device__ __forceinline__ unsigned conway_bits(const BRow& a, const BRow& b, const BRow& n) {
     const unsigned t0 = lop3_xor3(a.s0, b.s0, n.s0), c0 = lop3_maj(a.s0, b.s0, n.s0);
     const unsigned u1 = lop3_xor3(a.s1, b.s1, n.s1), c1 = lop3_maj(a.s1, b.s1, n.s1);
-    const unsigned t1 = u1 ^ c0, k1 = u1 & c0;
-    const unsigned t2 = c1 ^ k1, t3 = c1 & k1;
-    const unsigned x = ~t2 & t1 & t0, y = t2 & ~t1 & ~t0;
-    return (x | (y & b.c)) & ~t3;
+    const unsigned p3 = lop3_imm<0x60>(t0, u1, c0);            // t0 & (u1 ^ c0)
+    const unsigned q4 = lop3_imm<0x09>(t0, u1, c0);            // ~t0 & ~(u1 ^ c0)
+    const unsigned y4 = lop3_imm<0x60>(q4, u1, c1) & b.c;      // T == 4 and the centre is alive
+    return lop3_imm<0xBA>(p3, c1, y4);                         // (p3 & ~c1) | y4
 }
 template <bool CELLS01> __device__ __forceinline__ unsigned pack32(const uint4& lo, const uint4& hi) {
     unsigned w[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
@@ -736,16 +748,16 @@ __global__ void __launch_bounds__((LB_WARPS + 1) * 32, 3) life_bit_kernel(const 
                     const uint4 lo = *reinterpret_cast<const uint4*>(t), hi = *reinterpret_cast<const uint4*>(t + 16);
                     const unsigned w = pack32<CELLS01>(lo, hi);
                     // edge bits from the adjacent lanes' packed words; only the warp's end lanes read a halo byte
-                    unsigned lb = __shfl_up_sync(0xffffffffu, w, 1) >> 31, rb = __shfl_down_sync(0xffffffffu, w, 1) & 1u;
-                    if (lane == 0) lb = t[-1] != 0;
-                    if (lane == 31) rb = t[32] != 0;
-                    lv[0][J] = brow(w, lb, rb);
+                    unsigned prev = __shfl_up_sync(0xffffffffu, w, 1), next = __shfl_down_sync(0xffffffffu, w, 1);
+                    if (lane == 0) prev = t[-1] != 0 ? 0x80000000u : 0u;
+                    if (lane == 31) next = t[32] != 0;
+                    lv[0][J] = brow(w, prev, next);
                 }
 #pragma unroll
                 for (int g = 1; g < G; g++) {  // generation g of row i - g from generation g-1 of rows i-g-1, i-g, i-g+1
                     const unsigned x = conway_bits(lv[g - 1][(J - g - 1 + 9) % 3], lv[g - 1][(J - g + 9) % 3], lv[g - 1][(J - g + 1 + 9) % 3]);
-                    const unsigned lb = __shfl_up_sync(0xffffffffu, x, 1) >> 31, rb = __shfl_down_sync(0xffffffffu, x, 1) & 1u;
-                    lv[g][(J - g + 9) % 3] = brow(x, lb, rb);
+                    const unsigned prev = __shfl_up_sync(0xffffffffu, x, 1), next = __shfl_down_sync(0xffffffffu, x, 1);
+                    lv[g][(J - g + 9) % 3] = brow(x, prev, next);
                 }
                 if (i >= 2 * G && i < nsrc) {   // generation G of row i - G: the output row y0 + i - 2G
                     const unsigned y = conway_bits(lv[G - 1][(J - G - 1 + 9) % 3], lv[G - 1][(J - G + 9) % 3], lv[G - 1][(J - G + 1 + 9) % 3]);
