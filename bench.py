@@ -346,10 +346,10 @@ def slab_case(workload):
     from stencils_b200 import _abi as A
     from stencils_b200.stencils import Moore, VonNeumann
     if workload == "life":
-        return dict(st=Moore(1), reducer=A.LIFE, kw=dict(born_mask=1 << 3, survive_mask=0b1100), eltype=A.U8, R=1, ghost=32,
-                    bcs=(A.WRAP, A.WRAP))
+        return dict(st=Moore(1), reducer=A.LIFE, kw=dict(born_mask=1 << 3, survive_mask=0b1100), eltype=A.U8, R=1, ghost=0,
+                    bcs=(A.WRAP, A.WRAP))   # ghost = 0: the library's default (128 rows for slabs of >= 1024 rows)
     if workload == "diffusion":
-        return dict(st=VonNeumann(1, 3), reducer=A.DIFFUSION, kw=dict(alpha=0.1), eltype=A.F32, R=1, ghost=4, bcs=(A.WRAP, A.WRAP, A.WRAP))
+        return dict(st=VonNeumann(1, 3), reducer=A.DIFFUSION, kw=dict(alpha=0.1), eltype=A.F32, R=1, ghost=0, bcs=(A.WRAP, A.WRAP, A.WRAP))
     raise SystemExit(f"workload {workload} is not an iterated (slab-partitioned) configuration")
 
 
@@ -389,7 +389,9 @@ def bench_slabs(torch, dist, workload, spec, steps, warmup, strong, min_reps=10,
         A.check(lib.sb200_stream_sync(None))
         del field
         plan.mark_dirty()
-        k = c["ghost"] // c["R"]
+        st_ = plan.stats()
+        c["ghost"] = st_["ghost_planes"]            # what the library chose when asked for its default
+        k = st_["generations_per_exchange"]
         steps_timed = max(-(-steps // k) * k, 4 * k)
         plan.iterate(max(warmup, k))
         plan.sync()

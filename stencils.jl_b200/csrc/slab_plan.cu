@@ -236,7 +236,14 @@ static int plan_common_init(sb200_plan* p, const sb200_desc* g, int ghost, int p
     p->ndim = g->ndim;
     p->R = std::max(1, (int)g->radius);
     int G = ghost;
-    if (G <= 0) G = g->reducer == SB200_LIFE ? 32 * p->R : (g->reducer == SB200_DIFFUSION ? 4 * p->R : p->R);
+    // Library defaults (measured on 2 GPUs, r02i): Life 128 ghost rows — an exchange costs ~26 us whatever its size, the rows a
+    // wide halo recomputes are 0.8 % of a 16384-row slab; diffusion 4 planes (two double sweeps per cycle; 8 measured the same).
+    if (G <= 0) {
+        const long long n_est = g->size[g->ndim - 1] / nslabs_total;
+        G = g->reducer == SB200_LIFE ? (n_est >= 1024 ? 128 : 32) * p->R : (g->reducer == SB200_DIFFUSION ? 4 * p->R : p->R);
+        while (G > p->R && G > n_est) G /= 2;
+        G = std::max(p->R, G / p->R * p->R);
+    }
     if (G < p->R || G % p->R) { set_error("ghost thickness must be a positive multiple of the radius"); return SB200_EINVAL; }
     p->G = G;
     p->k = G / p->R;
@@ -246,7 +253,10 @@ static int plan_common_init(sb200_plan* p, const sb200_desc* g, int ghost, int p
     const long long n_min = g->size[last] / nslabs_total;
     if (n_min < G) { set_error("slab of %lld planes is thinner than the ghost zone (%d)", n_min, G); return SB200_ESIZE; }
     p->later_flags = (g->reducer == SB200_LIFE && g->eltype == SB200_U8) ? SB200_FLAG_CELLS_01 : 0;
-    p->overlap = (plan_flags & SB200_PLAN_OVERLAP_ON) ? true : (plan_flags & SB200_PLAN_OVERLAP_OFF) ? false : (p->plane_bytes * (size_t)G >= ((size_t)1 << 20));
+    // Overlap (boundary sweeps first, exchange under the interior sweep) pays for the 3-D planes (ghost zones of MiBs); for 2-D
+    // rows three thin multi-generation launches cost more than the exchange they hide (r02i: Life G = 64 0.923 with, G = 32 0.961 without)
+    p->overlap = (plan_flags & SB200_PLAN_OVERLAP_ON) ? true : (plan_flags & SB200_PLAN_OVERLAP_OFF) ? false
+                 : (g->ndim == 3 && p->plane_bytes * (size_t)G >= ((size_t)1 << 20));
     p->fused_xfer = p->plane_bytes % 16 == 0 && !(getenv("SB200_PLAN_FUSED_XFER") && atoi(getenv("SB200_PLAN_FUSED_XFER")) == 0);
     if (const char* e = getenv("SB200_WAIT_TIMEOUT_MS")) p->timeout_ns = (unsigned long long)std::max(1, atoi(e)) * 1000000ull;
     return SB200_OK;

@@ -212,9 +212,10 @@ __device__ __forceinline__ void d2_plane<float, 4>(float (&done)[4], float (&cpr
 // source cells AND out-of-bounds cells of the intermediate state read padval (Remove boundary: the second sweep sees
 // padval outside the array, not an update of it). Rows / planes / edge halos outside the array are not copied; the values
 // are substituted by selects. PAD = false is the measured Wrap kernel, its code is untouched (if constexpr).
-// MIRROR = true: EXPERIMENT (not yet run on a GPU; SB200_D2_MIRROR=1): the planes a neighbour GPU needs are also stored into
-// its landing slot by the sweep itself (sb200_desc.mirror_*), like stream3d_kernel's MIRROR variant; without it do_gather copies
-// them after the sweep (r01m: 0.954 weak-scaling efficiency at 2 GPUs against 0.999 for the single-step kernel with fused stores).
+// MIRROR = true (default for boundary sweeps of slab runs since r02i; SB200_D2_MIRROR=0 falls back to the copy): the planes a
+// neighbour GPU needs are also stored into its landing slot by the sweep itself (sb200_desc.mirror_*), like stream3d_kernel's
+// MIRROR variant; without it do_gather copies them after the sweep. Bit-exact on 2 GPUs (r02d); 2 x 1024^3 weak scaling 0.980
+// with, 0.973 without (r02i; round 1 measured 0.954 with the copy and the slower exchange of the Python iterator).
 template <typename T, bool PAD, bool MIRROR>
 __global__ void __launch_bounds__(D2_THREADS, 1) stream3d2_kernel(const __grid_constant__ D2Params<T> p) {
     constexpr int VX = 16 / (int)sizeof(T);
@@ -507,7 +508,8 @@ template <typename T> static int d2_try(const Plan& pl, const void* src, void* d
     const bool z_remove = d.boundary[2] == SB200_REMOVE && !(lo >= 2 && hi + 2 <= d.size[2]);
     p.mirror = nullptr; p.m_lo = p.m_hi = 0;
     if (d.boundary[0] == SB200_REMOVE || d.boundary[1] == SB200_REMOVE || z_remove) return d2_launch<T, true, false>(p, st);
-    if (g_mirror.ptr && getenv("SB200_D2_MIRROR")) {   // experiment: fused ghost-plane push (Wrap kernel only)
+    static const bool mirror_ok = !(getenv("SB200_D2_MIRROR") && atoi(getenv("SB200_D2_MIRROR")) == 0);
+    if (g_mirror.ptr && mirror_ok) {   // fused ghost-plane push (Wrap kernel; bit-exact on 2 GPUs r02d, +0.7 % at N = 2 r02i)
         p.mirror = (T*)g_mirror.ptr; p.m_lo = (int)g_mirror.lo; p.m_hi = (int)g_mirror.hi;
         g_mirror.honoured = true;
         return d2_launch<T, false, true>(p, st);
