@@ -242,7 +242,7 @@ def time_reps(torch, run, steps, warmup, min_reps=10, min_total_ms=50.0, max_rep
     e0, e1 = one()   # pilot repetition (untimed): sizes R
     torch.cuda.synchronize()
     pilot = max(e0.elapsed_time(e1), 1e-3)
-    reps = int(min(max_reps, max(min_reps, -(-min_total_ms // pilot))))
+    reps = int(min(max_reps, max(min_reps, -(-1.3 * min_total_ms // pilot))))   # 1.3: the pilot repetition runs cold
     evs = [one() for _ in range(reps)]
     torch.cuda.synchronize()
     return [a.elapsed_time(b) for a, b in evs]
@@ -377,8 +377,13 @@ def bench_slabs(torch, dist, workload, spec, steps, warmup, strong, min_reps=10,
     cells_local = int(np.prod(local))
     exchange = os.environ.get("SB200_EXCHANGE", "auto")
     pflags = {"1": A.PLAN_OVERLAP_ON, "0": A.PLAN_OVERLAP_OFF}.get(os.environ.get("SB200_OVERLAP", ""), 0)
-    plan = SlabPlan(gshape, offsets=c["st"].offsets(), radius=c["R"], reducer=c["reducer"], boundary=c["bcs"], eltype=c["eltype"],
-                    ghost=c["ghost"], rank=rank, world=world, reducer_kwargs=c["kw"], plan_flags=pflags)
+    try:
+        if exchange == "nccl":
+            raise A.SB200Error(A.ECUDA, "SB200_EXCHANGE=nccl: the NCCL fallback was requested")
+        plan = SlabPlan(gshape, offsets=c["st"].offsets(), radius=c["R"], reducer=c["reducer"], boundary=c["bcs"], eltype=c["eltype"],
+                        ghost=c["ghost"], rank=rank, world=world, reducer_kwargs=c["kw"], plan_flags=pflags)
+    except A.SB200Error as ex:   # raised on every rank together (the constructor votes): CUDA IPC is not available between the ranks
+        return bench_slabs_nccl(torch, dist, workload, spec, c, local, gshape, steps, warmup, strong, min_reps, min_total_ms, repr(ex))
     try:
         lo, hi, _, ptr = plan.slab(0)
         assert hi - lo == local[-1]
@@ -431,6 +436,61 @@ def bench_slabs(torch, dist, workload, spec, steps, warmup, strong, min_reps=10,
             "grid_per_gpu": list(local), "global_grid": list(gshape), "scaling": "strong" if strong else "weak",
             "cells_total": cells_local * world, "api": "sb200_plan_create_rank / sb200_plan_connect / sb200_plan_iterate_timed (C ABI)",
             "exchange_requested": exchange}
+
+
+def bench_slabs_nccl(torch, dist, workload, spec, c, local, gshape, steps, warmup, strong, min_reps, min_total_ms, why):
+    """Fallback when the ranks cannot open each other's memory (no CUDA IPC): the round-1 Python slab iterator with NCCL
+    send / recv for the ghost planes (stencils_b200.slab.SlabIterator). Same rounding of the timed step count to whole exchange
+    cycles; the line carries `warning` so that the fallback is visible."""
+    from stencils_b200 import _abi as A
+    from stencils_b200.slab import SlabIterator
+    from stencils_b200.synth import synth_torch
+    rank, world = dist.get_rank(), dist.get_world_size()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    cells_local = int(np.prod(local))
+    lo = rank * local[-1]
+    field = synth_torch(local, spec["dtype"], spec["seed"], dev, lo=lo * int(np.prod(local[:-1])))
+    t = field.permute(*reversed(range(len(local)))).contiguous()
+    del field
+    ghost = c["ghost"] or (32 if workload == "life" else 4)
+    it = SlabIterator(t, offsets=c["st"].offsets(), radius=c["R"], reducer=c["reducer"], boundary=c["bcs"], eltype=c["eltype"], ghost=ghost,
+                      rank=rank, world=world, reducer_kwargs=c["kw"], exchange="nccl")
+    del t
+    lib = A.lib()
+    k = ghost // c["R"]
+    steps_timed = max(-(-steps // k) * k, 4 * k)
+    it.step(max(warmup, k))
+    torch.cuda.synchronize()
+
+    def one():
+        dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        it.step(steps_timed)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1)
+    pilot = torch.tensor([one()], device=dev, dtype=torch.float64)
+    dist.all_reduce(pilot, op=dist.ReduceOp.MAX)
+    reps = int(min(200, max(min_reps, -(-min_total_ms // max(float(pilot.item()), 1e-3)))))
+    lib.sb200_launch_count(1)
+    times = [one() for _ in range(reps)]
+    launches = lib.sb200_launch_count(1)
+    tt = torch.tensor(times, device=dev, dtype=torch.float64)
+    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    times = [float(v) for v in tt.tolist()]
+    kernel = lib.sb200_last_kernel().decode()
+    dist.barrier()
+    it.close()
+    med = float(np.median(times))
+    return {"value": cells_local * world * steps_timed / (med * 1e-3) / 1e9, "unit": "Gcell-updates/s", "ms_per_step": med / steps_timed,
+            "steps_timed": steps_timed, "exchanges_in_timed_region": steps_timed / k, "steps_per_exchange": k, "ghost_planes": ghost,
+            "generations_per_launch_max": None, "launches": int(launches), "launches_per_rep": launches / reps,
+            "timing": rep_stats(times, steps_timed), "kernel": kernel, "sync": "nccl",
+            "exchange": "NCCL send / recv of the ghost planes (fallback: CUDA IPC peer access is not available between the ranks)",
+            "grid_per_gpu": list(local), "global_grid": list(gshape), "scaling": "strong" if strong else "weak",
+            "cells_total": cells_local * world, "api": "stencils_b200.slab.SlabIterator over sb200_gather (Python orchestration, NCCL exchange)",
+            "exchange_requested": os.environ.get("SB200_EXCHANGE", "auto"), "warning": "peer-memory exchange unavailable, NCCL fallback: " + why}
 
 
 # ------------------------------------------------------------------------------------------------ main
@@ -506,6 +566,8 @@ def main():
         steps_timed, launches, timing = res["steps_timed"], res["launches"], res["timing"]
         cells_total = res["cells_total"]
         extra_cfg = {k: res[k] for k in ("ghost_planes", "steps_per_exchange", "exchange", "sync", "global_grid", "api")}
+        if res.get("warning"):
+            warnings.append(res["warning"])
         sweeps_per_launch = steps_timed / max(res["launches_per_rep"], 1)
     else:
         st, run, cells_total = make_sweep(args.workload, spec, torch, sb)

@@ -33,7 +33,12 @@ UNIT_SCALE = {"Mbyte": 1.0, "Gbyte": 1e3, "Kbyte": 1e-3, "byte": 1e-6, "us": 1.0
 
 
 def read(rep):
-    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    """rep: a .ncu-rep capture, or the `ncu -i ... --page raw --csv` export of one (made on the GPU box when the captures
+    themselves are too large to bring back)."""
+    if rep.endswith(".csv"):
+        out = open(rep).read()
+    else:
+        out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     hdr, units = rows[0], rows[1]
     res = []
@@ -57,6 +62,8 @@ def main():
     summary = {}
     for wl in ("life", "mean", "mean_halo", "kernel", "kernel_fma", "circle", "positional", "scatter", "window3d", "diffusion", "diffusion2"):
         rep = os.path.join(out_dir, f"{rnd}_{wl}.ncu-rep")
+        if not os.path.exists(rep):
+            rep = os.path.join(out_dir, f"{rnd}_{wl}_raw.csv")
         if not os.path.exists(rep):
             continue
         ks = read(rep)

@@ -21,6 +21,12 @@
 
 namespace sb {
 
+#ifndef SB200_S2_VEC_HALO
+#define SB200_S2_VEC_HALO 0    // A/B switch (r02k): halo cells by aligned 128-bit loads
+#endif
+#ifndef SB200_S2_EDGE_WARP
+#define SB200_S2_EDGE_WARP 1   // Remove padval selects only in the warps that touch the array edge (r02j: Circle(4) max 620 -> 660, 7x7 246 -> 263 Gcell/s)
+#endif
 constexpr int S2_WARPS = 8;
 // kernelproduct with the multiply-add contracted into one FMA (SB200_FLAG_ALLOW_FMA): a reducer code of its own for the templates
 constexpr int S2_KDOT_FMA = 100;
@@ -155,6 +161,7 @@ template <typename T> struct S2Thread {
     int gx;         // global column of the thread's first cell
     int y0, nout;   // first output row of the run, number of output rows
     bool active, edge_l, edge_r, may_pad;
+    bool edge_warp; // Remove on axis 0: some lane of this warp has out-of-bounds halo cells (warp-uniform)
     int nl, rlim;   // Remove on axis 0: halo cells e < nl (left) and e >= rlim (right) of the segment are out of bounds
     T* dt;          // dest pointer of (row y0, column gx)
 };
@@ -188,23 +195,38 @@ __device__ __forceinline__ void s2_row(const S2Params<T>& p, const S2Thread<T>& 
         for (int e = 0; e < SEG; e++) seg[e] = p.pad;
     } else {
         const unsigned char* t = sbase + J * C::ROWB + C::LEFT + (SH ? p.delta : 0) + th.xtb;
-        if constexpr (!SH) {
+        constexpr bool VEC_HALO = SB200_S2_VEC_HALO && !SH && R >= 2;   // R = 1: one vector + two scalars is as cheap
+        if constexpr (VEC_HALO) {
+            // the halo cells as whole 16-byte vectors of the neighbouring lanes' cells: 2 HLB/16 + 1 aligned 128-bit loads instead of
+            // one plus 2R scalar loads (a scalar load at a 16-byte lane stride costs as many shared-memory wavefronts as a 128-bit one)
+            constexpr int NV = C::HLB / 16;
+            T buf[(2 * NV + 1) * VX];
+#pragma unroll
+            for (int j = 0; j <= 2 * NV; j++) s2_ldvec<T>(t + (j - NV) * 16, &buf[j * VX]);
+#pragma unroll
+            for (int e = 0; e < SEG; e++) seg[e] = buf[NV * VX - R + e];
+        } else if constexpr (!SH) {
             s2_ldvec<T>(t, &seg[R]);
         } else {   // ring on axis 0 whose thickness is not a multiple of 16 bytes: the thread's cells straddle two vectors
 #pragma unroll
             for (int v = 0; v < VX; v++) seg[R + v] = *reinterpret_cast<const T*>(t + v * (int)sizeof(T));
         }
-#pragma unroll
-        for (int e = 0; e < R; e++) {
-            seg[e] = *reinterpret_cast<const T*>(t - (R - e) * (int)sizeof(T));
-            seg[R + VX + e] = *reinterpret_cast<const T*>(t + (VX + e) * (int)sizeof(T));
-        }
-        if (p.bc0 == SB200_REMOVE) {
-            // branch-free: a divergent patch loop on the one edge warp would pace its whole CTA
+        if constexpr (!VEC_HALO) {
 #pragma unroll
             for (int e = 0; e < R; e++) {
-                seg[e] = e < th.nl ? p.pad : seg[e];
-                seg[R + VX + e] = e >= th.rlim ? p.pad : seg[R + VX + e];
+                seg[e] = *reinterpret_cast<const T*>(t - (R - e) * (int)sizeof(T));
+                seg[R + VX + e] = *reinterpret_cast<const T*>(t + (VX + e) * (int)sizeof(T));
+            }
+        }
+        if (p.bc0 == SB200_REMOVE) {
+            // branch-free inside the warp (a divergent patch loop on the one edge warp would pace its whole CTA), skipped by the
+            // warps that have no out-of-bounds halo cell at all (SB200_S2_EDGE_WARP: all but two warps of a 32768-wide row)
+            if (!SB200_S2_EDGE_WARP || th.edge_warp) {
+#pragma unroll
+                for (int e = 0; e < R; e++) {
+                    seg[e] = e < th.nl ? p.pad : seg[e];
+                    seg[R + VX + e] = e >= th.rlim ? p.pad : seg[R + VX + e];
+                }
             }
         } else if (th.edge_l || th.edge_r) {
             const unsigned char* row0 = sbase + J * C::ROWB + C::LEFT + (SH ? p.delta : 0) - th.x0b;  // address of global column 0
@@ -461,6 +483,7 @@ __global__ void __launch_bounds__(S2_THREADS, 2) stream2d_kernel(const __grid_co
         th.edge_r = th.active && !ring0 && p.bc0 != SB200_WRAP && th.gx + VX - 1 + R >= p.W;
         th.nl = ring0 ? 0 : R - th.gx;                 // > 0 only next to the left edge
         th.rlim = ring0 ? R : p.W - th.gx - VX;        // < R only next to the right edge
+        th.edge_warp = __any_sync(0xffffffffu, th.active && (th.nl > 0 || th.rlim < R));
         th.y0 = y0; th.nout = nout;
         th.may_pad = p.soff1 == 0 && p.bc1 == SB200_REMOVE;
         th.dt = p.dst + (long long)(y0 + p.doff1) * p.dpitch + p.doff0 + th.gx;
