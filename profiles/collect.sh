@@ -4,7 +4,8 @@
 set -x
 mkdir -p gpurun_out
 R=${1:-r02}
-ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/${R}_launches_life.csv \
+# launch list of the default bench command: only the library's kernels (the synthetic field generator launches hundreds of torch kernels first)
+ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"life_|stream|gather_|scatter_|box3d|halo_kernel|plan_|combine" -c 400 --csv --log-file gpurun_out/${R}_launches_life.csv \
     python bench.py --steps 200 --warmup 16 --no-extras > gpurun_out/${R}_launches_life.log 2>&1
 # (the .ncu-rep captures are 5-8 MB each and gpurun brings back at most 64 MiB: export the raw page as CSV on the box, drop the capture)
 export_rep() { ncu -i gpurun_out/$1.ncu-rep --page raw --csv > gpurun_out/$1_raw.csv 2>/dev/null; rm -f gpurun_out/$1.ncu-rep; }

@@ -21,9 +21,6 @@
 
 namespace sb {
 
-#ifndef SB200_S2_VEC_HALO
-#define SB200_S2_VEC_HALO 0    // A/B switch (r02k): halo cells by aligned 128-bit loads
-#endif
 #ifndef SB200_S2_EDGE_WARP
 #define SB200_S2_EDGE_WARP 1   // Remove padval selects only in the warps that touch the array edge (r02j: Circle(4) max 620 -> 660, 7x7 246 -> 263 Gcell/s)
 #endif
@@ -195,28 +192,18 @@ __device__ __forceinline__ void s2_row(const S2Params<T>& p, const S2Thread<T>& 
         for (int e = 0; e < SEG; e++) seg[e] = p.pad;
     } else {
         const unsigned char* t = sbase + J * C::ROWB + C::LEFT + (SH ? p.delta : 0) + th.xtb;
-        constexpr bool VEC_HALO = SB200_S2_VEC_HALO && !SH && R >= 2;   // R = 1: one vector + two scalars is as cheap
-        if constexpr (VEC_HALO) {
-            // the halo cells as whole 16-byte vectors of the neighbouring lanes' cells: 2 HLB/16 + 1 aligned 128-bit loads instead of
-            // one plus 2R scalar loads (a scalar load at a 16-byte lane stride costs as many shared-memory wavefronts as a 128-bit one)
-            constexpr int NV = C::HLB / 16;
-            T buf[(2 * NV + 1) * VX];
-#pragma unroll
-            for (int j = 0; j <= 2 * NV; j++) s2_ldvec<T>(t + (j - NV) * 16, &buf[j * VX]);
-#pragma unroll
-            for (int e = 0; e < SEG; e++) seg[e] = buf[NV * VX - R + e];
-        } else if constexpr (!SH) {
+        if constexpr (!SH) {
             s2_ldvec<T>(t, &seg[R]);
         } else {   // ring on axis 0 whose thickness is not a multiple of 16 bytes: the thread's cells straddle two vectors
 #pragma unroll
             for (int v = 0; v < VX; v++) seg[R + v] = *reinterpret_cast<const T*>(t + v * (int)sizeof(T));
         }
-        if constexpr (!VEC_HALO) {
+        // (halo cells as whole 128-bit vectors of the neighbouring lanes' cells instead of 2R scalar loads: measured r02l, no gain —
+        // Circle(4) 638 -> 618, 7 x 7 unchanged — and removed again)
 #pragma unroll
-            for (int e = 0; e < R; e++) {
-                seg[e] = *reinterpret_cast<const T*>(t - (R - e) * (int)sizeof(T));
-                seg[R + VX + e] = *reinterpret_cast<const T*>(t + (VX + e) * (int)sizeof(T));
-            }
+        for (int e = 0; e < R; e++) {
+            seg[e] = *reinterpret_cast<const T*>(t - (R - e) * (int)sizeof(T));
+            seg[R + VX + e] = *reinterpret_cast<const T*>(t + (VX + e) * (int)sizeof(T));
         }
         if (p.bc0 == SB200_REMOVE) {
             // branch-free inside the warp (a divergent patch loop on the one edge warp would pace its whole CTA), skipped by the
