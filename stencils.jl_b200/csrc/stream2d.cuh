@@ -16,6 +16,7 @@
 // per run (+2R rows per run of rows).
 #pragma once
 #include <algorithm>
+#include <cstdlib>
 #include "common.cuh"
 #include "tma.cuh"
 
@@ -512,7 +513,14 @@ int s2_launch_sh(const S2Params<T>& p0, cudaStream_t st) {
     const long long ctas = (long long)ctas_per_sm * num_sms();
     // four tasks per CTA, interleaved: every SM stays busy and the tail is a quarter of a task
     long long nruns = std::max<long long>(1, 4 * ctas / p.nstrips);
-    nruns = std::min<long long>(nruns, std::max(1, p.rows / (4 * C::P)));  // keep the 2R re-read rows per run small
+    const long long cap = std::max(1, p.rows / (4 * C::P));                  // keep the 2R re-read rows per run small
+    if (nruns > cap) {
+        // small grid: the cap alone would leave resident CTA slots idle (1000 x 1000 Float64: 166 tasks for 296 slots); one task
+        // per slot while a run keeps at least one rotation period of rows (r02m: 10.4 -> 8.3 us per sweep)
+        nruns = std::min<long long>(std::max<long long>(cap, ctas / p.nstrips), std::max(1, p.rows / C::P));
+    }
+    static const int nruns_env = getenv("SB200_S2_NRUNS") ? atoi(getenv("SB200_S2_NRUNS")) : 0;   // A/B knob (runs per strip)
+    if (nruns_env > 0) nruns = std::min<long long>(nruns_env, std::max(1, p.rows / C::P));
     p.nruns = (int)nruns;
     const long long grid = std::min<long long>(ctas, (long long)p.nstrips * p.nruns);
     stream2d_kernel<T, SHAPE, R, RED, SH><<<(unsigned)grid, S2_THREADS, C::SMEM, st>>>(p);

@@ -170,6 +170,32 @@ def scatter_case(what, r, offs, R, bc, w, rule=A.SCATTER_CENTER_WEIGHTS, op=A.OP
     s.free(); d.free()
 
 
+def plan_case(what, full_arr, offs, R, bcs, reducer, nslabs, ghost, pflags, nsteps, **kw):
+    """A slab plan (sb200_plan_*: csrc/slab_plan.cu) with several slabs on device 0 against the oracle's single-domain iteration —
+    puts the plan's own kernels (fused push / pull, signal, wait, end fills) and its peer copies under the sanitizer."""
+    from stencils_b200.slab import SlabPlan
+    et = A.ELTYPE_OF_DTYPE[full_arr.dtype]
+    h = build_desc(size=full_arr.shape, eltype=et, out_eltype=et, offsets=offs, radius=R, boundary=bcs, reducer=reducer, **kw)
+    want = orc.iterate(h, full_arr.copy(order="F"), np.zeros_like(full_arr, order="F"), nsteps)
+    if DRY:
+        seen.setdefault("(dry)", []).append(what)
+        print(f"  {what:58s} -> (dry)")
+        return
+    rk = {k: v for k, v in kw.items() if k in ("born_mask", "survive_mask", "alpha")}
+    plan = SlabPlan(full_arr.shape, offsets=offs, radius=R, reducer=reducer, boundary=bcs, eltype=et, ghost=ghost, devices=[0] * nslabs,
+                    reducer_kwargs=rk, padval=kw.get("padval", 0), plan_flags=pflags)
+    try:
+        plan.load(full_arr)
+        plan.iterate(nsteps)
+        plan.sync()
+        got = plan.store()
+    finally:
+        plan.close()
+    seen.setdefault("slab plan", []).append(what)
+    print(f"  {what:58s} -> slab plan ({_lib().sb200_last_kernel().decode()})")
+    same(got, want, what)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--dry", action="store_true", help="oracle side only (no GPU)")
@@ -263,6 +289,16 @@ def main():
         scatter_case("Positional + F32 reflect, zero dest", sf, pos, 2, RF, w4, flags=A.FLAG_ZERO_DEST)
         scatter_case("Moore(1) max F64 remove, 203x45", rand(rng, (203, 45), np.float64), moore, 1, RE, rng.random(8), rule=A.SCATTER_WEIGHTS, op=A.OP_MAX)
         scatter_case("VonNeumann(2) + Int64 wrap", rand(rng, (128, 40), np.int64), npr.offsets("VonNeumann", 2, 2), 2, WR, rng.integers(-3, 4, 12))
+
+    print("slab plans (several slabs on one device)")
+    plan_case("life 1024x200, 2 slabs, flags, G=16, 40 generations", rand(rng, (1024, 200), np.uint8), moore, 1, (WR, WR), A.LIFE, 2, 16,
+              A.PLAN_FLAGS_SYNC, 40)
+    plan_case("diffusion 64x24x60, 3 slabs, events, overlap, 11 steps", rand(rng, (64, 24, 60), np.float32), npr.offsets("VonNeumann", 1, 3), 1,
+              (WR, WR, WR), A.DIFFUSION, 3, 4, A.PLAN_OVERLAP_ON, 11, alpha=0.1)
+    if full:
+        plan_case("diffusion 64x20x50 remove/wrap/reflect, 2 slabs, flags, overlap", rand(rng, (64, 20, 50), np.float32), npr.offsets("VonNeumann", 1, 3),
+                  1, (RE, WR, RF), A.DIFFUSION, 2, 2, A.PLAN_FLAGS_SYNC | A.PLAN_OVERLAP_ON, 7, alpha=0.1, padval=0.5)
+        plan_case("life 512x150 wrap/remove, 3 slabs, events", rand(rng, (512, 150), np.uint8), moore, 1, (WR, RE), A.LIFE, 3, 4, 0, 9, padval=1)
 
     print("\nkernels exercised:")
     for k in sorted(seen):

@@ -1,5 +1,6 @@
 """GPU tests through the public host API (the Python mirror of the Julia API), written to read like the
 reference's own test/array.jl and test/stencils.jl, plus the host-buffer C-ABI entry points."""
+import builtins
 import operator
 
 import numpy as np
@@ -362,6 +363,23 @@ def test_layered_stencils(orc):
         sb.mapstencil(sb.LinearCombination(sb.layer(5, sb.sum)), a)                 # no such layer
     with pytest.raises(sb.ArgumentError):
         sb.mapstencil(sb.LinearCombination(sb.layer("l1", sb.sum)), a2)             # a nested Layered is not a leaf
+
+
+def test_kernel_from_distance_function(orc):
+    """Kernel(f, hood) (src/stencils/kernel.jl:98-106): weights = f.(distances(hood)); kernelproduct on the GPU against the
+    oracle with the same weights, for a Window, a Circle and a Positional hood, Float32 and Float64."""
+    rng = np.random.default_rng(44)
+    for dt in (np.float32, np.float64):
+        r = np.asfortranarray((rng.random((256, 80)) - 0.25).astype(dt))
+        for hood in (sb.Window(2), sb.Circle(3), sb.Positional((-1, 1), (-2, -1), (1, 0), (-2, 2))):
+            k = sb.Kernel(lambda d: dt(1.0) / dt(1.0 + d), hood)
+            assert len(k.kernel) == len(hood) and k.offsets() == hood.offsets()
+            want_w = np.array([dt(1.0) / dt(1.0 + np.sqrt(float(builtins.sum(v * v for v in o)))) for o in hood.offsets()], dtype=dt)
+            np.testing.assert_array_equal(np.asarray(k.kernel, dtype=dt), want_w)
+            a = sb.StencilArray(dev(r), sb.Kernel(hood, np.asarray(k.kernel, dtype=dt)), boundary=sb.Wrap())
+            got = sb.mapstencil(sb.kernelproduct, a)
+            want = orc.stencil_array_sweep(r, hood.offsets(), hood.radius, A.WRAP, "cond", A.KERNELDOT, weights=want_w)
+            bits_equal(host(got), want)
 
 
 def test_torch_free_case_table_matches_oracle():
