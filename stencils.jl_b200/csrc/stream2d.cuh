@@ -22,6 +22,11 @@
 
 namespace sb {
 
+#ifndef SB200_S2_PAIRFOLD_MAXR
+#define SB200_S2_PAIRFOLD_MAXR 3   // nested extrema fold rows in pairs through `cen` (three-input ops) up to this radius; beyond it the
+                                   // pending halves push the 9-row fold of Circle(4) over the 96-register cap (188 + 160 bytes of spills
+                                   // per thread and row): one two-input op per row instead — r02o: 620 -> 683 Gcell/s, 0.835 of the roofline
+#endif
 #ifndef SB200_S2_EDGE_WARP
 #define SB200_S2_EDGE_WARP 1   // Remove padval selects only in the warps that touch the array edge (r02j: Circle(4) max 620 -> 660, 7x7 246 -> 263 Gcell/s)
 #endif
@@ -236,15 +241,36 @@ __device__ __forceinline__ void s2_row(const S2Params<T>& p, const S2Thread<T>& 
     // running extrema m[w] over [-w, w] are built once per source row (2 ops per width) and every output takes the
     // one matching its row of the shape: 2R + (2R+1) ops per cell instead of L.
     constexpr bool NESTED = (RED == SB200_MAX || RED == SB200_MIN) && s2_convex_rows(SHAPE, R);
-    T m[NESTED ? R + 1 : 1][VX];
-    if (NESTED) {
+    if constexpr (NESTED) {
+        // The running extremum over [-w, w] is widened one step at a time and folded AT ONCE into every output whose row of the
+        // shape has that half-width (the outputs are independent accumulators, and max / min do not care about the order), so
+        // only one width is live at a time. (Round 1 built all R + 1 widths first: 20 more live registers, and the Circle(4)
+        // fold spilled 136 + 140 bytes per thread and row at the 96-register cap — more local-memory instructions than math.)
+        T mw[VX];
 #pragma unroll
-        for (int v = 0; v < VX; v++) {
-            m[0][v] = seg[R + v];
+        for (int v = 0; v < VX; v++) mw[v] = seg[R + v];
 #pragma unroll
-            for (int w_ = 1; w_ <= (NESTED ? R : 0); w_++) {
-                const T lo_ = seg[R + v - w_], hi_ = seg[R + v + w_];
-                m[w_][v] = RED == SB200_MAX ? jl_max3(m[w_ - 1][v], lo_, hi_) : jl_min3(m[w_ - 1][v], lo_, hi_);
+        for (int w_ = 0; w_ <= R; w_++) {
+            if (w_ > 0) {
+#pragma unroll
+                for (int v = 0; v < VX; v++)
+                    mw[v] = RED == SB200_MAX ? jl_max3(mw[v], seg[R + v - w_], seg[R + v + w_]) : jl_min3(mw[v], seg[R + v - w_], seg[R + v + w_]);
+            }
+#pragma unroll
+            for (int d = 0; d < P; d++) {
+                const int dy = d - R;
+                if (dy < DY0 || dy > DY1 || s2_row_halfwidth(SHAPE, R, dy) != w_) continue;
+                const int s = ROLL ? d : ((J_ - d) % P + P) % P;
+                const int q = dy - DY0;
+#pragma unroll
+                for (int v = 0; v < VX; v++) {
+                    // rows fold in pairs: the row's extremum waits in `cen` (unused by max / min) until the next row arrives and
+                    // both enter one three-input instruction; convex shapes span 2R+1 rows, so the last row is a pair's end
+                    if (q == 0) acc[s][v] = mw[v];
+                    else if (R > SB200_S2_PAIRFOLD_MAXR) acc[s][v] = RED == SB200_MAX ? jl_max(acc[s][v], mw[v]) : jl_min(acc[s][v], mw[v]);
+                    else if (q & 1) cen[s][v] = mw[v];
+                    else acc[s][v] = RED == SB200_MAX ? jl_max3(acc[s][v], cen[s][v], mw[v]) : jl_min3(acc[s][v], cen[s][v], mw[v]);
+                }
             }
         }
     }
@@ -257,17 +283,7 @@ __device__ __forceinline__ void s2_row(const S2Params<T>& p, const S2Thread<T>& 
         // compile-time rotation (stages hold a multiple of P rows)
         const int s = ROLL ? d : ((J_ - d) % P + P) % P;
         if (NESTED) {
-            const int hw = s2_row_halfwidth(SHAPE, R, dy);
-#pragma unroll
-            for (int v = 0; v < VX; v++) {
-                const T x = m[hw < 0 ? 0 : hw][v];
-                // rows fold in pairs: the row's extremum waits in `cen` (unused by max / min) until the next row arrives
-                // and both enter one three-input instruction; convex shapes span 2R+1 rows, so the last row is a pair's end
-                const int q = dy - DY0;
-                if (q == 0) acc[s][v] = x;
-                else if (q & 1) cen[s][v] = x;
-                else acc[s][v] = RED == SB200_MAX ? jl_max3(acc[s][v], cen[s][v], x) : jl_min3(acc[s][v], cen[s][v], x);
-            }
+            // folded above, width by width
         } else
         {
         if (RED == SB200_DIFFUSION && dy == 0) {
