@@ -275,34 +275,49 @@ __device__ __forceinline__ void s2_row(const S2Params<T>& p, const S2Thread<T>& 
         }
     }
     // ---- fold into the outputs o = i - d, d = dy + R ----
+    // Rolled form (R >= 2, one copy of the row body): after source row i slot d holds the fold of output o = i - d. Instead of
+    // updating in place and then shifting every accumulator one slot (2R x VX moves per row — IMAD.MOV on the same FMA pipe
+    // the folds run on: 5 % of the 7 x 7 kernel's instructions, ncu r02p), the slots are visited from the last to the first and
+    // the FIRST tap of a row reads the neighbouring slot: acc[d] = acc[d-1] (+) tap — the shift rides on a three-operand add.
 #pragma unroll
-    for (int d = 0; d < P; d++) {
+    for (int dd = 0; dd < P; dd++) {
+        const int d = ROLL ? P - 1 - dd : dd;
         const int dy = d - R;
         if (dy < DY0 || dy > DY1) continue;
-        // accumulator of output o = i - d: slot d when the accumulators are shifted after every row, else the
-        // compile-time rotation (stages hold a multiple of P rows)
+        // accumulator of output o = i - d: slot d in the rolled form, else the compile-time rotation (stages hold a multiple of P rows)
         const int s = ROLL ? d : ((J_ - d) % P + P) % P;
+        const int sp = ROLL ? (d > 0 ? d - 1 : 0) : s;   // where that output's fold stood before this row
         if (NESTED) {
             // folded above, width by width
         } else
         {
-        if (RED == SB200_DIFFUSION && dy == 0) {
+        if (RED == SB200_DIFFUSION) {
 #pragma unroll
-            for (int v = 0; v < VX; v++) cen[s][v] = seg[R + v];
+            for (int v = 0; v < VX; v++) {
+                if (dy == 0) cen[s][v] = seg[R + v];
+                else if (ROLL && dy > 0) cen[s][v] = cen[sp][v];
+            }
         }
+        bool first = true;   // compile time after unrolling: the first tap of this row of the shape
 #pragma unroll
         for (int dx = -R; dx <= R; dx++) {
             if (!s2_has(SHAPE, R, dx, dy)) continue;
             const int kk = s2_tap_index(SHAPE, R, dx, dy);
+            const int sr = first ? sp : s;
 #pragma unroll
             for (int v = 0; v < VX; v++) {
                 const T x = seg[R + v + dx];
-                if (RED == SB200_SUM || RED == SB200_MEAN || RED == SB200_DIFFUSION) acc[s][v] = kk == 0 ? x : add_rn(acc[s][v], x);
-                else if (RED == SB200_MAX) acc[s][v] = kk == 0 ? x : jl_max(acc[s][v], x);
-                else if (RED == SB200_MIN) acc[s][v] = kk == 0 ? x : jl_min(acc[s][v], x);
-                else if (RED == SB200_KERNELDOT) acc[s][v] = add_rn(kk == 0 ? T(0) : acc[s][v], mul_rn(x, p.weights[kk]));
-                else if (RED == S2_KDOT_FMA) acc[s][v] = s2_fma(x, p.weights[kk], kk == 0 ? T(0) : acc[s][v]);
+                if (RED == SB200_SUM || RED == SB200_MEAN || RED == SB200_DIFFUSION) acc[s][v] = kk == 0 ? x : add_rn(acc[sr][v], x);
+                else if (RED == SB200_MAX) acc[s][v] = kk == 0 ? x : jl_max(acc[sr][v], x);
+                else if (RED == SB200_MIN) acc[s][v] = kk == 0 ? x : jl_min(acc[sr][v], x);
+                else if (RED == SB200_KERNELDOT) acc[s][v] = add_rn(kk == 0 ? T(0) : acc[sr][v], mul_rn(x, p.weights[kk]));
+                else if (RED == S2_KDOT_FMA) acc[s][v] = s2_fma(x, p.weights[kk], kk == 0 ? T(0) : acc[sr][v]);
             }
+            first = false;
+        }
+        if (ROLL && first && dy > DY0) {   // a row of the shape without taps: the fold just moves on
+#pragma unroll
+            for (int v = 0; v < VX; v++) acc[s][v] = acc[sp][v];
         }
         }
         if (dy == DY1) {  // last row of the fold: output o = i - d is complete
@@ -318,15 +333,6 @@ __device__ __forceinline__ void s2_row(const S2Params<T>& p, const S2Thread<T>& 
             }
             if (o >= 0 && o < th.nout && th.active) s2_stvec(th.dt + (long long)o * p.dpitch, out);
         }
-    }
-    if (ROLL) {
-#pragma unroll
-        for (int d = P - 1; d >= 1; d--)
-#pragma unroll
-            for (int v = 0; v < VX; v++) {
-                acc[d][v] = acc[d - 1][v];
-                if (RED == SB200_DIFFUSION) cen[d][v] = cen[d - 1][v];
-            }
     }
 }
 
