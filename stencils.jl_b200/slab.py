@@ -176,6 +176,7 @@ class SlabIterator:
         # Life on UInt8: after the first sweep every cell this rank reads is a 0/1 output of the kernel (own cells or
         # exchanged ghosts); stale ghost planes outside the still-exact region only feed outputs that are discarded.
         self._later_flags = A.FLAG_CELLS_01 if (reducer == A.LIFE and eltype == A.U8) else 0
+        self._reducer = reducer
         # two generations per launch: Life on a device grid whose split axis is a ring (Remove / Reflect ends must be
         # re-imposed after every single generation) — the library has the last word (life2_accepts, csrc/life.cu)
         self._gen = 1
@@ -340,7 +341,10 @@ class SlabIterator:
             s = self.steps_since_exchange + m                 # generations since the exchange once this sweep is done
             lo, hi = self.R * s, self.ext - self.R * s        # parent planes that are still exact after this sweep
             last_of_cycle = s == self.k
-            if last_of_cycle and self.is_cuda and self.world > 1 and self.overlap:
+            # (thin boundary sweeps of G + 1 rows are below what the multi-generation Life kernels accept: no overlap for those
+            # launches, instead of a rejected launch that used to switch the multi-generation modes off for good — ADVICE r1)
+            thin_ok = m == 1 or self._reducer != A.LIFE or self.G + 1 >= 16
+            if last_of_cycle and self.is_cuda and self.world > 1 and self.overlap and thin_ok:
                 # boundary planes first, their exchange overlaps the interior update
                 # (one extra plane per side: a Reflect end mirrors planes G+1 .. 2G of the new state)
                 G, n = self.G + 1, self.n_local

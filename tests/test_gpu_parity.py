@@ -804,3 +804,40 @@ def test_kernelproduct_allow_fma(orc, dt):
     want = orc.gather(build_desc(**kw), g, dst_like(build_desc(**kw)))
     got, _ = gpu_gather(build_desc(flags=A.FLAG_ALLOW_FMA, **kw), g, dst_like(build_desc(**kw)))
     bits_equal(got, want)
+
+
+def test_multi_generation_flags_need_aligned_parents(orc):
+    """the multi-generation kernels need 16-byte aligned parents. A *_STEP flag on a parent that starts one element off
+    is SB200_EUNSUPPORTED (never a silent single sweep), and sb200_iterate on such buffers still returns the right state —
+    one generation per launch."""
+    import torch
+    from tests.util import stream, sync
+    rng = np.random.default_rng(77)
+    l = A.lib()
+    moore = npr.offsets("Moore", 1, 2)
+    W, H = 1024, 64
+    g = np.asfortranarray((rng.random((W, H)) < 0.4).astype(np.uint8))
+    h1 = build_desc(size=(W, H), eltype=A.U8, out_eltype=A.U8, offsets=moore, radius=1, boundary=A.WRAP, reducer=A.LIFE)
+    flat_a = torch.zeros(W * H + 16, dtype=torch.uint8, device="cuda")
+    flat_b = torch.zeros(W * H + 16, dtype=torch.uint8, device="cuda")
+    flat_a[1:1 + W * H] = torch.from_numpy(np.ascontiguousarray(g.T).reshape(-1)).cuda()
+    pa, pb = flat_a.data_ptr() + 1, flat_b.data_ptr() + 1
+    for fl in (A.FLAG_DOUBLE_STEP, A.FLAG_QUAD_STEP, A.FLAG_OCT_STEP):
+        hf = build_desc(size=(W, H), eltype=A.U8, out_eltype=A.U8, offsets=moore, radius=1, boundary=A.WRAP, reducer=A.LIFE, flags=fl)
+        assert l.sb200_gather(hf.ptr(), pa, pb, stream()) == A.EUNSUPPORTED
+    for n in (5, 20):
+        flat_a[1:1 + W * H] = torch.from_numpy(np.ascontiguousarray(g.T).reshape(-1)).cuda()
+        l.sb200_launch_count(1)
+        A.check(l.sb200_iterate(h1.ptr(), pa, pb, n, stream()))
+        sync()
+        assert l.sb200_launch_count(1) >= n      # one generation per launch (at least one kernel each)
+        res = (flat_a if n % 2 == 0 else flat_b)[1:1 + W * H].cpu().numpy().reshape(H, W).T
+        want = orc.iterate(h1, g.copy(order="F"), np.zeros_like(g, order="F"), n)
+        bits_equal(np.asfortranarray(res), want)
+    v = np.asfortranarray(rng.random((64, 16, 12)).astype(np.float32))
+    offs3 = npr.offsets("VonNeumann", 1, 3)
+    h3 = build_desc(size=v.shape, eltype=A.F32, out_eltype=A.F32, offsets=offs3, radius=1, boundary=A.WRAP, reducer=A.DIFFUSION, alpha=0.1,
+                    flags=A.FLAG_DOUBLE_STEP)
+    fa = torch.zeros(v.size + 8, dtype=torch.float32, device="cuda")
+    fb = torch.zeros(v.size + 8, dtype=torch.float32, device="cuda")
+    assert l.sb200_gather(h3.ptr(), fa.data_ptr() + 4, fb.data_ptr() + 4, stream()) == A.EUNSUPPORTED
