@@ -382,6 +382,22 @@ def test_kernel_from_distance_function(orc):
             bits_equal(host(got), want)
 
 
+def test_shutdown_releases_and_the_library_keeps_working(orc):
+    """sb200_shutdown frees the cached plans (device tables), the host-buffer scratch and the multi-gather scratch; the next call
+    rebuilds what it needs (the one-entry plan memo must not hand out a freed plan)."""
+    l = A.lib()
+    r = np.asfortranarray(np.random.default_rng(3).random((256, 64)))
+    a = sb.StencilArray(dev(r), sb.Window(1))
+    want = orc.stencil_array_sweep(r, npr.offsets("Window", 1, 2), 1, A.REMOVE, "cond", A.MEAN, padval=0.0)
+    for _ in range(3):
+        out = sb.mapstencil(sb.mean, a)
+        bits_equal(host(out), want)
+        hostout = np.zeros_like(r, order="F")
+        sb.mapstencil_(sb.mean, hostout, sb.StencilArray(r, sb.Window(1)))      # host path: allocates the scratch
+        bits_equal(hostout, want)
+        assert l.sb200_shutdown() == 0
+
+
 def test_torch_free_case_table_matches_oracle():
     """tests/sanitize_cases.py (the compute-sanitizer driver: every kernel family on exact cudaMalloc allocations, no torch)
     as a plain parity run: every case bit-identical to the oracle."""
