@@ -2,13 +2,20 @@
 """bench.py — headline benchmark of the stencil sweep (BASELINE.json metric: Gcell-updates/s and fraction of the
 HBM roofline per stencil config).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--strong] [--workload life|mean|mean1000|kernel|circle|positional|scatter|diffusion]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--strong]
+                    [--workload life|mean|mean1000|mean_halo|kernel|kernel_fma|circle|positional|scatter|window3d|diffusion]
     python bench.py --impl reference ...        # the reference algorithm on the host cores (CPU oracle)
 
-One "step" is one sweep of the hot path over the whole grid. The default workload is BASELINE.json configs[1]:
-Game of Life, Moore(1), UInt8 16384x16384, Wrap, SwitchingStencilArray iterated. With N > 1 (torchrun, one rank
-per GPU) every rank owns a 16384x16384 slab of a 16384 x (16384*N) torus (weak scaling) and ghost rows travel
-over NVLink (stencils_b200.slab). Prints ONE JSON line on rank 0.
+One "step" is one sweep of the hot path over the whole grid. The default workload is BASELINE.json configs[1]: Game of Life,
+Moore(1), UInt8 16384x16384, Wrap, SwitchingStencilArray iterated (sb200_iterate). Timing: W warm-up steps, then >= 10
+repetitions of the K-step region (>= 50 ms in total), each bracketed by CUDA events on the launching stream; `value` uses the
+median repetition.
+
+With N > 1 (torchrun, one rank per GPU) every rank owns a 16384x16384 slab of a 16384 x (16384*N) torus (weak scaling; --strong
+splits the one-GPU grid instead) and runs it through the C-ABI slab plan (sb200_plan_create_rank / _connect / _iterate_timed:
+ghost rows over NVLink peer memory). The timed step count is rounded up to whole exchange cycles (>= 4 per repetition), times
+are the max over ranks. BASELINE configs[4] (3-D diffusion 1024^3 per GPU, the configuration the north star names for
+scaling) is measured the same way beside the headline at every N: `c5_diffusion`. Prints ONE JSON line on rank 0.
 """
 from __future__ import annotations
 
@@ -638,6 +645,10 @@ def main():
         # ---- e2e: the reference-facing call with HOST buffers, copies inside the timed region ----
         try:
             line["e2e"] = e2e_host(torch, sb, lib, args.workload, spec)
+            if line["e2e"] and line["e2e"].get("iterated_call"):
+                # what a SwitchingStencilArray user over a host Array hits: one copy in, 100 generations, one copy out (sb200_iterate_host)
+                line["e2e_iterated"] = dict(line["e2e"]["iterated_call"], how="iterate_(Life(), SwitchingStencilArray(host array), 100) -> "
+                                            "sb200_iterate_host; wall clock around the blocking call, pinned host buffer")
         except Exception as e:  # pragma: no cover
             line["e2e"] = {"error": repr(e)}
         if args.workload == "life" and args.steps != 1000:
