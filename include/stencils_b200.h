@@ -181,6 +181,14 @@ typedef struct sb200_desc {
                                      Float32 / Float64, Wrap on axes 0 and 1, axis 2 Wrap or an output region two planes
                                      inside the parent. Anything else: SB200_EUNSUPPORTED (never a silent single sweep).
                                      sb200_iterate uses it by itself where it applies. */
+/* The three *_STEP bits together are a 3-bit field (flags >> 4) & 7 that names the generations of one launch: 1, 2 and 4 are the
+   flags above (2, 4, 8 generations), and the combinations 3, 5, 6, 7 mean that many generations (B3/S23 Life through the bit-sliced
+   kernel only; everything else answers SB200_EUNSUPPORTED). sb200_iterate uses them to split a step count into equal launches with
+   the launch-count parity the buffer contract needs (20 steps = 5 + 5 + 5 + 5 instead of 8 + 8 + 2 + 2). */
+#define SB200_FLAG_STEP_MASK 112
+#define SB200_FLAG_GENS(n) ((n) == 2 ? 16 : (n) == 4 ? 32 : (n) == 8 ? 64 : ((n) == 3 || ((n) >= 5 && (n) <= 7)) ? ((n) << 4) : 0)
+#define SB200_FLAG_GENS_OF(flags) ((((flags) >> 4) & 7) == 0 ? 1 : (((flags) >> 4) & 7) == 1 ? 2 : (((flags) >> 4) & 7) == 2 ? 4 : \
+                                   (((flags) >> 4) & 7) == 4 ? 8 : (((flags) >> 4) & 7))
 
 /* ---- library ---- */
 int32_t sb200_version(void);
@@ -269,6 +277,10 @@ int32_t sb200_wait_flag(const uint32_t* flag, uint32_t value, void* stream);
    tables), the host-buffer scratch of sb200_gather_host / sb200_iterate_host, the scratch of sb200_gather_multi. The caller
    guarantees that no call of the library is in flight. */
 int32_t sb200_shutdown(void);
+/* Diagnostics / tests: how sb200_iterate splits `nsteps` generations into launches when the sizes in `size_mask` (bit g set =
+   launches of g generations are available, g = 2 .. 8; single generations always are) can be used, with the relative launch
+   times of Life (life != 0) or of the two-step diffusion kernel. out[g] = launches of g generations, g = 0 .. 8. Host only. */
+int32_t sb200_debug_split_steps(int32_t nsteps, int32_t size_mask, int32_t life, int32_t* out);
 
 /* ---- slab-partitioned iterated sweeps: the multi-GPU form of the SwitchingStencilArray loop ----
  *

@@ -24,6 +24,14 @@ SUM, MEAN, MIN, MAX, KERNELDOT, LIFE, DIFFUSION = range(7)
 OP_ADD, OP_MAX, OP_MIN = range(3)
 SCATTER_WEIGHTS, SCATTER_CENTER_WEIGHTS = range(2)
 FLAG_FORCE_GENERIC, FLAG_ZERO_DEST, FLAG_NO_TMA, FLAG_CELLS_01, FLAG_DOUBLE_STEP, FLAG_QUAD_STEP, FLAG_OCT_STEP, FLAG_ALLOW_FMA = 1, 2, 4, 8, 16, 32, 64, 128
+FLAG_STEP_MASK = 112
+
+
+def flag_gens(n):
+    """SB200_FLAG_GENS(n): the *_STEP bits for n generations per launch (1 <= n <= 8)."""
+    return {1: 0, 2: 16, 4: 32, 8: 64, 3: 48, 5: 80, 6: 96, 7: 112}[n]
+
+
 MAX_OFFSETS = 1024
 # default of SB200_DIFFUSION_DOUBLE_STEP (two diffusion steps per launch in iterated runs); must agree with
 # kDiffusionDoubleStepDefault in csrc/api.cu
@@ -120,6 +128,7 @@ _SIGS = {
     "sb200_signal_flag": (C.c_int32, [C.c_void_p, C.c_uint32, C.c_void_p]),
     "sb200_wait_flag": (C.c_int32, [C.c_void_p, C.c_uint32, C.c_void_p]),
     "sb200_shutdown": (C.c_int32, []),
+    "sb200_debug_split_steps": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32)]),
     "sb200_plan_create": (C.c_int32, [C.POINTER(Desc), C.c_int32, C.POINTER(C.c_int32), C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]),
     "sb200_plan_create_rank": (C.c_int32, [C.POINTER(Desc), C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]),
     "sb200_plan_ipc_handle": (C.c_int32, [C.c_void_p, C.c_void_p]),

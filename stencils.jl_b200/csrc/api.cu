@@ -345,9 +345,9 @@ static int get_plan(const sb200_desc* d, int kind, Plan** out) {
 bool multistep_accepts(const sb200_desc* d) {
     Plan* pl = nullptr;
     if (get_plan(d, PK_GATHER, &pl) != SB200_OK) return false;
-    if (d->flags & SB200_FLAG_OCT_STEP) return !(d->flags & (SB200_FLAG_DOUBLE_STEP | SB200_FLAG_QUAD_STEP)) && life_multi_accepts(*d, *pl, 8);
-    if (d->flags & SB200_FLAG_QUAD_STEP) return !(d->flags & SB200_FLAG_DOUBLE_STEP) && life_multi_accepts(*d, *pl, 4);
-    if (d->flags & SB200_FLAG_DOUBLE_STEP) return life2_accepts(*d, *pl) || diffusion2_accepts(*d, *pl);
+    const int gens = SB200_FLAG_GENS_OF(d->flags);
+    if (gens == 2) return life2_accepts(*d, *pl) || diffusion2_accepts(*d, *pl);
+    if (gens > 2) return life_multi_accepts(*d, *pl, gens);
     return false;
 }
 
@@ -363,15 +363,13 @@ int do_gather(const sb200_desc* d, const void* src, void* dst, cudaStream_t st) 
         set_error("SB200_FLAG_*_STEP: source and dest parents must be 16-byte aligned");
         return SB200_EUNSUPPORTED;
     }
-    if ((d->flags & SB200_FLAG_QUAD_STEP) && ((d->flags & SB200_FLAG_DOUBLE_STEP) || !life_multi_accepts(*d, *pl, 4))) {
-        set_error("SB200_FLAG_QUAD_STEP: only B3/S23 Life / Moore(1) on an unpadded Bool or UInt8 grid, Wrap on axis 0, width % 32 == 0");
+    const int gens = SB200_FLAG_GENS_OF(d->flags);
+    if (gens > 2 && !life_multi_accepts(*d, *pl, gens)) {
+        set_error("SB200_FLAG_GENS(%d): only B3/S23 Life / Moore(1) on an unpadded Bool or UInt8 grid, Wrap on axis 0, width %% 32 == 0%s",
+                  gens, gens > 4 ? " (and a library built with -DSB200_LB_ONE_HALO_LANE=1, the default)" : "");
         return SB200_EUNSUPPORTED;
     }
-    if ((d->flags & SB200_FLAG_OCT_STEP) && ((d->flags & (SB200_FLAG_DOUBLE_STEP | SB200_FLAG_QUAD_STEP)) || !life_multi_accepts(*d, *pl, 8))) {
-        set_error("SB200_FLAG_OCT_STEP: experiment, needs a library built with -DSB200_LB_ONE_HALO_LANE=1 and the SB200_FLAG_QUAD_STEP layout");
-        return SB200_EUNSUPPORTED;
-    }
-    if ((d->flags & SB200_FLAG_DOUBLE_STEP) && !life2_accepts(*d, *pl) && !diffusion2_accepts(*d, *pl)) {
+    if (gens == 2 && !life2_accepts(*d, *pl) && !diffusion2_accepts(*d, *pl)) {
         set_error("SB200_FLAG_DOUBLE_STEP: only Life / Moore(1) on an unpadded Bool or UInt8 grid with Wrap on axis 0, or "
                   "Diffusion / VonNeumann(1,3) on an unpadded Float32 / Float64 grid with Wrap on axes 0 and 1");
         return SB200_EUNSUPPORTED;
@@ -613,6 +611,62 @@ int32_t sb200_gather_multi(const sb200_term* terms, int32_t nterms, void* dst, v
     return SB200_OK;
 }
 
+// Relative launch times by generations per launch (ncu r02r, Life 16384^2: 1 generation 102 us, 4 generations 103 us, 8 generations
+// 162 us; 5 .. 7 on the ALU-bound slope; diffusion: the two-step kernel runs at 1.45x the single-step rate).
+constexpr int kMaxGens = 8;
+static const double kLifeCost[kMaxGens + 1] = {0, 1.00, 1.00, 1.01, 1.02, 1.06, 1.22, 1.41, 1.60};
+static const double kDiffCost[kMaxGens + 1] = {0, 1.00, 1.38, 0, 0, 0, 0, 0, 0};
+
+// Split nsteps generations into launches of the allowed sizes (ok_size[1] is always true): least total cost with an odd / even
+// number of launches for an odd / even step count (the final state must land in the buffer sb200_iterate's contract names).
+// The bulk of a long run is launches of the cheapest size per generation; a dynamic programme over (generations, launch-count
+// parity) covers the last <= 72 generations. cnt[g] = launches of g generations.
+static void split_steps(int nsteps, const bool* ok_size, const double* cost, int* cnt) {
+    constexpr int MAXG = kMaxGens;
+    for (int g = 0; g <= MAXG; g++) cnt[g] = 0;
+    cnt[1] = nsteps;
+    int bulk = 1;
+    for (int g = 2; g <= MAXG; g++) if (ok_size[g] && cost[g] / g < cost[bulk] / bulk) bulk = g;
+    if (bulk == 1) return;
+    constexpr int TAIL = 64;
+    const int nb0 = nsteps > TAIL ? (nsteps - TAIL + bulk - 1) / bulk : 0;   // launches of `bulk` before the tail
+    double dp[TAIL + MAXG + 1][2];
+    int from[TAIL + MAXG + 1][2];
+    const int tmax = std::min(nsteps, TAIL + MAXG);
+    for (int n = 0; n <= tmax; n++) dp[n][0] = dp[n][1] = 1e300;
+    dp[0][0] = 0;
+    for (int n = 1; n <= tmax; n++)
+        for (int q = 0; q < 2; q++)
+            for (int g = 1; g <= MAXG && g <= n; g++)
+                if ((g == 1 || ok_size[g]) && dp[n - g][q ^ 1] + cost[g] < dp[n][q]) { dp[n][q] = dp[n - g][q ^ 1] + cost[g]; from[n][q] = g; }
+    // the parity of the tail's launch count depends on the number of bulk launches: try nb0 and nb0 - 1
+    double best = 1e300;
+    int best_nb = -1;
+    for (int nb = nb0; nb >= 0 && nb >= nb0 - 1; nb--) {
+        const int tail = nsteps - nb * bulk;
+        if (tail > tmax) break;
+        const double c = nb * cost[bulk] + dp[tail][(nsteps ^ nb) & 1];
+        if (c < best) { best = c; best_nb = nb; }
+    }
+    if (best_nb < 0 || best > 1e299) return;
+    cnt[1] = 0;
+    cnt[bulk] = best_nb;
+    int q = (nsteps ^ best_nb) & 1;
+    for (int n = nsteps - best_nb * bulk; n > 0; q ^= 1) { const int g = from[n][q]; cnt[g]++; n -= g; }
+}
+
+// Test hook (tests/test_host_api.py): the split sb200_iterate would use for `nsteps` with the sizes in `size_mask` (bit g = launches
+// of g generations allowed) and the Life (1) or diffusion (0) cost table. out[0 .. 8].
+int32_t sb200_debug_split_steps(int32_t nsteps, int32_t size_mask, int32_t life, int32_t* out) {
+    if (nsteps < 0 || !out) return SB200_EINVAL;
+    bool ok[kMaxGens + 1];
+    for (int g = 0; g <= kMaxGens; g++) ok[g] = g == 1 || ((size_mask >> g) & 1);
+    int cnt[kMaxGens + 1];
+    split_steps(nsteps, ok, life ? kLifeCost : kDiffCost, cnt);
+    for (int g = 0; g <= kMaxGens; g++) out[g] = cnt[g];
+    return SB200_OK;
+}
+
 // sb200_iterate schedules two diffusion steps per launch by itself when this is true (SB200_DIFFUSION_DOUBLE_STEP overrides).
 static constexpr bool kDiffusionDoubleStepDefault = true;
 
@@ -632,60 +686,42 @@ int32_t sb200_iterate(const sb200_desc* d, void* buf_a, void* buf_b, int32_t nst
     // packed kernel does not accept).
     sb200_desc later = *d;
     if (d->reducer == SB200_LIFE && d->eltype == SB200_U8) later.flags |= SB200_FLAG_CELLS_01;
-    // Several generations per launch where a kernel supports it (Life: 2 / 4 / 8 with the intermediate generations in
-    // registers, life.cu; Diffusion: 2, stream3d2.cu): the run is split into launches of 8, 4, 2 and 1 generations — as few
-    // launches as possible, and an odd / even number of them for an odd / even step count, so that the final state lands in
-    // the buffer the contract names. Small launches go first; the rest of the run is launches of the largest size.
-    // SB200_NO_DOUBLE_STEP / SB200_NO_QUAD_STEP / SB200_OCT_STEP=0 / SB200_DIFFUSION_DOUBLE_STEP=0 cap the size (A/B runs).
+    // Several generations per launch where a kernel supports it (Life: 2 .. 8 with the intermediate generations in
+    // registers, life.cu; Diffusion: 2, stream3d2.cu). The run is split into launches of 1 .. maxg generations with the least
+    // estimated time (kLaunchCost below: a launch of up to 4 Life generations costs about one trip through HBM, larger ones are
+    // ALU-bound) and an odd / even number of launches for an odd / even step count, so that the final state lands in the buffer
+    // the contract names: long runs are launches of 8 plus a fix-up, 20 steps are 5 + 5 + 5 + 5. Small launches go first.
+    // SB200_NO_DOUBLE_STEP / SB200_NO_QUAD_STEP / SB200_OCT_STEP=0 / SB200_DIFFUSION_DOUBLE_STEP=0 cap the size (A/B runs),
+    // SB200_POW2_STEPS=1 keeps the round-2 sizes 1 / 2 / 4 / 8.
     // The multi-generation kernels need 16-byte aligned parents: other pointers run one generation per launch.
     const bool aligned16 = ((((uintptr_t)buf_a | (uintptr_t)buf_b) & 15) == 0);
     const bool life = d->reducer == SB200_LIFE;
     const char* e_d2 = getenv("SB200_DIFFUSION_DOUBLE_STEP");
     const bool diff2 = d->reducer == SB200_DIFFUSION && (e_d2 ? atoi(e_d2) != 0 : kDiffusionDoubleStepDefault);
-    int maxg = 1;
-    if (aligned16 && (life || diff2) && nsteps >= 4 && !halo &&
-        !(d->flags & (SB200_FLAG_DOUBLE_STEP | SB200_FLAG_QUAD_STEP | SB200_FLAG_OCT_STEP)) && !getenv("SB200_NO_DOUBLE_STEP")) {
-        auto accepts = [&](int flag) {
+    constexpr int MAXG = kMaxGens;
+    bool ok_size[MAXG + 1] = {false, true, false, false, false, false, false, false, false};
+    if (aligned16 && (life || diff2) && nsteps >= 4 && !halo && !(d->flags & SB200_FLAG_STEP_MASK) && !getenv("SB200_NO_DOUBLE_STEP")) {
+        auto accepts = [&](int gens) {
             sb200_desc probe = *d;
-            probe.flags |= flag;
+            probe.flags |= SB200_FLAG_GENS(gens);
             return multistep_accepts(&probe);
         };
-        if (accepts(SB200_FLAG_DOUBLE_STEP)) {
-            maxg = 2;
-            if (life && !getenv("SB200_NO_QUAD_STEP") && accepts(SB200_FLAG_QUAD_STEP)) {
-                maxg = 4;
-                if (!(getenv("SB200_OCT_STEP") && atoi(getenv("SB200_OCT_STEP")) == 0) && accepts(SB200_FLAG_OCT_STEP)) maxg = 8;
-            }
-        }
+        const bool pow2 = getenv("SB200_POW2_STEPS") && atoi(getenv("SB200_POW2_STEPS")) != 0;
+        int cap = life ? MAXG : 2;
+        if (getenv("SB200_NO_QUAD_STEP")) cap = 2;
+        else if (getenv("SB200_OCT_STEP") && atoi(getenv("SB200_OCT_STEP")) == 0) cap = std::min(cap, 4);
+        ok_size[2] = accepts(2);
+        for (int g = 3; g <= cap && ok_size[2]; g++) ok_size[g] = !(pow2 && (g & (g - 1))) && accepts(g);
     }
-    int cnt[4] = {nsteps, 0, 0, 0};   // launches of 1, 2, 4, 8 generations
-    if (maxg > 1) {
-        const int top = maxg == 8 ? 3 : maxg == 4 ? 2 : 1;   // index of the largest size
-        int best = nsteps + 1;
-        for (int ntop = nsteps >> top; ntop >= 0 && ntop >= (nsteps >> top) - 4; ntop--) {
-            const int rest = nsteps - (ntop << top);
-            int lim[3] = {3, top >= 2 ? 3 : 0, top >= 3 ? 3 : 0};   // counts of 1, 2, 4 (sizes below the top one)
-            if (top == 1) lim[0] = rest;                              // only singles below doubles
-            for (int c4 = 0; c4 <= lim[2]; c4++)
-                for (int c2 = 0; c2 <= (top >= 2 ? lim[1] : 0); c2++) {
-                    const int c1 = rest - 4 * c4 - 2 * c2;
-                    if (c1 < 0 || c1 > lim[0]) continue;
-                    int c[4] = {c1, c2, c4, 0};
-                    c[top] += ntop;
-                    const int launches = c[0] + c[1] + c[2] + c[3];
-                    if (((launches ^ nsteps) & 1) == 0 && launches < best) { best = launches; memcpy(cnt, c, sizeof(c)); }
-                }
-        }
-    }
+    int cnt[kMaxGens + 1];   // launches of 1 .. 8 generations
+    split_steps(nsteps, ok_size, life ? kLifeCost : kDiffCost, cnt);
     // One launch of the loop body: [ring refresh] + sweep from -> to (gens generations).
     bool fresh = true;   // the next launch is the first one of the call (UInt8 cells not yet known to be 0/1)
     auto body = [&](int gens, void* from, void* to) -> int {
         int rc;
         if (halo && (rc = sb200_update_halo(d, from, stream))) return rc;
         sb200_desc cur = fresh ? *d : later;
-        if (gens == 2) cur.flags |= SB200_FLAG_DOUBLE_STEP;
-        if (gens == 4) cur.flags |= SB200_FLAG_QUAD_STEP;
-        if (gens == 8) cur.flags |= SB200_FLAG_OCT_STEP;
+        if (gens > 1) cur.flags |= SB200_FLAG_GENS(gens);
         rc = do_gather(&cur, from, to, (cudaStream_t)stream);
         if (rc == SB200_OK) fresh = false;
         return rc;
@@ -697,9 +733,8 @@ int32_t sb200_iterate(const sb200_desc* d, void* buf_a, void* buf_b, int32_t nst
     for (int a = 0; a < d->ndim; a++) cells *= d->size[a];
     constexpr int GRAPH_CHUNK = 32;
     bool want_graph = stream != nullptr && cells <= (4LL << 20) && !getenv("SB200_NO_GRAPH");
-    for (int size_idx = 0; size_idx < 4; size_idx++) {
-        const int per = 1 << size_idx;
-        int left = cnt[size_idx];
+    for (int per = 1; per <= MAXG; per++) {
+        int left = cnt[per];
         int issued = 0;   // direct launches of this size so far (the second one runs with the steady-state descriptor: its plan exists)
         while (left > 0) {
             if (want_graph && issued >= 2 && !fresh && left >= 2 * GRAPH_CHUNK) {

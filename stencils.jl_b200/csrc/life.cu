@@ -822,9 +822,10 @@ template <int G, bool CELLS01> static int launch_bit(const LifeParams& p, cudaSt
 bool life2_accepts(const sb200_desc& d, const Plan& pl) { return life_multi_accepts(d, pl, 2); }
 
 bool life_multi_accepts(const sb200_desc& d, const Plan& pl, int gens) {
-    if (gens >= 4 && (d.born_mask != (1u << 3) || d.survive_mask != ((1u << 2) | (1u << 3)) || d.size[0] % 32 || getenv("SB200_NO_BITSLICE")))
-        return false;   // four (eight) generations: the bit-sliced B3/S23 kernel only
-    if (gens == 8 && !SB200_LB_ONE_HALO_LANE) return false;   // eight generations need the one-halo-lane layout
+    if (gens < 2 || gens > 8) return false;
+    if (gens >= 3 && (d.born_mask != (1u << 3) || d.survive_mask != ((1u << 2) | (1u << 3)) || d.size[0] % 32 || getenv("SB200_NO_BITSLICE")))
+        return false;   // three and more generations: the bit-sliced B3/S23 kernel only
+    if (gens > 4 && !SB200_LB_ONE_HALO_LANE) return false;   // five to eight generations need the one-halo-lane layout
     if (d.reducer != SB200_LIFE || d.ndim != 2 || (d.eltype != SB200_BOOL && d.eltype != SB200_U8)) return false;
     if (pl.shape_tag != SB200_MOORE || pl.shape_ndim != 2 || d.radius != 1 || d.noffsets != 8) return false;
     if (d.flags & (SB200_FLAG_NO_TMA | SB200_FLAG_FORCE_GENERIC)) return false;
@@ -893,27 +894,32 @@ int try_life_swar(const Plan& pl, const void* src, void* dst, cudaStream_t st) {
     // Bool cells are 0/1 by type; UInt8 cells are 0/1 when the caller says so (sb200_iterate does for every
     // step after the first, because the source is then this kernel's own output).
     const bool cells01 = d.eltype == SB200_BOOL || (d.flags & SB200_FLAG_CELLS_01);
-    if (d.flags & SB200_FLAG_OCT_STEP) {   // needs the one-halo-lane layout (the default build)
-        if (!life_multi_accepts(d, pl, 8)) { set_error("eight generations per sweep: not supported by this build / layout / rule"); return SB200_EUNSUPPORTED; }
+    const int gens = SB200_FLAG_GENS_OF(d.flags);
+    if (gens > 2) {   // 3 .. 8 generations: the bit-sliced kernel (5 .. 8 need its one-halo-lane layout, the default build)
+        if (!life_multi_accepts(d, pl, gens)) { set_error("%d generations per sweep: layout / boundary / rule / build not supported", gens); return SB200_EUNSUPPORTED; }
+        p.mirror = nullptr; p.m_lo = p.m_hi = 0;
+        int rc = SB200_EUNSUPPORTED;
+        switch (gens) {
+            case 3: rc = cells01 ? launch_bit<3, true>(p, st) : launch_bit<3, false>(p, st); break;
+            case 4: rc = cells01 ? launch_bit<4, true>(p, st) : launch_bit<4, false>(p, st); break;
 #if SB200_LB_ONE_HALO_LANE
-        p.mirror = nullptr; p.m_lo = p.m_hi = 0;
-        const int rc = cells01 ? launch_bit<8, true>(p, st) : launch_bit<8, false>(p, st);
-        if (rc) return rc;
-        SB_LAUNCH_CHECK();
-        set_kernel_name(cells01 ? "life_bit_kernel<8,cells01>" : "life_bit_kernel<8,u8>");
-        return SB200_OK;
+            case 5: rc = cells01 ? launch_bit<5, true>(p, st) : launch_bit<5, false>(p, st); break;
+            case 6: rc = cells01 ? launch_bit<6, true>(p, st) : launch_bit<6, false>(p, st); break;
+            case 7: rc = cells01 ? launch_bit<7, true>(p, st) : launch_bit<7, false>(p, st); break;
+            case 8: rc = cells01 ? launch_bit<8, true>(p, st) : launch_bit<8, false>(p, st); break;
 #endif
-    }
-    if (d.flags & SB200_FLAG_QUAD_STEP) {
-        if (!life_multi_accepts(d, pl, 4)) { set_error("four generations per sweep: layout / boundary / rule not supported"); return SB200_EUNSUPPORTED; }
-        p.mirror = nullptr; p.m_lo = p.m_hi = 0;
-        const int rc = cells01 ? launch_bit<4, true>(p, st) : launch_bit<4, false>(p, st);
+            default: break;
+        }
         if (rc) return rc;
         SB_LAUNCH_CHECK();
-        set_kernel_name(cells01 ? "life_bit_kernel<4,cells01>" : "life_bit_kernel<4,u8>");
+        static const char* const names[2][6] = {
+            {"life_bit_kernel<3,u8>", "life_bit_kernel<4,u8>", "life_bit_kernel<5,u8>", "life_bit_kernel<6,u8>", "life_bit_kernel<7,u8>", "life_bit_kernel<8,u8>"},
+            {"life_bit_kernel<3,cells01>", "life_bit_kernel<4,cells01>", "life_bit_kernel<5,cells01>", "life_bit_kernel<6,cells01>",
+             "life_bit_kernel<7,cells01>", "life_bit_kernel<8,cells01>"}};
+        set_kernel_name(names[cells01 ? 1 : 0][gens - 3]);
         return SB200_OK;
     }
-    if (d.flags & SB200_FLAG_DOUBLE_STEP) {
+    if (gens == 2) {
         if (!life2_accepts(d, pl)) { set_error("two generations per sweep: layout / boundary not supported"); return SB200_EUNSUPPORTED; }
         p.mirror = nullptr; p.m_lo = p.m_hi = 0;
         int rc;

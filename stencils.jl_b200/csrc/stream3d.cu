@@ -316,7 +316,7 @@ template <typename T> static int s3_try(const Plan& pl, const void* src, void* d
 int try_diffusion3d(const Plan& pl, const void* src, void* dst, cudaStream_t st) {
     const sb200_desc& d = pl.d;
     if (d.flags & SB200_FLAG_NO_TMA) return -1;
-    if ((d.flags & SB200_FLAG_DOUBLE_STEP) && d.reducer == SB200_DIFFUSION) return try_diffusion3d_double(pl, src, dst, st);
+    if (SB200_FLAG_GENS_OF(d.flags) == 2 && d.reducer == SB200_DIFFUSION) return try_diffusion3d_double(pl, src, dst, st);
     if (d.ndim != 3 || pl.shape_tag != SB200_VONNEUMANN || pl.shape_ndim != 3 || d.radius != 1 || d.noffsets != 6) return -1;
     int rc = -1;
     if (d.eltype == SB200_F32) rc = s3_try<float>(pl, src, dst, st);

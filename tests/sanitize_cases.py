@@ -128,7 +128,7 @@ def gather_case(what, r, offs, R, bc, red, *, pad="cond", flags=0, region=None, 
         return
     s, d = Dev(parent), Dev(dst0)
     p_cpu = parent.copy(order="F")
-    gens = 8 if flags & A.FLAG_OCT_STEP else 4 if flags & A.FLAG_QUAD_STEP else 2 if flags & A.FLAG_DOUBLE_STEP else 1
+    gens = {0: 1, 1: 2, 2: 4, 4: 8}.get((flags >> 4) & 7, (flags >> 4) & 7)   # SB200_FLAG_GENS_OF
     if gens > 1:  # dest = f(f(src)) / f^4(src) on the output region, everything else of dest untouched
         A.check(l.sb200_gather(h.ptr(), s.p, d.p, None))
         A.check(l.sb200_stream_sync(None))
@@ -217,6 +217,10 @@ def main():
     gather_case("life 1024x96 wrap, two generations (bit-sliced)", g, moore, 1, WR, A.LIFE, flags=A.FLAG_DOUBLE_STEP)
     gather_case("life 1024x96 wrap, four generations (bit-sliced)", g, moore, 1, WR, A.LIFE, flags=A.FLAG_QUAD_STEP)
     gather_case("life 1024x96 wrap, eight generations (bit-sliced, one halo lane)", g, moore, 1, WR, A.LIFE, flags=A.FLAG_OCT_STEP)
+    gather_case("life 1024x96 wrap, five generations (bit-sliced)", g, moore, 1, WR, A.LIFE, flags=A.flag_gens(5))
+    if full:
+        for n in (3, 6, 7):
+            gather_case(f"life 1024x96 wrap, {n} generations (bit-sliced)", g, moore, 1, WR, A.LIFE, flags=A.flag_gens(n))
     gather_case("life 1024x96 wrap, iterate x21", g, moore, 1, WR, A.LIFE, nsteps=21)
     gather_case("life 1024x96 wrap, no TMA", g, moore, 1, WR, A.LIFE, flags=A.FLAG_NO_TMA)
     if full:

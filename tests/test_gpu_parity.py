@@ -759,6 +759,77 @@ def test_life_eight_generations_per_launch(orc, monkeypatch):
         monkeypatch.delenv("SB200_OCT_STEP")
 
 
+@pytest.mark.parametrize("gens", [3, 5, 6, 7])
+def test_life_any_generations_per_launch(orc, gens):
+    """SB200_FLAG_GENS(n) for the sizes between the power-of-two flags (include/stencils_b200.h): dest = step^n(src) in one launch
+    of life_bit_kernel<n> against n oracle sweeps — Wrap and Reflect on axis 1, an interior region, UInt8 cells that are not 0/1,
+    Bool cells — and refusals: a rule other than B3/S23, a diffusion sweep."""
+    rng = np.random.default_rng(530 + gens)
+    l = A.lib()
+    moore = npr.offsets("Moore", 1, 2)
+    fl = A.flag_gens(gens)
+    for (W, H), bc1, et in [((1024, 96), A.WRAP, np.uint8), ((3840 + 512, 67), A.WRAP, np.uint8), ((4096, 40), A.REFLECT, np.uint8),
+                            ((2048, 50), A.WRAP, np.bool_)]:
+        alive = rng.random((W, H)) < 0.4
+        g = np.asfortranarray(alive if et is np.bool_ else (alive * rng.integers(1, 255, size=(W, H))).astype(np.uint8))
+        e = A.ELTYPE_OF_DTYPE[np.dtype(et)]
+        kw = dict(size=(W, H), eltype=e, out_eltype=e, offsets=moore, radius=1, boundary=(A.WRAP, bc1), reducer=A.LIFE)
+        h1 = build_desc(**kw)
+        want = g
+        for _ in range(gens):
+            want = orc.gather(h1, want, dst_like(h1))
+        got, _ = gpu_gather(build_desc(flags=fl, **kw), g, dst_like(h1))
+        assert l.sb200_last_kernel().startswith(b"life_bit_kernel<%d" % gens)
+        bits_equal(got, want)
+        hr = build_desc(flags=fl, region=((0, gens, 0), (W, H - gens, 0)), **kw)
+        got, _ = gpu_gather(hr, g, dst_like(hr, 7))
+        want_r = dst_like(hr, 7)
+        want_r[:, gens:H - gens] = want[:, gens:H - gens]
+        bits_equal(got, want_r)
+    from tests.util import stream, to_dev
+    W, H = 1024, 64
+    g = np.asfortranarray((rng.random((W, H)) < 0.4).astype(np.uint8))
+    ta, tb = to_dev(g), to_dev(np.zeros_like(g, order="F"))
+    other = build_desc(size=(W, H), eltype=A.U8, out_eltype=A.U8, offsets=moore, radius=1, boundary=A.WRAP, reducer=A.LIFE,
+                       born_mask=(1 << 3) | (1 << 6), survive_mask=0b1100, flags=fl)
+    assert l.sb200_gather(other.ptr(), ta.data_ptr(), tb.data_ptr(), stream()) == A.EUNSUPPORTED
+    v = np.asfortranarray(rng.random((64, 16, 12)).astype(np.float32))
+    h3 = build_desc(size=v.shape, eltype=A.F32, out_eltype=A.F32, offsets=npr.offsets("VonNeumann", 1, 3), radius=1, boundary=A.WRAP,
+                    reducer=A.DIFFUSION, alpha=0.1, flags=fl)
+    fa, fb = to_dev(v), to_dev(np.zeros_like(v, order="F"))
+    assert l.sb200_gather(h3.ptr(), fa.data_ptr(), fb.data_ptr(), stream()) == A.EUNSUPPORTED
+
+
+def test_iterate_every_step_count(orc):
+    """sb200_iterate splits a run into launches of 1 .. 8 generations (split_steps in csrc/api.cu): every step count 0 .. 40 plus
+    a few long ones lands in the buffer the contract names, bit-identical to the oracle's single steps, with the launch count
+    sb200_debug_split_steps predicts."""
+    import ctypes as C
+    from tests.util import stream, sync, to_dev, to_host
+    rng = np.random.default_rng(59)
+    l = A.lib()
+    moore = npr.offsets("Moore", 1, 2)
+    W, H = 1024, 80
+    g = np.asfortranarray(((rng.random((W, H)) < 0.4) * rng.integers(1, 255, size=(W, H))).astype(np.uint8))
+    h1 = build_desc(size=(W, H), eltype=A.U8, out_eltype=A.U8, offsets=moore, radius=1, boundary=A.WRAP, reducer=A.LIFE)
+    want = g.copy(order="F")
+    done = 0
+    for n in list(range(0, 41)) + [57, 100, 131]:
+        while done < n:
+            want = orc.gather(h1, want, dst_like(h1))
+            done += 1
+        ta, tb = to_dev(g), to_dev(np.zeros_like(g, order="F"))
+        l.sb200_launch_count(1)
+        A.check(l.sb200_iterate(h1.ptr(), ta.data_ptr(), tb.data_ptr(), n, stream()))
+        sync()
+        launches = l.sb200_launch_count(1)
+        bits_equal(to_host(ta if n % 2 == 0 else tb, g.shape, g.dtype), want if n else g)
+        out = (C.c_int32 * 9)()
+        A.check(l.sb200_debug_split_steps(n, 0x1FC if n >= 4 else 0, 1, out))
+        assert sum(k * out[k] for k in range(9)) == n and sum(out) % 2 == n % 2
+        assert launches == sum(out), (n, launches, list(out))
+
+
 @pytest.mark.parametrize("dt", [np.float32, np.float64])
 def test_kernelproduct_allow_fma(orc, dt):
     """SB200_FLAG_ALLOW_FMA: acc = fma(v_k, w_k, acc) instead of the reference's separately rounded multiply and add

@@ -241,3 +241,40 @@ def test_layered_goldens():
     assert ah.parent.shape == (9, 9) and ah.shape == (5, 5)
     with pytest.raises(sb.ArgumentError):
         sb.Layered()
+
+
+def test_iterate_step_split_is_optimal_and_keeps_the_buffer_parity():
+    """split_steps (csrc/api.cu) behind sb200_debug_split_steps: the launches sb200_iterate issues for a step count add up to it,
+    their number has the parity of the step count (the final state lands in the buffer the contract names), and for step
+    counts a brute-force search can cover the split has the least total cost under the library's launch-time table."""
+    l = A.lib()
+    life_cost = [0, 1.00, 1.00, 1.01, 1.02, 1.06, 1.22, 1.41, 1.60]   # kLifeCost
+    diff_cost = [0, 1.00, 1.38]                                        # kDiffCost
+
+    def split(n, mask, life):
+        out = (C.c_int32 * 9)()
+        A.check(l.sb200_debug_split_steps(n, mask, life, out))
+        return list(out)
+
+    def best(n, sizes, cost):
+        INF = float("inf")
+        dp = [[INF, INF] for _ in range(n + 1)]
+        dp[0][0] = 0.0
+        for m in range(1, n + 1):
+            for q in (0, 1):
+                dp[m][q] = min((dp[m - g][q ^ 1] + cost[g] for g in sizes if g <= m), default=INF)
+        return dp[n][n & 1]
+
+    for mask, life, cost in [(0x1FC, 1, life_cost), (0x114, 1, life_cost), (0x14, 1, life_cost), (0x4, 1, life_cost), (0x4, 0, diff_cost), (0, 1, life_cost)]:
+        sizes = [1] + [g for g in range(2, 9) if (mask >> g) & 1]
+        for n in list(range(0, 150)) + [500, 1000, 1001, 4096, 99999]:
+            c = split(n, mask, life)
+            assert c[0] == 0 and sum(g * c[g] for g in range(9)) == n, (mask, n, c)
+            assert all(c[g] == 0 for g in range(9) if g not in sizes), (mask, n, c)
+            assert sum(c) % 2 == n % 2, (mask, n, c)
+            total = sum(cost[g] * c[g] for g in sizes)
+            assert total <= best(n, sizes, cost) * (1 + 1e-9) + 1e-9, (mask, n, c, total, best(n, sizes, cost))
+    assert split(20, 0x1FC, 1) == [0, 0, 0, 0, 0, 4, 0, 0, 0]             # the driver's --steps 20: 5 + 5 + 5 + 5
+    assert split(20, 0x114, 1) == [0, 0, 0, 0, 3, 0, 0, 0, 1]             # powers of two only: 4 + 4 + 4 + 8
+    assert split(100, 0x4, 0) == [0, 0, 50, 0, 0, 0, 0, 0, 0]
+    assert split(101, 0x4, 0) == [0, 1, 50, 0, 0, 0, 0, 0, 0]
