@@ -9,7 +9,9 @@ HBM roofline per stencil config).
 One "step" is one sweep of the hot path over the whole grid. The default workload is BASELINE.json configs[1]: Game of Life,
 Moore(1), UInt8 16384x16384, Wrap, SwitchingStencilArray iterated (sb200_iterate). Timing: W warm-up steps, then >= 10
 repetitions of the K-step region (>= 50 ms in total), each bracketed by CUDA events on the launching stream; `value` uses the
-median repetition.
+median repetition. For the iterated workloads (life, diffusion) K is rounded UP to whole exchange cycles
+of the slab plans (Life 126 generations, diffusion 4; >= 4 cycles) at EVERY N, N = 1 included, so that a scaling series times
+one schedule; `steps_timed` says what ran and `k_step_calls` carries the rate of sb200_iterate calls of exactly K generations.
 
 With N > 1 (torchrun, one rank per GPU) every rank owns a 16384x16384 slab of a 16384 x (16384*N) torus (weak scaling; --strong
 splits the one-GPU grid instead) and runs it through the C-ABI slab plan (sb200_plan_create_rank / _connect / _iterate_timed:
@@ -360,6 +362,12 @@ def slab_case(workload):
     raise SystemExit(f"workload {workload} is not an iterated (slab-partitioned) configuration")
 
 
+def plan_cycle(workload):
+    """Generations per ghost exchange of the slab plans' library defaults (csrc/slab_plan.cu: Life 126 rows = 18 launches of seven
+    generations, diffusion 4 planes); bench_slabs reads the same number from the plan's own stats at N > 1."""
+    return {"life": 126, "diffusion": 4}[workload]
+
+
 def bench_slabs(torch, dist, workload, spec, steps, warmup, strong, min_reps=10, min_total_ms=50.0):
     """One slab per rank through the C-ABI slab plan (sb200_plan_create_rank / _connect / _iterate_timed; csrc/slab_plan.cu).
     Weak scaling: every rank owns spec['shape'], the global last axis is world x as long; strong: spec['shape'] is split.
@@ -580,20 +588,30 @@ def main():
         st, run, cells_total = make_sweep(args.workload, spec, torch, sb)
         run(1)
         torch.cuda.synchronize()
-        with ClockSampler(local_rank) as cs:
-            lib.sb200_launch_count(1)
-            times = time_reps(torch, run, args.steps, args.warmup)
-            launches_all = lib.sb200_launch_count(1)
-        kernel = lib.sb200_last_kernel().decode()  # the kernel of the timed region (iterated runs fuse generations)
-        timing = rep_stats(times, args.steps)
-        # launches counted over warm-up + pilot + R repetitions of K steps each: per-repetition share
-        launches_per_rep = launches_all * args.steps / (args.warmup + (len(times) + 1) * args.steps) if spec["iterated"] else args.steps
-        launches = int(round(launches_per_rep * len(times)))
+        # Iterated workloads: a repetition is ONE sb200_iterate call whose step count is --steps rounded UP to whole exchange
+        # cycles of the slab plans (>= 4 cycles), exactly as bench_slabs rounds it at N > 1 — every N of a scaling series then
+        # times the same schedule (same generations per launch, same number of launches per step). The rate of calls of exactly
+        # --steps generations is reported beside it (`k_step_calls`).
         steps_timed = args.steps
-        ms_per_step = timing["rep_ms_median"] / args.steps
-        value = cells_total * args.steps / (timing["rep_ms_median"] * 1e-3) / 1e9
+        if spec["iterated"]:
+            cyc = plan_cycle(args.workload)
+            steps_timed = max(-(-args.steps // cyc) * cyc, 4 * cyc)
+        with ClockSampler(local_rank) as cs:
+            times = time_reps(torch, run, steps_timed, args.warmup)
+        kernel = lib.sb200_last_kernel().decode()  # the kernel of the timed region (iterated runs fuse generations)
+        timing = rep_stats(times, steps_timed)
+        lib.sb200_launch_count(1)
+        run(steps_timed)                           # one more (untimed) repetition: its launches, counted by the library
+        launches_per_rep = lib.sb200_launch_count(1)
+        torch.cuda.synchronize()
+        launches = int(launches_per_rep * len(times))
+        ms_per_step = timing["rep_ms_median"] / steps_timed
+        value = cells_total * steps_timed / (timing["rep_ms_median"] * 1e-3) / 1e9
         extra_cfg = {}
-        sweeps_per_launch = args.steps / max(launches_per_rep, 1e-9) if spec["iterated"] else 1.0
+        if steps_timed != args.steps:
+            extra_cfg["steps_rounding"] = (f"--steps {args.steps} rounded up to {steps_timed} = whole exchange cycles of the slab plans ({cyc} generations, "
+                                           f">= 4 cycles) in ONE sb200_iterate call per repetition: the schedule every N of the scaling series times")
+        sweeps_per_launch = steps_timed / max(launches_per_rep, 1e-9) if spec["iterated"] else 1.0
 
     line = {
         "metric": "gcell_updates_per_s", "value": value, "unit": "Gcell-updates/s", "n_gpus": world, "steps": args.steps,
@@ -651,14 +669,18 @@ def main():
                                             "sb200_iterate_host; wall clock around the blocking call, pinned host buffer")
         except Exception as e:  # pragma: no cover
             line["e2e"] = {"error": repr(e)}
-        if args.workload == "life" and args.steps != 1000:
-            # the BASELINE configuration is a 1000-step run; a short --steps K measures K-step calls (fewer 8-generation launches)
+        if spec["iterated"] and steps_timed != args.steps:
+            # calls of exactly --steps generations: a short call holds fewer full-size launches (20 Life steps = 4 + 4 + 6 + 6)
             try:
-                t1000 = time_reps(torch, run, 1000, 3, min_reps=5)
-                line["config_run_1000_steps"] = {"value": cells_total * 1000 / (float(np.median(t1000)) * 1e-3) / 1e9, "unit": "Gcell-updates/s",
-                                                 "timing": rep_stats(t1000, 1000)}
+                tk = time_reps(torch, run, args.steps, 3)
+                lib.sb200_launch_count(1)
+                run(args.steps)
+                lk = lib.sb200_launch_count(1)
+                torch.cuda.synchronize()
+                line["k_step_calls"] = {"steps_per_call": args.steps, "value": cells_total * args.steps / (float(np.median(tk)) * 1e-3) / 1e9,
+                                        "unit": "Gcell-updates/s", "launches_per_call": int(lk), "timing": rep_stats(tk, args.steps)}
             except Exception as e:  # pragma: no cover
-                line["config_run_1000_steps"] = {"error": repr(e)}
+                line["k_step_calls"] = {"error": repr(e)}
         # ---- the other BASELINE configs, same measurement, for context ----
         del st, run
         torch.cuda.empty_cache()

@@ -611,10 +611,12 @@ int32_t sb200_gather_multi(const sb200_term* terms, int32_t nterms, void* dst, v
     return SB200_OK;
 }
 
-// Relative launch times by generations per launch (ncu r02r, Life 16384^2: 1 generation 102 us, 4 generations 103 us, 8 generations
-// 162 us; 5 .. 7 on the ALU-bound slope; diffusion: the two-step kernel runs at 1.45x the single-step rate).
+// Relative launch times by generations per launch (tools/life_gens_probe.py, r02t, Life 16384^2 with 0/1 cells, us per launch: 94.8
+// (one generation, life_tma_kernel), 111.5, 110.2, 101.6, 113.6, 123.8, 136.9, 160.6 (two .. eight, life_bit_kernel<G>) — seven
+// generations per launch is the best rate, 13.7 against 13.4 Tcell-updates/s for eight; diffusion: the two-step kernel runs at 1.45x
+// the single-step rate).
 constexpr int kMaxGens = 8;
-static const double kLifeCost[kMaxGens + 1] = {0, 1.00, 1.00, 1.01, 1.02, 1.06, 1.22, 1.41, 1.60};
+static const double kLifeCost[kMaxGens + 1] = {0, 1.00, 1.18, 1.16, 1.07, 1.20, 1.31, 1.44, 1.69};
 static const double kDiffCost[kMaxGens + 1] = {0, 1.00, 1.38, 0, 0, 0, 0, 0, 0};
 
 // Split nsteps generations into launches of the allowed sizes (ok_size[1] is always true): least total cost with an odd / even

@@ -198,7 +198,7 @@ static sb200_desc sweep_desc(const sb200_plan* p, long long ext, long long lo, l
     d.boundary[last] = SB200_WRAP;   // never exercised: the output region stays R * gens planes inside the parent
     for (int a = 0; a < 3; a++) { d.region_lo[a] = 0; d.region_hi[a] = a < p->ndim ? d.size[a] : 0; }
     d.region_lo[last] = lo; d.region_hi[last] = hi;
-    d.flags = (first ? 0 : p->later_flags) | (gens == 2 ? SB200_FLAG_DOUBLE_STEP : gens == 4 ? SB200_FLAG_QUAD_STEP : gens == 8 ? SB200_FLAG_OCT_STEP : 0);
+    d.flags = (first ? 0 : p->later_flags) | SB200_FLAG_GENS(gens);
     d.mirror_parent = nullptr; d.mirror_lo = d.mirror_hi = 0;
     d.offsets_host = p->offsets.data();
     d.weights_host = p->weights.empty() ? nullptr : p->weights.data();
@@ -211,6 +211,14 @@ static void split_last(long long n, int world, int r, long long* lo, long long* 
     const long long base = n / world, rem = n % world;
     *lo = r * base + std::min<long long>(r, rem);
     *hi = *lo + base + (r < rem ? 1 : 0);
+}
+
+// SB200_POW2_STEPS=1 (or any of the round-2 caps SB200_NO_QUAD_STEP / SB200_OCT_STEP=0 / SB200_NO_DOUBLE_STEP): launches of 8 / 4 / 2
+// generations only, as in round 2; otherwise Life prefers launches of seven (tools/life_gens_probe.py, r02t: 13.7 against 13.4
+// Tcell-updates/s for eight — two rows less of redundant halo per strip and 80 instead of 96 registers).
+static bool life_pow2_only() {
+    return (getenv("SB200_POW2_STEPS") && atoi(getenv("SB200_POW2_STEPS")) != 0) || getenv("SB200_NO_QUAD_STEP") || getenv("SB200_NO_DOUBLE_STEP") ||
+           (getenv("SB200_OCT_STEP") && atoi(getenv("SB200_OCT_STEP")) == 0);
 }
 
 static int plan_common_init(sb200_plan* p, const sb200_desc* g, int ghost, int plan_flags, int nslabs_total) {
@@ -236,11 +244,15 @@ static int plan_common_init(sb200_plan* p, const sb200_desc* g, int ghost, int p
     p->ndim = g->ndim;
     p->R = std::max(1, (int)g->radius);
     int G = ghost;
-    // Library defaults (measured on 2 GPUs, r02i): Life 128 ghost rows — an exchange costs ~26 us whatever its size, the rows a
+    // Library defaults (measured on 2 GPUs, r02i): Life ~128 ghost rows — an exchange costs ~26 us whatever its size, the rows a
     // wide halo recomputes are 0.8 % of a 16384-row slab; diffusion 4 planes (two double sweeps per cycle; 8 measured the same).
+    // Life cycles are whole launches of seven generations (life_gens_pref below: 126 = 18 x 7, 28 = 4 x 7; 128 / 32 with
+    // SB200_POW2_STEPS=1, launches of eight).
     if (G <= 0) {
         const long long n_est = g->size[g->ndim - 1] / nslabs_total;
-        G = g->reducer == SB200_LIFE ? (n_est >= 1024 ? 128 : 32) * p->R : (g->reducer == SB200_DIFFUSION ? 4 * p->R : p->R);
+        const bool sevens = !life_pow2_only();
+        G = g->reducer == SB200_LIFE ? (n_est >= 1024 ? (sevens ? 126 : 128) : (sevens ? 28 : 32)) * p->R
+                                     : (g->reducer == SB200_DIFFUSION ? 4 * p->R : p->R);
         while (G > p->R && G > n_est) G /= 2;
         G = std::max(p->R, G / p->R * p->R);
     }
@@ -318,6 +330,11 @@ static int plan_make_sched(sb200_plan* p, const std::vector<long long>& exts, in
     int mg = 1;
     for (int m = std::max(cand, 1); m > 1; m >>= 1)
         if (c.accept((long long)p->R * m, -(long long)p->R * m, m)) { mg = m; break; }
+    if (mg == 8 && p->g.reducer == SB200_LIFE && !life_pow2_only()) {
+        // every size the bit-sliced kernel has, sevens first (the scheduler takes the first one that fits the cycle's room)
+        for (int m : {7, 8, 6, 5, 4, 3, 2})
+            if (m <= p->k && c.accept((long long)p->R * m, -(long long)p->R * m, m)) c.sizes.push_back(m);
+    }
     c.max_gens = mg;
     p->max_gens = mg;
     p->sched = new SlabSched(c);
@@ -740,6 +757,11 @@ int32_t sb200_slab_schedule(int32_t radius, int32_t ghost, int64_t n_min, int32_
     if (radius < 1 || ghost < radius || ghost % radius || nsteps < 0 || !count) { set_error("bad arguments to sb200_slab_schedule"); return SB200_EINVAL; }
     SlabSchedCfg c;
     c.R = radius; c.G = ghost; c.split_wrap = split_wrap != 0; c.overlap = overlap != 0; c.max_gens = std::max(1, (int)max_gens);
+    if (max_gens < 0) {   // -mask: bit g set = launches of g generations, preference order of the Life plans
+        c.max_gens = 1;
+        for (int m : {7, 8, 6, 5, 4, 3, 2})
+            if ((-max_gens >> m) & 1) { c.sizes.push_back(m); c.max_gens = std::max(c.max_gens, m); }
+    }
     c.n_min = n_min;
     const long long ext = n_min + 2 * (long long)ghost;
     c.accept = [ext, min_planes_multi](long long lo, long long hi, int) { return abs_plane(hi, ext) - abs_plane(lo, ext) >= min_planes_multi; };

@@ -4,7 +4,8 @@
 // [G ghost | n owned | G ghost] and ghosts are exchanged every k = G / R steps ("wide halo"). After an exchange the ghost
 // planes are exact; a sweep that advances the state to s generations after the exchange writes the planes that are still
 // exact, [R s, ext - R s) of the parent, so after k generations exactly the owned planes are valid again. A launch may
-// advance m = 1, 2, 4 or 8 generations (SB200_FLAG_DOUBLE/QUAD/OCT_STEP) while the cycle has room.
+// advance m = 1 .. 8 generations (SB200_FLAG_GENS) while the cycle has room: the sizes in `sizes`, tried in that order (Life
+// prefers 7: the bit-sliced kernel's best rate, so its default cycle is 126 = 18 x 7 generations), or 8 / 4 / 2 below max_gens.
 //
 // On the last sweep of a cycle the planes the neighbours need are computed first (two thin boundary sweeps that also
 // store them into the neighbours' landing slots: sb200_desc.mirror_*), published (SIGNAL), and pulled into the ghost zones
@@ -27,7 +28,8 @@ struct SlabSchedCfg {
     int R = 1, G = 1;
     bool split_wrap = true;   // Wrap on the split axis (ring); else Remove / Reflect ends re-imposed after every sweep
     bool overlap = false;     // boundary-first + async pull on the last sweep of a cycle
-    int max_gens = 1;         // largest generations-per-launch the reducer / layout supports (1, 2, 4, 8)
+    int max_gens = 1;         // largest generations-per-launch the reducer / layout supports
+    std::vector<int> sizes;   // generations per launch in order of preference (without 1); empty: max_gens, max_gens / 2, ..., 2
     // accept(lo, hi, gens): may the sweep of parent planes [lo, hi) (signed encoding) run `gens` generations in one launch on
     // EVERY slab? (gens == 1 is always accepted.)
     std::function<bool(long long, long long, int)> accept;
@@ -63,10 +65,17 @@ struct SlabSched {
             }
             const int room = k - since;
             int m = 1;
-            for (int cand = c.max_gens; cand > 1; cand >>= 1) {
-                if (cand > left || cand > room) continue;
+            auto fits = [&](int cand) {
+                if (cand <= 1 || cand > left || cand > room) return false;
                 const long long s = since + cand;
-                if (ok((long long)R * s, -(long long)R * s, cand)) { m = cand; break; }
+                return ok((long long)R * s, -(long long)R * s, cand);
+            };
+            if (c.sizes.empty()) {
+                for (int cand = c.max_gens; cand > 1; cand >>= 1)
+                    if (fits(cand)) { m = cand; break; }
+            } else {
+                for (int cand : c.sizes)
+                    if (fits(cand)) { m = cand; break; }
             }
             const long long s = since + m;
             const long long lo = (long long)R * s, hi = -(long long)R * s;   // parent planes [R s, ext - R s)

@@ -115,6 +115,10 @@ CASES = [
     ("life", (24, 61), (A.WRAP, A.WRAP), 8, 2, True, 4, 0, (16, 5, 11)),       # ragged slabs, overlap with multi-generation sweeps
     ("life", (24, 64), (A.WRAP, A.WRAP), 8, 2, True, 8, 12, (17, 15)),         # thin boundary sweeps rejected -> no overlap on those steps
     ("life", (24, 40), (A.WRAP, A.WRAP), 4, 1, True, 4, 0, (9,)),              # one slab: its own neighbour on the ring
+    # negative max_gens = -(mask of launch sizes), preference 7, 8, 6, 5, 4, 3, 2 (the Life plans since r02t)
+    ("life", (24, 90), (A.WRAP, A.WRAP), 14, 3, False, -0x1FC, 0, (31, 14, 5, 9)),   # cycles of two launches of seven
+    ("life", (24, 96), (A.WRAP, A.WRAP), 14, 2, True, -0x1FC, 0, (28, 17)),          # overlap on a seven-generation last sweep
+    ("life", (24, 70), (A.WRAP, A.WRAP), 10, 2, False, -0x0E8, 0, (23, 10)),         # sizes 7, 6, 5, 3: 7 + 3 per cycle
     ("life", (20, 37), (A.WRAP, A.REMOVE), 2, 3, False, 1, 0, (5, 2)),
     ("life", (20, 37), (A.REFLECT, A.REFLECT), 3, 2, True, 1, 0, (7,)),
     ("diffusion", (8, 6, 30), (A.WRAP, A.WRAP, A.WRAP), 4, 3, True, 2, 0, (10, 3, 4)),
