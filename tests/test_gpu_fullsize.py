@@ -218,7 +218,7 @@ def test_diffusion_1024_cubed_two_steps_per_launch():
 
 # ---- SURVEY 8d tier T3 long runs: the whole grid against the oracle over MANY schedule cycles ----
 def test_long_run_life_2048_1000_generations(orc):
-    """Life 2048 x 2048 UInt8 Wrap x 1000 generations through sb200_iterate (8 / 4 / 2 / 1 generations per launch, small-grid
+    """Life 2048 x 2048 UInt8 Wrap x 1000 generations through sb200_iterate (1 .. 8 generations per launch, sevens in bulk, small-grid
     CUDA-graph replay on a real stream) and through a three-slab plan, full grid against orc.iterate, bit for bit."""
     import torch
     from stencils_b200.slab import SlabPlan
