@@ -513,6 +513,13 @@ static thread_local unsigned g_push_seq = 0;
 
 using namespace sb;
 
+namespace sb {
+// Relative launch times by generations per launch (tools/life_gens_probe.py, r02w, Life 16384^2 with 0/1 cells, us per launch: 94.9
+// (one generation, life_tma_kernel), 107.7, 110.4, 108.6, 101.2, 111.3, 124.2, 137.8 (two .. eight, life_bit_kernel<G>): eight
+// generations per launch is the best rate, 15.6 Tcell-updates/s; diffusion: the two-step kernel runs at 1.45x the single-step rate).
+const double kLifeLaunchCost[kMaxGens + 1] = {0, 1.00, 1.13, 1.16, 1.14, 1.07, 1.17, 1.31, 1.45};
+}  // namespace sb
+
 extern "C" {
 
 int32_t sb200_version(void) { return SB200_VERSION; }
@@ -611,12 +618,7 @@ int32_t sb200_gather_multi(const sb200_term* terms, int32_t nterms, void* dst, v
     return SB200_OK;
 }
 
-// Relative launch times by generations per launch (tools/life_gens_probe.py, r02t, Life 16384^2 with 0/1 cells, us per launch: 94.8
-// (one generation, life_tma_kernel), 111.5, 110.2, 101.6, 113.6, 123.8, 136.9, 160.6 (two .. eight, life_bit_kernel<G>) — seven
-// generations per launch is the best rate, 13.7 against 13.4 Tcell-updates/s for eight; diffusion: the two-step kernel runs at 1.45x
-// the single-step rate).
-constexpr int kMaxGens = 8;
-static const double kLifeCost[kMaxGens + 1] = {0, 1.00, 1.18, 1.16, 1.07, 1.20, 1.31, 1.44, 1.69};
+static const double* const kLifeCost = sb::kLifeLaunchCost;
 static const double kDiffCost[kMaxGens + 1] = {0, 1.00, 1.38, 0, 0, 0, 0, 0, 0};
 
 // Split nsteps generations into launches of the allowed sizes (ok_size[1] is always true): least total cost with an odd / even

@@ -190,5 +190,15 @@ int num_sms();
 // several generations per launch.
 int do_gather(const sb200_desc* d, const void* src, void* dst, cudaStream_t st);
 bool multistep_accepts(const sb200_desc* d);
+// Launch time of the Life kernels by generations per launch, relative to one generation (api.cu; measured, tools/life_gens_probe.py),
+// and the size with the least time per generation (what long runs and the slab plans' cycles are made of).
+constexpr int kMaxGens = 8;
+extern const double kLifeLaunchCost[kMaxGens + 1];
+inline int life_bulk_gens() {
+    int best = 1;
+    for (int g = 2; g <= kMaxGens; g++)
+        if (kLifeLaunchCost[g] / g < kLifeLaunchCost[best] / best) best = g;
+    return best;
+}
 
 }  // namespace sb

@@ -627,9 +627,31 @@ __device__ __forceinline__ unsigned lop3_maj(unsigned a, unsigned b, unsigned c)
     return r;
 }
 // `prev` / `next` = the words of the 32 cells to the left / right (only their top / bottom bit is used): the one-bit shifts with
-// the neighbour's edge bit shifted in are single funnel shifts (SHF.L.W / SHF.R.W on two registers)
-__device__ __forceinline__ BRow brow(unsigned w, unsigned prev, unsigned next) {
+// the neighbour's edge bit shifted in are single funnel shifts (SHF.L.W / SHF.R.W on two registers).
+// SB200_LB_IMAD_SHIFT=1 computes them on the FMA pipe instead (the kernel is bound by the ALU pipe — LOP3 / SHF issue every other
+// cycle per scheduler — while the FMA pipe idles at 7 %): L = w * 2 + hi32(prev * 2), R = hi32(w * 2^31) + next * 2^31, four IMAD /
+// IMAD.HI with the multipliers read from constant memory (an immediate power of two is strength-reduced back to SHF / LEA).
+#ifndef SB200_LB_IMAD_SHIFT
+#define SB200_LB_IMAD_SHIFT 0
+#endif
+__constant__ unsigned lb_mul_consts[7] = {2u, 0x80000000u, 16u, 1u << 28, 1u << 24, 1u << 20, 1u << 16};
+struct LbMul { unsigned two, half, sixteen, un[4]; };
+#ifndef SB200_LB_IMAD_UNPACK
+#define SB200_LB_IMAD_UNPACK 0   // nibble k of a word as hi32((bits << (28 - 4k)) * 16): IMAD + IMAD.HI instead of SHF + LOP3
+#endif
+#ifndef SB200_LB_IMAD_PACK
+#define SB200_LB_IMAD_PACK 0     // acc = acc * 16 + hi32(product * 16): IMAD.HI + IMAD instead of SHF.L.W
+#endif
+__device__ __forceinline__ BRow brow(unsigned w, unsigned prev, unsigned next, const LbMul& m) {
+#if SB200_LB_IMAD_SHIFT
+    unsigned e, f, L, R;
+    asm("mul.hi.u32 %0, %1, %2;" : "=r"(e) : "r"(prev), "r"(m.two));
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(L) : "r"(w), "r"(m.two), "r"(e));
+    asm("mul.lo.u32 %0, %1, %2;" : "=r"(f) : "r"(next), "r"(m.half));
+    asm("mad.hi.u32 %0, %1, %2, %3;" : "=r"(R) : "r"(w), "r"(m.half), "r"(f));
+#else
     const unsigned L = __funnelshift_l(prev, w, 1), R = __funnelshift_r(w, next, 1);
+#endif
     return BRow{w, lop3_xor3(L, w, R), lop3_maj(L, w, R)};
 }
 // B3/S23 from the rows above, at and below: T = 3x3 total including the centre; alive' = (T == 3) | (centre & T == 4)
@@ -651,18 +673,32 @@ __device__ __forceinline__ unsigned conway_bits(const BRow& a, const BRow& b, co
     const unsigned y4 = lop3_imm<0x60>(q4, u1, c1) & b.c;      // T == 4 and the centre is alive
     return lop3_imm<0xBA>(p3, c1, y4);                         // (p3 & ~c1) | y4
 }
-template <bool CELLS01> __device__ __forceinline__ unsigned pack32(const uint4& lo, const uint4& hi) {
+// The product w * 0x10204080 holds the four 0/1 bytes of w in its top nibble; SHF.L.W (acc:product) << 4 appends exactly that
+// nibble to the accumulator (words 7 .. 0, so that cell 0 ends in bit 0): two instructions per word, no mask.
+template <bool CELLS01> __device__ __forceinline__ unsigned pack32(const uint4& lo, const uint4& hi, const LbMul& m) {
     unsigned w[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
     unsigned acc = 0;
 #pragma unroll
-    for (int k = 0; k < 8; k++) {
+    for (int k = 7; k >= 0; k--) {
         const unsigned v = CELLS01 ? w[k] : nz_bytes(w[k]);
-        acc = (acc >> 4) | ((v * 0x10204080u) & 0xF0000000u);
+#if SB200_LB_IMAD_PACK
+        unsigned nib;
+        asm("mul.hi.u32 %0, %1, %2;" : "=r"(nib) : "r"(v * 0x10204080u), "r"(m.sixteen));
+        asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(acc) : "r"(acc), "r"(m.sixteen), "r"(nib));
+#else
+        acc = __funnelshift_l(v * 0x10204080u, acc, 4);
+#endif
     }
     return acc;
 }
-__device__ __forceinline__ unsigned unpack4(unsigned bits, int k) {  // cells 4k .. 4k+3 as four 0/1 bytes
+__device__ __forceinline__ unsigned unpack4(unsigned bits, int k, const LbMul& m) {  // cells 4k .. 4k+3 as four 0/1 bytes
+#if SB200_LB_IMAD_UNPACK
+    unsigned nib;
+    asm("mul.hi.u32 %0, %1, %2;" : "=r"(nib) : "r"(bits * m.un[k]), "r"(m.sixteen));   // (bits << (28 - 4k)) >> 28
+    return (nib * 0x00204081u) & 0x01010101u;
+#else
     return (((bits >> (4 * k)) & 0xFu) * 0x00204081u) & 0x01010101u;
+#endif
 }
 
 template <int G, bool CELLS01>
@@ -680,6 +716,7 @@ __global__ void __launch_bounds__((LB_WARPS + 1) * 32, 3) life_bit_kernel(const 
     }
     __syncthreads();
     const int ntasks = q.nstrips * q.nruns;
+    const LbMul mul{lb_mul_consts[0], lb_mul_consts[1], lb_mul_consts[2], {lb_mul_consts[3], lb_mul_consts[4], lb_mul_consts[5], lb_mul_consts[6]}};
     unsigned k = 0;
     for (int task = blockIdx.x; task < ntasks; task += gridDim.x) {
         const int strip = task % q.nstrips, run = task / q.nstrips;
@@ -728,6 +765,7 @@ __global__ void __launch_bounds__((LB_WARPS + 1) * 32, 3) life_bit_kernel(const 
         const int cell0 = warp * C::WO + (lane - C::HLN) * 32;   // first final cell of this lane inside the strip
         const bool active = lane >= C::HLN && lane <= 31 - C::HLN && cell0 < wout;
         const unsigned act_mask = __ballot_sync(0xffffffffu, active);
+        const bool st_ok[2] = {((act_mask >> (lane >> 1)) & 1u) != 0, ((act_mask >> (16 + (lane >> 1))) & 1u) != 0};   // my two store slots
         // destination of the cells of lane 0 (a halo lane: never stored) in output row y0
         uint8_t* __restrict__ wp = p.dst + (long long)(y0 + p.doff1) * p.dpitch + x0 + warp * C::WO - C::HLN * 32;
         const int soff = C::D0 + C::HL + cell0;
@@ -746,18 +784,23 @@ __global__ void __launch_bounds__((LB_WARPS + 1) * 32, 3) life_bit_kernel(const 
                 {   // level 0: pack the source row
                     const uint8_t* t = sbase + J * LB_ROWB + soff;
                     const uint4 lo = *reinterpret_cast<const uint4*>(t), hi = *reinterpret_cast<const uint4*>(t + 16);
-                    const unsigned w = pack32<CELLS01>(lo, hi);
-                    // edge bits from the adjacent lanes' packed words; only the warp's end lanes read a halo byte
+                    const unsigned w = pack32<CELLS01>(lo, hi, mul);
+                    // edge bits from the adjacent lanes' packed words. With one halo lane per side the outer edge bit of an end lane
+                    // may be anything (the shuffle hands lane 0 / 31 its own word, as at every later level): a wrong bit moves one
+                    // cell per generation and stays inside the end lane, which owns no final cell. The G - 1 halo-lane layout of
+                    // round 1 reads the real halo byte.
                     unsigned prev = __shfl_up_sync(0xffffffffu, w, 1), next = __shfl_down_sync(0xffffffffu, w, 1);
+#if !SB200_LB_ONE_HALO_LANE
                     if (lane == 0) prev = t[-1] != 0 ? 0x80000000u : 0u;
                     if (lane == 31) next = t[32] != 0;
-                    lv[0][J] = brow(w, prev, next);
+#endif
+                    lv[0][J] = brow(w, prev, next, mul);
                 }
 #pragma unroll
                 for (int g = 1; g < G; g++) {  // generation g of row i - g from generation g-1 of rows i-g-1, i-g, i-g+1
                     const unsigned x = conway_bits(lv[g - 1][(J - g - 1 + 9) % 3], lv[g - 1][(J - g + 9) % 3], lv[g - 1][(J - g + 1 + 9) % 3]);
                     const unsigned prev = __shfl_up_sync(0xffffffffu, x, 1), next = __shfl_down_sync(0xffffffffu, x, 1);
-                    lv[g][(J - g + 9) % 3] = brow(x, prev, next);
+                    lv[g][(J - g + 9) % 3] = brow(x, prev, next, mul);
                 }
                 if (i >= 2 * G && i < nsrc) {   // generation G of row i - G: the output row y0 + i - 2G
                     const unsigned y = conway_bits(lv[G - 1][(J - G - 1 + 9) % 3], lv[G - 1][(J - G + 9) % 3], lv[G - 1][(J - G + 1 + 9) % 3]);
@@ -767,9 +810,8 @@ __global__ void __launch_bounds__((LB_WARPS + 1) * 32, 3) life_bit_kernel(const 
                     for (int hb = 0; hb < 2; hb++) {
                         const int sl = hb * 16 + (lane >> 1);
                         const unsigned h16 = __shfl_sync(0xffffffffu, y, sl) >> (16 * (lane & 1));
-                        if ((act_mask >> sl) & 1u)
-                            *reinterpret_cast<uint4*>(wp + hb * 512 + lane * 16) =
-                                make_uint4(unpack4(h16, 0), unpack4(h16, 1), unpack4(h16, 2), unpack4(h16, 3));
+                        const uint4 cells = make_uint4(unpack4(h16, 0, mul), unpack4(h16, 1, mul), unpack4(h16, 2, mul), unpack4(h16, 3, mul));
+                        if (st_ok[hb]) *reinterpret_cast<uint4*>(wp + hb * 512 + lane * 16) = cells;   // a predicated store, no branch
                     }
                     wp += p.dpitch;
                 }

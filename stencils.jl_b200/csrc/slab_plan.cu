@@ -214,8 +214,8 @@ static void split_last(long long n, int world, int r, long long* lo, long long* 
 }
 
 // SB200_POW2_STEPS=1 (or any of the round-2 caps SB200_NO_QUAD_STEP / SB200_OCT_STEP=0 / SB200_NO_DOUBLE_STEP): launches of 8 / 4 / 2
-// generations only, as in round 2; otherwise Life prefers launches of seven (tools/life_gens_probe.py, r02t: 13.7 against 13.4
-// Tcell-updates/s for eight — two rows less of redundant halo per strip and 80 instead of 96 registers).
+// generations only, as in round 2; otherwise every size the bit-sliced kernel has, the one with the best measured rate first
+// (life_bulk_gens(), common.cuh).
 static bool life_pow2_only() {
     return (getenv("SB200_POW2_STEPS") && atoi(getenv("SB200_POW2_STEPS")) != 0) || getenv("SB200_NO_QUAD_STEP") || getenv("SB200_NO_DOUBLE_STEP") ||
            (getenv("SB200_OCT_STEP") && atoi(getenv("SB200_OCT_STEP")) == 0);
@@ -246,12 +246,12 @@ static int plan_common_init(sb200_plan* p, const sb200_desc* g, int ghost, int p
     int G = ghost;
     // Library defaults (measured on 2 GPUs, r02i): Life ~128 ghost rows — an exchange costs ~26 us whatever its size, the rows a
     // wide halo recomputes are 0.8 % of a 16384-row slab; diffusion 4 planes (two double sweeps per cycle; 8 measured the same).
-    // Life cycles are whole launches of seven generations (life_gens_pref below: 126 = 18 x 7, 28 = 4 x 7; 128 / 32 with
-    // SB200_POW2_STEPS=1, launches of eight).
+    // Life cycles are whole launches of the kernel's best size b = life_bulk_gens(): the multiples of b next to 128 and 32 (b = 8: 128
+    // and 32; b = 7: 126 and 28).
     if (G <= 0) {
         const long long n_est = g->size[g->ndim - 1] / nslabs_total;
-        const bool sevens = !life_pow2_only();
-        G = g->reducer == SB200_LIFE ? (n_est >= 1024 ? (sevens ? 126 : 128) : (sevens ? 28 : 32)) * p->R
+        const int b = life_pow2_only() ? 8 : life_bulk_gens();
+        G = g->reducer == SB200_LIFE ? (n_est >= 1024 ? (128 + b / 2) / b * b : (32 + b / 2) / b * b) * p->R
                                      : (g->reducer == SB200_DIFFUSION ? 4 * p->R : p->R);
         while (G > p->R && G > n_est) G /= 2;
         G = std::max(p->R, G / p->R * p->R);
@@ -331,8 +331,10 @@ static int plan_make_sched(sb200_plan* p, const std::vector<long long>& exts, in
     for (int m = std::max(cand, 1); m > 1; m >>= 1)
         if (c.accept((long long)p->R * m, -(long long)p->R * m, m)) { mg = m; break; }
     if (mg == 8 && p->g.reducer == SB200_LIFE && !life_pow2_only()) {
-        // every size the bit-sliced kernel has, sevens first (the scheduler takes the first one that fits the cycle's room)
-        for (int m : {7, 8, 6, 5, 4, 3, 2})
+        // every size the bit-sliced kernel has, best rate first (the scheduler takes the first one that fits the cycle's room)
+        std::vector<int> order = {8, 7, 6, 5, 4, 3, 2};
+        std::stable_sort(order.begin(), order.end(), [](int a, int b) { return kLifeLaunchCost[a] / a < kLifeLaunchCost[b] / b; });
+        for (int m : order)
             if (m <= p->k && c.accept((long long)p->R * m, -(long long)p->R * m, m)) c.sizes.push_back(m);
     }
     c.max_gens = mg;

@@ -238,7 +238,7 @@ def test_long_run_life_2048_1000_generations(orc):
         A.check(l.sb200_iterate(h.ptr(), a.data_ptr(), b.data_ptr(), 1000, stream.cuda_stream if stream is not None else None))
         torch.cuda.synchronize()
         launches = l.sb200_launch_count(1)
-        assert launches <= 130, launches   # 124 x 8 + 2 x 4 generations
+        assert launches <= 146, launches   # launches of seven generations (+ a fix-up for the launch-count parity)
         bits_equal(np.asfortranarray(a.cpu().numpy().T), want)
     plan = SlabPlan(shape, offsets=npr.offsets("Moore", 1, 2), radius=1, reducer=A.LIFE, boundary=(A.WRAP, A.WRAP), eltype=A.U8, ghost=0,
                     devices=[0, 0, 0], reducer_kwargs=dict(born_mask=8, survive_mask=12))
