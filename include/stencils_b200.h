@@ -185,6 +185,13 @@ typedef struct sb200_desc {
    flags above (2, 4, 8 generations), and the combinations 3, 5, 6, 7 mean that many generations (B3/S23 Life through the bit-sliced
    kernel only; everything else answers SB200_EUNSUPPORTED). sb200_iterate uses them to split a step count into equal launches with
    the launch-count parity the buffer contract needs (20 steps = 5 + 5 + 5 + 5 instead of 8 + 8 + 2 + 2). */
+#define SB200_FLAG_SRC_BITS 256  /* LIFE with SB200_FLAG_GENS(2 .. 8) (a packed source: 1 .. 8), B3/S23, axis 0 a multiple of 128 cells: the SOURCE parent holds one BIT per
+                                     cell — row r starts at byte r * src_ext[0] / 8 and cell c of the row is bit c % 8 of its byte c / 8 (the
+                                     layout of a Julia BitMatrix whose first dimension is a multiple of 64). eltype / out_eltype keep
+                                     naming the unpacked type (UInt8 / Bool), the extents stay in cells. */
+#define SB200_FLAG_DST_BITS 512  /* the same for the DEST parent. sb200_iterate and the slab plans keep the state of a Life run packed
+                                     between its first and its last launch by themselves (pack and unpack are half of the instructions of
+                                     a byte-to-byte launch); a binding that keeps a BitMatrix can use the flags directly. */
 #define SB200_FLAG_STEP_MASK 112
 #define SB200_FLAG_GENS(n) ((n) == 2 ? 16 : (n) == 4 ? 32 : (n) == 8 ? 64 : ((n) == 3 || ((n) >= 5 && (n) <= 7)) ? ((n) << 4) : 0)
 #define SB200_FLAG_GENS_OF(flags) ((((flags) >> 4) & 7) == 0 ? 1 : (((flags) >> 4) & 7) == 1 ? 2 : (((flags) >> 4) & 7) == 2 ? 4 : \

@@ -25,6 +25,7 @@ OP_ADD, OP_MAX, OP_MIN = range(3)
 SCATTER_WEIGHTS, SCATTER_CENTER_WEIGHTS = range(2)
 FLAG_FORCE_GENERIC, FLAG_ZERO_DEST, FLAG_NO_TMA, FLAG_CELLS_01, FLAG_DOUBLE_STEP, FLAG_QUAD_STEP, FLAG_OCT_STEP, FLAG_ALLOW_FMA = 1, 2, 4, 8, 16, 32, 64, 128
 FLAG_STEP_MASK = 112
+FLAG_SRC_BITS, FLAG_DST_BITS = 256, 512
 
 
 def flag_gens(n):

@@ -369,6 +369,11 @@ int do_gather(const sb200_desc* d, const void* src, void* dst, cudaStream_t st) 
                   gens, gens > 4 ? " (and a library built with -DSB200_LB_ONE_HALO_LANE=1, the default)" : "");
         return SB200_EUNSUPPORTED;
     }
+    if ((d->flags & (SB200_FLAG_SRC_BITS | SB200_FLAG_DST_BITS)) && !life_multi_accepts(*d, *pl, gens)) {
+        set_error("SB200_FLAG_SRC_BITS / _DST_BITS: packed state is read and written by the bit-sliced Life kernel only (B3/S23, Moore(1), "
+                  "SB200_FLAG_GENS(2 .. 8) — a packed source also one generation —, axis 0 and the packed parents' axis-0 extents multiples of 128 cells, Wrap on axis 0)");
+        return SB200_EUNSUPPORTED;
+    }
     if (gens == 2 && !life2_accepts(*d, *pl) && !diffusion2_accepts(*d, *pl)) {
         set_error("SB200_FLAG_DOUBLE_STEP: only Life / Moore(1) on an unpadded Bool or UInt8 grid with Wrap on axis 0, or "
                   "Diffusion / VonNeumann(1,3) on an unpadded Float32 / Float64 grid with Wrap on axes 0 and 1");
@@ -716,6 +721,67 @@ int32_t sb200_iterate(const sb200_desc* d, void* buf_a, void* buf_b, int32_t nst
         else if (getenv("SB200_OCT_STEP") && atoi(getenv("SB200_OCT_STEP")) == 0) cap = std::min(cap, 4);
         ok_size[2] = accepts(2);
         for (int g = 3; g <= cap && ok_size[2]; g++) ok_size[g] = !(pow2 && (g & (g - 1))) && accepts(g);
+    }
+    // Life runs keep their state PACKED (one bit per cell, SB200_FLAG_SRC_BITS / _DST_BITS) between the first and the last launch:
+    // the first launch reads the bytes of buf_a and writes bits, the last one reads bits and writes the bytes of the buffer the
+    // contract names, every launch in between is packed -> packed (no pack / unpack instructions, 1 / 8 of the memory traffic).
+    // The packed grids live inside the two buffers themselves (each holds eight of them; regions 0 and 1 = the two halves of a
+    // buffer are used), always in the buffer that is neither being read as bytes nor about to receive the final bytes:
+    //   final state in buf_a:  a(bytes) -> b.0 -> b.1 -> b.0 ... -> a(bytes)
+    //   final state in buf_b:  a(bytes) -> b.0 -> a.0 -> a.1 -> a.0 ... -> b(bytes)
+    // so the launch count carries no parity constraint: launches of the best size plus one remainder. The content of the other
+    // buffer after the call is unspecified (as it already is with several generations per launch).
+    // SB200_LIFE_PACKED=0 turns the packed runs off, =1 forces them for grids of any size (default: grids above 4 Mi cells — smaller
+    // ones are launch-bound and replay CUDA graphs below).
+    {
+        long long ncells = 1, region_full = 1;
+        for (int a = 0; a < d->ndim; a++) {
+            ncells *= d->size[a];
+            region_full &= d->region_lo[a] == 0 && (d->region_hi[a] == 0 || d->region_hi[a] == d->size[a]);
+        }
+        const char* e_pk = getenv("SB200_LIFE_PACKED");
+        const bool want_packed = e_pk ? atoi(e_pk) != 0 : ncells > (4LL << 20);
+        if (life && ok_size[8] && want_packed && region_full && nsteps >= 12 && !(d->flags & (SB200_FLAG_SRC_BITS | SB200_FLAG_DST_BITS))) {
+            sb200_desc probe = *d;
+            probe.flags |= SB200_FLAG_GENS(8) | SB200_FLAG_SRC_BITS | SB200_FLAG_DST_BITS;
+            if (multistep_accepts(&probe)) {
+                const size_t half = ((size_t)d->src_ext[0] * (size_t)d->src_ext[1] / 2) & ~(size_t)15;
+                char *A0 = (char*)buf_a, *B0 = (char*)buf_b;
+                const bool final_in_a = (nsteps & 1) == 0;
+                // L = the fewest launches of <= 8 generations (at least two; three when the final bytes go to buf_b, whose first
+                // packed grid must be dead by then), the generations spread evenly over them, smaller launches first
+                const int L = std::max((nsteps + 7) / 8, final_in_a ? 2 : 3);
+                const int base = nsteps / L, extra = nsteps % L;   // L - extra launches of `base`, then `extra` of base + 1
+                const void* from = buf_a;
+                int region = 0;           // region of the buffer that holds the packed state being read next
+                bool in_a = false;        // ... and whether that buffer is buf_a
+                for (int j = 0; j < L; j++) {
+                    const int g = j < L - extra ? base : base + 1;
+                    sb200_desc cur = *d;
+                    cur.flags |= SB200_FLAG_GENS(g);
+                    void* to;
+                    if (j == 0) {                       // bytes of buf_a -> packed, region 0 of buf_b
+                        cur.flags |= SB200_FLAG_DST_BITS;
+                        to = B0; in_a = false; region = 0;
+                    } else if (j == L - 1) {            // packed -> bytes of the final buffer (the packed source is in the other one)
+                        cur.flags |= SB200_FLAG_SRC_BITS;
+                        to = final_in_a ? buf_a : buf_b;
+                    } else {
+                        cur.flags |= SB200_FLAG_SRC_BITS | SB200_FLAG_DST_BITS;
+                        if (in_a == final_in_a) {       // the packed state sits in the final buffer: hop to the other one (second launch only)
+                            in_a = !in_a; region = 0;
+                        } else {
+                            region ^= 1;
+                        }
+                        to = (in_a ? A0 : B0) + (size_t)region * half;
+                    }
+                    const int rc = do_gather(&cur, from, to, (cudaStream_t)stream);
+                    if (rc) return rc;
+                    from = to;
+                }
+                return SB200_OK;
+            }
+        }
     }
     int cnt[kMaxGens + 1];   // launches of 1 .. 8 generations
     split_steps(nsteps, ok_size, life ? kLifeCost : kDiffCost, cnt);

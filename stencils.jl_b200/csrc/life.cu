@@ -18,32 +18,10 @@
 #include <cstdlib>
 #include "common.cuh"
 #include "tma.cuh"
+#include "life_params.cuh"
 
 namespace sb {
 
-struct LifeParams {
-    const uint8_t* src;
-    uint8_t* dst;
-    long long spitch, dpitch;  // bytes per row of the parents
-    int W, H;                  // logical size (axis 0 = W contiguous)
-    int ncols;                 // W / 16
-    int colgroups;             // ceil(ncols / 32)
-    int soff1, doff1;          // ring / ghost rows on axis 1
-    uint8_t* mirror;           // fused ghost push: rows [m_lo, m_hi) are also stored here (row m_lo first), or null
-    int m_lo, m_hi;
-    int bc0, bc1;              // boundary per axis
-    unsigned pad01;            // Remove: (padval != 0)
-    int y_lo, rows;            // output rows [y_lo, y_lo + rows)
-    int nruns;                 // the rows are split into nruns equal runs; a warp owns one (column group, run)
-    unsigned born, survive;
-};
-
-// 0/1 per byte: byte != 0
-__device__ __forceinline__ unsigned nz_bytes(unsigned w) {
-    return ((((w & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | w) >> 7) & 0x01010101u;
-}
-// 0/1 per byte: byte == 0, valid for bytes <= 0x10
-__device__ __forceinline__ unsigned eqz_small(unsigned x) { return ((0x10101010u - x) >> 4) & 0x01010101u; }
 
 struct Row {
     unsigned h0, h1, h2, h3;  // horizontal 3-sums (left + centre + right), per byte
@@ -258,20 +236,6 @@ constexpr int LT_CH = 6;                       // source rows per stage (multipl
 constexpr int LT_STAGES = 4;
 constexpr int LT_SMEM = 128 + LT_STAGES * LT_CH * LT_ROWB;
 
-struct LifeTmaParams {
-    LifeParams lp;
-    int nstrips, nruns;
-    int outb;   // life_tma2_kernel: final cells per strip row (<= LT2_OUTB, a multiple of 128: equal strips)
-};
-
-// source row r (logical) -> parent row, or -1 for a Remove pad row
-__device__ __forceinline__ long long life_map_row(const LifeParams& p, int r) {
-    if (p.soff1 > 0) return (long long)r + p.soff1;
-    if (r >= 0 && r < p.H) return r;
-    if (p.bc1 == SB200_WRAP) return r < 0 ? r + p.H : r - p.H;
-    if (p.bc1 == SB200_REFLECT) return r < 0 ? -r : 2 * (p.H - 1) - r;
-    return -1;
-}
 
 // MIRROR: the fused ghost-row push (LifeParams::mirror) is compiled in only for the boundary sweeps of slab runs.
 template <bool CELLS01, bool CONWAY, bool MIRROR>
@@ -582,292 +546,20 @@ __global__ void __launch_bounds__((LT2_WARPS + 1) * 32, 3) life_tma2_kernel(cons
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// Bit-sliced Conway kernel: G generations per launch with the cells of a row packed ONE BIT each inside the kernel.
-// Memory keeps the reference's one byte per cell; a lane loads 32 cells (two 128-bit shared-memory loads), packs them
-// into one 32-bit word with four multiplies (w * 0x10204080 gathers the four 0/1 bytes of a word into its top nibble),
-// and every logic instruction then advances 32 cells: the horizontal 3-sum of a row is two LOP3 (xor3, majority) on the
-// word and its two one-bit shifts, the 3-row total a 4-bit carry-save sum (8 LOP3/LOP), B3/S23 four more — about 20
-// instructions per 32 cells and generation against ~18 per FOUR cells in the byte-SWAR kernels. The shifted-in edge bits
-// of an intermediate generation come from the adjacent lanes by warp shuffle, so lanes G-1 .. 32-G of a warp own final
-// cells (warps overlap by 2(G-1) lanes). Same TMA ring, same boundary support as life_tma2_kernel; B3/S23 only.
-constexpr int LB_WARPS = 6;
-constexpr int LB_CH = 3;
-constexpr int LB_STAGES = 4;
-constexpr int LB_ROWB = 6144;
-constexpr int LB_SMEM = 128 + LB_STAGES * LB_CH * LB_ROWB;
-// ONE halo lane per side of a warp instead of G - 1 (default since r02a; -DSB200_LB_ONE_HALO_LANE=0 restores the round-1 layout).
-// A wrong edge bit enters an end lane at one cell per generation, so after G <= 32 generations only the end lanes themselves
-// hold wrong cells (tools/model_life_bit_lanes.py emulates the scheme: lanes 1 .. 30 are exact for G = 2 .. 31). With G = 4 that
-// is 30 instead of 26 useful lanes per warp and smaller halos, and it is what makes 8 generations per launch worthwhile (18
-// useful lanes with G - 1 halo lanes). Measured r02a, 16384^2: 8508 (G - 1 halo lanes, 4 generations) -> 9843 (one halo lane,
-// one task per CTA) -> 10773 Gcell-updates/s (8 generations per launch); every Life test bit-identical to the CPU restatement.
-#ifndef SB200_LB_ONE_HALO_LANE
-#define SB200_LB_ONE_HALO_LANE 1
-#endif
-template <int G> struct LbCfg {
-    static constexpr int HLN = SB200_LB_ONE_HALO_LANE ? 1 : G - 1;   // halo lanes per side of a warp
-    static constexpr int VALID = 32 - 2 * HLN;               // lanes of a warp that own final cells
-    static constexpr int WO = VALID * 32;                     // final cells per warp row
-    static constexpr int CAP = LB_WARPS * WO;                 // final cells per strip row (multiple of 128)
-    static constexpr int HL = HLN * 32 + 16;                  // halo bytes per side of a shared-memory row
-    static constexpr int D0 = (128 - HL % 128) % 128;         // data start in a row: global x0 - HL is D0 mod 128
-    static_assert(D0 + 2 * HL + CAP <= LB_ROWB, "row does not fit");
-};
-
-struct BRow { unsigned c, s0, s1; };  // 32 cells, and their horizontal 3-sums (left + centre + right) as two bit planes
-
-__device__ __forceinline__ unsigned lop3_xor3(unsigned a, unsigned b, unsigned c) {
-    unsigned r;
-    asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
-    return r;
-}
-__device__ __forceinline__ unsigned lop3_maj(unsigned a, unsigned b, unsigned c) {
-    unsigned r;
-    asm("lop3.b32 %0, %1, %2, %3, 0xE8;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
-    return r;
-}
-// `prev` / `next` = the words of the 32 cells to the left / right (only their top / bottom bit is used): the one-bit shifts with
-// the neighbour's edge bit shifted in are single funnel shifts (SHF.L.W / SHF.R.W on two registers).
-// SB200_LB_IMAD_SHIFT=1 computes them on the FMA pipe instead (the kernel is bound by the ALU pipe — LOP3 / SHF issue every other
-// cycle per scheduler — while the FMA pipe idles at 7 %): L = w * 2 + hi32(prev * 2), R = hi32(w * 2^31) + next * 2^31, four IMAD /
-// IMAD.HI with the multipliers read from constant memory (an immediate power of two is strength-reduced back to SHF / LEA).
-#ifndef SB200_LB_IMAD_SHIFT
-#define SB200_LB_IMAD_SHIFT 0
-#endif
-__constant__ unsigned lb_mul_consts[7] = {2u, 0x80000000u, 16u, 1u << 28, 1u << 24, 1u << 20, 1u << 16};
-struct LbMul { unsigned two, half, sixteen, un[4]; };
-#ifndef SB200_LB_IMAD_UNPACK
-#define SB200_LB_IMAD_UNPACK 0   // nibble k of a word as hi32((bits << (28 - 4k)) * 16): IMAD + IMAD.HI instead of SHF + LOP3
-#endif
-#ifndef SB200_LB_IMAD_PACK
-#define SB200_LB_IMAD_PACK 0     // acc = acc * 16 + hi32(product * 16): IMAD.HI + IMAD instead of SHF.L.W
-#endif
-__device__ __forceinline__ BRow brow(unsigned w, unsigned prev, unsigned next, const LbMul& m) {
-#if SB200_LB_IMAD_SHIFT
-    unsigned e, f, L, R;
-    asm("mul.hi.u32 %0, %1, %2;" : "=r"(e) : "r"(prev), "r"(m.two));
-    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(L) : "r"(w), "r"(m.two), "r"(e));
-    asm("mul.lo.u32 %0, %1, %2;" : "=r"(f) : "r"(next), "r"(m.half));
-    asm("mad.hi.u32 %0, %1, %2, %3;" : "=r"(R) : "r"(w), "r"(m.half), "r"(f));
-#else
-    const unsigned L = __funnelshift_l(prev, w, 1), R = __funnelshift_r(w, next, 1);
-#endif
-    return BRow{w, lop3_xor3(L, w, R), lop3_maj(L, w, R)};
-}
-// B3/S23 from the rows above, at and below: T = 3x3 total including the centre; alive' = (T == 3) | (centre & T == 4)
-// T = t0 + 2 (u1 + c0) + 4 c1 with t0 / c0 = sum / carry of the three low bit planes and u1 / c1 of the three high ones, so
-//   T == 3  <=>  t0 & (u1 ^ c0) & ~c1          (bit 1 set without a carry into bit 2, no c1)
-//   T == 4  <=>  ~t0 & ~(u1 ^ c0) & (u1 ^ c1)  (u1 == c0: bit 1 clear, carry = u1; exactly one of carry and c1)
-// nine 3-input logic ops instead of the twelve of the ripple form (t1, k1, t2, t3, x, y, ...): the kernel is bound by the ALU pipe.
-// tests/test_kernel_models.py checks the identity over every input combination.
-template <int IMM> __device__ __forceinline__ unsigned lop3_imm(unsigned a, unsigned b, unsigned c) {
-    unsigned r;
-    asm("lop3.b32 %0, %1, %2, %3, %4;" : "=r"(r) : "r"(a), "r"(b), "r"(c), "n"(IMM));
-    return r;
-}
-__device__ __forceinline__ unsigned conway_bits(const BRow& a, const BRow& b, const BRow& n) {
-    const unsigned t0 = lop3_xor3(a.s0, b.s0, n.s0), c0 = lop3_maj(a.s0, b.s0, n.s0);
-    const unsigned u1 = lop3_xor3(a.s1, b.s1, n.s1), c1 = lop3_maj(a.s1, b.s1, n.s1);
-    const unsigned p3 = lop3_imm<0x60>(t0, u1, c0);            // t0 & (u1 ^ c0)
-    const unsigned q4 = lop3_imm<0x09>(t0, u1, c0);            // ~t0 & ~(u1 ^ c0)
-    const unsigned y4 = lop3_imm<0x60>(q4, u1, c1) & b.c;      // T == 4 and the centre is alive
-    return lop3_imm<0xBA>(p3, c1, y4);                         // (p3 & ~c1) | y4
-}
-// The product w * 0x10204080 holds the four 0/1 bytes of w in its top nibble; SHF.L.W (acc:product) << 4 appends exactly that
-// nibble to the accumulator (words 7 .. 0, so that cell 0 ends in bit 0): two instructions per word, no mask.
-template <bool CELLS01> __device__ __forceinline__ unsigned pack32(const uint4& lo, const uint4& hi, const LbMul& m) {
-    unsigned w[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
-    unsigned acc = 0;
-#pragma unroll
-    for (int k = 7; k >= 0; k--) {
-        const unsigned v = CELLS01 ? w[k] : nz_bytes(w[k]);
-#if SB200_LB_IMAD_PACK
-        unsigned nib;
-        asm("mul.hi.u32 %0, %1, %2;" : "=r"(nib) : "r"(v * 0x10204080u), "r"(m.sixteen));
-        asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(acc) : "r"(acc), "r"(m.sixteen), "r"(nib));
-#else
-        acc = __funnelshift_l(v * 0x10204080u, acc, 4);
-#endif
-    }
-    return acc;
-}
-__device__ __forceinline__ unsigned unpack4(unsigned bits, int k, const LbMul& m) {  // cells 4k .. 4k+3 as four 0/1 bytes
-#if SB200_LB_IMAD_UNPACK
-    unsigned nib;
-    asm("mul.hi.u32 %0, %1, %2;" : "=r"(nib) : "r"(bits * m.un[k]), "r"(m.sixteen));   // (bits << (28 - 4k)) >> 28
-    return (nib * 0x00204081u) & 0x01010101u;
-#else
-    return (((bits >> (4 * k)) & 0xFu) * 0x00204081u) & 0x01010101u;
-#endif
-}
-
-template <int G, bool CELLS01>
-__global__ void __launch_bounds__((LB_WARPS + 1) * 32, 3) life_bit_kernel(const LifeTmaParams q) {
-    using C = LbCfg<G>;
-    extern __shared__ __align__(128) uint8_t smem[];
-    const LifeParams& p = q.lp;
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem);
-    uint64_t* empty = full + LB_STAGES;
-    uint8_t* ring = smem + 128;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < LB_STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], LB_WARPS); }
-        mbar_fence_init();
-    }
-    __syncthreads();
-    const int ntasks = q.nstrips * q.nruns;
-    const LbMul mul{lb_mul_consts[0], lb_mul_consts[1], lb_mul_consts[2], {lb_mul_consts[3], lb_mul_consts[4], lb_mul_consts[5], lb_mul_consts[6]}};
-    unsigned k = 0;
-    for (int task = blockIdx.x; task < ntasks; task += gridDim.x) {
-        const int strip = task % q.nstrips, run = task / q.nstrips;
-        const int x0 = strip * q.outb;
-        const int wout = min(q.outb, p.W - x0);
-        const int y0 = p.y_lo + (int)((long long)p.rows * run / q.nruns);
-        const int y1 = p.y_lo + (int)((long long)p.rows * (run + 1) / q.nruns);
-        const int nsrc = y1 - y0 + 2 * G;  // source rows y0-G .. y1+G-1
-        const int nchunks = (nsrc + LB_CH - 1) / LB_CH;
-        if (warp == LB_WARPS) {
-            // ---------------- producer: shared-memory row byte b <-> global column x0 - HL + b (mod W) ----------------
-            if (lane == 0) {
-                const int lin = x0 >= C::HL ? C::HL : 0;
-                const int rin = min(C::HL, p.W - (x0 + wout));
-                const unsigned mlen = lin + wout + rin;
-                const unsigned rowbytes = 2 * C::HL + wout;
-                for (int c = 0; c < nchunks; c++, k++) {
-                    const int slot = k % LB_STAGES;
-                    mbar_wait_producer(&empty[slot], ((k / LB_STAGES) & 1) ^ 1);
-                    uint8_t* sbase = ring + slot * (LB_CH * LB_ROWB);
-                    const int nrows = min(LB_CH, nsrc - c * LB_CH);
-                    mbar_arrive_expect_tx(&full[slot], nrows * rowbytes);
-                    for (int j = 0; j < nrows; j++) {
-                        const uint8_t* g = p.src + life_map_row(p, y0 - G + c * LB_CH + j) * p.spitch;
-                        uint8_t* srow = sbase + j * LB_ROWB + C::D0;
-                        bulk_g2s(srow + C::HL - lin, g + x0 - lin, mlen, &full[slot]);
-                        if (!lin) bulk_g2s(srow, g + p.W - C::HL, C::HL, &full[slot]);                           // wrapped left halo
-                        if (rin < C::HL) bulk_g2s(srow + C::HL + wout + rin, g, C::HL - rin, &full[slot]);        // wrapped right halo
-                    }
-                }
-            } else {
-                k += nchunks;
-            }
-            continue;
-        }
-        // ---------------- consumers ----------------
-        if (warp * C::WO >= wout) {   // no final cell in this warp: keep the ring protocol only
-            for (int c = 0; c < nchunks; c++, k++) {
-                const int slot = k % LB_STAGES;
-                mbar_wait(&full[slot], (k / LB_STAGES) & 1);
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&empty[slot]);
-            }
-            continue;
-        }
-        const int cell0 = warp * C::WO + (lane - C::HLN) * 32;   // first final cell of this lane inside the strip
-        const bool active = lane >= C::HLN && lane <= 31 - C::HLN && cell0 < wout;
-        const unsigned act_mask = __ballot_sync(0xffffffffu, active);
-        const bool st_ok[2] = {((act_mask >> (lane >> 1)) & 1u) != 0, ((act_mask >> (16 + (lane >> 1))) & 1u) != 0};   // my two store slots
-        // destination of the cells of lane 0 (a halo lane: never stored) in output row y0
-        uint8_t* __restrict__ wp = p.dst + (long long)(y0 + p.doff1) * p.dpitch + x0 + warp * C::WO - C::HLN * 32;
-        const int soff = C::D0 + C::HL + cell0;
-        BRow lv[G][3];
-#pragma unroll
-        for (int a = 0; a < G; a++)
-#pragma unroll
-            for (int b = 0; b < 3; b++) lv[a][b] = BRow{0, 0, 0};
-        for (int c = 0; c < nchunks; c++, k++) {
-            const int slot = k % LB_STAGES;
-            mbar_wait(&full[slot], (k / LB_STAGES) & 1);
-            const uint8_t* sbase = ring + slot * (LB_CH * LB_ROWB);
-#pragma unroll
-            for (int J = 0; J < LB_CH; J++) {      // stream index i = c * LB_CH + J, i % 3 == J
-                const int i = c * LB_CH + J;
-                {   // level 0: pack the source row
-                    const uint8_t* t = sbase + J * LB_ROWB + soff;
-                    const uint4 lo = *reinterpret_cast<const uint4*>(t), hi = *reinterpret_cast<const uint4*>(t + 16);
-                    const unsigned w = pack32<CELLS01>(lo, hi, mul);
-                    // edge bits from the adjacent lanes' packed words. With one halo lane per side the outer edge bit of an end lane
-                    // may be anything (the shuffle hands lane 0 / 31 its own word, as at every later level): a wrong bit moves one
-                    // cell per generation and stays inside the end lane, which owns no final cell. The G - 1 halo-lane layout of
-                    // round 1 reads the real halo byte.
-                    unsigned prev = __shfl_up_sync(0xffffffffu, w, 1), next = __shfl_down_sync(0xffffffffu, w, 1);
-#if !SB200_LB_ONE_HALO_LANE
-                    if (lane == 0) prev = t[-1] != 0 ? 0x80000000u : 0u;
-                    if (lane == 31) next = t[32] != 0;
-#endif
-                    lv[0][J] = brow(w, prev, next, mul);
-                }
-#pragma unroll
-                for (int g = 1; g < G; g++) {  // generation g of row i - g from generation g-1 of rows i-g-1, i-g, i-g+1
-                    const unsigned x = conway_bits(lv[g - 1][(J - g - 1 + 9) % 3], lv[g - 1][(J - g + 9) % 3], lv[g - 1][(J - g + 1 + 9) % 3]);
-                    const unsigned prev = __shfl_up_sync(0xffffffffu, x, 1), next = __shfl_down_sync(0xffffffffu, x, 1);
-                    lv[g][(J - g + 9) % 3] = brow(x, prev, next, mul);
-                }
-                if (i >= 2 * G && i < nsrc) {   // generation G of row i - G: the output row y0 + i - 2G
-                    const unsigned y = conway_bits(lv[G - 1][(J - G - 1 + 9) % 3], lv[G - 1][(J - G + 9) % 3], lv[G - 1][(J - G + 1 + 9) % 3]);
-                    // two fully coalesced 512-byte stores per warp row: lane l writes 16 bytes at 16 l of the first / second
-                    // half of the warp's 1 KiB, i.e. half (l & 1) of the cells of lane l/2 resp. 16 + l/2
-#pragma unroll
-                    for (int hb = 0; hb < 2; hb++) {
-                        const int sl = hb * 16 + (lane >> 1);
-                        const unsigned h16 = __shfl_sync(0xffffffffu, y, sl) >> (16 * (lane & 1));
-                        const uint4 cells = make_uint4(unpack4(h16, 0, mul), unpack4(h16, 1, mul), unpack4(h16, 2, mul), unpack4(h16, 3, mul));
-                        if (st_ok[hb]) *reinterpret_cast<uint4*>(wp + hb * 512 + lane * 16) = cells;   // a predicated store, no branch
-                    }
-                    wp += p.dpitch;
-                }
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[slot]);
-        }
-    }
-}
-
-template <int G, bool CELLS01> static int launch_bit(const LifeParams& p, cudaStream_t st) {
-    using C = LbCfg<G>;
-    static thread_local int cfg_dev = -1, ctas_per_sm = 0;
-    int dev = 0;
-    SB_CUDA(cudaGetDevice(&dev));
-    if (dev != cfg_dev) {
-        SB_CUDA(cudaFuncSetAttribute(life_bit_kernel<G, CELLS01>, cudaFuncAttributeMaxDynamicSharedMemorySize, LB_SMEM));
-        int per_sm = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, life_bit_kernel<G, CELLS01>, (LB_WARPS + 1) * 32, LB_SMEM) != cudaSuccess || per_sm < 1)
-            per_sm = 1;
-        ctas_per_sm = per_sm;
-        cfg_dev = dev;
-    }
-    LifeTmaParams q;
-    q.lp = p;
-    q.nstrips = (p.W + C::CAP - 1) / C::CAP;
-    q.outb = std::min(C::CAP, ((p.W + q.nstrips - 1) / q.nstrips + 127) / 128 * 128);  // equal strips
-    q.nstrips = (p.W + q.outb - 1) / q.outb;
-    const long long ctas = (long long)ctas_per_sm * num_sms();
-    // Runs per strip: strips x runs fills whole waves of the resident CTAs (t tasks per CTA); every run re-reads 2 G source
-    // rows, so pick the t that minimises waves x (rows per run + 2 G). Measured r02a (16384^2, three strips, 444 CTAs): one task
-    // per CTA 9843 Gcell-updates/s, a clipped second wave (768 tasks) 8283. SB200_LB_TASKS overrides t for A/B runs.
-    static const int tpc_env = getenv("SB200_LB_TASKS") ? atoi(getenv("SB200_LB_TASKS")) : 0;
-    long long nruns = 1;
-    double best_cost = 1e300;
-    for (int t = (tpc_env > 0 ? tpc_env : 1); t <= (tpc_env > 0 ? tpc_env : 4); t++) {
-        long long r = std::max<long long>(1, t * ctas / q.nstrips);
-        r = std::min<long long>(r, std::max(1, p.rows / (4 * G)));   // at least 4 G rows per run
-        const long long waves = (q.nstrips * r + ctas - 1) / ctas;
-        const double cost = (double)waves * ((double)p.rows / (double)r + 2.0 * G);
-        if (cost < best_cost * 0.999) { best_cost = cost; nruns = r; }
-    }
-    q.nruns = (int)nruns;
-    const long long grid = std::min<long long>(ctas, (long long)q.nstrips * q.nruns);
-    life_bit_kernel<G, CELLS01><<<(unsigned)grid, (LB_WARPS + 1) * 32, LB_SMEM, st>>>(q);
-    return SB200_OK;
-}
-
 // Can this sweep run two generations per launch?
 bool life2_accepts(const sb200_desc& d, const Plan& pl) { return life_multi_accepts(d, pl, 2); }
 
 bool life_multi_accepts(const sb200_desc& d, const Plan& pl, int gens) {
-    if (gens < 2 || gens > 8) return false;
+    if (gens > 8 || gens < ((d.flags & SB200_FLAG_SRC_BITS) ? 1 : 2)) return false;   // a packed source also runs single generations
     if (gens >= 3 && (d.born_mask != (1u << 3) || d.survive_mask != ((1u << 2) | (1u << 3)) || d.size[0] % 32 || getenv("SB200_NO_BITSLICE")))
         return false;   // three and more generations: the bit-sliced B3/S23 kernel only
     if (gens > 4 && !SB200_LB_ONE_HALO_LANE) return false;   // five to eight generations need the one-halo-lane layout
+    if (d.flags & (SB200_FLAG_SRC_BITS | SB200_FLAG_DST_BITS)) {   // packed state: the bit-sliced kernel, rows of whole 16-byte groups
+        if (!SB200_LB_ONE_HALO_LANE || d.born_mask != (1u << 3) || d.survive_mask != ((1u << 2) | (1u << 3)) || getenv("SB200_NO_BITSLICE")) return false;
+        if (d.size[0] % 128) return false;
+        if ((d.flags & SB200_FLAG_SRC_BITS) && d.src_ext[0] % 128) return false;
+        if ((d.flags & SB200_FLAG_DST_BITS) && d.dst_ext[0] % 128) return false;
+    }
     if (d.reducer != SB200_LIFE || d.ndim != 2 || (d.eltype != SB200_BOOL && d.eltype != SB200_U8)) return false;
     if (pl.shape_tag != SB200_MOORE || pl.shape_ndim != 2 || d.radius != 1 || d.noffsets != 8) return false;
     if (d.flags & (SB200_FLAG_NO_TMA | SB200_FLAG_FORCE_GENERIC)) return false;
@@ -909,6 +601,10 @@ template <bool CELLS01, bool CONWAY> static int launch_tma2(const LifeParams& p,
     return SB200_OK;
 }
 
+int launch_life_bit_u8(int gens, bool cells01, const LifeParams& p, cudaStream_t st);        // life_bit_u8.cu
+int launch_life_bit_to_bits(int gens, bool cells01, const LifeParams& p, cudaStream_t st);   // life_bit_pk_a.cu
+int launch_life_bit_from_bits(int gens, bool out_bits, const LifeParams& p, cudaStream_t st); // life_bit_pk_b.cu
+
 int try_life_swar(const Plan& pl, const void* src, void* dst, cudaStream_t st) {
     const sb200_desc& d = pl.d;
     if (d.reducer != SB200_LIFE || d.ndim != 2) return -1;
@@ -937,28 +633,20 @@ int try_life_swar(const Plan& pl, const void* src, void* dst, cudaStream_t st) {
     // step after the first, because the source is then this kernel's own output).
     const bool cells01 = d.eltype == SB200_BOOL || (d.flags & SB200_FLAG_CELLS_01);
     const int gens = SB200_FLAG_GENS_OF(d.flags);
-    if (gens > 2) {   // 3 .. 8 generations: the bit-sliced kernel (5 .. 8 need its one-halo-lane layout, the default build)
-        if (!life_multi_accepts(d, pl, gens)) { set_error("%d generations per sweep: layout / boundary / rule / build not supported", gens); return SB200_EUNSUPPORTED; }
+    const bool src_bits = (d.flags & SB200_FLAG_SRC_BITS) != 0, dst_bits = (d.flags & SB200_FLAG_DST_BITS) != 0;
+    if (dst_bits && !src_bits && gens < 2) { set_error("SB200_FLAG_DST_BITS on a byte source needs SB200_FLAG_GENS(2 .. 8)"); return SB200_EUNSUPPORTED; }
+    if (gens > 2 || src_bits || dst_bits) {   // the bit-sliced kernel (5 .. 8 generations and the packed formats need its one-halo-lane layout, the default build)
+        if (!life_multi_accepts(d, pl, gens)) { set_error("%d generations per sweep%s: layout / boundary / rule / build not supported", gens, src_bits || dst_bits ? " on packed state" : ""); return SB200_EUNSUPPORTED; }
         p.mirror = nullptr; p.m_lo = p.m_hi = 0;
-        int rc = SB200_EUNSUPPORTED;
-        switch (gens) {
-            case 3: rc = cells01 ? launch_bit<3, true>(p, st) : launch_bit<3, false>(p, st); break;
-            case 4: rc = cells01 ? launch_bit<4, true>(p, st) : launch_bit<4, false>(p, st); break;
-#if SB200_LB_ONE_HALO_LANE
-            case 5: rc = cells01 ? launch_bit<5, true>(p, st) : launch_bit<5, false>(p, st); break;
-            case 6: rc = cells01 ? launch_bit<6, true>(p, st) : launch_bit<6, false>(p, st); break;
-            case 7: rc = cells01 ? launch_bit<7, true>(p, st) : launch_bit<7, false>(p, st); break;
-            case 8: rc = cells01 ? launch_bit<8, true>(p, st) : launch_bit<8, false>(p, st); break;
-#endif
-            default: break;
-        }
+        if (src_bits) p.spitch = d.src_ext[0] / 8;   // bytes per packed row
+        if (dst_bits) p.dpitch = d.dst_ext[0] / 8;
+        const int rc = src_bits ? launch_life_bit_from_bits(gens, dst_bits, p, st)
+                                : dst_bits ? launch_life_bit_to_bits(gens, cells01, p, st) : launch_life_bit_u8(gens, cells01, p, st);
         if (rc) return rc;
         SB_LAUNCH_CHECK();
-        static const char* const names[2][6] = {
-            {"life_bit_kernel<3,u8>", "life_bit_kernel<4,u8>", "life_bit_kernel<5,u8>", "life_bit_kernel<6,u8>", "life_bit_kernel<7,u8>", "life_bit_kernel<8,u8>"},
-            {"life_bit_kernel<3,cells01>", "life_bit_kernel<4,cells01>", "life_bit_kernel<5,cells01>", "life_bit_kernel<6,cells01>",
-             "life_bit_kernel<7,cells01>", "life_bit_kernel<8,cells01>"}};
-        set_kernel_name(names[cells01 ? 1 : 0][gens - 3]);
+        static thread_local char name[64];
+        snprintf(name, sizeof(name), "life_bit_kernel<%d,%s%s>", gens, src_bits ? "bits" : cells01 ? "cells01" : "u8", dst_bits ? "->bits" : src_bits ? "->u8" : "");
+        set_kernel_name(name);
         return SB200_OK;
     }
     if (gens == 2) {
@@ -967,7 +655,7 @@ int try_life_swar(const Plan& pl, const void* src, void* dst, cudaStream_t st) {
         int rc;
         if (conway && p.W % 32 == 0 && !getenv("SB200_NO_BITSLICE")) {
             // B3/S23: the bit-sliced kernel (one bit per cell inside the kernel)
-            rc = cells01 ? launch_bit<2, true>(p, st) : launch_bit<2, false>(p, st);
+            rc = launch_life_bit_u8(2, cells01, p, st);
             if (rc) return rc;
             SB_LAUNCH_CHECK();
             set_kernel_name(cells01 ? "life_bit_kernel<2,cells01>" : "life_bit_kernel<2,u8>");

@@ -130,6 +130,33 @@ __global__ void plan_planes_kernel(unsigned char* base, size_t plane_bytes, long
     }
 }
 
+// Packed Life runs (SB200_FLAG_SRC_BITS / _DST_BITS): a plan_iterate call packs the byte parent of every slab once (cell != 0 -> bit
+// c % 32 of word c / 32; rows are multiples of 128 cells, so the parent is one flat array of words), runs every sweep and every
+// exchange on the packed parents, and unpacks the final state once.
+__global__ void plan_pack_kernel(const uint4* __restrict__ src, uint32_t* __restrict__ dst, size_t nwords) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nwords; i += (size_t)gridDim.x * blockDim.x) {
+        const uint4 a = src[2 * i], b = src[2 * i + 1];
+        const unsigned w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        unsigned acc = 0;
+#pragma unroll
+        for (int k = 7; k >= 0; k--) {
+            const unsigned nz = ((((w[k] & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | w[k]) >> 7) & 0x01010101u;   // byte != 0
+            acc = (acc << 4) | ((nz * 0x10204080u) >> 28);
+        }
+        dst[i] = acc;
+    }
+}
+__global__ void plan_unpack_kernel(const uint32_t* __restrict__ src, uint4* __restrict__ dst, size_t nwords) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nwords; i += (size_t)gridDim.x * blockDim.x) {
+        const unsigned v = src[i];
+        unsigned o[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) o[k] = (((v >> (4 * k)) & 0xFu) * 0x00204081u) & 0x01010101u;
+        dst[2 * i] = make_uint4(o[0], o[1], o[2], o[3]);
+        dst[2 * i + 1] = make_uint4(o[4], o[5], o[6], o[7]);
+    }
+}
+
 // Fill `count` elements of `es` bytes with the low bytes of `bits` (Remove ends: ghost planes <- padval).
 __global__ void plan_fill_kernel(unsigned char* p, size_t count, int es, unsigned long long bits) {
     for (size_t j = blockIdx.x * (size_t)blockDim.x + threadIdx.x; j < count; j += (size_t)gridDim.x * blockDim.x) {
@@ -143,6 +170,7 @@ struct Slab {
     int dev = 0;
     long long lo = 0, hi = 0, n = 0, ext = 0;   // owned global planes [lo, hi); parent = [G | n | G]
     void* buf[2] = {nullptr, nullptr};
+    void* pk[2] = {nullptr, nullptr};             // packed parents (Life plans that run packed): ext rows of plane_bytes / 8
     int cur = 0;
     unsigned char* mailbox = nullptr;             // MB_FLAGS + 4 landing slots: (side 0 = from below, side 1 = from above) x parity
     unsigned char* peer_down = nullptr;           // the lower neighbour's mailbox (as addressable from this slab's device)
@@ -168,6 +196,8 @@ struct sb200_plan {
     size_t plane_bytes = 0, es = 0;
     bool rank_form = false, use_flags = false, overlap = false, split_wrap = true;
     bool fused_xfer = false;            // flag form with 16-byte aligned zones: push + publish / wait + ghost copy as one kernel each
+    bool packed = false;                // Life: sweeps and exchanges of a plan_iterate call run on packed parents (one bit per cell)
+    bool run_packed = false;            // ... and the interpreter is inside such a call right now
     int rank = 0, world = 1;
     int later_flags = 0;
     std::vector<Slab> slabs;
@@ -198,7 +228,7 @@ static sb200_desc sweep_desc(const sb200_plan* p, long long ext, long long lo, l
     d.boundary[last] = SB200_WRAP;   // never exercised: the output region stays R * gens planes inside the parent
     for (int a = 0; a < 3; a++) { d.region_lo[a] = 0; d.region_hi[a] = a < p->ndim ? d.size[a] : 0; }
     d.region_lo[last] = lo; d.region_hi[last] = hi;
-    d.flags = (first ? 0 : p->later_flags) | SB200_FLAG_GENS(gens);
+    d.flags = (first ? 0 : p->later_flags) | SB200_FLAG_GENS(gens) | (p->run_packed ? SB200_FLAG_SRC_BITS | SB200_FLAG_DST_BITS : 0);
     d.mirror_parent = nullptr; d.mirror_lo = d.mirror_hi = 0;
     d.offsets_host = p->offsets.data();
     d.weights_host = p->weights.empty() ? nullptr : p->weights.data();
@@ -337,6 +367,30 @@ static int plan_make_sched(sb200_plan* p, const std::vector<long long>& exts, in
         for (int m : order)
             if (m <= p->k && c.accept((long long)p->R * m, -(long long)p->R * m, m)) c.sizes.push_back(m);
     }
+    // Packed runs: Life on a ring (Remove / Reflect ends would need packed end fills), rows of whole 128-cell groups, and the
+    // full-width sweep of every size in use accepted with packed parents. SB200_LIFE_PACKED=0 turns them off.
+    p->packed = false;
+    if (mg >= 2 && p->g.reducer == SB200_LIFE && p->split_wrap && p->plane_bytes % 16 == 0 && !p->overlap &&
+        !(getenv("SB200_LIFE_PACKED") && atoi(getenv("SB200_LIFE_PACKED")) == 0)) {
+        p->run_packed = true;   // sweep_desc adds the packed flags
+        bool ok = true;
+        for (int m = 2; m <= mg && ok; m++)
+            if (c.sizes.empty() ? (m & (m - 1)) == 0 : std::find(c.sizes.begin(), c.sizes.end(), m) != c.sizes.end())
+                ok = c.accept((long long)p->R * m, -(long long)p->R * m, m);
+        p->run_packed = false;
+        p->packed = ok;
+    }
+    if (p->packed) {
+        DevGuard guard;
+        for (Slab& s : p->slabs) {
+            SB_CUDA(cudaSetDevice(s.dev));
+            const size_t bytes = (size_t)s.ext * p->plane_bytes / 8;
+            for (int b = 0; b < 2; b++) {
+                SB_CUDA(cudaMalloc(&s.pk[b], bytes));
+                SB_CUDA(cudaMemset(s.pk[b], 0, bytes));
+            }
+        }
+    }
     c.max_gens = mg;
     p->max_gens = mg;
     p->sched = new SlabSched(c);
@@ -348,6 +402,7 @@ static void slab_free(Slab& s) {
     if (s.peer_down_ipc && s.peer_down) cudaIpcCloseMemHandle(s.peer_down);
     if (s.peer_up_ipc && s.peer_up && s.peer_up != s.peer_down) cudaIpcCloseMemHandle(s.peer_up);
     for (int b = 0; b < 2; b++) if (s.buf[b]) cudaFree(s.buf[b]);
+    for (int b = 0; b < 2; b++) if (s.pk[b]) cudaFree(s.pk[b]);
     if (s.mailbox) cudaFree(s.mailbox);
     if (s.compute) cudaStreamDestroy(s.compute);
     if (s.comm) cudaStreamDestroy(s.comm);
@@ -395,9 +450,9 @@ static int end_fill(sb200_plan* p, Slab& s, void* buf, cudaStream_t st) {
 static int exec_op(sb200_plan* p, Slab& s, const sb200_slab_op& o) {
     SB_CUDA(cudaSetDevice(s.dev));
     const int G = p->G;
-    const size_t pb = p->plane_bytes, gb = pb * (size_t)G;
-    void* cur = s.buf[s.cur];
-    void* nxt = s.buf[1 - s.cur];
+    const size_t pb = p->run_packed ? p->plane_bytes / 8 : p->plane_bytes, gb = pb * (size_t)G;
+    void* cur = p->run_packed ? s.pk[s.cur] : s.buf[s.cur];
+    void* nxt = p->run_packed ? s.pk[1 - s.cur] : s.buf[1 - s.cur];
     switch (o.kind) {
     case SB200_SLAB_SWEEP: {
         const long long lo = abs_plane(o.lo, s.ext), hi = abs_plane(o.hi, s.ext);
@@ -505,14 +560,34 @@ static int plan_run(sb200_plan* p, int nsteps) {
     if (nsteps < 0) { set_error("negative step count"); return SB200_EINVAL; }
     if (p->rank_form && p->world > 1 && !p->connected) { set_error("sb200_plan_connect has not been called"); return SB200_EINVAL; }
     std::vector<sb200_slab_op> ops;
+    const bool packed = p->packed && nsteps >= 2;
+    p->run_packed = packed;   // the scheduler's acceptance probes see the descriptors the sweeps will use
     p->sched->plan(nsteps, ops);
+    p->run_packed = false;
     DevGuard guard;
-    // op by op over all slabs: in the event-ordered form a slab's PULL must be enqueued after its neighbours' SIGNAL
-    for (const sb200_slab_op& o : ops)
+    auto convert = [&](bool pack) -> int {
         for (Slab& s : p->slabs) {
-            const int rc = exec_op(p, s, o);
-            if (rc) return rc;
+            SB_CUDA(cudaSetDevice(s.dev));
+            const size_t nwords = (size_t)s.ext * p->plane_bytes / 32;
+            const unsigned blocks = (unsigned)std::min<size_t>((nwords + 255) / 256, (size_t)num_sms() * 16);
+            if (pack) plan_pack_kernel<<<blocks, 256, 0, s.compute>>>((const uint4*)s.buf[s.cur], (uint32_t*)s.pk[s.cur], nwords);
+            else plan_unpack_kernel<<<blocks, 256, 0, s.compute>>>((const uint32_t*)s.pk[s.cur], (uint4*)s.buf[s.cur], nwords);
+            SB_LAUNCH_CHECK();
         }
+        return SB200_OK;
+    };
+    int rc = SB200_OK;
+    if (packed && (rc = convert(true))) return rc;
+    p->run_packed = packed;
+    // op by op over all slabs: in the event-ordered form a slab's PULL must be enqueued after its neighbours' SIGNAL
+    for (const sb200_slab_op& o : ops) {
+        for (Slab& s : p->slabs)
+            if ((rc = exec_op(p, s, o))) break;
+        if (rc) break;
+    }
+    p->run_packed = false;
+    if (rc) return rc;
+    if (packed && (rc = convert(false))) return rc;
     p->steps += nsteps;
     return SB200_OK;
 }

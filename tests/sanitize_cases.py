@@ -222,6 +222,10 @@ def main():
         for n in (3, 6, 7):
             gather_case(f"life 1024x96 wrap, {n} generations (bit-sliced)", g, moore, 1, WR, A.LIFE, flags=A.flag_gens(n))
     gather_case("life 1024x96 wrap, iterate x21", g, moore, 1, WR, A.LIFE, nsteps=21)
+    os.environ["SB200_LIFE_PACKED"] = "1"   # packed runs on a small grid: byte -> bits, bits -> bits, bits -> byte launches
+    gather_case("life 1024x96 wrap, iterate x41 with the state packed between the launches", g, moore, 1, WR, A.LIFE, nsteps=41)
+    gather_case("life 1024x96 wrap, iterate x58 with the state packed between the launches", g, moore, 1, WR, A.LIFE, nsteps=58)
+    del os.environ["SB200_LIFE_PACKED"]
     gather_case("life 1024x96 wrap, no TMA", g, moore, 1, WR, A.LIFE, flags=A.FLAG_NO_TMA)
     if full:
         gather_case("life 8192x40 wrap/reflect, four generations", rand(rng, (8192, 40), np.uint8), moore, 1, (WR, RF), A.LIFE, flags=A.FLAG_QUAD_STEP)

@@ -800,6 +800,94 @@ def test_life_any_generations_per_launch(orc, gens):
     assert l.sb200_gather(h3.ptr(), fa.data_ptr(), fb.data_ptr(), stream()) == A.EUNSUPPORTED
 
 
+@pytest.mark.parametrize("gens", [1, 2, 3, 5, 8])
+def test_life_packed_state(orc, gens):
+    """SB200_FLAG_SRC_BITS / SB200_FLAG_DST_BITS (include/stencils_b200.h): the Life state one bit per cell — row r of a packed parent
+    starts at byte r * ext[0] / 8, cell c is bit c % 8 of byte c / 8 (np.packbits(..., bitorder="little") along axis 0). Byte -> packed,
+    packed -> packed and packed -> byte launches of `gens` generations against the oracle's single sweeps on the byte grid: Wrap and
+    Reflect on axis 1, an interior region, cells that are not 0 / 1 on the byte side; and the refusals."""
+    import torch
+    from tests.util import stream, sync, to_dev
+    rng = np.random.default_rng(640 + gens)
+    l = A.lib()
+    moore = npr.offsets("Moore", 1, 2)
+    fl = A.flag_gens(gens)
+
+    def pack(a):      # (W, H) 0/1 -> (W / 8, H) bytes, the packed parent
+        return np.asfortranarray(np.packbits(np.asfortranarray(a != 0), axis=0, bitorder="little"))
+
+    def run(h, src_np, dst_np):
+        ts, td = to_dev(src_np), to_dev(dst_np)
+        A.check(l.sb200_gather(h.ptr(), ts.data_ptr(), td.data_ptr(), stream()))
+        sync()
+        return np.asfortranarray(td.cpu().numpy().T)
+
+    for (W, H), bc1 in [((1024, 96), A.WRAP), ((3840 + 512, 67), A.WRAP), ((4096, 40), A.REFLECT), ((16384, 48), A.WRAP)]:
+        g = np.asfortranarray(((rng.random((W, H)) < 0.4) * rng.integers(1, 255, size=(W, H))).astype(np.uint8))
+        kw = dict(size=(W, H), eltype=A.U8, out_eltype=A.U8, offsets=moore, radius=1, boundary=(A.WRAP, bc1), reducer=A.LIFE)
+        h1 = build_desc(**kw)
+        want = g
+        for _ in range(gens):
+            want = orc.gather(h1, want, dst_like(h1))
+        zeros_b = np.zeros((W // 8, H), dtype=np.uint8, order="F")
+        # byte -> packed (two generations and more; a packed source also runs single generations)
+        if gens >= 2:
+            got = run(build_desc(flags=fl | A.FLAG_DST_BITS, **kw), g, zeros_b)
+            assert l.sb200_last_kernel() == b"life_bit_kernel<%d,u8->bits>" % gens
+            bits_equal(got, pack(want))
+        # packed -> packed, packed -> byte
+        got = run(build_desc(flags=fl | A.FLAG_SRC_BITS | A.FLAG_DST_BITS, **kw), pack(g), zeros_b)
+        assert l.sb200_last_kernel() == b"life_bit_kernel<%d,bits->bits>" % gens
+        bits_equal(got, pack(want))
+        got = run(build_desc(flags=fl | A.FLAG_SRC_BITS, **kw), pack(g), dst_like(h1))
+        assert l.sb200_last_kernel() == b"life_bit_kernel<%d,bits->u8>" % gens
+        bits_equal(got, want)
+        # an interior region (the sweeps of the slab plans): everything outside stays as it was
+        reg = dict(region=((0, gens, 0), (W, H - gens, 0)))
+        got = run(build_desc(flags=fl | A.FLAG_SRC_BITS | A.FLAG_DST_BITS, **reg, **kw), pack(g), np.full((W // 8, H), 0x5A, dtype=np.uint8, order="F"))
+        want_r = np.full((W // 8, H), 0x5A, dtype=np.uint8, order="F")
+        want_r[:, gens:H - gens] = pack(want)[:, gens:H - gens]
+        bits_equal(got, want_r)
+    # refusals: a width that is not a multiple of 128 cells, one generation, another reducer, another rule
+    W, H = 1024 + 32, 64
+    ta, tb = torch.zeros(W * H, dtype=torch.uint8, device="cuda"), torch.zeros(W * H, dtype=torch.uint8, device="cuda")
+    kw = dict(size=(W, H), eltype=A.U8, out_eltype=A.U8, offsets=moore, radius=1, boundary=A.WRAP, reducer=A.LIFE)
+    assert l.sb200_gather(build_desc(flags=fl | A.FLAG_SRC_BITS | A.FLAG_DST_BITS, **kw).ptr(), ta.data_ptr(), tb.data_ptr(), stream()) == A.EUNSUPPORTED
+    kw = dict(kw, size=(1024, 64))
+    assert l.sb200_gather(build_desc(flags=A.FLAG_DST_BITS, **kw).ptr(), ta.data_ptr(), tb.data_ptr(), stream()) == A.EUNSUPPORTED
+    assert l.sb200_gather(build_desc(flags=fl | A.FLAG_SRC_BITS, **dict(kw, born_mask=(1 << 3) | (1 << 6))).ptr(), ta.data_ptr(), tb.data_ptr(),
+                          stream()) == A.EUNSUPPORTED
+    assert l.sb200_gather(build_desc(flags=fl | A.FLAG_SRC_BITS, **dict(kw, reducer=A.MAX)).ptr(), ta.data_ptr(), tb.data_ptr(),
+                          stream()) == A.EUNSUPPORTED
+
+
+def test_iterate_packed_runs(orc, monkeypatch):
+    """sb200_iterate keeps Life runs of >= 12 generations packed between the first and the last launch (bytes -> bits ... bits ->
+    bytes, the packed grids inside the two buffers themselves). SB200_LIFE_PACKED=1 forces the path for a small grid: step counts of
+    every residue mod 8 and both parities land in the buffer the contract names, bit-identical to the oracle; UInt8 cells that
+    are not 0 / 1 and Bool cells; Reflect on axis 1; a width the packed kernels refuse falls back to byte launches."""
+    from tests.util import stream, sync, to_dev, to_host
+    rng = np.random.default_rng(61)
+    l = A.lib()
+    moore = npr.offsets("Moore", 1, 2)
+    monkeypatch.setenv("SB200_LIFE_PACKED", "1")
+    for (W, H), bc1, et in [((1024, 80), A.WRAP, np.uint8), ((2048, 50), A.REFLECT, np.uint8), ((1280, 64), A.WRAP, np.bool_), ((1024 + 32, 64), A.WRAP, np.uint8)]:
+        alive = rng.random((W, H)) < 0.4
+        g = np.asfortranarray(alive if et is np.bool_ else (alive * rng.integers(1, 255, size=(W, H))).astype(np.uint8))
+        e = A.ELTYPE_OF_DTYPE[np.dtype(et)]
+        h1 = build_desc(size=(W, H), eltype=e, out_eltype=e, offsets=moore, radius=1, boundary=(A.WRAP, bc1), reducer=A.LIFE)
+        want, done = g.copy(order="F"), 0
+        for n in (12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 22, 23, 24, 25, 31, 32, 33, 47, 64, 101):
+            while done < n:
+                want = orc.gather(h1, want, dst_like(h1))
+                done += 1
+            ta, tb = to_dev(g), to_dev(np.full_like(g, 1, order="F"))
+            A.check(l.sb200_iterate(h1.ptr(), ta.data_ptr(), tb.data_ptr(), n, stream()))
+            sync()
+            assert (b"bits->u8" in l.sb200_last_kernel()) == (W % 128 == 0), l.sb200_last_kernel()
+            bits_equal(to_host(ta if n % 2 == 0 else tb, g.shape, g.dtype), want)
+
+
 def test_iterate_every_step_count(orc):
     """sb200_iterate splits a run into launches of 1 .. 8 generations (split_steps in csrc/api.cu): every step count 0 .. 40 plus
     a few long ones lands in the buffer the contract names, bit-identical to the oracle's single steps, with the launch count

@@ -63,7 +63,7 @@ def test_life_bit_lane_scheme_needs_one_halo_lane():
 def test_life_bit_strip_decomposition_covers_every_column_once():
     """launch_bit's strips / warps / lanes for the measured layout (G - 1 halo lanes) and the one-halo-lane experiment."""
     m = _load("model_life_bit_lanes")
-    cu = open(os.path.join(ROOT, "stencils.jl_b200", "csrc", "life.cu")).read()
+    cu = open(os.path.join(ROOT, "stencils.jl_b200", "csrc", "life_bit.cuh")).read()
     assert "constexpr int LB_WARPS = 6;" in cu and "constexpr int LB_ROWB = 6144;" in cu
     assert "static constexpr int HL = HLN * 32 + 16;" in cu and "static constexpr int VALID = 32 - 2 * HLN;" in cu
     for W in (1024, 4352, 16384):
@@ -73,13 +73,13 @@ def test_life_bit_strip_decomposition_covers_every_column_once():
 
 
 def test_life_bit_conway_identity_matches_the_kernel_source():
-    """conway_bits in csrc/life.cu evaluates B3/S23 from the bit-sliced row sums with four immediate LOP3 tables (0x60, 0x09,
+    """conway_bits in csrc/life_bit.cuh evaluates B3/S23 from the bit-sliced row sums with four immediate LOP3 tables (0x60, 0x09,
     0x60, 0xBA). The tables are read out of the CUDA source and evaluated over every input combination against the rule
     itself: alive' = (T == 3) | (centre & T == 4), T = the 3 x 3 total including the centre."""
     import itertools
     import os
     import re
-    src = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "stencils.jl_b200", "csrc", "life.cu")).read()
+    src = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "stencils.jl_b200", "csrc", "life_bit.cuh")).read()
     body = src[src.index("__device__ __forceinline__ unsigned conway_bits"):]
     body = body[:body.index("\n}") + 2]
     imms = [int(v, 16) for v in re.findall(r"lop3_imm<(0x[0-9A-Fa-f]+)>", body)]
