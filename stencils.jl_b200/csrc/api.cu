@@ -523,6 +523,9 @@ namespace sb {
 // (one generation, life_tma_kernel), 107.7, 110.4, 108.6, 101.2, 111.3, 124.2, 137.8 (two .. eight, life_bit_kernel<G>): eight
 // generations per launch is the best rate, 15.6 Tcell-updates/s; diffusion: the two-step kernel runs at 1.45x the single-step rate).
 const double kLifeLaunchCost[kMaxGens + 1] = {0, 1.00, 1.13, 1.16, 1.14, 1.07, 1.17, 1.31, 1.45};
+// packed -> packed launches, us (r02y): 30.5, 37.6, 45.7, 52.4, 62.2, 72.4, 86.6, 98.9 — six generations per launch is the best rate
+// (22.2 Tcell-updates/s; 21.7 for seven and eight)
+const double kLifePackedLaunchCost[kMaxGens + 1] = {0, 30.5, 37.6, 45.7, 52.4, 62.2, 72.4, 86.6, 98.9};
 }  // namespace sb
 
 extern "C" {
@@ -748,9 +751,11 @@ int32_t sb200_iterate(const sb200_desc* d, void* buf_a, void* buf_b, int32_t nst
                 const size_t half = ((size_t)d->src_ext[0] * (size_t)d->src_ext[1] / 2) & ~(size_t)15;
                 char *A0 = (char*)buf_a, *B0 = (char*)buf_b;
                 const bool final_in_a = (nsteps & 1) == 0;
-                // L = the fewest launches of <= 8 generations (at least two; three when the final bytes go to buf_b, whose first
+                // L = the fewest launches of <= kLifePackedBulkGens generations (at least two; three when the final bytes go to buf_b, whose first
                 // packed grid must be dead by then), the generations spread evenly over them, smaller launches first
-                const int L = std::max((nsteps + 7) / 8, final_in_a ? 2 : 3);
+                const char* e_g = getenv("SB200_LIFE_PACKED_GENS");   // A/B: the largest launch size of a packed run (default: the best measured)
+                const int gmax = e_g ? std::min(8, std::max(2, atoi(e_g))) : kLifePackedBulkGens;
+                const int L = std::max((nsteps + gmax - 1) / gmax, final_in_a ? 2 : 3);
                 const int base = nsteps / L, extra = nsteps % L;   // L - extra launches of `base`, then `extra` of base + 1
                 const void* from = buf_a;
                 int region = 0;           // region of the buffer that holds the packed state being read next

@@ -194,6 +194,9 @@ bool multistep_accepts(const sb200_desc* d);
 // and the size with the least time per generation (what long runs and the slab plans' cycles are made of).
 constexpr int kMaxGens = 8;
 extern const double kLifeLaunchCost[kMaxGens + 1];
+// the same for packed -> packed launches (life_bit_kernel<G, bits, bits>), and the size packed runs are made of
+extern const double kLifePackedLaunchCost[kMaxGens + 1];
+constexpr int kLifePackedBulkGens = 6;
 inline int life_bulk_gens() {
     int best = 1;
     for (int g = 2; g <= kMaxGens; g++)

@@ -74,8 +74,10 @@ __device__ __forceinline__ BRow brow(unsigned w, unsigned prev, unsigned next, c
 // T = t0 + 2 (u1 + c0) + 4 c1 with t0 / c0 = sum / carry of the three low bit planes and u1 / c1 of the three high ones, so
 //   T == 3  <=>  t0 & (u1 ^ c0) & ~c1          (bit 1 set without a carry into bit 2, no c1)
 //   T == 4  <=>  ~t0 & ~(u1 ^ c0) & (u1 ^ c1)  (u1 == c0: bit 1 clear, carry = u1; exactly one of carry and c1)
-// nine 3-input logic ops instead of the twelve of the ripple form (t1, k1, t2, t3, x, y, ...): the kernel is bound by the ALU pipe.
-// tests/test_kernel_models.py checks the identity over every input combination.
+// so alive' = t0 ? (u1 ^ c0) & ~c1 : ~(u1 ^ c0) & (u1 ^ c1) & centre: two tables over (u1, c0, c1), the centre AND and one select —
+// EIGHT logic ops for the 3-row total and the rule (round 1's ripple form took twelve, round 2's first table form nine): every
+// instruction counts, the packed launches are bound by instruction issue. tests/test_kernel_models.py checks the identity over
+// every input combination with the tables read out of this source.
 template <int IMM> __device__ __forceinline__ unsigned lop3_imm(unsigned a, unsigned b, unsigned c) {
     unsigned r;
     asm("lop3.b32 %0, %1, %2, %3, %4;" : "=r"(r) : "r"(a), "r"(b), "r"(c), "n"(IMM));
@@ -84,10 +86,9 @@ template <int IMM> __device__ __forceinline__ unsigned lop3_imm(unsigned a, unsi
 __device__ __forceinline__ unsigned conway_bits(const BRow& a, const BRow& b, const BRow& n) {
     const unsigned t0 = lop3_xor3(a.s0, b.s0, n.s0), c0 = lop3_maj(a.s0, b.s0, n.s0);
     const unsigned u1 = lop3_xor3(a.s1, b.s1, n.s1), c1 = lop3_maj(a.s1, b.s1, n.s1);
-    const unsigned p3 = lop3_imm<0x60>(t0, u1, c0);            // t0 & (u1 ^ c0)
-    const unsigned q4 = lop3_imm<0x09>(t0, u1, c0);            // ~t0 & ~(u1 ^ c0)
-    const unsigned y4 = lop3_imm<0x60>(q4, u1, c1) & b.c;      // T == 4 and the centre is alive
-    return lop3_imm<0xBA>(p3, c1, y4);                         // (p3 & ~c1) | y4
+    const unsigned a3 = lop3_imm<0x14>(u1, c0, c1);            // (u1 ^ c0) & ~c1: T == 3 once t0 is set
+    const unsigned b4 = lop3_imm<0x42>(u1, c0, c1) & b.c;      // ~(u1 ^ c0) & (u1 ^ c1): T == 4 once t0 is clear; and the centre is alive
+    return lop3_imm<0xCA>(t0, a3, b4);                         // t0 ? a3 : b4
 }
 // The product w * 0x10204080 holds the four 0/1 bytes of w in its top nibble; SHF.L.W (acc:product) << 4 appends exactly that
 // nibble to the accumulator (words 7 .. 0, so that cell 0 ends in bit 0): two instructions per word, no mask.
@@ -125,11 +126,24 @@ __device__ __forceinline__ unsigned unpack4(unsigned bits, int k, const LbMul& m
 // unpack, and the launches in between move W * H / 8 bytes each way instead of W * H.
 enum { LB_U8 = 0, LB_U8_01 = 1, LB_BITS = 2 };
 constexpr int LB_HLB = 16;   // packed rows: halo bytes per side of a strip (128 cells: bulk copies move multiples of 16 bytes)
+constexpr int LB_ROWB_PK = 768;   // shared-memory row of a packed source: 16 + 5760 / 8 + 16 = 752 bytes
+template <int IN> constexpr int lb_rowb() { return IN == LB_BITS ? LB_ROWB_PK : LB_ROWB; }
+template <int IN> constexpr int lb_smem() { return 128 + LB_STAGES * LB_CH * lb_rowb<IN>(); }
+// Resident CTAs per SM the kernel is compiled for. Byte launches: 3 (74 KB of ring each, <= 96 registers). Packed -> packed launches
+// have a 9 KB ring, so the registers decide: 9 G state registers + temporaries fit 4 CTAs (<= 72 registers) up to G = 6 and 5 CTAs
+// (<= 56) up to G = 4; more resident warps hide the latency of the dependent LOP3 chains. SB200_LB_PK_CTAS=0 keeps 3 everywhere.
+#ifndef SB200_LB_PK_CTAS
+#define SB200_LB_PK_CTAS 1
+#endif
+template <int G, int IN, bool OUT_BITS> constexpr int lb_min_ctas() {
+    return (SB200_LB_PK_CTAS && IN == LB_BITS && OUT_BITS) ? (G <= 4 ? 5 : G <= 6 + (SB200_LB_PK_CTAS > 1 ? SB200_LB_PK_CTAS - 1 : 0) ? 4 : 3) : 3;
+}
 
 template <int G, int IN, bool OUT_BITS>
-__global__ void __launch_bounds__((LB_WARPS + 1) * 32, 3) life_bit_kernel(const LifeTmaParams q) {
+__global__ void __launch_bounds__((LB_WARPS + 1) * 32, lb_min_ctas<G, IN, OUT_BITS>()) life_bit_kernel(const LifeTmaParams q) {
     using C = LbCfg<G>;
     constexpr bool CELLS01 = IN == LB_U8_01;
+    constexpr int ROWB = lb_rowb<IN>();
     static_assert((IN != LB_BITS && !OUT_BITS) || SB200_LB_ONE_HALO_LANE, "the packed formats use the one-halo-lane layout");
     extern __shared__ __align__(128) uint8_t smem[];
     const LifeParams& p = q.lp;
@@ -167,12 +181,12 @@ __global__ void __launch_bounds__((LB_WARPS + 1) * 32, 3) life_bit_kernel(const 
                 for (int c = 0; c < nchunks; c++, k++) {
                     const int slot = k % LB_STAGES;
                     mbar_wait_producer(&empty[slot], ((k / LB_STAGES) & 1) ^ 1);
-                    uint8_t* sbase = ring + slot * (LB_CH * LB_ROWB);
+                    uint8_t* sbase = ring + slot * (LB_CH * ROWB);
                     const int nrows = min(LB_CH, nsrc - c * LB_CH);
                     mbar_arrive_expect_tx(&full[slot], nrows * rowbytes);
                     for (int j = 0; j < nrows; j++) {
                         const uint8_t* g = p.src + life_map_row(p, y0 - G + c * LB_CH + j) * p.spitch;
-                        uint8_t* srow = sbase + j * LB_ROWB + D0x;
+                        uint8_t* srow = sbase + j * ROWB + D0x;
                         bulk_g2s(srow + HLx - lin, g + xb - lin, mlen, &full[slot]);
                         if (!lin) bulk_g2s(srow, g + Wb - HLx, HLx, &full[slot]);                           // wrapped left halo
                         if (rin < HLx) bulk_g2s(srow + HLx + wb + rin, g, HLx - rin, &full[slot]);          // wrapped right halo
@@ -200,6 +214,8 @@ __global__ void __launch_bounds__((LB_WARPS + 1) * 32, 3) life_bit_kernel(const 
         // destination of the cells of lane 0 (a halo lane: never stored) in output row y0; packed dest: of this lane's own word
         uint8_t* __restrict__ wp = OUT_BITS ? p.dst + (long long)(y0 + p.doff1) * p.dpitch + ((x0 + warp * C::WO) >> 3) + (lane - C::HLN) * 4
                                             : p.dst + (long long)(y0 + p.doff1) * p.dpitch + x0 + warp * C::WO - C::HLN * 32;
+        long long dpitch = p.dpitch;
+        asm volatile("" : "+l"(dpitch));   // keep the pitch in registers: ptxas otherwise reloads it from the constant bank every row (LDCU + long-scoreboard stall)
         const int soff = IN == LB_BITS ? LB_HLB + ((warp * C::WO) >> 3) + (lane - C::HLN) * 4 : C::D0 + C::HL + cell0;
         BRow lv[G][3];
 #pragma unroll
@@ -209,12 +225,12 @@ __global__ void __launch_bounds__((LB_WARPS + 1) * 32, 3) life_bit_kernel(const 
         for (int c = 0; c < nchunks; c++, k++) {
             const int slot = k % LB_STAGES;
             mbar_wait(&full[slot], (k / LB_STAGES) & 1);
-            const uint8_t* sbase = ring + slot * (LB_CH * LB_ROWB);
+            const uint8_t* sbase = ring + slot * (LB_CH * ROWB);
 #pragma unroll
             for (int J = 0; J < LB_CH; J++) {      // stream index i = c * LB_CH + J, i % 3 == J
                 const int i = c * LB_CH + J;
                 {   // level 0: pack the source row (or load it packed)
-                    const uint8_t* t = sbase + J * LB_ROWB + soff;
+                    const uint8_t* t = sbase + J * ROWB + soff;
                     unsigned w;
                     if constexpr (IN == LB_BITS) {
                         w = *reinterpret_cast<const unsigned*>(t);
@@ -254,7 +270,7 @@ __global__ void __launch_bounds__((LB_WARPS + 1) * 32, 3) life_bit_kernel(const 
                         if (st_ok[hb]) *reinterpret_cast<uint4*>(wp + hb * 512 + lane * 16) = cells;   // a predicated store, no branch
                     }
                     }
-                    wp += p.dpitch;
+                    wp += dpitch;
                 }
             }
             __syncwarp();
@@ -269,9 +285,9 @@ template <int G, int IN, bool OUT_BITS> static int launch_bit(const LifeParams& 
     int dev = 0;
     SB_CUDA(cudaGetDevice(&dev));
     if (dev != cfg_dev) {
-        SB_CUDA(cudaFuncSetAttribute(life_bit_kernel<G, IN, OUT_BITS>, cudaFuncAttributeMaxDynamicSharedMemorySize, LB_SMEM));
+        SB_CUDA(cudaFuncSetAttribute(life_bit_kernel<G, IN, OUT_BITS>, cudaFuncAttributeMaxDynamicSharedMemorySize, lb_smem<IN>()));
         int per_sm = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, life_bit_kernel<G, IN, OUT_BITS>, (LB_WARPS + 1) * 32, LB_SMEM) != cudaSuccess || per_sm < 1)
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, life_bit_kernel<G, IN, OUT_BITS>, (LB_WARPS + 1) * 32, lb_smem<IN>()) != cudaSuccess || per_sm < 1)
             per_sm = 1;
         ctas_per_sm = per_sm;
         cfg_dev = dev;
@@ -297,7 +313,7 @@ template <int G, int IN, bool OUT_BITS> static int launch_bit(const LifeParams& 
     }
     q.nruns = (int)nruns;
     const long long grid = std::min<long long>(ctas, (long long)q.nstrips * q.nruns);
-    life_bit_kernel<G, IN, OUT_BITS><<<(unsigned)grid, (LB_WARPS + 1) * 32, LB_SMEM, st>>>(q);
+    life_bit_kernel<G, IN, OUT_BITS><<<(unsigned)grid, (LB_WARPS + 1) * 32, lb_smem<IN>(), st>>>(q);
     return SB200_OK;
 }
 

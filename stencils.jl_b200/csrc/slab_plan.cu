@@ -379,6 +379,8 @@ static int plan_make_sched(sb200_plan* p, const std::vector<long long>& exts, in
                 ok = c.accept((long long)p->R * m, -(long long)p->R * m, m);
         p->run_packed = false;
         p->packed = ok;
+        if (ok && !c.sizes.empty())   // packed launches have their own best size
+            std::stable_sort(c.sizes.begin(), c.sizes.end(), [](int a, int b) { return kLifePackedLaunchCost[a] / a < kLifePackedLaunchCost[b] / b; });
     }
     if (p->packed) {
         DevGuard guard;

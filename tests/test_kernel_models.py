@@ -73,8 +73,8 @@ def test_life_bit_strip_decomposition_covers_every_column_once():
 
 
 def test_life_bit_conway_identity_matches_the_kernel_source():
-    """conway_bits in csrc/life_bit.cuh evaluates B3/S23 from the bit-sliced row sums with four immediate LOP3 tables (0x60, 0x09,
-    0x60, 0xBA). The tables are read out of the CUDA source and evaluated over every input combination against the rule
+    """conway_bits in csrc/life_bit.cuh evaluates B3/S23 from the bit-sliced row sums with three immediate LOP3 tables (0x14, 0x42,
+    0xCA). The tables are read out of the CUDA source and evaluated over every input combination against the rule
     itself: alive' = (T == 3) | (centre & T == 4), T = the 3 x 3 total including the centre."""
     import itertools
     import os
@@ -83,9 +83,8 @@ def test_life_bit_conway_identity_matches_the_kernel_source():
     body = src[src.index("__device__ __forceinline__ unsigned conway_bits"):]
     body = body[:body.index("\n}") + 2]
     imms = [int(v, 16) for v in re.findall(r"lop3_imm<(0x[0-9A-Fa-f]+)>", body)]
-    assert imms == [0x60, 0x09, 0x60, 0xBA], imms
-    assert "lop3_imm<0x60>(t0, u1, c0)" in body and "lop3_imm<0x09>(t0, u1, c0)" in body
-    assert "lop3_imm<0x60>(q4, u1, c1) & b.c" in body and "lop3_imm<0xBA>(p3, c1, y4)" in body
+    assert imms == [0x14, 0x42, 0xCA], imms
+    assert "lop3_imm<0x14>(u1, c0, c1)" in body and "lop3_imm<0x42>(u1, c0, c1) & b.c" in body and "lop3_imm<0xCA>(t0, a3, b4)" in body
 
     def lop3(a, b, c, imm):
         return (imm >> ((a << 2) | (b << 1) | c)) & 1
@@ -95,8 +94,8 @@ def test_life_bit_conway_identity_matches_the_kernel_source():
     for as0, as1, bs0, bs1, ns0, ns1, c in itertools.product([0, 1], repeat=7):
         t0, c0 = as0 ^ bs0 ^ ns0, maj(as0, bs0, ns0)
         u1, c1 = as1 ^ bs1 ^ ns1, maj(as1, bs1, ns1)
-        p3, q4 = lop3(t0, u1, c0, imms[0]), lop3(t0, u1, c0, imms[1])
-        y4 = lop3(q4, u1, c1, imms[2]) & c
-        got = lop3(p3, c1, y4, imms[3])
+        a3 = lop3(u1, c0, c1, imms[0])
+        b4 = lop3(u1, c0, c1, imms[1]) & c
+        got = lop3(t0, a3, b4, imms[2])
         total = (as0 + 2 * as1) + (bs0 + 2 * bs1) + (ns0 + 2 * ns1)
         assert got == int(total == 3 or (c == 1 and total == 4)), (as0, as1, bs0, bs1, ns0, ns1, c)

@@ -54,7 +54,30 @@ for cells01 in (1, 0):
         print(f"gens {n} cells01={cells01}: {us:8.1f} us per launch (min {mn / 8 * 1e3:.1f}), {cells * n / us / 1e6:9.1f} Gcell-updates/s, "
               f"kernel {lib.sb200_last_kernel().decode()}", flush=True)
 
+# packed -> packed launches (SB200_FLAG_SRC_BITS | SB200_FLAG_DST_BITS): the two buffers hold the packed grids (garbage bits are as good as any)
+for n in range(1, 9):
+    d = build_desc(size=shape, eltype=A.U8, out_eltype=A.U8, offsets=moore, radius=1, boundary=A.WRAP, reducer=A.LIFE,
+                   flags=A.flag_gens(n) | A.FLAG_SRC_BITS | A.FLAG_DST_BITS)
+
+    def one_pk():
+        for _ in range(4):
+            A.check(lib.sb200_gather(d.ptr(), a.data_ptr(), b.data_ptr(), st))
+            A.check(lib.sb200_gather(d.ptr(), b.data_ptr(), a.data_ptr(), st))
+    med, mn = timed(one_pk)
+    us = med / 8 * 1e3
+    print(f"gens {n} packed -> packed: {us:8.1f} us per launch (min {mn / 8 * 1e3:.1f}), {cells * n / us / 1e6:9.1f} Gcell-updates/s, "
+          f"kernel {lib.sb200_last_kernel().decode()}", flush=True)
+a.copy_(synth_torch(shape, np.uint8, 0x5EED0005, dev))
+
 h1 = build_desc(size=shape, eltype=A.U8, out_eltype=A.U8, offsets=moore, radius=1, boundary=A.WRAP, reducer=A.LIFE)
+for gm in ("5", "6", "7", "8"):
+    os.environ["SB200_LIFE_PACKED_GENS"] = gm
+    for n in (20, 100, 1000):
+        def run_pk():
+            A.check(lib.sb200_iterate(h1.ptr(), a.data_ptr(), b.data_ptr(), n, st))
+        med, mn = timed(run_pk, reps=10 if n < 1000 else 5)
+        print(f"sb200_iterate {n:5d} steps, SB200_LIFE_PACKED_GENS={gm}: {cells * n / med / 1e6:9.1f} Gcell-updates/s (best {cells * n / mn / 1e6:.1f})", flush=True)
+del os.environ["SB200_LIFE_PACKED_GENS"]
 for pow2 in ("0", "1"):
     os.environ["SB200_POW2_STEPS"] = pow2
     for n in (10, 20, 21, 30, 50, 100, 1000):
