@@ -10,7 +10,7 @@ One "step" is one sweep of the hot path over the whole grid. The default workloa
 Moore(1), UInt8 16384x16384, Wrap, SwitchingStencilArray iterated (sb200_iterate). Timing: W warm-up steps, then >= 10
 repetitions of the K-step region (>= 50 ms in total), each bracketed by CUDA events on the launching stream; `value` uses the
 median repetition. For the iterated workloads (life, diffusion) K is rounded UP to whole exchange cycles
-of the slab plans (Life 128 generations, diffusion 4; >= 4 cycles) at EVERY N, N = 1 included, so that a scaling series times
+of the slab plans (Life 126 generations, diffusion 4; >= 4 cycles) at EVERY N, N = 1 included, so that a scaling series times
 one schedule; `steps_timed` says what ran and `k_step_calls` carries the rate of sb200_iterate calls of exactly K generations.
 
 With N > 1 (torchrun, one rank per GPU) every rank owns a 16384x16384 slab of a 16384 x (16384*N) torus (weak scaling; --strong
@@ -363,9 +363,9 @@ def slab_case(workload):
 
 
 def plan_cycle(workload):
-    """Generations per ghost exchange of the slab plans' library defaults (csrc/slab_plan.cu: Life 128 rows = 16 launches of eight
+    """Generations per ghost exchange of the slab plans' library defaults (csrc/slab_plan.cu: Life 126 rows = 21 packed launches of six
     generations, diffusion 4 planes); bench_slabs reads the same number from the plan's own stats at N > 1."""
-    return {"life": 128, "diffusion": 4}[workload]
+    return {"life": 126, "diffusion": 4}[workload]
 
 
 def bench_slabs(torch, dist, workload, spec, steps, warmup, strong, min_reps=10, min_total_ms=50.0):

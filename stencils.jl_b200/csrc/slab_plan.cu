@@ -130,33 +130,6 @@ __global__ void plan_planes_kernel(unsigned char* base, size_t plane_bytes, long
     }
 }
 
-// Packed Life runs (SB200_FLAG_SRC_BITS / _DST_BITS): a plan_iterate call packs the byte parent of every slab once (cell != 0 -> bit
-// c % 32 of word c / 32; rows are multiples of 128 cells, so the parent is one flat array of words), runs every sweep and every
-// exchange on the packed parents, and unpacks the final state once.
-__global__ void plan_pack_kernel(const uint4* __restrict__ src, uint32_t* __restrict__ dst, size_t nwords) {
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nwords; i += (size_t)gridDim.x * blockDim.x) {
-        const uint4 a = src[2 * i], b = src[2 * i + 1];
-        const unsigned w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-        unsigned acc = 0;
-#pragma unroll
-        for (int k = 7; k >= 0; k--) {
-            const unsigned nz = ((((w[k] & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | w[k]) >> 7) & 0x01010101u;   // byte != 0
-            acc = (acc << 4) | ((nz * 0x10204080u) >> 28);
-        }
-        dst[i] = acc;
-    }
-}
-__global__ void plan_unpack_kernel(const uint32_t* __restrict__ src, uint4* __restrict__ dst, size_t nwords) {
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nwords; i += (size_t)gridDim.x * blockDim.x) {
-        const unsigned v = src[i];
-        unsigned o[8];
-#pragma unroll
-        for (int k = 0; k < 8; k++) o[k] = (((v >> (4 * k)) & 0xFu) * 0x00204081u) & 0x01010101u;
-        dst[2 * i] = make_uint4(o[0], o[1], o[2], o[3]);
-        dst[2 * i + 1] = make_uint4(o[4], o[5], o[6], o[7]);
-    }
-}
-
 // Fill `count` elements of `es` bytes with the low bytes of `bits` (Remove ends: ghost planes <- padval).
 __global__ void plan_fill_kernel(unsigned char* p, size_t count, int es, unsigned long long bits) {
     for (size_t j = blockIdx.x * (size_t)blockDim.x + threadIdx.x; j < count; j += (size_t)gridDim.x * blockDim.x) {
@@ -197,7 +170,9 @@ struct sb200_plan {
     bool rank_form = false, use_flags = false, overlap = false, split_wrap = true;
     bool fused_xfer = false;            // flag form with 16-byte aligned zones: push + publish / wait + ghost copy as one kernel each
     bool packed = false;                // Life: sweeps and exchanges of a plan_iterate call run on packed parents (one bit per cell)
-    bool run_packed = false;            // ... and the interpreter is inside such a call right now
+    bool run_packed = false;            // ... the state the interpreter is working on right now is the packed one
+    bool sweep_to_packed = false;       // ... the sweep being issued converts: byte source -> packed dest (first sweep of a call)
+    bool sweep_to_bytes = false;        // ... packed source -> byte dest (last sweep of a call)
     int rank = 0, world = 1;
     int later_flags = 0;
     std::vector<Slab> slabs;
@@ -228,7 +203,8 @@ static sb200_desc sweep_desc(const sb200_plan* p, long long ext, long long lo, l
     d.boundary[last] = SB200_WRAP;   // never exercised: the output region stays R * gens planes inside the parent
     for (int a = 0; a < 3; a++) { d.region_lo[a] = 0; d.region_hi[a] = a < p->ndim ? d.size[a] : 0; }
     d.region_lo[last] = lo; d.region_hi[last] = hi;
-    d.flags = (first ? 0 : p->later_flags) | SB200_FLAG_GENS(gens) | (p->run_packed ? SB200_FLAG_SRC_BITS | SB200_FLAG_DST_BITS : 0);
+    const bool src_bits = p->run_packed, dst_bits = (p->run_packed && !p->sweep_to_bytes) || p->sweep_to_packed;
+    d.flags = (first ? 0 : p->later_flags) | SB200_FLAG_GENS(gens) | (src_bits ? SB200_FLAG_SRC_BITS : 0) | (dst_bits ? SB200_FLAG_DST_BITS : 0);
     d.mirror_parent = nullptr; d.mirror_lo = d.mirror_hi = 0;
     d.offsets_host = p->offsets.data();
     d.weights_host = p->weights.empty() ? nullptr : p->weights.data();
@@ -280,7 +256,10 @@ static int plan_common_init(sb200_plan* p, const sb200_desc* g, int ghost, int p
     // and 32; b = 7: 126 and 28).
     if (G <= 0) {
         const long long n_est = g->size[g->ndim - 1] / nslabs_total;
-        const int b = life_pow2_only() ? 8 : life_bulk_gens();
+        // (a plan that will run packed — the static part of plan_make_sched's decision — is made of packed launches)
+        const bool will_pack = g->reducer == SB200_LIFE && bc == SB200_WRAP && g->size[0] % 128 == 0 && !(plan_flags & SB200_PLAN_OVERLAP_ON) &&
+                               !(plan_flags & SB200_PLAN_SINGLE_STEP) && !(getenv("SB200_LIFE_PACKED") && atoi(getenv("SB200_LIFE_PACKED")) == 0);
+        const int b = life_pow2_only() ? 8 : will_pack ? kLifePackedBulkGens : life_bulk_gens();
         G = g->reducer == SB200_LIFE ? (n_est >= 1024 ? (128 + b / 2) / b * b : (32 + b / 2) / b * b) * p->R
                                      : (g->reducer == SB200_DIFFUSION ? 4 * p->R : p->R);
         while (G > p->R && G > n_est) G /= 2;
@@ -466,7 +445,10 @@ static int exec_op(sb200_plan* p, Slab& s, const sb200_slab_op& o) {
         } else if (o.mirror == SB200_SLAB_MIRROR_UP && s.peer_up) {   // my top owned planes arrive at the upper neighbour from below: side 0
             d.mirror_parent = s.peer_up + slot_off(p, 0, par); d.mirror_lo = s.n; d.mirror_hi = s.n + G;
         }
-        const int rc = do_gather(&d, cur, nxt, s.compute);
+        // a converting sweep reads one representation and writes the other (same double-buffer index)
+        void* from = cur;
+        void* to = p->sweep_to_packed ? s.pk[1 - s.cur] : p->sweep_to_bytes ? s.buf[1 - s.cur] : nxt;
+        const int rc = do_gather(&d, from, to, s.compute);
         if (rc) return rc;
         p->launches++;
         return SB200_OK;
@@ -562,34 +544,37 @@ static int plan_run(sb200_plan* p, int nsteps) {
     if (nsteps < 0) { set_error("negative step count"); return SB200_EINVAL; }
     if (p->rank_form && p->world > 1 && !p->connected) { set_error("sb200_plan_connect has not been called"); return SB200_EINVAL; }
     std::vector<sb200_slab_op> ops;
-    const bool packed = p->packed && nsteps >= 2;
-    p->run_packed = packed;   // the scheduler's acceptance probes see the descriptors the sweeps will use
+    p->run_packed = p->packed;   // the scheduler's acceptance probes see the descriptors most sweeps will use
     p->sched->plan(nsteps, ops);
     p->run_packed = false;
     DevGuard guard;
-    auto convert = [&](bool pack) -> int {
-        for (Slab& s : p->slabs) {
-            SB_CUDA(cudaSetDevice(s.dev));
-            const size_t nwords = (size_t)s.ext * p->plane_bytes / 32;
-            const unsigned blocks = (unsigned)std::min<size_t>((nwords + 255) / 256, (size_t)num_sms() * 16);
-            if (pack) plan_pack_kernel<<<blocks, 256, 0, s.compute>>>((const uint4*)s.buf[s.cur], (uint32_t*)s.pk[s.cur], nwords);
-            else plan_unpack_kernel<<<blocks, 256, 0, s.compute>>>((const uint32_t*)s.pk[s.cur], (uint4*)s.buf[s.cur], nwords);
-            SB_LAUNCH_CHECK();
-        }
-        return SB200_OK;
-    };
+    // Packed calls: the first sweep of >= 2 generations reads the byte parent and writes the packed one, every op after it works on
+    // the packed state (sweeps, pushes, pulls: rows of plane_bytes / 8), and the LAST sweep of the call writes the byte parent
+    // again — no conversion passes. Sweeps in front of the converting one (single generations) stay byte -> byte; a call whose
+    // sweeps leave no room for both conversions runs on the bytes.
+    int conv_in = -1, conv_out = -1;
+    if (p->packed) {
+        for (int i = 0; i < (int)ops.size(); i++)
+            if (ops[i].kind == SB200_SLAB_SWEEP) {
+                if (conv_in < 0 && ops[i].gens >= 2) conv_in = i;
+                conv_out = i;
+            }
+        // boundary-first cycles issue three sweeps per step (overlap): packed plans have overlap off, so sweeps and steps coincide
+        if (conv_in < 0 || conv_out <= conv_in) conv_in = conv_out = -1;
+    }
     int rc = SB200_OK;
-    if (packed && (rc = convert(true))) return rc;
-    p->run_packed = packed;
-    // op by op over all slabs: in the event-ordered form a slab's PULL must be enqueued after its neighbours' SIGNAL
-    for (const sb200_slab_op& o : ops) {
+    for (int i = 0; i < (int)ops.size() && !rc; i++) {
+        const sb200_slab_op& o = ops[i];
+        p->sweep_to_packed = i == conv_in;
+        p->sweep_to_bytes = i == conv_out;
+        // op by op over all slabs: in the event-ordered form a slab's PULL must be enqueued after its neighbours' SIGNAL
         for (Slab& s : p->slabs)
             if ((rc = exec_op(p, s, o))) break;
-        if (rc) break;
+        if (i == conv_in) p->run_packed = true;     // from here on the current state is the packed one
+        if (i == conv_out) p->run_packed = false;
     }
-    p->run_packed = false;
+    p->run_packed = p->sweep_to_packed = p->sweep_to_bytes = false;
     if (rc) return rc;
-    if (packed && (rc = convert(false))) return rc;
     p->steps += nsteps;
     return SB200_OK;
 }
