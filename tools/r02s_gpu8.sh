@@ -1,5 +1,5 @@
 #!/bin/bash
-# r02s: the whole weak-scaling series N = 1, 2, 4, 8 on ONE 8-GPU box (same silicon, same thermal state history as the driver's SCALE run)
+# r02s (final build: packed Life plans): the whole weak-scaling series N = 1, 2, 4, 8 on ONE 8-GPU box (same silicon, same thermal state history as the driver's SCALE run)
 O=gpurun_out/r02s
 mkdir -p $O
 S=$O/status.txt
