@@ -57,6 +57,16 @@ def ncu_traffic(workload):
     return None
 
 
+def ncu_pipes(workload):
+    """Pipe / issue utilisation of the dominant kernel from the same committed ncu capture (what `binding` refers to)."""
+    p = os.path.join(ROOT, "profiles", "ncu_summary.json")
+    try:
+        e = json.load(open(p)).get(workload, {})
+        return {k: e[k] for k in ("kernel", "pipe_alu_pct", "pipe_fma_pct", "issue_active_pct", "dram_pct_of_peak") if k in e} or None
+    except Exception:
+        return None
+
+
 # ------------------------------------------------------------------------------------------------ synthetic inputs
 def synth(shape, dtype, seed):
     from stencils_b200.synth import synth_np
@@ -524,7 +534,7 @@ def roofline_of(workload, spec, value_per_gpu, kernel, peak, peak_src, sweeps_pe
     if workload == "diffusion" and "stream3d2" not in kernel:
         binding = "hbm"
     return {"bound": "hbm", "binding": binding, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            "dram_frac": dram_frac, "traffic": traffic,
+            "dram_frac": dram_frac, "traffic": traffic, "binding_util_ncu": ncu_pipes(workload),
             "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel, ncu --set full capture "
                               "committed as profiles/ncu_summary.json (not re-measured in this run)" if traffic else None,
             "peak_source": peak_src, "kernel": kernel, "algorithmic_bytes_per_cell": spec["bytes_per_cell"],
