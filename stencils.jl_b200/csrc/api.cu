@@ -597,6 +597,26 @@ int32_t sb200_gather_multi(const sb200_term* terms, int32_t nterms, void* dst, v
                 return SB200_ESIZE;
             }
     }
+    // One pass over all arguments where the kernel of multi_tile.cu takes the combination (opt-in, SB200_MULTI_SINGLE_PASS=1; 2-D
+    // Float32 / Float64, the reducer menu of the streaming kernels, R <= 4): every source is read once, the dest written once, no
+    // scratch parent.
+    {
+        Plan* pls[SB200_MAX_TERMS];
+        sb200_desc dj[SB200_MAX_TERMS];
+        bool ok = true;
+        for (int j = 0; j < nterms && ok; j++) {
+            dj[j] = *terms[j].desc;
+            memset(dj[j].region_lo, 0, sizeof(dj[j].region_lo)); memset(dj[j].region_hi, 0, sizeof(dj[j].region_hi));
+            ok = get_plan(&dj[j], PK_GATHER, &pls[j]) == SB200_OK;
+        }
+        if (ok && try_multi_tile2d(pls, terms, nterms, dst, st, true) == SB200_OK) {
+            for (int j = 0; j < nterms; j++) {
+                int rc;
+                if (needs_halo(&dj[j]) && (rc = do_halo(&dj[j], const_cast<void*>(terms[j].src_parent), st))) return rc;   // update_boundary!(source)
+            }
+            return try_multi_tile2d(pls, terms, nterms, dst, st, false);
+        }
+    }
     const size_t db = parent_bytes(d0, false);
     const bool need_scratch = nterms > 1 || terms[0].has_coef;
     if (need_scratch && !scratch) {

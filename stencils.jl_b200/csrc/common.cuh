@@ -182,6 +182,7 @@ int try_gather_stream(const Plan& pl, const void* src, void* dst, cudaStream_t s
 int try_gather_stream3d(const Plan& pl, const void* src, void* dst, cudaStream_t st);
 int try_box3d(const Plan& pl, const void* src, void* dst, cudaStream_t st);   // Window(1,3) / Moore(1,3) at compile time (box3d.cu)
 int try_scatter_fast(const Plan& pl, const void* src, void* dst, cudaStream_t st);
+int try_multi_tile2d(const Plan* const* plans, const sb200_term* terms, int nterms, void* dst, cudaStream_t st, bool dry);   // multi_tile.cu
 int try_scatter_stream(const Plan& pl, const void* src, void* dst, cudaStream_t st, int x_lo, int x_hi, int y_lo, int y_hi);
 
 int num_sms();

@@ -325,6 +325,56 @@ def test_multi_stencilarray_mapstencil(orc):
     bits_equal(host(got), want)
 
 
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+def test_multi_array_single_pass_kernel(orc, dt, monkeypatch):
+    """multi_tile2d_kernel (csrc/multi_tile.cu): the arguments of a multi-array gather in ONE pass — every source read once, the
+    dest written once (opt-in, SB200_MULTI_SINGLE_PASS=1) — against the oracle's per-argument sweeps combined left to right, and against
+    the default sweep-per-argument path, bit for bit: sizes that are no multiples of the 128 x 8 tile, a radius-4 shape, Wrap +
+    Halo{:out}, Reflect, Remove with a non-zero padval, Halo{:in}, coefficients, a plain-array argument; a 3-D combination keeps
+    the old path."""
+    rng = np.random.default_rng(17)
+    l = A.lib()
+    shape = (333, 77)
+    X, Y, Z, P = (np.asfortranarray((rng.random(shape) - 0.4).astype(dt)) for _ in range(4))
+    w = rng.random((5, 5)).astype(dt)
+    sx = sb.StencilArray(dev(X), sb.Circle(4), boundary=sb.Wrap(), padding=sb.Halo("out"))
+    sy = sb.StencilArray(dev(Y), sb.Kernel(sb.Window(2), w), boundary=sb.Reflect())
+    sz = sb.StencilArray(dev(Z), sb.VonNeumann(2), boundary=sb.Remove(dt(0.5)))
+    f = sb.LinearCombination((0.25, sb.maximum), sb.kernelproduct, (-1.5, sb.mean), (2.0, sb.center))
+
+    def run():
+        return host(sb.mapstencil(f, sx, sy, sz, dev(P)))
+    monkeypatch.setenv("SB200_MULTI_SINGLE_PASS", "1")   # opt-in: the sweep-per-argument path measured faster (csrc/multi_tile.cu)
+    got = run()
+    assert l.sb200_last_kernel() == b"multi_tile2d_kernel"
+    t1 = orc.stencil_array_sweep(X, npr.offsets("Circle", 4, 2), 4, A.WRAP, "cond", A.MAX)
+    t2 = orc.stencil_array_sweep(Y, npr.offsets("Window", 2, 2), 2, A.REFLECT, "cond", A.KERNELDOT, weights=w)
+    t3 = orc.stencil_array_sweep(Z, npr.offsets("VonNeumann", 2, 2), 2, A.REMOVE, "cond", A.MEAN, padval=0.5)
+    want = ((dt(0.25) * t1 + t2) + dt(-1.5) * t3) + dt(2.0) * P
+    assert want.dtype == np.dtype(dt)
+    bits_equal(got, want)
+    monkeypatch.delenv("SB200_MULTI_SINGLE_PASS")
+    old = run()
+    assert l.sb200_last_kernel() != b"multi_tile2d_kernel"
+    bits_equal(old, got)
+    monkeypatch.setenv("SB200_MULTI_SINGLE_PASS", "1")
+    # Halo{:in} sources (the logical array is the inside of the parent) and a single argument with a coefficient
+    big = np.asfortranarray(rng.random((140, 40)).astype(dt))
+    si = sb.StencilArray(dev(big), sb.Moore(1), boundary=sb.Wrap(), padding=sb.Halo("in"))
+    g1 = host(sb.mapstencil(sb.LinearCombination((3.0, sb.sum)), si))
+    assert l.sb200_last_kernel() == b"multi_tile2d_kernel"
+    inner = np.asfortranarray(big[1:-1, 1:-1])
+    bits_equal(g1, dt(3.0) * orc.stencil_array_sweep(inner, npr.offsets("Moore", 1, 2), 1, A.WRAP, "cond", A.SUM))
+    # 3-D: the sweep-per-argument path
+    V, U = (np.asfortranarray(rng.random((40, 12, 9)).astype(dt)) for _ in range(2))
+    sv, su = sb.StencilArray(dev(V), sb.VonNeumann(1, 3), boundary=sb.Wrap()), sb.StencilArray(dev(U), sb.Window(1, 3), boundary=sb.Wrap())
+    g3 = host(sb.mapstencil(sb.LinearCombination(sb.sum, (0.5, sb.mean)), sv, su))
+    assert l.sb200_last_kernel() != b"multi_tile2d_kernel"
+    w3 = orc.stencil_array_sweep(V, npr.offsets("VonNeumann", 1, 3), 1, A.WRAP, "cond", A.SUM) + \
+        dt(0.5) * orc.stencil_array_sweep(U, npr.offsets("Window", 1, 3), 1, A.WRAP, "cond", A.MEAN)
+    bits_equal(g3, w3)
+
+
 def test_layered_stencils(orc):
     """Layered (src/stencils/layered.jl:13-57; reference test test/stencils.jl:242-264): `sum(l[1]) - sum(l[2])` and
     `sum(l.l1.b) - sum(l.l2.a)` as multi-table gathers over ONE parent, on the reference's 5 x 5 array and on random Float32
