@@ -392,6 +392,7 @@ int do_gather(const sb200_desc* d, const void* src, void* dst, cudaStream_t st) 
     if (!(d->flags & SB200_FLAG_FORCE_GENERIC)) {
         rc = try_life_swar(*pl, src, dst, st);
         if (rc < 0) rc = try_diffusion3d(*pl, src, dst, st);
+        if (rc < 0) rc = try_small2d(*pl, src, dst, st);   // radius-1 shapes on grids that fit the L2 (small2d.cu)
         if (rc < 0) rc = try_tile2d(*pl, src, dst, st);
         if (rc < 0) rc = try_gather_stream(*pl, src, dst, st);
         if (rc < 0) rc = try_box3d(*pl, src, dst, st);

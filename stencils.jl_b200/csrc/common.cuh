@@ -175,6 +175,7 @@ int try_life_swar(const Plan& pl, const void* src, void* dst, cudaStream_t st);
 bool life2_accepts(const sb200_desc& d, const Plan& pl);  // SB200_FLAG_DOUBLE_STEP
 bool life_multi_accepts(const sb200_desc& d, const Plan& pl, int gens);  // gens = 2 (DOUBLE_STEP) or 4 (QUAD_STEP)
 int try_tile2d(const Plan& pl, const void* src, void* dst, cudaStream_t st);
+int try_small2d(const Plan& pl, const void* src, void* dst, cudaStream_t st);   // small2d.cu: radius-1 shapes, L2-resident grids
 int try_diffusion3d(const Plan& pl, const void* src, void* dst, cudaStream_t st);
 int try_diffusion3d_double(const Plan& pl, const void* src, void* dst, cudaStream_t st);  // SB200_FLAG_DOUBLE_STEP (stream3d2.cu)
 bool diffusion2_accepts(const sb200_desc& d, const Plan& pl);

@@ -861,6 +861,37 @@ def test_life_packed_state(orc, gens):
                           stream()) == A.EUNSUPPORTED
 
 
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+def test_small_grid_kernel(orc, dt, monkeypatch):
+    """small2d_kernel (csrc/small2d.cu): radius-1 shapes on grids that fit the L2 — no ring, every thread reads its three rows
+    directly. Window / Moore / VonNeumann x sum / mean / minimum / maximum x Remove(padval) / Wrap / Reflect x Conditional / Halo{:out}
+    (ring read straight through, refreshed ring compared too) on sizes that are no multiples of the 16-byte groups, against the oracle
+    AND against the streaming kernel on the same input, bit for bit; larger grids keep the streaming kernel. The kernel is an
+    experiment that is OFF by default (it measured no faster than the streaming kernel at 1000 x 1000): SB200_SMALL2D_MAX_CELLS enables it."""
+    rng = np.random.default_rng(23)
+    l = A.lib()
+    for (W, H) in ((1000, 37), (131, 64), (66, 5), (258, 130)):
+        r = np.asfortranarray((rng.random((W, H)) - 0.3).astype(dt))
+        r[rng.random((W, H)) < 0.01] = -0.0
+        for name in ("Window", "Moore", "VonNeumann"):
+            offs = npr.offsets(name, 1, 2)
+            for bc in ("remove", "wrap", "reflect"):
+                for pad in ("cond", "out"):
+                    for red in ("sum", "mean", "min", "max"):
+                        monkeypatch.setenv("SB200_SMALL2D_MAX_CELLS", "1500000")
+                        got = both(orc, r, offs, 1, bc, pad, red, padval=1.25)
+                        assert l.sb200_last_kernel() == b"small2d_kernel", (name, bc, pad, red, l.sb200_last_kernel())
+                        monkeypatch.delenv("SB200_SMALL2D_MAX_CELLS")
+                        ref = both(orc, r, offs, 1, bc, pad, red, padval=1.25)
+                        assert l.sb200_last_kernel() != b"small2d_kernel"
+                        if got is not None and ref is not None:
+                            bits_equal(got, ref)
+    monkeypatch.setenv("SB200_SMALL2D_MAX_CELLS", "1500000")
+    big = np.asfortranarray(rng.random((2048, 1024)).astype(dt))
+    both(orc, big, npr.offsets("Window", 1, 2), 1, "remove", "cond", "mean", padval=0.0)
+    assert l.sb200_last_kernel() == b"stream2d_kernel"
+
+
 def test_iterate_packed_runs(orc, monkeypatch):
     """sb200_iterate keeps Life runs of >= 12 generations packed between the first and the last launch (bytes -> bits ... bits ->
     bytes, the packed grids inside the two buffers themselves). SB200_LIFE_PACKED=1 forces the path for a small grid: step counts of
