@@ -241,7 +241,12 @@ typedef struct sb200_term {
 int32_t sb200_gather_multi(const sb200_term* terms, int32_t nterms, void* dst_parent, void* scratch, void* stream);
 
 /* nsteps x { update_halo(src) if the source has a ring and boundary != USE; gather(src->dst); swap }.
-   buf_a holds the state on entry; the final state is in buf_a if nsteps is even, else buf_b. */
+   buf_a holds the state on entry; the final state is in buf_a if nsteps is even, else buf_b. The contents of the OTHER buffer
+   after the call are unspecified: where a kernel advances several generations per launch (SB200_FLAG_GENS: Life, Diffusion) the
+   intermediate states never exist in memory, and B3/S23 Life runs of >= 12 generations on grids above 4 Mi cells (axis 0 a
+   multiple of 128) keep their state one bit per cell between the first and the last launch (SB200_FLAG_SRC_BITS / _DST_BITS),
+   in packed grids placed inside the two buffers themselves — nothing is allocated. SB200_LIFE_PACKED=0 / 1 turns the packed
+   runs off / on for every grid size. */
 int32_t sb200_iterate(const sb200_desc* d, void* buf_a, void* buf_b, int32_t nsteps, void* stream);
 
 /* ---- host-buffer entry points (what a StencilArray over a CPU Array lowers to) ---- */

@@ -217,9 +217,11 @@ def test_diffusion_1024_cubed_two_steps_per_launch():
 
 
 # ---- SURVEY 8d tier T3 long runs: the whole grid against the oracle over MANY schedule cycles ----
-def test_long_run_life_2048_1000_generations(orc):
-    """Life 2048 x 2048 UInt8 Wrap x 1000 generations through sb200_iterate (1 .. 8 generations per launch, sevens in bulk, small-grid
-    CUDA-graph replay on a real stream) and through a three-slab plan, full grid against orc.iterate, bit for bit."""
+def test_long_run_life_2048_1000_generations(orc, monkeypatch):
+    """Life 2048 x 2048 UInt8 Wrap x 1000 generations through sb200_iterate (byte launches of 1 .. 8 generations, small-grid
+    CUDA-graph replay on a real stream), through sb200_iterate with the state packed between the launches (the path of grids above
+    4 Mi cells, forced here: 167 launches, bytes -> bits ... bits -> bytes; 999 generations for the other final buffer) and through a
+    three-slab plan (packed, cycles of 126), full grid against orc.iterate, bit for bit."""
     import torch
     from stencils_b200.slab import SlabPlan
     from stencils_b200.synth import synth_np
@@ -240,6 +242,16 @@ def test_long_run_life_2048_1000_generations(orc):
         launches = l.sb200_launch_count(1)
         assert launches <= 146, launches   # launches of seven generations (+ a fix-up for the launch-count parity)
         bits_equal(np.asfortranarray(a.cpu().numpy().T), want)
+    monkeypatch.setenv("SB200_LIFE_PACKED", "1")
+    want999 = orc.iterate(h, g.copy(order="F"), np.zeros_like(g, order="F"), 999)
+    for n, w in ((1000, want), (999, want999)):
+        a = torch.from_numpy(np.ascontiguousarray(g.T)).cuda()
+        b = torch.full_like(a, 3)
+        A.check(l.sb200_iterate(h.ptr(), a.data_ptr(), b.data_ptr(), n, None))
+        torch.cuda.synchronize()
+        assert l.sb200_last_kernel().endswith(b"bits->u8>"), l.sb200_last_kernel()
+        bits_equal(np.asfortranarray((a if n % 2 == 0 else b).cpu().numpy().T), w)
+    monkeypatch.delenv("SB200_LIFE_PACKED")
     plan = SlabPlan(shape, offsets=npr.offsets("Moore", 1, 2), radius=1, reducer=A.LIFE, boundary=(A.WRAP, A.WRAP), eltype=A.U8, ghost=0,
                     devices=[0, 0, 0], reducer_kwargs=dict(born_mask=8, survive_mask=12))
     try:
