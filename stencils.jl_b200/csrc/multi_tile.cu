@@ -6,7 +6,7 @@
 // argument: 7 array transits for two arguments where 3 are needed (2 reads + 1 write). Here a CTA owns a tile of MT_TX x MT_TY
 // destination cells; per argument it stages the tile plus the argument's own radius-R halo in shared memory — boundary rule,
 // Halo ring and padval of THAT argument resolved at load time (src/array.jl:91-138) —, every thread folds the argument's taps in
-// table order for its four cells (the reference's offset order: bit-identical to the per-argument kernels and to the oracle)
+// table order for its four cells (the reference's offset order: bit-identical to the per-argument kernels)
 // and adds the term to its running results; the destination is written once. Every source cell is read from HBM once plus
 // the tile halo (1.08x for R = 1 at 128 x 32; neighbouring CTAs find it in L2), no scratch parent is needed.
 // 3-D arrays, integer element types and reducers outside the menu below keep the sweep-per-argument path (api.cu) — which is also

@@ -6,7 +6,7 @@
 // hand-offs — on a 1000 x 1000 grid every CTA streams ~3400 cells and the sweep lasts 6.4 us (tools/mean1000_probe.py). The question
 // this file answers is whether that is pipeline start-up. Here nothing is staged: a thread owns 16 bytes of one row (two Float64 / four Float32 cells), reads its
 // three source rows straight from L1 / L2 (one 128-bit load per row plus the two neighbour cells), folds the taps in the
-// reference's offset order (bit-identical to the streaming kernels and the oracle) and stores 16 bytes; ~2000 small CTAs cover the
+// reference's offset order (bit-identical to the streaming kernels) and stores 16 bytes; ~2000 small CTAs cover the
 // grid in under two waves. Threads whose cells touch the array edge resolve every neighbour through the boundary rule
 // (Remove padval / Wrap / Reflect, or the Halo ring read straight through).
 // Window(1), Moore(1), VonNeumann(1) x sum / mean / minimum / maximum x Float32 / Float64, whole-array sweeps up to
