@@ -302,11 +302,15 @@ template <int G, int IN, bool OUT_BITS> static int launch_bit(const LifeParams& 
     // rows, so pick the t that minimises waves x (rows per run + 2 G). Measured r02a (16384^2, three strips, 444 CTAs): one task
     // per CTA 9843 Gcell-updates/s, a clipped second wave (768 tasks) 8283. SB200_LB_TASKS overrides t for A/B runs.
     static const int tpc_env = getenv("SB200_LB_TASKS") ? atoi(getenv("SB200_LB_TASKS")) : 0;
+    // small grids: a run may be as short as G rows (it re-reads 2 G more) when that is what fills the SMs — the cost below decides;
+    // SB200_LB_MIN_ROWS_X (default 1) x G rows is the floor (4 = the round-2 behaviour)
+    static const int min_rows_x = getenv("SB200_LB_MIN_ROWS_X") ? std::max(1, atoi(getenv("SB200_LB_MIN_ROWS_X"))) : 1;
+    const int lb_min_rows = min_rows_x * G;
     long long nruns = 1;
     double best_cost = 1e300;
     for (int t = (tpc_env > 0 ? tpc_env : 1); t <= (tpc_env > 0 ? tpc_env : 4); t++) {
         long long r = std::max<long long>(1, t * ctas / q.nstrips);
-        r = std::min<long long>(r, std::max(1, p.rows / (4 * G)));   // at least 4 G rows per run
+        r = std::min<long long>(r, std::max(1, p.rows / lb_min_rows));   // at least lb_min_rows rows per run
         const long long waves = (q.nstrips * r + ctas - 1) / ctas;
         const double cost = (double)waves * ((double)p.rows / (double)r + 2.0 * G);
         if (cost < best_cost * 0.999) { best_cost = cost; nruns = r; }
