@@ -72,6 +72,19 @@ def test_life_bit_strip_decomposition_covers_every_column_once():
             assert (stored == 1).all() and inside, (W, G, one)
 
 
+def test_life_bit_packed_rows_model():
+    """The packed source / dest forms (SB200_FLAG_SRC_BITS / _DST_BITS): byte-level model of the producer's three bulk copies per row
+    (16-byte aligned, Wrap halos), the lanes' word offsets and the dest word offsets, tied to the constants in the CUDA source."""
+    m = _load("model_life_bit_lanes")
+    cu = open(os.path.join(ROOT, "stencils.jl_b200", "csrc", "life_bit.cuh")).read()
+    assert "constexpr int LB_HLB = 16;" in cu and "constexpr int LB_ROWB_PK = 768;" in cu
+    assert "LB_HLB + ((warp * C::WO) >> 3) + (lane - C::HLN) * 4" in cu and "((x0 + warp * C::WO) >> 3) + (lane - C::HLN) * 4" in cu
+    for W in (512, 1024, 4352, 5760, 5888, 16384, 32768):
+        for G in (1, 6, 8):
+            once, words, aligned = m.packed_row_model(W, G)
+            assert once and words and aligned, (W, G, once, words, aligned)
+
+
 def test_life_bit_conway_identity_matches_the_kernel_source():
     """conway_bits in csrc/life_bit.cuh evaluates B3/S23 from the bit-sliced row sums with three immediate LOP3 tables (0x14, 0x42,
     0xCA). The tables are read out of the CUDA source and evaluated over every input combination against the rule

@@ -93,6 +93,60 @@ def strip_cover(W, G, one_halo_lane, warps=6, rowb=6144):
     return stored, inside
 
 
+def packed_row_model(W, G, warps=6, rowb=768, hlb=16):
+    """The packed source / dest forms of life_bit_kernel (IN == LB_BITS / OUT_BITS; csrc/life_bit.cuh): a row is W / 8 bytes, a strip's
+    shared-memory row holds [x0 / 8 - 16, (x0 + wout) / 8 + 16) of it (mod W / 8: the producer's main copy + the two wrapped 16-byte
+    halo copies), lane l of warp w reads the 32-bit word at byte 16 + w * 120 + (l - 1) * 4 and, when active, stores its word at byte
+    (x0 + w * 960) / 8 + (l - 1) * 4 of the dest row. Emulates the byte movement with NumPy on a random row and returns
+    (every dest word written exactly once with the word of the same cells, every lane's word is the right global word, every copy is
+    16-byte aligned and sized)."""
+    assert W % 128 == 0
+    rng = np.random.default_rng(W + G)
+    Wb = W // 8
+    row = rng.integers(0, 256, Wb, dtype=np.uint8)
+    wo = 30 * 32
+    cap = warps * wo
+    nstrips = (W + cap - 1) // cap
+    outb = min(cap, ((W + nstrips - 1) // nstrips + 127) // 128 * 128)
+    nstrips = (W + outb - 1) // outb
+    written = np.zeros(Wb // 4, int)
+    dest = np.zeros(Wb, dtype=np.uint8)
+    words_ok, aligned = True, True
+    for strip in range(nstrips):
+        x0 = strip * outb
+        wout = min(outb, W - x0)
+        xb, wb = x0 // 8, wout // 8
+        srow = np.full(rowb, 0xEE, dtype=np.uint8)   # stale shared memory
+        lin = hlb if xb >= hlb else 0
+        rin = min(hlb, Wb - (xb + wb))
+        copies = [(hlb - lin, xb - lin, lin + wb + rin)]
+        if not lin:
+            copies.append((0, Wb - hlb, hlb))
+        if rin < hlb:
+            copies.append((hlb + wb + rin, 0, hlb - rin))
+        for dst_off, src_off, n in copies:
+            aligned &= dst_off % 16 == 0 and src_off % 16 == 0 and n % 16 == 0 and n > 0 and src_off + n <= Wb and dst_off + n <= rowb
+            srow[dst_off:dst_off + n] = row[src_off:src_off + n]
+        for w in range(warps):
+            if w * wo >= wout:
+                continue
+            for lane in range(32):
+                cell0 = w * wo + (lane - 1) * 32
+                off = hlb + (w * wo) // 8 + (lane - 1) * 4
+                word = srow[off:off + 4]
+                active = 1 <= lane <= 30 and cell0 < wout
+                # lanes next to an active lane feed its edge bits: their word must be the real neighbour word (mod W)
+                need = active or (1 <= lane + 1 <= 30 and cell0 + 32 < wout) or (1 <= lane - 1 <= 30 and 0 <= cell0 - 32 < wout)
+                if need:
+                    g = ((x0 + cell0) // 8) % Wb
+                    words_ok &= bool((word == row[g:g + 4]).all())
+                if active:
+                    d = (x0 + w * wo) // 8 + (lane - 1) * 4
+                    dest[d:d + 4] = word
+                    written[d // 4] += 1
+    return bool((written == 1).all()) and bool((dest == row).all()), words_ok, aligned
+
+
 def check_strips():
     ok = True
     for W in (1024, 4096, 4352, 9216, 16384, 32768):
