@@ -304,7 +304,9 @@ int32_t sb200_debug_split_steps(int32_t nsteps, int32_t size_mask, int32_t life,
  * schedule: ghosts are exchanged every G / radius generations, the boundary planes of the last sweep of a cycle are stored
  * straight into the neighbour's mailbox over NVLink by the sweep kernel and pulled into the ghost zones on a side stream
  * while the interior sweep runs. Results are bit-identical to sb200_iterate on the undivided array for any number of
- * slabs and any G.
+ * slabs and any G. B3/S23 Life plans on a ring whose rows are multiples of 128 cells run PACKED inside a sb200_plan_iterate
+ * call (the first sweep reads the byte parents and writes one bit per cell, sweeps and ghost exchanges work on packed rows, the
+ * last sweep writes the byte parents again): sb200_plan_slab / _load_host / _store_host always see bytes.
  *
  * `global` describes the UNDIVIDED array: unpadded (src_off = dst_off = 0, ext = size), out_eltype == eltype, boundary
  * per axis (Wrap / Remove / Reflect on the split axis), region / mirror fields unused.
