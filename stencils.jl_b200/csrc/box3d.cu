@@ -34,6 +34,10 @@ constexpr int B3_TXB = B3_WX * 512;             // tile width in bytes
 #ifndef SB200_B3_BACKOFF_NS
 #define SB200_B3_BACKOFF_NS 0      // producer back-off while the ring is full: measured r02g, 0 / 1000 / 4000 ns all 556-558 Gcell/s
 #endif
+#ifndef SB200_B3_UNROLL
+XX
+#endif
+constexpr int B3_UNROLL = SB200_B3_UNROLL;
 #ifndef SB200_B3_PACKED
 #define SB200_B3_PACKED 0          // Float32 sums with packed add.rn.f32x2 (two cells per issue slot). Measured r02h, Window(1,3) mean
                                    // 768^3: scalar 571 Gcell/s, packed 504 — assembling the (x-1, x) / (x+1, x+2) operand pairs costs more
@@ -191,6 +195,7 @@ __global__ void __launch_bounds__(B3_THREADS, 2) box3d_kernel(const __grid_const
 #pragma unroll
         for (int r = 0; r < B3_RT; r++) { a1p[r][0] = a1p[r][1] = 0ull; a2p[r][0] = a2p[r][1] = 0ull; }
         T* __restrict__ dbase = p.dst + (long long)(y0 + ry0 + p.do1) * p.dp1 + p.do0 + gx;
+#pragma unroll B3_UNROLL
         for (int i = 0; i < nsrc; i++, k++) {
             const int slot = k % B3_STAGES;
             const int z = z0 - 1 + i;                  // logical plane held by this stage
