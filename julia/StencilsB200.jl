@@ -27,6 +27,12 @@ const ELTYPE = Dict(Bool => 0, UInt8 => 1, Int32 => 2, Int64 => 3, Float32 => 4,
 const SB_REMOVE, SB_WRAP, SB_REFLECT, SB_USE = Int32(0), Int32(1), Int32(2), Int32(3)
 const SB_SUM, SB_MEAN, SB_MIN, SB_MAX, SB_KERNELDOT, SB_LIFE, SB_DIFFUSION = Int32.(0:6)
 const SB_EUNSUPPORTED, SB_ESIZE = 2, 3
+# sb200_desc.flags (a binding normally leaves the *_STEP / *_BITS bits to sb200_iterate and the slab plans, which set them by themselves)
+const SB_FLAG_ZERO_DEST, SB_FLAG_CELLS_01, SB_FLAG_ALLOW_FMA = Int32(2), Int32(8), Int32(128)
+sb_flag_gens(n::Integer) = Int32(n == 2 ? 16 : n == 4 ? 32 : n == 8 ? 64 : (n == 3 || 5 <= n <= 7) ? n << 4 : 0)   # SB200_FLAG_GENS(n)
+# Life state one bit per cell: the layout of a BitMatrix whose first dimension is a multiple of 128 (chunks of 64 bits, column-major),
+# so `pointer(A.chunks)` of such a BitMatrix can be handed to sb200_gather with these flags and SB200_FLAG_GENS(2 .. 8)
+const SB_FLAG_SRC_BITS, SB_FLAG_DST_BITS = Int32(256), Int32(512)
 
 # struct sb200_desc — field order and sizes must match the header (248 bytes).
 struct Desc
