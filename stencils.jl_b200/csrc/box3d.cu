@@ -35,7 +35,8 @@ constexpr int B3_TXB = B3_WX * 512;             // tile width in bytes
 #define SB200_B3_BACKOFF_NS 0      // producer back-off while the ring is full: measured r02g, 0 / 1000 / 4000 ns all 556-558 Gcell/s
 #endif
 #ifndef SB200_B3_UNROLL
-XX
+#define SB200_B3_UNROLL 1   // unroll factor of the consumers' plane loop. Measured r02an, Window(1,3) mean 768^3: 2 spills at the 96-register cap
+                            // (570 -> 497 Gcell/s) — unlike stream3d2_kernel, whose loop gained 3 % from the renaming. Stays 1.
 #endif
 constexpr int B3_UNROLL = SB200_B3_UNROLL;
 #ifndef SB200_B3_PACKED
