@@ -132,6 +132,10 @@ template <int IN> constexpr int lb_smem() { return 128 + LB_STAGES * LB_CH * lb_
 // Resident CTAs per SM the kernel is compiled for. Byte launches: 3 (74 KB of ring each, <= 96 registers). Packed -> packed launches
 // have a 9 KB ring, so the registers decide: 9 G state registers + temporaries fit 4 CTAs (<= 72 registers) up to G = 6 and 5 CTAs
 // (<= 56) up to G = 4; more resident warps hide the latency of the dependent LOP3 chains. SB200_LB_PK_CTAS=0 keeps 3 everywhere.
+#ifndef SB200_LB_PRED_EMIT
+#define SB200_LB_PRED_EMIT 0   // packed dest: the output row as a predicated store instead of a branch around the store. Measured r02ar:
+                               // slower (six generations 72.4 -> 76.5 us: the last generation is computed for rows that store nothing). Off.
+#endif
 #ifndef SB200_LB_PK_CTAS
 #define SB200_LB_PK_CTAS 1
 #endif
@@ -255,7 +259,15 @@ __global__ void __launch_bounds__((LB_WARPS + 1) * 32, lb_min_ctas<G, IN, OUT_BI
                     const unsigned prev = __shfl_up_sync(0xffffffffu, x, 1), next = __shfl_down_sync(0xffffffffu, x, 1);
                     lv[g][(J - g + 9) % 3] = brow(x, prev, next, mul);
                 }
-                if (i >= 2 * G && i < nsrc) {   // generation G of row i - G: the output row y0 + i - 2G
+                if constexpr (OUT_BITS && SB200_LB_PRED_EMIT) {
+                    // generation G of row i - G = the output row y0 + i - 2G, as ONE predicated store: no branch in the row body, so
+                    // ptxas keeps the three rows of an iteration in one basic block (the branch around a store block costs a divergence
+                    // check — BRA.DIV — in front of the next row's shuffles)
+                    const bool emit = i >= 2 * G && i < nsrc;
+                    const unsigned y = conway_bits(lv[G - 1][(J - G - 1 + 9) % 3], lv[G - 1][(J - G + 9) % 3], lv[G - 1][(J - G + 1 + 9) % 3]);
+                    if (emit && active) *reinterpret_cast<unsigned*>(wp) = y;   // 30 consecutive words per warp row
+                    wp += emit ? dpitch : 0;
+                } else if (i >= 2 * G && i < nsrc) {   // generation G of row i - G: the output row y0 + i - 2G
                     const unsigned y = conway_bits(lv[G - 1][(J - G - 1 + 9) % 3], lv[G - 1][(J - G + 9) % 3], lv[G - 1][(J - G + 1 + 9) % 3]);
                     if constexpr (OUT_BITS) {
                         if (active) *reinterpret_cast<unsigned*>(wp) = y;   // 30 consecutive words per warp row
