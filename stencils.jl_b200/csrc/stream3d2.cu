@@ -49,6 +49,11 @@ constexpr int D2_WARPS = D2_WX * D2_WY;
                             // 1117 -> 1151 Gcell-updates/s; 3: 1143, 4: 1158)
 #endif
 constexpr int D2_UNROLL = SB200_D2_UNROLL;
+#ifndef SB200_D2_XSCALAR
+#define SB200_D2_XSCALAR 1   // scalar FADDs for the x-neighbour adds of the packed fold (no pair assembly; the operand pairs
+                             // (x-1, x) / (x+1, x+2) are not register-aligned). r02at, 1024^3 under the power cap:
+                             // 1135 -> 1164 Gcell-updates/s, two runs each, parity green; 0 = packed adds
+#endif
 #ifndef SB200_D2_PACKED
 #define SB200_D2_PACKED 1
 #endif
@@ -204,8 +209,19 @@ __device__ __forceinline__ void d2_plane<float, 4>(float (&done)[4], float (&cpr
         d2_upk(d2_add2(cc, d2_mul2_opaque(al, u)), done[2 * h], done[2 * h + 1]);
         // part = (((cc + ym) + xm) + xp) + yp
         unsigned long long a = d2_add2(cc, d2_pk(ym[2 * h], ym[2 * h + 1]));
+#if SB200_D2_XSCALAR
+        {   // the two x-neighbour adds as scalar FADDs: their operand pairs (x-1, x) / (x+1, x+2) are not register-aligned
+            float a0, a1;
+            d2_upk(a, a0, a1);
+            const float xm0 = h == 0 ? l_ : c[1], xm1 = h == 0 ? c[0] : c[2], xp0 = h == 0 ? c[1] : c[3], xp1 = h == 0 ? c[2] : r_;
+            a0 = __fadd_rn(__fadd_rn(a0, xm0), xp0);
+            a1 = __fadd_rn(__fadd_rn(a1, xm1), xp1);
+            a = d2_pk(a0, a1);
+        }
+#else
         a = d2_add2(a, xm[h]);
         a = d2_add2(a, xp[h]);
+#endif
         a = d2_add2(a, d2_pk(yp[2 * h], yp[2 * h + 1]));
         d2_upk(a, part[2 * h], part[2 * h + 1]);
         cprev[2 * h] = c[2 * h];
