@@ -60,6 +60,8 @@ constexpr int D2_UNROLL = SB200_D2_UNROLL;
 // producer warps (the rows of a stage dealt round-robin). Measured on 1024^3 Float32 (r01j): 2 producers 935, 3 producers
 // 1092, 4 producers (register cap 80) 1073 Gcell-updates/s: with two, the consumers waited for data 23 % of the time
 // (each bulk copy costs ~14 issue slots of lane-by-lane serialisation: ELECT / R2UR / UBLKCP / BRA.U.ANY).
+// Re-measured after the instruction cuts of round 2 (r02av, one box, two runs each): 3 producers / 6 stages 1181.2, 1179.9;
+// 4 producers 1181.9, 1181.3; 8 stages (225 KB) 1185.7, 1187.6; 4 producers + 8 stages 1171.9, 1172.2: the defaults stay.
 constexpr int D2_PRODUCERS = SB200_D2_PRODUCERS;
 constexpr int D2_RIMWARP = D2_WARPS;               // one more consumer warp: the rim columns of the intermediate plane, one cell per lane
 constexpr int D2_CONSUMERS = D2_WARPS + 1;
