@@ -57,6 +57,15 @@ constexpr int D2_UNROLL = SB200_D2_UNROLL;
 #ifndef SB200_D2_PACKED
 #define SB200_D2_PACKED 1
 #endif
+#ifndef SB200_D2_SPLIT
+#define SB200_D2_SPLIT 0     // split-phase level barrier (A/B): a warp ARRIVES on an mbarrier once its part of intermediate plane i is in
+                             // shared memory, goes on, and only WAITS for the other warps' arrivals of plane i-1 when it starts level 2 of
+                             // that plane, one iteration later (four intermediate planes instead of two; level 2 re-reads its own rows).
+                             // Measured r02ay (one box, two runs each): bit-exact (13 GPU parity tests incl. the slab plans), but 1206.2 /
+                             // 1206.0 against 1248.6 / 1250.0 Gcell-updates/s: the loop grows from 356 to 433 instructions per two planes
+                             // (two more LDS.128, the mbarrier polls, the loop skew's predicates), which costs more than the barrier slack
+                             // returns. Off.
+#endif
 // producer warps (the rows of a stage dealt round-robin). Measured on 1024^3 Float32 (r01j): 2 producers 935, 3 producers
 // 1092, 4 producers (register cap 80) 1073 Gcell-updates/s: with two, the consumers waited for data 23 % of the time
 // (each bulk copy costs ~14 issue slots of lane-by-lane serialisation: ELECT / R2UR / UBLKCP / BRA.U.ANY).
@@ -77,10 +86,11 @@ constexpr int D2_STAGE = D2_ROWS * D2_ROWB;
 constexpr int D2_STAGES = SB200_D2_STAGES;
 constexpr int D2_MROWS = D2_TY + 2;               // intermediate plane: tile rows + one rim row on each side
 constexpr int D2_MSTAGE = D2_MROWS * D2_ROWB;
-constexpr int D2_SMEM = 128 + D2_STAGES * D2_STAGE + 2 * D2_MSTAGE;
+constexpr int D2_MBUFS = SB200_D2_SPLIT ? 4 : 2;   // intermediate planes in shared memory
+constexpr int D2_SMEM = 128 + D2_STAGES * D2_STAGE + D2_MBUFS * D2_MSTAGE;
 static_assert(D2_SMEM <= 227 * 1024, "ring does not fit");
 static_assert(D2_ROWS <= 32 * D2_PRODUCERS, "one producer lane per row");
-static_assert(2 * D2_STAGES * 8 <= 128, "barrier header");
+static_assert((2 * D2_STAGES + 2) * 8 <= 128, "barrier header");
 
 template <typename T> struct D2Params {
     const T* src;
@@ -248,10 +258,12 @@ __global__ void __launch_bounds__(D2_THREADS, 1) stream3d2_kernel(const __grid_c
     uint64_t* full = reinterpret_cast<uint64_t*>(smem);
     uint64_t* empty = full + D2_STAGES;
     unsigned char* ring = smem + 128;
-    unsigned char* mbuf = ring + D2_STAGES * D2_STAGE;   // two intermediate planes
+    uint64_t* midbar = empty + D2_STAGES;                // SPLIT: arrivals of the consumer warps per intermediate plane (two, alternating)
+    unsigned char* mbuf = ring + D2_STAGES * D2_STAGE;   // D2_MBUFS intermediate planes
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         for (int s = 0; s < D2_STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], D2_CONSUMERS); }
+        if (SB200_D2_SPLIT) { mbar_init(&midbar[0], D2_CONSUMERS); mbar_init(&midbar[1], D2_CONSUMERS); }
         mbar_fence_init();
     }
     __syncthreads();
@@ -318,7 +330,13 @@ __global__ void __launch_bounds__(D2_THREADS, 1) stream3d2_kernel(const __grid_c
             const int yr = y0 - 1 + mrow;
             const bool x_oob = padx && ((lane >> 4) ? x0b + wbytes == Xb : x0b == 0);
             const bool row_oob = pady && (yr < 0 || yr >= p.Y), up_oob = pady && (yr - 1 < 0 || yr - 1 >= p.Y), dn_oob = pady && (yr + 1 < 0 || yr + 1 >= p.Y);
+#if SB200_D2_SPLIT
+            for (int i = 0; i <= nsrc; i++) {
+                if (i >= 1) mbar_wait(&midbar[(k - 1) & 1], ((k - 1) >> 1) & 1);   // keeps this warp within the other warps' window of planes
+                if (i == nsrc) break;
+#else
             for (int i = 0; i < nsrc; i++, k++) {
+#endif
                 mbar_wait(&full[slot], phase);
                 const unsigned char* t = ring + slot * D2_STAGE + (mrow + 1) * D2_ROWB + pos;   // intermediate row m <-> source row m + 1
                 T c = *reinterpret_cast<const T*>(t);
@@ -342,8 +360,15 @@ __global__ void __launch_bounds__(D2_THREADS, 1) stream3d2_kernel(const __grid_c
                 ce = c;
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&empty[slot]);
+#if SB200_D2_SPLIT
+                *reinterpret_cast<T*>(mbuf + (k & 3) * D2_MSTAGE + mrow * D2_ROWB + pos) = m;
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&midbar[k & 1]);
+                k++;
+#else
                 *reinterpret_cast<T*>(mbuf + (k & 1) * D2_MSTAGE + mrow * D2_ROWB + pos) = m;
                 d2_level_barrier();
+#endif
                 if (++slot == D2_STAGES) { slot = 0; phase ^= 1; }
             }
             continue;
@@ -365,9 +390,10 @@ __global__ void __launch_bounds__(D2_THREADS, 1) stream3d2_kernel(const __grid_c
         bool rowok[D2_RT];
 #pragma unroll
         for (int r = 0; r < D2_RT; r++) rowok[r] = lvl2 && xact && y0 + r1 + r < p.Y && r1 + r < p.ty;
-        T* __restrict__ dptr = p.dst + (long long)(y0 + r1) * p.p1 + gx + (long long)(z0 - 4) * p.p2;
+        constexpr int LAG = SB200_D2_SPLIT ? 1 : 0;   // SPLIT: level 2 of a plane runs one iteration after its level 1
+        T* __restrict__ dptr = p.dst + (long long)(y0 + r1) * p.p1 + gx + (long long)(z0 - 4 - LAG) * p.p2;
         T* mptr = nullptr;   // MIRROR: where output plane z0-4+i of this thread's rows lands in the neighbour's slot
-        if constexpr (MIRROR) mptr = p.mirror + (long long)(y0 + r1) * p.p1 + gx + (long long)(z0 - 4 - p.m_lo) * p.p2;
+        if constexpr (MIRROR) mptr = p.mirror + (long long)(y0 + r1) * p.p1 + gx + (long long)(z0 - 4 - LAG - p.m_lo) * p.p2;
         const bool l0 = lane == 0, l31 = lane == 31;
         int slot = k % D2_STAGES;
         unsigned phase = (k / D2_STAGES) & 1;
@@ -379,12 +405,22 @@ __global__ void __launch_bounds__(D2_THREADS, 1) stream3d2_kernel(const __grid_c
         for (int q = 0; q < D2_RT + 2; q++) srow_oob[q] = pady && (y0 + r1 - 2 + q < 0 || y0 + r1 - 2 + q >= p.Y);
 #pragma unroll
         for (int j = 0; j < D2_RT; j++) mrow_oob[j] = xoob || (pady && (y0 + r1 - 1 + j < 0 || y0 + r1 - 1 + j >= p.Y));
+#if SB200_D2_SPLIT
+#pragma unroll D2_UNROLL
+        for (int i = 0; i <= nsrc; i++) {
+            const unsigned kprev = k - 1;              // the intermediate plane of the previous iteration
+            if (i < nsrc) {
+            mbar_wait(&full[slot], phase);
+            const unsigned char* sb_ = ring + slot * D2_STAGE + D2_LEFT + xtb + r1 * D2_ROWB;   // source row r1
+            unsigned char* mb_ = mbuf + (k & 3) * D2_MSTAGE + D2_LEFT + xtb + r1 * D2_ROWB;    // intermediate row r1
+#else
 #pragma unroll D2_UNROLL
         for (int i = 0; i < nsrc; i++, k++) {
             mbar_wait(&full[slot], phase);
             // this thread's 16 bytes in shared-memory row 0; tile row t lives in source row t + 2 and intermediate row t + 1
             const unsigned char* sb_ = ring + slot * D2_STAGE + D2_LEFT + xtb + r1 * D2_ROWB;   // source row r1
             unsigned char* mb_ = mbuf + (k & 1) * D2_MSTAGE + D2_LEFT + xtb + r1 * D2_ROWB;    // intermediate row r1
+#endif
             // ---- level 1: source plane s completes intermediate plane s-1 on tile rows r1-1, r1 ----
             T rowv[D2_RT + 2][VX];                     // source tile rows r1-2 .. r1+1 = source rows r1 .. r1+3
 #pragma unroll
@@ -426,6 +462,23 @@ __global__ void __launch_bounds__(D2_THREADS, 1) stream3d2_kernel(const __grid_c
             for (int j = 0; j < D2_RT; j++) {
                 d2_st<T, VX>(mb_ + j * D2_ROWB, mid[j]);
             }
+#if SB200_D2_SPLIT
+            __syncwarp();
+            if (l0) mbar_arrive(&midbar[k & 1]);        // this warp's part of intermediate plane k is in shared memory
+            k++;
+            if (++slot == D2_STAGES) { slot = 0; phase ^= 1; }
+            }
+            if (i >= 1) mbar_wait(&midbar[kprev & 1], (kprev >> 1) & 1);   // every warp's part of the previous plane
+            // ---- level 2 of the PREVIOUS plane: intermediate plane m completes final plane m-1 on tile rows r1, r1+1 ----
+            if (lvl2 && i >= 1) {
+                const unsigned char* mb_ = mbuf + (kprev & 3) * D2_MSTAGE + D2_LEFT + xtb + r1 * D2_ROWB;
+                T mid[D2_RT][VX], m2[VX], m3[VX];       // own rows (re-read) and intermediate tile rows r1+1, r1+2 (the warp below)
+                d2_lds<T, VX>(mid[0], mb_);
+                d2_lds<T, VX>(mid[1], mb_ + D2_ROWB);
+                d2_lds<T, VX>(m2, mb_ + 2 * D2_ROWB);
+                d2_lds<T, VX>(m3, mb_ + 3 * D2_ROWB);
+                const bool store = i >= 4 + LAG;
+#else
             d2_level_barrier();
             // ---- level 2: intermediate plane m = s-1 completes final plane m-1 = s-2 on tile rows r1, r1+1 ----
             if (lvl2) {
@@ -433,6 +486,7 @@ __global__ void __launch_bounds__(D2_THREADS, 1) stream3d2_kernel(const __grid_c
                 d2_lds<T, VX>(m2, mb_ + 2 * D2_ROWB);
                 d2_lds<T, VX>(m3, mb_ + 3 * D2_ROWB);
                 const bool store = i >= 4;
+#endif
 #pragma unroll
                 for (int r = 0; r < D2_RT; r++) {      // final tile row r1+r: centre = intermediate row r1+r+1
                     const T(&ym)[VX] = r == 0 ? mid[0] : mid[1];
@@ -447,14 +501,16 @@ __global__ void __launch_bounds__(D2_THREADS, 1) stream3d2_kernel(const __grid_c
                     d2_plane<T, VX>(out, c2[r], q2[r], cc, ym, yp, l_, r_, p.alpha);
                     if (store && rowok[r]) d2_st<T, VX>(dptr + (long long)r * p.p1, out);
                     if constexpr (MIRROR) {
-                        const int zo = z0 - 4 + i;
+                        const int zo = z0 - 4 - LAG + i;
                         if (store && rowok[r] && zo >= p.m_lo && zo < p.m_hi) d2_st<T, VX>(mptr + (long long)r * p.p1, out);
                     }
                 }
             }
             if constexpr (MIRROR) mptr += p.p2;
             dptr += p.p2;
+#if !SB200_D2_SPLIT
             if (++slot == D2_STAGES) { slot = 0; phase ^= 1; }
+#endif
         }
     }
 }
