@@ -42,7 +42,11 @@ constexpr int B3_UNROLL = SB200_B3_UNROLL;
 #ifndef SB200_B3_PACKED
 #define SB200_B3_PACKED 0          // Float32 sums with packed add.rn.f32x2 (two cells per issue slot). Measured r02h, Window(1,3) mean
                                    // 768^3: scalar 571 Gcell/s, packed 504 — assembling the (x-1, x) / (x+1, x+2) operand pairs costs more
-                                   // moves than the 208 saved FADD issue slots (stream3d2's pairs are register-aligned, these are not)
+                                   // moves than the 208 saved FADD issue slots (stream3d2's pairs are register-aligned, these are not).
+                                   // 2 = mixed fold: the centre taps as packed adds, the x-neighbour taps as scalar adds on the halves of
+                                   // the accumulator pair (no pair assembly; 418 FADD -> 290 FADD + 64 FADD2 per plane and thread).
+                                   // Measured r02az: bit-exact (29 GPU parity tests), 572.5 / 566.9 against 570.8 / 562.4 Gcell/s: no gain,
+                                   // the kernel is not bound by its FP issue slots alone. Stays 0.
 #endif
 constexpr int B3_RT = SB200_B3_RT;              // rows per thread
 constexpr int B3_TY = B3_WY * B3_RT;            // tile height in rows
@@ -282,9 +286,39 @@ __global__ void __launch_bounds__(B3_THREADS, 2) box3d_kernel(const __grid_const
                     for (int h = 0; h < 2; h++) { fin[r][h] = a2p[r][h]; n2[r][h] = a1p[r][h]; n1[r][h] = 0ull; }
 #pragma unroll
                 for (int w = 0; w < NR; w++) {
+                    const unsigned long long pc[2] = {b3_pk(rowv[w][0], rowv[w][1]), b3_pk(rowv[w][2], rowv[w][3])};
+#if SB200_B3_PACKED == 2
+                    // mixed form: only the centre taps (register-aligned pairs) are packed adds, the x-neighbour taps are scalar
+                    // adds on the halves of the accumulator pair (no pair assembly)
+                    const float m0[2] = {xl[w], rowv[w][1]}, m1[2] = {rowv[w][0], rowv[w][2]};   // left neighbours of a pair's cells
+                    const float q0[2] = {rowv[w][1], rowv[w][3]}, q1[2] = {rowv[w][2], xr[w]};   // right neighbours
+                    auto adds = [](unsigned long long a, float x0, float x1) {
+                        float a0, a1;
+                        b3_upk(a, a0, a1);
+                        return b3_pk(__fadd_rn(a0, x0), __fadd_rn(a1, x1));
+                    };
+#pragma unroll
+                    for (int dy = 0; dy < 3; dy++) {
+                        const int r = w - dy;
+                        if (r < 0 || r >= B3_RT) continue;
+#pragma unroll
+                        for (int h = 0; h < 2; h++) {
+                            fin[r][h] = adds(b3_add2(adds(fin[r][h], m0[h], m1[h]), pc[h]), q0[h], q1[h]);
+                            unsigned long long b = adds(n2[r][h], m0[h], m1[h]);
+                            if (!(MOORE && dy == 1)) b = b3_add2(b, pc[h]);
+                            n2[r][h] = adds(b, q0[h], q1[h]);
+                            if (dy == 0) {
+                                const float c0 = rowv[w][2 * h], c1 = rowv[w][2 * h + 1];
+                                n1[r][h] = b3_pk(__fadd_rn(__fadd_rn(m0[h], c0), q0[h]), __fadd_rn(__fadd_rn(m1[h], c1), q1[h]));
+                            } else {
+                                n1[r][h] = adds(b3_add2(adds(n1[r][h], m0[h], m1[h]), pc[h]), q0[h], q1[h]);
+                            }
+                        }
+                    }
+                    continue;
+#endif
                     const unsigned long long mid = b3_pk(rowv[w][1], rowv[w][2]);
                     const unsigned long long pm[2] = {b3_pk(xl[w], rowv[w][0]), mid};
-                    const unsigned long long pc[2] = {b3_pk(rowv[w][0], rowv[w][1]), b3_pk(rowv[w][2], rowv[w][3])};
                     const unsigned long long pq[2] = {mid, b3_pk(rowv[w][3], xr[w])};
 #pragma unroll
                     for (int dy = 0; dy < 3; dy++) {
